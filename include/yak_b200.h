@@ -1,0 +1,69 @@
+/* yak_b200.h - GPU-side extensions of the drop-in library (libyakb200.so), C ABI.
+ *
+ * yak.h is the reference's API; the entry points here expose the same hot path at chunk
+ * granularity on raw host/device pointers, for callers that already hold data on the device
+ * (bench.py, the multi-GPU harness, tests).  No torch types, plain pointers and sizes.
+ * All functions return 0 on success and a negative value on error (message on stderr), unless
+ * stated otherwise.
+ */
+#ifndef YAK_B200_H
+#define YAK_B200_H
+
+#include <stdint.h>
+#include "yak.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *yakb_version(void);
+int yakb_device_count(void);                       /* 0 when no CUDA device is usable */
+
+/* stats[4] = {k-mer events, pending (not in table before the chunk), put-events, new keys} */
+
+/* One chunk of the count path (reference count.c:111-143 + htab.c:51-78) on a device-resident
+ * ASCII base stream: any byte that is not A/C/G/T/U (either case) or 0..3 separates reads. */
+int yakb_count_ascii_dev(yak_ch_t *h, const void *d_asc, uint64_t n, int create_new, uint64_t stats[4]);
+/* same, bases in host memory (copied to the device inside the call) */
+int yakb_count_ascii_host(yak_ch_t *h, const char *asc, uint64_t n, int create_new, uint64_t stats[4]);
+/* One chunk given as already hashed k-mers in file order (what count.c:17-26 buffers hold, all
+ * sub-tables mixed); the receive side of the multi-GPU exchange. */
+int yakb_count_events_dev(yak_ch_t *h, const uint64_t *d_ev, uint64_t n, int create_new, uint64_t stats[4]);
+
+/* Extraction only (reference count.c:28-60): hashed canonical k-mers of a device ASCII stream in
+ * file order, stably partitioned by owner rank = (hash & (2^pre-1)) * world >> pre.
+ * d_out must hold n entries; counts[world] (host) receives the per-rank counts. */
+int yakb_extract_route_dev(const void *d_asc, uint64_t n, int k, int pre, int world,
+                           uint64_t *d_out, uint64_t *counts, void *cuda_stream);
+
+/* batched yak_ch_get (reference htab.c:93-100): out[i] = count or -1 */
+int yakb_ch_get_batch(const yak_ch_t *h, uint64_t n, const uint64_t *x, int32_t *out);
+int yakb_ch_get_batch_dev(const yak_ch_t *h, uint64_t n, const uint64_t *d_x, int32_t *d_out);
+
+/* qv scan (reference qv.c:34-86) over sequences already in host memory: `cat` holds the
+ * sequences back to back, lens[i] their lengths.  cnt[1024] is accumulated like yak_qv's;
+ * tot/non0 (may be NULL) receive the per-sequence numbers of the SQ line. */
+int yakb_qv_seqs(const yak_ch_t *h, int64_t n_seq, const int64_t *lens, const char *cat,
+                 int min_len, double min_frac, int64_t cnt[YAK_N_COUNTS], int32_t *tot, int32_t *non0);
+
+/* serialise exactly the bytes yak_ch_dump writes into a malloc'd buffer; returns the length */
+int64_t yakb_ch_dump_mem(const yak_ch_t *h, uint8_t **out);
+/* make room for this many distinct keys per sub-table up front (optional) */
+int yakb_ch_reserve(yak_ch_t *h, uint64_t keys_per_subtable);
+/* the CUDA stream (cudaStream_t) every kernel of this table is launched on, for event timing */
+void *yakb_ch_stream(const yak_ch_t *h);
+/* bytes of device memory held by the table, bloom and journal */
+uint64_t yakb_ch_device_bytes(const yak_ch_t *h);
+/* number of kernels this library launched so far in this process */
+uint64_t yakb_kernel_launches(void);
+
+/* seeded synthetic data on the device (same stream as yak_b200/synth.py):
+ * genome as 2-bit codes packed 32 per u64; reads as ASCII with '\n' after each read */
+int yakb_synth_genome_dev(uint64_t seed_g, uint64_t G, uint64_t *d_genome2, void *cuda_stream);
+int yakb_synth_reads_dev(const uint64_t *d_genome2, uint64_t G, uint64_t seed_r, uint64_t first, uint64_t n_reads,
+                         int L, double err, int n_pct, uint8_t *d_asc, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,213 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit-exact .yak bytes."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _count_both(oracle, yakb, fn, k, pre, b, fn2=None):
+    ho, ne = oracle.count_file(fn, k=k, pre=pre, bf_shift=b, fn2=fn2)
+    ref = oracle.dump_bytes(ho)
+    hg = yakb.count_file(fn, k=k, pre=pre, bf_shift=b, fn2=fn2)
+    assert hg
+    mine = yakb.dump_bytes(hg)
+    return ho, hg, ref, mine, ne
+
+
+@pytest.fixture(scope="module")
+def reads_fa():
+    return util.write_reads(os.path.join(util.TMP, "yakb_reads.fa"))
+
+
+@pytest.fixture(scope="module")
+def reads_fq():
+    return util.write_reads(os.path.join(util.TMP, "yakb_reads.fq"), seed_r=12, n_reads=3000, fastq=True)
+
+
+@pytest.mark.parametrize("k,pre,b", [(31, 12, 0), (31, 10, 0), (21, 11, 0), (15, 10, 0), (47, 12, 0), (63, 10, 0),
+                                     (31, 12, 22), (31, 10, 20), (31, 12, 24), (27, 11, 21), (63, 10, 21), (31, 12, 12)])
+def test_count_matches_oracle(oracle, yakb, reads_fa, k, pre, b):
+    ho, hg, ref, mine, ne = _count_both(oracle, yakb, reads_fa, k, pre, b)
+    try:
+        assert mine == ref, util.explain_diff(mine, ref)
+        assert hg.contents.tot == ho.contents.tot
+    finally:
+        yakb.lib().yak_ch_destroy(hg)
+        oracle.lib().yo_ch_destroy(ho)
+
+
+def test_count_fastq_two_files(oracle, yakb, reads_fa, reads_fq):
+    # pass 2 over a different file (main.c:57)
+    ho, hg, ref, mine, _ = _count_both(oracle, yakb, reads_fq, 31, 12, 23, fn2=reads_fa)
+    try:
+        assert mine == ref, util.explain_diff(mine, ref)
+    finally:
+        yakb.lib().yak_ch_destroy(hg)
+        oracle.lib().yo_ch_destroy(ho)
+
+
+@pytest.mark.parametrize("b", [0, 22])
+def test_many_small_chunks(oracle, yakb, reads_fa, b, monkeypatch):
+    # results must not depend on how the input is cut into batches
+    monkeypatch.setenv("YAKB_BATCH", "50000")
+    ho, hg, ref, mine, _ = _count_both(oracle, yakb, reads_fa, 31, 12, b)
+    try:
+        assert mine == ref, util.explain_diff(mine, ref)
+    finally:
+        yakb.lib().yak_ch_destroy(hg)
+        oracle.lib().yo_ch_destroy(ho)
+
+
+def _edge_file(path):
+    rng = np.random.default_rng(5)
+    def rnd(n):
+        return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+    recs = []
+    recs.append(">short\n" + rnd(20) + "\n")                       # shorter than k: dropped (count.c:95)
+    recs.append(">exact31\n" + rnd(31) + "\n")
+    recs.append(">lower case\n" + rnd(200).lower() + "\n")
+    s = rnd(500)
+    recs.append(">multi line comment here\n" + "\n".join(s[i:i + 60] for i in range(0, 500, 60)) + "\n")
+    recs.append(">withN\n" + rnd(40) + "N" + rnd(30) + "NN" + rnd(100) + "\n")
+    recs.append(">iupac\n" + rnd(50) + "RYKM" + rnd(50) + "\n")
+    recs.append(">uracil\n" + rnd(80).replace("T", "U") + "\n")
+    recs.append(">crlf\r\n" + rnd(100) + "\r\n" + rnd(50) + "\r\n")
+    recs.append(">polyA\n" + "A" * 3000 + "\n")                    # one k-mer 2970 times: saturates at 1023
+    recs.append(">dinuc\n" + "AC" * 700 + "\n")
+    recs.append(">empty\n\n")
+    recs.append(">dup1\n" + s + "\n>dup2\n" + s + "\n")
+    recs.append("\n\n>blank lines before\n\n" + rnd(90) + "\n\n")
+    recs.append(">palin\n" + "ACGT" * 40 + "\n")
+    fq = "@q1 c\n" + rnd(100) + "\n+\n" + "@" * 100 + "\n@q2\n" + rnd(64) + "\n+q2\n" + "+" * 64 + "\n"
+    with open(path, "w", newline="") as f:
+        f.write("".join(recs) + fq)
+    return path
+
+
+@pytest.mark.parametrize("k,pre,b", [(31, 10, 0), (31, 10, 19), (21, 10, 0), (33, 10, 0), (5, 10, 0)])
+def test_edge_case_records(oracle, yakb, k, pre, b):
+    fn = _edge_file(os.path.join(util.TMP, "yakb_edge.fa"))
+    ho, hg, ref, mine, ne = _count_both(oracle, yakb, fn, k, pre, b)
+    try:
+        assert ne > 0
+        assert mine == ref, util.explain_diff(mine, ref)
+    finally:
+        yakb.lib().yak_ch_destroy(hg)
+        oracle.lib().yo_ch_destroy(ho)
+
+
+def test_empty_and_missing_input(yakb):
+    L = yakb.lib()
+    o = yakb.copt(31, 10)
+    assert not L.yak_count(b"/nonexistent/file.fa", C.byref(o), None)      # count.c:152
+    fn = os.path.join(util.TMP, "yakb_empty.fa")
+    open(fn, "w").close()
+    h = L.yak_count(fn.encode(), C.byref(o), None)
+    assert h and h.contents.tot == 0
+    data = yakb.dump_bytes(h)
+    assert len(data) == 16 + 8 * 1024 and data[16:] == bytes(8 * 1024)     # capacity 0, size 0 everywhere
+    L.yak_ch_destroy(h)
+    assert not L.yak_ch_init(31, 9, 4, 0)                                    # htab.c:17
+
+
+def test_insert_list_get_hist_clear(oracle, yakb, reads_fa):
+    """The reference's own call pattern: per-sub-table lists into yak_ch_insert_list (count.c:82)."""
+    OL, L = oracle.lib(), yakb.lib()
+    k, pre = 31, 10
+    seqs = [ln.strip() for ln in open(reads_fa) if not ln.startswith(">")][:1500]
+    ev = []
+    for s in seqs:
+        buf = (C.c_uint64 * len(s))()
+        n = OL.yo_extract(k, len(s), s.encode(), buf)
+        ev.append(np.frombuffer(buf, dtype=np.uint64, count=n).copy())
+    ev = np.concatenate(ev)
+    ho = OL.yo_ch_init(k, pre, 4, 0)
+    hg = L.yak_ch_init(k, pre, 4, 0)
+    half = len(ev) // 2
+    for part in (ev[:half], ev[half:]):                      # two "chunks"
+        sub = (part & np.uint64((1 << pre) - 1)).astype(np.int64)
+        order = np.argsort(sub, kind="stable")
+        part_s, sub_s = part[order], sub[order]
+        bounds = np.flatnonzero(np.diff(sub_s)) + 1
+        for lst in np.split(part_s, bounds):
+            a, p = util.u64_array(lst)
+            n1 = OL.yo_ch_insert_list(ho, 1, len(a), p)
+            n2 = L.yak_ch_insert_list(hg, 1, len(a), p)
+            assert n1 == n2
+    # a list with foreign elements: only those sharing a[0]'s sub-table count (htab.c:61)
+    a, p = util.u64_array(ev[:4000])
+    assert OL.yo_ch_insert_list(ho, 1, len(a), p) == L.yak_ch_insert_list(hg, 1, len(a), p)
+    assert yakb.dump_bytes(hg) == oracle.dump_bytes(ho)
+    # lookups, present and absent
+    probe = np.concatenate([ev[::97], ev[::89] ^ np.uint64(0x5555555555)])
+    a, p = util.u64_array(probe)
+    got = np.zeros(len(a), dtype=np.int32)
+    assert L.yakb_ch_get_batch(hg, len(a), p, got.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+    want = np.array([OL.yo_ch_get(ho, int(x)) for x in a], dtype=np.int32)
+    assert np.array_equal(got, want)
+    assert L.yak_ch_get(hg, int(a[0])) == want[0] and L.yak_ch_get(hg, int(a[-1])) == want[-1]
+    h1, h2 = (C.c_int64 * 1024)(), (C.c_int64 * 1024)()
+    OL.yo_ch_hist(ho, h1); L.yak_ch_hist(hg, h2, 4)
+    assert list(h1) == list(h2)
+    # count-existing mode then clear
+    a, p = util.u64_array(ev[:5000])
+    OL.yo_ch_insert_list(ho, 0, len(a), p); L.yak_ch_insert_list(hg, 0, len(a), p)
+    assert yakb.dump_bytes(hg) == oracle.dump_bytes(ho)
+    OL.yo_ch_clear(ho); L.yak_ch_clear(hg, 4)
+    assert yakb.dump_bytes(hg) == oracle.dump_bytes(ho)
+    L.yak_ch_destroy(hg); OL.yo_ch_destroy(ho)
+
+
+def test_trailing_put_and_shrink_quirks(oracle, yakb):
+    """SURVEY section 4 KATs: Q3 trailing-put doubling {4,3}->{8,3}; Q9 shrink of empty sub-tables."""
+    L = yakb.lib()
+    pre = 10
+    keys = np.array([(i * 7919 + 3) << pre | 5 for i in range(1, 4)], dtype=np.uint64)
+    import struct
+    for extra, want in ((False, (4, 3)), (True, (8, 3))):
+        h = L.yak_ch_init(31, pre, 4, 0)
+        lst = np.concatenate([keys, keys[:1]]) if extra else keys
+        a, p = util.u64_array(lst)
+        L.yak_ch_insert_list(h, 1, len(a), p)
+        data = yakb.dump_bytes(h)
+        off = 16
+        for s in range(5):
+            cap, size = struct.unpack_from("<II", data, off); off += 8 + 8 * size
+        assert struct.unpack_from("<II", data, off) == want
+        L.yak_ch_shrink(h, 1, 1023, 1)                        # Q9: empty sub-tables now have capacity 4
+        data = yakb.dump_bytes(h)
+        assert struct.unpack_from("<II", data, 16) == (4, 0)
+        L.yak_ch_destroy(h)
+
+
+def test_restore_roundtrip_and_qv(oracle, yakb, reads_fa):
+    OL, L = oracle.lib(), yakb.lib()
+    k, pre, b = 31, 12, 22
+    ho, _ = oracle.count_file(reads_fa, k=k, pre=pre, bf_shift=b)
+    fn = os.path.join(util.TMP, "yakb_sr.yak")
+    assert OL.yo_ch_dump(ho, fn.encode()) == 0
+    hg = L.yak_ch_restore(fn.encode())
+    assert hg and hg.contents.k == k and hg.contents.pre == pre
+    ho2 = OL.yo_ch_restore(fn.encode())
+    assert yakb.dump_bytes(hg) == oracle.dump_bytes(ho2)      # restore -> dump goes through khashl re-placement
+    # qv scan of contigs cut from the genome
+    from yak_b200 import synth
+    ctg = synth.contigs_bytes(7, 200_000, 3, 6, 20_000, sub=1e-3)
+    seqs = [ln for ln in ctg.split(b"\n") if ln and not ln.startswith(b">")] + [b"ACGTNNNN", b"ACGT" * 20]
+    lens = (C.c_int64 * len(seqs))(*[len(s) for s in seqs])
+    cat = b"".join(seqs)
+    for min_len, min_frac in ((0, 0.5), (100, 0.999)):
+        c1, c2 = (C.c_int64 * 1024)(), (C.c_int64 * 1024)()
+        t1, z1 = (C.c_int32 * len(seqs))(), (C.c_int32 * len(seqs))()
+        t2, z2 = (C.c_int32 * len(seqs))(), (C.c_int32 * len(seqs))()
+        OL.yo_qv_seqs(ho2, len(seqs), lens, cat, min_len, min_frac, c1, t1, z1)
+        assert L.yakb_qv_seqs(hg, len(seqs), lens, cat, min_len, min_frac, c2, t2, z2) == 0
+        assert list(t1) == list(t2) and list(z1) == list(z2)
+        assert list(c1) == list(c2)
+        assert sum(c1) > 0
+    L.yak_ch_destroy(hg); OL.yo_ch_destroy(ho); OL.yo_ch_destroy(ho2)

@@ -1,0 +1,665 @@
+// capi.cu - the C ABI of libyakb200.so: the reference's yak.h entry points (include/yak.h) and
+// the chunk-level extensions (include/yak_b200.h), over the device engine.
+//
+// A yak_ch_t handed out here is the head of a larger host object; `h[i].h` points at a small
+// per-sub-table handle (the reference keeps a khashl set there) and `h[i].b`, when a bloom
+// filter exists, at a yak_bf_t whose `b` is the DEVICE address of that sub-filter.
+#include "../../include/yak.h"
+#include "../../include/yak_b200.h"
+#include "engine.cuh"
+#include "extras.cuh"
+#include "fastx.h"
+#include "yakb_dev.cuh"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <assert.h>
+#include <math.h>
+#include <algorithm>
+#include <mutex>
+#include <chrono>
+#include <sys/resource.h>
+#include <sys/time.h>
+
+using namespace yakb;
+
+struct yak_ht_t { struct ChBox *owner; int idx; };
+
+struct ChBox {
+	yak_ch_t pub;          // must stay first: yak_ch_t* <-> ChBox*
+	uint32_t magic;
+	Engine *eng;
+	std::vector<yak_ht_t> handles;
+	std::vector<yak_bf_t> filters;
+	std::mutex mu;
+	DBuf d_in, d_aux, d_aux2;
+	uint8_t *pinned[2] = {nullptr, nullptr};
+	size_t pinned_cap = 0;
+};
+static const uint32_t kMagic = 0x59414B42; // "YAKB"
+
+static ChBox *box_of(const yak_ch_t *h)
+{
+	ChBox *b = (ChBox*)h;
+	if (b == nullptr || b->magic != kMagic) { fprintf(stderr, "[yakb] ERROR: yak_ch_t was not created by this library\n"); abort(); }
+	return b;
+}
+
+#define GUARD_BEGIN try {
+#define GUARD_END(ret) } catch (const std::exception &e) { fprintf(stderr, "[yakb] ERROR: %s\n", e.what()); return ret; }
+#define GUARD_END_VOID } catch (const std::exception &e) { fprintf(stderr, "[yakb] FATAL: %s\n", e.what()); abort(); }
+
+// ------------------------------------------------------------------ misc.c / sys.c equivalents
+
+extern "C" {
+
+int yak_verbose = 3;
+
+unsigned char seq_nt4_table[256];
+static struct Nt4Init { Nt4Init() { for (int c = 0; c < 256; ++c) seq_nt4_table[c] = (unsigned char)nt4((uint32_t)c); } } g_nt4_init;
+
+void yak_copt_init(yak_copt_t *o) // misc.c:23-32
+{
+	memset(o, 0, sizeof(*o));
+	o->bf_shift = 0; o->bf_n_hash = 4; o->k = 31; o->pre = 10; o->n_thread = 4; o->chunk_size = 10000000;
+}
+
+void yak_qopt_init(yak_qopt_t *o) // qv.c:137-144
+{
+	memset(o, 0, sizeof(*o));
+	o->chunk_size = 1000000000; o->n_threads = 4; o->min_frac = 0.5; o->fpr = 0.00004;
+}
+
+} // extern "C"
+
+static double wall_now() { struct timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec + tv.tv_usec * 1e-6; }
+static double g_t0 = wall_now();
+static double cpu_now() { struct rusage r; getrusage(RUSAGE_SELF, &r); return r.ru_utime.tv_sec + r.ru_stime.tv_sec + 1e-6 * (r.ru_utime.tv_usec + r.ru_stime.tv_usec); }
+
+// ------------------------------------------------------------------ yak_ch_*
+
+static void attach_handles(ChBox *b)
+{
+	const int P = 1 << b->pub.pre;
+	b->handles.resize(P);
+	b->filters.clear();
+	if (b->eng->bloom) b->filters.resize(P);
+	b->pub.h = (yak_ch1_t*)calloc(P, sizeof(yak_ch1_t));
+	for (int i = 0; i < P; ++i) {
+		b->handles[i].owner = b; b->handles[i].idx = i;
+		b->pub.h[i].h = &b->handles[i];
+		if (b->eng->bloom) {
+			b->filters[i].n_shift = b->eng->n_shift - b->eng->pre;
+			b->filters[i].n_hashes = b->eng->n_hash;
+			b->filters[i].b = b->eng->bloom + ((size_t)i << (b->eng->n_shift - b->eng->pre - 3));
+			b->pub.h[i].b = &b->filters[i];
+		}
+	}
+}
+
+extern "C" yak_ch_t *yak_ch_init(int k, int pre, int n_hash, int n_shift) // htab.c:13-29
+{
+	GUARD_BEGIN
+	if (pre < YAK_COUNTER_BITS) return 0;
+	Engine *e = Engine::create(k, pre, n_hash, n_shift);
+	if (!e) return 0;
+	ChBox *b = new ChBox;
+	memset(&b->pub, 0, sizeof(b->pub));
+	b->magic = kMagic; b->eng = e;
+	b->pub.k = k; b->pub.pre = pre; b->pub.n_hash = e->n_hash; b->pub.n_shift = e->n_shift; b->pub.tot = 0;
+	attach_handles(b);
+	return &b->pub;
+	GUARD_END(0)
+}
+
+extern "C" void yak_ch_destroy_bf(yak_ch_t *h) // htab.c:31-39
+{
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	b->eng->destroy_bloom();
+	for (int i = 0; i < 1 << h->pre; ++i) h->h[i].b = 0;
+	b->filters.clear();
+}
+
+extern "C" void yak_ch_destroy(yak_ch_t *h) // htab.c:41-49
+{
+	if (h == 0) return;
+	ChBox *b = box_of(h);
+	delete b->eng;
+	free(b->pub.h);
+	for (int i = 0; i < 2; ++i) if (b->pinned[i]) cudaFreeHost(b->pinned[i]);
+	b->d_in.release(); b->d_aux.release(); b->d_aux2.release();
+	b->magic = 0;
+	delete b;
+}
+
+extern "C" int yak_ch_insert_list(yak_ch_t *h, int create_new, int n, const uint64_t *a) // htab.c:51-78
+{
+	GUARD_BEGIN
+	if (n <= 0) return 0;
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	uint64_t *d = b->d_in.as<uint64_t>(n);
+	YAKB_CUDA(cudaMemcpyAsync(d, a, (size_t)n * 8, cudaMemcpyHostToDevice, b->eng->stream));
+	const int only = (int)(a[0] & ((1ull << h->pre) - 1));
+	ChunkStats st = b->eng->count_events(d, n, create_new, only);
+	return (int)st.n_new; // the caller adds this to h->tot (count.c:138)
+	GUARD_END(0)
+}
+
+extern "C" int yakb_ch_get_batch(const yak_ch_t *h, uint64_t n, const uint64_t *x, int32_t *out)
+{
+	GUARD_BEGIN
+	if (n == 0) return 0;
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	uint64_t *dx = b->d_in.as<uint64_t>(n);
+	int32_t *dout = b->d_aux.as<int32_t>(n);
+	YAKB_CUDA(cudaMemcpyAsync(dx, x, n * 8, cudaMemcpyHostToDevice, b->eng->stream));
+	b->eng->get_batch(dx, n, dout);
+	YAKB_CUDA(cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, b->eng->stream));
+	YAKB_CUDA(cudaStreamSynchronize(b->eng->stream));
+	return 0;
+	GUARD_END(-1)
+}
+
+extern "C" int yakb_ch_get_batch_dev(const yak_ch_t *h, uint64_t n, const uint64_t *d_x, int32_t *d_out)
+{
+	GUARD_BEGIN
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	b->eng->get_batch(d_x, n, d_out);
+	return 0;
+	GUARD_END(-1)
+}
+
+extern "C" int yak_ch_get(const yak_ch_t *h, uint64_t x) // htab.c:93-100
+{
+	int32_t r = -1;
+	if (yakb_ch_get_batch(h, 1, &x, &r) != 0) return -1;
+	return r;
+}
+
+extern "C" int yak_ch_inc(yak_ch_t *h, uint64_t x) // htab.c:80-91
+{
+	GUARD_BEGIN
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	return inc_one(b->eng, x);
+	GUARD_END(-1)
+}
+
+extern "C" void yak_ch_clear(yak_ch_t *h, int n_thread) // htab.c:116-130
+{
+	GUARD_BEGIN
+	(void)n_thread;
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	b->eng->clear();
+	GUARD_END_VOID
+}
+
+extern "C" void yak_ch_hist(const yak_ch_t *h, int64_t cnt[YAK_N_COUNTS], int n_thread) // htab.c:156-169
+{
+	GUARD_BEGIN
+	(void)n_thread;
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	b->eng->hist(cnt);
+	GUARD_END_VOID
+}
+
+extern "C" void yak_ch_shrink(yak_ch_t *h, int min, int max, int n_thread) // htab.c:199-208
+{
+	GUARD_BEGIN
+	(void)n_thread;
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	b->eng->shrink(min, max);
+	h->tot = b->eng->tot;
+	GUARD_END_VOID
+}
+
+extern "C" void yak_ch_setcnt(yak_ch_t *h, int cnt, int n_thread) // htab.c:229-235
+{
+	GUARD_BEGIN
+	(void)n_thread;
+	assert(cnt >= 0 && cnt <= YAK_MAX_COUNT);
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	setcnt(b->eng, cnt);
+	GUARD_END_VOID
+}
+
+extern "C" yak_knt_t *yak_ch_getseq(const yak_ch_t *h, int w, uint32_t *n) // htab.c:353-367
+{
+	GUARD_BEGIN
+	assert(h->k < 32 && w < 1 << h->pre);
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	LayoutOut lo;
+	b->eng->layout(w, w + 1, lo, true);
+	*n = lo.size[0];
+	yak_knt_t *a = (yak_knt_t*)calloc(*n ? *n : 1, sizeof(yak_knt_t));
+	const uint64_t mask = (1ULL << h->k * 2) - 1;
+	for (uint32_t i = 0; i < *n; ++i) {
+		a[i].x = hash64_inv(lo.keys[i] >> YAK_COUNTER_BITS << h->pre | (uint64_t)w, mask);
+		a[i].c = (int)(lo.keys[i] & YAK_MAX_COUNT);
+	}
+	return a;
+	GUARD_END(0)
+}
+
+static void unsupported(const char *fn)
+{
+	fprintf(stderr, "[yakb] ERROR: %s is not implemented by the B200 library yet (SURVEY 8(f) rank 1)\n", fn);
+	abort();
+}
+extern "C" void yak_ch_tighten(yak_ch_t *h) { (void)h; unsupported("yak_ch_tighten"); }
+extern "C" void yak_ch_merge(yak_ch_t *h0, yak_ch_t *h1, int min, int max, int n_thread, int pre_resize)
+{ (void)h0; (void)h1; (void)min; (void)max; (void)n_thread; (void)pre_resize; unsupported("yak_ch_merge"); }
+extern "C" void yak_ch_subtract(yak_ch_t *h0, const yak_ch_t *h1, int n_thread) { (void)h0; (void)h1; (void)n_thread; unsupported("yak_ch_subtract"); }
+extern "C" void yak_ch_isec(yak_ch_t *h0, const yak_ch_t *h1, int n_thread) { (void)h0; (void)h1; (void)n_thread; unsupported("yak_ch_isec"); }
+
+// ------------------------------------------------------------------ dump / restore
+
+// htab.c:373-394; sink(ptr,len) receives the bytes in order
+template<class Sink> static void serialise(ChBox *b, Sink &&sink)
+{
+	const yak_ch_t *h = &b->pub;
+	const int P = 1 << h->pre;
+	uint32_t t[3] = {(uint32_t)h->k, (uint32_t)h->pre, YAK_COUNTER_BITS};
+	sink(YAK_MAGIC, 4);
+	sink(t, 12);
+	const int step = 1024;
+	for (int s0 = 0; s0 < P; s0 += step) {
+		const int s1 = std::min(P, s0 + step);
+		LayoutOut lo;
+		b->eng->layout(s0, s1, lo, true);
+		for (int s = s0; s < s1; ++s) {
+			uint32_t u[2] = {lo.cap[s - s0], lo.size[s - s0]};
+			sink(u, 8);
+			if (u[1]) sink(lo.keys.data() + lo.off[s - s0], (size_t)u[1] * 8);
+		}
+	}
+}
+
+extern "C" int yak_ch_dump(const yak_ch_t *h, const char *fn)
+{
+	GUARD_BEGIN
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	FILE *fp = strcmp(fn, "-") ? fopen(fn, "wb") : stdout;
+	if (fp == 0) return -1;
+	static char iobuf[1 << 20];
+	setvbuf(fp, iobuf, _IOFBF, sizeof(iobuf));
+	serialise(b, [&](const void *p, size_t n) { fwrite(p, 1, n, fp); });
+	fprintf(stderr, "[M::%s] dumpped the hash table to file '%s'.\n", __func__, fn);
+	if (fp != stdout) fclose(fp); else { fflush(fp); setvbuf(fp, nullptr, _IOLBF, 0); }
+	return 0;
+	GUARD_END(-1)
+}
+
+extern "C" int64_t yakb_ch_dump_mem(const yak_ch_t *h, uint8_t **out)
+{
+	GUARD_BEGIN
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	std::vector<uint8_t> acc;
+	serialise(b, [&](const void *p, size_t n) { acc.insert(acc.end(), (const uint8_t*)p, (const uint8_t*)p + n); });
+	*out = (uint8_t*)malloc(acc.size() ? acc.size() : 1);
+	memcpy(*out, acc.data(), acc.size());
+	return (int64_t)acc.size();
+	GUARD_END(-1)
+}
+
+extern "C" yak_ch_t *yak_ch_restore_core(yak_ch_t *ch0, const char *fn, int mode, ...) // htab.c:396-476
+{
+	GUARD_BEGIN
+	if (mode != YAK_LOAD_ALL) {
+		if (mode < YAK_LOAD_ALL || mode > YAK_LOAD_SEXCHR3) return 0;
+		unsupported("yak_ch_restore_core(mode != YAK_LOAD_ALL)");
+	}
+	FILE *fp;
+	char magic[4];
+	uint32_t t[3];
+	if ((fp = fopen(fn, "rb")) == 0) return 0;
+	if (fread(magic, 1, 4, fp) != 4) { fclose(fp); return 0; }
+	if (strncmp(magic, YAK_MAGIC, 4) != 0) { fprintf(stderr, "ERROR: wrong file magic.\n"); fclose(fp); return 0; }
+	if (fread(t, 4, 3, fp) != 3) { fclose(fp); return 0; }
+	if (t[2] != YAK_COUNTER_BITS) {
+		fprintf(stderr, "ERROR: saved counter bits: %d; compile-time counter bits: %d\n", t[2], YAK_COUNTER_BITS);
+		fclose(fp);
+		return 0;
+	}
+	if (ch0) unsupported("yak_ch_restore_core(ch0 != NULL)");
+	yak_ch_t *ch = yak_ch_init(t[0], t[1], 0, 0);
+	if (!ch) { fclose(fp); return 0; }
+	ChBox *b = box_of(ch);
+	const int P = 1 << ch->pre;
+	std::vector<uint32_t> caps(P, 0);
+	std::vector<uint64_t> off(P + 1, 0), keys;
+	for (int s = 0; s < P; ++s) {
+		uint32_t u[2] = {0, 0};
+		if (fread(u, 4, 2, fp) != 2) u[0] = u[1] = 0;
+		caps[s] = u[0];
+		const size_t base = keys.size();
+		keys.resize(base + u[1]);
+		size_t got = u[1] ? fread(keys.data() + base, 8, u[1], fp) : 0;
+		keys.resize(base + got);
+		off[s + 1] = keys.size();
+	}
+	fclose(fp);
+	b->eng->load_subtables(caps, off, keys.data());
+	ch->tot = 0; // the reference leaves tot untouched on restore (htab.c:441)
+	fprintf(stderr, "[M::%s] inserted %ld k-mers, of which %ld are new\n", __func__, (long)keys.size(), (long)keys.size());
+	return ch;
+	GUARD_END(0)
+}
+
+extern "C" yak_ch_t *yak_ch_restore(const char *fn) { return yak_ch_restore_core(0, fn, YAK_LOAD_ALL); }
+
+// ------------------------------------------------------------------ chunk-level entry points
+
+static int run_ascii_dev(ChBox *b, const uint8_t *d_asc, uint64_t n, int create_new, uint64_t stats[4])
+{
+	ChunkStats st = b->eng->count_ascii(d_asc, n, create_new);
+	b->pub.tot = b->eng->tot;
+	if (stats) { stats[0] = st.n_events; stats[1] = st.n_pending; stats[2] = st.n_put; stats[3] = st.n_new; }
+	return 0;
+}
+
+extern "C" int yakb_count_ascii_dev(yak_ch_t *h, const void *d_asc, uint64_t n, int create_new, uint64_t stats[4])
+{
+	GUARD_BEGIN
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	return run_ascii_dev(b, (const uint8_t*)d_asc, n, create_new, stats);
+	GUARD_END(-1)
+}
+
+extern "C" int yakb_count_ascii_host(yak_ch_t *h, const char *asc, uint64_t n, int create_new, uint64_t stats[4])
+{
+	GUARD_BEGIN
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	uint8_t *d = b->d_in.as<uint8_t>(n + 64);
+	YAKB_CUDA(cudaMemcpyAsync(d, asc, n, cudaMemcpyHostToDevice, b->eng->stream));
+	return run_ascii_dev(b, d, n, create_new, stats);
+	GUARD_END(-1)
+}
+
+extern "C" int yakb_count_events_dev(yak_ch_t *h, const uint64_t *d_ev, uint64_t n, int create_new, uint64_t stats[4])
+{
+	GUARD_BEGIN
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	ChunkStats st = b->eng->count_events(d_ev, n, create_new, -1);
+	b->pub.tot = b->eng->tot;
+	if (stats) { stats[0] = st.n_events; stats[1] = st.n_pending; stats[2] = st.n_put; stats[3] = st.n_new; }
+	return 0;
+	GUARD_END(-1)
+}
+
+static DBuf g_route_scratch[8];
+static std::mutex g_route_mu;
+extern "C" int yakb_extract_route_dev(const void *d_asc, uint64_t n, int k, int pre, int world, uint64_t *d_out, uint64_t *counts, void *cuda_stream)
+{
+	GUARD_BEGIN
+	std::lock_guard<std::mutex> lk(g_route_mu);
+	return extract_events((const uint8_t*)d_asc, n, k, pre, world, d_out, counts, (cudaStream_t)cuda_stream, g_route_scratch);
+	GUARD_END(-1)
+}
+
+extern "C" int yakb_ch_reserve(yak_ch_t *h, uint64_t keys_per_subtable)
+{
+	GUARD_BEGIN
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	b->eng->reserve(keys_per_subtable);
+	return 0;
+	GUARD_END(-1)
+}
+
+extern "C" void *yakb_ch_stream(const yak_ch_t *h) { return (void*)box_of(h)->eng->stream; }
+extern "C" uint64_t yakb_ch_device_bytes(const yak_ch_t *h) { return box_of(h)->eng->device_bytes(); }
+extern "C" const char *yakb_version(void) { return YAKS_VERSION; }
+extern "C" int yakb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+extern "C" uint64_t yakb_kernel_launches(void) { return Engine::launches(); }
+
+extern "C" int yakb_synth_genome_dev(uint64_t seed_g, uint64_t G, uint64_t *d_genome2, void *cuda_stream)
+{
+	GUARD_BEGIN
+	synth_genome(seed_g, G, d_genome2, (cudaStream_t)cuda_stream);
+	return 0;
+	GUARD_END(-1)
+}
+extern "C" int yakb_synth_reads_dev(const uint64_t *d_genome2, uint64_t G, uint64_t seed_r, uint64_t first, uint64_t n_reads,
+                                    int L, double err, int n_pct, uint8_t *d_asc, void *cuda_stream)
+{
+	GUARD_BEGIN
+	synth_reads(d_genome2, G, seed_r, first, n_reads, L, err, n_pct, d_asc, (cudaStream_t)cuda_stream);
+	return 0;
+	GUARD_END(-1)
+}
+
+// ------------------------------------------------------------------ yak_count / yak_recount
+
+static uint64_t batch_bases(int64_t chunk_size)
+{
+	uint64_t b = 256ull << 20;
+	const char *e = getenv("YAKB_BATCH");
+	if (e && atoll(e) > 0) b = (uint64_t)atoll(e);
+	if ((uint64_t)chunk_size > b) b = (uint64_t)chunk_size;
+	if (b > 0x70000000ull) b = 0x70000000ull;
+	return b;
+}
+
+// count.c:147-166 with 85-145 folded in: read records, drop those shorter than k (count.c:95),
+// concatenate with '\n' separators into pinned memory, ship the batch, run the device path.
+extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *h0)
+{
+	GUARD_BEGIN
+	FastxReader rd;
+	if (!rd.open(fn)) return 0;
+	yak_ch_t *h = h0;
+	if (h0) assert(h0->k == opt->k && h0->pre == opt->pre);
+	else h = yak_ch_init(opt->k, opt->pre, opt->bf_n_hash, opt->bf_shift);
+	if (!h) return 0;
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	const int create_new = h0 == 0;
+	const uint64_t cap = batch_bases(opt->chunk_size);
+	std::vector<uint8_t> carry; // a record that did not fit the previous batch
+	bool done = false;
+	int64_t len;
+	size_t need = cap + (cap >> 4) + 4096;
+	if (b->pinned_cap < need) {
+		for (int i = 0; i < 2; ++i) { if (b->pinned[i]) cudaFreeHost(b->pinned[i]); b->pinned[i] = nullptr; }
+		YAKB_CUDA(cudaMallocHost(&b->pinned[0], need));
+		b->pinned_cap = need;
+	}
+	while (!done) {
+		uint8_t *buf = b->pinned[0];
+		uint64_t n = 0;
+		int n_seq = 0;
+		if (!carry.empty()) {
+			if (carry.size() + 1 > b->pinned_cap) { // a single record larger than the batch: grow
+				cudaFreeHost(b->pinned[0]);
+				b->pinned_cap = carry.size() + (carry.size() >> 3) + 4096;
+				YAKB_CUDA(cudaMallocHost(&b->pinned[0], b->pinned_cap));
+				buf = b->pinned[0];
+			}
+			memcpy(buf, carry.data(), carry.size());
+			n = carry.size(); buf[n++] = '\n'; ++n_seq;
+			carry.clear();
+		}
+		while (n < cap) {
+			len = rd.next();
+			if (len < 0) { done = true; break; }
+			if (len < opt->k) continue;
+			if (n + len + 1 > b->pinned_cap || n + (uint64_t)len + 1 > 0x7FFFFE00ull) { carry.assign(rd.seq().begin(), rd.seq().end()); break; }
+			memcpy(buf + n, rd.seq().data(), len);
+			n += len; buf[n++] = '\n'; ++n_seq;
+		}
+		if (n == 0) continue;
+		uint8_t *d = b->d_in.as<uint8_t>(n + 64);
+		YAKB_CUDA(cudaMemcpyAsync(d, buf, n, cudaMemcpyHostToDevice, b->eng->stream));
+		run_ascii_dev(b, d, n, create_new, nullptr);
+		fprintf(stderr, "[M::%s::%.3f*%.2f] processed %d sequences; %ld distinct k-mers in the hash table\n", __func__,
+		        wall_now() - g_t0, cpu_now() / (wall_now() - g_t0 + 1e-9), n_seq, (long)h->tot);
+	}
+	return h;
+	GUARD_END(0)
+}
+
+extern "C" void yak_recount(const char *fn, yak_ch_t *h) // count.c:168-193: clear, then count existing k-mers only
+{
+	yak_copt_t o;
+	yak_copt_init(&o);
+	o.k = h->k; o.pre = h->pre;
+	FILE *probe = (fn && strcmp(fn, "-")) ? fopen(fn, "rb") : stdin;
+	if (probe == 0) return; // count.c:172
+	if (probe != stdin) fclose(probe);
+	yak_ch_clear(h, 1);
+	// NB the reference does not drop reads shorter than k here, which changes nothing: they hold no k-mer
+	yak_count(fn, &o, h);
+}
+
+// ------------------------------------------------------------------ qv
+
+// one batch of sequences already concatenated with '\n' separators in pinned/host memory
+static void qv_batch(ChBox *b, const uint8_t *cat, uint64_t n, const std::vector<uint64_t> &seq_off, int min_len, double min_frac,
+                     unsigned long long *d_hist, int32_t *tot, int32_t *non0, std::vector<int16_t> *cnt_back)
+{
+	Engine *e = b->eng;
+	const uint64_t n_seq = seq_off.size() - 1;
+	uint8_t *d = b->d_in.as<uint8_t>(n + 64);
+	YAKB_CUDA(cudaMemcpyAsync(d, cat, n, cudaMemcpyHostToDevice, e->stream));
+	// layout of d_aux: int16 cnt[n] | u64 seq_off[n_seq+1] | i32 tot[n_seq] | i32 non0[n_seq] | u8 pass[n_seq]
+	const size_t o_cnt = 0, o_off = (n * 2 + 15) & ~(size_t)15, o_tot = o_off + (n_seq + 1) * 8, o_non0 = o_tot + n_seq * 4, o_pass = o_non0 + n_seq * 4;
+	uint8_t *base = b->d_aux.as<uint8_t>(o_pass + n_seq + 16);
+	int16_t *d_cnt = (int16_t*)(base + o_cnt);
+	uint64_t *d_off = (uint64_t*)(base + o_off);
+	int32_t *d_tot = (int32_t*)(base + o_tot), *d_non0 = (int32_t*)(base + o_non0);
+	uint8_t *d_pass = base + o_pass;
+	YAKB_CUDA(cudaMemcpyAsync(d_off, seq_off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+	qv_scan_ascii(e, d, n, d_cnt);
+	qv_stats(d_cnt, d_off, n_seq, min_len, min_frac, d_tot, d_non0, d_pass, d_hist, e->stream);
+	if (tot) YAKB_CUDA(cudaMemcpyAsync(tot, d_tot, n_seq * 4, cudaMemcpyDeviceToHost, e->stream));
+	if (non0) YAKB_CUDA(cudaMemcpyAsync(non0, d_non0, n_seq * 4, cudaMemcpyDeviceToHost, e->stream));
+	if (cnt_back) { cnt_back->resize(n); YAKB_CUDA(cudaMemcpyAsync(cnt_back->data(), d_cnt, n * 2, cudaMemcpyDeviceToHost, e->stream)); }
+	YAKB_CUDA(cudaStreamSynchronize(e->stream));
+}
+
+extern "C" int yakb_qv_seqs(const yak_ch_t *h, int64_t n_seq, const int64_t *lens, const char *cat,
+                            int min_len, double min_frac, int64_t cnt[YAK_N_COUNTS], int32_t *tot, int32_t *non0)
+{
+	GUARD_BEGIN
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	assert(h->k < 32); // qv.c:43
+	unsigned long long *d_hist = (unsigned long long*)b->d_aux2.need(1024 * 8);
+	YAKB_CUDA(cudaMemsetAsync(d_hist, 0, 1024 * 8, b->eng->stream));
+	const uint64_t cap = batch_bases(0);
+	int64_t s = 0, src = 0;
+	std::vector<uint8_t> buf;
+	while (s < n_seq) {
+		std::vector<uint64_t> off(1, 0);
+		buf.clear();
+		int64_t s_first = s;
+		while (s < n_seq && (buf.empty() || buf.size() + lens[s] + 1 <= cap)) {
+			buf.insert(buf.end(), cat + src, cat + src + lens[s]);
+			buf.push_back('\n');
+			off.push_back(buf.size());
+			src += lens[s]; ++s;
+		}
+		qv_batch(b, buf.data(), buf.size(), off, min_len, min_frac, d_hist, tot ? tot + s_first : nullptr, non0 ? non0 + s_first : nullptr, nullptr);
+	}
+	YAKB_CUDA(cudaMemcpyAsync(cnt, d_hist, 1024 * 8, cudaMemcpyDeviceToHost, b->eng->stream));
+	YAKB_CUDA(cudaStreamSynchronize(b->eng->stream));
+	return 0;
+	GUARD_END(-1)
+}
+
+// qv.c:116-135 (+ the SQ / EK printing of worker_qv, qv.c:62-81, done in input order)
+extern "C" void yak_qv(const yak_qopt_t *opt, const char *fn, const yak_ch_t *ch, int64_t *cnt)
+{
+	GUARD_BEGIN
+	ChBox *b = box_of(ch);
+	std::lock_guard<std::mutex> lk(b->mu);
+	assert(ch->k < 32); // qv.c:43
+	memset(cnt, 0, YAK_N_COUNTS * sizeof(int64_t));
+	FastxReader rd;
+	if (!rd.open(fn)) return;
+	unsigned long long *d_hist = (unsigned long long*)b->d_aux2.need(1024 * 8);
+	YAKB_CUDA(cudaMemsetAsync(d_hist, 0, 1024 * 8, b->eng->stream));
+	const uint64_t cap = std::min<uint64_t>(batch_bases(0), (uint64_t)std::max<int64_t>(opt->chunk_size, 1));
+	bool done = false;
+	std::vector<uint8_t> buf;
+	std::vector<std::string> names;
+	std::vector<int32_t> tot, non0;
+	std::vector<int16_t> back;
+	while (!done) {
+		std::vector<uint64_t> off(1, 0);
+		buf.clear(); names.clear();
+		while (buf.size() < cap) { // bseq.c:33-57: a batch closes once it holds >= chunk_size bases
+			int64_t len = rd.next();
+			if (len < 0) { done = true; break; }
+			buf.insert(buf.end(), rd.seq().begin(), rd.seq().end());
+			buf.push_back('\n');
+			off.push_back(buf.size());
+			if (opt->print_each || opt->print_err_kmer) names.push_back(rd.name());
+		}
+		const size_t n_seq = off.size() - 1;
+		fprintf(stderr, "[M::%s] read %d sequences\n", "yak_qv_cb", (int)n_seq);
+		if (n_seq == 0) break;
+		tot.resize(n_seq); non0.resize(n_seq);
+		qv_batch(b, buf.data(), buf.size(), off, opt->min_len, opt->min_frac, d_hist, tot.data(), non0.data(),
+		         opt->print_err_kmer ? &back : nullptr);
+		for (size_t s = 0; s < n_seq; ++s) {
+			const int l_seq = (int)(off[s + 1] - off[s] - 1);
+			if (l_seq < opt->min_len) continue;
+			if (opt->print_err_kmer)
+				for (uint64_t p = off[s]; p + 1 < off[s + 1]; ++p)
+					if (back[p] == 0) printf("EK\t%s\t%d\n", names[s].c_str(), (int)(p - off[s]) + 1 - ch->k);
+			if (opt->print_each) { // qv.c:70-81
+				double qv = -1.0;
+				if (tot[s] > 0) {
+					if (non0[s] > 0) {
+						if (tot[s] > non0[s]) { qv = log((double)tot[s] / non0[s]) / ch->k; qv = -4.3429448190325175 * log(qv); }
+						else qv = 99.0;
+					} else qv = 0.0;
+				}
+				printf("SQ\t%s\t%d\t%d\t%d\t%.2f\n", names[s].c_str(), l_seq, tot[s], non0[s], qv);
+			}
+		}
+		fprintf(stderr, "[M::%s@%.2f*%.2f] processed %d sequences\n", "yak_qv_cb", wall_now() - g_t0, cpu_now() / (wall_now() - g_t0 + 1e-6), (int)n_seq);
+	}
+	YAKB_CUDA(cudaMemcpyAsync(cnt, d_hist, 1024 * 8, cudaMemcpyDeviceToHost, b->eng->stream));
+	YAKB_CUDA(cudaStreamSynchronize(b->eng->stream));
+	GUARD_END_VOID
+}
+
+// ------------------------------------------------------------------ bbf.c as a stand-alone device filter
+
+extern "C" yak_bf_t *yak_bf_init(int n_shift, int n_hashes) // bbf.c:5-18
+{
+	GUARD_BEGIN
+	if (n_shift + YAK_BLK_SHIFT > 64 || n_shift < YAK_BLK_SHIFT) return 0;
+	if (yakb_device_count() == 0) { fprintf(stderr, "[yakb] ERROR: no CUDA device; this library has no CPU path\n"); return 0; }
+	yak_bf_t *b = (yak_bf_t*)calloc(1, sizeof(yak_bf_t));
+	b->n_shift = n_shift; b->n_hashes = n_hashes;
+	YAKB_CUDA(cudaMalloc((void**)&b->b, (size_t)1 << (n_shift - 3)));
+	YAKB_CUDA(cudaMemset(b->b, 0, (size_t)1 << (n_shift - 3)));
+	return b;
+	GUARD_END(0)
+}
+extern "C" void yak_bf_destroy(yak_bf_t *b) { if (b == 0) return; cudaFree(b->b); free(b); } // bbf.c:20-24
+extern "C" int yak_bf_insert(yak_bf_t *b, uint64_t hash) // bbf.c:25-42
+{
+	GUARD_BEGIN
+	return bf_insert_one(b->b, b->n_shift, b->n_hashes, hash);
+	GUARD_END(-1)
+}

@@ -1,0 +1,964 @@
+// engine.cu - the device-resident count table and the per-chunk hot path (sm_100a).
+//
+// Per chunk (pass 1, create_new=1; reference count.c:111-143 + htab.c:51-78):
+//   pack_ascii      ASCII -> 2-bit words + invalid mask                     (misc.c:4-21)
+//   k1_fused        roll canonical k-mers, yak_hash64, probe the table: a key already present is
+//                   a put-event whatever the bloom says (all its bits are set) -> counter++;
+//                   otherwise the position is flagged "pending"              (count.c:28-60)
+//   compact_*       pending events, in file order
+//   sort by group   group = bloom block (= low n_shift-9 bits of the hash) or a hash-bit bucket
+//   group_insert    one thread walks a group in file order: exact sequential bloom semantics
+//                   (bbf.c:25-42), first-put detection, insert + counter++    (htab.c:62-71)
+//   journal         new keys ordered by (sub-table, first-put time) appended as a segment
+// Pass 2 / lookups (create_new=0) are k1_fused alone.
+// v1 uses cub for the scans/sorts between our kernels; see DESIGN.md for what replaces them.
+#include "engine.cuh"
+#include "yakb_dev.cuh"
+#include "kernels.cuh"
+#include "extras.cuh"
+#include <cub/cub.cuh>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <atomic>
+
+namespace yakb {
+
+void cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+	char buf[512];
+	snprintf(buf, sizeof(buf), "[yakb] CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+	fprintf(stderr, "%s\n", buf);
+	throw CudaError(buf);
+}
+
+void *DBuf::need(size_t bytes)
+{
+	if (bytes > cap) {
+		if (p) YAKB_CUDA(cudaFree(p));
+		p = nullptr;
+		size_t want = bytes + (bytes >> 3) + 256;
+		YAKB_CUDA(cudaMalloc(&p, want));
+		cap = want;
+	}
+	return p;
+}
+void DBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+
+static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// number of OUR kernels launched (cub's are not counted); reported by bench.py as gpu_launches
+static std::atomic<uint64_t> g_launches{0};
+uint64_t Engine::launches() { return g_launches.load(); }
+void Engine::note_launch(int n) { g_launches += n; }
+
+// ============================================================ kernels
+
+// probe one event; returns 1 if the key is in the table (and bumps it by one), 0 if not
+__device__ __forceinline__ int probe_inc(uint64_t *slots, uint32_t cap, int pre, uint32_t Pmask, uint64_t v, int do_inc)
+{
+	if (cap == 0) return 0;
+	const uint32_t s = (uint32_t)v & Pmask;
+	const uint64_t x = v >> pre;
+	uint64_t *reg = slots + (uint64_t)s * cap;
+	uint32_t i = tab_home(x, cap);
+	for (uint32_t n = 0; n < cap; ++n) {
+		uint64_t cur = __ldcg((const unsigned long long*)&reg[i]);
+		if (cur == YAKB_EMPTY) return 0;
+		if ((cur >> YAKB_COUNTER_BITS) == x) { if (do_inc) slot_inc(&reg[i], cur, 1); return 1; }
+		if (++i == cap) i = 0;
+	}
+	return 0;
+}
+
+// ---- K1, fused front end: extraction + table probe.  One thread per 32-position word, persistent
+//      CTAs over 256-word tiles.  flags[W] bit r = position 32W+r is a pending event.
+//      stats[0] += events, glob_lput[s] = max(pos+1) over found (= put) events of sub-table s.
+template<bool LONGK>
+__global__ void __launch_bounds__(256) k1_fused(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords,
+                                                int k, int pre, uint32_t Pmask, uint64_t *slots, uint32_t cap, int create_new,
+                                                uint32_t *__restrict__ flags, uint32_t *__restrict__ tilecnt,
+                                                uint32_t *glob_lput, int smem_lp, unsigned long long *stats)
+{
+	extern __shared__ uint32_t s_lp[];
+	__shared__ uint32_t s_cnt;
+	__shared__ unsigned long long s_ev;
+	const uint32_t P = Pmask + 1;
+	if (smem_lp) for (uint32_t i = threadIdx.x; i < P; i += 256) s_lp[i] = 0;
+	if (threadIdx.x == 0) s_ev = 0;
+	__syncthreads();
+	const uint64_t ntiles = (nwords + 255) / 256;
+	uint32_t my_ev = 0;
+	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		if (threadIdx.x == 0) s_cnt = 0;
+		__syncthreads();
+		const uint64_t W = tile * 256 + threadIdx.x;
+		if (W < nwords) {
+			uint64_t v[32];
+			uint32_t vm = 0, pend = 0;
+			roll_word<LONGK>(w2, wm, W, k, [&](int r, uint64_t h) { v[r] = h; vm |= 1u << r; });
+			my_ev += __popc(vm);
+#pragma unroll
+			for (int r = 0; r < 32; ++r) {
+				if (vm >> r & 1) {
+					int found = probe_inc(slots, cap, pre, Pmask, v[r], 1);
+					if (create_new) {
+						if (!found) pend |= 1u << r;
+						else {
+							uint32_t t = (uint32_t)(W * 32 + r) + 1;
+							if (smem_lp) atomicMax(&s_lp[(uint32_t)v[r] & Pmask], t);
+							else atomicMax(&glob_lput[(uint32_t)v[r] & Pmask], t);
+						}
+					}
+				}
+			}
+			if (create_new) {
+				flags[W] = pend;
+				if (pend) atomicAdd(&s_cnt, __popc(pend));
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x == 0 && create_new) tilecnt[tile] = s_cnt;
+	}
+	if (my_ev) atomicAdd(&s_ev, (unsigned long long)my_ev);
+	__syncthreads();
+	if (threadIdx.x == 0 && s_ev) atomicAdd(&stats[0], s_ev);
+	if (smem_lp && create_new)
+		for (uint32_t i = threadIdx.x; i < P; i += 256) if (s_lp[i]) atomicMax(&glob_lput[i], s_lp[i]);
+}
+
+// ---- K1, array front end (events already hashed: yak_ch_insert_list, multi-GPU receive side).
+//      word W = events 32W..32W+31, lane = bit.
+__global__ void __launch_bounds__(256) k1_array(const uint64_t *__restrict__ ev, uint64_t n, int pre, uint32_t Pmask,
+                                                uint64_t *slots, uint32_t cap, int create_new, int only_s,
+                                                uint32_t *__restrict__ flags, uint32_t *__restrict__ tilecnt,
+                                                uint32_t *glob_lput, int smem_lp, unsigned long long *stats)
+{
+	extern __shared__ uint32_t s_lp[];
+	__shared__ uint32_t s_cnt;
+	__shared__ unsigned long long s_ev;
+	const uint32_t P = Pmask + 1;
+	if (smem_lp) for (uint32_t i = threadIdx.x; i < P; i += 256) s_lp[i] = 0;
+	if (threadIdx.x == 0) s_ev = 0;
+	__syncthreads();
+	const uint64_t nwords = (n + 31) / 32, ntiles = (nwords + 255) / 256;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t my_ev = 0;
+	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		if (threadIdx.x == 0) s_cnt = 0;
+		__syncthreads();
+		for (int it = 0; it < 32; ++it) {
+			const uint64_t W = tile * 256 + warp * 32 + it;
+			if (W >= nwords) break;
+			const uint64_t i = W * 32 + lane;
+			int valid = i < n, found = 0;
+			uint64_t v = valid ? ev[i] : 0;
+			if (valid && only_s >= 0 && ((uint32_t)v & Pmask) != (uint32_t)only_s) valid = 0;
+			if (valid) {
+				++my_ev;
+				found = probe_inc(slots, cap, pre, Pmask, v, 1);
+				if (found && create_new) {
+					uint32_t t = (uint32_t)i + 1;
+					if (smem_lp) atomicMax(&s_lp[(uint32_t)v & Pmask], t);
+					else atomicMax(&glob_lput[(uint32_t)v & Pmask], t);
+				}
+			}
+			if (create_new) {
+				uint32_t pend = __ballot_sync(0xffffffffu, valid && !found);
+				if (lane == 0) { flags[W] = pend; if (pend) atomicAdd(&s_cnt, __popc(pend)); }
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x == 0 && create_new) tilecnt[tile] = s_cnt;
+	}
+	if (my_ev) atomicAdd(&s_ev, (unsigned long long)my_ev);
+	__syncthreads();
+	if (threadIdx.x == 0 && s_ev) atomicAdd(&stats[0], s_ev);
+	if (smem_lp && create_new)
+		for (uint32_t i = threadIdx.x; i < P; i += 256) if (s_lp[i]) atomicMax(&glob_lput[i], s_lp[i]);
+}
+
+__global__ void __launch_bounds__(256) compact_array(const uint64_t *__restrict__ ev, uint64_t nwords,
+                                                     const uint32_t *__restrict__ flags, const uint32_t *__restrict__ tileoff,
+                                                     uint64_t *__restrict__ pv, uint32_t *__restrict__ ppos)
+{
+	const uint64_t W = blockIdx.x * 256ull + threadIdx.x;
+	uint32_t f = W < nwords ? flags[W] : 0;
+	uint32_t o = tileoff[blockIdx.x] + block_excl_scan_256(__popc(f), nullptr);
+	while (f) {
+		int r = __ffs(f) - 1;
+		f &= f - 1;
+		pv[o] = ev[W * 32 + r]; ppos[o] = (uint32_t)(W * 32 + r); ++o;
+	}
+}
+
+__global__ void iota_kernel(uint32_t *a, uint64_t n)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i < n) a[i] = (uint32_t)i;
+}
+
+__global__ void pend_hist_kernel(const uint64_t *__restrict__ pv, uint64_t n, uint32_t Pmask, uint32_t *pend)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i < n) atomicAdd(&pend[(uint32_t)pv[i] & Pmask], 1u);
+}
+
+__global__ void max_need_kernel(const uint32_t *nkeys, const uint32_t *pend, uint32_t P, uint32_t *out)
+{
+	__shared__ uint32_t s_m;
+	if (threadIdx.x == 0) s_m = 0;
+	__syncthreads();
+	uint32_t m = 0;
+	for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) m = max(m, nkeys[i] + (pend ? pend[i] : 0));
+	atomicMax(&s_m, m);
+	__syncthreads();
+	if (threadIdx.x == 0) *out = s_m;
+}
+
+// ---- the ordered part: one thread per group, events of a group walked in file order.
+//      pflag[j]: bit0 = put-event, bit1 = this put inserted a new key.
+__global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__ sv, const uint32_t *__restrict__ sj, uint64_t n,
+                                                    int G, int pre, uint32_t Pmask, uint64_t *slots, uint32_t cap,
+                                                    uint32_t *bloom32, int nb, int sub_shift, int n_hash,
+                                                    uint8_t *__restrict__ pflag)
+{
+	const uint64_t i = blockIdx.x * 256ull + threadIdx.x;
+	if (i >= n) return;
+	const uint64_t gmask = G >= 64 ? ~0ull : (1ull << G) - 1;
+	const uint64_t gk = sv[i] & gmask;
+	if (i > 0 && (sv[i - 1] & gmask) == gk) return;
+	for (uint64_t e = i; e < n; ++e) {
+		const uint64_t v = sv[e];
+		if ((v & gmask) != gk) break;
+		const uint32_t j = sj[e];
+		const uint32_t s = (uint32_t)v & Pmask;
+		const uint64_t x = v >> pre;
+		int put = 1;
+		if (bloom32) { // bbf.c:25-42 on the 64-byte block this group owns
+			uint32_t *blk = bloom32 + (((uint64_t)s << nb) | (x & ((1ull << nb) - 1))) * 16;
+			uint32_t h1 = (uint32_t)(x >> nb) & 511, h2 = (uint32_t)(x >> sub_shift) & 511, z;
+			int c = 0;
+			if ((h2 & 31) == 0) h2 = (h2 + 1) & 511;
+			z = h1;
+			for (int t = 0; t < n_hash; ++t, z = (z + h2) & 511) {
+				uint32_t w = __ldcg(&blk[z >> 5]), m = 1u << (z & 31);
+				c += (w & m) != 0;
+				__stcg(&blk[z >> 5], w | m);
+			}
+			put = c == n_hash;
+		}
+		uint8_t flag = 0;
+		if (put) { // htab.c:66-70
+			uint64_t *reg = slots + (uint64_t)s * cap;
+			uint32_t q = tab_home(x, cap);
+			const uint64_t fresh_val = x << YAKB_COUNTER_BITS | 1;
+			for (;;) {
+				uint64_t cur = __ldcg((const unsigned long long*)&reg[q]);
+				if (cur == YAKB_EMPTY) {
+					uint64_t prev = atomicCAS((unsigned long long*)&reg[q], (unsigned long long)YAKB_EMPTY, (unsigned long long)fresh_val);
+					if (prev == YAKB_EMPTY) { flag = 3; break; }
+					cur = prev;
+				}
+				if ((cur >> YAKB_COUNTER_BITS) == x) { slot_inc(&reg[q], cur, 1); flag = 1; break; }
+				if (++q == cap) q = 0;
+			}
+		}
+		pflag[j] = flag;
+	}
+}
+
+// ---- per sub-table max position (+1) of pending put-events / new-key puts of this chunk
+__global__ void __launch_bounds__(256) post_pending(const uint64_t *__restrict__ pv, const uint32_t *__restrict__ ppos,
+                                                    uint8_t *__restrict__ pflag, uint64_t n, uint32_t Pmask,
+                                                    uint32_t *glob_lput, uint32_t *glob_lnew, int smem_ok, unsigned long long *stats)
+{
+	extern __shared__ uint32_t s_arr[];
+	const uint32_t P = Pmask + 1;
+	uint32_t *s_lp = s_arr, *s_ln = s_arr + P;
+	if (smem_ok) for (uint32_t i = threadIdx.x; i < 2 * P; i += 256) s_arr[i] = 0;
+	__syncthreads();
+	uint32_t nput = 0;
+	for (uint64_t j = blockIdx.x * 256ull + threadIdx.x; j < n; j += gridDim.x * 256ull) {
+		uint8_t f = pflag[j];
+		pflag[n + j] = f >> 1 & 1;
+		if (!(f & 1)) continue;
+		++nput;
+		uint32_t s = (uint32_t)pv[j] & Pmask, t = ppos[j] + 1;
+		if (smem_ok) { atomicMax(&s_lp[s], t); if (f & 2) atomicMax(&s_ln[s], t); }
+		else { atomicMax(&glob_lput[s], t); if (f & 2) atomicMax(&glob_lnew[s], t); }
+	}
+	if (nput) atomicAdd(&stats[1], (unsigned long long)nput);
+	__syncthreads();
+	if (smem_ok)
+		for (uint32_t i = threadIdx.x; i < P; i += 256) {
+			if (s_lp[i]) atomicMax(&glob_lput[i], s_lp[i]);
+			if (s_ln[i]) atomicMax(&glob_lnew[i], s_ln[i]);
+		}
+}
+
+__global__ void merge_times_kernel(uint32_t P, uint32_t seq, const uint32_t *lput, const uint32_t *lnew, uint64_t *last_put, uint64_t *last_new)
+{
+	uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= P) return;
+	if (lput[s]) last_put[s] = (uint64_t)(seq + 1) << 32 | lput[s];
+	if (lnew[s]) last_new[s] = (uint64_t)(seq + 1) << 32 | lnew[s];
+}
+
+// off[s] = first index whose sub-table >= s (sorted by the low `pre` bits), s in [0, P]
+__global__ void seg_offsets_kernel(const uint64_t *__restrict__ sorted, uint64_t n, uint32_t Pmask, uint64_t *off, uint32_t *nkeys)
+{
+	uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s > Pmask + 1) return;
+	uint64_t lo = 0, hi = n;
+	while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (((uint32_t)sorted[mid] & Pmask) < s) lo = mid + 1; else hi = mid; }
+	off[s] = lo;
+}
+__global__ void seg_addkeys_kernel(const uint64_t *off, uint32_t P, uint32_t *nkeys)
+{
+	uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s < P) nkeys[s] += (uint32_t)(off[s + 1] - off[s]);
+}
+__global__ void seg_keys_kernel(const uint64_t *__restrict__ sorted, uint64_t n, int pre, uint64_t *__restrict__ keys)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i < n) keys[i] = sorted[i] >> pre << YAKB_COUNTER_BITS;
+}
+
+// ---- re-place every used slot into a table with a different per-sub-table capacity
+__global__ void rehash_kernel(const uint64_t *__restrict__ old_slots, uint32_t old_cap, uint64_t total, uint64_t *new_slots, uint32_t new_cap)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i >= total) return;
+	uint64_t val = old_slots[i];
+	if (val == YAKB_EMPTY) return;
+	uint64_t *reg = new_slots + (i / old_cap) * new_cap;
+	uint32_t q = tab_home(val >> YAKB_COUNTER_BITS, new_cap);
+	for (;;) {
+		uint64_t prev = atomicCAS((unsigned long long*)&reg[q], (unsigned long long)YAKB_EMPTY, (unsigned long long)val);
+		if (prev == YAKB_EMPTY) return;
+		if (++q == new_cap) q = 0;
+	}
+}
+
+// stored keys (with counts) of sub-tables given by off[] into the table (restore / shrink rebuild)
+__global__ void bulk_insert_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ off, uint32_t P, uint64_t n,
+                                   uint64_t *slots, uint32_t cap)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t lo = 0, hi = P; // sub-table s with off[s] <= i < off[s+1]
+	while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
+	uint64_t val = keys[i], x = val >> YAKB_COUNTER_BITS;
+	uint64_t *reg = slots + (uint64_t)lo * cap;
+	uint32_t q = tab_home(x, cap);
+	for (;;) {
+		uint64_t cur = __ldcg((const unsigned long long*)&reg[q]);
+		if (cur == YAKB_EMPTY) {
+			uint64_t prev = atomicCAS((unsigned long long*)&reg[q], (unsigned long long)YAKB_EMPTY, (unsigned long long)val);
+			if (prev == YAKB_EMPTY) return;
+			cur = prev;
+		}
+		if ((cur >> YAKB_COUNTER_BITS) == x) return; // duplicate key in the file: first claim wins
+		if (++q == cap) q = 0;
+	}
+}
+
+__global__ void clear_kernel(uint64_t *slots, uint64_t total)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i < total) { uint64_t v = slots[i]; if (v != YAKB_EMPTY) slots[i] = v & ~(uint64_t)YAKB_MAX_COUNT; }
+}
+
+__global__ void __launch_bounds__(256) hist_kernel(const uint64_t *__restrict__ slots, uint64_t total, unsigned long long *hist)
+{
+	__shared__ uint32_t s_h[1024];
+	for (int i = threadIdx.x; i < 1024; i += 256) s_h[i] = 0;
+	__syncthreads();
+	for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < total; i += gridDim.x * 256ull) {
+		uint64_t v = slots[i];
+		if (v != YAKB_EMPTY) atomicAdd(&s_h[v & YAKB_MAX_COUNT], 1u);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < 1024; i += 256) if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
+}
+
+// htab.c:93-100
+__global__ void get_batch_kernel(const uint64_t *__restrict__ xs, uint64_t n, int pre, uint32_t Pmask,
+                                 const uint64_t *__restrict__ slots, uint32_t cap, int32_t *__restrict__ out)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint64_t v = xs[i];
+	int32_t r = -1;
+	if (cap) {
+		int64_t q = tab_find(slots + (uint64_t)((uint32_t)v & Pmask) * cap, cap, v >> pre);
+		if (q >= 0) r = (int32_t)(slots[(uint64_t)((uint32_t)v & Pmask) * cap + q] & YAKB_MAX_COUNT);
+	}
+	out[i] = r;
+}
+
+// qv.c:48-66: per position the count of its k-mer (absent -> 0), or -1 where no k-mer ends
+template<bool LONGK>
+__global__ void __launch_bounds__(256) qv_scan_kernel(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords, uint64_t n,
+                                                      int k, int pre, uint32_t Pmask, const uint64_t *__restrict__ slots, uint32_t cap,
+                                                      int16_t *__restrict__ out)
+{
+	const uint64_t W = blockIdx.x * 256ull + threadIdx.x;
+	if (W >= nwords) return;
+	int16_t res[32];
+#pragma unroll
+	for (int r = 0; r < 32; ++r) res[r] = -1;
+	roll_word<LONGK>(w2, wm, W, k, [&](int r, uint64_t v) {
+		int16_t c = 0;
+		if (cap) {
+			const uint64_t *reg = slots + (uint64_t)((uint32_t)v & Pmask) * cap;
+			int64_t q = tab_find(reg, cap, v >> pre);
+			if (q >= 0) c = (int16_t)(reg[q] & YAKB_MAX_COUNT);
+		}
+		res[r] = c;
+	});
+#pragma unroll
+	for (int r = 0; r < 32; ++r) if (W * 32 + r < n) out[W * 32 + r] = res[r];
+}
+
+// ---- rebuild the reference's khashl layout (khashl.h:137-221) from the insertion journal.
+//      One thread per sub-table: the kick-out rehash is a sequential procedure per table.
+__global__ void build_layout_kernel(const uint64_t *__restrict__ cat, const uint64_t *__restrict__ catoff,
+                                    const uint8_t *__restrict__ pre_flag, const uint32_t *__restrict__ pre_val,
+                                    const uint8_t *__restrict__ trailing,
+                                    uint64_t *keys_all, const uint64_t *__restrict__ koff,
+                                    uint32_t *bm_all, const uint64_t *__restrict__ boff,
+                                    int ns, uint32_t *out_cap, uint32_t *out_size, uint64_t *outkeys)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= ns) return;
+	uint64_t *K = keys_all + koff[t];
+	const uint64_t bwords = (boff[t + 1] - boff[t]) / 2;
+	uint32_t *used = bm_all + boff[t], *occ = used + bwords;
+	uint32_t bits = 0, n = 0, count = 0;
+	const uint64_t *src = cat + catoff[t];
+	const uint64_t m = catoff[t + 1] - catoff[t];
+	auto fw = [](uint32_t nb) { return nb < 32 ? 1u : nb >> 5; };
+	auto resize = [&](uint32_t request) { // khashl.h:152-195
+		uint32_t lg = 0, q = request;
+		while ((q >>= 1) != 0) ++lg;
+		if (request & (request - 1)) ++lg;
+		const uint32_t new_bits = lg > 2 ? lg : 2, new_n = 1u << new_bits, new_mask = new_n - 1;
+		if (count > (new_n >> 1) + (new_n >> 2)) return;
+		for (uint32_t w = 0; w < fw(new_n); ++w) occ[w] = 0;
+		for (uint32_t j = 0; j != n; ++j) {
+			if (!(used[j >> 5] >> (j & 31) & 1)) continue;
+			uint64_t key = K[j];
+			used[j >> 5] &= ~(1u << (j & 31));
+			for (;;) {
+				uint32_t i = kh_home(key, new_bits);
+				while (occ[i >> 5] >> (i & 31) & 1) i = (i + 1) & new_mask;
+				occ[i >> 5] |= 1u << (i & 31);
+				if (i < n && (used[i >> 5] >> (i & 31) & 1)) {
+					uint64_t ev = K[i]; K[i] = key; key = ev;
+					used[i >> 5] &= ~(1u << (i & 31));
+				} else { K[i] = key; break; }
+			}
+		}
+		uint32_t *tmp = used; used = occ; occ = tmp;
+		bits = new_bits; n = new_n;
+	};
+	used[0] = 0;
+	if (pre_flag[t]) resize(pre_val[t]);
+	for (uint64_t e = 0; e < m; ++e) { // khashl.h:197-221
+		const uint64_t key = src[e];
+		if (count >= (n >> 1) + (n >> 2)) resize(n + 1);
+		const uint32_t mask = n - 1;
+		uint32_t i = kh_home(key, bits), start = i;
+		while ((used[i >> 5] >> (i & 31) & 1) && (K[i] >> YAKB_COUNTER_BITS) != (key >> YAKB_COUNTER_BITS)) {
+			i = (i + 1) & mask;
+			if (i == start) break;
+		}
+		if (!(used[i >> 5] >> (i & 31) & 1)) { K[i] = key; used[i >> 5] |= 1u << (i & 31); ++count; }
+	}
+	if (trailing[t] && count >= (n >> 1) + (n >> 2)) resize(n + 1); // a later put of an existing key (quirk Q3)
+	out_cap[t] = n; out_size[t] = count;
+	uint64_t *dst = outkeys + catoff[t];
+	uint64_t r = 0;
+	for (uint32_t i = 0; i < n; ++i) if (used[i >> 5] >> (i & 31) & 1) dst[r++] = K[i];
+}
+
+// attach the current counts to slot-ordered keys of sub-tables s0.. (off[] local to the range)
+__global__ void fill_counts_kernel(uint64_t *keys, const uint64_t *__restrict__ off, int ns, int s0, uint64_t n,
+                                   const uint64_t *__restrict__ slots, uint32_t cap)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t lo = 0, hi = ns;
+	while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
+	const uint64_t *reg = slots + (uint64_t)(s0 + lo) * cap;
+	uint64_t key = keys[i];
+	int64_t q = tab_find(reg, cap, key >> YAKB_COUNTER_BITS);
+	if (q >= 0) keys[i] = (key & ~(uint64_t)YAKB_MAX_COUNT) | (reg[q] & YAKB_MAX_COUNT);
+}
+
+// copy the runs of sub-tables [s0, s0+ns) of one journal segment behind what earlier segments put
+__global__ void gather_seg_kernel(const uint64_t *__restrict__ seg_keys, const uint64_t *__restrict__ seg_off, int s0, int ns,
+                                  const uint64_t *__restrict__ catoff, const uint64_t *__restrict__ run, uint64_t *__restrict__ cat)
+{
+	const uint64_t base = seg_off[s0], n = seg_off[s0 + ns] - base;
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t lo = 0, hi = ns;
+	while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (seg_off[s0 + mid] - base <= i) lo = mid; else hi = mid; }
+	cat[catoff[lo] + run[lo] + (i - (seg_off[s0 + lo] - base))] = seg_keys[base + i];
+}
+__global__ void advance_run_kernel(const uint64_t *__restrict__ seg_off, int s0, int ns, uint64_t *run)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < ns) run[t] += seg_off[s0 + t + 1] - seg_off[s0 + t];
+}
+
+// ============================================================ host side
+
+Engine *Engine::create(int k, int pre, int n_hash, int n_shift)
+{
+	if (pre < YAKB_COUNTER_BITS) return nullptr; // htab.c:17
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) {
+		fprintf(stderr, "[yakb] ERROR: no CUDA device (%s); this library has no CPU path\n", cudaGetErrorString(e));
+		return nullptr;
+	}
+	Engine *g = new Engine;
+	g->k = k, g->pre = pre, g->P = 1 << pre;
+	YAKB_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+	YAKB_CUDA(cudaMalloc(&g->nkeys, g->P * sizeof(uint32_t)));
+	YAKB_CUDA(cudaMalloc(&g->last_put, g->P * sizeof(uint64_t)));
+	YAKB_CUDA(cudaMalloc(&g->last_new, g->P * sizeof(uint64_t)));
+	YAKB_CUDA(cudaMemsetAsync(g->nkeys, 0, g->P * sizeof(uint32_t), g->stream));
+	YAKB_CUDA(cudaMemsetAsync(g->last_put, 0, g->P * sizeof(uint64_t), g->stream));
+	YAKB_CUDA(cudaMemsetAsync(g->last_new, 0, g->P * sizeof(uint64_t), g->stream));
+	g->presize_flag.assign(g->P, 0);
+	g->presize_val.assign(g->P, 0);
+	// htab.c:23-27 + bbf.c:9: a filter exists iff n_hash>0, n_shift>pre and 9 <= n_shift-pre <= 55
+	if (n_hash > 0 && n_shift > pre) {
+		g->n_hash = n_hash, g->n_shift = n_shift;
+		int sub = n_shift - pre;
+		if (sub >= 9 && sub + 9 <= 64) {
+			g->nb = sub - 9;
+			size_t bytes = (size_t)1 << (n_shift - 3);
+			YAKB_CUDA(cudaMalloc(&g->bloom, bytes));
+			YAKB_CUDA(cudaMemsetAsync(g->bloom, 0, bytes, g->stream));
+		}
+	}
+	YAKB_CUDA(cudaStreamSynchronize(g->stream));
+	return g;
+}
+
+Engine::~Engine()
+{
+	if (slots) cudaFree(slots);
+	if (nkeys) cudaFree(nkeys);
+	if (bloom) cudaFree(bloom);
+	if (last_put) cudaFree(last_put);
+	if (last_new) cudaFree(last_new);
+	for (auto &s : journal) { cudaFree(s.keys); cudaFree(s.off); }
+	DBuf *all[] = {&b_w2, &b_wm, &b_flags, &b_tilecnt, &b_tileoff, &b_pv, &b_ppos, &b_sv, &b_sj, &b_iota, &b_pflag, &b_newv,
+	               &b_newsorted, &b_tmp, &b_pend, &b_lput, &b_lnew, &b_stats, &b_misc};
+	for (DBuf *b : all) b->release();
+	if (stream) cudaStreamDestroy(stream);
+}
+
+void Engine::destroy_bloom() { if (bloom) { cudaFree(bloom); bloom = nullptr; } }
+
+uint64_t Engine::device_bytes() const
+{
+	uint64_t b = (uint64_t)P * cap * 8 + (bloom ? (uint64_t)1 << (n_shift - 3) : 0);
+	for (auto &s : journal) b += s.n * 8 + (uint64_t)(P + 1) * 8;
+	return b;
+}
+
+void Engine::grow(uint32_t new_cap)
+{
+	uint64_t *ns = nullptr;
+	const uint64_t total_new = (uint64_t)P * new_cap;
+	YAKB_CUDA(cudaMalloc(&ns, total_new * 8));
+	YAKB_CUDA(cudaMemsetAsync(ns, 0xFF, total_new * 8, stream));
+	if (slots && cap) {
+		const uint64_t total_old = (uint64_t)P * cap;
+		rehash_kernel<<<cdiv(total_old, 256), 256, 0, stream>>>(slots, cap, total_old, ns, new_cap);
+		YAKB_CUDA(cudaGetLastError());
+		YAKB_CUDA(cudaStreamSynchronize(stream));
+		YAKB_CUDA(cudaFree(slots));
+	}
+	slots = ns; cap = new_cap;
+}
+
+void Engine::reserve(uint64_t keys_per_subtable)
+{
+	uint64_t want = (uint64_t)(keys_per_subtable / load_limit) + 16;
+	if (want > 0xFFFFFFF0ull) throw CudaError("[yakb] sub-table capacity overflow");
+	if (want > cap) grow((uint32_t)want);
+}
+
+static int smem_lp_ok(int P, int arrays) { return (size_t)P * 4 * arrays <= 64 * 1024; }
+
+template<class K> static void set_smem(K kern, size_t bytes)
+{
+	if (bytes > 48 * 1024) YAKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+ChunkStats Engine::count_ascii(const uint8_t *d_asc, uint64_t n, int create_new)
+{
+	ChunkStats st = {0, 0, 0, 0};
+	if (n == 0) return st;
+	if (n >= 0x7FFFFF00ull) throw CudaError("[yakb] chunk too large (positions are 31-bit)");
+	const uint64_t nwords = (n + 31) / 32;
+	uint64_t *w2 = b_w2.as<uint64_t>(nwords);
+	uint32_t *wm = b_wm.as<uint32_t>(nwords);
+	pack_ascii_kernel<<<cdiv(nwords, 256), 256, 0, stream>>>(d_asc, n, w2, wm, nwords);
+	YAKB_CUDA(cudaGetLastError());
+	note_launch(1);
+	return finish_chunk(nwords, create_new, w2, wm, nullptr, n, -1);
+}
+
+ChunkStats Engine::count_events(const uint64_t *d_ev, uint64_t n, int create_new, int only_s)
+{
+	ChunkStats st = {0, 0, 0, 0};
+	if (n == 0) return st;
+	if (n >= 0x7FFFFF00ull) throw CudaError("[yakb] chunk too large (positions are 31-bit)");
+	return finish_chunk((n + 31) / 32, create_new, nullptr, nullptr, d_ev, n, only_s);
+}
+
+// common tail of both front ends.  n_units: #bases (ASCII) or #events (array front end)
+ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t *w2, const uint32_t *wm,
+                                const uint64_t *d_ev, uint64_t n_units, int only_s)
+{
+	ChunkStats st = {0, 0, 0, 0};
+	const uint32_t Pmask = P - 1;
+	const bool longk = k >= 32;
+	const uint64_t n_ev_in = n_units;
+	const uint64_t ntiles = (nwords + 255) / 256;
+	uint32_t *flags = create_new ? b_flags.as<uint32_t>(nwords) : nullptr;
+	uint32_t *tilecnt = create_new ? b_tilecnt.as<uint32_t>(ntiles + 1) : nullptr;
+	uint32_t *tileoff = create_new ? b_tileoff.as<uint32_t>(ntiles + 1) : nullptr;
+	uint32_t *lput = b_lput.as<uint32_t>(P), *lnew = b_lnew.as<uint32_t>(P);
+	unsigned long long *stats = b_stats.as<unsigned long long>(4);
+	YAKB_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned long long), stream));
+	if (create_new) {
+		YAKB_CUDA(cudaMemsetAsync(lput, 0, P * 4, stream));
+		YAKB_CUDA(cudaMemsetAsync(lnew, 0, P * 4, stream));
+		YAKB_CUDA(cudaMemsetAsync(tilecnt + ntiles, 0, 4, stream));
+	}
+	int dev = 0, nsm = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+	const int smem1 = create_new && smem_lp_ok(P, 1);
+	const size_t sm1 = smem1 ? (size_t)P * 4 : 0;
+	const uint32_t grid1 = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)nsm * 4);
+	if (d_ev == nullptr) {
+		if (longk) {
+			set_smem(k1_fused<true>, sm1);
+			k1_fused<true><<<grid1, 256, sm1, stream>>>(w2, wm, nwords, k, pre, Pmask, slots, cap, create_new, flags, tilecnt, lput, smem1, stats);
+		} else {
+			set_smem(k1_fused<false>, sm1);
+			k1_fused<false><<<grid1, 256, sm1, stream>>>(w2, wm, nwords, k, pre, Pmask, slots, cap, create_new, flags, tilecnt, lput, smem1, stats);
+		}
+	} else {
+		set_smem(k1_array, sm1);
+		k1_array<<<grid1, 256, sm1, stream>>>(d_ev, n_ev_in, pre, Pmask, slots, cap, create_new, only_s, flags, tilecnt, lput, smem1, stats);
+	}
+	YAKB_CUDA(cudaGetLastError());
+	note_launch(1); // k1
+	unsigned long long h_stats[4] = {0, 0, 0, 0};
+	if (!create_new) {
+		YAKB_CUDA(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
+		YAKB_CUDA(cudaStreamSynchronize(stream));
+		st.n_events = h_stats[0];
+		++chunk_seq;
+		return st;
+	}
+	// pending list in file order
+	size_t tmp_bytes = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, tilecnt, tileoff, (int)(ntiles + 1), stream);
+	cub::DeviceScan::ExclusiveSum(b_tmp.need(tmp_bytes), tmp_bytes, tilecnt, tileoff, (int)(ntiles + 1), stream);
+	uint32_t n_pending = 0;
+	YAKB_CUDA(cudaMemcpyAsync(&n_pending, tileoff + ntiles, 4, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+	st.n_pending = n_pending;
+	uint64_t n_new = 0;
+	if (n_pending) {
+		uint64_t *pv = b_pv.as<uint64_t>(n_pending);
+		uint32_t *ppos = b_ppos.as<uint32_t>(n_pending);
+		if (d_ev == nullptr) {
+			if (longk) compact_fused<true><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, flags, tileoff, pv, ppos);
+			else compact_fused<false><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, flags, tileoff, pv, ppos);
+		} else compact_array<<<(uint32_t)ntiles, 256, 0, stream>>>(d_ev, nwords, flags, tileoff, pv, ppos);
+		YAKB_CUDA(cudaGetLastError());
+		// make room: every pending event may be a new key of its sub-table
+		uint32_t *pend = b_pend.as<uint32_t>(P + 1);
+		YAKB_CUDA(cudaMemsetAsync(pend, 0, (P + 1) * 4, stream));
+		pend_hist_kernel<<<cdiv(n_pending, 256), 256, 0, stream>>>(pv, n_pending, Pmask, pend);
+		max_need_kernel<<<1, 1024, 0, stream>>>(nkeys, pend, P, pend + P);
+		uint32_t need = 0;
+		YAKB_CUDA(cudaMemcpyAsync(&need, pend + P, 4, cudaMemcpyDeviceToHost, stream));
+		YAKB_CUDA(cudaStreamSynchronize(stream));
+		if ((double)need > load_limit * cap) {
+			uint64_t want = std::max<uint64_t>((uint64_t)(need / load_limit) + 16, (uint64_t)cap + cap / 2);
+			if (want > 0xFFFFFFF0ull) throw CudaError("[yakb] sub-table capacity overflow");
+			grow((uint32_t)want);
+		}
+		// group key: the bloom block (bbf.c:27-28: low n_shift-9 bits of the hash, sub-table included)
+		// or, without a filter, enough low hash bits to keep groups short
+		int G;
+		const int vbits = longk ? 64 : 2 * k;
+		if (bloom) G = n_shift - 9;
+		else { G = pre; while (G < vbits && (1ull << G) < (uint64_t)n_pending / 2) ++G; }
+		if (G > vbits) G = vbits;
+		uint32_t *iota = b_iota.as<uint32_t>(n_pending);
+		iota_kernel<<<cdiv(n_pending, 256), 256, 0, stream>>>(iota, n_pending);
+		uint64_t *sv = b_sv.as<uint64_t>(n_pending);
+		uint32_t *sj = b_sj.as<uint32_t>(n_pending);
+		tmp_bytes = 0;
+		cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, pv, sv, iota, sj, (int)n_pending, 0, G, stream);
+		cub::DeviceRadixSort::SortPairs(b_tmp.need(tmp_bytes), tmp_bytes, pv, sv, iota, sj, (int)n_pending, 0, G, stream);
+		uint8_t *pflag = b_pflag.as<uint8_t>(2 * (size_t)n_pending); // [0,n): put/new bits, [n,2n): new-key flag
+		group_insert<<<cdiv(n_pending, 256), 256, 0, stream>>>(sv, sj, n_pending, G, pre, Pmask, slots, cap,
+		                                                       (uint32_t*)bloom, nb, n_shift - pre, n_hash, pflag);
+		YAKB_CUDA(cudaGetLastError());
+		const int smem2 = smem_lp_ok(P, 2);
+		const size_t sm2 = smem2 ? (size_t)P * 8 : 0;
+		set_smem(post_pending, sm2);
+		post_pending<<<std::min<uint32_t>(cdiv(n_pending, 256), nsm * 4), 256, sm2, stream>>>(pv, ppos, pflag, n_pending, Pmask, lput, lnew, smem2, stats);
+		YAKB_CUDA(cudaGetLastError());
+		note_launch(6); // compact, pend_hist, max_need, iota, group_insert, post_pending
+		// new keys in file order, then stably by sub-table -> journal segment
+		uint64_t *newv = b_newv.as<uint64_t>(n_pending);
+		uint32_t *d_nsel = (uint32_t*)(stats + 2);
+		const uint8_t *isnew = pflag + n_pending; // written by post_pending
+		tmp_bytes = 0;
+		cub::DeviceSelect::Flagged(nullptr, tmp_bytes, pv, isnew, newv, d_nsel, (int)n_pending, stream);
+		cub::DeviceSelect::Flagged(b_tmp.need(tmp_bytes), tmp_bytes, pv, isnew, newv, d_nsel, (int)n_pending, stream);
+		YAKB_CUDA(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
+		YAKB_CUDA(cudaStreamSynchronize(stream));
+		n_new = (uint32_t)h_stats[2];
+		if (n_new) {
+			uint64_t *sorted = b_newsorted.as<uint64_t>(n_new);
+			tmp_bytes = 0;
+			cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, newv, sorted, (int)n_new, 0, pre, stream);
+			cub::DeviceRadixSort::SortKeys(b_tmp.need(tmp_bytes), tmp_bytes, newv, sorted, (int)n_new, 0, pre, stream);
+			Segment seg;
+			seg.n = n_new;
+			YAKB_CUDA(cudaMalloc(&seg.keys, n_new * 8));
+			YAKB_CUDA(cudaMalloc(&seg.off, (uint64_t)(P + 1) * 8));
+			seg_offsets_kernel<<<cdiv(P + 1, 256), 256, 0, stream>>>(sorted, n_new, Pmask, seg.off, nkeys);
+			seg_addkeys_kernel<<<cdiv(P, 256), 256, 0, stream>>>(seg.off, P, nkeys);
+			seg_keys_kernel<<<cdiv(n_new, 256), 256, 0, stream>>>(sorted, n_new, pre, seg.keys);
+			YAKB_CUDA(cudaGetLastError());
+			journal.push_back(seg);
+			note_launch(3);
+		}
+	} else {
+		YAKB_CUDA(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
+		YAKB_CUDA(cudaStreamSynchronize(stream));
+	}
+	merge_times_kernel<<<cdiv(P, 256), 256, 0, stream>>>(P, chunk_seq, lput, lnew, last_put, last_new);
+	YAKB_CUDA(cudaGetLastError());
+	note_launch(1);
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+	st.n_events = h_stats[0];
+	st.n_put = h_stats[1] + (st.n_events - st.n_pending);
+	st.n_new = n_new;
+	tot += n_new;
+	++chunk_seq;
+	return st;
+}
+
+void Engine::clear()
+{
+	const uint64_t total = (uint64_t)P * cap;
+	if (total) clear_kernel<<<cdiv(total, 256), 256, 0, stream>>>(slots, total);
+	YAKB_CUDA(cudaGetLastError());
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Engine::hist(int64_t cnt[1024])
+{
+	unsigned long long *d = (unsigned long long*)b_tmp.need(1024 * 8);
+	YAKB_CUDA(cudaMemsetAsync(d, 0, 1024 * 8, stream));
+	const uint64_t total = (uint64_t)P * cap;
+	if (total) hist_kernel<<<std::min<uint32_t>(cdiv(total, 256), 148 * 8), 256, 0, stream>>>(slots, total, d);
+	YAKB_CUDA(cudaGetLastError());
+	YAKB_CUDA(cudaMemcpyAsync(cnt, d, 1024 * 8, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Engine::get_batch(const uint64_t *d_x, uint64_t n, int32_t *d_out)
+{
+	if (n == 0) return;
+	get_batch_kernel<<<cdiv(n, 256), 256, 0, stream>>>(d_x, n, pre, P - 1, slots, cap, d_out);
+	YAKB_CUDA(cudaGetLastError());
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+}
+
+// capacity khashl ends with after `presize`, m distinct puts and the optional trailing put
+static uint32_t final_capacity(bool pflag, uint32_t pval, uint64_t m, bool trailing)
+{
+	uint64_t n = 0, count = 0;
+	if (pflag) {
+		uint32_t lg = 0, q = pval;
+		while ((q >>= 1) != 0) ++lg;
+		if (pval & (pval - 1)) ++lg;
+		n = 1ull << (lg > 2 ? lg : 2);
+	}
+	// puts: a doubling happens whenever count reaches 3/4 n before a put
+	while (count < m) {
+		uint64_t thr = (n >> 1) + (n >> 2);
+		if (count >= thr) { n = n ? n * 2 : 4; continue; }
+		count = std::min<uint64_t>(m, thr);
+	}
+	if (trailing && count >= (n >> 1) + (n >> 2)) n = n ? n * 2 : 4;
+	return (uint32_t)n;
+}
+
+void Engine::layout(int s0, int s1, LayoutOut &out, bool with_counts)
+{
+	const int nsub = s1 - s0;
+	out.cap.assign(nsub, 0); out.size.assign(nsub, 0); out.off.assign(nsub + 1, 0); out.keys.clear();
+	// per-sub-table journal lengths and trailing flags
+	std::vector<uint32_t> h_nkeys(nsub);
+	std::vector<uint64_t> h_lp(nsub), h_ln(nsub);
+	YAKB_CUDA(cudaMemcpyAsync(h_nkeys.data(), nkeys + s0, nsub * 4, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaMemcpyAsync(h_lp.data(), last_put + s0, nsub * 8, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaMemcpyAsync(h_ln.data(), last_new + s0, nsub * 8, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+	// process in batches bounded by scratch memory
+	const uint64_t budget = 6ull << 30;
+	int b0 = 0;
+	while (b0 < nsub) {
+		std::vector<uint64_t> catoff(1, 0), koff(1, 0), boff(1, 0);
+		std::vector<uint8_t> trail, pf;
+		std::vector<uint32_t> pvv;
+		int b1 = b0;
+		uint64_t bytes = 0;
+		while (b1 < nsub) {
+			const int s = s0 + b1;
+			const bool tr = h_lp[b1] > h_ln[b1];
+			const uint32_t capf = final_capacity(presize_flag[s], presize_val[s], h_nkeys[b1], tr);
+			const uint64_t bw = 2 * (uint64_t)(capf < 32 ? 1 : capf >> 5);
+			const uint64_t add = (uint64_t)capf * 8 + bw * 4 + (uint64_t)h_nkeys[b1] * 16;
+			if (b1 > b0 && bytes + add > budget) break;
+			bytes += add;
+			catoff.push_back(catoff.back() + h_nkeys[b1]);
+			koff.push_back(koff.back() + std::max<uint32_t>(capf, 4));
+			boff.push_back(boff.back() + std::max<uint64_t>(bw, 2));
+			trail.push_back(tr); pf.push_back(presize_flag[s]); pvv.push_back(presize_val[s]);
+			++b1;
+		}
+		const int ns = b1 - b0;
+		const uint64_t ncat = catoff.back();
+		uint64_t *d_cat, *d_out, *d_keys, *d_catoff, *d_koff, *d_boff, *d_run;
+		uint32_t *d_bm, *d_pv, *d_ocap, *d_osize;
+		uint8_t *d_trail, *d_pf;
+		YAKB_CUDA(cudaMalloc(&d_cat, std::max<uint64_t>(ncat, 1) * 8));
+		YAKB_CUDA(cudaMalloc(&d_out, std::max<uint64_t>(ncat, 1) * 8));
+		YAKB_CUDA(cudaMalloc(&d_keys, koff.back() * 8));
+		YAKB_CUDA(cudaMalloc(&d_bm, boff.back() * 4));
+		YAKB_CUDA(cudaMalloc(&d_catoff, (ns + 1) * 8)); YAKB_CUDA(cudaMalloc(&d_koff, (ns + 1) * 8)); YAKB_CUDA(cudaMalloc(&d_boff, (ns + 1) * 8));
+		YAKB_CUDA(cudaMalloc(&d_run, ns * 8));
+		YAKB_CUDA(cudaMalloc(&d_pv, ns * 4)); YAKB_CUDA(cudaMalloc(&d_ocap, ns * 4)); YAKB_CUDA(cudaMalloc(&d_osize, ns * 4));
+		YAKB_CUDA(cudaMalloc(&d_trail, ns)); YAKB_CUDA(cudaMalloc(&d_pf, ns));
+		YAKB_CUDA(cudaMemcpyAsync(d_catoff, catoff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
+		YAKB_CUDA(cudaMemcpyAsync(d_koff, koff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
+		YAKB_CUDA(cudaMemcpyAsync(d_boff, boff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
+		YAKB_CUDA(cudaMemcpyAsync(d_pv, pvv.data(), ns * 4, cudaMemcpyHostToDevice, stream));
+		YAKB_CUDA(cudaMemcpyAsync(d_trail, trail.data(), ns, cudaMemcpyHostToDevice, stream));
+		YAKB_CUDA(cudaMemcpyAsync(d_pf, pf.data(), ns, cudaMemcpyHostToDevice, stream));
+		YAKB_CUDA(cudaMemsetAsync(d_run, 0, ns * 8, stream));
+		for (auto &seg : journal) {
+			gather_seg_kernel<<<std::max<uint32_t>(1, cdiv(seg.n, 256)), 256, 0, stream>>>(seg.keys, seg.off, s0 + b0, ns, d_catoff, d_run, d_cat);
+			advance_run_kernel<<<cdiv(ns, 256), 256, 0, stream>>>(seg.off, s0 + b0, ns, d_run);
+		}
+		YAKB_CUDA(cudaGetLastError());
+		build_layout_kernel<<<cdiv(ns, 32), 32, 0, stream>>>(d_cat, d_catoff, d_pf, d_pv, d_trail, d_keys, d_koff, d_bm, d_boff, ns, d_ocap, d_osize, d_out);
+		YAKB_CUDA(cudaGetLastError());
+		if (with_counts && ncat && cap)
+			fill_counts_kernel<<<cdiv(ncat, 256), 256, 0, stream>>>(d_out, d_catoff, ns, s0 + b0, ncat, slots, cap);
+		YAKB_CUDA(cudaGetLastError());
+		const size_t base = out.keys.size();
+		out.keys.resize(base + ncat);
+		if (ncat) YAKB_CUDA(cudaMemcpyAsync(out.keys.data() + base, d_out, ncat * 8, cudaMemcpyDeviceToHost, stream));
+		YAKB_CUDA(cudaMemcpyAsync(out.cap.data() + b0, d_ocap, ns * 4, cudaMemcpyDeviceToHost, stream));
+		YAKB_CUDA(cudaMemcpyAsync(out.size.data() + b0, d_osize, ns * 4, cudaMemcpyDeviceToHost, stream));
+		YAKB_CUDA(cudaStreamSynchronize(stream));
+		for (int t = 0; t < ns; ++t) out.off[b0 + t + 1] = out.off[b0 + t] + (catoff[t + 1] - catoff[t]);
+		cudaFree(d_cat); cudaFree(d_out); cudaFree(d_keys); cudaFree(d_bm); cudaFree(d_catoff); cudaFree(d_koff); cudaFree(d_boff);
+		cudaFree(d_run); cudaFree(d_pv); cudaFree(d_ocap); cudaFree(d_osize); cudaFree(d_trail); cudaFree(d_pf);
+		b0 = b1;
+	}
+	// journal duplicates (only possible from a malformed restore) would make size < run length
+	for (int t = 0; t < nsub; ++t)
+		if (out.size[t] != out.off[t + 1] - out.off[t]) throw CudaError("[yakb] layout: journal holds duplicate keys");
+}
+
+void Engine::load_subtables(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys)
+{
+	const uint64_t n = off[P];
+	uint32_t mx = 0;
+	std::vector<uint32_t> cnt(P);
+	for (int s = 0; s < P; ++s) { cnt[s] = (uint32_t)(off[s + 1] - off[s]); mx = std::max(mx, cnt[s]); presize_flag[s] = 1; presize_val[s] = caps[s]; }
+	reserve(std::max<uint32_t>(mx, 8));
+	Segment seg;
+	seg.n = n;
+	YAKB_CUDA(cudaMalloc(&seg.keys, std::max<uint64_t>(n, 1) * 8));
+	YAKB_CUDA(cudaMalloc(&seg.off, (uint64_t)(P + 1) * 8));
+	YAKB_CUDA(cudaMemcpyAsync(seg.off, off.data(), (uint64_t)(P + 1) * 8, cudaMemcpyHostToDevice, stream));
+	if (n) {
+		YAKB_CUDA(cudaMemcpyAsync(seg.keys, keys, n * 8, cudaMemcpyHostToDevice, stream));
+		bulk_insert_kernel<<<cdiv(n, 256), 256, 0, stream>>>(seg.keys, seg.off, P, n, slots, cap);
+		clear_kernel<<<cdiv(n, 256), 256, 0, stream>>>(seg.keys, n); // journal keeps keys without counts
+		YAKB_CUDA(cudaGetLastError());
+	}
+	YAKB_CUDA(cudaMemcpyAsync(nkeys, cnt.data(), P * 4, cudaMemcpyHostToDevice, stream));
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+	journal.push_back(seg);
+	tot = n;
+}
+
+void Engine::shrink(int min, int max)
+{
+	if (!(max >= min && max <= 1023)) max = 1023;
+	// htab.c:183-193: old slots upward, keep min<=count<=max, into a set pre-sized to the OLD size
+	LayoutOut lo;
+	layout(0, P, lo, true);
+	std::vector<uint64_t> kept; kept.reserve(lo.keys.size());
+	std::vector<uint64_t> off(P + 1, 0);
+	std::vector<uint32_t> caps(P);
+	for (int s = 0; s < P; ++s) {
+		for (uint64_t i = lo.off[s]; i < lo.off[s + 1]; ++i) {
+			int c = (int)(lo.keys[i] & YAKB_MAX_COUNT);
+			if (c >= min && c <= max) kept.push_back(lo.keys[i]);
+		}
+		off[s + 1] = kept.size();
+		caps[s] = lo.size[s]; // yak_ht_resize(f, kh_size(g))
+	}
+	// drop the old table and journal, rebuild from the kept keys
+	for (auto &sg : journal) { cudaFree(sg.keys); cudaFree(sg.off); }
+	journal.clear();
+	if (slots) { YAKB_CUDA(cudaFree(slots)); slots = nullptr; cap = 0; }
+	YAKB_CUDA(cudaMemsetAsync(last_put, 0, P * 8, stream));
+	YAKB_CUDA(cudaMemsetAsync(last_new, 0, P * 8, stream));
+	load_subtables(caps, off, kept.data());
+}
+
+void qv_scan_ascii(Engine *e, const uint8_t *d_asc, uint64_t n, int16_t *d_cnt)
+{
+	if (n == 0) return;
+	const uint64_t nwords = (n + 31) / 32;
+	uint64_t *w2 = e->b_w2.as<uint64_t>(nwords);
+	uint32_t *wm = e->b_wm.as<uint32_t>(nwords);
+	pack_ascii_kernel<<<cdiv(nwords, 256), 256, 0, e->stream>>>(d_asc, n, w2, wm, nwords);
+	if (e->k >= 32) qv_scan_kernel<true><<<cdiv(nwords, 256), 256, 0, e->stream>>>(w2, wm, nwords, n, e->k, e->pre, e->P - 1, e->slots, e->cap, d_cnt);
+	else qv_scan_kernel<false><<<cdiv(nwords, 256), 256, 0, e->stream>>>(w2, wm, nwords, n, e->k, e->pre, e->P - 1, e->slots, e->cap, d_cnt);
+	YAKB_CUDA(cudaGetLastError());
+	YAKB_CUDA(cudaStreamSynchronize(e->stream));
+}
+
+} // namespace yakb

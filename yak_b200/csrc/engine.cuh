@@ -1,0 +1,96 @@
+// engine.cuh - host-side view of the device-resident count table and its per-chunk pipeline.
+//
+// One Engine backs one yak_ch_t.  HBM layout (all device memory unless noted):
+//   slots[P*cap]      u64   count table; region s = sub-table s; slot = (v>>pre)<<10 | count
+//   nkeys[P]          u32   distinct keys per sub-table
+//   bloom             u8    2^(n_shift-3) bytes; block b of sub-filter s at ((s<<nb)|b)*64
+//   journal           list of segments; segment = new keys of one chunk ordered by
+//                     (sub-table, first-put time) + P+1 offsets.  Concatenating a sub-table's
+//                     runs over segments gives the order in which the reference's khashl saw
+//                     its distinct keys, which (with `presize` and `trailing`) determines the
+//                     .yak slot layout.
+//   last_put/last_new[P] u64 time of the last put-event / last new-key put (trailing flag, Q3)
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <vector>
+#include <string>
+#include <stdexcept>
+#include <cuda_runtime.h>
+
+namespace yakb {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+void cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+#define YAKB_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) ::yakb::cuda_fail(e__, #x, __FILE__, __LINE__); } while (0)
+
+// grow-only device buffer
+struct DBuf {
+	void *p = nullptr; size_t cap = 0;
+	void *need(size_t bytes);
+	template<class T> T *as(size_t n) { return (T*)need(n * sizeof(T)); }
+	void release();
+};
+
+struct Segment { uint64_t *keys; uint64_t *off; uint64_t n; };
+
+struct ChunkStats { uint64_t n_events, n_pending, n_put, n_new; };
+
+// result of rebuilding the reference layout for a range of sub-tables (host memory)
+struct LayoutOut {
+	std::vector<uint32_t> cap, size;    // per sub-table in the range
+	std::vector<uint64_t> off;          // size+1 offsets into keys
+	std::vector<uint64_t> keys;         // stored keys (with counts) in slot order
+};
+
+struct Engine {
+	int k = 0, pre = 0, n_hash = 0, n_shift = 0, P = 0;
+	uint64_t *slots = nullptr; uint32_t cap = 0;
+	uint32_t *nkeys = nullptr;
+	uint8_t *bloom = nullptr; int nb = 0;
+	uint64_t *last_put = nullptr, *last_new = nullptr;
+	std::vector<uint8_t> presize_flag;      // host
+	std::vector<uint32_t> presize_val;      // host
+	std::vector<Segment> journal;
+	uint32_t chunk_seq = 0;
+	uint64_t tot = 0;
+	cudaStream_t stream = nullptr;
+	double load_limit = 0.6;
+	// scratch (grow-only, reused by every chunk)
+	DBuf b_w2, b_wm, b_flags, b_tilecnt, b_tileoff, b_pv, b_ppos, b_sv, b_sj, b_iota, b_pflag, b_newv, b_newsorted,
+	     b_tmp, b_pend, b_lput, b_lnew, b_stats, b_misc;
+
+	static Engine *create(int k, int pre, int n_hash, int n_shift);
+	~Engine();
+	void destroy_bloom();
+
+	// ---- per-chunk hot path ----
+	// bases: device ASCII (any non-ACGTU byte separates reads), n bytes
+	ChunkStats count_ascii(const uint8_t *d_asc, uint64_t n, int create_new);
+	// events: device array of hashed k-mers in file order; only_s >= 0 keeps one sub-table (htab.c:61)
+	ChunkStats count_events(const uint64_t *d_ev, uint64_t n, int create_new, int only_s);
+
+	// ---- table-wide ops ----
+	void clear();                                  // htab.c:116-130
+	void hist(int64_t cnt[1024]);                  // htab.c:136-169
+	void shrink(int min, int max);                 // htab.c:175-208
+	void get_batch(const uint64_t *d_x, uint64_t n, int32_t *d_out);  // htab.c:93-100, device in/out
+	void reserve(uint64_t keys_per_subtable);      // grow regions so every sub-table can take this many
+	// rebuild the reference's khashl layout of sub-tables [s0, s1) and bring it to the host
+	void layout(int s0, int s1, LayoutOut &out, bool with_counts = true);
+	// restore: sub-table s gets `keys` (stored form, with counts) in file order, khashl pre-sized to cap
+	void load_subtables(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys);
+	uint64_t device_bytes() const;
+	static uint64_t launches();
+	static void note_launch(int n);
+
+private:
+	ChunkStats finish_chunk(uint64_t n_words, int create_new, const uint64_t *w2, const uint32_t *wm,
+	                        const uint64_t *d_ev, uint64_t n_units, int only_s);
+	void grow(uint32_t new_cap);
+};
+
+// lookups for qv (qv.c:34-86): per position count (-1 = no k-mer event there), device in/out
+void qv_scan_ascii(Engine *e, const uint8_t *d_asc, uint64_t n, int16_t *d_cnt);
+
+} // namespace yakb

@@ -1,0 +1,260 @@
+// extras.cu - kernels around the count path: event extraction to an array (multi-GPU routing),
+// qv per-sequence statistics, single-key ops, the seeded synthetic generator.
+#include "engine.cuh"
+#include "yakb_dev.cuh"
+#include "kernels.cuh"
+#include "extras.cuh"
+#include <cub/cub.cuh>
+#include <stdio.h>
+#include <algorithm>
+
+namespace yakb {
+
+static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+
+// bit r of vmask[W] = a k-mer ends at position 32W+r (depends on the invalid mask only); tile counts
+__global__ void __launch_bounds__(256) valid_mask_kernel(const uint32_t *__restrict__ wm, uint64_t nwords, int k,
+                                                         uint32_t *__restrict__ vmask, uint32_t *__restrict__ tilecnt)
+{
+	__shared__ uint32_t s_cnt;
+	if (threadIdx.x == 0) s_cnt = 0;
+	__syncthreads();
+	const uint64_t W = blockIdx.x * 256ull + threadIdx.x;
+	if (W < nwords) {
+		int l = 0;
+		for (int64_t p = (int64_t)(W * 32) - (k - 1); p < (int64_t)(W * 32); ++p) {
+			if (p < 0) continue;
+			l = (wm[p >> 5] >> (31 - (p & 31)) & 1) ? 0 : l + 1;
+		}
+		const uint32_t cm = wm[W];
+		uint32_t m = 0;
+#pragma unroll
+		for (int r = 0; r < 32; ++r) {
+			l = (cm >> (31 - r) & 1) ? 0 : (l < 64 ? l + 1 : l);
+			if (l >= k) m |= 1u << r;
+		}
+		vmask[W] = m;
+		if (m) atomicAdd(&s_cnt, __popc(m));
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) tilecnt[blockIdx.x] = s_cnt;
+}
+
+__global__ void rank_offsets_kernel(const uint64_t *__restrict__ sorted, uint64_t n, int pre, int lw, int world, uint64_t *off)
+{
+	int r = threadIdx.x;
+	if (r > world) return;
+	const uint32_t fmask = (1u << lw) - 1;
+	uint64_t lo = 0, hi = n;
+	while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if ((uint32_t)((sorted[mid] >> (pre - lw)) & fmask) < (uint32_t)r) lo = mid + 1; else hi = mid; }
+	off[r] = lo;
+}
+
+int extract_events(const uint8_t *d_asc, uint64_t n, int k, int pre, int world, uint64_t *d_out, uint64_t *counts,
+                   cudaStream_t stream, DBuf *scratch /* 8 buffers */)
+{
+	for (int r = 0; r < world; ++r) counts[r] = 0;
+	if (n == 0) return 0;
+	const uint64_t nwords = (n + 31) / 32, ntiles = (nwords + 255) / 256;
+	uint64_t *w2 = scratch[0].as<uint64_t>(nwords);
+	uint32_t *wm = scratch[1].as<uint32_t>(nwords);
+	uint32_t *vmask = scratch[2].as<uint32_t>(nwords);
+	uint32_t *tilecnt = scratch[3].as<uint32_t>(ntiles + 1), *tileoff = scratch[4].as<uint32_t>(ntiles + 1);
+	uint32_t *ppos = scratch[5].as<uint32_t>(n);
+	pack_ascii_kernel<<<cdiv(nwords, 256), 256, 0, stream>>>(d_asc, n, w2, wm, nwords);
+	valid_mask_kernel<<<(uint32_t)ntiles, 256, 0, stream>>>(wm, nwords, k, vmask, tilecnt);
+	YAKB_CUDA(cudaMemsetAsync(tilecnt + ntiles, 0, 4, stream));
+	size_t tb = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, tb, tilecnt, tileoff, (int)(ntiles + 1), stream);
+	cub::DeviceScan::ExclusiveSum(scratch[6].need(tb), tb, tilecnt, tileoff, (int)(ntiles + 1), stream);
+	uint32_t n_ev = 0;
+	YAKB_CUDA(cudaMemcpyAsync(&n_ev, tileoff + ntiles, 4, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+	if (n_ev == 0) return 0;
+	int lw = 0;
+	while ((1 << lw) < world) ++lw;
+	if ((1 << lw) != world || lw > pre) { fprintf(stderr, "[yakb] ERROR: world size must be a power of two <= 2^pre\n"); return -1; }
+	uint64_t *ev = lw ? scratch[7].as<uint64_t>(n_ev) : d_out;
+	if (k >= 32) compact_fused<true><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, vmask, tileoff, ev, ppos);
+	else compact_fused<false><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, vmask, tileoff, ev, ppos);
+	YAKB_CUDA(cudaGetLastError());
+	if (lw == 0) { counts[0] = n_ev; YAKB_CUDA(cudaStreamSynchronize(stream)); return 0; }
+	// owner rank = top lw bits of the sub-table index = hash bits [pre-lw, pre); stable sort on them
+	tb = 0;
+	cub::DeviceRadixSort::SortKeys(nullptr, tb, ev, d_out, (int)n_ev, pre - lw, pre, stream);
+	cub::DeviceRadixSort::SortKeys(scratch[6].need(tb), tb, ev, d_out, (int)n_ev, pre - lw, pre, stream);
+	// per-rank counts: lower bounds in the sorted owner field (host binary search over device data
+	// would sync per probe; a tiny kernel does all ranks at once)
+	uint64_t *d_off = (uint64_t*)scratch[4].need((world + 1) * 8);
+	rank_offsets_kernel<<<1, 64, 0, stream>>>(d_out, n_ev, pre, lw, world, d_off);
+	std::vector<uint64_t> off(world + 1);
+	YAKB_CUDA(cudaMemcpyAsync(off.data(), d_off, (world + 1) * 8, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+	for (int r = 0; r < world; ++r) counts[r] = off[r + 1] - off[r];
+	return 0;
+}
+
+// ---- qv.c:44-85 per sequence: tot / non0 and the min_frac gate.  One warp per sequence.
+//      seq_off[s] = offset of sequence s in the position array; its last position is a separator.
+__global__ void __launch_bounds__(256) qv_seq_stats_kernel(const int16_t *__restrict__ cnt, const uint64_t *__restrict__ seq_off, uint64_t n_seq,
+                                                           int min_len, double min_frac, int32_t *__restrict__ tot, int32_t *__restrict__ non0,
+                                                           uint8_t *__restrict__ pass)
+{
+	const uint64_t s = (blockIdx.x * 256ull + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (s >= n_seq) return;
+	const uint64_t b = seq_off[s], e = seq_off[s + 1] - 1;
+	int t = 0, z = 0;
+	if ((int64_t)(e - b) >= min_len)
+		for (uint64_t p = b + lane; p < e; p += 32) { int c = cnt[p]; t += c >= 0; z += c > 0; }
+#pragma unroll
+	for (int d = 16; d; d >>= 1) { t += __shfl_xor_sync(0xffffffffu, t, d); z += __shfl_xor_sync(0xffffffffu, z, d); }
+	if (lane == 0) {
+		tot[s] = t; non0[s] = z;
+		pass[s] = (int64_t)(e - b) >= min_len && !((double)z < (double)t * min_frac);
+	}
+}
+
+__global__ void __launch_bounds__(256) qv_hist_kernel(const int16_t *__restrict__ cnt, const uint64_t *__restrict__ seq_off, uint64_t n_seq,
+                                                      const uint8_t *__restrict__ pass, unsigned long long *hist)
+{
+	__shared__ uint32_t s_h[1024];
+	for (int i = threadIdx.x; i < 1024; i += 256) s_h[i] = 0;
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	for (uint64_t s = (blockIdx.x * 256ull + threadIdx.x) >> 5; s < n_seq; s += (gridDim.x * 256ull) >> 5) {
+		if (!pass[s]) continue;
+		const uint64_t b = seq_off[s], e = seq_off[s + 1] - 1;
+		for (uint64_t p = b + lane; p < e; p += 32) { int c = cnt[p]; if (c >= 0) atomicAdd(&s_h[c], 1u); }
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < 1024; i += 256) if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
+}
+
+void qv_stats(const int16_t *d_cnt, const uint64_t *d_seq_off, uint64_t n_seq, int min_len, double min_frac,
+              int32_t *d_tot, int32_t *d_non0, uint8_t *d_pass, unsigned long long *d_hist, cudaStream_t stream)
+{
+	if (n_seq == 0) return;
+	qv_seq_stats_kernel<<<cdiv(n_seq * 32, 256), 256, 0, stream>>>(d_cnt, d_seq_off, n_seq, min_len, min_frac, d_tot, d_non0, d_pass);
+	qv_hist_kernel<<<std::min<uint32_t>(cdiv(n_seq * 32, 256), 148 * 8), 256, 0, stream>>>(d_cnt, d_seq_off, n_seq, d_pass, d_hist);
+	YAKB_CUDA(cudaGetLastError());
+}
+
+// ---- htab.c:80-91 for one key
+__global__ void inc_one_kernel(uint64_t *slots, uint32_t cap, int pre, uint32_t Pmask, uint64_t v, int32_t *out)
+{
+	int32_t r = -1;
+	if (cap) {
+		uint64_t *reg = slots + (uint64_t)((uint32_t)v & Pmask) * cap;
+		int64_t q = tab_find(reg, cap, v >> pre);
+		if (q >= 0) {
+			uint64_t cur = reg[q];
+			if ((cur & YAKB_MAX_COUNT) < YAKB_MAX_COUNT) reg[q] = ++cur;
+			r = (int32_t)(cur & YAKB_MAX_COUNT);
+		}
+	}
+	*out = r;
+}
+int inc_one(Engine *e, uint64_t v)
+{
+	int32_t *d = (int32_t*)e->b_misc.need(16), h = -1;
+	inc_one_kernel<<<1, 1, 0, e->stream>>>(e->slots, e->cap, e->pre, e->P - 1, v, d);
+	YAKB_CUDA(cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, e->stream));
+	YAKB_CUDA(cudaStreamSynchronize(e->stream));
+	return h;
+}
+
+// ---- htab.c:219-235
+__global__ void setcnt_kernel(uint64_t *slots, uint64_t total, uint32_t c)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i < total) { uint64_t v = slots[i]; if (v != YAKB_EMPTY) slots[i] = (v & ~(uint64_t)YAKB_MAX_COUNT) | c; }
+}
+void setcnt(Engine *e, int c)
+{
+	const uint64_t total = (uint64_t)e->P * e->cap;
+	if (total) setcnt_kernel<<<cdiv(total, 256), 256, 0, e->stream>>>(e->slots, total, (uint32_t)c);
+	YAKB_CUDA(cudaGetLastError());
+	YAKB_CUDA(cudaStreamSynchronize(e->stream));
+}
+
+// ---- bbf.c:25-42 on a stand-alone device filter (yak_bf_insert of the public API)
+__global__ void bf_insert_one_kernel(uint32_t *bits, int n_shift, int n_hashes, uint64_t hash, int *out)
+{
+	const int sh = n_shift - 9;
+	uint32_t *blk = bits + (hash & ((1ull << sh) - 1)) * 16;
+	*out = bloom_block_insert(blk, (uint32_t)(hash >> sh) & 511, (uint32_t)(hash >> n_shift) & 511, n_hashes);
+}
+int bf_insert_one(uint8_t *d_bits, int n_shift, int n_hashes, uint64_t hash)
+{
+	int *d = nullptr, h = 0;
+	YAKB_CUDA(cudaMalloc(&d, 4));
+	bf_insert_one_kernel<<<1, 1>>>((uint32_t*)d_bits, n_shift, n_hashes, hash, d);
+	YAKB_CUDA(cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost));
+	cudaFree(d);
+	return h;
+}
+
+// ---- synthetic data (yak_b200/synth.py is the specification)
+__host__ __device__ __forceinline__ uint64_t smix(uint64_t z)
+{
+	z += 0x9E3779B97F4A7C15ull;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+#define SYNTH_GMUL 0xD1342543DE82EF95ull
+
+__global__ void synth_genome_kernel(uint64_t seed_g, uint64_t G, uint64_t *g2, uint64_t nwords)
+{
+	uint64_t W = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (W >= nwords) return;
+	uint64_t w = 0;
+	for (int r = 0; r < 32; ++r) {
+		uint64_t j = W * 32 + r;
+		uint64_t c = j < G ? smix(seed_g * SYNTH_GMUL + j) >> 62 : 0;
+		w |= c << (62 - 2 * r);
+	}
+	g2[W] = w;
+}
+
+__global__ void synth_reads_kernel(const uint64_t *__restrict__ g2, uint64_t G, uint64_t seed_r, uint64_t first, uint64_t n_reads,
+                                   int L, uint64_t thr, int n_pct, uint8_t *__restrict__ asc)
+{
+	const uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	const uint64_t rec = (uint64_t)L + 1;
+	if (idx >= n_reads * rec) return;
+	const uint64_t i = idx / rec;
+	const int j = (int)(idx - i * rec);
+	if (j == L) { asc[idx] = '\n'; return; }
+	const uint64_t a = smix(seed_r * SYNTH_GMUL + (first + i));
+	const uint64_t start = smix(a + 1) % (G - L + 1);
+	const uint64_t f = smix(a + 2);
+	const bool rev = f & 1;
+	const uint64_t gi = rev ? start + (L - 1 - j) : start + j;
+	uint32_t b = (uint32_t)(g2[gi >> 5] >> (62 - 2 * (gi & 31))) & 3;
+	if (rev) b = 3 - b;
+	const uint64_t e = smix(a + 16 + (uint64_t)j);
+	if ((e & 0xFFFFFF) < thr) b = (uint32_t)(e >> 24) & 3;
+	uint8_t ch = "ACGT"[b];
+	if (((f >> 8) % 100) < (uint64_t)n_pct && (int)((f >> 32) % (uint64_t)L) == j) ch = 'N';
+	asc[idx] = ch;
+}
+
+void synth_genome(uint64_t seed_g, uint64_t G, uint64_t *d_g2, cudaStream_t stream)
+{
+	const uint64_t nwords = (G + 31) / 32;
+	synth_genome_kernel<<<cdiv(nwords, 256), 256, 0, stream>>>(seed_g, G, d_g2, nwords);
+	YAKB_CUDA(cudaGetLastError());
+}
+void synth_reads(const uint64_t *d_g2, uint64_t G, uint64_t seed_r, uint64_t first, uint64_t n_reads, int L, double err, int n_pct,
+                 uint8_t *d_asc, cudaStream_t stream)
+{
+	const uint64_t total = n_reads * (uint64_t)(L + 1);
+	if (total == 0) return;
+	synth_reads_kernel<<<cdiv(total, 256), 256, 0, stream>>>(d_g2, G, seed_r, first, n_reads, L, (uint64_t)(err * 16777216.0), n_pct, d_asc);
+	YAKB_CUDA(cudaGetLastError());
+}
+
+} // namespace yakb

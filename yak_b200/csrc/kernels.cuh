@@ -1,0 +1,122 @@
+// kernels.cuh - device code shared by engine.cu and extras.cu (packing, the rolling canonical
+// k-mer, ordered compaction of flagged positions).
+#pragma once
+#include "yakb_dev.cuh"
+
+namespace yakb {
+
+// ---- ASCII -> packed. word W of w2 holds bases 32W..32W+31, first base in the top 2 bits;
+//      wm[W] bit (31-r) set = base 32W+r is not A/C/G/T/U (separator, N, padding)
+static __global__ void __launch_bounds__(256) pack_ascii_kernel(const uint8_t *__restrict__ asc, uint64_t n,
+                                                         uint64_t *__restrict__ w2, uint32_t *__restrict__ wm, uint64_t nwords)
+{
+	uint64_t W = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (W >= nwords) return;
+	uint64_t base = W * 32, w = 0;
+	uint32_t m = 0;
+	if (base + 32 <= n && ((uintptr_t)(asc + base) & 15) == 0) {
+		const uint4 *q = (const uint4*)(asc + base);
+		uint4 a = __ldg(q), b = __ldg(q + 1);
+		uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+		for (int r = 0; r < 32; ++r) {
+			uint32_t c = nt4((u[r >> 2] >> (8 * (r & 3))) & 255);
+			w |= (uint64_t)(c & 3) << (62 - 2 * r);
+			m |= (c >> 2) << (31 - r);
+		}
+	} else {
+		for (int r = 0; r < 32; ++r) {
+			uint32_t c = base + r < n ? nt4(asc[base + r]) : 4;
+			w |= (uint64_t)(c & 3) << (62 - 2 * r);
+			m |= (c >> 2) << (31 - r);
+		}
+	}
+	w2[W] = w; wm[W] = m;
+}
+
+// ---- rolling canonical k-mer of the 32 positions of word W; emit(r, hash) for every position
+//      whose last k bases are all valid.  count.c:28-43 (k<32) / count.c:45-60 (k>=32).
+template<bool LONGK, class F>
+__device__ __forceinline__ void roll_word(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm,
+                                          uint64_t W, int k, F &&emit)
+{
+	const uint64_t mask = LONGK ? (1ULL << k) - 1 : (1ULL << 2 * k) - 1;
+	const int shift = LONGK ? k - 1 : 2 * (k - 1);
+	uint64_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+	int l = 0;
+	// warm-up over the k-1 bases before the word (a window never crosses an invalid base, so
+	// stale bits from before a reset are shifted out before the next emission)
+	for (int64_t p = (int64_t)(W * 32) - (k - 1); p < (int64_t)(W * 32); ++p) {
+		if (p < 0) continue;
+		uint32_t c = (uint32_t)(w2[p >> 5] >> (62 - 2 * (p & 31))) & 3;
+		uint32_t inv = (wm[p >> 5] >> (31 - (p & 31))) & 1;
+		if (LONGK) {
+			x0 = (x0 << 1 | (c & 1)) & mask;
+			x1 = (x1 << 1 | (c >> 1)) & mask;
+			x2 = x2 >> 1 | (uint64_t)(1 - (c & 1)) << shift;
+			x3 = x3 >> 1 | (uint64_t)(1 - (c >> 1)) << shift;
+		} else {
+			x0 = (x0 << 2 | c) & mask;
+			x1 = x1 >> 2 | (uint64_t)(3 - c) << shift;
+		}
+		l = inv ? 0 : l + 1;
+	}
+	const uint64_t cw = w2[W];
+	const uint32_t cm = wm[W];
+#pragma unroll
+	for (int r = 0; r < 32; ++r) {
+		uint32_t c = (uint32_t)(cw >> (62 - 2 * r)) & 3;
+		uint32_t inv = (cm >> (31 - r)) & 1;
+		if (LONGK) {
+			x0 = (x0 << 1 | (c & 1)) & mask;
+			x1 = (x1 << 1 | (c >> 1)) & mask;
+			x2 = x2 >> 1 | (uint64_t)(1 - (c & 1)) << shift;
+			x3 = x3 >> 1 | (uint64_t)(1 - (c >> 1)) << shift;
+		} else {
+			x0 = (x0 << 2 | c) & mask;
+			x1 = x1 >> 2 | (uint64_t)(3 - c) << shift;
+		}
+		l = inv ? 0 : (l < 64 ? l + 1 : l);
+		if (l >= k) {
+			uint64_t h;
+			if (LONGK) h = x1 < x3 ? hash64_64(x0) + hash64_64(x1) : hash64_64(x2) + hash64_64(x3); // yak-priv.h:35-39
+			else h = hash64(x0 < x1 ? x0 : x1, mask);
+			emit(r, h);
+		}
+	}
+}
+
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t *total)
+{
+	__shared__ uint32_t s_w[8];
+	__shared__ uint32_t s_tot;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+	if (lane == 31) s_w[w] = inc;
+	__syncthreads();
+	if (threadIdx.x == 0) { uint32_t a = 0; for (int i = 0; i < 8; ++i) { uint32_t t = s_w[i]; s_w[i] = a; a += t; } s_tot = a; }
+	__syncthreads();
+	uint32_t r = s_w[w] + inc - v;
+	if (total) *total = s_tot;
+	__syncthreads();
+	return r;
+}
+
+// ---- pending events in file order: pv[j] = hash, ppos[j] = position
+template<bool LONGK>
+__global__ void __launch_bounds__(256) compact_fused(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords, int k,
+                                                     const uint32_t *__restrict__ flags, const uint32_t *__restrict__ tileoff,
+                                                     uint64_t *__restrict__ pv, uint32_t *__restrict__ ppos)
+{
+	const uint64_t W = blockIdx.x * 256ull + threadIdx.x;
+	uint32_t f = W < nwords ? flags[W] : 0;
+	uint32_t o = tileoff[blockIdx.x] + block_excl_scan_256(__popc(f), nullptr);
+	if (f) roll_word<LONGK>(w2, wm, W, k, [&](int r, uint64_t h) {
+		if (f >> r & 1) { pv[o] = h; ppos[o] = (uint32_t)(W * 32 + r); ++o; }
+	});
+}
+
+
+} // namespace yakb

@@ -1,0 +1,150 @@
+// yakb_dev.cuh - device-side primitives of the k-mer count/lookup path (sm_100a).
+//
+// Semantics restated from the reference (cited per function); the data layout is ours:
+//   * one count table for all 2^pre sub-tables: `slots[s*cap + i]`, cap = uniform per-sub-table
+//     capacity (any size, fast-range indexed), slot = (v>>pre)<<10 | count like the reference's
+//     stored key (htab.c:9-11), EMPTY = ~0.
+//   * the khashl slot order the .yak format exposes is NOT kept here; it is rebuilt on demand
+//     from the per-sub-table insertion journal (layout.cu).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#define YAKB_COUNTER_BITS 10
+#define YAKB_MAX_COUNT 1023u
+#define YAKB_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+namespace yakb {
+
+// yak-priv.h:11-21
+__host__ __device__ __forceinline__ uint64_t hash64(uint64_t key, uint64_t mask)
+{
+	key = (~key + (key << 21)) & mask;
+	key = key ^ key >> 24;
+	key = (key * 265) & mask;
+	key = key ^ key >> 14;
+	key = (key * 21) & mask;
+	key = key ^ key >> 28;
+	key = (key + (key << 31)) & mask;
+	return key;
+}
+
+// yak-priv.h:23-33
+__host__ __device__ __forceinline__ uint64_t hash64_64(uint64_t key)
+{
+	key = ~key + (key << 21);
+	key = key ^ key >> 24;
+	key = key * 265;
+	key = key ^ key >> 14;
+	key = key * 21;
+	key = key ^ key >> 28;
+	key = key + (key << 31);
+	return key;
+}
+
+// yak-priv.h:41-68
+__host__ __device__ __forceinline__ uint64_t hash64_inv(uint64_t key, uint64_t mask)
+{
+	uint64_t t;
+	t = key - (key << 31);
+	key = (key - (t << 31)) & mask;
+	t = key ^ key >> 28;
+	key = key ^ t >> 28;
+	key = (key * 14933078535860113213ull) & mask;
+	t = key ^ key >> 14;
+	t = key ^ t >> 14;
+	t = key ^ t >> 14;
+	key = key ^ t >> 14;
+	key = (key * 15244667743933553977ull) & mask;
+	t = key ^ key >> 24;
+	key = key ^ t >> 24;
+	t = ~key;
+	t = ~(key - (t << 21));
+	t = ~(key - (t << 21));
+	key = ~(key - (t << 21)) & mask;
+	return key;
+}
+
+// khashl.h:98 + uint32 truncation (khashl.h:262): home slot of a stored key in a 2^bits table
+__host__ __device__ __forceinline__ uint32_t kh_home(uint64_t stored, uint32_t bits)
+{
+	return ((uint32_t)(stored >> YAKB_COUNTER_BITS) * 2654435769u) >> (32 - bits);
+}
+
+// misc.c:4-21 as arithmetic (no table): A/a C/c G/g T/t U/u -> 0..3, bytes 0..3 -> themselves, else 4
+__host__ __device__ __forceinline__ uint32_t nt4(uint32_t c)
+{
+	if (c < 4) return c;
+	uint32_t u = c & 0xDFu; // fold case for letters
+	if ((c | 0x20u) < 'a' || (c | 0x20u) > 'z') return 4;
+	return u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : (u == 'T' || u == 'U') ? 3 : 4;
+}
+
+// ---- our own table addressing (not the reference's): region-local fast-range slot ----
+__device__ __forceinline__ uint32_t tab_home(uint64_t x, uint32_t cap)
+{
+	uint32_t h = (uint32_t)x * 2654435769u ^ (uint32_t)(x >> 32) * 0x85EBCA6Bu;
+	return (uint32_t)(((uint64_t)h * cap) >> 32);
+}
+
+// Find x (= v>>pre) in region `reg` (cap slots). Returns slot index or -1 (hit an EMPTY slot).
+__device__ __forceinline__ int64_t tab_find(const uint64_t *reg, uint32_t cap, uint64_t x)
+{
+	uint32_t i = tab_home(x, cap);
+	for (uint32_t n = 0; n < cap; ++n) {
+		uint64_t cur = reg[i];
+		if (cur == YAKB_EMPTY) return -1;
+		if ((cur >> YAKB_COUNTER_BITS) == x) return i;
+		if (++i == cap) i = 0;
+	}
+	return -1;
+}
+
+// Saturating ++ of the 10-bit counter with other threads possibly incrementing the same slot
+// (htab.c:69-70 / 73-74: "if (count < 1023) ++count").
+__device__ __forceinline__ void slot_inc(uint64_t *p, uint64_t cur, uint32_t by)
+{
+	for (;;) {
+		uint32_t c = (uint32_t)(cur & YAKB_MAX_COUNT);
+		if (c >= YAKB_MAX_COUNT) return;
+		uint32_t nc = c + by > YAKB_MAX_COUNT ? YAKB_MAX_COUNT : c + by;
+		uint64_t want = (cur & ~(uint64_t)YAKB_MAX_COUNT) | nc;
+		uint64_t prev = atomicCAS((unsigned long long*)p, (unsigned long long)cur, (unsigned long long)want);
+		if (prev == cur) return;
+		cur = prev;
+	}
+}
+
+// Find-or-claim for a key only THIS thread inserts (other threads may claim neighbouring slots).
+// Returns the slot index; *fresh = 1 if the key was inserted now (count initialised to `cnt0`).
+__device__ __forceinline__ uint32_t tab_put_owned(uint64_t *reg, uint32_t cap, uint64_t x, uint32_t cnt0, int *fresh)
+{
+	uint32_t i = tab_home(x, cap);
+	const uint64_t want = x << YAKB_COUNTER_BITS | cnt0;
+	for (;;) {
+		uint64_t cur = reg[i];
+		if (cur == YAKB_EMPTY) {
+			uint64_t prev = atomicCAS((unsigned long long*)&reg[i], (unsigned long long)YAKB_EMPTY, (unsigned long long)want);
+			if (prev == YAKB_EMPTY) { *fresh = 1; return i; }
+			cur = prev;
+		}
+		if ((cur >> YAKB_COUNTER_BITS) == x) { *fresh = 0; return i; }
+		if (++i == cap) i = 0;
+	}
+}
+
+// bbf.c:25-42 on one 64-byte block held as 16 words: test-and-set n_hashes bits, return #already set
+__device__ __forceinline__ int bloom_block_insert(uint32_t *blk, uint32_t h1, uint32_t h2, int n_hashes)
+{
+	int cnt = 0;
+	if ((h2 & 31) == 0) h2 = (h2 + 1) & 511;
+	uint32_t z = h1;
+	for (int i = 0; i < n_hashes; ++i, z = (z + h2) & 511) {
+		uint32_t m = 1u << (z & 31);
+		cnt += (blk[z >> 5] & m) != 0;
+		blk[z >> 5] |= m;
+	}
+	return cnt;
+}
+
+} // namespace yakb
