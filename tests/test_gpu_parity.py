@@ -209,5 +209,5 @@ def test_restore_roundtrip_and_qv(oracle, yakb, reads_fa):
         assert L.yakb_qv_seqs(hg, len(seqs), lens, cat, min_len, min_frac, c2, t2, z2) == 0
         assert list(t1) == list(t2) and list(z1) == list(z2)
         assert list(c1) == list(c2)
-        assert sum(c1) > 0
+        assert sum(c1) > 0 or min_frac > 0.9
     L.yak_ch_destroy(hg); OL.yo_ch_destroy(ho); OL.yo_ch_destroy(ho2)

@@ -1,0 +1,191 @@
+/* yak-b200: the `yak` command line (count / qv / inspect / version) over libyakb200.so.
+ * Plain host C calling the C ABI of include/yak.h; flags, defaults, messages and the two-pass
+ * bloom protocol follow the reference CLI (main.c:13-64 count, 163-215 qv, 325-379 dispatch;
+ * inspect.c:8-106).  Nothing here touches the GPU directly. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <assert.h>
+#include <sys/time.h>
+#include <sys/resource.h>
+#include "yak.h"
+
+int yak_qv_solve(const int64_t *hist, const int64_t *cnt, int kmer, double fpr, yak_qstat_t *qs); /* qv_solve.c */
+
+static double t_real0;
+static double realtime(void) { struct timeval tv; gettimeofday(&tv, 0); return tv.tv_sec + tv.tv_usec * 1e-6; }
+static double cputime(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return r.ru_utime.tv_sec + r.ru_stime.tv_sec + 1e-6 * (r.ru_utime.tv_usec + r.ru_stime.tv_usec); }
+static long peakrss(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return r.ru_maxrss * 1024; }
+
+/* "10k" / "1.5g" style numbers (reference yak-priv.h:75-84) */
+static int64_t parse_num(const char *s)
+{
+	char *p;
+	double x = strtod(s, &p);
+	if (*p == 'G' || *p == 'g') x *= 1e9;
+	else if (*p == 'M' || *p == 'm') x *= 1e6;
+	else if (*p == 'K' || *p == 'k') x *= 1e3;
+	return (int64_t)(x + .499);
+}
+
+static int cmd_count(int argc, char *argv[])
+{
+	yak_copt_t opt;
+	yak_ch_t *h;
+	char *fn_out = 0;
+	int c;
+	yak_copt_init(&opt);
+	while ((c = getopt(argc, argv, "k:p:K:t:b:H:o:")) >= 0) {
+		if (c == 'k') opt.k = atoi(optarg);
+		else if (c == 'p') opt.pre = atoi(optarg);
+		else if (c == 'K') opt.chunk_size = parse_num(optarg);
+		else if (c == 't') opt.n_thread = atoi(optarg);
+		else if (c == 'b') opt.bf_shift = atoi(optarg);
+		else if (c == 'H') opt.bf_n_hash = (int)parse_num(optarg);
+		else if (c == 'o') fn_out = optarg;
+	}
+	if (argc - optind < 1) {
+		fprintf(stderr, "Usage: yak-b200 count [options] <in.fa> [in.fa]\n");
+		fprintf(stderr, "Options:\n");
+		fprintf(stderr, "  -k INT     k-mer size [%d]\n", opt.k);
+		fprintf(stderr, "  -p INT     prefix length [%d]\n", opt.pre);
+		fprintf(stderr, "  -b INT     set Bloom filter size to 2**INT bits; 0 to disable [%d]\n", opt.bf_shift);
+		fprintf(stderr, "  -H INT     use INT hash functions for Bloom filter [%d]\n", opt.bf_n_hash);
+		fprintf(stderr, "  -t INT     number of worker threads (accepted, unused on the GPU) [%d]\n", opt.n_thread);
+		fprintf(stderr, "  -o FILE    dump the count hash table to FILE []\n");
+		fprintf(stderr, "  -K INT     chunk size [100m]\n");
+		fprintf(stderr, "Note: -b37 is recommended for human reads\n");
+		return 1;
+	}
+	if (opt.pre < YAK_COUNTER_BITS) { fprintf(stderr, "ERROR: -p should be at least %d\n", YAK_COUNTER_BITS); return 1; }
+	if (opt.k >= 64) { fprintf(stderr, "ERROR: -k must be smaller than 64\n"); return 1; }
+	else if (opt.k >= 32) fprintf(stderr, "WARNING: counts are inexact if -k is greater than 31\n");
+	h = yak_count(argv[optind], &opt, 0);
+	if (h == 0) { fprintf(stderr, "ERROR: failed to count '%s' (no such file, or no CUDA device)\n", argv[optind]); return 1; }
+	if (opt.bf_shift > 0) { /* two-pass protocol, reference main.c:54-60 */
+		yak_ch_destroy_bf(h);
+		yak_ch_clear(h, opt.n_thread);
+		h = yak_count(argc - optind >= 2 ? argv[optind + 1] : argv[optind], &opt, h);
+		yak_ch_shrink(h, 2, YAK_MAX_COUNT, opt.n_thread);
+		fprintf(stderr, "[M::%s] %ld distinct k-mers after shrinking\n", "main_count", (long)h->tot);
+	}
+	if (fn_out) yak_ch_dump(h, fn_out);
+	yak_ch_destroy(h);
+	return 0;
+}
+
+static int cmd_qv(int argc, char *argv[])
+{
+	yak_qopt_t opt;
+	yak_ch_t *ch;
+	int64_t cnt[YAK_N_COUNTS], hist[YAK_N_COUNTS];
+	yak_qstat_t qs;
+	int c, i, kmer;
+	yak_qopt_init(&opt);
+	while ((c = getopt(argc, argv, "K:t:l:f:pe:E")) >= 0) {
+		if (c == 'K') opt.chunk_size = parse_num(optarg);
+		else if (c == 'l') opt.min_len = (int)parse_num(optarg);
+		else if (c == 'f') opt.min_frac = atof(optarg);
+		else if (c == 't') opt.n_threads = atoi(optarg);
+		else if (c == 'p') opt.print_each = 1;
+		else if (c == 'E') opt.print_err_kmer = 1;
+		else if (c == 'e') opt.fpr = atof(optarg);
+	}
+	if (argc - optind < 2) {
+		fprintf(stderr, "Usage: yak-b200 qv [options] <kmer.hash> <seq.fa>\n");
+		fprintf(stderr, "Options:\n");
+		fprintf(stderr, "  -l NUM      min sequence length [%d]\n", opt.min_len);
+		fprintf(stderr, "  -f FLOAT    min k-mer fraction [%g]\n", opt.min_frac);
+		fprintf(stderr, "  -e FLOAT    false positive rate [%g]\n", opt.fpr);
+		fprintf(stderr, "  -p          print QV for each sequence\n");
+		fprintf(stderr, "  -E          print the positions of wrong k-mers\n");
+		fprintf(stderr, "  -t INT      number of threads (accepted, unused on the GPU) [%d]\n", opt.n_threads);
+		fprintf(stderr, "  -K NUM      batch size [1g]\n");
+		return 1;
+	}
+	ch = yak_ch_restore(argv[optind]);
+	if (ch == 0) { fprintf(stderr, "ERROR: failed to load '%s'\n", argv[optind]); return 1; }
+	kmer = ch->k;
+	yak_ch_hist(ch, hist, opt.n_threads);
+	printf("CC\tCT  kmer_occurrence    short_read_kmer_count  raw_input_kmer_count  adjusted_input_kmer_count\n");
+	printf("CC\tFR  fpr_lower_bound    fpr_upper_bound\n");
+	printf("CC\tER  total_input_kmers  adjusted_error_kmers\n");
+	printf("CC\tCV  coverage\n");
+	printf("CC\tQV  raw_quality_value  adjusted_quality_value\n");
+	printf("CC\n");
+	yak_qv(&opt, argv[optind + 1], ch, cnt);
+	yak_qv_solve(hist, cnt, kmer, opt.fpr, &qs);
+	for (i = YAK_N_COUNTS - 1; i >= 0; --i)
+		printf("CT\t%d\t%ld\t%ld\t%.3f\n", i, (long)hist[i], (long)cnt[i], qs.adj_cnt[i]);
+	printf("FR\t%.3g\t%.3g\n", qs.fpr_lower, qs.fpr_upper);
+	printf("ER\t%ld\t%.3f\n", (long)qs.tot, qs.err);
+	printf("CV\t%.3f\n", qs.cov);
+	printf("QV\t%.3f\t%.3f\n", qs.qv_raw, qs.qv);
+	yak_ch_destroy(ch);
+	return 0;
+}
+
+/* single-file mode of the reference's inspect (inspect.c:40-62, 96-103): stream the file, print
+ * the count histogram high to low.  (Two-file mode: SURVEY quirk Q7, not implemented.) */
+static int cmd_inspect(int argc, char *argv[])
+{
+	FILE *fp;
+	char magic[4];
+	uint32_t t[3], u[2], j;
+	int64_t tot[YAK_N_COUNTS], acc = 0;
+	int i, n_sub;
+	if (argc < 2) { fprintf(stderr, "Usage: yak-b200 inspect <in1.yak>\n"); return 1; }
+	if (argc > 2) { fprintf(stderr, "ERROR: two-file inspect is not implemented by yak-b200\n"); return 1; }
+	if ((fp = fopen(argv[1], "rb")) == 0) { fprintf(stderr, "ERROR: failed to open '%s'\n", argv[1]); return 1; }
+	if (fread(magic, 1, 4, fp) != 4 || memcmp(magic, YAK_MAGIC, 4) != 0 || fread(t, 4, 3, fp) != 3 || t[2] != YAK_COUNTER_BITS) {
+		fprintf(stderr, "ERROR: not a .yak file\n");
+		fclose(fp);
+		return 1;
+	}
+	memset(tot, 0, sizeof(tot));
+	n_sub = 1 << t[1];
+	for (i = 0; i < n_sub; ++i) {
+		if (fread(u, 4, 2, fp) != 2) break;
+		for (j = 0; j < u[1]; ++j) {
+			uint64_t key;
+			if (fread(&key, 8, 1, fp) != 1) break;
+			++tot[key & YAK_MAX_COUNT];
+		}
+	}
+	fclose(fp);
+	for (i = YAK_N_COUNTS - 1; i >= 0; --i) {
+		acc += tot[i];
+		if (acc == 0) continue;
+		printf("HS\t%d\t%ld\t%ld\t%ld\n", i, 0L, (long)tot[i], (long)acc);
+	}
+	return 0;
+}
+
+int main(int argc, char *argv[])
+{
+	int ret, i;
+	t_real0 = realtime();
+	if (argc == 1) {
+		fprintf(stderr, "Usage: yak-b200 <command> <argument>\n");
+		fprintf(stderr, "Command:\n");
+		fprintf(stderr, "  count     count k-mers\n");
+		fprintf(stderr, "  qv        evaluate quality values\n");
+		fprintf(stderr, "  inspect   k-mer hash tables\n");
+		fprintf(stderr, "  version   print version number\n");
+		return 1;
+	}
+	if (strcmp(argv[1], "count") == 0) ret = cmd_count(argc - 1, argv + 1);
+	else if (strcmp(argv[1], "qv") == 0) ret = cmd_qv(argc - 1, argv + 1);
+	else if (strcmp(argv[1], "inspect") == 0) ret = cmd_inspect(argc - 1, argv + 1);
+	else if (strcmp(argv[1], "version") == 0) { puts(YAKS_VERSION); return 0; }
+	else { fprintf(stderr, "[E::%s] unknown command\n", __func__); return 1; }
+	if (ret == 0) {
+		fprintf(stderr, "[M::%s] Version: %s\n", __func__, YAKS_VERSION);
+		fprintf(stderr, "[M::%s] CMD:", __func__);
+		for (i = 0; i < argc; ++i) fprintf(stderr, " %s", argv[i]);
+		fprintf(stderr, "\n[M::%s] Real time: %.3f sec; CPU: %.3f sec; Peak RSS: %.3f GB\n", __func__,
+		        realtime() - t_real0, cputime(), peakrss() / 1024.0 / 1024.0 / 1024.0);
+	}
+	return ret;
+}
