@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py - k-mer events/s of the count hot path at BASELINE.json configs[1] geometry.
+
+Workload (config.workload = "cfg2"): k=31, -p12, -b37 -H4, 150 bp reads sampled from a 3 Gbp
+uniform genome (e=0.005, 1 % reads with an N), pass 1 of `yak count` (bloom + insert), the same
+synthetic stream as yak_b200/synth.py generated on the device.  A *step* is one batch of reads
+(--chunk-reads, default 2 M reads = 300 Mbp > L2) through the whole per-chunk path
+(pack -> fused extract+probe -> ordered bloom/insert of pending events -> journal).  Steps are
+consecutive batches from the start of the job; the table, bloom and journal persist across steps.
+
+  value     events/s with the batch's ASCII bases already resident in HBM (CUDA events on the
+            library's stream around exactly K steps, max over ranks)
+  e2e       the same metric through the reference-facing C call yak_count(file) on a FASTQ file in
+            host memory (tmpfs): parse + H2D + both passes + shrink + dump, D2H included
+  roofline  dominant kernel of the timed region (per-kernel CUDA events inside the library)
+  cpu_baseline  oracle/_ref/yak (the unmodified reference) `count` on the same sample file
+
+`--impl reference` times only the reference's CPU implementation (oracle/_ref/yak, else the port).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, PRE, BF, NH, L = 31, 12, 37, 4, 150
+SEED_G, SEED_R = 20260925, 7
+ERR, NPCT = 0.005, 1
+# SURVEY 8(d) algorithmic bytes per k-mer event
+ALG = {"extract": 0.31 + 8.0, "insert": 24.0, "bloom": 128.0, "pass1_bloom": 160.3, "plain": 32.3, "lookup": 8.31}
+
+
+def shm_dir():
+    for d in ("/dev/shm", tempfile.gettempdir()):
+        if os.path.isdir(d) and os.access(d, os.W_OK):
+            return d
+    return "."
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    def __init__(self, gpu: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback"
+
+
+def ref_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "yak")
+    return p if os.path.exists(p) else None
+
+
+def cpu_reference_run(fn: str, n_events: int, threads: int, bf: int):
+    """`yak count` of the unmodified reference on the host cores; returns (events/s, seconds, kind)."""
+    out = os.path.join(shm_dir(), f"yakb_ref_{os.getpid()}.yak")
+    ref = ref_binary()
+    t0 = time.time()
+    if ref:
+        cmd = [ref, "count", f"-k{K}", f"-p{PRE}", f"-t{threads}", f"-H{NH}", "-o", out]
+        if bf > 0:
+            cmd.append(f"-b{bf}")
+        subprocess.run(cmd + [fn], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        kind = "reference"
+    else:  # the oracle port (single thread)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        h, _ = oracle_lib.count_file(fn, k=K, pre=PRE, bf_shift=bf, bf_n_hash=NH)
+        oracle_lib.lib().yo_ch_dump(h, out.encode())
+        oracle_lib.lib().yo_ch_destroy(h)
+        kind, threads = "port", 1
+    dt = time.time() - t0
+    try:
+        os.unlink(out)
+    except OSError:
+        pass
+    return n_events / dt, dt, kind, threads
+
+
+def make_sample_file(torch, lib, genome2, G, n_reads: int, first: int, path: str):
+    """FASTQ sample of the workload written from the device generator; returns #k-mer events."""
+    rec = 2 * L + 7
+    buf = torch.empty(n_reads * rec, dtype=torch.uint8, device="cuda")
+    lib.yakb_synth_reads_dev(genome2.data_ptr(), G, SEED_R, first, n_reads, L, ERR, NPCT, 2, buf.data_ptr(),
+                             torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    host = buf.cpu().numpy()
+    host.tofile(path)
+    # events = windows of k valid bases: count from the sequence lines
+    import numpy as np
+    seq = host.reshape(n_reads, rec)[:, 3:3 + L]
+    valid = (seq != ord("N")).astype(np.int32)
+    c = np.cumsum(valid, axis=1)
+    win = c[:, K - 1:] - np.concatenate([np.zeros((n_reads, 1), np.int32), c[:, :L - K]], axis=1)
+    return int((win == K).sum())
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from yak_b200 import synth
+    threads = os.cpu_count() or 1
+    # bounded sample of the cfg2 stream: a window of the genome keeps host generation cheap while
+    # the read model (length, error, N rate, strand) and the -b/-p/-k flags stay those of cfg2
+    n_reads = args.ref_reads
+    Gs = min(args.genome, 50_000_000)
+    fn = os.path.join(shm_dir(), f"yakb_refarm_{os.getpid()}.fq")
+    genome = synth.genome_codes(SEED_G, Gs)
+    with open(fn, "wb") as f:
+        f.write(synth.reads_file_bytes(SEED_G, Gs, SEED_R, n_reads, L, ERR, NPCT, fastq=True, genome=genome))
+    codes = synth.read_codes(SEED_G, Gs, SEED_R, 0, n_reads, L, ERR, NPCT, genome)
+    n_ev = synth.count_events(codes, K)
+    bf = args.bf_shift
+    times = []
+    kind = "reference"
+    for i in range(args.warmup + args.steps):
+        v, dt, kind, threads = cpu_reference_run(fn, n_ev, threads, bf)
+        if i >= args.warmup:
+            times.append(dt)
+    os.unlink(fn)
+    ms = 1000.0 * sum(times) / len(times)
+    val = n_ev / (ms / 1000.0)
+    line = {"impl": "reference", "metric": "k-mer events/s (k=31 count, both passes of -b)", "value": val, "unit": "events/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "cfg2", "k": K, "pre": PRE, "bf_shift": bf, "read_len": L, "sample": f"{n_reads} reads of a {Gs} bp window"},
+            "cpu_baseline": {"value": val, "unit": "events/s", "cores": threads, "kind": kind,
+                             "sample": f"yak count -k{K} -p{PRE} -b{bf} -t{threads} on {n_reads} FASTQ reads ({n_ev} events)"},
+            "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genome", type=int, default=3_000_000_000)
+    ap.add_argument("--chunk-reads", type=int, default=2_000_000)
+    ap.add_argument("--bf-shift", type=int, default=BF)
+    ap.add_argument("--e2e-reads", type=int, default=2_000_000)
+    ap.add_argument("--ref-reads", type=int, default=2_000_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from yak_b200 import capi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    capi.require_gpu()
+    lib = capi.lib()
+    G = args.genome
+    W, KS = args.warmup, args.steps
+    nr = args.chunk_reads
+    rec = L + 1
+    genome2 = torch.empty((G + 31) // 32 + 1, dtype=torch.int64, device="cuda")
+    cur = torch.cuda.current_stream().cuda_stream
+    lib.yakb_synth_genome_dev(SEED_G, G, genome2.data_ptr(), cur)
+    # every rank takes its own contiguous slice of the read stream (weak scaling: per-GPU work fixed)
+    bufs = []
+    for i in range(W + KS):
+        b = torch.empty(nr * rec, dtype=torch.uint8, device="cuda")
+        first = (rank * (W + KS) + i) * nr
+        lib.yakb_synth_reads_dev(genome2.data_ptr(), G, SEED_R, first, nr, L, ERR, NPCT, 0, b.data_ptr(), cur)
+        bufs.append(b)
+    torch.cuda.synchronize()
+
+    h = lib.yak_ch_init(K, PRE, NH, args.bf_shift)
+    assert h, "yak_ch_init failed"
+    stream = torch.cuda.ExternalStream(lib.yakb_ch_stream(h))
+    stats = (C.c_uint64 * 4)()
+    ev_total = 0
+    per_step = []
+    for i in range(W):
+        lib.yakb_count_ascii_dev(h, bufs[i].data_ptr(), nr * rec, 1, stats)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = lib.yakb_kernel_launches()
+    lib.yakb_prof_enable(1)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for i in range(W, W + KS):
+        t_s = time.time()
+        rc = lib.yakb_count_ascii_dev(h, bufs[i].data_ptr(), nr * rec, 1, stats)
+        assert rc == 0
+        ev_total += stats[0]
+        per_step.append(list(stats) + [round((time.time() - t_s) * 1e3, 3)])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    launches = lib.yakb_kernel_launches() - launches0
+    pj = C.create_string_buffer(1 << 16)
+    lib.yakb_prof_json(pj, 1 << 16)
+    prof = json.loads(pj.value.decode())
+    lib.yakb_prof_enable(0)
+    if world > 1:
+        t = torch.tensor([ms, float(ev_total)], dtype=torch.float64, device="cuda")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, ev_all = float(tmax[0]), float(tsum[1])
+    else:
+        ev_all = float(ev_total)
+    value = ev_all / (ms / 1000.0)
+    dev_bytes = lib.yakb_ch_device_bytes(h)
+    lib.yak_ch_destroy(h)
+    del bufs
+    torch.cuda.empty_cache()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event times from inside the library)
+    peak, peak_kind = measured_peaks()
+    n_pending = sum(s[1] for s in per_step)
+    alg_bytes = {  # algorithmic bytes per launch set = SURVEY 8(d) per-event figure x events the kernel processed
+        "k1_fused": (0.31 + 8.0) * ev_total,            # read 2-bit bases, one 8-B slot probe per event
+        "group_insert": (8.0 + 128.0 + 16.0) * n_pending,  # sorted event + bloom block RMW + slot read/write
+        "group_sort(cub)": 2 * 12.0 * n_pending,
+        "compact": 8.0 * n_pending,
+        "pack_ascii": 1.375 * nr * rec * KS,
+    }
+    dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, [0, 0])
+    roof = None
+    if dom[0]:
+        nm, (tms, nl) = dom
+        ab = alg_bytes.get(nm, 0.0)
+        ach = ab / (tms / 1000.0) / 1e9 if tms > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": nm, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_kind, "launches": nl, "kernel_ms_total": tms,
+                "algorithmic_bytes_per_launch": ab / max(nl, 1),
+                "share_of_step": tms / ms if ms > 0 else None}
+    line = {"metric": "k-mer events/s (k=31, pass 1 of `yak count -b37`, chunk steps)", "value": value, "unit": "events/s",
+            "n_gpus": world, "steps": KS, "warmup": W, "ms_per_step": ms / KS, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "cfg2", "k": K, "pre": PRE, "bf_shift": args.bf_shift, "bf_n_hash": NH, "read_len": L,
+                       "genome_bp": G, "reads_per_step": nr, "bases_per_step": nr * L, "l2": "inputs larger than L2 (no flush)",
+                       "parallelism": f"dp{world} (independent read slices)" if world > 1 else "1 GPU",
+                       "device_bytes": int(dev_bytes)},
+            "input_gbp_per_s": (nr * L * KS * world) / (ms / 1000.0) / 1e9,
+            "gpu_launches": int(launches), "kernels_ms": {k: round(v[0], 3) for k, v in prof.items()},
+            "clocks": clk, "roofline": roof}
+
+    # ---- e2e through yak_count(file) + cpu baseline on the same sample file
+    if not args.no_e2e:
+        fn = os.path.join(shm_dir(), f"yakb_bench_{os.getpid()}.fq")
+        n_ev = make_sample_file(torch, lib, genome2, G, args.e2e_reads, 0, fn)
+        out = os.path.join(shm_dir(), f"yakb_bench_{os.getpid()}.yak")
+        fsz = os.path.getsize(fn)
+        t0 = time.time()
+        hh = capi.count_file(fn, k=K, pre=PRE, bf_shift=args.bf_shift, bf_n_hash=NH)
+        lib.yak_ch_dump(hh, out.encode())
+        dt = time.time() - t0
+        osz = os.path.getsize(out)
+        lib.yak_ch_destroy(hh)
+        line["e2e"] = {"value": n_ev / dt, "unit": "events/s", "h2d_bytes_per_step": 2 * args.e2e_reads * (L + 1),
+                       "d2h_bytes_per_step": osz, "seconds": dt,
+                       "what": f"yak_count x2 + shrink + dump of {args.e2e_reads} FASTQ reads ({fsz} B in tmpfs), {n_ev} events"}
+        if not args.no_cpu:
+            threads = os.cpu_count() or 1
+            v, dtc, kind, threads = cpu_reference_run(fn, n_ev, threads, args.bf_shift)
+            line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": threads, "kind": kind, "seconds": dtc,
+                                    "sample": f"yak count -k{K} -p{PRE} -b{args.bf_shift} -t{threads} on the e2e sample file ({n_ev} events)"}
+        for p in (fn, out):
+            try:
+                os.unlink(p)
+            except OSError:
+                pass
+    if args.verbose:
+        sys.stderr.write(json.dumps(per_step) + "\n")
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -57,11 +57,17 @@ uint64_t yakb_ch_device_bytes(const yak_ch_t *h);
 /* number of kernels this library launched so far in this process */
 uint64_t yakb_kernel_launches(void);
 
-/* seeded synthetic data on the device (same stream as yak_b200/synth.py):
- * genome as 2-bit codes packed 32 per u64; reads as ASCII with '\n' after each read */
+/* per-kernel device time (CUDA events on the table's stream): enable, run chunks, read
+ * {"kernel": [total_ms, launches], ...} as JSON text; returns its length or -1 if buf is too small */
+void yakb_prof_enable(int on);
+int yakb_prof_json(char *buf, uint64_t cap);
+
+/* seeded synthetic data on the device (same stream as yak_b200/synth.py): genome as 2-bit codes
+ * packed 32 per u64; reads as text records of fixed size: fmt 0 "SEQ\n" (L+1 bytes),
+ * fmt 1 FASTA ">r\nSEQ\n" (L+4), fmt 2 FASTQ "@r\nSEQ\n+\nIII..\n" (2L+7) */
 int yakb_synth_genome_dev(uint64_t seed_g, uint64_t G, uint64_t *d_genome2, void *cuda_stream);
 int yakb_synth_reads_dev(const uint64_t *d_genome2, uint64_t G, uint64_t seed_r, uint64_t first, uint64_t n_reads,
-                         int L, double err, int n_pct, uint8_t *d_asc, void *cuda_stream);
+                         int L, double err, int n_pct, int fmt, uint8_t *d_asc, void *cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -89,8 +89,10 @@ def lib() -> C.CDLL:
         "yakb_ch_stream": (vp, [ChP]),
         "yakb_ch_device_bytes": (u64, [ChP]),
         "yakb_kernel_launches": (u64, []),
+        "yakb_prof_enable": (None, [C.c_int]),
+        "yakb_prof_json": (C.c_int, [C.c_char_p, u64]),
         "yakb_synth_genome_dev": (C.c_int, [u64, u64, vp, vp]),
-        "yakb_synth_reads_dev": (C.c_int, [vp, u64, u64, u64, u64, C.c_int, C.c_double, C.c_int, vp, vp]),
+        "yakb_synth_reads_dev": (C.c_int, [vp, u64, u64, u64, u64, C.c_int, C.c_double, C.c_int, C.c_int, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -92,7 +92,7 @@ static void attach_handles(ChBox *b)
 		if (b->eng->bloom) {
 			b->filters[i].n_shift = b->eng->n_shift - b->eng->pre;
 			b->filters[i].n_hashes = b->eng->n_hash;
-			b->filters[i].b = b->eng->bloom + ((size_t)i << (b->eng->n_shift - b->eng->pre - 3));
+			b->filters[i].b = b->eng->bloom + (size_t)i * 64; // first block of sub-filter i (blocks interleave by sub-table)
 			b->pub.h[i].b = &b->filters[i];
 		}
 	}
@@ -427,6 +427,14 @@ extern "C" uint64_t yakb_ch_device_bytes(const yak_ch_t *h) { return box_of(h)->
 extern "C" const char *yakb_version(void) { return YAKS_VERSION; }
 extern "C" int yakb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 extern "C" uint64_t yakb_kernel_launches(void) { return Engine::launches(); }
+extern "C" void yakb_prof_enable(int on) { Prof::enable(on != 0); if (on) Prof::reset(); }
+extern "C" int yakb_prof_json(char *buf, uint64_t cap)
+{
+	std::string j = Prof::json();
+	if (j.size() + 1 > cap) return -1;
+	memcpy(buf, j.c_str(), j.size() + 1);
+	return (int)j.size();
+}
 
 extern "C" int yakb_synth_genome_dev(uint64_t seed_g, uint64_t G, uint64_t *d_genome2, void *cuda_stream)
 {
@@ -436,10 +444,10 @@ extern "C" int yakb_synth_genome_dev(uint64_t seed_g, uint64_t G, uint64_t *d_ge
 	GUARD_END(-1)
 }
 extern "C" int yakb_synth_reads_dev(const uint64_t *d_genome2, uint64_t G, uint64_t seed_r, uint64_t first, uint64_t n_reads,
-                                    int L, double err, int n_pct, uint8_t *d_asc, void *cuda_stream)
+                                    int L, double err, int n_pct, int fmt, uint8_t *d_asc, void *cuda_stream)
 {
 	GUARD_BEGIN
-	synth_reads(d_genome2, G, seed_r, first, n_reads, L, err, n_pct, d_asc, (cudaStream_t)cuda_stream);
+	synth_reads(d_genome2, G, seed_r, first, n_reads, L, err, n_pct, fmt, d_asc, (cudaStream_t)cuda_stream);
 	return 0;
 	GUARD_END(-1)
 }

@@ -52,30 +52,87 @@ static std::atomic<uint64_t> g_launches{0};
 uint64_t Engine::launches() { return g_launches.load(); }
 void Engine::note_launch(int n) { g_launches += n; }
 
+// ---- per-kernel timing (off unless enabled)
+#include <map>
+static bool g_prof_on = false;
+struct ProfPair { const char *name; cudaEvent_t a, b; };
+static std::vector<ProfPair> g_prof_open, g_prof_done;
+static std::map<std::string, std::pair<double, uint64_t>> g_prof_acc;
+void Prof::enable(bool on) { g_prof_on = on; }
+bool Prof::on() { return g_prof_on; }
+void Prof::reset() { g_prof_acc.clear(); }
+void Prof::begin(const char *name, cudaStream_t s)
+{
+	ProfPair p; p.name = name;
+	cudaEventCreate(&p.a); cudaEventCreate(&p.b);
+	cudaEventRecord(p.a, s);
+	g_prof_open.push_back(p);
+}
+void Prof::end(cudaStream_t s)
+{
+	ProfPair p = g_prof_open.back(); g_prof_open.pop_back();
+	cudaEventRecord(p.b, s);
+	g_prof_done.push_back(p);
+}
+void Prof::resolve()
+{
+	for (auto &p : g_prof_done) {
+		float ms = 0;
+		if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+			auto &e = g_prof_acc[p.name]; e.first += ms; e.second += 1;
+		}
+		cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+	}
+	g_prof_done.clear();
+}
+std::string Prof::json()
+{
+	std::string o = "{";
+	char buf[256];
+	bool first = true;
+	for (auto &kv : g_prof_acc) {
+		snprintf(buf, sizeof(buf), "%s\"%s\": [%.6f, %llu]", first ? "" : ", ", kv.first.c_str(), kv.second.first, (unsigned long long)kv.second.second);
+		o += buf; first = false;
+	}
+	return o + "}";
+}
+
 // ============================================================ kernels
 
-// probe one event; returns 1 if the key is in the table (and bumps it by one), 0 if not
-__device__ __forceinline__ int probe_inc(uint64_t *slots, uint32_t cap, int pre, uint32_t Pmask, uint64_t v, int do_inc)
+// Probe one event per lane, all 32 lanes in lock step (explicit convergence: data-dependent
+// probe lengths otherwise leave the warp serialised).  `first` is the already loaded home bucket.
+// Returns 1 if the key is in the table (its counter bumped by one, saturating), 0 if absent.
+__device__ __forceinline__ int probe_inc_warp(uint64_t *reg, uint32_t nbk, uint64_t x, uint32_t bi, Bucket b, bool valid)
 {
-	if (cap == 0) return 0;
-	const uint32_t s = (uint32_t)v & Pmask;
-	const uint64_t x = v >> pre;
-	uint64_t *reg = slots + (uint64_t)s * cap;
-	uint32_t i = tab_home(x, cap);
-	for (uint32_t n = 0; n < cap; ++n) {
-		uint64_t cur = __ldcg((const unsigned long long*)&reg[i]);
-		if (cur == YAKB_EMPTY) return 0;
-		if ((cur >> YAKB_COUNTER_BITS) == x) { if (do_inc) slot_inc(&reg[i], cur, 1); return 1; }
-		if (++i == cap) i = 0;
+	bool done = !valid;
+	int found = 0;
+	while (__any_sync(0xffffffffu, !done)) {
+		if (!done) {
+			int f, m = bucket_match(b, x, &f);
+			if (m >= 0) {
+				const uint64_t c = bucket_get(b, m);
+				if ((c & YAKB_MAX_COUNT) == YAKB_MAX_COUNT) { found = 1; done = true; }
+				else {
+					uint64_t *p = reg + (uint64_t)bi * YAKB_BUCKET + m;
+					const uint64_t prev = atomicCAS((unsigned long long*)p, (unsigned long long)c, (unsigned long long)(c + 1));
+					if (prev == c) { found = 1; done = true; }
+					else b = load_bucket(reg + (uint64_t)bi * YAKB_BUCKET); // lost a race on this counter: look again
+				}
+			} else if (f >= 0) done = true;
+			else {
+				if (++bi == nbk) bi = 0;
+				b = load_bucket(reg + (uint64_t)bi * YAKB_BUCKET);
+			}
+		}
 	}
-	return 0;
+	return found;
 }
 
 // ---- K1, fused front end: extraction + table probe.  One thread per 32-position word, persistent
 //      CTAs over 256-word tiles.  flags[W] bit r = position 32W+r is a pending event.
 //      stats[0] += events, glob_lput[s] = max(pos+1) over found (= put) events of sub-table s.
 template<bool LONGK>
-__global__ void __launch_bounds__(256) k1_fused(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords,
+__global__ void __launch_bounds__(256, 3) k1_fused(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords,
                                                 int k, int pre, uint32_t Pmask, uint64_t *slots, uint32_t cap, int create_new,
                                                 uint32_t *__restrict__ flags, uint32_t *__restrict__ tilecnt,
                                                 uint32_t *glob_lput, int smem_lp, unsigned long long *stats)
@@ -93,26 +150,46 @@ __global__ void __launch_bounds__(256) k1_fused(const uint64_t *__restrict__ w2,
 		if (threadIdx.x == 0) s_cnt = 0;
 		__syncthreads();
 		const uint64_t W = tile * 256 + threadIdx.x;
-		if (W < nwords) {
-			uint64_t v[32];
-			uint32_t vm = 0, pend = 0;
-			roll_word<LONGK>(w2, wm, W, k, [&](int r, uint64_t h) { v[r] = h; vm |= 1u << r; });
-			my_ev += __popc(vm);
+		const bool live = W < nwords; // dead lanes walk along with no events so the warp stays whole
+		{
+			uint32_t pend = 0;
+			const uint32_t nbk = cap / YAKB_BUCKET;
+			Roller<LONGK> ro;
+			if (live) ro.init(w2, wm, W, k);
 #pragma unroll
-			for (int r = 0; r < 32; ++r) {
-				if (vm >> r & 1) {
-					int found = probe_inc(slots, cap, pre, Pmask, v[r], 1);
-					if (create_new) {
-						if (!found) pend |= 1u << r;
+			for (int b = 0; b < 32; b += 4) { // 4 positions at a time: 4 independent home-bucket loads in flight
+				uint64_t v[4];
+				Bucket bk[4];
+				uint32_t bi[4], vm = 0;
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					bi[j] = 0; v[j] = 0;
+					if (live && ro.step(b + j, v[j])) {
+						vm |= 1u << j;
+						if (cap) {
+							bi[j] = tab_home(v[j] >> pre, nbk);
+							bk[j] = load_bucket(slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET);
+						}
+					}
+				}
+				__syncwarp();
+				my_ev += __popc(vm);
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const bool valid = vm >> j & 1;
+					const uint32_t s = (uint32_t)v[j] & Pmask;
+					const int found = cap ? probe_inc_warp(slots + (uint64_t)s * cap, nbk, v[j] >> pre, bi[j], bk[j], valid) : 0;
+					if (create_new && valid) {
+						if (!found) pend |= 1u << (b + j);
 						else {
-							uint32_t t = (uint32_t)(W * 32 + r) + 1;
-							if (smem_lp) atomicMax(&s_lp[(uint32_t)v[r] & Pmask], t);
-							else atomicMax(&glob_lput[(uint32_t)v[r] & Pmask], t);
+							uint32_t t = (uint32_t)(W * 32 + b + j) + 1;
+							if (smem_lp) atomicMax(&s_lp[s], t);
+							else atomicMax(&glob_lput[s], t);
 						}
 					}
 				}
 			}
-			if (create_new) {
+			if (create_new && live) {
 				flags[W] = pend;
 				if (pend) atomicAdd(&s_cnt, __popc(pend));
 			}
@@ -149,14 +226,21 @@ __global__ void __launch_bounds__(256) k1_array(const uint64_t *__restrict__ ev,
 		__syncthreads();
 		for (int it = 0; it < 32; ++it) {
 			const uint64_t W = tile * 256 + warp * 32 + it;
-			if (W >= nwords) break;
+			if (W >= nwords) break; // warp-uniform
 			const uint64_t i = W * 32 + lane;
 			int valid = i < n, found = 0;
 			uint64_t v = valid ? ev[i] : 0;
 			if (valid && only_s >= 0 && ((uint32_t)v & Pmask) != (uint32_t)only_s) valid = 0;
+			if (valid) ++my_ev;
+			if (cap) {
+				const uint32_t nbk = cap / YAKB_BUCKET, s = (uint32_t)v & Pmask;
+				uint64_t *reg = slots + (uint64_t)s * cap;
+				uint32_t bi = 0;
+				Bucket bk;
+				if (valid) { bi = tab_home(v >> pre, nbk); bk = load_bucket(reg + (uint64_t)bi * YAKB_BUCKET); }
+				found = probe_inc_warp(reg, nbk, v >> pre, bi, bk, valid);
+			}
 			if (valid) {
-				++my_ev;
-				found = probe_inc(slots, cap, pre, Pmask, v, 1);
 				if (found && create_new) {
 					uint32_t t = (uint32_t)i + 1;
 					if (smem_lp) atomicMax(&s_lp[(uint32_t)v & Pmask], t);
@@ -198,10 +282,20 @@ __global__ void iota_kernel(uint32_t *a, uint64_t n)
 	if (i < n) a[i] = (uint32_t)i;
 }
 
-__global__ void pend_hist_kernel(const uint64_t *__restrict__ pv, uint64_t n, uint32_t Pmask, uint32_t *pend)
+// pending events per sub-table (upper bound of the new keys a chunk can add): shared-memory bins
+__global__ void __launch_bounds__(256) pend_hist_kernel(const uint64_t *__restrict__ pv, uint64_t n, uint32_t Pmask, uint32_t *pend, int smem_ok)
 {
-	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-	if (i < n) atomicAdd(&pend[(uint32_t)pv[i] & Pmask], 1u);
+	extern __shared__ uint32_t s_bins[];
+	const uint32_t P = Pmask + 1;
+	if (smem_ok) { for (uint32_t i = threadIdx.x; i < P; i += 256) s_bins[i] = 0; __syncthreads(); }
+	for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) {
+		const uint32_t s = (uint32_t)pv[i] & Pmask;
+		if (smem_ok) atomicAdd(&s_bins[s], 1u); else atomicAdd(&pend[s], 1u);
+	}
+	if (smem_ok) {
+		__syncthreads();
+		for (uint32_t i = threadIdx.x; i < P; i += 256) if (s_bins[i]) atomicAdd(&pend[i], s_bins[i]);
+	}
 }
 
 __global__ void max_need_kernel(const uint32_t *nkeys, const uint32_t *pend, uint32_t P, uint32_t *out)
@@ -228,6 +322,8 @@ __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__
 	const uint64_t gmask = G >= 64 ? ~0ull : (1ull << G) - 1;
 	const uint64_t gk = sv[i] & gmask;
 	if (i > 0 && (sv[i - 1] & gmask) == gk) return;
+	uint32_t blk[16];
+	int have_blk = 0, dirty = 0;
 	for (uint64_t e = i; e < n; ++e) {
 		const uint64_t v = sv[e];
 		if ((v & gmask) != gk) break;
@@ -235,36 +331,43 @@ __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__
 		const uint32_t s = (uint32_t)v & Pmask;
 		const uint64_t x = v >> pre;
 		int put = 1;
-		if (bloom32) { // bbf.c:25-42 on the 64-byte block this group owns
-			uint32_t *blk = bloom32 + (((uint64_t)s << nb) | (x & ((1ull << nb) - 1))) * 16;
+		if (bloom32) { // bbf.c:25-42 on the 64-byte block this group owns (held in registers)
+			if (!have_blk) {
+				const uint4 *q = (const uint4*)(bloom32 + gk * 16);
+				uint4 a0 = __ldcg(q), a1 = __ldcg(q + 1), a2 = __ldcg(q + 2), a3 = __ldcg(q + 3);
+				blk[0] = a0.x; blk[1] = a0.y; blk[2] = a0.z; blk[3] = a0.w; blk[4] = a1.x; blk[5] = a1.y; blk[6] = a1.z; blk[7] = a1.w;
+				blk[8] = a2.x; blk[9] = a2.y; blk[10] = a2.z; blk[11] = a2.w; blk[12] = a3.x; blk[13] = a3.y; blk[14] = a3.z; blk[15] = a3.w;
+				have_blk = 1;
+			}
 			uint32_t h1 = (uint32_t)(x >> nb) & 511, h2 = (uint32_t)(x >> sub_shift) & 511, z;
 			int c = 0;
 			if ((h2 & 31) == 0) h2 = (h2 + 1) & 511;
 			z = h1;
 			for (int t = 0; t < n_hash; ++t, z = (z + h2) & 511) {
-				uint32_t w = __ldcg(&blk[z >> 5]), m = 1u << (z & 31);
-				c += (w & m) != 0;
-				__stcg(&blk[z >> 5], w | m);
+				const uint32_t w = z >> 5, m = 1u << (z & 31);
+#pragma unroll
+				for (int i = 0; i < 16; ++i) { // compile-time register index, run-time predicate
+					const bool hit = w == (uint32_t)i;
+					c += hit && (blk[i] & m);
+					if (hit && !(blk[i] & m)) { blk[i] |= m; dirty = 1; }
+				}
 			}
 			put = c == n_hash;
 		}
 		uint8_t flag = 0;
 		if (put) { // htab.c:66-70
-			uint64_t *reg = slots + (uint64_t)s * cap;
-			uint32_t q = tab_home(x, cap);
-			const uint64_t fresh_val = x << YAKB_COUNTER_BITS | 1;
-			for (;;) {
-				uint64_t cur = __ldcg((const unsigned long long*)&reg[q]);
-				if (cur == YAKB_EMPTY) {
-					uint64_t prev = atomicCAS((unsigned long long*)&reg[q], (unsigned long long)YAKB_EMPTY, (unsigned long long)fresh_val);
-					if (prev == YAKB_EMPTY) { flag = 3; break; }
-					cur = prev;
-				}
-				if ((cur >> YAKB_COUNTER_BITS) == x) { slot_inc(&reg[q], cur, 1); flag = 1; break; }
-				if (++q == cap) q = 0;
-			}
+			uint64_t *slot, cur;
+			if (tab_insert(slots + (uint64_t)s * cap, cap, x << YAKB_COUNTER_BITS | 1, &slot, &cur)) flag = 3;
+			else { slot_inc(slot, cur, 1); flag = 1; }
 		}
 		pflag[j] = flag;
+	}
+	if (dirty) {
+		uint4 *q = (uint4*)(bloom32 + gk * 16);
+		__stcg(q, make_uint4(blk[0], blk[1], blk[2], blk[3]));
+		__stcg(q + 1, make_uint4(blk[4], blk[5], blk[6], blk[7]));
+		__stcg(q + 2, make_uint4(blk[8], blk[9], blk[10], blk[11]));
+		__stcg(q + 3, make_uint4(blk[12], blk[13], blk[14], blk[15]));
 	}
 }
 
@@ -332,13 +435,8 @@ __global__ void rehash_kernel(const uint64_t *__restrict__ old_slots, uint32_t o
 	if (i >= total) return;
 	uint64_t val = old_slots[i];
 	if (val == YAKB_EMPTY) return;
-	uint64_t *reg = new_slots + (i / old_cap) * new_cap;
-	uint32_t q = tab_home(val >> YAKB_COUNTER_BITS, new_cap);
-	for (;;) {
-		uint64_t prev = atomicCAS((unsigned long long*)&reg[q], (unsigned long long)YAKB_EMPTY, (unsigned long long)val);
-		if (prev == YAKB_EMPTY) return;
-		if (++q == new_cap) q = 0;
-	}
+	uint64_t *slot, cur;
+	tab_insert(new_slots + (i / old_cap) * new_cap, new_cap, val, &slot, &cur);
 }
 
 // stored keys (with counts) of sub-tables given by off[] into the table (restore / shrink rebuild)
@@ -349,19 +447,8 @@ __global__ void bulk_insert_kernel(const uint64_t *__restrict__ keys, const uint
 	if (i >= n) return;
 	uint32_t lo = 0, hi = P; // sub-table s with off[s] <= i < off[s+1]
 	while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
-	uint64_t val = keys[i], x = val >> YAKB_COUNTER_BITS;
-	uint64_t *reg = slots + (uint64_t)lo * cap;
-	uint32_t q = tab_home(x, cap);
-	for (;;) {
-		uint64_t cur = __ldcg((const unsigned long long*)&reg[q]);
-		if (cur == YAKB_EMPTY) {
-			uint64_t prev = atomicCAS((unsigned long long*)&reg[q], (unsigned long long)YAKB_EMPTY, (unsigned long long)val);
-			if (prev == YAKB_EMPTY) return;
-			cur = prev;
-		}
-		if ((cur >> YAKB_COUNTER_BITS) == x) return; // duplicate key in the file: first claim wins
-		if (++q == cap) q = 0;
-	}
+	uint64_t *slot, cur;
+	tab_insert(slots + (uint64_t)lo * cap, cap, keys[i], &slot, &cur); // a duplicate key in the file: first claim wins
 }
 
 __global__ void clear_kernel(uint64_t *slots, uint64_t total)
@@ -593,7 +680,7 @@ void Engine::grow(uint32_t new_cap)
 
 void Engine::reserve(uint64_t keys_per_subtable)
 {
-	uint64_t want = (uint64_t)(keys_per_subtable / load_limit) + 16;
+	uint64_t want = ((uint64_t)(keys_per_subtable / load_limit) + 16 + 3) & ~3ull;
 	if (want > 0xFFFFFFF0ull) throw CudaError("[yakb] sub-table capacity overflow");
 	if (want > cap) grow((uint32_t)want);
 }
@@ -613,7 +700,7 @@ ChunkStats Engine::count_ascii(const uint8_t *d_asc, uint64_t n, int create_new)
 	const uint64_t nwords = (n + 31) / 32;
 	uint64_t *w2 = b_w2.as<uint64_t>(nwords);
 	uint32_t *wm = b_wm.as<uint32_t>(nwords);
-	pack_ascii_kernel<<<cdiv(nwords, 256), 256, 0, stream>>>(d_asc, n, w2, wm, nwords);
+	{ ProfScope ps("pack_ascii", stream); pack_ascii_kernel<<<cdiv(nwords, 256), 256, 0, stream>>>(d_asc, n, w2, wm, nwords); }
 	YAKB_CUDA(cudaGetLastError());
 	note_launch(1);
 	return finish_chunk(nwords, create_new, w2, wm, nullptr, n, -1);
@@ -653,6 +740,7 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 	const int smem1 = create_new && smem_lp_ok(P, 1);
 	const size_t sm1 = smem1 ? (size_t)P * 4 : 0;
 	const uint32_t grid1 = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)nsm * 4);
+	{ ProfScope ps(d_ev ? "k1_array" : "k1_fused", stream);
 	if (d_ev == nullptr) {
 		if (longk) {
 			set_smem(k1_fused<true>, sm1);
@@ -665,12 +753,14 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 		set_smem(k1_array, sm1);
 		k1_array<<<grid1, 256, sm1, stream>>>(d_ev, n_ev_in, pre, Pmask, slots, cap, create_new, only_s, flags, tilecnt, lput, smem1, stats);
 	}
+	}
 	YAKB_CUDA(cudaGetLastError());
 	note_launch(1); // k1
 	unsigned long long h_stats[4] = {0, 0, 0, 0};
 	if (!create_new) {
 		YAKB_CUDA(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaStreamSynchronize(stream));
+		Prof::resolve();
 		st.n_events = h_stats[0];
 		++chunk_seq;
 		return st;
@@ -687,21 +777,27 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 	if (n_pending) {
 		uint64_t *pv = b_pv.as<uint64_t>(n_pending);
 		uint32_t *ppos = b_ppos.as<uint32_t>(n_pending);
+		{ ProfScope ps("compact", stream);
 		if (d_ev == nullptr) {
 			if (longk) compact_fused<true><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, flags, tileoff, pv, ppos);
 			else compact_fused<false><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, flags, tileoff, pv, ppos);
 		} else compact_array<<<(uint32_t)ntiles, 256, 0, stream>>>(d_ev, nwords, flags, tileoff, pv, ppos);
+		}
 		YAKB_CUDA(cudaGetLastError());
 		// make room: every pending event may be a new key of its sub-table
+		const int smem1h = smem_lp_ok(P, 1);
+		const size_t sm1h = smem1h ? (size_t)P * 4 : 0;
 		uint32_t *pend = b_pend.as<uint32_t>(P + 1);
 		YAKB_CUDA(cudaMemsetAsync(pend, 0, (P + 1) * 4, stream));
-		pend_hist_kernel<<<cdiv(n_pending, 256), 256, 0, stream>>>(pv, n_pending, Pmask, pend);
-		max_need_kernel<<<1, 1024, 0, stream>>>(nkeys, pend, P, pend + P);
+		{ ProfScope ps("pend_hist", stream);
+		set_smem(pend_hist_kernel, sm1h);
+		pend_hist_kernel<<<std::min<uint32_t>(cdiv(n_pending, 256), nsm * 4), 256, sm1h, stream>>>(pv, n_pending, Pmask, pend, smem1h);
+		max_need_kernel<<<1, 1024, 0, stream>>>(nkeys, pend, P, pend + P); }
 		uint32_t need = 0;
 		YAKB_CUDA(cudaMemcpyAsync(&need, pend + P, 4, cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaStreamSynchronize(stream));
 		if ((double)need > load_limit * cap) {
-			uint64_t want = std::max<uint64_t>((uint64_t)(need / load_limit) + 16, (uint64_t)cap + cap / 2);
+			uint64_t want = (std::max<uint64_t>((uint64_t)(need / load_limit) + 16, (uint64_t)cap + cap / 2) + 3) & ~3ull;
 			if (want > 0xFFFFFFF0ull) throw CudaError("[yakb] sub-table capacity overflow");
 			grow((uint32_t)want);
 		}
@@ -718,15 +814,19 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 		uint32_t *sj = b_sj.as<uint32_t>(n_pending);
 		tmp_bytes = 0;
 		cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, pv, sv, iota, sj, (int)n_pending, 0, G, stream);
-		cub::DeviceRadixSort::SortPairs(b_tmp.need(tmp_bytes), tmp_bytes, pv, sv, iota, sj, (int)n_pending, 0, G, stream);
+		void *tmp_sort = b_tmp.need(tmp_bytes);
+		{ ProfScope ps("group_sort(cub)", stream);
+		cub::DeviceRadixSort::SortPairs(tmp_sort, tmp_bytes, pv, sv, iota, sj, (int)n_pending, 0, G, stream); }
 		uint8_t *pflag = b_pflag.as<uint8_t>(2 * (size_t)n_pending); // [0,n): put/new bits, [n,2n): new-key flag
+		{ ProfScope ps("group_insert", stream);
 		group_insert<<<cdiv(n_pending, 256), 256, 0, stream>>>(sv, sj, n_pending, G, pre, Pmask, slots, cap,
-		                                                       (uint32_t*)bloom, nb, n_shift - pre, n_hash, pflag);
+		                                                       (uint32_t*)bloom, nb, n_shift - pre, n_hash, pflag); }
 		YAKB_CUDA(cudaGetLastError());
 		const int smem2 = smem_lp_ok(P, 2);
 		const size_t sm2 = smem2 ? (size_t)P * 8 : 0;
 		set_smem(post_pending, sm2);
-		post_pending<<<std::min<uint32_t>(cdiv(n_pending, 256), nsm * 4), 256, sm2, stream>>>(pv, ppos, pflag, n_pending, Pmask, lput, lnew, smem2, stats);
+		{ ProfScope ps("post_pending", stream);
+		post_pending<<<std::min<uint32_t>(cdiv(n_pending, 256), nsm * 4), 256, sm2, stream>>>(pv, ppos, pflag, n_pending, Pmask, lput, lnew, smem2, stats); }
 		YAKB_CUDA(cudaGetLastError());
 		note_launch(6); // compact, pend_hist, max_need, iota, group_insert, post_pending
 		// new keys in file order, then stably by sub-table -> journal segment
@@ -735,7 +835,9 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 		const uint8_t *isnew = pflag + n_pending; // written by post_pending
 		tmp_bytes = 0;
 		cub::DeviceSelect::Flagged(nullptr, tmp_bytes, pv, isnew, newv, d_nsel, (int)n_pending, stream);
-		cub::DeviceSelect::Flagged(b_tmp.need(tmp_bytes), tmp_bytes, pv, isnew, newv, d_nsel, (int)n_pending, stream);
+		void *tmp_sel = b_tmp.need(tmp_bytes);
+		{ ProfScope ps("journal(cub select)", stream);
+		cub::DeviceSelect::Flagged(tmp_sel, tmp_bytes, pv, isnew, newv, d_nsel, (int)n_pending, stream); }
 		YAKB_CUDA(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaStreamSynchronize(stream));
 		n_new = (uint32_t)h_stats[2];
@@ -743,7 +845,9 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 			uint64_t *sorted = b_newsorted.as<uint64_t>(n_new);
 			tmp_bytes = 0;
 			cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, newv, sorted, (int)n_new, 0, pre, stream);
-			cub::DeviceRadixSort::SortKeys(b_tmp.need(tmp_bytes), tmp_bytes, newv, sorted, (int)n_new, 0, pre, stream);
+			void *tmp_js = b_tmp.need(tmp_bytes);
+			ProfScope ps("journal(cub sort+seg)", stream);
+			cub::DeviceRadixSort::SortKeys(tmp_js, tmp_bytes, newv, sorted, (int)n_new, 0, pre, stream);
 			Segment seg;
 			seg.n = n_new;
 			YAKB_CUDA(cudaMalloc(&seg.keys, n_new * 8));
@@ -763,6 +867,7 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 	YAKB_CUDA(cudaGetLastError());
 	note_launch(1);
 	YAKB_CUDA(cudaStreamSynchronize(stream));
+	Prof::resolve();
 	st.n_events = h_stats[0];
 	st.n_put = h_stats[1] + (st.n_events - st.n_pending);
 	st.n_new = n_new;

@@ -3,7 +3,9 @@
 // One Engine backs one yak_ch_t.  HBM layout (all device memory unless noted):
 //   slots[P*cap]      u64   count table; region s = sub-table s; slot = (v>>pre)<<10 | count
 //   nkeys[P]          u32   distinct keys per sub-table
-//   bloom             u8    2^(n_shift-3) bytes; block b of sub-filter s at ((s<<nb)|b)*64
+//   bloom             u8    2^(n_shift-3) bytes; the 64-byte block of hash v sits at
+//                     (v & (2^(n_shift-9)-1))*64, i.e. blocks are ordered like the group sort, so a
+//                     chunk sweeps the filter front to back (block b of sub-filter s = (b<<pre|s)*64)
 //   journal           list of segments; segment = new keys of one chunk ordered by
 //                     (sub-table, first-put time) + P+1 offsets.  Concatenating a sub-table's
 //                     runs over segments gives the order in which the reference's khashl saw
@@ -30,6 +32,22 @@ struct DBuf {
 	void *need(size_t bytes);
 	template<class T> T *as(size_t n) { return (T*)need(n * sizeof(T)); }
 	void release();
+};
+
+// optional per-kernel timing with CUDA events on the engine's stream (bench.py roofline leg)
+struct Prof {
+	static void enable(bool on);
+	static bool on();
+	static void reset();
+	static void begin(const char *name, cudaStream_t s);
+	static void end(cudaStream_t s);
+	static void resolve();                       // call after the stream was synchronised
+	static std::string json();                   // {"name": [total_ms, launches], ...}
+};
+struct ProfScope {
+	cudaStream_t s; bool live;
+	ProfScope(const char *name, cudaStream_t st) : s(st), live(Prof::on()) { if (live) Prof::begin(name, s); }
+	~ProfScope() { if (live) Prof::end(s); }
 };
 
 struct Segment { uint64_t *keys; uint64_t *off; uint64_t n; };

@@ -219,15 +219,23 @@ __global__ void synth_genome_kernel(uint64_t seed_g, uint64_t G, uint64_t *g2, u
 	g2[W] = w;
 }
 
+// fmt 0: SEQ\n   fmt 1 (FASTA): >r\nSEQ\n   fmt 2 (FASTQ): @r\nSEQ\n+\nQUAL\n  (fixed record size)
+__host__ __device__ inline uint64_t synth_rec_bytes(int L, int fmt) { return fmt == 0 ? L + 1 : fmt == 1 ? L + 4 : 2 * (uint64_t)L + 7; }
+
 __global__ void synth_reads_kernel(const uint64_t *__restrict__ g2, uint64_t G, uint64_t seed_r, uint64_t first, uint64_t n_reads,
-                                   int L, uint64_t thr, int n_pct, uint8_t *__restrict__ asc)
+                                   int L, uint64_t thr, int n_pct, int fmt, uint8_t *__restrict__ asc)
 {
 	const uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-	const uint64_t rec = (uint64_t)L + 1;
+	const uint64_t rec = synth_rec_bytes(L, fmt);
 	if (idx >= n_reads * rec) return;
 	const uint64_t i = idx / rec;
-	const int j = (int)(idx - i * rec);
+	int j = (int)(idx - i * rec);
+	if (fmt) { // header "Xr\n"
+		if (j < 3) { asc[idx] = j == 0 ? (fmt == 1 ? '>' : '@') : j == 1 ? 'r' : '\n'; return; }
+		j -= 3;
+	}
 	if (j == L) { asc[idx] = '\n'; return; }
+	if (j > L) { j -= L + 1; asc[idx] = j == 0 ? '+' : (j == 1 || j == L + 2) ? '\n' : 'I'; return; }
 	const uint64_t a = smix(seed_r * SYNTH_GMUL + (first + i));
 	const uint64_t start = smix(a + 1) % (G - L + 1);
 	const uint64_t f = smix(a + 2);
@@ -249,11 +257,11 @@ void synth_genome(uint64_t seed_g, uint64_t G, uint64_t *d_g2, cudaStream_t stre
 	YAKB_CUDA(cudaGetLastError());
 }
 void synth_reads(const uint64_t *d_g2, uint64_t G, uint64_t seed_r, uint64_t first, uint64_t n_reads, int L, double err, int n_pct,
-                 uint8_t *d_asc, cudaStream_t stream)
+                 int fmt, uint8_t *d_asc, cudaStream_t stream)
 {
-	const uint64_t total = n_reads * (uint64_t)(L + 1);
+	const uint64_t total = n_reads * synth_rec_bytes(L, fmt);
 	if (total == 0) return;
-	synth_reads_kernel<<<cdiv(total, 256), 256, 0, stream>>>(d_g2, G, seed_r, first, n_reads, L, (uint64_t)(err * 16777216.0), n_pct, d_asc);
+	synth_reads_kernel<<<cdiv(total, 256), 256, 0, stream>>>(d_g2, G, seed_r, first, n_reads, L, (uint64_t)(err * 16777216.0), n_pct, fmt, d_asc);
 	YAKB_CUDA(cudaGetLastError());
 }
 

@@ -15,6 +15,6 @@ void setcnt(Engine *e, int c);
 int bf_insert_one(uint8_t *d_bits, int n_shift, int n_hashes, uint64_t hash);
 void synth_genome(uint64_t seed_g, uint64_t G, uint64_t *d_g2, cudaStream_t stream);
 void synth_reads(const uint64_t *d_g2, uint64_t G, uint64_t seed_r, uint64_t first, uint64_t n_reads, int L, double err, int n_pct,
-                 uint8_t *d_asc, cudaStream_t stream);
+                 int fmt, uint8_t *d_asc, cudaStream_t stream);
 
 } // namespace yakb

@@ -34,39 +34,54 @@ static __global__ void __launch_bounds__(256) pack_ascii_kernel(const uint8_t *_
 	w2[W] = w; wm[W] = m;
 }
 
-// ---- rolling canonical k-mer of the 32 positions of word W; emit(r, hash) for every position
-//      whose last k bases are all valid.  count.c:28-43 (k<32) / count.c:45-60 (k>=32).
-template<bool LONGK, class F>
-__device__ __forceinline__ void roll_word(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm,
-                                          uint64_t W, int k, F &&emit)
-{
-	const uint64_t mask = LONGK ? (1ULL << k) - 1 : (1ULL << 2 * k) - 1;
-	const int shift = LONGK ? k - 1 : 2 * (k - 1);
-	uint64_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
-	int l = 0;
-	// warm-up over the k-1 bases before the word (a window never crosses an invalid base, so
-	// stale bits from before a reset are shifted out before the next emission)
-	for (int64_t p = (int64_t)(W * 32) - (k - 1); p < (int64_t)(W * 32); ++p) {
-		if (p < 0) continue;
-		uint32_t c = (uint32_t)(w2[p >> 5] >> (62 - 2 * (p & 31))) & 3;
-		uint32_t inv = (wm[p >> 5] >> (31 - (p & 31))) & 1;
-		if (LONGK) {
-			x0 = (x0 << 1 | (c & 1)) & mask;
-			x1 = (x1 << 1 | (c >> 1)) & mask;
-			x2 = x2 >> 1 | (uint64_t)(1 - (c & 1)) << shift;
-			x3 = x3 >> 1 | (uint64_t)(1 - (c >> 1)) << shift;
+// ---- rolling canonical k-mer over the 32 positions of word W.  count.c:28-43 (k<32) /
+//      count.c:45-60 (k>=32).  init() builds the state after the k-1 bases before the word;
+//      step(r, h) consumes position r and returns true (with the hash) when a k-mer ends there.
+template<bool LONGK>
+struct Roller {
+	uint64_t x0, x1, x2, x3, mask, cw;
+	uint32_t cm;
+	int l, k, shift;
+
+	__device__ __forceinline__ void init(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t W, int k_)
+	{
+		k = k_;
+		mask = LONGK ? (1ULL << k) - 1 : (1ULL << 2 * k) - 1;
+		shift = LONGK ? k - 1 : 2 * (k - 1);
+		x0 = x1 = x2 = x3 = 0; l = 0;
+		if (!LONGK) {
+			// the last k-1 (<= 30) bases of the previous word are its low 2(k-1) bits.  A window never
+			// crosses an invalid base, so whatever sits under invalid positions is shifted out before
+			// the next emission.
+			if (W > 0) {
+				const int n = k - 1;
+				const uint64_t pw = w2[W - 1];
+				const uint32_t pm = n ? (wm[W - 1] & (uint32_t)((1ull << n) - 1)) : 0;
+				x0 = n ? pw & ((1ull << 2 * n) - 1) : 0;
+				// reverse complement of those n bases, newest at the top: reverse the 2-bit groups
+				uint64_t c = ~x0 & (n ? (1ull << 2 * n) - 1 : 0), r = __brevll(c);
+				r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+				x1 = n ? (r >> (64 - 2 * n)) << 2 : 0;
+				l = pm ? __ffs(pm) - 1 : n;
+			}
 		} else {
-			x0 = (x0 << 2 | c) & mask;
-			x1 = x1 >> 2 | (uint64_t)(3 - c) << shift;
+			for (int64_t p = (int64_t)(W * 32) - (k - 1); p < (int64_t)(W * 32); ++p) {
+				if (p < 0) continue;
+				uint32_t c = (uint32_t)(w2[p >> 5] >> (62 - 2 * (p & 31))) & 3;
+				uint32_t inv = (wm[p >> 5] >> (31 - (p & 31))) & 1;
+				x0 = (x0 << 1 | (c & 1)) & mask;
+				x1 = (x1 << 1 | (c >> 1)) & mask;
+				x2 = x2 >> 1 | (uint64_t)(1 - (c & 1)) << shift;
+				x3 = x3 >> 1 | (uint64_t)(1 - (c >> 1)) << shift;
+				l = inv ? 0 : l + 1;
+			}
 		}
-		l = inv ? 0 : l + 1;
+		cw = w2[W]; cm = wm[W];
 	}
-	const uint64_t cw = w2[W];
-	const uint32_t cm = wm[W];
-#pragma unroll
-	for (int r = 0; r < 32; ++r) {
-		uint32_t c = (uint32_t)(cw >> (62 - 2 * r)) & 3;
-		uint32_t inv = (cm >> (31 - r)) & 1;
+
+	__device__ __forceinline__ bool step(int r, uint64_t &h)
+	{
+		const uint32_t c = (uint32_t)(cw >> (62 - 2 * r)) & 3, inv = (cm >> (31 - r)) & 1;
 		if (LONGK) {
 			x0 = (x0 << 1 | (c & 1)) & mask;
 			x1 = (x1 << 1 | (c >> 1)) & mask;
@@ -77,13 +92,21 @@ __device__ __forceinline__ void roll_word(const uint64_t *__restrict__ w2, const
 			x1 = x1 >> 2 | (uint64_t)(3 - c) << shift;
 		}
 		l = inv ? 0 : (l < 64 ? l + 1 : l);
-		if (l >= k) {
-			uint64_t h;
-			if (LONGK) h = x1 < x3 ? hash64_64(x0) + hash64_64(x1) : hash64_64(x2) + hash64_64(x3); // yak-priv.h:35-39
-			else h = hash64(x0 < x1 ? x0 : x1, mask);
-			emit(r, h);
-		}
+		if (l < k) return false;
+		if (LONGK) h = x1 < x3 ? hash64_64(x0) + hash64_64(x1) : hash64_64(x2) + hash64_64(x3); // yak-priv.h:35-39
+		else h = hash64(x0 < x1 ? x0 : x1, mask);
+		return true;
 	}
+};
+
+template<bool LONGK, class F>
+__device__ __forceinline__ void roll_word(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm,
+                                          uint64_t W, int k, F &&emit)
+{
+	Roller<LONGK> ro;
+	ro.init(w2, wm, W, k);
+#pragma unroll
+	for (int r = 0; r < 32; ++r) { uint64_t h; if (ro.step(r, h)) emit(r, h); }
 }
 
 __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t *total)

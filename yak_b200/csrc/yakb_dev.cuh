@@ -80,22 +80,58 @@ __host__ __device__ __forceinline__ uint32_t nt4(uint32_t c)
 	return u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : (u == 'T' || u == 'U') ? 3 : 4;
 }
 
-// ---- our own table addressing (not the reference's): region-local fast-range slot ----
-__device__ __forceinline__ uint32_t tab_home(uint64_t x, uint32_t cap)
+// ---- our own table addressing (not the reference's) ----------------------------------------
+// A sub-table region is an array of 32-byte buckets of 4 slots (one DRAM sector).  A key lives in
+// the first bucket of its probe sequence (home bucket, then +1 ...) that had a free slot when it
+// was inserted; slots are never freed, so a lookup may stop at the first bucket that still has an
+// EMPTY slot.  Most lookups therefore cost exactly one sector.
+#define YAKB_BUCKET 4
+
+struct Bucket { uint64_t k[4]; };
+
+__device__ __forceinline__ uint32_t tab_home(uint64_t x, uint32_t nbk) // home bucket of x among nbk buckets
 {
 	uint32_t h = (uint32_t)x * 2654435769u ^ (uint32_t)(x >> 32) * 0x85EBCA6Bu;
-	return (uint32_t)(((uint64_t)h * cap) >> 32);
+	return (uint32_t)(((uint64_t)h * nbk) >> 32);
 }
 
-// Find x (= v>>pre) in region `reg` (cap slots). Returns slot index or -1 (hit an EMPTY slot).
+__device__ __forceinline__ Bucket load_bucket(const uint64_t *p)
+{
+	const ulonglong2 a = __ldcg((const ulonglong2*)p), b = __ldcg((const ulonglong2*)p + 1);
+	Bucket r; r.k[0] = a.x; r.k[1] = a.y; r.k[2] = b.x; r.k[3] = b.y;
+	return r;
+}
+
+// slot (0..3) of the bucket holding x, or -1; *free_slot = first EMPTY slot or -1
+__device__ __forceinline__ int bucket_match(const Bucket &b, uint64_t x, int *free_slot)
+{
+	int m = -1, f = -1;
+#pragma unroll
+	for (int i = 3; i >= 0; --i) {
+		if (b.k[i] == YAKB_EMPTY) f = i;
+		else if ((b.k[i] >> YAKB_COUNTER_BITS) == x) m = i;
+	}
+	*free_slot = f;
+	return m;
+}
+
+// b.k[m] without a run-time register index
+__device__ __forceinline__ uint64_t bucket_get(const Bucket &b, int m)
+{
+	return m == 0 ? b.k[0] : m == 1 ? b.k[1] : m == 2 ? b.k[2] : b.k[3];
+}
+
+// Find x (= v>>pre) in region `reg` (cap slots, cap % 4 == 0). Returns the slot index or -1.
 __device__ __forceinline__ int64_t tab_find(const uint64_t *reg, uint32_t cap, uint64_t x)
 {
-	uint32_t i = tab_home(x, cap);
-	for (uint32_t n = 0; n < cap; ++n) {
-		uint64_t cur = reg[i];
-		if (cur == YAKB_EMPTY) return -1;
-		if ((cur >> YAKB_COUNTER_BITS) == x) return i;
-		if (++i == cap) i = 0;
+	const uint32_t nbk = cap / YAKB_BUCKET;
+	uint32_t bi = tab_home(x, nbk);
+	for (uint32_t n = 0; n < nbk; ++n) {
+		const Bucket b = load_bucket(reg + (uint64_t)bi * YAKB_BUCKET);
+		int f, m = bucket_match(b, x, &f);
+		if (m >= 0) return (int64_t)bi * YAKB_BUCKET + m;
+		if (f >= 0) return -1;
+		if (++bi == nbk) bi = 0;
 	}
 	return -1;
 }
@@ -115,21 +151,24 @@ __device__ __forceinline__ void slot_inc(uint64_t *p, uint64_t cur, uint32_t by)
 	}
 }
 
-// Find-or-claim for a key only THIS thread inserts (other threads may claim neighbouring slots).
-// Returns the slot index; *fresh = 1 if the key was inserted now (count initialised to `cnt0`).
-__device__ __forceinline__ uint32_t tab_put_owned(uint64_t *reg, uint32_t cap, uint64_t x, uint32_t cnt0, int *fresh)
+// Insert-or-find `val` (stored form, key = val>>10).  Returns 1 if inserted, 0 if the key was
+// already there (*slot_out = its slot).  Safe against concurrent inserts of OTHER keys.
+__device__ __forceinline__ int tab_insert(uint64_t *reg, uint32_t cap, uint64_t val, uint64_t **slot_out, uint64_t *cur_out)
 {
-	uint32_t i = tab_home(x, cap);
-	const uint64_t want = x << YAKB_COUNTER_BITS | cnt0;
+	const uint64_t x = val >> YAKB_COUNTER_BITS;
+	const uint32_t nbk = cap / YAKB_BUCKET;
+	uint32_t bi = tab_home(x, nbk);
 	for (;;) {
-		uint64_t cur = reg[i];
-		if (cur == YAKB_EMPTY) {
-			uint64_t prev = atomicCAS((unsigned long long*)&reg[i], (unsigned long long)YAKB_EMPTY, (unsigned long long)want);
-			if (prev == YAKB_EMPTY) { *fresh = 1; return i; }
-			cur = prev;
+		uint64_t *bp = reg + (uint64_t)bi * YAKB_BUCKET;
+		const Bucket b = load_bucket(bp);
+		int f, m = bucket_match(b, x, &f);
+		if (m >= 0) { *slot_out = bp + m; *cur_out = bucket_get(b, m); return 0; }
+		if (f >= 0) {
+			uint64_t prev = atomicCAS((unsigned long long*)(bp + f), (unsigned long long)YAKB_EMPTY, (unsigned long long)val);
+			if (prev == YAKB_EMPTY) { *slot_out = bp + f; *cur_out = val; return 1; }
+			continue; // somebody took that slot: look at the same bucket again
 		}
-		if ((cur >> YAKB_COUNTER_BITS) == x) { *fresh = 0; return i; }
-		if (++i == cap) i = 0;
+		if (++bi == nbk) bi = 0;
 	}
 }
 
