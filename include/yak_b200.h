@@ -57,6 +57,13 @@ uint64_t yakb_ch_device_bytes(const yak_ch_t *h);
 /* number of kernels this library launched so far in this process */
 uint64_t yakb_kernel_launches(void);
 
+/* the host-side FASTA/FASTQ record reader yak_count/yak_qv use (reference kseq.h:192-232
+ * semantics; plain or gzip; NULL or "-" = stdin).  next() returns the sequence length, -1 at EOF,
+ * -2 on a truncated quality string; *seq / *name stay valid until the following call. */
+void *yakb_fastx_open(const char *fn);
+int64_t yakb_fastx_next(void *reader, const char **seq, const char **name);
+void yakb_fastx_close(void *reader);
+
 /* per-kernel device time (CUDA events on the table's stream): enable, run chunks, read
  * {"kernel": [total_ms, launches], ...} as JSON text; returns its length or -1 if buf is too small */
 void yakb_prof_enable(int on);

@@ -1,0 +1,260 @@
+"""CPU tests: the oracle against the reference's golden vectors; host logic; the C ABI surface."""
+import ctypes as C
+import hashlib
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util as G
+import oracle_lib as O
+import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------- oracle pinned to the reference
+
+def test_inputs_are_reproducible():
+    for name, meta in G.GOLD["inputs"].items():
+        data = open(G.input_path(name), "rb").read()
+        assert hashlib.sha256(data).hexdigest() == meta["sha256"], name
+
+
+def test_primitive_kats():
+    L = O.lib()
+    kat = G.GOLD["kat"]
+    for x, m, want in kat["hash64"]:
+        assert L.yo_hash64(x, m) == want
+        assert L.yo_hash64_inv(want, m) == x
+    for x, want in kat["hash64_64"]:
+        assert L.yo_hash64_64(x) == want
+    for q, want in kat["hash_long"]:
+        assert L.yo_hash_long((C.c_uint64 * 4)(*q)) == want
+    for h, bits, want in kat["h2b"]:
+        assert L.yo_slot_home(h << 10, bits) == want
+    # SURVEY section 4 table (captured from the reference in the survey session)
+    m62 = (1 << 62) - 1
+    assert [L.yo_hash64(x, m62) for x in (0, 1, 0x123456789abcdef, m62)] == \
+        [0x1df3e87bbc06f2a4, 0x1bca7c69b794f8ce, 0x2437e41bd0ec327b, 0x37ba6eccef93ff51]
+    assert L.yo_hash64(0x2a, (1 << 42) - 1) == 0x2f1e7b6f7a
+    assert [L.yo_hash64_64(x) for x in (0, 1)] == [0x77cfa1eef01bca90, 0x5bca7c69b794f8ce]
+    assert L.yo_hash_long((C.c_uint64 * 4)(5, 9, 3, 7)) == 0x95ea2abb2bd45540
+    assert [L.yo_slot_home(h << 10, b) for h, b in ((1, 2), (0xdeadbeef, 20), (12345, 10))] == [2, 598639, 644]
+    b = L.yo_bloom_init(25, 4)
+    assert (L.yo_bloom_insert(b, 0x1234567) , L.yo_bloom_insert(b, 0x1234567)) == (0, 4)
+    L.yo_bloom_destroy(b)
+    assert not L.yo_bloom_init(8, 4) and not L.yo_bloom_init(56, 4)          # bbf.c:9
+
+
+def test_khashl_quirks():
+    L = O.lib()
+    pre = 10
+    keys = np.array([(i * 7919 + 3) << pre | 5 for i in range(1, 4)], dtype=np.uint64)
+    import struct
+    for extra, want in ((False, (4, 3)), (True, (8, 3))):                    # Q3 trailing-put doubling
+        h = L.yo_ch_init(31, pre, 4, 0)
+        a, p = util.u64_array(np.concatenate([keys, keys[:1]]) if extra else keys)
+        L.yo_ch_insert_list(h, 1, len(a), p)
+        data = O.dump_bytes(h)
+        off = 16
+        for _ in range(5):
+            cap, size = struct.unpack_from("<II", data, off); off += 8 + 8 * size
+        assert struct.unpack_from("<II", data, off) == want
+        assert data[:16] == bytes.fromhex("59414b02" "1f000000" "0a000000" "0a000000")
+        L.yo_ch_shrink(h, 1, 1023)                                            # Q9
+        assert struct.unpack_from("<II", O.dump_bytes(h), 16) == (4, 0)
+        L.yo_ch_destroy(h)
+    assert not L.yo_ch_init(31, 9, 4, 0)
+
+
+@pytest.mark.parametrize("case", G.GOLD["cases"], ids=G.case_id)
+def test_oracle_matches_reference_golden(case):
+    if case["input"] == "cfg1" and case["bf_shift"] == 0 and os.environ.get("YAKB_FAST_TESTS"):
+        pytest.skip("fast mode")
+    fn = G.input_path(case["input"])
+    fn2 = G.input_path(case["second"]) if case["second"] else None
+    h, ne = O.count_file(fn, k=case["k"], pre=case["pre"], bf_shift=case["bf_shift"], fn2=fn2)
+    data = O.dump_bytes(h)
+    O.lib().yo_ch_destroy(h)
+    assert len(data) == case["bytes"]
+    assert hashlib.sha256(data).hexdigest() == case["sha256"]
+
+
+def test_oracle_restore_and_qv_against_reference_output():
+    """yo_ch_restore + yo_qv_seqs reproduce the SQ lines and CT histogram the reference printed."""
+    L = O.lib()
+    y = os.path.join(G.HERE, "reads_c_k31_p10_b22.yak")
+    h = L.yo_ch_restore(y.encode())
+    assert h
+    from yak_b200 import synth
+    ctg = synth.contigs_bytes(7, 100_000, 3, 8, 20_000, sub=2e-3)
+    seqs = [ln for ln in ctg.split(b"\n") if ln and not ln.startswith(b">")]
+    lens = (C.c_int64 * len(seqs))(*[len(s) for s in seqs])
+    cnt = (C.c_int64 * 1024)()
+    tot, non0 = (C.c_int32 * len(seqs))(), (C.c_int32 * len(seqs))()
+    L.yo_qv_seqs(h, len(seqs), lens, b"".join(seqs), 0, 0.5, cnt, tot, non0)
+    hist = (C.c_int64 * 1024)()
+    L.yo_ch_hist(h, hist)
+    ref = open(os.path.join(G.HERE, "qv_reads_c_ctg.txt")).read().splitlines()
+    sq = [ln.split("\t") for ln in ref if ln.startswith("SQ")]
+    assert [(int(x[3]), int(x[4])) for x in sq] == list(zip(tot, non0))
+    ct = {int(x[1]): (int(x[2]), int(x[3])) for x in (ln.split("\t") for ln in ref if ln.startswith("CT"))}
+    assert all(ct[i] == (hist[i], cnt[i]) for i in range(1024))
+    L.yo_ch_destroy(h)
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_YAK), reason="oracle/_ref not built (no /root/reference here)")
+def test_oracle_vs_live_reference_edge_cases():
+    import test_gpu_parity as T
+    fn = T._edge_file(os.path.join(util.TMP, "yakb_edge_cpu.fa"))
+    for k, pre, b in ((31, 10, 0), (31, 10, 19), (33, 10, 0), (5, 10, 0)):
+        y = os.path.join(util.TMP, "yakb_edge_ref.yak")
+        O.ref_count(fn, y, k=k, pre=pre, bf_shift=b)
+        h, _ = O.count_file(fn, k=k, pre=pre, bf_shift=b)
+        assert O.dump_bytes(h) == open(y, "rb").read()
+        O.lib().yo_ch_destroy(h)
+
+
+# ---------------------------------------------------------------- host logic of the product (no GPU)
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from yak_b200 import capi
+    L = capi.lib()
+    names = set()
+    for hdr in ("yak.h", "yak_b200.h"):
+        txt = open(os.path.join(ROOT, "include", hdr)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        names |= set(re.findall(r"\b(yakb?_[a-z0-9_]+)\s*\(", txt))
+    assert len(names) > 40
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+    for var in ("yak_verbose", "seq_nt4_table"):
+        assert C.c_int.in_dll(L, var) is not None
+    assert L.yakb_version().startswith(b"0.1")
+
+
+def test_nt4_table_and_option_defaults():
+    from yak_b200 import capi
+    L = capi.lib()
+    tab = (C.c_ubyte * 256).in_dll(L, "seq_nt4_table")
+    want = (C.c_ubyte * 256).in_dll(O.lib(), "yo_nt4")
+    assert bytes(tab) == bytes(want)
+    o = capi.YakCopt()
+    L.yak_copt_init(C.byref(o))
+    assert (o.k, o.pre, o.bf_shift, o.bf_n_hash, o.n_thread, o.chunk_size) == (31, 10, 0, 4, 4, 10_000_000)   # misc.c:23-32
+    q = capi.YakQopt()
+    L.yak_qopt_init(C.byref(q))
+    assert (q.chunk_size, q.n_threads, q.min_frac, q.fpr, q.min_len) == (1_000_000_000, 4, 0.5, 0.00004, 0)  # qv.c:137-144
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    from yak_b200 import capi
+    L = capi.lib()
+    if L.yakb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    assert not L.yak_ch_init(31, 12, 4, 0)
+    o = capi.copt(31, 12)
+    assert not L.yak_count(G.input_path("reads_a").encode(), C.byref(o), None)
+    with pytest.raises(RuntimeError):
+        capi.require_gpu()
+
+
+def _records_product(path):
+    from yak_b200 import capi
+    L = capi.lib()
+    r = L.yakb_fastx_open(path.encode())
+    assert r
+    out = []
+    seq, name = C.c_char_p(), C.c_char_p()
+    while True:
+        n = L.yakb_fastx_next(r, C.byref(seq), C.byref(name))
+        if n < 0:
+            out.append(n)
+            break
+        out.append((name.value, seq.value))
+        assert len(seq.value) == n
+    L.yakb_fastx_close(r)
+    return out
+
+
+def _records_oracle(path):
+    L = O.lib()
+    L.yo_reader_open.restype = C.c_void_p; L.yo_reader_open.argtypes = [C.c_char_p]
+    L.yo_reader_next.restype = C.c_int64; L.yo_reader_next.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
+    L.yo_reader_close.argtypes = [C.c_void_p]
+    r = L.yo_reader_open(path.encode())
+    out = []
+    seq, name = C.c_char_p(), C.c_char_p()
+    while True:
+        n = L.yo_reader_next(r, C.byref(seq), C.byref(name))
+        if n < 0:
+            out.append(n)
+            break
+        out.append((name.value, seq.value))
+    L.yo_reader_close(r)
+    return out
+
+
+def test_fastx_reader_matches_kseq_semantics():
+    import gzip
+    import test_gpu_parity as T
+    fn = T._edge_file(os.path.join(util.TMP, "yakb_edge_rd.fa"))
+    a, b = _records_product(fn), _records_oracle(fn)
+    assert a == b and len(a) > 15 and a[-1] == -1
+    gz = fn + ".gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(open(fn, "rb").read())
+    assert _records_product(gz) == a
+    trunc = os.path.join(util.TMP, "yakb_trunc.fq")
+    open(trunc, "w").write("@r1\nACGTACGT\n+\nIIII\n")
+    assert _records_product(trunc)[-1] == -2 and _records_oracle(trunc)[-1] == -2   # kseq.h:190
+    big = G.input_path("reads_q")
+    assert _records_product(big) == _records_oracle(big)
+    from yak_b200 import capi
+    assert not capi.lib().yakb_fastx_open(b"/nonexistent/x.fa")
+
+
+def test_cli_front_end_without_gpu():
+    exe = os.path.join(ROOT, "yak_b200", "bin", "yak-b200")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe, "version"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("0.1")
+    assert subprocess.run([exe], capture_output=True).returncode == 1
+    assert subprocess.run([exe, "count"], capture_output=True).returncode == 1
+    r = subprocess.run([exe, "count", "-p9", "x.fa"], capture_output=True, text=True)          # main.c:43-46
+    assert r.returncode == 1 and "-p should be at least 10" in r.stderr
+    r = subprocess.run([exe, "count", "-k64", "x.fa"], capture_output=True, text=True)         # main.c:47-49
+    assert r.returncode == 1 and "smaller than 64" in r.stderr
+    y = os.path.join(G.HERE, "reads_c_k31_p10_b22.yak")
+    r = subprocess.run([exe, "inspect", y], capture_output=True, text=True)                     # inspect.c:96-103
+    assert r.returncode == 0
+    case = next(c for c in G.GOLD["cases"] if c["input"] == "reads_c")
+    assert hashlib.sha256(r.stdout.encode()).hexdigest() == case["inspect_sha256"]
+    assert subprocess.run([exe, "bogus"], capture_output=True).returncode == 1
+
+
+def test_qv_solver_matches_reference_output():
+    """qv_solve.c (host FP64, CLI side) against the CT/FR/ER/CV/QV lines the reference printed."""
+    src = os.path.join(ROOT, "yak_b200", "cli", "qv_solve.c")
+    so = os.path.join(util.TMP, "yakb_qvsolve.so")
+    subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), "-o", so, src, "-lm"], check=True)
+    S = C.CDLL(so)
+
+    class Qs(C.Structure):
+        _fields_ = [("tot", C.c_int64), ("qv_raw", C.c_double), ("qv", C.c_double), ("cov", C.c_double), ("err", C.c_double),
+                    ("fpr_lower", C.c_double), ("fpr_upper", C.c_double), ("adj_cnt", C.c_double * 1024)]
+    ref = open(os.path.join(G.HERE, "qv_reads_c_ctg.txt")).read().splitlines()
+    ct = {int(x[1]): x for x in (ln.split("\t") for ln in ref if ln.startswith("CT"))}
+    hist = (C.c_int64 * 1024)(*[int(ct[i][2]) for i in range(1024)])
+    cnt = (C.c_int64 * 1024)(*[int(ct[i][3]) for i in range(1024)])
+    qs = Qs()
+    S.yak_qv_solve.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int, C.c_double, C.POINTER(Qs)]
+    S.yak_qv_solve(hist, cnt, 31, 0.00004, C.byref(qs))
+    lines = ["CT\t%d\t%d\t%d\t%.3f" % (i, hist[i], cnt[i], qs.adj_cnt[i]) for i in range(1023, -1, -1)]
+    lines += ["FR\t%.3g\t%.3g" % (qs.fpr_lower, qs.fpr_upper), "ER\t%d\t%.3f" % (qs.tot, qs.err), "CV\t%.3f" % qs.cov,
+              "QV\t%.3f\t%.3f" % (qs.qv_raw, qs.qv)]
+    want = [ln for ln in ref if ln[:2] in ("CT", "FR", "ER", "CV", "QV")]
+    assert lines == want

@@ -89,6 +89,9 @@ def lib() -> C.CDLL:
         "yakb_ch_stream": (vp, [ChP]),
         "yakb_ch_device_bytes": (u64, [ChP]),
         "yakb_kernel_launches": (u64, []),
+        "yakb_fastx_open": (vp, [C.c_char_p]),
+        "yakb_fastx_next": (i64, [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]),
+        "yakb_fastx_close": (None, [vp]),
         "yakb_prof_enable": (None, [C.c_int]),
         "yakb_prof_json": (C.c_int, [C.c_char_p, u64]),
         "yakb_synth_genome_dev": (C.c_int, [u64, u64, vp, vp]),

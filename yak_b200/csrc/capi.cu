@@ -452,6 +452,24 @@ extern "C" int yakb_synth_reads_dev(const uint64_t *d_genome2, uint64_t G, uint6
 	GUARD_END(-1)
 }
 
+// ------------------------------------------------------------------ host-only helpers (no GPU needed)
+
+extern "C" void *yakb_fastx_open(const char *fn)
+{
+	FastxReader *r = new FastxReader;
+	if (!r->open(fn)) { delete r; return 0; }
+	return r;
+}
+extern "C" int64_t yakb_fastx_next(void *reader, const char **seq, const char **name)
+{
+	FastxReader *r = (FastxReader*)reader;
+	int64_t len = r->next();
+	if (seq) *seq = r->seq().c_str();
+	if (name) *name = r->name().c_str();
+	return len;
+}
+extern "C" void yakb_fastx_close(void *reader) { delete (FastxReader*)reader; }
+
 // ------------------------------------------------------------------ yak_count / yak_recount
 
 static uint64_t batch_bases(int64_t chunk_size)
