@@ -229,14 +229,31 @@ def main():
         bufs.append(b)
     torch.cuda.synchronize()
 
-    h = lib.yak_ch_init(K, PRE, NH, args.bf_shift)
-    assert h, "yak_ch_init failed"
-    stream = torch.cuda.ExternalStream(lib.yakb_ch_stream(h))
     stats = (C.c_uint64 * 4)()
     ev_total = 0
     per_step = []
+    if world == 1:
+        h = lib.yak_ch_init(K, PRE, NH, args.bf_shift)
+        assert h, "yak_ch_init failed"
+        stream = torch.cuda.ExternalStream(lib.yakb_ch_stream(h))
+
+        def step(i):
+            rc = lib.yakb_count_ascii_dev(h, bufs[i].data_ptr(), nr * rec, 1, stats)
+            assert rc == 0
+            return list(stats)
+    else:
+        # sub-tables sharded over the ranks, one all-to-all per step (yak_b200/dist.py)
+        from yak_b200 import dist as ydist
+        be = ydist.GpuBackend(K, PRE, args.bf_shift, NH, rank, world)
+        sc = ydist.ShardedCounter(be)
+        h = be.h
+        stream = torch.cuda.current_stream()
+
+        def step(i):
+            n = sc.count_chunk(bufs[i], 1)
+            return [n, int(be.stats[1]), int(be.stats[2]), int(be.stats[3])]
     for i in range(W):
-        lib.yakb_count_ascii_dev(h, bufs[i].data_ptr(), nr * rec, 1, stats)
+        step(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -250,12 +267,13 @@ def main():
     e0.record(stream)
     for i in range(W, W + KS):
         t_s = time.time()
-        rc = lib.yakb_count_ascii_dev(h, bufs[i].data_ptr(), nr * rec, 1, stats)
-        assert rc == 0
-        ev_total += stats[0]
-        per_step.append(list(stats) + [round((time.time() - t_s) * 1e3, 3)])
+        st = step(i)
+        ev_total += st[0]
+        per_step.append(st + [round((time.time() - t_s) * 1e3, 3)])
     e1.record(stream)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
     launches = lib.yakb_kernel_launches() - launches0
@@ -272,7 +290,10 @@ def main():
         ev_all = float(ev_total)
     value = ev_all / (ms / 1000.0)
     dev_bytes = lib.yakb_ch_device_bytes(h)
-    lib.yak_ch_destroy(h)
+    if world == 1:
+        lib.yak_ch_destroy(h)
+    else:
+        be.close()
     del bufs
     torch.cuda.empty_cache()
     if rank != 0:
@@ -284,7 +305,8 @@ def main():
     peak, peak_kind = measured_peaks()
     n_pending = sum(s[1] for s in per_step)
     alg_bytes = {  # algorithmic bytes per launch set = SURVEY 8(d) per-event figure x events the kernel processed
-        "k1_fused": (0.31 + 8.0) * ev_total,            # read 2-bit bases, one 8-B slot probe per event
+        "k1_fused": (0.31 + 16.0) * ev_total,           # read 2-bit bases; slot read + counter write per event
+        "k1_array": (8.0 + 16.0) * ev_total,            # read the routed event; slot read + counter write
         "group_insert": (8.0 + 128.0 + 16.0) * n_pending,  # sorted event + bloom block RMW + slot read/write
         "group_sort(cub)": 2 * 12.0 * n_pending,
         "compact": 8.0 * n_pending,
@@ -305,7 +327,7 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "cfg2", "k": K, "pre": PRE, "bf_shift": args.bf_shift, "bf_n_hash": NH, "read_len": L,
                        "genome_bp": G, "reads_per_step": nr, "bases_per_step": nr * L, "l2": "inputs larger than L2 (no flush)",
-                       "parallelism": f"dp{world} (independent read slices)" if world > 1 else "1 GPU",
+                       "parallelism": f"{world} GPUs: reads split by rank, 2^{PRE}/{world} sub-tables per rank, one NCCL all-to-all per step" if world > 1 else "1 GPU",
                        "device_bytes": int(dev_bytes)},
             "input_gbp_per_s": (nr * L * KS * world) / (ms / 1000.0) / 1e9,
             "gpu_launches": int(launches), "kernels_ms": {k: round(v[0], 3) for k, v in prof.items()},

@@ -36,6 +36,14 @@ int yakb_count_events_dev(yak_ch_t *h, const uint64_t *d_ev, uint64_t n, int cre
 int yakb_extract_route_dev(const void *d_asc, uint64_t n, int k, int pre, int world,
                            uint64_t *d_out, uint64_t *counts, void *cuda_stream);
 
+/* Multi-GPU: one shard of a table whose 2^pre sub-tables are split over `world` (power of two)
+ * GPUs; shard `rank` owns sub-tables [rank*2^pre/world, (rank+1)*2^pre/world) and ignores events
+ * of other sub-tables.  Feed it with yakb_count_events_dev after the all-to-all.  The shards'
+ * yakb_ch_dump_shard_mem outputs concatenated in rank order (header from rank 0 only) are the
+ * bytes yak_ch_dump would write for the whole table. */
+yak_ch_t *yakb_ch_init_shard(int k, int pre, int n_hash, int n_shift, int rank, int world);
+int64_t yakb_ch_dump_shard_mem(const yak_ch_t *h, int with_header, uint8_t **out);
+
 /* batched yak_ch_get (reference htab.c:93-100): out[i] = count or -1 */
 int yakb_ch_get_batch(const yak_ch_t *h, uint64_t n, const uint64_t *x, int32_t *out);
 int yakb_ch_get_batch_dev(const yak_ch_t *h, uint64_t n, const uint64_t *d_x, int32_t *d_out);
@@ -63,6 +71,11 @@ uint64_t yakb_kernel_launches(void);
 void *yakb_fastx_open(const char *fn);
 int64_t yakb_fastx_next(void *reader, const char **seq, const char **name);
 void yakb_fastx_close(void *reader);
+/* skip n_skip records, then append up to n_take records (those of length >= min_len) to buf as
+ * "SEQ\n"; returns the records consumed (-1: buf too small).  Lets each rank of a multi-GPU job
+ * take its contiguous slice of every chunk of one shared input file. */
+int64_t yakb_fastx_read_slice(void *reader, int64_t n_skip, int64_t n_take, int min_len,
+                              char *buf, uint64_t cap, uint64_t *n_bytes, int64_t *n_seq);
 
 /* per-kernel device time (CUDA events on the table's stream): enable, run chunks, read
  * {"kernel": [total_ms, launches], ...} as JSON text; returns its length or -1 if buf is too small */

@@ -278,6 +278,14 @@ int yo_ch_insert_list(yo_ch_t *h, int create_new, int n, const uint64_t *a)
 	return n_new;
 }
 
+/* a stream of events of mixed sub-tables in file order, one by one (what count.c:129-143 does
+ * per chunk through the per-sub-table lists); h->tot maintained like count.c:138 */
+void yo_ch_insert_events(yo_ch_t *h, int create_new, int64_t n, const uint64_t *a)
+{
+	int64_t i;
+	for (i = 0; i < n; ++i) h->tot += yo_ch_insert_list(h, create_new, 1, &a[i]);
+}
+
 /* htab.c:93-100 */
 int yo_ch_get(const yo_ch_t *h, uint64_t x)
 {

@@ -64,6 +64,7 @@ yo_ch_t *yo_ch_init(int k, int pre, int n_hash, int n_shift);
 void yo_ch_destroy(yo_ch_t *h);
 void yo_ch_destroy_bf(yo_ch_t *h);
 int  yo_ch_insert_list(yo_ch_t *h, int create_new, int n, const uint64_t *a);
+void yo_ch_insert_events(yo_ch_t *h, int create_new, int64_t n, const uint64_t *a);
 int  yo_ch_get(const yo_ch_t *h, uint64_t x);
 int  yo_ch_inc(yo_ch_t *h, uint64_t x);
 void yo_ch_clear(yo_ch_t *h);

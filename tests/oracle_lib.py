@@ -47,6 +47,7 @@ def lib():
     L.yo_ch_destroy_bf.argtypes = [C.POINTER(YoCh)]
     L.yo_ch_insert_list.restype = C.c_int
     L.yo_ch_insert_list.argtypes = [C.POINTER(YoCh), C.c_int, C.c_int, C.POINTER(u64)]
+    L.yo_ch_insert_events.argtypes = [C.POINTER(YoCh), C.c_int, i64, C.POINTER(u64)]
     L.yo_ch_get.restype = C.c_int; L.yo_ch_get.argtypes = [C.POINTER(YoCh), u64]
     L.yo_ch_clear.argtypes = [C.POINTER(YoCh)]
     L.yo_ch_hist.argtypes = [C.POINTER(YoCh), C.POINTER(i64)]

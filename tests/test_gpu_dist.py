@@ -1,0 +1,51 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the NCCL-routed sharded count
+through the C ABI equals the oracle's single-table bytes."""
+import os
+import socket
+
+import pytest
+
+import golden_util as G
+import oracle_lib as O
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, fn, k, pre, b, out):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    from yak_b200 import dist as yd
+    be = yd.GpuBackend(k, pre, b, 4, rank, world)
+    sc = yd.count_file_sharded(fn, be, records_per_chunk=2000, k=k, two_pass=b > 0)
+    tot = sc.total_distinct()
+    data = sc.dump_bytes()
+    if rank == 0:
+        open(out, "wb").write(data)
+        open(out + ".tot", "w").write(str(tot))
+    be.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k,pre,b", [(31, 12, 0), (31, 10, 20), (47, 12, 0)])
+def test_nccl_sharded_count_equals_oracle(yakb, k, pre, b):
+    import torch
+    import torch.multiprocessing as mp
+    world = 1
+    while world * 2 <= min(torch.cuda.device_count(), 8):
+        world *= 2
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    fn = G.input_path("reads_q")
+    out = os.path.join(util.TMP, f"yakb_nccl_{k}_{pre}_{b}.yak")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(world, port, fn, k, pre, b, out), nprocs=world, join=True)
+    h, _ = O.count_file(fn, k=k, pre=pre, bf_shift=b)
+    want = O.dump_bytes(h)
+    got = open(out, "rb").read()
+    assert got == want, util.explain_diff(got, want)
+    assert int(open(out + ".tot").read()) == h.contents.tot
+    O.lib().yo_ch_destroy(h)

@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
         "yakb_qv_seqs": (C.c_int, [ChP, i64, C.POINTER(i64), C.c_char_p, C.c_int, C.c_double, C.POINTER(i64),
                                    C.POINTER(i32), C.POINTER(i32)]),
         "yakb_ch_dump_mem": (i64, [ChP, C.POINTER(vp)]),
+        "yakb_ch_init_shard": (ChP, [C.c_int] * 6),
+        "yakb_ch_dump_shard_mem": (i64, [ChP, C.c_int, C.POINTER(vp)]),
         "yakb_ch_reserve": (C.c_int, [ChP, u64]),
         "yakb_ch_stream": (vp, [ChP]),
         "yakb_ch_device_bytes": (u64, [ChP]),
@@ -92,6 +94,7 @@ def lib() -> C.CDLL:
         "yakb_fastx_open": (vp, [C.c_char_p]),
         "yakb_fastx_next": (i64, [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]),
         "yakb_fastx_close": (None, [vp]),
+        "yakb_fastx_read_slice": (i64, [vp, i64, i64, C.c_int, vp, u64, C.POINTER(u64), C.POINTER(i64)]),
         "yakb_prof_enable": (None, [C.c_int]),
         "yakb_prof_json": (C.c_int, [C.c_char_p, u64]),
         "yakb_synth_genome_dev": (C.c_int, [u64, u64, vp, vp]),

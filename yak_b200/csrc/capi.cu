@@ -92,17 +92,17 @@ static void attach_handles(ChBox *b)
 		if (b->eng->bloom) {
 			b->filters[i].n_shift = b->eng->n_shift - b->eng->pre;
 			b->filters[i].n_hashes = b->eng->n_hash;
-			b->filters[i].b = b->eng->bloom + (size_t)i * 64; // first block of sub-filter i (blocks interleave by sub-table)
+			b->filters[i].b = b->eng->bloom + (size_t)(i & (b->eng->P - 1)) * 64; // first block of sub-filter i (blocks interleave by sub-table)
 			b->pub.h[i].b = &b->filters[i];
 		}
 	}
 }
 
-extern "C" yak_ch_t *yak_ch_init(int k, int pre, int n_hash, int n_shift) // htab.c:13-29
+static yak_ch_t *ch_init_shard(int k, int pre, int n_hash, int n_shift, int rank, int world)
 {
 	GUARD_BEGIN
 	if (pre < YAK_COUNTER_BITS) return 0;
-	Engine *e = Engine::create(k, pre, n_hash, n_shift);
+	Engine *e = Engine::create(k, pre, n_hash, n_shift, rank, world);
 	if (!e) return 0;
 	ChBox *b = new ChBox;
 	memset(&b->pub, 0, sizeof(b->pub));
@@ -111,6 +111,16 @@ extern "C" yak_ch_t *yak_ch_init(int k, int pre, int n_hash, int n_shift) // hta
 	attach_handles(b);
 	return &b->pub;
 	GUARD_END(0)
+}
+
+extern "C" yak_ch_t *yak_ch_init(int k, int pre, int n_hash, int n_shift) // htab.c:13-29
+{
+	return ch_init_shard(k, pre, n_hash, n_shift, 0, 1);
+}
+
+extern "C" yak_ch_t *yakb_ch_init_shard(int k, int pre, int n_hash, int n_shift, int rank, int world)
+{
+	return ch_init_shard(k, pre, n_hash, n_shift, rank, world);
 }
 
 extern "C" void yak_ch_destroy_bf(yak_ch_t *h) // htab.c:31-39
@@ -142,7 +152,7 @@ extern "C" int yak_ch_insert_list(yak_ch_t *h, int create_new, int n, const uint
 	std::lock_guard<std::mutex> lk(b->mu);
 	uint64_t *d = b->d_in.as<uint64_t>(n);
 	YAKB_CUDA(cudaMemcpyAsync(d, a, (size_t)n * 8, cudaMemcpyHostToDevice, b->eng->stream));
-	const int only = (int)(a[0] & ((1ull << h->pre) - 1));
+	const int only = (int)(a[0] & (uint64_t)(b->eng->P - 1)); // region index; foreign shards are filtered by owner
 	ChunkStats st = b->eng->count_events(d, n, create_new, only);
 	return (int)st.n_new; // the caller adds this to h->tot (count.c:138)
 	GUARD_END(0)
@@ -265,13 +275,15 @@ extern "C" void yak_ch_isec(yak_ch_t *h0, const yak_ch_t *h1, int n_thread) { (v
 // ------------------------------------------------------------------ dump / restore
 
 // htab.c:373-394; sink(ptr,len) receives the bytes in order
-template<class Sink> static void serialise(ChBox *b, Sink &&sink)
+template<class Sink> static void serialise(ChBox *b, Sink &&sink, bool header = true)
 {
 	const yak_ch_t *h = &b->pub;
-	const int P = 1 << h->pre;
+	const int P = b->eng->P; // a shard writes its own contiguous range of sub-tables
 	uint32_t t[3] = {(uint32_t)h->k, (uint32_t)h->pre, YAK_COUNTER_BITS};
-	sink(YAK_MAGIC, 4);
-	sink(t, 12);
+	if (header) {
+		sink(YAK_MAGIC, 4);
+		sink(t, 12);
+	}
 	const int step = 1024;
 	for (int s0 = 0; s0 < P; s0 += step) {
 		const int s1 = std::min(P, s0 + step);
@@ -290,6 +302,7 @@ extern "C" int yak_ch_dump(const yak_ch_t *h, const char *fn)
 	GUARD_BEGIN
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
+	if (b->eng->lw) { fprintf(stderr, "[yakb] ERROR: yak_ch_dump on one shard of a multi-GPU table; use yakb_ch_dump_shard_mem\n"); return -1; }
 	FILE *fp = strcmp(fn, "-") ? fopen(fn, "wb") : stdout;
 	if (fp == 0) return -1;
 	static char iobuf[1 << 20];
@@ -301,18 +314,20 @@ extern "C" int yak_ch_dump(const yak_ch_t *h, const char *fn)
 	GUARD_END(-1)
 }
 
-extern "C" int64_t yakb_ch_dump_mem(const yak_ch_t *h, uint8_t **out)
+static int64_t dump_mem(const yak_ch_t *h, uint8_t **out, bool header)
 {
 	GUARD_BEGIN
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
 	std::vector<uint8_t> acc;
-	serialise(b, [&](const void *p, size_t n) { acc.insert(acc.end(), (const uint8_t*)p, (const uint8_t*)p + n); });
+	serialise(b, [&](const void *p, size_t n) { acc.insert(acc.end(), (const uint8_t*)p, (const uint8_t*)p + n); }, header);
 	*out = (uint8_t*)malloc(acc.size() ? acc.size() : 1);
 	memcpy(*out, acc.data(), acc.size());
 	return (int64_t)acc.size();
 	GUARD_END(-1)
 }
+extern "C" int64_t yakb_ch_dump_mem(const yak_ch_t *h, uint8_t **out) { return dump_mem(h, out, true); }
+extern "C" int64_t yakb_ch_dump_shard_mem(const yak_ch_t *h, int with_header, uint8_t **out) { return dump_mem(h, out, with_header != 0); }
 
 extern "C" yak_ch_t *yak_ch_restore_core(yak_ch_t *ch0, const char *fn, int mode, ...) // htab.c:396-476
 {
@@ -469,6 +484,31 @@ extern "C" int64_t yakb_fastx_next(void *reader, const char **seq, const char **
 	return len;
 }
 extern "C" void yakb_fastx_close(void *reader) { delete (FastxReader*)reader; }
+
+// Skip n_skip records, then append up to n_take records of length >= min_len to buf as "SEQ\n".
+// Returns the number of records CONSUMED (skipped + taken + dropped short ones counted among the taken);
+// fewer than n_skip + n_take means end of input.  *n_bytes / *n_seq describe what was appended.
+extern "C" int64_t yakb_fastx_read_slice(void *reader, int64_t n_skip, int64_t n_take, int min_len,
+                                         char *buf, uint64_t cap, uint64_t *n_bytes, int64_t *n_seq)
+{
+	FastxReader *r = (FastxReader*)reader;
+	int64_t used = 0;
+	uint64_t n = 0;
+	*n_bytes = 0; *n_seq = 0;
+	for (int64_t i = 0; i < n_skip; ++i) { if (r->next() < 0) return used; ++used; }
+	for (int64_t i = 0; i < n_take; ++i) {
+		int64_t len = r->next();
+		if (len < 0) break;
+		++used;
+		if (len < min_len) continue;
+		if (n + (uint64_t)len + 1 > cap) return -1; // caller's buffer too small
+		memcpy(buf + n, r->seq().data(), len);
+		n += len; buf[n++] = '\n';
+		++*n_seq;
+	}
+	*n_bytes = n;
+	return used;
+}
 
 // ------------------------------------------------------------------ yak_count / yak_recount
 

@@ -133,7 +133,7 @@ __device__ __forceinline__ int probe_inc_warp(uint64_t *reg, uint32_t nbk, uint6
 //      stats[0] += events, glob_lput[s] = max(pos+1) over found (= put) events of sub-table s.
 template<bool LONGK>
 __global__ void __launch_bounds__(256, 3) k1_fused(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords,
-                                                int k, int pre, uint32_t Pmask, uint64_t *slots, uint32_t cap, int create_new,
+                                                int k, int pre, uint32_t Pmask, Own own, uint64_t *slots, uint32_t cap, int create_new,
                                                 uint32_t *__restrict__ flags, uint32_t *__restrict__ tilecnt,
                                                 uint32_t *glob_lput, int smem_lp, unsigned long long *stats)
 {
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256, 3) k1_fused(const uint64_t *__restrict__ 
 #pragma unroll
 				for (int j = 0; j < 4; ++j) {
 					bi[j] = 0; v[j] = 0;
-					if (live && ro.step(b + j, v[j])) {
+					if (live && ro.step(b + j, v[j]) && ((uint32_t)(v[j] >> own.shift) & own.mask) == own.rank) {
 						vm |= 1u << j;
 						if (cap) {
 							bi[j] = tab_home(v[j] >> pre, nbk);
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256, 3) k1_fused(const uint64_t *__restrict__ 
 
 // ---- K1, array front end (events already hashed: yak_ch_insert_list, multi-GPU receive side).
 //      word W = events 32W..32W+31, lane = bit.
-__global__ void __launch_bounds__(256) k1_array(const uint64_t *__restrict__ ev, uint64_t n, int pre, uint32_t Pmask,
+__global__ void __launch_bounds__(256) k1_array(const uint64_t *__restrict__ ev, uint64_t n, int pre, uint32_t Pmask, Own own,
                                                 uint64_t *slots, uint32_t cap, int create_new, int only_s,
                                                 uint32_t *__restrict__ flags, uint32_t *__restrict__ tilecnt,
                                                 uint32_t *glob_lput, int smem_lp, unsigned long long *stats)
@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(256) k1_array(const uint64_t *__restrict__ ev,
 			int valid = i < n, found = 0;
 			uint64_t v = valid ? ev[i] : 0;
 			if (valid && only_s >= 0 && ((uint32_t)v & Pmask) != (uint32_t)only_s) valid = 0;
+			if (valid && ((uint32_t)(v >> own.shift) & own.mask) != own.rank) valid = 0; // not this shard's sub-table
 			if (valid) ++my_ev;
 			if (cap) {
 				const uint32_t nbk = cap / YAKB_BUCKET, s = (uint32_t)v & Pmask;
@@ -313,7 +314,7 @@ __global__ void max_need_kernel(const uint32_t *nkeys, const uint32_t *pend, uin
 // ---- the ordered part: one thread per group, events of a group walked in file order.
 //      pflag[j]: bit0 = put-event, bit1 = this put inserted a new key.
 __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__ sv, const uint32_t *__restrict__ sj, uint64_t n,
-                                                    int G, int pre, uint32_t Pmask, uint64_t *slots, uint32_t cap,
+                                                    int G, int pre, uint32_t Pmask, int lw, uint64_t *slots, uint32_t cap,
                                                     uint32_t *bloom32, int nb, int sub_shift, int n_hash,
                                                     uint8_t *__restrict__ pflag)
 {
@@ -324,6 +325,8 @@ __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__
 	if (i > 0 && (sv[i - 1] & gmask) == gk) return;
 	uint32_t blk[16];
 	int have_blk = 0, dirty = 0;
+	// block address: the group key with the (constant) owner bits of a shard squeezed out
+	const uint64_t baddr = lw ? ((gk >> pre) << (pre - lw)) | (gk & Pmask) : gk;
 	for (uint64_t e = i; e < n; ++e) {
 		const uint64_t v = sv[e];
 		if ((v & gmask) != gk) break;
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__
 		int put = 1;
 		if (bloom32) { // bbf.c:25-42 on the 64-byte block this group owns (held in registers)
 			if (!have_blk) {
-				const uint4 *q = (const uint4*)(bloom32 + gk * 16);
+				const uint4 *q = (const uint4*)(bloom32 + baddr * 16);
 				uint4 a0 = __ldcg(q), a1 = __ldcg(q + 1), a2 = __ldcg(q + 2), a3 = __ldcg(q + 3);
 				blk[0] = a0.x; blk[1] = a0.y; blk[2] = a0.z; blk[3] = a0.w; blk[4] = a1.x; blk[5] = a1.y; blk[6] = a1.z; blk[7] = a1.w;
 				blk[8] = a2.x; blk[9] = a2.y; blk[10] = a2.z; blk[11] = a2.w; blk[12] = a3.x; blk[13] = a3.y; blk[14] = a3.z; blk[15] = a3.w;
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__
 		pflag[j] = flag;
 	}
 	if (dirty) {
-		uint4 *q = (uint4*)(bloom32 + gk * 16);
+		uint4 *q = (uint4*)(bloom32 + baddr * 16);
 		__stcg(q, make_uint4(blk[0], blk[1], blk[2], blk[3]));
 		__stcg(q + 1, make_uint4(blk[4], blk[5], blk[6], blk[7]));
 		__stcg(q + 2, make_uint4(blk[8], blk[9], blk[10], blk[11]));
@@ -471,14 +474,14 @@ __global__ void __launch_bounds__(256) hist_kernel(const uint64_t *__restrict__ 
 }
 
 // htab.c:93-100
-__global__ void get_batch_kernel(const uint64_t *__restrict__ xs, uint64_t n, int pre, uint32_t Pmask,
+__global__ void get_batch_kernel(const uint64_t *__restrict__ xs, uint64_t n, int pre, uint32_t Pmask, Own own,
                                  const uint64_t *__restrict__ slots, uint32_t cap, int32_t *__restrict__ out)
 {
 	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	uint64_t v = xs[i];
 	int32_t r = -1;
-	if (cap) {
+	if (cap && ((uint32_t)(v >> own.shift) & own.mask) == own.rank) {
 		int64_t q = tab_find(slots + (uint64_t)((uint32_t)v & Pmask) * cap, cap, v >> pre);
 		if (q >= 0) r = (int32_t)(slots[(uint64_t)((uint32_t)v & Pmask) * cap + q] & YAKB_MAX_COUNT);
 	}
@@ -488,7 +491,7 @@ __global__ void get_batch_kernel(const uint64_t *__restrict__ xs, uint64_t n, in
 // qv.c:48-66: per position the count of its k-mer (absent -> 0), or -1 where no k-mer ends
 template<bool LONGK>
 __global__ void __launch_bounds__(256) qv_scan_kernel(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords, uint64_t n,
-                                                      int k, int pre, uint32_t Pmask, const uint64_t *__restrict__ slots, uint32_t cap,
+                                                      int k, int pre, uint32_t Pmask, Own own, const uint64_t *__restrict__ slots, uint32_t cap,
                                                       int16_t *__restrict__ out)
 {
 	const uint64_t W = blockIdx.x * 256ull + threadIdx.x;
@@ -498,7 +501,7 @@ __global__ void __launch_bounds__(256) qv_scan_kernel(const uint64_t *__restrict
 	for (int r = 0; r < 32; ++r) res[r] = -1;
 	roll_word<LONGK>(w2, wm, W, k, [&](int r, uint64_t v) {
 		int16_t c = 0;
-		if (cap) {
+		if (cap && ((uint32_t)(v >> own.shift) & own.mask) == own.rank) {
 			const uint64_t *reg = slots + (uint64_t)((uint32_t)v & Pmask) * cap;
 			int64_t q = tab_find(reg, cap, v >> pre);
 			if (q >= 0) c = (int16_t)(reg[q] & YAKB_MAX_COUNT);
@@ -604,9 +607,15 @@ __global__ void advance_run_kernel(const uint64_t *__restrict__ seg_off, int s0,
 
 // ============================================================ host side
 
-Engine *Engine::create(int k, int pre, int n_hash, int n_shift)
+Engine *Engine::create(int k, int pre, int n_hash, int n_shift, int rank, int world)
 {
 	if (pre < YAKB_COUNTER_BITS) return nullptr; // htab.c:17
+	int lw = 0;
+	while ((1 << lw) < world) ++lw;
+	if ((1 << lw) != world || lw > pre || rank < 0 || rank >= world) {
+		fprintf(stderr, "[yakb] ERROR: world size must be a power of two <= 2^pre and 0 <= rank < world\n");
+		return nullptr;
+	}
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount(&ndev);
 	if (e != cudaSuccess || ndev == 0) {
@@ -614,7 +623,7 @@ Engine *Engine::create(int k, int pre, int n_hash, int n_shift)
 		return nullptr;
 	}
 	Engine *g = new Engine;
-	g->k = k, g->pre = pre, g->P = 1 << pre;
+	g->k = k, g->pre = pre, g->P = 1 << (pre - lw), g->lw = lw, g->rank = rank;
 	YAKB_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
 	YAKB_CUDA(cudaMalloc(&g->nkeys, g->P * sizeof(uint32_t)));
 	YAKB_CUDA(cudaMalloc(&g->last_put, g->P * sizeof(uint64_t)));
@@ -630,7 +639,7 @@ Engine *Engine::create(int k, int pre, int n_hash, int n_shift)
 		int sub = n_shift - pre;
 		if (sub >= 9 && sub + 9 <= 64) {
 			g->nb = sub - 9;
-			size_t bytes = (size_t)1 << (n_shift - 3);
+			size_t bytes = (size_t)1 << (n_shift - 3 - lw);
 			YAKB_CUDA(cudaMalloc(&g->bloom, bytes));
 			YAKB_CUDA(cudaMemsetAsync(g->bloom, 0, bytes, g->stream));
 		}
@@ -657,7 +666,7 @@ void Engine::destroy_bloom() { if (bloom) { cudaFree(bloom); bloom = nullptr; } 
 
 uint64_t Engine::device_bytes() const
 {
-	uint64_t b = (uint64_t)P * cap * 8 + (bloom ? (uint64_t)1 << (n_shift - 3) : 0);
+	uint64_t b = (uint64_t)P * cap * 8 + (bloom ? (uint64_t)1 << (n_shift - 3 - lw) : 0);
 	for (auto &s : journal) b += s.n * 8 + (uint64_t)(P + 1) * 8;
 	return b;
 }
@@ -744,14 +753,14 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 	if (d_ev == nullptr) {
 		if (longk) {
 			set_smem(k1_fused<true>, sm1);
-			k1_fused<true><<<grid1, 256, sm1, stream>>>(w2, wm, nwords, k, pre, Pmask, slots, cap, create_new, flags, tilecnt, lput, smem1, stats);
+			k1_fused<true><<<grid1, 256, sm1, stream>>>(w2, wm, nwords, k, pre, Pmask, own(), slots, cap, create_new, flags, tilecnt, lput, smem1, stats);
 		} else {
 			set_smem(k1_fused<false>, sm1);
-			k1_fused<false><<<grid1, 256, sm1, stream>>>(w2, wm, nwords, k, pre, Pmask, slots, cap, create_new, flags, tilecnt, lput, smem1, stats);
+			k1_fused<false><<<grid1, 256, sm1, stream>>>(w2, wm, nwords, k, pre, Pmask, own(), slots, cap, create_new, flags, tilecnt, lput, smem1, stats);
 		}
 	} else {
 		set_smem(k1_array, sm1);
-		k1_array<<<grid1, 256, sm1, stream>>>(d_ev, n_ev_in, pre, Pmask, slots, cap, create_new, only_s, flags, tilecnt, lput, smem1, stats);
+		k1_array<<<grid1, 256, sm1, stream>>>(d_ev, n_ev_in, pre, Pmask, own(), slots, cap, create_new, only_s, flags, tilecnt, lput, smem1, stats);
 	}
 	}
 	YAKB_CUDA(cudaGetLastError());
@@ -819,7 +828,7 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 		cub::DeviceRadixSort::SortPairs(tmp_sort, tmp_bytes, pv, sv, iota, sj, (int)n_pending, 0, G, stream); }
 		uint8_t *pflag = b_pflag.as<uint8_t>(2 * (size_t)n_pending); // [0,n): put/new bits, [n,2n): new-key flag
 		{ ProfScope ps("group_insert", stream);
-		group_insert<<<cdiv(n_pending, 256), 256, 0, stream>>>(sv, sj, n_pending, G, pre, Pmask, slots, cap,
+		group_insert<<<cdiv(n_pending, 256), 256, 0, stream>>>(sv, sj, n_pending, G, pre, Pmask, lw, slots, cap,
 		                                                       (uint32_t*)bloom, nb, n_shift - pre, n_hash, pflag); }
 		YAKB_CUDA(cudaGetLastError());
 		const int smem2 = smem_lp_ok(P, 2);
@@ -844,10 +853,10 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 		if (n_new) {
 			uint64_t *sorted = b_newsorted.as<uint64_t>(n_new);
 			tmp_bytes = 0;
-			cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, newv, sorted, (int)n_new, 0, pre, stream);
+			cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, newv, sorted, (int)n_new, 0, pre - lw, stream);
 			void *tmp_js = b_tmp.need(tmp_bytes);
 			ProfScope ps("journal(cub sort+seg)", stream);
-			cub::DeviceRadixSort::SortKeys(tmp_js, tmp_bytes, newv, sorted, (int)n_new, 0, pre, stream);
+			cub::DeviceRadixSort::SortKeys(tmp_js, tmp_bytes, newv, sorted, (int)n_new, 0, pre - lw, stream);
 			Segment seg;
 			seg.n = n_new;
 			YAKB_CUDA(cudaMalloc(&seg.keys, n_new * 8));
@@ -898,7 +907,7 @@ void Engine::hist(int64_t cnt[1024])
 void Engine::get_batch(const uint64_t *d_x, uint64_t n, int32_t *d_out)
 {
 	if (n == 0) return;
-	get_batch_kernel<<<cdiv(n, 256), 256, 0, stream>>>(d_x, n, pre, P - 1, slots, cap, d_out);
+	get_batch_kernel<<<cdiv(n, 256), 256, 0, stream>>>(d_x, n, pre, P - 1, own(), slots, cap, d_out);
 	YAKB_CUDA(cudaGetLastError());
 	YAKB_CUDA(cudaStreamSynchronize(stream));
 }
@@ -1060,8 +1069,8 @@ void qv_scan_ascii(Engine *e, const uint8_t *d_asc, uint64_t n, int16_t *d_cnt)
 	uint64_t *w2 = e->b_w2.as<uint64_t>(nwords);
 	uint32_t *wm = e->b_wm.as<uint32_t>(nwords);
 	pack_ascii_kernel<<<cdiv(nwords, 256), 256, 0, e->stream>>>(d_asc, n, w2, wm, nwords);
-	if (e->k >= 32) qv_scan_kernel<true><<<cdiv(nwords, 256), 256, 0, e->stream>>>(w2, wm, nwords, n, e->k, e->pre, e->P - 1, e->slots, e->cap, d_cnt);
-	else qv_scan_kernel<false><<<cdiv(nwords, 256), 256, 0, e->stream>>>(w2, wm, nwords, n, e->k, e->pre, e->P - 1, e->slots, e->cap, d_cnt);
+	if (e->k >= 32) qv_scan_kernel<true><<<cdiv(nwords, 256), 256, 0, e->stream>>>(w2, wm, nwords, n, e->k, e->pre, e->P - 1, e->own(), e->slots, e->cap, d_cnt);
+	else qv_scan_kernel<false><<<cdiv(nwords, 256), 256, 0, e->stream>>>(w2, wm, nwords, n, e->k, e->pre, e->P - 1, e->own(), e->slots, e->cap, d_cnt);
 	YAKB_CUDA(cudaGetLastError());
 	YAKB_CUDA(cudaStreamSynchronize(e->stream));
 }

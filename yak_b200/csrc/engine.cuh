@@ -61,8 +61,15 @@ struct LayoutOut {
 	std::vector<uint64_t> keys;         // stored keys (with counts) in slot order
 };
 
+// which sub-tables a (sharded) engine owns: those whose top `lw` index bits equal `rank`
+struct Own { int shift; uint32_t mask, rank; };
+
 struct Engine {
+	// P = number of sub-tables held HERE (2^pre, or 2^pre / world for one shard of a multi-GPU
+	// table: shard `rank` owns the contiguous sub-table range [rank*P, (rank+1)*P))
 	int k = 0, pre = 0, n_hash = 0, n_shift = 0, P = 0;
+	int lw = 0, rank = 0;
+	Own own() const { Own o; o.shift = pre - lw; o.mask = (1u << lw) - 1; o.rank = (uint32_t)rank; return o; }
 	uint64_t *slots = nullptr; uint32_t cap = 0;
 	uint32_t *nkeys = nullptr;
 	uint8_t *bloom = nullptr; int nb = 0;
@@ -78,7 +85,7 @@ struct Engine {
 	DBuf b_w2, b_wm, b_flags, b_tilecnt, b_tileoff, b_pv, b_ppos, b_sv, b_sj, b_iota, b_pflag, b_newv, b_newsorted,
 	     b_tmp, b_pend, b_lput, b_lnew, b_stats, b_misc;
 
-	static Engine *create(int k, int pre, int n_hash, int n_shift);
+	static Engine *create(int k, int pre, int n_hash, int n_shift, int rank = 0, int world = 1);
 	~Engine();
 	void destroy_bloom();
 

@@ -142,10 +142,10 @@ void qv_stats(const int16_t *d_cnt, const uint64_t *d_seq_off, uint64_t n_seq, i
 }
 
 // ---- htab.c:80-91 for one key
-__global__ void inc_one_kernel(uint64_t *slots, uint32_t cap, int pre, uint32_t Pmask, uint64_t v, int32_t *out)
+__global__ void inc_one_kernel(uint64_t *slots, uint32_t cap, int pre, uint32_t Pmask, Own own, uint64_t v, int32_t *out)
 {
 	int32_t r = -1;
-	if (cap) {
+	if (cap && ((uint32_t)(v >> own.shift) & own.mask) == own.rank) {
 		uint64_t *reg = slots + (uint64_t)((uint32_t)v & Pmask) * cap;
 		int64_t q = tab_find(reg, cap, v >> pre);
 		if (q >= 0) {
@@ -159,7 +159,7 @@ __global__ void inc_one_kernel(uint64_t *slots, uint32_t cap, int pre, uint32_t 
 int inc_one(Engine *e, uint64_t v)
 {
 	int32_t *d = (int32_t*)e->b_misc.need(16), h = -1;
-	inc_one_kernel<<<1, 1, 0, e->stream>>>(e->slots, e->cap, e->pre, e->P - 1, v, d);
+	inc_one_kernel<<<1, 1, 0, e->stream>>>(e->slots, e->cap, e->pre, e->P - 1, e->own(), v, d);
 	YAKB_CUDA(cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, e->stream));
 	YAKB_CUDA(cudaStreamSynchronize(e->stream));
 	return h;

@@ -1,0 +1,171 @@
+"""Multi-GPU k-mer counting: sub-table shards + one all-to-all per chunk.
+
+One process per GPU (torchrun).  Rank r owns the contiguous sub-table range
+[r*P/G, (r+1)*P/G).  For every chunk each rank extracts the hashed k-mers of ITS contiguous slice
+of the chunk's reads, stably grouped by owner rank; one all-to-all (counts, then payload) routes
+them; the receiver sees source ranks 0..G-1 in order, i.e. file order per sub-table, and feeds the
+run to its shard.  torch.distributed is the plumbing (NCCL on GPUs; gloo in the CPU tests); the
+compute is the C library behind `GpuBackend` (tests substitute an oracle-backed backend to
+exercise exactly this routing logic without a GPU).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class GpuBackend:
+    """The product: libyakb200 on the current CUDA device."""
+
+    def __init__(self, k, pre, bf_shift, bf_n_hash, rank, world):
+        from . import capi
+        capi.require_gpu()
+        self.capi, self.lib = capi, capi.lib()
+        self.k, self.pre, self.rank, self.world = k, pre, rank, world
+        self.h = self.lib.yakb_ch_init_shard(k, pre, bf_n_hash, bf_shift, rank, world)
+        if not self.h:
+            raise RuntimeError("yakb_ch_init_shard failed")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.stats = (C.c_uint64 * 4)()
+
+    def to_device(self, asc: bytes | np.ndarray | torch.Tensor) -> torch.Tensor:
+        if isinstance(asc, torch.Tensor):
+            return asc.to(self.device)
+        a = np.frombuffer(asc, dtype=np.uint8) if isinstance(asc, (bytes, bytearray)) else asc
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+    def extract_route(self, asc: torch.Tensor):
+        n = asc.numel()
+        out = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        counts = (C.c_uint64 * self.world)()
+        torch.cuda.current_stream().synchronize()
+        rc = self.lib.yakb_extract_route_dev(asc.data_ptr(), n, self.k, self.pre, self.world, out.data_ptr(), counts,
+                                             torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            raise RuntimeError("yakb_extract_route_dev failed")
+        cl = [int(c) for c in counts]
+        return out[:sum(cl)], cl
+
+    def count_events(self, ev: torch.Tensor, create_new: int) -> int:
+        torch.cuda.current_stream().synchronize()
+        rc = self.lib.yakb_count_events_dev(self.h, ev.data_ptr(), ev.numel(), create_new, self.stats)
+        if rc != 0:
+            raise RuntimeError("yakb_count_events_dev failed")
+        return int(self.stats[0])
+
+    def destroy_bf(self): self.lib.yak_ch_destroy_bf(self.h)
+    def clear(self): self.lib.yak_ch_clear(self.h, 1)
+    def shrink(self, lo, hi): self.lib.yak_ch_shrink(self.h, lo, hi, 1)
+    def tot(self): return int(self.h.contents.tot)
+
+    def dump_shard(self, with_header: bool) -> bytes:
+        out = C.c_void_p()
+        n = self.lib.yakb_ch_dump_shard_mem(self.h, int(with_header), C.byref(out))
+        if n < 0:
+            raise RuntimeError("yakb_ch_dump_shard_mem failed")
+        data = C.string_at(out, n)
+        C.CDLL(None).free(out)
+        return data
+
+    def close(self):
+        if self.h:
+            self.lib.yak_ch_destroy(self.h)
+            self.h = None
+
+
+class ShardedCounter:
+    """`yak count` over `world` shards.  `backend` does the per-rank compute."""
+
+    def __init__(self, backend, group=None):
+        self.b = backend
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.events = 0
+
+    def count_chunk(self, asc_local, create_new: int = 1) -> int:
+        """asc_local: this rank's contiguous slice of the chunk (ASCII, any non-ACGTU byte separates reads)."""
+        ev, counts = self.b.extract_route(self.b.to_device(asc_local))
+        if self.world == 1:
+            recv = ev
+        else:
+            dev = ev.device
+            c_out = torch.tensor(counts, dtype=torch.int64, device=dev)
+            c_in = torch.empty_like(c_out)
+            dist.all_to_all_single(c_in, c_out, group=self.group)          # tiny count exchange
+            in_splits = [int(x) for x in c_in.tolist()]
+            recv = torch.empty(sum(in_splits), dtype=torch.int64, device=dev)
+            dist.all_to_all_single(recv, ev.contiguous(), output_split_sizes=in_splits, input_split_sizes=counts,
+                                   group=self.group)                        # the one payload all-to-all of the chunk
+        n = self.b.count_events(recv, create_new)
+        self.events += n
+        return n
+
+    def second_pass_prepare(self):
+        """main.c:55-56 on every shard."""
+        self.b.destroy_bf()
+        self.b.clear()
+
+    def shrink(self, lo=2, hi=1023):
+        self.b.shrink(lo, hi)
+
+    def total_distinct(self) -> int:
+        t = torch.tensor([self.b.tot()], dtype=torch.int64, device=self._dev())
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+        return int(t[0])
+
+    def _dev(self):
+        return getattr(self.b, "device", torch.device("cpu"))
+
+    def dump_bytes(self) -> bytes | None:
+        """The whole .yak image on rank 0 (rank-ordered concatenation of the shard images)."""
+        part = self.b.dump_shard(self.rank == 0)
+        if self.world == 1:
+            return part
+        parts = [None] * self.world if self.rank == 0 else None
+        dist.gather_object(part, parts, dst=0, group=self.group)
+        return b"".join(parts) if self.rank == 0 else None
+
+
+def count_file_sharded(fn: str, backend, records_per_chunk: int = 1 << 20, k: int = 31, two_pass: bool = False,
+                       fn2: str | None = None, group=None) -> ShardedCounter:
+    """`yak count` of one shared file on all ranks: every rank walks the file and keeps its slice."""
+    from . import capi
+    L = capi.lib()
+    sc = ShardedCounter(backend, group)
+    G, r = sc.world, sc.rank
+    per = max(1, records_per_chunk // G)
+
+    def one_pass(path, create_new):
+        rd = L.yakb_fastx_open(path.encode())
+        if not rd:
+            raise FileNotFoundError(path)
+        cap = 1 << 24
+        buf = np.empty(cap, dtype=np.uint8)
+        nb, ns = C.c_uint64(), C.c_int64()
+        while True:
+            while True:
+                used = L.yakb_fastx_read_slice(rd, r * per, per, k, buf.ctypes.data, cap, C.byref(nb), C.byref(ns))
+                if used != -1:
+                    break
+                raise RuntimeError("record slice larger than the staging buffer; raise records_per_chunk granularity")
+            tail = L.yakb_fastx_read_slice(rd, (G - 1 - r) * per, 0, k, buf.ctypes.data + nb.value, 0, C.byref(C.c_uint64()), C.byref(C.c_int64()))
+            sc.count_chunk(buf[:nb.value].copy(), create_new)
+            # every rank must take part in every all-to-all: stop only when ALL ranks ran dry
+            more = torch.tensor([1 if used + max(tail, 0) == G * per else 0], dtype=torch.int64, device=sc._dev())
+            if G > 1:
+                dist.all_reduce(more, op=dist.ReduceOp.MAX, group=group)
+            if int(more[0]) == 0:
+                break
+        L.yakb_fastx_close(rd)
+
+    one_pass(fn, 1)
+    if two_pass:
+        sc.second_pass_prepare()
+        one_pass(fn2 or fn, 0)
+        sc.shrink(2, 1023)
+    return sc
