@@ -71,6 +71,10 @@ uint64_t yakb_kernel_launches(void);
 void *yakb_fastx_open(const char *fn);
 int64_t yakb_fastx_next(void *reader, const char **seq, const char **name);
 void yakb_fastx_close(void *reader);
+/* bulk form used by yak_count: append whole records (length >= min_len) as "SEQ\n" until `target`
+ * bytes; returns bytes appended; *done = input exhausted; *need != 0: grow buf to that size */
+int64_t yakb_fastx_fill(void *reader, char *buf, uint64_t cap, uint64_t target, int min_len,
+                        int64_t *n_seq, int *done, uint64_t *need);
 /* skip n_skip records, then append up to n_take records (those of length >= min_len) to buf as
  * "SEQ\n"; returns the records consumed (-1: buf too small).  Lets each rank of a multi-GPU job
  * take its contiguous slice of every chunk of one shared input file. */

@@ -258,3 +258,52 @@ def test_qv_solver_matches_reference_output():
               "QV\t%.3f\t%.3f" % (qs.qv_raw, qs.qv)]
     want = [ln for ln in ref if ln[:2] in ("CT", "FR", "ER", "CV", "QV")]
     assert lines == want
+
+
+def _fill_all(path, cap, target, min_len):
+    """Drive yakb_fastx_fill the way yak_count does; returns the concatenated 'SEQ\\n' stream."""
+    from yak_b200 import capi
+    L = capi.lib()
+    r = L.yakb_fastx_open(path.encode())
+    out, nseq = bytearray(), 0
+    buf = C.create_string_buffer(cap)
+    while True:
+        ns, done, need = C.c_int64(), C.c_int(), C.c_uint64()
+        n = L.yakb_fastx_fill(r, buf, cap, target, min_len, C.byref(ns), C.byref(done), C.byref(need))
+        if need.value:
+            cap = need.value + 7
+            buf = C.create_string_buffer(cap)
+            continue
+        out += buf.raw[:n]
+        nseq += ns.value
+        if done.value:
+            break
+    L.yakb_fastx_close(r)
+    return bytes(out), nseq
+
+
+@pytest.mark.parametrize("cap,target", [(1 << 20, 1 << 20), (4096, 1000), (700, 100), (64, 64)])
+def test_bulk_fill_equals_record_reader(cap, target):
+    import gzip
+    import test_gpu_parity as T
+    fn = T._edge_file(os.path.join(util.TMP, "yakb_edge_fill.fa"))
+    for min_len in (0, 31):
+        recs = [r for r in _records_oracle(fn) if not isinstance(r, int)]
+        want = b"".join(s + b"\n" for _, s in recs if len(s) >= min_len)
+        got, nseq = _fill_all(fn, cap, target, min_len)
+        assert got == want
+        assert nseq == sum(1 for _, s in recs if len(s) >= min_len)
+    gz = fn + ".gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(open(fn, "rb").read())
+    assert _fill_all(gz, cap, target, 0)[0] == _fill_all(fn, cap, target, 0)[0]
+    # FASTQ: final record without a trailing newline is valid; a short quality is dropped (kseq -2)
+    p = os.path.join(util.TMP, "yakb_tail.fq")
+    open(p, "w").write("@a\nACGTAC\n+\nIIIIII\n@b\nGGGTTT\n+\nIIIIII")
+    assert _fill_all(p, cap, target, 0)[0] == b"ACGTAC\nGGGTTT\n"
+    open(p, "w").write("@a\nACGTAC\n+\nIIIIII\n@b\nGGGTTT\n+\nIII\n@c\nAAAA\n+\nIIII\n")
+    want = b"".join(s + b"\n" for _, s in (r for r in _records_oracle(p) if not isinstance(r, int)))
+    assert _fill_all(p, cap, target, 0)[0] == want == b"ACGTAC\n"
+    big = G.input_path("reads_q")
+    want = b"".join(s + b"\n" for _, s in (r for r in _records_oracle(big) if not isinstance(r, int)))
+    assert _fill_all(big, max(cap, 4096), target, 0)[0] == want

@@ -18,6 +18,8 @@
 #include <math.h>
 #include <algorithm>
 #include <mutex>
+#include <thread>
+#include <atomic>
 #include <chrono>
 #include <sys/resource.h>
 #include <sys/time.h>
@@ -484,6 +486,18 @@ extern "C" int64_t yakb_fastx_next(void *reader, const char **seq, const char **
 	return len;
 }
 extern "C" void yakb_fastx_close(void *reader) { delete (FastxReader*)reader; }
+extern "C" int64_t yakb_fastx_fill(void *reader, char *buf, uint64_t cap, uint64_t target, int min_len, int64_t *n_seq, int *done, uint64_t *need)
+{
+	FastxReader *r = (FastxReader*)reader;
+	bool d = false;
+	size_t nd = 0;
+	int64_t ns = 0;
+	size_t n = r->fill((uint8_t*)buf, cap, target, min_len, &ns, &d, &nd);
+	if (n_seq) *n_seq = ns;
+	if (done) *done = d;
+	if (need) *need = nd;
+	return (int64_t)n;
+}
 
 // Skip n_skip records, then append up to n_take records of length >= min_len to buf as "SEQ\n".
 // Returns the number of records CONSUMED (skipped + taken + dropped short ones counted among the taken);
@@ -537,44 +551,43 @@ extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *
 	std::lock_guard<std::mutex> lk(b->mu);
 	const int create_new = h0 == 0;
 	const uint64_t cap = batch_bases(opt->chunk_size);
-	std::vector<uint8_t> carry; // a record that did not fit the previous batch
-	bool done = false;
-	int64_t len;
 	size_t need = cap + (cap >> 4) + 4096;
-	if (b->pinned_cap < need) {
+	auto ensure_pinned = [&](size_t bytes) {
+		if (b->pinned_cap >= bytes) return;
 		for (int i = 0; i < 2; ++i) { if (b->pinned[i]) cudaFreeHost(b->pinned[i]); b->pinned[i] = nullptr; }
-		YAKB_CUDA(cudaMallocHost(&b->pinned[0], need));
-		b->pinned_cap = need;
-	}
-	while (!done) {
-		uint8_t *buf = b->pinned[0];
-		uint64_t n = 0;
-		int n_seq = 0;
-		if (!carry.empty()) {
-			if (carry.size() + 1 > b->pinned_cap) { // a single record larger than the batch: grow
-				cudaFreeHost(b->pinned[0]);
-				b->pinned_cap = carry.size() + (carry.size() >> 3) + 4096;
-				YAKB_CUDA(cudaMallocHost(&b->pinned[0], b->pinned_cap));
-				buf = b->pinned[0];
-			}
-			memcpy(buf, carry.data(), carry.size());
-			n = carry.size(); buf[n++] = '\n'; ++n_seq;
-			carry.clear();
+		for (int i = 0; i < 2; ++i) YAKB_CUDA(cudaMallocHost(&b->pinned[i], bytes));
+		b->pinned_cap = bytes;
+	};
+	ensure_pinned(need);
+	// producer thread parses the next batch into one pinned buffer while the device works on the other
+	struct Batch { size_t n = 0; int64_t n_seq = 0; bool done = false; size_t need = 0; };
+	Batch batch[2];
+	auto parse = [&](int slot) {
+		Batch &t = batch[slot];
+		t = Batch();
+		t.n = rd.fill(b->pinned[slot], b->pinned_cap, cap, opt->k, &t.n_seq, &t.done, &t.need);
+	};
+	int slot = 0;
+	parse(0);
+	for (;;) {
+		Batch cur = batch[slot];
+		if (cur.need) { // one record larger than the staging buffers: grow them and parse again
+			ensure_pinned(cur.need + (cur.need >> 3) + 4096);
+			parse(slot);
+			continue;
 		}
-		while (n < cap) {
-			len = rd.next();
-			if (len < 0) { done = true; break; }
-			if (len < opt->k) continue;
-			if (n + len + 1 > b->pinned_cap || n + (uint64_t)len + 1 > 0x7FFFFE00ull) { carry.assign(rd.seq().begin(), rd.seq().end()); break; }
-			memcpy(buf + n, rd.seq().data(), len);
-			n += len; buf[n++] = '\n'; ++n_seq;
+		std::thread producer;
+		if (!cur.done) producer = std::thread(parse, slot ^ 1);
+		if (cur.n) {
+			uint8_t *d = b->d_in.as<uint8_t>(cur.n + 64);
+			YAKB_CUDA(cudaMemcpyAsync(d, b->pinned[slot], cur.n, cudaMemcpyHostToDevice, b->eng->stream));
+			run_ascii_dev(b, d, cur.n, create_new, nullptr);
+			fprintf(stderr, "[M::%s::%.3f*%.2f] processed %d sequences; %ld distinct k-mers in the hash table\n", __func__,
+			        wall_now() - g_t0, cpu_now() / (wall_now() - g_t0 + 1e-9), (int)cur.n_seq, (long)h->tot);
 		}
-		if (n == 0) continue;
-		uint8_t *d = b->d_in.as<uint8_t>(n + 64);
-		YAKB_CUDA(cudaMemcpyAsync(d, buf, n, cudaMemcpyHostToDevice, b->eng->stream));
-		run_ascii_dev(b, d, n, create_new, nullptr);
-		fprintf(stderr, "[M::%s::%.3f*%.2f] processed %d sequences; %ld distinct k-mers in the hash table\n", __func__,
-		        wall_now() - g_t0, cpu_now() / (wall_now() - g_t0 + 1e-9), n_seq, (long)h->tot);
+		if (producer.joinable()) producer.join();
+		if (cur.done) break;
+		slot ^= 1;
 	}
 	return h;
 	GUARD_END(0)

@@ -806,7 +806,7 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 		YAKB_CUDA(cudaMemcpyAsync(&need, pend + P, 4, cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaStreamSynchronize(stream));
 		if ((double)need > load_limit * cap) {
-			uint64_t want = (std::max<uint64_t>((uint64_t)(need / load_limit) + 16, (uint64_t)cap + cap / 2) + 3) & ~3ull;
+			uint64_t want = (std::max<uint64_t>((uint64_t)(need / load_limit) + 16, (uint64_t)cap * 2) + 3) & ~3ull;
 			if (want > 0xFFFFFFF0ull) throw CudaError("[yakb] sub-table capacity overflow");
 			grow((uint32_t)want);
 		}

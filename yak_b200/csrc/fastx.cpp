@@ -70,6 +70,109 @@ bool FastxReader::line_(std::string &s, int64_t *count_only)
 	return got;
 }
 
+bool FastxReader::refill_()
+{
+	if (beg_ < end_) return true;
+	if (eof_) return false;
+	beg_ = 0;
+	int got = gzread(fp_, buf_.data(), (unsigned)buf_.size());
+	end_ = got > 0 ? got : 0;
+	if (end_ < (int64_t)buf_.size()) eof_ = true;
+	return end_ > 0;
+}
+
+size_t FastxReader::fill(uint8_t *dst, size_t cap, size_t target, int min_len, int64_t *n_seq, bool *done, size_t *need)
+{
+	size_t n = 0, rec_start = 0;
+	*done = false;
+	if (need) *need = 0;
+	if (target > cap) target = cap;
+	if (carry_ready_) { // the record that overflowed the previous buffer
+		if (carry_.size() + 1 > cap) { if (need) *need = carry_.size() + 1; return 0; }
+		memcpy(dst, carry_.data(), carry_.size());
+		n = carry_.size(); dst[n++] = '\n'; ++*n_seq;
+		carry_.clear(); carry_ready_ = false;
+	}
+	// close the record being parsed: keep it (terminator appended) or drop it
+	auto finish_record = [&](bool keep) {
+		if (in_carry_) {
+			if (keep && cur_len_ >= min_len) carry_ready_ = true; else carry_.clear();
+			in_carry_ = false;
+		} else if (keep && cur_len_ >= min_len) { dst[n++] = '\n'; ++*n_seq; }
+		else n = rec_start;
+	};
+	auto put = [&](const unsigned char *p, int64_t len) { // append sequence bytes of the current record
+		if (!in_carry_ && n + (size_t)len + 1 > cap) { // would not fit (1 byte kept for the terminator): move to carry_
+			carry_.assign((const char*)dst + rec_start, n - rec_start);
+			n = rec_start; in_carry_ = true;
+		}
+		if (in_carry_) carry_.append((const char*)p, len); else { memcpy(dst + n, p, len); n += len; }
+		cur_len_ += len;
+	};
+	auto drop_cr = [&]() { // kseq.h:146: one trailing CR once the accumulated length exceeds 1
+		if (cur_len_ > 1) {
+			if (in_carry_) { if (carry_.back() == '\r') { carry_.pop_back(); --cur_len_; } }
+			else if (dst[n - 1] == '\r') { --n; --cur_len_; }
+		}
+	};
+	for (;;) {
+		if (carry_ready_) break;                       // buffer is full: hand over what we have
+		if (st_ == S_FIND && n >= target) break;       // enough for this batch, stop between records
+		if (!refill_()) {                              // end of input
+			if (st_ == S_SEQ) { if (!bol_) drop_cr(); finish_record(true); } // FASTA record ended by EOF
+			else if (st_ == S_QUAL) {                    // kseq.h:224-226: EOF ends the quality; lengths must agree
+				if (!bol_ && qual_len_ > 1 && last_qual_ == '\r') --qual_len_;
+				finish_record(qual_len_ == cur_len_);
+			} else if (st_ == S_PLUS) finish_record(false); // kseq.h:222: no quality string at all
+			st_ = S_FIND; last_ = 0;
+			*done = true;
+			break;
+		}
+		const unsigned char *p = buf_.data() + beg_;
+		const int64_t avail = end_ - beg_;
+		if (st_ == S_FIND) {
+			if (last_) { st_ = S_NAME; bol_ = false; rec_start = n; cur_len_ = 0; in_carry_ = false; last_ = 0; continue; }
+			int64_t i = 0;
+			while (i < avail && p[i] != '>' && p[i] != '@') ++i;
+			beg_ += i;
+			if (i < avail) { ++beg_; st_ = S_NAME; rec_start = n; cur_len_ = 0; in_carry_ = false; }
+		} else if (st_ == S_NAME || st_ == S_PLUS) {   // skip the rest of the header / '+' line
+			const unsigned char *nl = (const unsigned char*)memchr(p, '\n', avail);
+			if (!nl) { beg_ = end_; continue; }
+			beg_ += nl - p + 1;
+			if (st_ == S_NAME) { st_ = S_SEQ; bol_ = true; } else { st_ = S_QUAL; qual_len_ = 0; qual_lines_ = 0; bol_ = true; }
+		} else if (st_ == S_SEQ) {
+			if (bol_) {
+				const unsigned char c = p[0];
+				if (c == '\n') { ++beg_; continue; }
+				if (c == '>' || c == '@') { ++beg_; finish_record(true); last_ = c; st_ = S_FIND; continue; }
+				if (c == '+') { ++beg_; st_ = S_PLUS; continue; }
+				bol_ = false;
+			}
+			const unsigned char *nl = (const unsigned char*)memchr(p, '\n', avail);
+			const int64_t len = nl ? nl - p : avail;
+			put(p, len);
+			beg_ += len + (nl ? 1 : 0);
+			if (nl) { drop_cr(); bol_ = true; }
+		} else { // S_QUAL: only lengths matter
+			if (bol_ && qual_lines_ > 0 && qual_len_ >= cur_len_) { // kseq.h:224: at least one line, stop once long enough
+				const bool ok = qual_len_ == cur_len_;
+				finish_record(ok);
+				st_ = S_FIND; last_ = 0;
+				if (!ok) { eof_ = true; beg_ = end_; *done = true; break; } // kseq's -2: the caller's loop ends
+				continue;
+			}
+			const unsigned char *nl = (const unsigned char*)memchr(p, '\n', avail);
+			const int64_t len = nl ? nl - p : avail;
+			if (len > 0) { qual_len_ += len; last_qual_ = p[len - 1]; }
+			bol_ = false;
+			beg_ += len + (nl ? 1 : 0);
+			if (nl) { if (qual_len_ > 1 && last_qual_ == '\r' && len > 0) --qual_len_; bol_ = true; ++qual_lines_; }
+		}
+	}
+	return n;
+}
+
 int64_t FastxReader::next()
 {
 	int c;

@@ -19,6 +19,13 @@ public:
 	int64_t next();
 	const std::string &seq() const { return seq_; }
 	const std::string &name() const { return name_; }
+	// Bulk path of yak_count: append whole records (those with length >= min_len) to dst as
+	// "SEQ\n" until at least `target` bytes are in, dst is full, or the input ends.  Sequence lines
+	// go from the block buffer straight into dst.  Returns bytes appended; *n_seq += records kept;
+	// *done = input exhausted (or a malformed FASTQ record stopped the parse, like kseq's -2).
+	// A record that does not fit is carried over to the next call; if it can never fit, *need is
+	// set to the dst size required.
+	size_t fill(uint8_t *dst, size_t cap, size_t target, int min_len, int64_t *n_seq, bool *done, size_t *need);
 
 private:
 	int getc_();
@@ -30,6 +37,14 @@ private:
 	bool eof_ = false;
 	int last_ = 0, last_qual_ = 0;
 	std::string seq_, name_;
+	// fill() state machine
+	bool refill_();
+	enum { S_FIND, S_NAME, S_SEQ, S_PLUS, S_QUAL } st_ = S_FIND;
+	bool bol_ = true;          // at the beginning of a line
+	int64_t cur_len_ = 0, qual_len_ = 0, qual_lines_ = 0;
+	std::string carry_;        // a record that did not fit the caller's buffer
+	bool carry_ready_ = false; // carry_ holds a COMPLETE record waiting for the next fill()
+	bool in_carry_ = false;    // the current record is being collected in carry_
 };
 
 } // namespace yakb
