@@ -6,7 +6,10 @@ uniform genome (e=0.005, 1 % reads with an N), pass 1 of `yak count` (bloom + in
 synthetic stream as yak_b200/synth.py generated on the device.  A *step* is one batch of reads
 (--chunk-reads, default 2 M reads = 300 Mbp > L2) through the whole per-chunk path
 (pack -> fused extract+probe -> ordered bloom/insert of pending events -> journal).  Steps are
-consecutive batches from the start of the job; the table, bloom and journal persist across steps.
+consecutive batches from the start of the job; the table, bloom and journal persist across steps
+(the default 3 + 60 steps walk coverage 0 -> 6x of the 30x job: table growth and rehash included).
+Each step is bracketed by its own pair of CUDA events; the step's input batch is generated on the
+device just before it, outside the timed region (max over ranks of the summed step times).
 
   value     events/s with the batch's ASCII bases already resident in HBM (CUDA events on the
             library's stream around exactly K steps, max over ranks)
@@ -187,7 +190,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome", type=int, default=3_000_000_000)
@@ -220,14 +223,15 @@ def main():
     genome2 = torch.empty((G + 31) // 32 + 1, dtype=torch.int64, device="cuda")
     cur = torch.cuda.current_stream().cuda_stream
     lib.yakb_synth_genome_dev(SEED_G, G, genome2.data_ptr(), cur)
-    # every rank takes its own contiguous slice of the read stream (weak scaling: per-GPU work fixed)
-    bufs = []
-    for i in range(W + KS):
-        b = torch.empty(nr * rec, dtype=torch.uint8, device="cuda")
-        first = (rank * (W + KS) + i) * nr
-        lib.yakb_synth_reads_dev(genome2.data_ptr(), G, SEED_R, first, nr, L, ERR, NPCT, 0, b.data_ptr(), cur)
-        bufs.append(b)
-    torch.cuda.synchronize()
+    # every step takes the next batch of the read stream; with N ranks, step i is the N consecutive
+    # slices i*N .. i*N+N-1, one per rank (weak scaling: per-GPU work fixed).  The batch is generated
+    # on the device before its step and is not part of the timed region.
+    buf = torch.empty(nr * rec, dtype=torch.uint8, device="cuda")
+
+    def make_input(i):
+        first = (i * world + rank) * nr
+        lib.yakb_synth_reads_dev(genome2.data_ptr(), G, SEED_R, first, nr, L, ERR, NPCT, 0, buf.data_ptr(), cur)
+        torch.cuda.synchronize()
 
     stats = (C.c_uint64 * 4)()
     ev_total = 0
@@ -238,7 +242,7 @@ def main():
         stream = torch.cuda.ExternalStream(lib.yakb_ch_stream(h))
 
         def step(i):
-            rc = lib.yakb_count_ascii_dev(h, bufs[i].data_ptr(), nr * rec, 1, stats)
+            rc = lib.yakb_count_ascii_dev(h, buf.data_ptr(), nr * rec, 1, stats)
             assert rc == 0
             return list(stats)
     else:
@@ -250,9 +254,10 @@ def main():
         stream = torch.cuda.current_stream()
 
         def step(i):
-            n = sc.count_chunk(bufs[i], 1)
+            n = sc.count_chunk(buf, 1)
             return [n, int(be.stats[1]), int(be.stats[2]), int(be.stats[3])]
     for i in range(W):
+        make_input(i)
         step(i)
     torch.cuda.synchronize()
     if world > 1:
@@ -262,19 +267,21 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record(stream)
+    ms = 0.0
     for i in range(W, W + KS):
-        t_s = time.time()
-        st = step(i)
+        make_input(i)                                   # untimed
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        st = step(i)                                    # exactly one step between the two events
+        e1.record(stream)
+        torch.cuda.synchronize()
+        dt = e0.elapsed_time(e1)
+        ms += dt
         ev_total += st[0]
-        per_step.append(st + [round((time.time() - t_s) * 1e3, 3)])
-    e1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
+        per_step.append(st + [round(dt, 3)])
     clk = clocks.stop() if rank == 0 else None
     launches = lib.yakb_kernel_launches() - launches0
     pj = C.create_string_buffer(1 << 16)
@@ -294,7 +301,7 @@ def main():
         lib.yak_ch_destroy(h)
     else:
         be.close()
-    del bufs
+    del buf
     torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
@@ -308,7 +315,7 @@ def main():
         "k1_fused": (0.31 + 16.0) * ev_total,           # read 2-bit bases; slot read + counter write per event
         "k1_array": (8.0 + 16.0) * ev_total,            # read the routed event; slot read + counter write
         "group_insert": (8.0 + 128.0 + 16.0) * n_pending,  # sorted event + bloom block RMW + slot read/write
-        "group_sort(cub)": 2 * 12.0 * n_pending,
+        "group_sort": 4 * 2 * 12.0 * n_pending,      # 4 passes, read + write of a 12-byte record
         "compact": 8.0 * n_pending,
         "pack_ascii": 1.375 * nr * rec * KS,
     }

@@ -77,6 +77,12 @@ void yak_qopt_init(yak_qopt_t *o) // qv.c:137-144
 
 static double wall_now() { struct timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec + tv.tv_usec * 1e-6; }
 static double g_t0 = wall_now();
+static bool timing_on() { static int v = -1; if (v < 0) { const char *e = getenv("YAKB_TIMING"); v = e && atoi(e) > 0; } return v != 0; }
+struct StageTimer {
+	const char *name; double t0;
+	StageTimer(const char *n) : name(n), t0(wall_now()) {}
+	~StageTimer() { if (timing_on()) fprintf(stderr, "[T::%s] %.3f s\n", name, wall_now() - t0); }
+};
 static double cpu_now() { struct rusage r; getrusage(RUSAGE_SELF, &r); return r.ru_utime.tv_sec + r.ru_stime.tv_sec + 1e-6 * (r.ru_utime.tv_usec + r.ru_stime.tv_usec); }
 
 // ------------------------------------------------------------------ yak_ch_*
@@ -103,6 +109,7 @@ static void attach_handles(ChBox *b)
 static yak_ch_t *ch_init_shard(int k, int pre, int n_hash, int n_shift, int rank, int world)
 {
 	GUARD_BEGIN
+	StageTimer tm("yak_ch_init");
 	if (pre < YAK_COUNTER_BITS) return 0;
 	Engine *e = Engine::create(k, pre, n_hash, n_shift, rank, world);
 	if (!e) return 0;
@@ -137,6 +144,7 @@ extern "C" void yak_ch_destroy_bf(yak_ch_t *h) // htab.c:31-39
 extern "C" void yak_ch_destroy(yak_ch_t *h) // htab.c:41-49
 {
 	if (h == 0) return;
+	StageTimer tm("yak_ch_destroy");
 	ChBox *b = box_of(h);
 	delete b->eng;
 	free(b->pub.h);
@@ -226,6 +234,7 @@ extern "C" void yak_ch_shrink(yak_ch_t *h, int min, int max, int n_thread) // ht
 {
 	GUARD_BEGIN
 	(void)n_thread;
+	StageTimer tm("yak_ch_shrink");
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
 	b->eng->shrink(min, max);
@@ -304,6 +313,7 @@ extern "C" int yak_ch_dump(const yak_ch_t *h, const char *fn)
 	GUARD_BEGIN
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
+	StageTimer tm("yak_ch_dump");
 	if (b->eng->lw) { fprintf(stderr, "[yakb] ERROR: yak_ch_dump on one shard of a multi-GPU table; use yakb_ch_dump_shard_mem\n"); return -1; }
 	FILE *fp = strcmp(fn, "-") ? fopen(fn, "wb") : stdout;
 	if (fp == 0) return -1;
@@ -419,7 +429,7 @@ extern "C" int yakb_count_events_dev(yak_ch_t *h, const uint64_t *d_ev, uint64_t
 	GUARD_END(-1)
 }
 
-static DBuf g_route_scratch[8];
+static DBuf g_route_scratch[13];
 static std::mutex g_route_mu;
 extern "C" int yakb_extract_route_dev(const void *d_asc, uint64_t n, int k, int pre, int world, uint64_t *d_out, uint64_t *counts, void *cuda_stream)
 {
@@ -526,9 +536,11 @@ extern "C" int64_t yakb_fastx_read_slice(void *reader, int64_t n_skip, int64_t n
 
 // ------------------------------------------------------------------ yak_count / yak_recount
 
+// bases per device batch on the host-fed paths.  Results do not depend on it; 64 M
+// keeps the two pinned staging buffers cheap to allocate while each batch still fills the GPU.
 static uint64_t batch_bases(int64_t chunk_size)
 {
-	uint64_t b = 256ull << 20;
+	uint64_t b = 64ull << 20;
 	const char *e = getenv("YAKB_BATCH");
 	if (e && atoll(e) > 0) b = (uint64_t)atoll(e);
 	if ((uint64_t)chunk_size > b) b = (uint64_t)chunk_size;
@@ -541,6 +553,7 @@ static uint64_t batch_bases(int64_t chunk_size)
 extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *h0)
 {
 	GUARD_BEGIN
+	StageTimer tm("yak_count");
 	FastxReader rd;
 	if (!rd.open(fn)) return 0;
 	yak_ch_t *h = h0;
@@ -558,7 +571,7 @@ extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *
 		for (int i = 0; i < 2; ++i) YAKB_CUDA(cudaMallocHost(&b->pinned[i], bytes));
 		b->pinned_cap = bytes;
 	};
-	ensure_pinned(need);
+	{ StageTimer tp("yak_count:pinned"); ensure_pinned(need); }
 	// producer thread parses the next batch into one pinned buffer while the device works on the other
 	struct Batch { size_t n = 0; int64_t n_seq = 0; bool done = false; size_t need = 0; };
 	Batch batch[2];

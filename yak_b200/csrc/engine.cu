@@ -11,16 +11,21 @@
 //                   (bbf.c:25-42), first-put detection, insert + counter++    (htab.c:62-71)
 //   journal         new keys ordered by (sub-table, first-put time) appended as a segment
 // Pass 2 / lookups (create_new=0) are k1_fused alone.
-// v1 uses cub for the scans/sorts between our kernels; see DESIGN.md for what replaces them.
+// The scans, the stable radix sorts and the ordered compactions between these kernels are ours too
+// (radix.cu); no library kernels run on this path.
 #include "engine.cuh"
 #include "yakb_dev.cuh"
 #include "kernels.cuh"
 #include "extras.cuh"
-#include <cub/cub.cuh>
+#include "radix.cuh"
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <map>
+#include <string>
 #include <atomic>
+#include <time.h>
+#include <stdlib.h>
 
 namespace yakb {
 
@@ -52,8 +57,9 @@ static std::atomic<uint64_t> g_launches{0};
 uint64_t Engine::launches() { return g_launches.load(); }
 void Engine::note_launch(int n) { g_launches += n; }
 
+static double wall_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
+
 // ---- per-kernel timing (off unless enabled)
-#include <map>
 static bool g_prof_on = false;
 struct ProfPair { const char *name; cudaEvent_t a, b; };
 static std::vector<ProfPair> g_prof_open, g_prof_done;
@@ -138,68 +144,118 @@ __global__ void __launch_bounds__(256, 3) k1_fused(const uint64_t *__restrict__ 
                                                 uint32_t *glob_lput, int smem_lp, unsigned long long *stats)
 {
 	extern __shared__ uint32_t s_lp[];
-	__shared__ uint32_t s_cnt;
-	__shared__ unsigned long long s_ev;
+	// the packed read batch is staged tile by tile in shared memory with bulk async copies
+	// (cp.async.bulk -> UBLKCP) two tiles deep: 2 halo + 256 words of bases, 4 halo + 256 mask words
+	__shared__ alignas(128) uint64_t s_w2[2][264];
+	__shared__ alignas(128) uint32_t s_wm[2][264];
+	__shared__ alignas(8) uint64_t s_full[2], s_empty[2];
 	const uint32_t P = Pmask + 1;
 	if (smem_lp) for (uint32_t i = threadIdx.x; i < P; i += 256) s_lp[i] = 0;
-	if (threadIdx.x == 0) s_ev = 0;
+	if (threadIdx.x == 0) {
+		mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+		mbar_init(&s_empty[0], 8); mbar_init(&s_empty[1], 8);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
 	__syncthreads();
 	const uint64_t ntiles = (nwords + 255) / 256;
+	const uint32_t nbk = cap / YAKB_BUCKET;
+	const int lane = threadIdx.x & 31;
 	uint32_t my_ev = 0;
-	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-		if (threadIdx.x == 0) s_cnt = 0;
-		__syncthreads();
+	auto stage_tile = [&](uint32_t it, uint64_t tile) { // thread 0 only
+		const int sidx = it & 1;
+		if (it >= 2) mbar_wait(&s_empty[sidx], ((it >> 1) - 1) & 1); // all 8 warps are done with the previous use
+		mbar_expect_tx(&s_full[sidx], 258 * 8 + 260 * 4);
+		bulk_g2s(&s_w2[sidx][0], w2 + (int64_t)tile * 256 - 2, 258 * 8, &s_full[sidx]);
+		bulk_g2s(&s_wm[sidx][0], wm + (int64_t)tile * 256 - 4, 260 * 4, &s_full[sidx]);
+	};
+	if (threadIdx.x == 0 && blockIdx.x < ntiles) stage_tile(0, blockIdx.x);
+	uint32_t it = 0;
+	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) { // no block barrier inside: warps run free
+		if (threadIdx.x == 0 && tile + gridDim.x < ntiles) stage_tile(it + 1, tile + gridDim.x);
+		__syncwarp();
+		const int sidx = it & 1;
+		mbar_wait(&s_full[sidx], (it >> 1) & 1);
 		const uint64_t W = tile * 256 + threadIdx.x;
 		const bool live = W < nwords; // dead lanes walk along with no events so the warp stays whole
-		{
-			uint32_t pend = 0;
-			const uint32_t nbk = cap / YAKB_BUCKET;
-			Roller<LONGK> ro;
-			if (live) ro.init(w2, wm, W, k);
+		uint32_t pend = 0;
+		Roller<LONGK> ro;
+		if (live) ro.init(&s_w2[sidx][2], &s_wm[sidx][4], (int64_t)threadIdx.x, k);
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&s_empty[sidx]); // the roller keeps what it needs in registers
+#pragma unroll 1
+		for (int b = 0; b < 32; b += 4) { // 4 positions at a time: 4 independent home-bucket loads in flight
+			uint64_t v[4];
+			Bucket bk[4];
+			uint32_t bi[4], vm = 0;
 #pragma unroll
-			for (int b = 0; b < 32; b += 4) { // 4 positions at a time: 4 independent home-bucket loads in flight
-				uint64_t v[4];
-				Bucket bk[4];
-				uint32_t bi[4], vm = 0;
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					bi[j] = 0; v[j] = 0;
-					if (live && ro.step(b + j, v[j]) && ((uint32_t)(v[j] >> own.shift) & own.mask) == own.rank) {
-						vm |= 1u << j;
-						if (cap) {
-							bi[j] = tab_home(v[j] >> pre, nbk);
-							bk[j] = load_bucket(slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET);
-						}
-					}
-				}
-				__syncwarp();
-				my_ev += __popc(vm);
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					const bool valid = vm >> j & 1;
-					const uint32_t s = (uint32_t)v[j] & Pmask;
-					const int found = cap ? probe_inc_warp(slots + (uint64_t)s * cap, nbk, v[j] >> pre, bi[j], bk[j], valid) : 0;
-					if (create_new && valid) {
-						if (!found) pend |= 1u << (b + j);
-						else {
-							uint32_t t = (uint32_t)(W * 32 + b + j) + 1;
-							if (smem_lp) atomicMax(&s_lp[s], t);
-							else atomicMax(&glob_lput[s], t);
-						}
+			for (int j = 0; j < 4; ++j) {
+				bi[j] = 0; v[j] = 0;
+				if (live && ro.step(b + j, v[j]) && ((uint32_t)(v[j] >> own.shift) & own.mask) == own.rank) {
+					vm |= 1u << j;
+					if (cap) {
+						bi[j] = tab_home(v[j] >> pre, nbk);
+						bk[j] = load_bucket(slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET);
 					}
 				}
 			}
-			if (create_new && live) {
-				flags[W] = pend;
-				if (pend) atomicAdd(&s_cnt, __popc(pend));
+			__syncwarp();
+			my_ev += __popc(vm);
+			if (cap == 0) { pend |= vm << b; continue; }
+			// first look at the 4 home buckets: issue every counter CAS before waiting for any result
+			uint64_t expect[4], prev[4];
+			uint32_t todo = 0, hit = 0; // todo: needs the slow path (next bucket / lost CAS); hit: found
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				expect[j] = prev[j] = 0;
+				if (vm >> j & 1) {
+					int f, m = bucket_match(bk[j], v[j] >> pre, &f);
+					if (m >= 0) {
+						const uint64_t c = bucket_get(bk[j], m);
+						hit |= 1u << j;
+						if ((c & YAKB_MAX_COUNT) != YAKB_MAX_COUNT) {
+							uint64_t *q = slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET + m;
+							expect[j] = c;
+							prev[j] = atomicCAS((unsigned long long*)q, (unsigned long long)c, (unsigned long long)(c + 1));
+						}
+					} else if (f < 0) todo |= 1u << j; // home bucket full without the key: keep probing
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < 4; ++j) if (prev[j] != expect[j]) { todo |= 1u << j; hit &= ~(1u << j); } // lost a race: redo
+			if (__any_sync(0xffffffffu, todo != 0)) {
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const bool redo = todo >> j & 1;
+					if (__any_sync(0xffffffffu, redo)) {
+						uint64_t *reg = slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap;
+						Bucket bb = bk[j];
+						if (redo && prev[j] != expect[j]) bb = load_bucket(reg + (uint64_t)bi[j] * YAKB_BUCKET);
+						if (probe_inc_warp(reg, nbk, v[j] >> pre, bi[j], bb, redo)) hit |= 1u << j;
+					}
+				}
+			}
+			if (create_new) {
+				pend |= (vm & ~hit) << b;
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+					if (hit >> j & 1) {
+						const uint32_t s = (uint32_t)v[j] & Pmask, t = (uint32_t)(W * 32 + b + j) + 1;
+						if (smem_lp) atomicMax(&s_lp[s], t); else atomicMax(&glob_lput[s], t);
+					}
 			}
 		}
-		__syncthreads();
-		if (threadIdx.x == 0 && create_new) tilecnt[tile] = s_cnt;
+		if (create_new) {
+			if (live) flags[W] = pend;
+			uint32_t c = __popc(pend);
+#pragma unroll
+			for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+			if (lane == 0 && c) atomicAdd(&tilecnt[tile], c); // tilecnt zeroed by the host before the launch
+		}
 	}
-	if (my_ev) atomicAdd(&s_ev, (unsigned long long)my_ev);
+#pragma unroll
+	for (int d = 16; d; d >>= 1) my_ev += __shfl_xor_sync(0xffffffffu, my_ev, d);
+	if (lane == 0 && my_ev) atomicAdd(&stats[0], (unsigned long long)my_ev);
 	__syncthreads();
-	if (threadIdx.x == 0 && s_ev) atomicAdd(&stats[0], s_ev);
 	if (smem_lp && create_new)
 		for (uint32_t i = threadIdx.x; i < P; i += 256) if (s_lp[i]) atomicMax(&glob_lput[i], s_lp[i]);
 }
@@ -323,8 +379,6 @@ __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__
 	const uint64_t gmask = G >= 64 ? ~0ull : (1ull << G) - 1;
 	const uint64_t gk = sv[i] & gmask;
 	if (i > 0 && (sv[i - 1] & gmask) == gk) return;
-	uint32_t blk[16];
-	int have_blk = 0, dirty = 0;
 	// block address: the group key with the (constant) owner bits of a shard squeezed out
 	const uint64_t baddr = lw ? ((gk >> pre) << (pre - lw)) | (gk & Pmask) : gk;
 	for (uint64_t e = i; e < n; ++e) {
@@ -334,25 +388,40 @@ __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__
 		const uint32_t s = (uint32_t)v & Pmask;
 		const uint64_t x = v >> pre;
 		int put = 1;
-		if (bloom32) { // bbf.c:25-42 on the 64-byte block this group owns (held in registers)
-			if (!have_blk) {
-				const uint4 *q = (const uint4*)(bloom32 + baddr * 16);
-				uint4 a0 = __ldcg(q), a1 = __ldcg(q + 1), a2 = __ldcg(q + 2), a3 = __ldcg(q + 3);
-				blk[0] = a0.x; blk[1] = a0.y; blk[2] = a0.z; blk[3] = a0.w; blk[4] = a1.x; blk[5] = a1.y; blk[6] = a1.z; blk[7] = a1.w;
-				blk[8] = a2.x; blk[9] = a2.y; blk[10] = a2.z; blk[11] = a2.w; blk[12] = a3.x; blk[13] = a3.y; blk[14] = a3.z; blk[15] = a3.w;
-				have_blk = 1;
-			}
-			uint32_t h1 = (uint32_t)(x >> nb) & 511, h2 = (uint32_t)(x >> sub_shift) & 511, z;
-			int c = 0;
+		if (bloom32) { // bbf.c:25-42 on the 64-byte block this group owns
+			uint32_t *blk = bloom32 + baddr * 16;
+			uint32_t h1 = (uint32_t)(x >> nb) & 511, h2 = (uint32_t)(x >> sub_shift) & 511;
 			if ((h2 & 31) == 0) h2 = (h2 + 1) & 511;
-			z = h1;
-			for (int t = 0; t < n_hash; ++t, z = (z + h2) & 511) {
-				const uint32_t w = z >> 5, m = 1u << (z & 31);
+			int c = 0;
+			if (n_hash <= 8) {
+				// the n_hash bit positions are distinct (h2 is not a multiple of 32), so the tests are
+				// independent: fetch the words first, then decide, then write back the changed words
+				uint32_t w[8], m[8], old[8];
 #pragma unroll
-				for (int i = 0; i < 16; ++i) { // compile-time register index, run-time predicate
-					const bool hit = w == (uint32_t)i;
-					c += hit && (blk[i] & m);
-					if (hit && !(blk[i] & m)) { blk[i] |= m; dirty = 1; }
+				for (int t = 0; t < 8; ++t)
+					if (t < n_hash) {
+						const uint32_t z = (h1 + t * h2) & 511;
+						w[t] = z >> 5; m[t] = 1u << (z & 31);
+						old[t] = __ldcg(&blk[w[t]]);
+					}
+#pragma unroll
+				for (int t = 0; t < 8; ++t) if (t < n_hash) c += (old[t] & m[t]) != 0;
+				if (c != n_hash) {
+#pragma unroll
+					for (int t = 0; t < 8; ++t)
+						if (t < n_hash) {
+							uint32_t nw = old[t];
+#pragma unroll
+							for (int u = 0; u < 8; ++u) if (u < n_hash && w[u] == w[t]) nw |= m[u];
+							if (nw != old[t]) __stcg(&blk[w[t]], nw);
+						}
+				}
+			} else {
+				uint32_t z = h1;
+				for (int t = 0; t < n_hash; ++t, z = (z + h2) & 511) {
+					const uint32_t ww = __ldcg(&blk[z >> 5]), mm = 1u << (z & 31);
+					c += (ww & mm) != 0;
+					if (!(ww & mm)) __stcg(&blk[z >> 5], ww | mm);
 				}
 			}
 			put = c == n_hash;
@@ -364,13 +433,6 @@ __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__
 			else { slot_inc(slot, cur, 1); flag = 1; }
 		}
 		pflag[j] = flag;
-	}
-	if (dirty) {
-		uint4 *q = (uint4*)(bloom32 + baddr * 16);
-		__stcg(q, make_uint4(blk[0], blk[1], blk[2], blk[3]));
-		__stcg(q + 1, make_uint4(blk[4], blk[5], blk[6], blk[7]));
-		__stcg(q + 2, make_uint4(blk[8], blk[9], blk[10], blk[11]));
-		__stcg(q + 3, make_uint4(blk[12], blk[13], blk[14], blk[15]));
 	}
 }
 
@@ -622,6 +684,8 @@ Engine *Engine::create(int k, int pre, int n_hash, int n_shift, int rank, int wo
 		fprintf(stderr, "[yakb] ERROR: no CUDA device (%s); this library has no CPU path\n", cudaGetErrorString(e));
 		return nullptr;
 	}
+	// the table is probed with independent 32-byte sector reads: ask L2 not to fetch wider lines
+	if (!getenv("YAKB_L2_FETCH_DEFAULT")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
 	Engine *g = new Engine;
 	g->k = k, g->pre = pre, g->P = 1 << (pre - lw), g->lw = lw, g->rank = rank;
 	YAKB_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
@@ -656,8 +720,8 @@ Engine::~Engine()
 	if (last_put) cudaFree(last_put);
 	if (last_new) cudaFree(last_new);
 	for (auto &s : journal) { cudaFree(s.keys); cudaFree(s.off); }
-	DBuf *all[] = {&b_w2, &b_wm, &b_flags, &b_tilecnt, &b_tileoff, &b_pv, &b_ppos, &b_sv, &b_sj, &b_iota, &b_pflag, &b_newv,
-	               &b_newsorted, &b_tmp, &b_pend, &b_lput, &b_lnew, &b_stats, &b_misc};
+	DBuf *all[] = {&b_w2, &b_wm, &b_flags, &b_tilecnt, &b_tileoff, &b_pv, &b_ppos, &b_sv, &b_sj, &b_sv2, &b_sj2, &b_pflag, &b_newv,
+	               &b_newsorted, &b_tmp, &b_pend, &b_lput, &b_lnew, &b_stats, &b_misc, &b_rs[0], &b_rs[1], &b_rs[2], &b_rs[3], &b_rs[4]};
 	for (DBuf *b : all) b->release();
 	if (stream) cudaStreamDestroy(stream);
 }
@@ -707,9 +771,10 @@ ChunkStats Engine::count_ascii(const uint8_t *d_asc, uint64_t n, int create_new)
 	if (n == 0) return st;
 	if (n >= 0x7FFFFF00ull) throw CudaError("[yakb] chunk too large (positions are 31-bit)");
 	const uint64_t nwords = (n + 31) / 32;
-	uint64_t *w2 = b_w2.as<uint64_t>(nwords);
-	uint32_t *wm = b_wm.as<uint32_t>(nwords);
-	{ ProfScope ps("pack_ascii", stream); pack_ascii_kernel<<<cdiv(nwords, 256), 256, 0, stream>>>(d_asc, n, w2, wm, nwords); }
+	uint64_t *w2 = b_w2.as<uint64_t>(packed_words(nwords)) + YAKB_PADW;
+	uint32_t *wm = b_wm.as<uint32_t>(packed_words(nwords)) + YAKB_PADW;
+	{ ProfScope ps("pack_ascii", stream);
+	pack_ascii_kernel<<<cdiv(packed_npad(nwords) + YAKB_PADW, 256), 256, 0, stream>>>(d_asc, n, w2, wm, nwords, packed_npad(nwords)); }
 	YAKB_CUDA(cudaGetLastError());
 	note_launch(1);
 	return finish_chunk(nwords, create_new, w2, wm, nullptr, n, -1);
@@ -741,7 +806,7 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 	if (create_new) {
 		YAKB_CUDA(cudaMemsetAsync(lput, 0, P * 4, stream));
 		YAKB_CUDA(cudaMemsetAsync(lnew, 0, P * 4, stream));
-		YAKB_CUDA(cudaMemsetAsync(tilecnt + ntiles, 0, 4, stream));
+		YAKB_CUDA(cudaMemsetAsync(tilecnt, 0, (ntiles + 1) * 4, stream));
 	}
 	int dev = 0, nsm = 148;
 	cudaGetDevice(&dev);
@@ -775,9 +840,8 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 		return st;
 	}
 	// pending list in file order
-	size_t tmp_bytes = 0;
-	cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, tilecnt, tileoff, (int)(ntiles + 1), stream);
-	cub::DeviceScan::ExclusiveSum(b_tmp.need(tmp_bytes), tmp_bytes, tilecnt, tileoff, (int)(ntiles + 1), stream);
+	RadixScratch &rs = *reinterpret_cast<RadixScratch*>(b_rs);
+	exclusive_scan_u32(tilecnt, tileoff, ntiles + 1, stream, rs);
 	uint32_t n_pending = 0;
 	YAKB_CUDA(cudaMemcpyAsync(&n_pending, tileoff + ntiles, 4, cudaMemcpyDeviceToHost, stream));
 	YAKB_CUDA(cudaStreamSynchronize(stream));
@@ -817,15 +881,10 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 		if (bloom) G = n_shift - 9;
 		else { G = pre; while (G < vbits && (1ull << G) < (uint64_t)n_pending / 2) ++G; }
 		if (G > vbits) G = vbits;
-		uint32_t *iota = b_iota.as<uint32_t>(n_pending);
-		iota_kernel<<<cdiv(n_pending, 256), 256, 0, stream>>>(iota, n_pending);
-		uint64_t *sv = b_sv.as<uint64_t>(n_pending);
-		uint32_t *sj = b_sj.as<uint32_t>(n_pending);
-		tmp_bytes = 0;
-		cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, pv, sv, iota, sj, (int)n_pending, 0, G, stream);
-		void *tmp_sort = b_tmp.need(tmp_bytes);
-		{ ProfScope ps("group_sort(cub)", stream);
-		cub::DeviceRadixSort::SortPairs(tmp_sort, tmp_bytes, pv, sv, iota, sj, (int)n_pending, 0, G, stream); }
+		uint64_t *sv = b_sv.as<uint64_t>(n_pending), *sv2 = b_sv2.as<uint64_t>(n_pending);
+		uint32_t *sj = b_sj.as<uint32_t>(n_pending), *sj2 = b_sj2.as<uint32_t>(n_pending);
+		{ ProfScope ps("group_sort", stream);
+		if (radix_sort_pairs(pv, nullptr, sv, sj, sv2, sj2, n_pending, 0, G, stream, rs)) { sv = sv2; sj = sj2; } }
 		uint8_t *pflag = b_pflag.as<uint8_t>(2 * (size_t)n_pending); // [0,n): put/new bits, [n,2n): new-key flag
 		{ ProfScope ps("group_insert", stream);
 		group_insert<<<cdiv(n_pending, 256), 256, 0, stream>>>(sv, sj, n_pending, G, pre, Pmask, lw, slots, cap,
@@ -842,21 +901,16 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 		uint64_t *newv = b_newv.as<uint64_t>(n_pending);
 		uint32_t *d_nsel = (uint32_t*)(stats + 2);
 		const uint8_t *isnew = pflag + n_pending; // written by post_pending
-		tmp_bytes = 0;
-		cub::DeviceSelect::Flagged(nullptr, tmp_bytes, pv, isnew, newv, d_nsel, (int)n_pending, stream);
-		void *tmp_sel = b_tmp.need(tmp_bytes);
-		{ ProfScope ps("journal(cub select)", stream);
-		cub::DeviceSelect::Flagged(tmp_sel, tmp_bytes, pv, isnew, newv, d_nsel, (int)n_pending, stream); }
+		{ ProfScope ps("journal(compact)", stream);
+		compact_flagged_u64(pv, isnew, n_pending, newv, d_nsel, stream, rs); }
 		YAKB_CUDA(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaStreamSynchronize(stream));
 		n_new = (uint32_t)h_stats[2];
 		if (n_new) {
-			uint64_t *sorted = b_newsorted.as<uint64_t>(n_new);
-			tmp_bytes = 0;
-			cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, newv, sorted, (int)n_new, 0, pre - lw, stream);
-			void *tmp_js = b_tmp.need(tmp_bytes);
-			ProfScope ps("journal(cub sort+seg)", stream);
-			cub::DeviceRadixSort::SortKeys(tmp_js, tmp_bytes, newv, sorted, (int)n_new, 0, pre - lw, stream);
+			// stable by sub-table (the low pre-lw bits): newv is in file order, so each run is in first-put order
+			uint64_t *sorted = b_newsorted.as<uint64_t>(n_new), *sorted2 = b_sv.as<uint64_t>(n_new);
+			ProfScope ps("journal(sort+seg)", stream);
+			if (radix_sort_pairs(newv, nullptr, sorted, nullptr, sorted2, nullptr, n_new, 0, pre - lw, stream, rs)) sorted = sorted2;
 			Segment seg;
 			seg.n = n_new;
 			YAKB_CUDA(cudaMalloc(&seg.keys, n_new * 8));
@@ -986,13 +1040,16 @@ void Engine::layout(int s0, int s1, LayoutOut &out, bool with_counts)
 		YAKB_CUDA(cudaMemcpyAsync(d_trail, trail.data(), ns, cudaMemcpyHostToDevice, stream));
 		YAKB_CUDA(cudaMemcpyAsync(d_pf, pf.data(), ns, cudaMemcpyHostToDevice, stream));
 		YAKB_CUDA(cudaMemsetAsync(d_run, 0, ns * 8, stream));
+		double t_a = getenv("YAKB_TIMING") ? (cudaStreamSynchronize(stream), wall_s()) : 0;
 		for (auto &seg : journal) {
 			gather_seg_kernel<<<std::max<uint32_t>(1, cdiv(seg.n, 256)), 256, 0, stream>>>(seg.keys, seg.off, s0 + b0, ns, d_catoff, d_run, d_cat);
 			advance_run_kernel<<<cdiv(ns, 256), 256, 0, stream>>>(seg.off, s0 + b0, ns, d_run);
 		}
 		YAKB_CUDA(cudaGetLastError());
+		double t_b = getenv("YAKB_TIMING") ? (cudaStreamSynchronize(stream), wall_s()) : 0;
 		build_layout_kernel<<<cdiv(ns, 32), 32, 0, stream>>>(d_cat, d_catoff, d_pf, d_pv, d_trail, d_keys, d_koff, d_bm, d_boff, ns, d_ocap, d_osize, d_out);
 		YAKB_CUDA(cudaGetLastError());
+		double t_c = getenv("YAKB_TIMING") ? (cudaStreamSynchronize(stream), wall_s()) : 0;
 		if (with_counts && ncat && cap)
 			fill_counts_kernel<<<cdiv(ncat, 256), 256, 0, stream>>>(d_out, d_catoff, ns, s0 + b0, ncat, slots, cap);
 		YAKB_CUDA(cudaGetLastError());
@@ -1002,6 +1059,7 @@ void Engine::layout(int s0, int s1, LayoutOut &out, bool with_counts)
 		YAKB_CUDA(cudaMemcpyAsync(out.cap.data() + b0, d_ocap, ns * 4, cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaMemcpyAsync(out.size.data() + b0, d_osize, ns * 4, cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaStreamSynchronize(stream));
+		if (getenv("YAKB_TIMING")) fprintf(stderr, "[T::layout] %d sub-tables %llu keys: gather %.4f build %.4f fill+copy %.4f s\n", ns, (unsigned long long)ncat, t_b - t_a, t_c - t_b, wall_s() - t_c);
 		for (int t = 0; t < ns; ++t) out.off[b0 + t + 1] = out.off[b0 + t] + (catoff[t + 1] - catoff[t]);
 		cudaFree(d_cat); cudaFree(d_out); cudaFree(d_keys); cudaFree(d_bm); cudaFree(d_catoff); cudaFree(d_koff); cudaFree(d_boff);
 		cudaFree(d_run); cudaFree(d_pv); cudaFree(d_ocap); cudaFree(d_osize); cudaFree(d_trail); cudaFree(d_pf);
@@ -1066,9 +1124,9 @@ void qv_scan_ascii(Engine *e, const uint8_t *d_asc, uint64_t n, int16_t *d_cnt)
 {
 	if (n == 0) return;
 	const uint64_t nwords = (n + 31) / 32;
-	uint64_t *w2 = e->b_w2.as<uint64_t>(nwords);
-	uint32_t *wm = e->b_wm.as<uint32_t>(nwords);
-	pack_ascii_kernel<<<cdiv(nwords, 256), 256, 0, e->stream>>>(d_asc, n, w2, wm, nwords);
+	uint64_t *w2 = e->b_w2.as<uint64_t>(packed_words(nwords)) + YAKB_PADW;
+	uint32_t *wm = e->b_wm.as<uint32_t>(packed_words(nwords)) + YAKB_PADW;
+	pack_ascii_kernel<<<cdiv(packed_npad(nwords) + YAKB_PADW, 256), 256, 0, e->stream>>>(d_asc, n, w2, wm, nwords, packed_npad(nwords));
 	if (e->k >= 32) qv_scan_kernel<true><<<cdiv(nwords, 256), 256, 0, e->stream>>>(w2, wm, nwords, n, e->k, e->pre, e->P - 1, e->own(), e->slots, e->cap, d_cnt);
 	else qv_scan_kernel<false><<<cdiv(nwords, 256), 256, 0, e->stream>>>(w2, wm, nwords, n, e->k, e->pre, e->P - 1, e->own(), e->slots, e->cap, d_cnt);
 	YAKB_CUDA(cudaGetLastError());

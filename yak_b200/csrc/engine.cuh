@@ -82,8 +82,8 @@ struct Engine {
 	cudaStream_t stream = nullptr;
 	double load_limit = 0.6;
 	// scratch (grow-only, reused by every chunk)
-	DBuf b_w2, b_wm, b_flags, b_tilecnt, b_tileoff, b_pv, b_ppos, b_sv, b_sj, b_iota, b_pflag, b_newv, b_newsorted,
-	     b_tmp, b_pend, b_lput, b_lnew, b_stats, b_misc;
+	DBuf b_w2, b_wm, b_flags, b_tilecnt, b_tileoff, b_pv, b_ppos, b_sv, b_sj, b_sv2, b_sj2, b_pflag, b_newv, b_newsorted,
+	     b_tmp, b_pend, b_lput, b_lnew, b_stats, b_misc, b_rs[5];
 
 	static Engine *create(int k, int pre, int n_hash, int n_shift, int rank = 0, int world = 1);
 	~Engine();

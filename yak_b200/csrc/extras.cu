@@ -4,7 +4,7 @@
 #include "yakb_dev.cuh"
 #include "kernels.cuh"
 #include "extras.cuh"
-#include <cub/cub.cuh>
+#include "radix.cuh"
 #include <stdio.h>
 #include <algorithm>
 
@@ -52,22 +52,21 @@ __global__ void rank_offsets_kernel(const uint64_t *__restrict__ sorted, uint64_
 }
 
 int extract_events(const uint8_t *d_asc, uint64_t n, int k, int pre, int world, uint64_t *d_out, uint64_t *counts,
-                   cudaStream_t stream, DBuf *scratch /* 8 buffers */)
+                   cudaStream_t stream, DBuf *scratch /* 8 buffers + a RadixScratch (5 more) */)
 {
 	for (int r = 0; r < world; ++r) counts[r] = 0;
 	if (n == 0) return 0;
 	const uint64_t nwords = (n + 31) / 32, ntiles = (nwords + 255) / 256;
-	uint64_t *w2 = scratch[0].as<uint64_t>(nwords);
-	uint32_t *wm = scratch[1].as<uint32_t>(nwords);
+	uint64_t *w2 = scratch[0].as<uint64_t>(packed_words(nwords)) + YAKB_PADW;
+	uint32_t *wm = scratch[1].as<uint32_t>(packed_words(nwords)) + YAKB_PADW;
 	uint32_t *vmask = scratch[2].as<uint32_t>(nwords);
 	uint32_t *tilecnt = scratch[3].as<uint32_t>(ntiles + 1), *tileoff = scratch[4].as<uint32_t>(ntiles + 1);
 	uint32_t *ppos = scratch[5].as<uint32_t>(n);
-	pack_ascii_kernel<<<cdiv(nwords, 256), 256, 0, stream>>>(d_asc, n, w2, wm, nwords);
+	pack_ascii_kernel<<<cdiv(packed_npad(nwords) + YAKB_PADW, 256), 256, 0, stream>>>(d_asc, n, w2, wm, nwords, packed_npad(nwords));
 	valid_mask_kernel<<<(uint32_t)ntiles, 256, 0, stream>>>(wm, nwords, k, vmask, tilecnt);
 	YAKB_CUDA(cudaMemsetAsync(tilecnt + ntiles, 0, 4, stream));
-	size_t tb = 0;
-	cub::DeviceScan::ExclusiveSum(nullptr, tb, tilecnt, tileoff, (int)(ntiles + 1), stream);
-	cub::DeviceScan::ExclusiveSum(scratch[6].need(tb), tb, tilecnt, tileoff, (int)(ntiles + 1), stream);
+	RadixScratch &rs = *reinterpret_cast<RadixScratch*>(scratch + 8);
+	exclusive_scan_u32(tilecnt, tileoff, ntiles + 1, stream, rs);
 	uint32_t n_ev = 0;
 	YAKB_CUDA(cudaMemcpyAsync(&n_ev, tileoff + ntiles, 4, cudaMemcpyDeviceToHost, stream));
 	YAKB_CUDA(cudaStreamSynchronize(stream));
@@ -80,10 +79,10 @@ int extract_events(const uint8_t *d_asc, uint64_t n, int k, int pre, int world, 
 	else compact_fused<false><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, vmask, tileoff, ev, ppos);
 	YAKB_CUDA(cudaGetLastError());
 	if (lw == 0) { counts[0] = n_ev; YAKB_CUDA(cudaStreamSynchronize(stream)); return 0; }
-	// owner rank = top lw bits of the sub-table index = hash bits [pre-lw, pre); stable sort on them
-	tb = 0;
-	cub::DeviceRadixSort::SortKeys(nullptr, tb, ev, d_out, (int)n_ev, pre - lw, pre, stream);
-	cub::DeviceRadixSort::SortKeys(scratch[6].need(tb), tb, ev, d_out, (int)n_ev, pre - lw, pre, stream);
+	// owner rank = top lw bits of the sub-table index = hash bits [pre-lw, pre); one stable pass on them
+	uint64_t *alt = scratch[6].as<uint64_t>(n_ev);
+	if (radix_sort_pairs(ev, nullptr, d_out, nullptr, alt, nullptr, n_ev, pre - lw, pre, stream, rs) != 0)
+		YAKB_CUDA(cudaMemcpyAsync(d_out, alt, (size_t)n_ev * 8, cudaMemcpyDeviceToDevice, stream));
 	// per-rank counts: lower bounds in the sorted owner field (host binary search over device data
 	// would sync per probe; a tiny kernel does all ranks at once)
 	uint64_t *d_off = (uint64_t*)scratch[4].need((world + 1) * 8);

@@ -5,7 +5,7 @@
 namespace yakb {
 
 // hashed canonical k-mers of a device ASCII stream in file order, stably grouped by owner rank;
-// scratch = 8 grow-only buffers owned by the caller
+// scratch = 13 grow-only buffers owned by the caller (8 + a RadixScratch)
 int extract_events(const uint8_t *d_asc, uint64_t n, int k, int pre, int world, uint64_t *d_out, uint64_t *counts,
                    cudaStream_t stream, DBuf *scratch);
 void qv_stats(const int16_t *d_cnt, const uint64_t *d_seq_off, uint64_t n_seq, int min_len, double min_frac,

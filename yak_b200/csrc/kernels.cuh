@@ -5,14 +5,19 @@
 
 namespace yakb {
 
-// ---- ASCII -> packed. word W of w2 holds bases 32W..32W+31, first base in the top 2 bits;
-//      wm[W] bit (31-r) set = base 32W+r is not A/C/G/T/U (separator, N, padding)
+// ---- ASCII -> packed.  Word W of w2 holds bases 32W..32W+31, first base in the top 2 bits;
+//      wm[W] bit (31-r) set = base 32W+r is not A/C/G/T/U (separator, N, padding).
+//      Both arrays carry YAKB_PADW words in front of word 0 and are padded behind to a whole
+//      256-word tile; every padding word reads "32 invalid bases", so window code never needs a
+//      bounds test and whole tiles can be bulk-copied.  The kernel writes words -PADW .. npad-1.
+#define YAKB_PADW 4
 static __global__ void __launch_bounds__(256) pack_ascii_kernel(const uint8_t *__restrict__ asc, uint64_t n,
-                                                         uint64_t *__restrict__ w2, uint32_t *__restrict__ wm, uint64_t nwords)
+                                                         uint64_t *__restrict__ w2, uint32_t *__restrict__ wm, uint64_t nwords, uint64_t npad)
 {
-	uint64_t W = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-	if (W >= nwords) return;
-	uint64_t base = W * 32, w = 0;
+	const int64_t W = (int64_t)(blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) - YAKB_PADW;
+	if (W >= (int64_t)npad) return;
+	if (W < 0 || W >= (int64_t)nwords) { w2[W] = 0; wm[W] = 0xFFFFFFFFu; return; }
+	uint64_t base = (uint64_t)W * 32, w = 0;
 	uint32_t m = 0;
 	if (base + 32 <= n && ((uintptr_t)(asc + base) & 15) == 0) {
 		const uint4 *q = (const uint4*)(asc + base);
@@ -33,6 +38,41 @@ static __global__ void __launch_bounds__(256) pack_ascii_kernel(const uint8_t *_
 	}
 	w2[W] = w; wm[W] = m;
 }
+// words a packed buffer needs for nwords data words (front pad + whole tiles + slack for bulk copies)
+static inline uint64_t packed_words(uint64_t nwords) { return YAKB_PADW + (nwords + 255) / 256 * 256 + 8; }
+static inline uint64_t packed_npad(uint64_t nwords) { return (nwords + 255) / 256 * 256 + 8; }
+
+// ---- TMA-style bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 // ---- rolling canonical k-mer over the 32 positions of word W.  count.c:28-43 (k<32) /
 //      count.c:45-60 (k>=32).  init() builds the state after the k-1 bases before the word;
@@ -43,7 +83,9 @@ struct Roller {
 	uint32_t cm;
 	int l, k, shift;
 
-	__device__ __forceinline__ void init(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t W, int k_)
+	// w2 / wm may be global arrays (index = word number) or a staged tile (index local to the tile):
+	// indices down to W-2 (w2) and W-2 (wm) are read, which the padding / the tile halo provide
+	__device__ __forceinline__ void init(const uint64_t *w2, const uint32_t *wm, int64_t W, int k_)
 	{
 		k = k_;
 		mask = LONGK ? (1ULL << k) - 1 : (1ULL << 2 * k) - 1;
@@ -53,7 +95,7 @@ struct Roller {
 			// the last k-1 (<= 30) bases of the previous word are its low 2(k-1) bits.  A window never
 			// crosses an invalid base, so whatever sits under invalid positions is shifted out before
 			// the next emission.
-			if (W > 0) {
+			{
 				const int n = k - 1;
 				const uint64_t pw = w2[W - 1];
 				const uint32_t pm = n ? (wm[W - 1] & (uint32_t)((1ull << n) - 1)) : 0;
@@ -65,8 +107,7 @@ struct Roller {
 				l = pm ? __ffs(pm) - 1 : n;
 			}
 		} else {
-			for (int64_t p = (int64_t)(W * 32) - (k - 1); p < (int64_t)(W * 32); ++p) {
-				if (p < 0) continue;
+			for (int64_t p = W * 32 - (k - 1); p < W * 32; ++p) { // p may be negative: >>5 floors, &31 wraps
 				uint32_t c = (uint32_t)(w2[p >> 5] >> (62 - 2 * (p & 31))) & 3;
 				uint32_t inv = (wm[p >> 5] >> (31 - (p & 31))) & 1;
 				x0 = (x0 << 1 | (c & 1)) & mask;
@@ -104,7 +145,7 @@ __device__ __forceinline__ void roll_word(const uint64_t *__restrict__ w2, const
                                           uint64_t W, int k, F &&emit)
 {
 	Roller<LONGK> ro;
-	ro.init(w2, wm, W, k);
+	ro.init(w2, wm, (int64_t)W, k);
 #pragma unroll
 	for (int r = 0; r < 32; ++r) { uint64_t h; if (ro.step(r, h)) emit(r, h); }
 }
