@@ -719,11 +719,33 @@ Engine::~Engine()
 	if (bloom) cudaFree(bloom);
 	if (last_put) cudaFree(last_put);
 	if (last_new) cudaFree(last_new);
-	for (auto &s : journal) { cudaFree(s.keys); cudaFree(s.off); }
+	journal_free_all();
 	DBuf *all[] = {&b_w2, &b_wm, &b_flags, &b_tilecnt, &b_tileoff, &b_pv, &b_ppos, &b_sv, &b_sj, &b_sv2, &b_sj2, &b_pflag, &b_newv,
 	               &b_newsorted, &b_tmp, &b_pend, &b_lput, &b_lnew, &b_stats, &b_misc, &b_rs[0], &b_rs[1], &b_rs[2], &b_rs[3], &b_rs[4]};
 	for (DBuf *b : all) b->release();
 	if (stream) cudaStreamDestroy(stream);
+}
+
+void *Engine::journal_alloc(size_t bytes)
+{
+	bytes = (bytes + 255) & ~(size_t)255;
+	if (slabs.empty() || slabs.back().used + bytes > slabs.back().cap) {
+		Slab sl;
+		sl.cap = std::max<size_t>(bytes, (size_t)1 << 30);
+		sl.used = 0;
+		YAKB_CUDA(cudaMalloc((void**)&sl.p, sl.cap));
+		slabs.push_back(sl);
+	}
+	void *r = slabs.back().p + slabs.back().used;
+	slabs.back().used += bytes;
+	return r;
+}
+
+void Engine::journal_free_all()
+{
+	for (auto &sl : slabs) cudaFree(sl.p);
+	slabs.clear();
+	journal.clear();
 }
 
 void Engine::destroy_bloom() { if (bloom) { cudaFree(bloom); bloom = nullptr; } }
@@ -731,7 +753,7 @@ void Engine::destroy_bloom() { if (bloom) { cudaFree(bloom); bloom = nullptr; } 
 uint64_t Engine::device_bytes() const
 {
 	uint64_t b = (uint64_t)P * cap * 8 + (bloom ? (uint64_t)1 << (n_shift - 3 - lw) : 0);
-	for (auto &s : journal) b += s.n * 8 + (uint64_t)(P + 1) * 8;
+	for (auto &sl : slabs) b += sl.cap;
 	return b;
 }
 
@@ -913,8 +935,8 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 			if (radix_sort_pairs(newv, nullptr, sorted, nullptr, sorted2, nullptr, n_new, 0, pre - lw, stream, rs)) sorted = sorted2;
 			Segment seg;
 			seg.n = n_new;
-			YAKB_CUDA(cudaMalloc(&seg.keys, n_new * 8));
-			YAKB_CUDA(cudaMalloc(&seg.off, (uint64_t)(P + 1) * 8));
+			seg.keys = (uint64_t*)journal_alloc(n_new * 8);
+			seg.off = (uint64_t*)journal_alloc((uint64_t)(P + 1) * 8);
 			seg_offsets_kernel<<<cdiv(P + 1, 256), 256, 0, stream>>>(sorted, n_new, Pmask, seg.off, nkeys);
 			seg_addkeys_kernel<<<cdiv(P, 256), 256, 0, stream>>>(seg.off, P, nkeys);
 			seg_keys_kernel<<<cdiv(n_new, 256), 256, 0, stream>>>(sorted, n_new, pre, seg.keys);
@@ -1079,8 +1101,8 @@ void Engine::load_subtables(const std::vector<uint32_t> &caps, const std::vector
 	reserve(std::max<uint32_t>(mx, 8));
 	Segment seg;
 	seg.n = n;
-	YAKB_CUDA(cudaMalloc(&seg.keys, std::max<uint64_t>(n, 1) * 8));
-	YAKB_CUDA(cudaMalloc(&seg.off, (uint64_t)(P + 1) * 8));
+	seg.keys = (uint64_t*)journal_alloc(std::max<uint64_t>(n, 1) * 8);
+	seg.off = (uint64_t*)journal_alloc((uint64_t)(P + 1) * 8);
 	YAKB_CUDA(cudaMemcpyAsync(seg.off, off.data(), (uint64_t)(P + 1) * 8, cudaMemcpyHostToDevice, stream));
 	if (n) {
 		YAKB_CUDA(cudaMemcpyAsync(seg.keys, keys, n * 8, cudaMemcpyHostToDevice, stream));
@@ -1112,8 +1134,7 @@ void Engine::shrink(int min, int max)
 		caps[s] = lo.size[s]; // yak_ht_resize(f, kh_size(g))
 	}
 	// drop the old table and journal, rebuild from the kept keys
-	for (auto &sg : journal) { cudaFree(sg.keys); cudaFree(sg.off); }
-	journal.clear();
+	journal_free_all();
 	if (slots) { YAKB_CUDA(cudaFree(slots)); slots = nullptr; cap = 0; }
 	YAKB_CUDA(cudaMemsetAsync(last_put, 0, P * 8, stream));
 	YAKB_CUDA(cudaMemsetAsync(last_new, 0, P * 8, stream));

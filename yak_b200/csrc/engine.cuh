@@ -77,6 +77,11 @@ struct Engine {
 	std::vector<uint8_t> presize_flag;      // host
 	std::vector<uint32_t> presize_val;      // host
 	std::vector<Segment> journal;
+	// journal segments are carved from big slabs (a cudaMalloc per chunk costs milliseconds)
+	struct Slab { char *p; size_t cap, used; };
+	std::vector<Slab> slabs;
+	void *journal_alloc(size_t bytes);
+	void journal_free_all();
 	uint32_t chunk_seq = 0;
 	uint64_t tot = 0;
 	cudaStream_t stream = nullptr;

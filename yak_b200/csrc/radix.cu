@@ -66,6 +66,20 @@ void exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, cudaStrea
 
 #define RTILE 4096 // 256 threads x 16 records
 
+// lanes of the warp holding the same digit as this lane (invalid lanes match nobody): built from
+// one ballot per digit bit - MATCH.ANY runs on the slow ADU pipe (ncu: 91 % busy with it)
+__device__ __forceinline__ uint32_t same_digit_lanes(uint32_t d, bool ok, int nbits)
+{
+	uint32_t peers = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+	for (int b = 0; b < 8; ++b)
+		if (b < nbits) {
+			const uint32_t bit = d >> b & 1, m = __ballot_sync(0xffffffffu, bit);
+			peers &= bit ? m : ~m;
+		}
+	return ok ? peers : 0;
+}
+
 __global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int shift, uint32_t dmask,
                                                          uint32_t *__restrict__ hist, uint32_t ntiles)
 {
@@ -82,17 +96,26 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t *__restr
 	if (threadIdx.x <= dmask) hist[(uint64_t)threadIdx.x * ntiles + blockIdx.x] = s_h[threadIdx.x];
 }
 
-// hist holds the exclusive prefix over (digit-major, tile) = the first output index of each (digit, tile)
+// hist holds the exclusive prefix over (digit-major, tile) = the first output index of each (digit, tile).
+// Records are ranked stably inside the tile ((warp, round, lane) order), parked in shared memory at
+// their tile-local sorted position, and written out run by run so that stores coalesce.
 template<bool IOTA, bool HASVAL>
 __global__ void __launch_bounds__(256) radix_scatter_kernel(const uint64_t *__restrict__ k_in, const uint32_t *__restrict__ v_in,
                                                             uint64_t *__restrict__ k_out, uint32_t *__restrict__ v_out, uint64_t n,
                                                             int shift, uint32_t dmask, const uint32_t *__restrict__ hist, uint32_t ntiles)
 {
-	__shared__ uint32_t s_c[8][256];
+	extern __shared__ unsigned char s_raw[];
+	uint64_t *s_key = (uint64_t*)s_raw;                       // RTILE keys
+	uint32_t *s_val = (uint32_t*)(s_raw + RTILE * 8);         // RTILE payloads (when HASVAL)
+	__shared__ uint32_t s_c[8][256];   // per warp: count, then tile-local start, then running position
+	__shared__ uint32_t s_dstart[256]; // tile-local start of each digit's run
+	__shared__ uint32_t s_gbase[256];  // global index of the first record of each digit's run
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int nbits = 32 - __clz(dmask);
 	for (int i = threadIdx.x; i < 8 * 256; i += 256) (&s_c[0][0])[i] = 0;
 	__syncthreads();
-	const uint64_t wbase = blockIdx.x * (uint64_t)RTILE + (uint64_t)w * 512;
+	const uint64_t tbase = blockIdx.x * (uint64_t)RTILE, wbase = tbase + (uint64_t)w * 512;
+	const uint32_t tcount = (uint32_t)(n - tbase < RTILE ? n - tbase : RTILE);
 	uint64_t key[16];
 	uint32_t val[16];
 	// pass A: this warp's count per digit, elements taken in (round, lane) order
@@ -102,26 +125,40 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const uint64_t *__re
 		const bool ok = e < n;
 		key[r] = ok ? k_in[e] : 0;
 		if (HASVAL) val[r] = IOTA ? (uint32_t)e : (ok ? v_in[e] : 0);
-		const uint32_t d = ok ? ((uint32_t)(key[r] >> shift) & dmask) : 0x10000u + lane;
-		const uint32_t peers = __match_any_sync(0xffffffffu, d);
+		const uint32_t d = (uint32_t)(key[r] >> shift) & dmask;
+		const uint32_t peers = same_digit_lanes(d, ok, nbits);
 		if (ok && lane == __ffs(peers) - 1) s_c[w][d] += __popc(peers);
 		__syncwarp();
 	}
 	__syncthreads();
-	// first output index of every (warp, digit) of this tile
-	if (threadIdx.x <= dmask) {
-		uint32_t acc = hist[(uint64_t)threadIdx.x * ntiles + blockIdx.x];
+	// digit totals of the tile -> tile-local run starts (exclusive scan over digits, 256 threads)
+	{
+		uint32_t tot = 0;
+		if (threadIdx.x <= dmask) for (int i = 0; i < 8; ++i) tot += s_c[i][threadIdx.x];
+		uint32_t inc = tot;
 #pragma unroll
-		for (int i = 0; i < 8; ++i) { const uint32_t t = s_c[i][threadIdx.x]; s_c[i][threadIdx.x] = acc; acc += t; }
+		for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+		__shared__ uint32_t s_ws[8];
+		if (lane == 31) s_ws[w] = inc;
+		__syncthreads();
+		uint32_t woff = 0;
+		for (int i = 0; i < w; ++i) woff += s_ws[i];
+		const uint32_t start = woff + inc - tot;
+		s_dstart[threadIdx.x] = start;
+		if (threadIdx.x <= dmask) {
+			s_gbase[threadIdx.x] = hist[(uint64_t)threadIdx.x * ntiles + blockIdx.x];
+			uint32_t acc = start;
+			for (int i = 0; i < 8; ++i) { const uint32_t t = s_c[i][threadIdx.x]; s_c[i][threadIdx.x] = acc; acc += t; }
+		}
 	}
 	__syncthreads();
-	// pass B: same order again, now with running positions
+	// pass B: same order again, now with running tile-local positions; park in shared memory
 #pragma unroll
 	for (int r = 0; r < 16; ++r) {
 		const uint64_t e = wbase + r * 32 + lane;
 		const bool ok = e < n;
-		const uint32_t d = ok ? ((uint32_t)(key[r] >> shift) & dmask) : 0x10000u + lane;
-		const uint32_t peers = __match_any_sync(0xffffffffu, d);
+		const uint32_t d = (uint32_t)(key[r] >> shift) & dmask;
+		const uint32_t peers = same_digit_lanes(d, ok, nbits);
 		uint32_t pos = 0;
 		if (ok) pos = s_c[w][d];
 		__syncwarp();
@@ -129,9 +166,18 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const uint64_t *__re
 		__syncwarp();
 		if (ok) {
 			pos += __popc(peers & ((1u << lane) - 1));
-			k_out[pos] = key[r];
-			if (HASVAL) v_out[pos] = val[r];
+			s_key[pos] = key[r];
+			if (HASVAL) s_val[pos] = val[r];
 		}
+	}
+	__syncthreads();
+	// write-out: consecutive threads take consecutive sorted records; a digit's run is contiguous globally
+	for (uint32_t j = threadIdx.x; j < tcount; j += 256) {
+		const uint64_t kk = s_key[j];
+		const uint32_t d = (uint32_t)(kk >> shift) & dmask;
+		const uint32_t dst = s_gbase[d] + (j - s_dstart[d]);
+		k_out[dst] = kk;
+		if (HASVAL) v_out[dst] = s_val[j];
 	}
 }
 
@@ -168,9 +214,17 @@ int radix_sort_pairs(const uint64_t *k_src, const uint32_t *v_src, uint64_t *k_a
 		uint64_t *kout = where == 0 ? k_b : k_a;
 		uint32_t *vout = where == 0 ? v_b : v_a;
 		const bool iota = hasval && vin == nullptr;
-		if (!hasval) radix_scatter_kernel<false, false><<<ntiles, 256, 0, st>>>(kin, nullptr, kout, nullptr, n, lo, dmask, hist, ntiles);
-		else if (iota) radix_scatter_kernel<true, true><<<ntiles, 256, 0, st>>>(kin, nullptr, kout, vout, n, lo, dmask, hist, ntiles);
-		else radix_scatter_kernel<false, true><<<ntiles, 256, 0, st>>>(kin, vin, kout, vout, n, lo, dmask, hist, ntiles);
+		const size_t sm = hasval ? RTILE * 12 : RTILE * 8;
+		if (!hasval) {
+			cudaFuncSetAttribute(radix_scatter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+			radix_scatter_kernel<false, false><<<ntiles, 256, sm, st>>>(kin, nullptr, kout, nullptr, n, lo, dmask, hist, ntiles);
+		} else if (iota) {
+			cudaFuncSetAttribute(radix_scatter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+			radix_scatter_kernel<true, true><<<ntiles, 256, sm, st>>>(kin, nullptr, kout, vout, n, lo, dmask, hist, ntiles);
+		} else {
+			cudaFuncSetAttribute(radix_scatter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+			radix_scatter_kernel<false, true><<<ntiles, 256, sm, st>>>(kin, vin, kout, vout, n, lo, dmask, hist, ntiles);
+		}
 		YAKB_CUDA(cudaGetLastError());
 		Engine::note_launch(2);
 		where = where == 0 ? 1 : 0;
