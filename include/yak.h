@@ -25,7 +25,7 @@ extern "C" {
 #define YAK_BLK_MASK     ((1<<(YAK_BLK_SHIFT)) - 1)
 
 /* reference yak.h:16-21 - yak_ch_restore_core() modes (only YAK_LOAD_ALL is implemented; the
- * trio/sex-chromosome remaps are SURVEY 8(f) rank 2) */
+ * trio/sex-chromosome remaps are SURVEY 8(f) rank 2 and abort with a message) */
 #define YAK_LOAD_ALL       1
 #define YAK_LOAD_TRIOBIN1  2
 #define YAK_LOAD_TRIOBIN2  3
@@ -131,7 +131,8 @@ yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *h0);
 void yak_recount(const char *fn, yak_ch_t *h);
 
 /* reference yak.h:105-107, qv.c:116-244.  yak_qv_solve (host FP64, off the hot path) is NOT
- * exported by this library: link the reference's qv.c:146-244 + 6gjdn.c for it */
+ * exported by this library: link the reference's qv.c:146-244 + 6gjdn.c for it;
+ * the CLI carries its own restatement (yak_b200/cli/qv_solve.c) */
 void yak_qopt_init(yak_qopt_t *opt);
 void yak_qv(const yak_qopt_t *opt, const char *fn, const yak_ch_t *ch, int64_t *cnt);
 

@@ -352,6 +352,80 @@ void yo_ch_shrink(yo_ch_t *h, int min, int max)
 	}
 }
 
+/* htab.c:102-110 */
+void yo_ch_tighten(yo_ch_t *h)
+{
+	int w;
+	for (w = 0; w < 1 << h->pre; ++w) {
+		yo_set_t *g = &h->h[w];
+		if (g->count * 3 < yo_set_capacity(g)) yo_set_resize(g, g->count * 3);
+	}
+}
+
+/* htab.c:214-235 */
+void yo_ch_setcnt(yo_ch_t *h, int cnt)
+{
+	int w;
+	for (w = 0; w < 1 << h->pre; ++w) {
+		yo_set_t *g = &h->h[w];
+		uint32_t i, n = yo_set_capacity(g);
+		for (i = 0; i < n; ++i)
+			if (bit_get(g->used, i)) g->keys[i] = (g->keys[i] & ~(uint64_t)YO_MAX_COUNT) | (uint64_t)cnt;
+	}
+}
+
+/* htab.c:241-285: h1 is consumed */
+void yo_ch_merge(yo_ch_t *h0, yo_ch_t *h1, int min, int max, int pre_resize)
+{
+	int w;
+	if (!(max >= min && max <= YO_MAX_COUNT)) max = YO_MAX_COUNT;
+	h0->tot = 0;
+	for (w = 0; w < 1 << h0->pre; ++w) {
+		yo_set_t *g0 = &h0->h[w], *g1 = &h1->h[w];
+		uint32_t i, n1 = yo_set_capacity(g1);
+		if (pre_resize) {
+			uint32_t want = (g0->count + g1->count) * 4 / 3 + 1;
+			if (want > yo_set_capacity(g0)) yo_set_resize(g0, want);
+		}
+		for (i = 0; i < n1; ++i) {
+			int c, absent;
+			uint32_t l;
+			if (!bit_get(g1->used, i)) continue;
+			c = (int)(g1->keys[i] & YO_MAX_COUNT);
+			if (c < min || c > max) continue;
+			l = yo_set_put(g0, g1->keys[i] & ~(uint64_t)YO_MAX_COUNT, &absent);
+			if ((g0->keys[l] & YO_MAX_COUNT) < YO_MAX_COUNT) ++g0->keys[l];
+		}
+		h0->tot += g0->count;
+	}
+	yo_ch_destroy(h1);
+}
+
+/* htab.c:287-347: keep the keys of h0 that are absent from (keep_present=0) / present in h1 */
+static void filter_members(yo_ch_t *h0, const yo_ch_t *h1, int keep_present)
+{
+	int w;
+	h0->tot = 0;
+	for (w = 0; w < 1 << h0->pre; ++w) {
+		yo_set_t *g0 = &h0->h[w], f;
+		const yo_set_t *g1 = &h1->h[w];
+		uint32_t i, n0 = yo_set_capacity(g0);
+		memset(&f, 0, sizeof(f));
+		yo_set_resize(&f, g0->count);
+		for (i = 0; i < n0; ++i) {
+			int absent, present;
+			if (!bit_get(g0->used, i)) continue;
+			present = yo_set_get(g1, g0->keys[i]) != yo_set_capacity(g1);
+			if (present == keep_present) yo_set_put(&f, g0->keys[i], &absent);
+		}
+		set_free(g0);
+		*g0 = f;
+		h0->tot += g0->count;
+	}
+}
+void yo_ch_subtract(yo_ch_t *h0, const yo_ch_t *h1) { filter_members(h0, h1, 0); }
+void yo_ch_isec(yo_ch_t *h0, const yo_ch_t *h1) { filter_members(h0, h1, 1); }
+
 /* htab.c:373-394 */
 static int64_t dump_to(const yo_ch_t *h, FILE *fp, uint8_t *mem)
 {

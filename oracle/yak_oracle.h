@@ -5,9 +5,11 @@
  * use it, and only as the checker.  It is a plain sequential C restatement of the reference
  * algorithm (no threads, no GPU), each function citing the reference file:line it follows.
  *
- * Parity pin: oracle/_ref/ (the unmodified reference compiled from /root/reference by
- * oracle/Makefile) is run on the same seeded inputs in tests/test_oracle_vs_ref.py, and the
- * known-answer vectors of SURVEY.md section 4 are checked in tests/test_oracle_kat.py.
+ * Parity pin: the outputs of oracle/_ref/ (the unmodified reference compiled from
+ * /root/reference by oracle/Makefile) on seeded inputs are committed as digests under
+ * tests/golden/ and reproduced by this code in tests/test_oracle_cpu.py, together with the
+ * known-answer vectors of SURVEY.md section 4 and the reference's own table set-ops called
+ * through oracle/_ref/libyakref.so (tests/test_setops.py).
  */
 #ifndef YAK_ORACLE_H
 #define YAK_ORACLE_H
@@ -70,6 +72,11 @@ int  yo_ch_inc(yo_ch_t *h, uint64_t x);
 void yo_ch_clear(yo_ch_t *h);
 void yo_ch_hist(const yo_ch_t *h, int64_t cnt[YO_N_COUNTS]);
 void yo_ch_shrink(yo_ch_t *h, int min, int max);
+void yo_ch_tighten(yo_ch_t *h);
+void yo_ch_setcnt(yo_ch_t *h, int cnt);
+void yo_ch_merge(yo_ch_t *h0, yo_ch_t *h1, int min, int max, int pre_resize); /* consumes h1 */
+void yo_ch_subtract(yo_ch_t *h0, const yo_ch_t *h1);
+void yo_ch_isec(yo_ch_t *h0, const yo_ch_t *h1);
 int  yo_ch_dump(const yo_ch_t *h, const char *fn);
 yo_ch_t *yo_ch_restore(const char *fn);
 /* serialise into a malloc'd buffer (same bytes as yo_ch_dump); returns length */

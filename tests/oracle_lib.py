@@ -52,6 +52,11 @@ def lib():
     L.yo_ch_clear.argtypes = [C.POINTER(YoCh)]
     L.yo_ch_hist.argtypes = [C.POINTER(YoCh), C.POINTER(i64)]
     L.yo_ch_shrink.argtypes = [C.POINTER(YoCh), C.c_int, C.c_int]
+    L.yo_ch_tighten.argtypes = [C.POINTER(YoCh)]
+    L.yo_ch_setcnt.argtypes = [C.POINTER(YoCh), C.c_int]
+    L.yo_ch_merge.argtypes = [C.POINTER(YoCh), C.POINTER(YoCh), C.c_int, C.c_int, C.c_int]
+    L.yo_ch_subtract.argtypes = [C.POINTER(YoCh), C.POINTER(YoCh)]
+    L.yo_ch_isec.argtypes = [C.POINTER(YoCh), C.POINTER(YoCh)]
     L.yo_ch_dump.restype = C.c_int; L.yo_ch_dump.argtypes = [C.POINTER(YoCh), C.c_char_p]
     L.yo_ch_dump_mem.restype = i64; L.yo_ch_dump_mem.argtypes = [C.POINTER(YoCh), C.POINTER(p)]
     L.yo_ch_restore.restype = C.POINTER(YoCh); L.yo_ch_restore.argtypes = [C.c_char_p]

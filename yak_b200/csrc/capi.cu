@@ -274,14 +274,130 @@ extern "C" yak_knt_t *yak_ch_getseq(const yak_ch_t *h, int w, uint32_t *n) // ht
 
 static void unsupported(const char *fn)
 {
-	fprintf(stderr, "[yakb] ERROR: %s is not implemented by the B200 library yet (SURVEY 8(f) rank 1)\n", fn);
+	fprintf(stderr, "[yakb] ERROR: %s is not implemented by the B200 library yet (SURVEY 8(f))\n", fn);
 	abort();
 }
-extern "C" void yak_ch_tighten(yak_ch_t *h) { (void)h; unsupported("yak_ch_tighten"); }
+
+// htab.c:102-110: per sub-table `if (size*3 < capacity) resize(size*3)`; the condition needs the khashl
+// capacity, so it is recorded as an operation and evaluated when the layout is replayed
+extern "C" void yak_ch_tighten(yak_ch_t *h)
+{
+	GUARD_BEGIN
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	std::vector<uint64_t> op(b->eng->P, (uint64_t)Engine::OP_TIGHTEN);
+	b->eng->append_ops(op);
+	GUARD_END_VOID
+}
+
+// all sub-tables of a table in slot order with counts, brought to the host in slices
+template<class F> static void for_each_slice(Engine *e, F &&fn)
+{
+	const int step = 1024;
+	for (int s0 = 0; s0 < e->P; s0 += step) {
+		const int s1 = std::min(e->P, s0 + step);
+		LayoutOut lo;
+		e->layout(s0, s1, lo, true);
+		fn(s0, s1, lo);
+	}
+}
+
+// htab.c:241-285: every key of h1 (slot order, min <= count <= max) is put into h0 and bumps its
+// counter by one; h1 is destroyed.  The puts run through the ordinary event path of h0 (file order =
+// h1's slot order per sub-table), which also records first-put order for the layout.
 extern "C" void yak_ch_merge(yak_ch_t *h0, yak_ch_t *h1, int min, int max, int n_thread, int pre_resize)
-{ (void)h0; (void)h1; (void)min; (void)max; (void)n_thread; (void)pre_resize; unsupported("yak_ch_merge"); }
-extern "C" void yak_ch_subtract(yak_ch_t *h0, const yak_ch_t *h1, int n_thread) { (void)h0; (void)h1; (void)n_thread; unsupported("yak_ch_subtract"); }
-extern "C" void yak_ch_isec(yak_ch_t *h0, const yak_ch_t *h1, int n_thread) { (void)h0; (void)h1; (void)n_thread; unsupported("yak_ch_isec"); }
+{
+	GUARD_BEGIN
+	(void)n_thread;
+	ChBox *b0 = box_of(h0), *b1 = box_of(h1);
+	assert(h0->k == h1->k && h0->pre == h1->pre && b0->eng->P == b1->eng->P);
+	if (!(max >= min && max <= YAK_MAX_COUNT)) max = YAK_MAX_COUNT;
+	{
+		std::lock_guard<std::mutex> lk(b0->mu);
+		Engine *e0 = b0->eng, *e1 = b1->eng;
+		const int pre = h0->pre;
+		const uint64_t own_hi = (uint64_t)e0->rank << (pre - e0->lw);
+		if (pre_resize) { // htab.c:250-254
+			std::vector<uint32_t> z0, z1;
+			e0->sizes(z0); e1->sizes(z1);
+			std::vector<uint64_t> op(e0->P);
+			for (int s = 0; s < e0->P; ++s) op[s] = ((uint64_t)(((uint64_t)z0[s] + z1[s]) * 4 / 3 + 1) << 10) | Engine::OP_RESIZE_IF_LARGER;
+			e0->append_ops(op);
+		}
+		for_each_slice(e1, [&](int s0, int s1, LayoutOut &lo) {
+			std::vector<uint64_t> ev;
+			ev.reserve(lo.keys.size());
+			for (int s = s0; s < s1; ++s)
+				for (uint64_t i = lo.off[s - s0]; i < lo.off[s - s0 + 1]; ++i) {
+					const int c = (int)(lo.keys[i] & YAK_MAX_COUNT);
+					if (c >= min && c <= max) ev.push_back((lo.keys[i] >> YAK_COUNTER_BITS) << pre | own_hi | (uint64_t)s);
+				}
+			if (ev.empty()) return;
+			uint64_t *d = b0->d_in.as<uint64_t>(ev.size());
+			YAKB_CUDA(cudaMemcpyAsync(d, ev.data(), ev.size() * 8, cudaMemcpyHostToDevice, e0->stream));
+			e0->count_events(d, ev.size(), 1, -1, true);
+		});
+		std::vector<uint32_t> z;
+		e0->sizes(z);
+		uint64_t tot = 0;
+		for (uint32_t v : z) tot += v;
+		e0->tot = tot;
+		h0->tot = tot; // htab.c:283-284
+	}
+	yak_ch_destroy(h1);
+	GUARD_END_VOID
+}
+
+// htab.c:287-347: h0 keeps the keys (with their counts, in its own slot order) that are absent from
+// (subtract) / present in (isec) h1, re-put into sets pre-sized to h0's old sizes
+static void filter_by_membership(yak_ch_t *h0, const yak_ch_t *h1, bool keep_present)
+{
+	ChBox *b0 = box_of(h0), *b1 = box_of(h1);
+	assert(h0->k == h1->k && h0->pre == h1->pre && b0->eng->P == b1->eng->P);
+	std::lock_guard<std::mutex> lk(b0->mu);
+	Engine *e0 = b0->eng, *e1 = b1->eng;
+	const int pre = h0->pre, P = e0->P;
+	const uint64_t own_hi = (uint64_t)e0->rank << (pre - e0->lw);
+	std::vector<uint64_t> kept, off(P + 1, 0);
+	std::vector<uint32_t> caps(P, 0);
+	for_each_slice(e0, [&](int s0, int s1, LayoutOut &lo) {
+		const uint64_t n = lo.keys.size();
+		std::vector<uint64_t> q(n);
+		std::vector<int32_t> r(n, -1);
+		for (int s = s0; s < s1; ++s)
+			for (uint64_t i = lo.off[s - s0]; i < lo.off[s - s0 + 1]; ++i) q[i] = (lo.keys[i] >> YAK_COUNTER_BITS) << pre | own_hi | (uint64_t)s;
+		if (n) {
+			uint64_t *dq = b1->d_in.as<uint64_t>(n);
+			int32_t *dr = b1->d_aux.as<int32_t>(n);
+			YAKB_CUDA(cudaMemcpyAsync(dq, q.data(), n * 8, cudaMemcpyHostToDevice, e1->stream));
+			e1->get_batch(dq, n, dr);
+			YAKB_CUDA(cudaMemcpyAsync(r.data(), dr, n * 4, cudaMemcpyDeviceToHost, e1->stream));
+			YAKB_CUDA(cudaStreamSynchronize(e1->stream));
+		}
+		for (int s = s0; s < s1; ++s) {
+			for (uint64_t i = lo.off[s - s0]; i < lo.off[s - s0 + 1]; ++i)
+				if ((r[i] >= 0) == keep_present) kept.push_back(lo.keys[i]);
+			off[s + 1] = kept.size();
+			caps[s] = lo.size[s - s0]; // yak_ht_resize(f, kh_size(g0))
+		}
+	});
+	e0->rebuild(caps, off, kept.data());
+	h0->tot = e0->tot;
+}
+extern "C" void yak_ch_subtract(yak_ch_t *h0, const yak_ch_t *h1, int n_thread)
+{
+	GUARD_BEGIN
+	(void)n_thread;
+	filter_by_membership(h0, h1, false);
+	GUARD_END_VOID
+}
+extern "C" void yak_ch_isec(yak_ch_t *h0, const yak_ch_t *h1, int n_thread)
+{
+	GUARD_BEGIN
+	(void)n_thread;
+	filter_by_membership(h0, h1, true);
+	GUARD_END_VOID
+}
 
 // ------------------------------------------------------------------ dump / restore
 

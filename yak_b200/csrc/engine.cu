@@ -620,6 +620,15 @@ __global__ void build_layout_kernel(const uint64_t *__restrict__ cat, const uint
 	if (pre_flag[t]) resize(pre_val[t]);
 	for (uint64_t e = 0; e < m; ++e) { // khashl.h:197-221
 		const uint64_t key = src[e];
+		const uint32_t op = (uint32_t)key & YAKB_MAX_COUNT;
+		if (op) { // an operation recorded in the journal (Engine::OP_*)
+			const uint32_t r = (uint32_t)(key >> YAKB_COUNTER_BITS);
+			if (op == 1) resize(r);
+			else if (op == 2) { if (count >= (n >> 1) + (n >> 2)) resize(n + 1); }
+			else if (op == 3) { if ((uint64_t)count * 3 < n) resize(count * 3); }
+			else if (op == 4) { if (r > n) resize(r); }
+			continue;
+		}
 		if (count >= (n >> 1) + (n >> 2)) resize(n + 1);
 		const uint32_t mask = n - 1;
 		uint32_t i = kh_home(key, bits), start = i;
@@ -697,6 +706,8 @@ Engine *Engine::create(int k, int pre, int n_hash, int n_shift, int rank, int wo
 	YAKB_CUDA(cudaMemsetAsync(g->last_new, 0, g->P * sizeof(uint64_t), g->stream));
 	g->presize_flag.assign(g->P, 0);
 	g->presize_val.assign(g->P, 0);
+	g->nops.assign(g->P, 0);
+	g->max_req.assign(g->P, 0);
 	// htab.c:23-27 + bbf.c:9: a filter exists iff n_hash>0, n_shift>pre and 9 <= n_shift-pre <= 55
 	if (n_hash > 0 && n_shift > pre) {
 		g->n_hash = n_hash, g->n_shift = n_shift;
@@ -802,18 +813,19 @@ ChunkStats Engine::count_ascii(const uint8_t *d_asc, uint64_t n, int create_new)
 	return finish_chunk(nwords, create_new, w2, wm, nullptr, n, -1);
 }
 
-ChunkStats Engine::count_events(const uint64_t *d_ev, uint64_t n, int create_new, int only_s)
+ChunkStats Engine::count_events(const uint64_t *d_ev, uint64_t n, int create_new, int only_s, bool ignore_bloom)
 {
 	ChunkStats st = {0, 0, 0, 0};
 	if (n == 0) return st;
 	if (n >= 0x7FFFFF00ull) throw CudaError("[yakb] chunk too large (positions are 31-bit)");
-	return finish_chunk((n + 31) / 32, create_new, nullptr, nullptr, d_ev, n, only_s);
+	return finish_chunk((n + 31) / 32, create_new, nullptr, nullptr, d_ev, n, only_s, ignore_bloom);
 }
 
 // common tail of both front ends.  n_units: #bases (ASCII) or #events (array front end)
 ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t *w2, const uint32_t *wm,
-                                const uint64_t *d_ev, uint64_t n_units, int only_s)
+                                const uint64_t *d_ev, uint64_t n_units, int only_s, bool ignore_bloom)
 {
+	uint8_t *const bloom = ignore_bloom ? nullptr : this->bloom; // yak_ch_merge puts straight into the set (htab.c:262)
 	ChunkStats st = {0, 0, 0, 0};
 	const uint32_t Pmask = P - 1;
 	const bool longk = k >= 32;
@@ -1031,12 +1043,19 @@ void Engine::layout(int s0, int s1, LayoutOut &out, bool with_counts)
 		while (b1 < nsub) {
 			const int s = s0 + b1;
 			const bool tr = h_lp[b1] > h_ln[b1];
-			const uint32_t capf = final_capacity(presize_flag[s], presize_val[s], h_nkeys[b1], tr);
+			uint32_t capf = final_capacity(presize_flag[s], presize_val[s], h_nkeys[b1], tr);
+			if (nops[s]) { // scratch bound when operations sit in the journal: never below any explicit request
+				uint64_t bound = std::max<uint64_t>(final_capacity(presize_flag[s], presize_val[s], h_nkeys[b1], true), 4);
+				uint64_t want = std::max<uint64_t>((uint64_t)max_req[s], 3ull * h_nkeys[b1] + 4);
+				while (bound < want) bound *= 2;
+				capf = (uint32_t)std::min<uint64_t>(bound * 2, 0x80000000ull);
+			}
+			const uint64_t jlen = (uint64_t)h_nkeys[b1] + nops[s];
 			const uint64_t bw = 2 * (uint64_t)(capf < 32 ? 1 : capf >> 5);
-			const uint64_t add = (uint64_t)capf * 8 + bw * 4 + (uint64_t)h_nkeys[b1] * 16;
+			const uint64_t add = (uint64_t)capf * 8 + bw * 4 + jlen * 16;
 			if (b1 > b0 && bytes + add > budget) break;
 			bytes += add;
-			catoff.push_back(catoff.back() + h_nkeys[b1]);
+			catoff.push_back(catoff.back() + jlen);
 			koff.push_back(koff.back() + std::max<uint32_t>(capf, 4));
 			boff.push_back(boff.back() + std::max<uint64_t>(bw, 2));
 			trail.push_back(tr); pf.push_back(presize_flag[s]); pvv.push_back(presize_val[s]);
@@ -1049,6 +1068,7 @@ void Engine::layout(int s0, int s1, LayoutOut &out, bool with_counts)
 		uint8_t *d_trail, *d_pf;
 		YAKB_CUDA(cudaMalloc(&d_cat, std::max<uint64_t>(ncat, 1) * 8));
 		YAKB_CUDA(cudaMalloc(&d_out, std::max<uint64_t>(ncat, 1) * 8));
+		YAKB_CUDA(cudaMemsetAsync(d_out, 0, std::max<uint64_t>(ncat, 1) * 8, stream));
 		YAKB_CUDA(cudaMalloc(&d_keys, koff.back() * 8));
 		YAKB_CUDA(cudaMalloc(&d_bm, boff.back() * 4));
 		YAKB_CUDA(cudaMalloc(&d_catoff, (ns + 1) * 8)); YAKB_CUDA(cudaMalloc(&d_koff, (ns + 1) * 8)); YAKB_CUDA(cudaMalloc(&d_boff, (ns + 1) * 8));
@@ -1075,21 +1095,21 @@ void Engine::layout(int s0, int s1, LayoutOut &out, bool with_counts)
 		if (with_counts && ncat && cap)
 			fill_counts_kernel<<<cdiv(ncat, 256), 256, 0, stream>>>(d_out, d_catoff, ns, s0 + b0, ncat, slots, cap);
 		YAKB_CUDA(cudaGetLastError());
-		const size_t base = out.keys.size();
-		out.keys.resize(base + ncat);
-		if (ncat) YAKB_CUDA(cudaMemcpyAsync(out.keys.data() + base, d_out, ncat * 8, cudaMemcpyDeviceToHost, stream));
+		std::vector<uint64_t> tmp(ncat);
+		if (ncat) YAKB_CUDA(cudaMemcpyAsync(tmp.data(), d_out, ncat * 8, cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaMemcpyAsync(out.cap.data() + b0, d_ocap, ns * 4, cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaMemcpyAsync(out.size.data() + b0, d_osize, ns * 4, cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaStreamSynchronize(stream));
+		for (int t = 0; t < ns; ++t) { // a sub-table's run may be shorter than its journal (operation entries)
+			if (out.size[b0 + t] > catoff[t + 1] - catoff[t]) throw CudaError("[yakb] layout: inconsistent journal");
+			out.keys.insert(out.keys.end(), tmp.begin() + catoff[t], tmp.begin() + catoff[t] + out.size[b0 + t]);
+			out.off[b0 + t + 1] = out.keys.size();
+		}
 		if (getenv("YAKB_TIMING")) fprintf(stderr, "[T::layout] %d sub-tables %llu keys: gather %.4f build %.4f fill+copy %.4f s\n", ns, (unsigned long long)ncat, t_b - t_a, t_c - t_b, wall_s() - t_c);
-		for (int t = 0; t < ns; ++t) out.off[b0 + t + 1] = out.off[b0 + t] + (catoff[t + 1] - catoff[t]);
 		cudaFree(d_cat); cudaFree(d_out); cudaFree(d_keys); cudaFree(d_bm); cudaFree(d_catoff); cudaFree(d_koff); cudaFree(d_boff);
 		cudaFree(d_run); cudaFree(d_pv); cudaFree(d_ocap); cudaFree(d_osize); cudaFree(d_trail); cudaFree(d_pf);
 		b0 = b1;
 	}
-	// journal duplicates (only possible from a malformed restore) would make size < run length
-	for (int t = 0; t < nsub; ++t)
-		if (out.size[t] != out.off[t + 1] - out.off[t]) throw CudaError("[yakb] layout: journal holds duplicate keys");
 }
 
 void Engine::load_subtables(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys)
@@ -1097,7 +1117,7 @@ void Engine::load_subtables(const std::vector<uint32_t> &caps, const std::vector
 	const uint64_t n = off[P];
 	uint32_t mx = 0;
 	std::vector<uint32_t> cnt(P);
-	for (int s = 0; s < P; ++s) { cnt[s] = (uint32_t)(off[s + 1] - off[s]); mx = std::max(mx, cnt[s]); presize_flag[s] = 1; presize_val[s] = caps[s]; }
+	for (int s = 0; s < P; ++s) { cnt[s] = (uint32_t)(off[s + 1] - off[s]); mx = std::max(mx, cnt[s]); presize_flag[s] = 1; presize_val[s] = caps[s]; nops[s] = 0; max_req[s] = caps[s]; }
 	reserve(std::max<uint32_t>(mx, 8));
 	Segment seg;
 	seg.n = n;
@@ -1133,12 +1153,54 @@ void Engine::shrink(int min, int max)
 		off[s + 1] = kept.size();
 		caps[s] = lo.size[s]; // yak_ht_resize(f, kh_size(g))
 	}
-	// drop the old table and journal, rebuild from the kept keys
+	rebuild(caps, off, kept.data());
+}
+
+void Engine::rebuild(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys)
+{
+	// drop the old table and journal, start again from the given keys
 	journal_free_all();
 	if (slots) { YAKB_CUDA(cudaFree(slots)); slots = nullptr; cap = 0; }
 	YAKB_CUDA(cudaMemsetAsync(last_put, 0, P * 8, stream));
 	YAKB_CUDA(cudaMemsetAsync(last_new, 0, P * 8, stream));
-	load_subtables(caps, off, kept.data());
+	load_subtables(caps, off, keys);
+}
+
+void Engine::sizes(std::vector<uint32_t> &out)
+{
+	out.resize(P);
+	YAKB_CUDA(cudaMemcpyAsync(out.data(), nkeys, P * 4, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Engine::append_ops(const std::vector<uint64_t> &op)
+{
+	// a pending "put of an existing key after the last new key" must be replayed before the operation
+	std::vector<uint64_t> h_lp(P), h_ln(P), ent, off(P + 1, 0);
+	YAKB_CUDA(cudaMemcpyAsync(h_lp.data(), last_put, P * 8, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaMemcpyAsync(h_ln.data(), last_new, P * 8, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+	for (int s = 0; s < P; ++s) {
+		if (op[s]) {
+			if (h_lp[s] > h_ln[s]) { ent.push_back(OP_CHECK); ++nops[s]; }
+			ent.push_back(op[s]); ++nops[s];
+			const uint32_t kind = (uint32_t)op[s] & 1023;
+			if (kind == OP_RESIZE || kind == OP_RESIZE_IF_LARGER) max_req[s] = std::max<uint32_t>(max_req[s], (uint32_t)(op[s] >> 10));
+		}
+		off[s + 1] = ent.size();
+	}
+	if (ent.empty()) return;
+	Segment seg;
+	seg.n = ent.size();
+	seg.keys = (uint64_t*)journal_alloc(seg.n * 8);
+	seg.off = (uint64_t*)journal_alloc((uint64_t)(P + 1) * 8);
+	YAKB_CUDA(cudaMemcpyAsync(seg.keys, ent.data(), seg.n * 8, cudaMemcpyHostToDevice, stream));
+	YAKB_CUDA(cudaMemcpyAsync(seg.off, off.data(), (uint64_t)(P + 1) * 8, cudaMemcpyHostToDevice, stream));
+	// the replayed check clears the trailing state of the sub-tables that got an operation
+	for (int s = 0; s < P; ++s) if (op[s]) h_lp[s] = h_ln[s];
+	YAKB_CUDA(cudaMemcpyAsync(last_put, h_lp.data(), P * 8, cudaMemcpyHostToDevice, stream));
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+	journal.push_back(seg);
 }
 
 void qv_scan_ascii(Engine *e, const uint8_t *d_asc, uint64_t n, int16_t *d_cnt)

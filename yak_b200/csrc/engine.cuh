@@ -76,6 +76,15 @@ struct Engine {
 	uint64_t *last_put = nullptr, *last_new = nullptr;
 	std::vector<uint8_t> presize_flag;      // host
 	std::vector<uint32_t> presize_val;      // host
+	// Journal entries: low 10 bits 0 = put of key (entry>>10); otherwise an operation on the khashl
+	// set that is replayed at that point of the sequence (table set-ops):
+	//   1 resize(entry>>10)            htab.c:108 / khashl.h:152
+	//   2 load check of a put of an existing key (khashl.h:202-205, quirk Q3)
+	//   3 tighten: if (size*3 < capacity) resize(size*3)             htab.c:107-108
+	//   4 resize(r) if r > capacity, r = entry>>10                   htab.c:250-254 (merge pre_resize)
+	enum { OP_PUT = 0, OP_RESIZE = 1, OP_CHECK = 2, OP_TIGHTEN = 3, OP_RESIZE_IF_LARGER = 4 };
+	std::vector<uint32_t> nops;             // host: operation entries per sub-table
+	std::vector<uint32_t> max_req;          // host: largest explicit resize request per sub-table
 	std::vector<Segment> journal;
 	// journal segments are carved from big slabs (a cudaMalloc per chunk costs milliseconds)
 	struct Slab { char *p; size_t cap, used; };
@@ -98,7 +107,13 @@ struct Engine {
 	// bases: device ASCII (any non-ACGTU byte separates reads), n bytes
 	ChunkStats count_ascii(const uint8_t *d_asc, uint64_t n, int create_new);
 	// events: device array of hashed k-mers in file order; only_s >= 0 keeps one sub-table (htab.c:61)
-	ChunkStats count_events(const uint64_t *d_ev, uint64_t n, int create_new, int only_s);
+	ChunkStats count_events(const uint64_t *d_ev, uint64_t n, int create_new, int only_s, bool ignore_bloom = false);
+	// append one operation entry (0 = none) per sub-table to the journal
+	void append_ops(const std::vector<uint64_t> &op);
+	// replace the table by `keys` (stored form, per sub-table runs given by off) put in that order into
+	// khashl sets pre-sized to caps[] (htab.c:183 shrink, 295 subtract, 326 isec, 438 restore)
+	void rebuild(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys);
+	void sizes(std::vector<uint32_t> &out);  // distinct keys per sub-table
 
 	// ---- table-wide ops ----
 	void clear();                                  // htab.c:116-130
@@ -116,7 +131,7 @@ struct Engine {
 
 private:
 	ChunkStats finish_chunk(uint64_t n_words, int create_new, const uint64_t *w2, const uint32_t *wm,
-	                        const uint64_t *d_ev, uint64_t n_units, int only_s);
+	                        const uint64_t *d_ev, uint64_t n_units, int only_s, bool ignore_bloom = false);
 	void grow(uint32_t new_cap);
 };
 
