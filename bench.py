@@ -6,8 +6,9 @@ uniform genome (e=0.005, 1 % reads with an N), pass 1 of `yak count` (bloom + in
 synthetic stream as yak_b200/synth.py generated on the device.  A *step* is one batch of reads
 (--chunk-reads, default 2 M reads = 300 Mbp > L2) through the whole per-chunk path
 (pack -> fused extract+probe -> ordered bloom/insert of pending events -> journal).  Steps are
-consecutive batches from the start of the job; the table, bloom and journal persist across steps
-(the default 3 + 60 steps walk coverage 0 -> 6x of the 30x job: table growth and rehash included).
+consecutive batches from the start of the job; the table, bloom and journal persist across steps.
+The default 3 + 297 steps are the WHOLE first pass of cfg2 (600 M reads = 90 Gbp = 30x of 3 Gbp),
+table growth and rehash included.
 Each step is bracketed by its own pair of CUDA events; the step's input batch is generated on the
 device just before it, outside the timed region (max over ranks of the summed step times).
 
@@ -150,39 +151,84 @@ def make_sample_file(torch, lib, genome2, G, n_reads: int, first: int, path: str
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation on a bounded sample per step."""
+    """--impl reference: the UNMODIFIED reference (oracle/_ref/yak count) on the host cores, same metric.
+
+    One run of `yak count -k31 -p12 -b<bf> -K<step bases> -t<cores>` over (W+K) batches of the cfg2 read
+    stream; the reference prints one progress line per batch with its wall clock (count.c:140), so the
+    time of step i is the difference of consecutive pass-1 lines.  The batches are a bounded sample
+    (at most ~12 M reads in total) so the whole run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import re
     import numpy as np
-    from yak_b200 import synth
-    threads = os.cpu_count() or 1
-    # bounded sample of the cfg2 stream: a window of the genome keeps host generation cheap while
-    # the read model (length, error, N rate, strand) and the -b/-p/-k flags stay those of cfg2
-    n_reads = args.ref_reads
-    Gs = min(args.genome, 50_000_000)
+    W, KS = args.warmup, args.steps
+    total_reads = int(min(12_000_000, (W + KS) * args.chunk_reads))
+    per = max(2000, total_reads // (W + KS))
+    n_reads = per * (W + KS)
+    G = args.genome
     fn = os.path.join(shm_dir(), f"yakb_refarm_{os.getpid()}.fq")
-    genome = synth.genome_codes(SEED_G, Gs)
-    with open(fn, "wb") as f:
-        f.write(synth.reads_file_bytes(SEED_G, Gs, SEED_R, n_reads, L, ERR, NPCT, fastq=True, genome=genome))
-    codes = synth.read_codes(SEED_G, Gs, SEED_R, 0, n_reads, L, ERR, NPCT, genome)
-    n_ev = synth.count_events(codes, K)
+    n_ev = None
+    try:  # the device generator (not on the timed path) writes the sample when a GPU is present
+        import torch
+        from yak_b200 import capi
+        if capi.lib().yakb_device_count() > 0:
+            lib = capi.lib()
+            genome2 = torch.empty((G + 31) // 32 + 1, dtype=torch.int64, device="cuda")
+            lib.yakb_synth_genome_dev(SEED_G, G, genome2.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            n_ev = make_sample_file(torch, lib, genome2, G, n_reads, 0, fn)
+            del genome2
+            torch.cuda.empty_cache()
+    except Exception:  # noqa: BLE001
+        n_ev = None
+    if n_ev is None:  # no GPU: numpy generator on a window of the genome (same read model)
+        from yak_b200 import synth
+        G = min(G, 50_000_000)
+        genome = synth.genome_codes(SEED_G, G)
+        with open(fn, "wb") as f:
+            f.write(synth.reads_file_bytes(SEED_G, G, SEED_R, n_reads, L, ERR, NPCT, fastq=True, genome=genome))
+        n_ev = synth.count_events(synth.read_codes(SEED_G, G, SEED_R, 0, n_reads, L, ERR, NPCT, genome), K)
+    threads = os.cpu_count() or 1
     bf = args.bf_shift
-    times = []
+    ref = ref_binary()
+    out = os.path.join(shm_dir(), f"yakb_refarm_{os.getpid()}.yak")
     kind = "reference"
-    for i in range(args.warmup + args.steps):
-        v, dt, kind, threads = cpu_reference_run(fn, n_ev, threads, bf)
-        if i >= args.warmup:
-            times.append(dt)
-    os.unlink(fn)
-    ms = 1000.0 * sum(times) / len(times)
-    val = n_ev / (ms / 1000.0)
-    line = {"impl": "reference", "metric": "k-mer events/s (k=31 count, both passes of -b)", "value": val, "unit": "events/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "cfg2", "k": K, "pre": PRE, "bf_shift": bf, "read_len": L, "sample": f"{n_reads} reads of a {Gs} bp window"},
+    if ref:
+        cmd = [ref, "count", f"-k{K}", f"-p{PRE}", f"-t{threads}", f"-H{NH}", f"-K{per * L}", "-o", out]
+        if bf > 0:
+            cmd.append(f"-b{bf}")
+        t0 = time.time()
+        r = subprocess.run(cmd + [fn], check=True, capture_output=True, text=True)
+        wall = time.time() - t0
+        stamps = [float(m.group(1)) for m in re.finditer(r"\[M::worker_pipeline::([0-9.]+)\*", r.stderr)]
+        stamps = stamps[:W + KS]  # pass 1 (the second pass prints the same number of lines again)
+        if len(stamps) == W + KS and KS > 0:
+            t_start = stamps[W - 1] if W > 0 else 0.0
+            ms_total = (stamps[-1] - t_start) * 1000.0
+        else:  # fewer lines than expected (reads shorter than a batch): fall back to the whole pass
+            ms_total = wall * 1000.0 * KS / (2 * (W + KS) if bf > 0 else (W + KS))
+    else:  # the oracle port, single thread, whole run
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        t0 = time.time()
+        h = oracle_lib.lib().yo_count_file(fn.encode(), K, PRE, bf, NH, None, None)
+        ms_total = (time.time() - t0) * 1000.0 * KS / (W + KS)
+        oracle_lib.lib().yo_ch_destroy(h)
+        kind, threads = "port", 1
+    for p in (fn, out):
+        try:
+            os.unlink(p)
+        except OSError:
+            pass
+    ev_per_step = n_ev / (W + KS)
+    val = ev_per_step * KS / (ms_total / 1000.0)
+    line = {"impl": "reference", "metric": "k-mer events/s (k=31, pass 1 of `yak count -b37`, chunk steps)", "value": val,
+            "unit": "events/s", "n_gpus": args.gpus, "steps": KS, "warmup": W, "ms_per_step": ms_total / KS,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "cfg2", "k": K, "pre": PRE, "bf_shift": bf, "bf_n_hash": NH, "read_len": L, "genome_bp": G,
+                       "reads_per_step": per, "sample": f"{n_reads} reads in {W + KS} batches of {per}"},
             "cpu_baseline": {"value": val, "unit": "events/s", "cores": threads, "kind": kind,
-                             "sample": f"yak count -k{K} -p{PRE} -b{bf} -t{threads} on {n_reads} FASTQ reads ({n_ev} events)"},
+                             "sample": f"yak count -k{K} -p{PRE} -b{bf} -t{threads} -K{per * L}: pass-1 batches {W + 1}..{W + KS} of {per} reads ({int(ev_per_step)} events each), timed from the reference's own progress lines"},
             "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -190,14 +236,13 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=297)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome", type=int, default=3_000_000_000)
     ap.add_argument("--chunk-reads", type=int, default=2_000_000)
     ap.add_argument("--bf-shift", type=int, default=BF)
     ap.add_argument("--e2e-reads", type=int, default=2_000_000)
-    ap.add_argument("--ref-reads", type=int, default=2_000_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verbose", action="store_true")
