@@ -242,7 +242,7 @@ def main():
     ap.add_argument("--genome", type=int, default=3_000_000_000)
     ap.add_argument("--chunk-reads", type=int, default=2_000_000)
     ap.add_argument("--bf-shift", type=int, default=BF)
-    ap.add_argument("--e2e-reads", type=int, default=2_000_000)
+    ap.add_argument("--e2e-reads", type=int, default=4_000_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verbose", action="store_true")
@@ -364,6 +364,9 @@ def main():
         "compact": 8.0 * n_pending,
         "pack_ascii": 1.375 * nr * rec * KS,
     }
+    # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r01_top_kernels_ncu.md,
+    # step ~10 of this workload; dram__bytes_read.sum + dram__bytes_write.sum)
+    ncu_traffic = {"k1_fused": 7.852583e9 + 1.164658e9, "group_insert": 20.139495e9 + 15.937980e9}
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, [0, 0])
     roof = None
     if dom[0]:
@@ -371,7 +374,8 @@ def main():
         ab = alg_bytes.get(nm, 0.0)
         ach = ab / (tms / 1000.0) / 1e9 if tms > 0 else 0.0
         roof = {"bound": "hbm", "kernel": nm, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_kind, "launches": nl, "kernel_ms_total": tms,
+                "traffic": ncu_traffic.get(nm), "traffic_source": "profiles/r01_top_kernels_ncu.md" if nm in ncu_traffic else None,
+                "peak_source": peak_kind, "launches": nl, "kernel_ms_total": tms,
                 "algorithmic_bytes_per_launch": ab / max(nl, 1),
                 "share_of_step": tms / ms if ms > 0 else None}
     line = {"metric": "k-mer events/s (k=31, pass 1 of `yak count -b37`, chunk steps)", "value": value, "unit": "events/s",
@@ -385,26 +389,38 @@ def main():
             "gpu_launches": int(launches), "kernels_ms": {k: round(v[0], 3) for k, v in prof.items()},
             "clocks": clk, "roofline": roof}
 
-    # ---- e2e through yak_count(file) + cpu baseline on the same sample file
+    # ---- e2e: the same metric (pass-1 events/s) through the reference-facing C call on a HOST file:
+    #      yak_count(fn, opt, NULL) = parse + H2D + every kernel of the pass, result (h->tot) read back.
+    #      The whole `yak count -b37` job (both passes + shrink + dump) on the same file is reported next
+    #      to it together with the unmodified reference's time for that job (cpu_baseline).
     if not args.no_e2e:
         fn = os.path.join(shm_dir(), f"yakb_bench_{os.getpid()}.fq")
         n_ev = make_sample_file(torch, lib, genome2, G, args.e2e_reads, 0, fn)
         out = os.path.join(shm_dir(), f"yakb_bench_{os.getpid()}.yak")
         fsz = os.path.getsize(fn)
+        o = capi.copt(K, PRE, args.bf_shift, NH)
+        lib.yak_ch_destroy(lib.yak_count(fn.encode(), C.byref(o), None))   # warm-up: page cache, pinned buffers, context
+        t0 = time.time()
+        hh = lib.yak_count(fn.encode(), C.byref(o), None)
+        tot1 = int(hh.contents.tot)
+        dt1 = time.time() - t0
+        lib.yak_ch_destroy(hh)
         t0 = time.time()
         hh = capi.count_file(fn, k=K, pre=PRE, bf_shift=args.bf_shift, bf_n_hash=NH)
         lib.yak_ch_dump(hh, out.encode())
         dt = time.time() - t0
         osz = os.path.getsize(out)
         lib.yak_ch_destroy(hh)
-        line["e2e"] = {"value": n_ev / dt, "unit": "events/s", "h2d_bytes_per_step": 2 * args.e2e_reads * (L + 1),
-                       "d2h_bytes_per_step": osz, "seconds": dt,
-                       "what": f"yak_count x2 + shrink + dump of {args.e2e_reads} FASTQ reads ({fsz} B in tmpfs), {n_ev} events"}
+        line["e2e"] = {"value": n_ev / dt1, "unit": "events/s", "h2d_bytes_per_step": args.e2e_reads * (L + 1),
+                       "d2h_bytes_per_step": 8, "seconds": dt1, "distinct_after_pass1": tot1,
+                       "what": f"yak_count(pass 1, -b{args.bf_shift}) of {args.e2e_reads} FASTQ reads ({fsz} B in tmpfs): parse + H2D + kernels, {n_ev} events"}
+        line["e2e_full_job"] = {"value": n_ev / dt, "unit": "input events/s", "seconds": dt, "h2d_bytes": 2 * args.e2e_reads * (L + 1),
+                                "d2h_bytes": osz, "what": "yak_count x2 + yak_ch_shrink + yak_ch_dump of the same file (= `yak count -b37 -o`)"}
         if not args.no_cpu:
             threads = os.cpu_count() or 1
             v, dtc, kind, threads = cpu_reference_run(fn, n_ev, threads, args.bf_shift)
-            line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": threads, "kind": kind, "seconds": dtc,
-                                    "sample": f"yak count -k{K} -p{PRE} -b{args.bf_shift} -t{threads} on the e2e sample file ({n_ev} events)"}
+            line["cpu_baseline"] = {"value": v, "unit": "input events/s", "cores": threads, "kind": kind, "seconds": dtc,
+                                    "sample": f"whole job `yak count -k{K} -p{PRE} -b{args.bf_shift} -t{threads} -o` on the e2e sample file ({n_ev} events); compare with e2e_full_job"}
         for p in (fn, out):
             try:
                 os.unlink(p)
