@@ -145,3 +145,24 @@ def test_gpu_counting_continues_after_setops(oracle, yakb):
     OL.yo_ch_tighten(ho); L.yak_ch_tighten(hg)
     assert yakb.dump_bytes(hg) == oracle.dump_bytes(ho)
     L.yak_ch_destroy(hg); OL.yo_ch_destroy(ho)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(O.REF_YAK), reason="oracle/_ref not built")
+def test_cli_setop_commands_equal_reference_binary():
+    """recount / subtract / isec / print of the CLI against the reference binary's output"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "yak_b200", "bin", "yak-b200")
+    fa, fb, fc = _yak_files()
+    reads = G.input_path("reads_q")
+    for args in (["subtract", fa, fb], ["isec", fa, fb, fc], ["recount", fc, reads]):
+        o1, o2 = os.path.join(util.TMP, "yakb_cli_a.yak"), os.path.join(util.TMP, "yakb_cli_b.yak")
+        subprocess.run([O.REF_YAK, args[0], "-o", o1] + args[1:], check=True, capture_output=True)
+        subprocess.run([exe, args[0], "-o", o2] + args[1:], check=True, capture_output=True)
+        a, b = open(o1, "rb").read(), open(o2, "rb").read()
+        assert a == b, args[0] + ": " + util.explain_diff(b, a)
+    for flags in ([], ["-c"]):
+        r1 = subprocess.run([O.REF_YAK, "print"] + flags + [fc], check=True, capture_output=True).stdout
+        r2 = subprocess.run([exe, "print"] + flags + [fc], check=True, capture_output=True).stdout
+        assert r1 == r2 and len(r1) > 1000

@@ -162,6 +162,70 @@ static int cmd_inspect(int argc, char *argv[])
 	return 0;
 }
 
+/* reference main.c:66-88: tighten, count the k-mers of a table again from other reads */
+static int cmd_recount(int argc, char *argv[])
+{
+	yak_ch_t *h;
+	char *fn_out = "-";
+	int c;
+	while ((c = getopt(argc, argv, "o:")) >= 0)
+		if (c == 'o') fn_out = optarg;
+	if (argc - optind < 2) { fprintf(stderr, "Usage: yak-b200 recount [-o out.yak] <in.yak> <in.fa>\n"); return 1; }
+	if ((h = yak_ch_restore(argv[optind])) == 0) { fprintf(stderr, "ERROR: failed to load '%s'\n", argv[optind]); return 1; }
+	yak_ch_tighten(h);
+	yak_recount(argv[optind + 1], h);
+	yak_ch_dump(h, fn_out);
+	yak_ch_destroy(h);
+	return 0;
+}
+
+/* reference main.c:217-284: k-mers of the first table absent from (subtract) / present in (isec) the others */
+static int cmd_setop(int argc, char *argv[], int isec)
+{
+	yak_ch_t *h0, *h1;
+	char *fn_out = "-";
+	int c, i, n_thread = 8;
+	while ((c = getopt(argc, argv, "o:t:")) >= 0) {
+		if (c == 'o') fn_out = optarg;
+		else if (c == 't') n_thread = atoi(optarg);
+	}
+	if (argc - optind < 2) { fprintf(stderr, "Usage: yak-b200 %s [-o out.yak] <in0.yak> <in1.yak> [...]\n", isec ? "isec" : "subtract"); return 1; }
+	if ((h0 = yak_ch_restore(argv[optind])) == 0) { fprintf(stderr, "ERROR: failed to load '%s'\n", argv[optind]); return 1; }
+	for (i = optind + 1; i < argc; ++i) {
+		if ((h1 = yak_ch_restore(argv[i])) == 0) { fprintf(stderr, "ERROR: failed to load '%s'\n", argv[i]); return 1; }
+		if (isec) yak_ch_isec(h0, h1, n_thread); else yak_ch_subtract(h0, h1, n_thread);
+		yak_ch_destroy(h1);
+	}
+	yak_ch_dump(h0, fn_out);
+	yak_ch_destroy(h0);
+	return 0;
+}
+
+/* reference main.c:286-323: the k-mers of a table as text (k <= 31), optionally with counts */
+static int cmd_print(int argc, char *argv[])
+{
+	yak_ch_t *h;
+	int w, j, c, out_cnt = 0;
+	uint32_t i, n;
+	char buf[65];
+	while ((c = getopt(argc, argv, "c")) >= 0)
+		if (c == 'c') out_cnt = 1;
+	if (argc - optind < 1) { fprintf(stderr, "Usage: yak-b200 print [-c] <in.yak>\n"); return 1; }
+	if ((h = yak_ch_restore(argv[optind])) == 0) return 1;
+	yak_ch_tighten(h);
+	for (w = 0; w < 1 << h->pre; ++w) {
+		yak_knt_t *a = yak_ch_getseq(h, w, &n);
+		for (i = 0; i < n; ++i) {
+			for (j = 0; j < h->k; ++j) buf[h->k - j - 1] = "ACGT"[a[i].x >> j * 2 & 3];
+			buf[h->k] = 0;
+			if (out_cnt) printf("%s\t%d\n", buf, a[i].c); else puts(buf);
+		}
+		free(a);
+	}
+	yak_ch_destroy(h);
+	return 0;
+}
+
 int main(int argc, char *argv[])
 {
 	int ret, i;
@@ -170,12 +234,20 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "Usage: yak-b200 <command> <argument>\n");
 		fprintf(stderr, "Command:\n");
 		fprintf(stderr, "  count     count k-mers\n");
+		fprintf(stderr, "  recount   count existing k-mers\n");
+		fprintf(stderr, "  subtract  subtract k-mer sets\n");
+		fprintf(stderr, "  isec      intersect k-mer sets\n");
+		fprintf(stderr, "  print     print k-mers for k<=31\n");
 		fprintf(stderr, "  qv        evaluate quality values\n");
 		fprintf(stderr, "  inspect   k-mer hash tables\n");
 		fprintf(stderr, "  version   print version number\n");
 		return 1;
 	}
 	if (strcmp(argv[1], "count") == 0) ret = cmd_count(argc - 1, argv + 1);
+	else if (strcmp(argv[1], "recount") == 0) ret = cmd_recount(argc - 1, argv + 1);
+	else if (strcmp(argv[1], "subtract") == 0) ret = cmd_setop(argc - 1, argv + 1, 0);
+	else if (strcmp(argv[1], "isec") == 0) ret = cmd_setop(argc - 1, argv + 1, 1);
+	else if (strcmp(argv[1], "print") == 0) ret = cmd_print(argc - 1, argv + 1);
 	else if (strcmp(argv[1], "qv") == 0) ret = cmd_qv(argc - 1, argv + 1);
 	else if (strcmp(argv[1], "inspect") == 0) ret = cmd_inspect(argc - 1, argv + 1);
 	else if (strcmp(argv[1], "version") == 0) { puts(YAKS_VERSION); return 0; }

@@ -333,12 +333,6 @@ __global__ void __launch_bounds__(256) compact_array(const uint64_t *__restrict_
 	}
 }
 
-__global__ void iota_kernel(uint32_t *a, uint64_t n)
-{
-	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-	if (i < n) a[i] = (uint32_t)i;
-}
-
 // pending events per sub-table (upper bound of the new keys a chunk can add): shared-memory bins
 __global__ void __launch_bounds__(256) pend_hist_kernel(const uint64_t *__restrict__ pv, uint64_t n, uint32_t Pmask, uint32_t *pend, int smem_ok)
 {
@@ -930,7 +924,7 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 		{ ProfScope ps("post_pending", stream);
 		post_pending<<<std::min<uint32_t>(cdiv(n_pending, 256), nsm * 4), 256, sm2, stream>>>(pv, ppos, pflag, n_pending, Pmask, lput, lnew, smem2, stats); }
 		YAKB_CUDA(cudaGetLastError());
-		note_launch(6); // compact, pend_hist, max_need, iota, group_insert, post_pending
+		note_launch(5); // compact, pend_hist, max_need, group_insert, post_pending
 		// new keys in file order, then stably by sub-table -> journal segment
 		uint64_t *newv = b_newv.as<uint64_t>(n_pending);
 		uint32_t *d_nsel = (uint32_t*)(stats + 2);
