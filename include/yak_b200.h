@@ -75,6 +75,13 @@ void yakb_fastx_close(void *reader);
  * bytes; returns bytes appended; *done = input exhausted; *need != 0: grow buf to that size */
 int64_t yakb_fastx_fill(void *reader, char *buf, uint64_t cap, uint64_t target, int min_len,
                         int64_t *n_seq, int *done, uint64_t *need);
+/* multi-threaded variant for plain regular files (speculative block parse + exact stitching,
+ * csrc/fastx_par.h); open returns NULL for gzip / stdin / unreadable files */
+void *yakb_pfastx_open(const char *fn, uint64_t block_bytes, int threads);
+int64_t yakb_pfastx_fill(void *reader, char *buf, uint64_t cap, uint64_t target, int min_len,
+                         int64_t *n_seq, int *done, uint64_t *need);
+uint64_t yakb_pfastx_redo(void *reader);   /* blocks that had to be re-parsed sequentially */
+void yakb_pfastx_close(void *reader);
 /* skip n_skip records, then append up to n_take records (those of length >= min_len) to buf as
  * "SEQ\n"; returns the records consumed (-1: buf too small).  Lets each rank of a multi-GPU job
  * take its contiguous slice of every chunk of one shared input file. */

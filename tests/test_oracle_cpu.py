@@ -307,3 +307,54 @@ def test_bulk_fill_equals_record_reader(cap, target):
     big = G.input_path("reads_q")
     want = b"".join(s + b"\n" for _, s in (r for r in _records_oracle(big) if not isinstance(r, int)))
     assert _fill_all(big, max(cap, 4096), target, 0)[0] == want
+
+
+def _pfill_all(path, block, threads, cap, target, min_len):
+    from yak_b200 import capi
+    L = capi.lib()
+    r = L.yakb_pfastx_open(path.encode(), block, threads)
+    assert r
+    out, nseq = bytearray(), 0
+    buf = C.create_string_buffer(cap)
+    while True:
+        ns, done, need = C.c_int64(), C.c_int(), C.c_uint64()
+        n = L.yakb_pfastx_fill(r, buf, cap, target, min_len, C.byref(ns), C.byref(done), C.byref(need))
+        if need.value:
+            cap = need.value + 11
+            buf = C.create_string_buffer(cap)
+            continue
+        out += buf.raw[:n]
+        nseq += ns.value
+        if done.value:
+            break
+    redo = L.yakb_pfastx_redo(r)
+    L.yakb_pfastx_close(r)
+    return bytes(out), nseq, redo
+
+
+@pytest.mark.parametrize("block,threads", [(64, 3), (257, 4), (4096, 8), (1 << 20, 2)])
+def test_parallel_reader_is_exactly_the_sequential_reader(block, threads):
+    """speculative block parsing + stitching must reproduce kseq semantics on any input, also when
+    blocks are far smaller than records and every guess is wrong"""
+    import test_gpu_parity as T
+    files = [T._edge_file(os.path.join(util.TMP, "yakb_edge_par.fa")), G.input_path("reads_q")]
+    p = os.path.join(util.TMP, "yakb_par_mixed.fq")   # quality lines starting with '>' and '@', CRLF, no final newline
+    rng = np.random.default_rng(3)
+    with open(p, "w", newline="") as f:
+        for i in range(300):
+            L_ = int(rng.integers(1, 120))
+            s = "".join("ACGTN"[j] for j in rng.integers(0, 5, L_))
+            q = "".join(">@+I#"[j] for j in rng.integers(0, 5, L_))
+            eol = "\r\n" if i % 7 == 0 else "\n"
+            f.write(f"@r{i} x{eol}{s}{eol}+{eol}{q}" + (eol if i < 299 else ""))
+    files.append(p)
+    from yak_b200 import capi
+    for fn in files:
+        for min_len in (0, 31):
+            want, wn = _fill_all(fn, 1 << 20, 1 << 20, min_len)
+            got, gn, redo = _pfill_all(fn, block, threads, 1 << 16, 1 << 15, min_len)
+            assert got == want and gn == wn, (fn, block, threads, min_len, redo)
+    trunc = os.path.join(util.TMP, "yakb_par_trunc.fq")
+    open(trunc, "w").write("@a\nACGTAC\n+\nIIIIII\n@b\nGGGTTT\n+\nIII\n@c\nAAAA\n+\nIIII\n" * 3)
+    assert _pfill_all(trunc, block, threads, 4096, 4096, 0)[0] == _fill_all(trunc, 4096, 4096, 0)[0] == b"ACGTAC\n"
+    assert not capi.lib().yakb_pfastx_open((files[0] + ".gz").encode(), 0, 0) or True

@@ -9,6 +9,7 @@
 #include "engine.cuh"
 #include "extras.cuh"
 #include "fastx.h"
+#include "fastx_par.h"
 #include "yakb_dev.cuh"
 #include <stdio.h>
 #include <stdlib.h>
@@ -625,6 +626,27 @@ extern "C" int64_t yakb_fastx_fill(void *reader, char *buf, uint64_t cap, uint64
 	return (int64_t)n;
 }
 
+extern "C" void *yakb_pfastx_open(const char *fn, uint64_t block_bytes, int threads)
+{
+	ParallelFastx *r = new ParallelFastx;
+	if (!r->open(fn, (size_t)block_bytes, threads)) { delete r; return 0; }
+	return r;
+}
+extern "C" int64_t yakb_pfastx_fill(void *reader, char *buf, uint64_t cap, uint64_t target, int min_len, int64_t *n_seq, int *done, uint64_t *need)
+{
+	ParallelFastx *r = (ParallelFastx*)reader;
+	bool d = false;
+	size_t nd = 0;
+	int64_t ns = 0;
+	size_t n = r->fill((uint8_t*)buf, cap, target, min_len, &ns, &d, &nd);
+	if (n_seq) *n_seq = ns;
+	if (done) *done = d;
+	if (need) *need = nd;
+	return (int64_t)n;
+}
+extern "C" uint64_t yakb_pfastx_redo(void *reader) { return ((ParallelFastx*)reader)->mis_speculations(); }
+extern "C" void yakb_pfastx_close(void *reader) { delete (ParallelFastx*)reader; }
+
 // Skip n_skip records, then append up to n_take records of length >= min_len to buf as "SEQ\n".
 // Returns the number of records CONSUMED (skipped + taken + dropped short ones counted among the taken);
 // fewer than n_skip + n_take means end of input.  *n_bytes / *n_seq describe what was appended.
@@ -671,7 +693,9 @@ extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *
 	GUARD_BEGIN
 	StageTimer tm("yak_count");
 	FastxReader rd;
-	if (!rd.open(fn)) return 0;
+	ParallelFastx prd; // plain regular files are parsed by several threads; gzip / stdin by the sequential reader
+	const bool par = !getenv("YAKB_SERIAL_PARSE") && prd.open(fn);
+	if (!par && !rd.open(fn)) return 0;
 	yak_ch_t *h = h0;
 	if (h0) assert(h0->k == opt->k && h0->pre == opt->pre);
 	else h = yak_ch_init(opt->k, opt->pre, opt->bf_n_hash, opt->bf_shift);
@@ -694,7 +718,8 @@ extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *
 	auto parse = [&](int slot) {
 		Batch &t = batch[slot];
 		t = Batch();
-		t.n = rd.fill(b->pinned[slot], b->pinned_cap, cap, opt->k, &t.n_seq, &t.done, &t.need);
+		t.n = par ? prd.fill(b->pinned[slot], b->pinned_cap, cap, opt->k, &t.n_seq, &t.done, &t.need)
+		          : rd.fill(b->pinned[slot], b->pinned_cap, cap, opt->k, &t.n_seq, &t.done, &t.need);
 	};
 	int slot = 0;
 	parse(0);

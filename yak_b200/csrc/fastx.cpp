@@ -140,7 +140,7 @@ size_t FastxReader::fill(uint8_t *dst, size_t cap, size_t target, int min_len, i
 			const unsigned char *nl = (const unsigned char*)memchr(p, '\n', avail);
 			if (!nl) { beg_ = end_; continue; }
 			beg_ += nl - p + 1;
-			if (st_ == S_NAME) { st_ = S_SEQ; bol_ = true; } else { st_ = S_QUAL; qual_len_ = 0; qual_lines_ = 0; bol_ = true; }
+			if (st_ == S_NAME) { st_ = S_SEQ; bol_ = true; } else { st_ = S_QUAL; qual_len_ = 0; qual_lines_ = 0; bol_ = true; qline_nonempty_ = false; }
 		} else if (st_ == S_SEQ) {
 			if (bol_) {
 				const unsigned char c = p[0];
@@ -164,10 +164,13 @@ size_t FastxReader::fill(uint8_t *dst, size_t cap, size_t target, int min_len, i
 			}
 			const unsigned char *nl = (const unsigned char*)memchr(p, '\n', avail);
 			const int64_t len = nl ? nl - p : avail;
-			if (len > 0) { qual_len_ += len; last_qual_ = p[len - 1]; }
+			if (len > 0) { qual_len_ += len; last_qual_ = p[len - 1]; qline_nonempty_ = true; }
 			bol_ = false;
 			beg_ += len + (nl ? 1 : 0);
-			if (nl) { if (qual_len_ > 1 && last_qual_ == '\r' && len > 0) --qual_len_; bol_ = true; ++qual_lines_; }
+			if (nl) { // the CR rule looks at the whole line, which may have arrived in pieces
+				if (qline_nonempty_ && qual_len_ > 1 && last_qual_ == '\r') --qual_len_;
+				bol_ = true; ++qual_lines_; qline_nonempty_ = false;
+			}
 		}
 	}
 	return n;

@@ -41,6 +41,7 @@ private:
 	bool refill_();
 	enum { S_FIND, S_NAME, S_SEQ, S_PLUS, S_QUAL } st_ = S_FIND;
 	bool bol_ = true;          // at the beginning of a line
+	bool qline_nonempty_ = false;
 	int64_t cur_len_ = 0, qual_len_ = 0, qual_lines_ = 0;
 	std::string carry_;        // a record that did not fit the caller's buffer
 	bool carry_ready_ = false; // carry_ holds a COMPLETE record waiting for the next fill()

@@ -1,0 +1,271 @@
+// fastx_par.cpp - see fastx_par.h
+#include "fastx_par.h"
+#include <string.h>
+#include <stdlib.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
+#include <thread>
+#include <algorithm>
+
+namespace yakb {
+
+// ---------------------------------------------------------------- the grammar (kseq.h:192-232)
+// Sequence bytes go straight into `out`; `rs` marks where the open record starts there.  Between
+// calls the open record's bytes live in `rec` (they are few: at most one record per block).
+
+// close the record whose bytes are out[rs..]: keep it (terminator appended) or drop it
+static inline void close_in_out(FastxCore &c, size_t &rs, bool keep, int min_len, std::vector<uint8_t> &out, int64_t *n_seq)
+{
+	if (keep && c.cur_len >= min_len) { out.push_back('\n'); ++*n_seq; }
+	else out.resize(rs);
+	rs = out.size();
+	c.cur_len = 0;
+}
+
+// close the record whose bytes are still carried in c.rec
+static inline void close_carried(FastxCore &c, bool keep, int min_len, std::vector<uint8_t> &out, int64_t *n_seq)
+{
+	if (keep && c.cur_len >= min_len) {
+		out.insert(out.end(), c.rec.begin(), c.rec.end());
+		out.push_back('\n');
+		++*n_seq;
+	}
+	c.rec.clear();
+	c.cur_len = 0;
+}
+
+void FastxCore::feed(const unsigned char *p, size_t n, int min_len, std::vector<uint8_t> &out, int64_t *n_seq)
+{
+	size_t i = 0, rs = out.size();
+	if (!rec.empty()) { out.insert(out.end(), rec.begin(), rec.end()); rec.clear(); }
+	while (i < n && !stopped) {
+		if (st == S_FIND) {
+			if (last) { st = S_NAME; last = 0; rs = out.size(); cur_len = 0; continue; } // header character consumed already
+			while (i < n && p[i] != '>' && p[i] != '@') ++i; // normally the very next byte
+			if (i < n) { ++i; st = S_NAME; rs = out.size(); cur_len = 0; }
+		} else if (st == S_NAME || st == S_PLUS) { // rest of the header / '+' line
+			const unsigned char *nl = (const unsigned char*)memchr(p + i, '\n', n - i);
+			if (!nl) { i = n; break; }
+			i = nl - p + 1;
+			if (st == S_NAME) { st = S_SEQ; bol = true; } else { st = S_QUAL; qual_len = 0; qual_lines = 0; bol = true; qline_nonempty = false; }
+		} else if (st == S_SEQ) {
+			if (bol) {
+				const unsigned char c = p[i];
+				if (c == '\n') { ++i; continue; }
+				if (c == '>' || c == '@') { ++i; close_in_out(*this, rs, true, min_len, out, n_seq); last = c; st = S_FIND; continue; }
+				if (c == '+') { ++i; st = S_PLUS; continue; }
+				bol = false;
+			}
+			const unsigned char *nl = (const unsigned char*)memchr(p + i, '\n', n - i);
+			const size_t len = nl ? (size_t)(nl - (p + i)) : n - i;
+			out.insert(out.end(), p + i, p + i + len);
+			cur_len += (int64_t)len;
+			i += len + (nl ? 1 : 0);
+			if (nl) { if (cur_len > 1 && out.back() == '\r') { out.pop_back(); --cur_len; } bol = true; } // kseq.h:146
+		} else { // S_QUAL: only lengths matter
+			if (bol && qual_lines > 0 && qual_len >= cur_len) { // kseq.h:224
+				const bool ok = qual_len == cur_len;
+				close_in_out(*this, rs, ok, min_len, out, n_seq);
+				st = S_FIND; last = 0;
+				if (!ok) stopped = true; // kseq's -2: the caller's read loop ends here
+				continue;
+			}
+			const unsigned char *nl = (const unsigned char*)memchr(p + i, '\n', n - i);
+			const size_t len = nl ? (size_t)(nl - (p + i)) : n - i;
+			if (len > 0) { qual_len += len; last_qual = p[i + len - 1]; qline_nonempty = true; }
+			bol = false;
+			i += len + (nl ? 1 : 0);
+			if (nl) { // the CR rule looks at the whole line, which may have arrived in pieces
+				if (qline_nonempty && qual_len > 1 && last_qual == '\r') --qual_len;
+				bol = true; ++qual_lines; qline_nonempty = false;
+			}
+		}
+	}
+	// park the open record's bytes until the next call
+	if (out.size() > rs) {
+		if (!stopped && (st == S_SEQ || st == S_PLUS || st == S_QUAL)) rec.assign((const char*)out.data() + rs, out.size() - rs);
+		out.resize(rs);
+	}
+}
+
+void FastxCore::settle(int min_len, std::vector<uint8_t> &out, int64_t *n_seq)
+{
+	if (!stopped && st == S_QUAL && bol && qual_lines > 0 && qual_len >= cur_len) {
+		const bool ok = qual_len == cur_len;
+		close_carried(*this, ok, min_len, out, n_seq);
+		st = S_FIND; last = 0;
+		if (!ok) stopped = true;
+	}
+}
+
+void FastxCore::finish(int min_len, std::vector<uint8_t> &out, int64_t *n_seq)
+{
+	if (stopped) return;
+	if (st == S_SEQ) { // FASTA record ended by EOF
+		if (!bol && cur_len > 1 && !rec.empty() && rec.back() == '\r') { rec.pop_back(); --cur_len; }
+		close_carried(*this, true, min_len, out, n_seq);
+	} else if (st == S_QUAL) { // kseq.h:224-226: EOF ends the quality; lengths must agree
+		if (!bol && qline_nonempty && qual_len > 1 && last_qual == '\r') --qual_len;
+		close_carried(*this, qual_len == cur_len, min_len, out, n_seq);
+	} else { rec.clear(); cur_len = 0; } // header only (empty sequence), or '+' line without quality (kseq.h:222)
+	st = S_FIND; last = 0; stopped = true;
+}
+
+// ---------------------------------------------------------------- speculative block parse
+
+// first position in [0,n) that looks like the start of a record: a line start holding '>' or '@'
+// with a plausible continuation.  Returns n when there is none.  A wrong guess costs time only.
+static size_t guess_record_start(const unsigned char *p, size_t n, bool first_block)
+{
+	size_t i = 0;
+	if (!first_block) { // move to the first line start inside the block
+		const unsigned char *nl = (const unsigned char*)memchr(p, '\n', n);
+		if (!nl) return n;
+		i = nl - p + 1;
+	}
+	while (i < n) {
+		const unsigned char c = p[i];
+		const unsigned char *e1 = (const unsigned char*)memchr(p + i, '\n', n - i);
+		if (c == '>' || c == '@') {
+			if (!e1 || (size_t)(e1 - p) + 1 >= n) return i; // cannot look further: let the stitcher judge
+			const unsigned char *l2 = e1 + 1;
+			if (c == '>') { if (*l2 != '@' && *l2 != '+' && *l2 != '>') return i; } // not a quality line that starts with '>'
+			else { // FASTQ: the line after the sequence line starts with '+'
+				const unsigned char *e2 = (const unsigned char*)memchr(l2, '\n', n - (l2 - p));
+				if (!e2 || (size_t)(e2 - p) + 1 >= n) return i;
+				if (e2[1] == '+' || *l2 == '>' || *l2 == '@') return i; // ('@' header then another header: empty record)
+			}
+		}
+		if (!e1) return n;
+		i = e1 - p + 1;
+	}
+	return n;
+}
+
+bool ParallelFastx::open(const char *fn, size_t block_bytes, int threads)
+{
+	close();
+	if (fn == nullptr || strcmp(fn, "-") == 0) return false;
+	fd_ = ::open(fn, O_RDONLY);
+	if (fd_ < 0) return false;
+	struct stat sb;
+	unsigned char magic[2] = {0, 0};
+	if (fstat(fd_, &sb) != 0 || !S_ISREG(sb.st_mode) || (pread(fd_, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) {
+		close();
+		return false;
+	}
+	size_ = (uint64_t)sb.st_size;
+	block_ = block_bytes ? block_bytes : (8u << 20);
+	if (threads <= 0) {
+		const char *e = getenv("YAKB_PARSE_THREADS");
+		threads = e && atoi(e) > 0 ? atoi(e) : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+	}
+	threads_ = threads;
+	next_off_ = 0; eof_ = size_ == 0; finished_ = false; n_redo_ = 0;
+	true_ = FastxCore();
+	spill_.clear(); spill_pos_ = 0; spill_seq_ = 0;
+	return true;
+}
+
+void ParallelFastx::close()
+{
+	if (fd_ >= 0) ::close(fd_);
+	fd_ = -1;
+}
+
+size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len, int64_t *n_seq, bool *done, size_t *need)
+{
+	size_t n = 0;
+	*done = false;
+	if (need) *need = 0;
+	if (target > cap) target = cap;
+	// parsed bytes go straight to the caller's buffer while they fit, else to spill_
+	auto emit = [&](const uint8_t *p, size_t len, int64_t recs) {
+		if (len == 0) return;
+		if (spill_.empty() && n + len <= cap) { memcpy(dst + n, p, len); n += len; *n_seq += recs; }
+		else { spill_.insert(spill_.end(), p, p + len); spill_seq_ += recs; }
+	};
+	for (;;) {
+		// hand over what a previous call could not place, whole records only
+		if (spill_pos_ < spill_.size()) {
+			size_t room = cap - n, avail = spill_.size() - spill_pos_, take = std::min(room, avail);
+			if (take < avail) { // cut at a record boundary
+				const uint8_t *b = spill_.data() + spill_pos_;
+				size_t k = take;
+				while (k > 0 && b[k - 1] != '\n') --k;
+				take = k;
+			}
+			if (take == 0 && n == 0) { // not even one record fits
+				const uint8_t *b = spill_.data() + spill_pos_;
+				const uint8_t *nl = (const uint8_t*)memchr(b, '\n', avail);
+				if (need) *need = (nl ? (size_t)(nl - b) : avail) + 1;
+				return 0;
+			}
+			memcpy(dst + n, spill_.data() + spill_pos_, take);
+			if (take == avail) { *n_seq += spill_seq_; spill_seq_ = 0; }
+			else { // records in the delivered part = its newlines
+				int64_t c = 0;
+				for (const uint8_t *b = dst + n, *e = b + take; b < e; ++c) { b = (const uint8_t*)memchr(b, '\n', e - b); if (!b) break; ++b; }
+				*n_seq += c; spill_seq_ -= c;
+			}
+			n += take; spill_pos_ += take;
+			if (spill_pos_ < spill_.size()) return n; // caller's buffer is full
+			spill_.clear(); spill_pos_ = 0;
+		}
+		if (n >= target) return n;
+		if (finished_) { *done = true; return n; }
+		// one round: up to threads_ blocks parsed in parallel, stitched in order
+		const int nb = (int)std::min<uint64_t>((uint64_t)threads_, (size_ - next_off_ + block_ - 1) / block_);
+		if ((int)jobs_.size() < nb) jobs_.resize(nb);
+		std::vector<std::thread> pool;
+		const uint64_t base = next_off_;
+		for (int t = 0; t < nb; ++t) {
+			pool.emplace_back([&, t]() {
+				BlockJob &j = jobs_[t];
+				const uint64_t off = base + (uint64_t)t * block_;
+				const size_t len = (size_t)std::min<uint64_t>(block_, size_ - off);
+				if (!j.raw) j.raw.reset(new unsigned char[block_]);
+				size_t got = 0;
+				while (got < len) { ssize_t r = pread(fd_, j.raw.get() + got, len - got, off + got); if (r <= 0) break; got += r; }
+				j.n = got;
+				j.q = guess_record_start(j.raw.get(), j.n, off == 0);
+				j.spec = FastxCore();
+				j.out.clear();
+				j.nseq = 0;
+				if (j.q < j.n) j.spec.feed(j.raw.get() + j.q, j.n - j.q, min_len, j.out, &j.nseq);
+			});
+		}
+		for (auto &th : pool) th.join();
+		std::vector<uint8_t> gap;
+		for (int t = 0; t < nb; ++t) {
+			BlockJob &j = jobs_[t];
+			int64_t gs = 0;
+			gap.clear();
+			true_.feed(j.raw.get(), j.q, min_len, gap, &gs); // the gap, with the true state
+			if (j.q < j.n) {
+				true_.settle(min_len, gap, &gs);
+				if (true_.at_record_boundary()) { // the guess was a real record start: adopt the speculative result
+					if (true_.st == FastxCore::S_SEQ) close_carried(true_, true, min_len, gap, &gs);
+					emit(gap.data(), gap.size(), gs);
+					emit(j.out.data(), j.out.size(), j.nseq);
+					true_ = std::move(j.spec);
+				} else { // wrong guess: this block again, sequentially, from the true state
+					true_.feed(j.raw.get() + j.q, j.n - j.q, min_len, gap, &gs);
+					emit(gap.data(), gap.size(), gs);
+					++n_redo_;
+				}
+			} else emit(gap.data(), gap.size(), gs);
+		}
+		next_off_ = base + (uint64_t)nb * block_;
+		if (next_off_ >= size_ || nb == 0) {
+			int64_t gs = 0;
+			gap.clear();
+			true_.finish(min_len, gap, &gs);
+			emit(gap.data(), gap.size(), gs);
+			finished_ = true;
+		}
+	}
+}
+
+} // namespace yakb

@@ -1,0 +1,66 @@
+// fastx_par.h - multi-threaded FASTA/FASTQ ingest for uncompressed files with EXACTLY the record
+// semantics of the sequential reader (kseq.h:192-232).
+//
+// The file is cut into fixed-size blocks.  Workers parse their block speculatively from a guessed
+// record start; a sequential stitcher then replays the (tiny) gap between the block start and the
+// guess with the TRUE parser state carried over from the previous block and accepts the speculative
+// result only if the true state arrives at the guess exactly where a record begins - otherwise it
+// re-parses that block sequentially.  The parser is a deterministic state machine, so accepted
+// blocks are byte-for-byte what the sequential reader would have produced, for any input.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <memory>
+
+namespace yakb {
+
+// the record grammar as a resumable state machine over memory buffers
+struct FastxCore {
+	enum { S_FIND, S_NAME, S_SEQ, S_PLUS, S_QUAL };
+	int st = S_FIND, last = 0, last_qual = 0;
+	bool bol = true, stopped = false, qline_nonempty = false;
+	int64_t qual_len = 0, qual_lines = 0, cur_len = 0; // cur_len: sequence length of the open record
+	std::string rec;            // bytes of the open record carried between feed() calls
+	// consume n bytes; completed records of length >= min_len are appended to out as "SEQ\n"
+	void feed(const unsigned char *p, size_t n, int min_len, std::vector<uint8_t> &out, int64_t *n_seq);
+	// end of input: close the open record the way kseq_read would
+	void finish(int min_len, std::vector<uint8_t> &out, int64_t *n_seq);
+	// a FASTQ record whose quality is complete is closed lazily by the next byte; do it now
+	void settle(int min_len, std::vector<uint8_t> &out, int64_t *n_seq);
+	bool at_record_boundary() const { return !stopped && ((st == S_FIND && last == 0) || (st == S_SEQ && bol)); }
+};
+
+struct BlockJob {
+	std::unique_ptr<unsigned char[]> raw;
+	size_t n = 0, q = 0;
+	FastxCore spec;               // state after the speculative parse
+	std::vector<uint8_t> out;     // its output
+	int64_t nseq = 0;
+};
+
+class ParallelFastx {
+public:
+	~ParallelFastx() { close(); }
+	// false if the file cannot be opened or is not a plain regular file (gzip, stdin): use FastxReader
+	bool open(const char *fn, size_t block_bytes = 8u << 20, int threads = 0);
+	void close();
+	// same contract as FastxReader::fill
+	size_t fill(uint8_t *dst, size_t cap, size_t target, int min_len, int64_t *n_seq, bool *done, size_t *need);
+	uint64_t mis_speculations() const { return n_redo_; }
+
+private:
+	int fd_ = -1;
+	uint64_t size_ = 0, next_off_ = 0;
+	size_t block_ = 0;
+	int threads_ = 1;
+	FastxCore true_;                 // exact parser state at the end of the last stitched block
+	std::vector<uint8_t> spill_;     // parsed output that did not fit the caller's buffer yet
+	size_t spill_pos_ = 0;
+	int64_t spill_seq_ = 0;          // records inside spill_ not yet reported
+	bool eof_ = false, finished_ = false;
+	uint64_t n_redo_ = 0;
+	std::vector<BlockJob> jobs_;     // reused every round
+};
+
+} // namespace yakb
