@@ -191,11 +191,12 @@ static int cmd_setop(int argc, char *argv[], int isec)
 	}
 	if (argc - optind < 2) { fprintf(stderr, "Usage: yak-b200 %s [-o out.yak] <in0.yak> <in1.yak> [...]\n", isec ? "isec" : "subtract"); return 1; }
 	if ((h0 = yak_ch_restore(argv[optind])) == 0) { fprintf(stderr, "ERROR: failed to load '%s'\n", argv[optind]); return 1; }
-	for (i = optind + 1; i < argc; ++i) {
+	for (i = optind + 1; i < (isec ? argc : optind + 2); ++i) { /* subtract takes exactly one subtrahend (main.c:234-235) */
 		if ((h1 = yak_ch_restore(argv[i])) == 0) { fprintf(stderr, "ERROR: failed to load '%s'\n", argv[i]); return 1; }
 		if (isec) yak_ch_isec(h0, h1, n_thread); else yak_ch_subtract(h0, h1, n_thread);
 		yak_ch_destroy(h1);
 	}
+	yak_ch_tighten(h0); /* main.c:243, 279 */
 	yak_ch_dump(h0, fn_out);
 	yak_ch_destroy(h0);
 	return 0;

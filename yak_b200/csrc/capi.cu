@@ -413,16 +413,21 @@ template<class Sink> static void serialise(ChBox *b, Sink &&sink, bool header = 
 		sink(t, 12);
 	}
 	const int step = 1024;
+	double t_lay = 0, t_sink = 0;
 	for (int s0 = 0; s0 < P; s0 += step) {
 		const int s1 = std::min(P, s0 + step);
 		LayoutOut lo;
+		double t0 = wall_now();
 		b->eng->layout(s0, s1, lo, true);
+		double t1 = wall_now();
 		for (int s = s0; s < s1; ++s) {
 			uint32_t u[2] = {lo.cap[s - s0], lo.size[s - s0]};
 			sink(u, 8);
 			if (u[1]) sink(lo.keys.data() + lo.off[s - s0], (size_t)u[1] * 8);
 		}
+		t_lay += t1 - t0; t_sink += wall_now() - t1;
 	}
+	if (timing_on()) fprintf(stderr, "[T::serialise] layout %.3f s, sink %.3f s\n", t_lay, t_sink);
 }
 
 extern "C" int yak_ch_dump(const yak_ch_t *h, const char *fn)

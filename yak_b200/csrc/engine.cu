@@ -57,8 +57,6 @@ static std::atomic<uint64_t> g_launches{0};
 uint64_t Engine::launches() { return g_launches.load(); }
 void Engine::note_launch(int n) { g_launches += n; }
 
-static double wall_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
-
 // ---- per-kernel timing (off unless enabled)
 static bool g_prof_on = false;
 struct ProfPair { const char *name; cudaEvent_t a, b; };
@@ -569,24 +567,17 @@ __global__ void __launch_bounds__(256) qv_scan_kernel(const uint64_t *__restrict
 }
 
 // ---- rebuild the reference's khashl layout (khashl.h:137-221) from the insertion journal.
-//      One thread per sub-table: the kick-out rehash is a sequential procedure per table.
-__global__ void build_layout_kernel(const uint64_t *__restrict__ cat, const uint64_t *__restrict__ catoff,
-                                    const uint8_t *__restrict__ pre_flag, const uint32_t *__restrict__ pre_val,
-                                    const uint8_t *__restrict__ trailing,
-                                    uint64_t *keys_all, const uint64_t *__restrict__ koff,
-                                    uint32_t *bm_all, const uint64_t *__restrict__ boff,
-                                    int ns, uint32_t *out_cap, uint32_t *out_size, uint64_t *outkeys)
-{
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= ns) return;
-	uint64_t *K = keys_all + koff[t];
-	const uint64_t bwords = (boff[t + 1] - boff[t]) / 2;
-	uint32_t *used = bm_all + boff[t], *occ = used + bwords;
+//      The kick-out rehash is a sequential procedure per table, so one thread replays one
+//      sub-table; small tables are replayed in shared memory (one warp per sub-table, lane 0 walks
+//      the journal the other lanes stage), large ones in global scratch.
+struct KhReplay {
+	uint64_t *K;
+	uint32_t *used, *occ;
 	uint32_t bits = 0, n = 0, count = 0;
-	const uint64_t *src = cat + catoff[t];
-	const uint64_t m = catoff[t + 1] - catoff[t];
-	auto fw = [](uint32_t nb) { return nb < 32 ? 1u : nb >> 5; };
-	auto resize = [&](uint32_t request) { // khashl.h:152-195
+	static __device__ __forceinline__ uint32_t fw(uint32_t nb) { return nb < 32 ? 1u : nb >> 5; }
+	__device__ __forceinline__ bool is_used(uint32_t i) const { return used[i >> 5] >> (i & 31) & 1; }
+	__device__ void resize(uint32_t request) // khashl.h:152-195
+	{
 		uint32_t lg = 0, q = request;
 		while ((q >>= 1) != 0) ++lg;
 		if (request & (request - 1)) ++lg;
@@ -594,14 +585,14 @@ __global__ void build_layout_kernel(const uint64_t *__restrict__ cat, const uint
 		if (count > (new_n >> 1) + (new_n >> 2)) return;
 		for (uint32_t w = 0; w < fw(new_n); ++w) occ[w] = 0;
 		for (uint32_t j = 0; j != n; ++j) {
-			if (!(used[j >> 5] >> (j & 31) & 1)) continue;
+			if (!is_used(j)) continue;
 			uint64_t key = K[j];
 			used[j >> 5] &= ~(1u << (j & 31));
 			for (;;) {
 				uint32_t i = kh_home(key, new_bits);
 				while (occ[i >> 5] >> (i & 31) & 1) i = (i + 1) & new_mask;
 				occ[i >> 5] |= 1u << (i & 31);
-				if (i < n && (used[i >> 5] >> (i & 31) & 1)) {
+				if (i < n && is_used(i)) {
 					uint64_t ev = K[i]; K[i] = key; key = ev;
 					used[i >> 5] &= ~(1u << (i & 31));
 				} else { K[i] = key; break; }
@@ -609,34 +600,102 @@ __global__ void build_layout_kernel(const uint64_t *__restrict__ cat, const uint
 		}
 		uint32_t *tmp = used; used = occ; occ = tmp;
 		bits = new_bits; n = new_n;
-	};
-	used[0] = 0;
-	if (pre_flag[t]) resize(pre_val[t]);
-	for (uint64_t e = 0; e < m; ++e) { // khashl.h:197-221
-		const uint64_t key = src[e];
+	}
+	__device__ __forceinline__ void check() { if (count >= (n >> 1) + (n >> 2)) resize(n + 1); } // khashl.h:202-205
+	__device__ void entry(uint64_t key) // one journal entry: a put (khashl.h:197-221) or an operation (Engine::OP_*)
+	{
 		const uint32_t op = (uint32_t)key & YAKB_MAX_COUNT;
-		if (op) { // an operation recorded in the journal (Engine::OP_*)
+		if (op) {
 			const uint32_t r = (uint32_t)(key >> YAKB_COUNTER_BITS);
 			if (op == 1) resize(r);
-			else if (op == 2) { if (count >= (n >> 1) + (n >> 2)) resize(n + 1); }
+			else if (op == 2) check();
 			else if (op == 3) { if ((uint64_t)count * 3 < n) resize(count * 3); }
 			else if (op == 4) { if (r > n) resize(r); }
-			continue;
+			return;
 		}
-		if (count >= (n >> 1) + (n >> 2)) resize(n + 1);
+		check();
 		const uint32_t mask = n - 1;
 		uint32_t i = kh_home(key, bits), start = i;
-		while ((used[i >> 5] >> (i & 31) & 1) && (K[i] >> YAKB_COUNTER_BITS) != (key >> YAKB_COUNTER_BITS)) {
+		while (is_used(i) && (K[i] >> YAKB_COUNTER_BITS) != (key >> YAKB_COUNTER_BITS)) {
 			i = (i + 1) & mask;
 			if (i == start) break;
 		}
-		if (!(used[i >> 5] >> (i & 31) & 1)) { K[i] = key; used[i >> 5] |= 1u << (i & 31); ++count; }
+		if (!is_used(i)) { K[i] = key; used[i >> 5] |= 1u << (i & 31); ++count; }
 	}
-	if (trailing[t] && count >= (n >> 1) + (n >> 2)) resize(n + 1); // a later put of an existing key (quirk Q3)
-	out_cap[t] = n; out_size[t] = count;
+};
+
+// global-scratch variant: one thread per listed sub-table
+__global__ void build_layout_kernel(const int *__restrict__ list, int nlist,
+                                    const uint64_t *__restrict__ cat, const uint64_t *__restrict__ catoff,
+                                    const uint8_t *__restrict__ pre_flag, const uint32_t *__restrict__ pre_val,
+                                    const uint8_t *__restrict__ trailing,
+                                    uint64_t *keys_all, const uint64_t *__restrict__ koff,
+                                    uint32_t *bm_all, const uint64_t *__restrict__ boff,
+                                    uint32_t *out_cap, uint32_t *out_size, uint64_t *outkeys)
+{
+	const int li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= nlist) return;
+	const int t = list[li];
+	KhReplay R;
+	R.K = keys_all + koff[t];
+	const uint64_t bwords = (boff[t + 1] - boff[t]) / 2;
+	R.used = bm_all + boff[t]; R.occ = R.used + bwords;
+	R.used[0] = 0;
+	const uint64_t *src = cat + catoff[t];
+	const uint64_t m = catoff[t + 1] - catoff[t];
+	if (pre_flag[t]) R.resize(pre_val[t]);
+	for (uint64_t e = 0; e < m; ++e) R.entry(src[e]);
+	if (trailing[t]) R.check(); // a later put of an existing key (quirk Q3)
+	out_cap[t] = R.n; out_size[t] = R.count;
 	uint64_t *dst = outkeys + catoff[t];
 	uint64_t r = 0;
-	for (uint32_t i = 0; i < n; ++i) if (used[i >> 5] >> (i & 31) & 1) dst[r++] = K[i];
+	for (uint32_t i = 0; i < R.n; ++i) if (R.is_used(i)) dst[r++] = R.K[i];
+}
+
+// shared-memory variant: one warp per listed sub-table whose table never exceeds `slots` entries.
+// dynamic smem: slots*8 (keys) + 2*fw(slots)*4 (bitmaps) + 512*8 (journal staging)
+__global__ void __launch_bounds__(32) build_layout_smem_kernel(const int *__restrict__ list, uint32_t slots,
+                                    const uint64_t *__restrict__ cat, const uint64_t *__restrict__ catoff,
+                                    const uint8_t *__restrict__ pre_flag, const uint32_t *__restrict__ pre_val,
+                                    const uint8_t *__restrict__ trailing,
+                                    uint32_t *out_cap, uint32_t *out_size, uint64_t *outkeys)
+{
+	extern __shared__ unsigned char s_dyn[];
+	const int t = list[blockIdx.x], lane = threadIdx.x;
+	uint64_t *sK = (uint64_t*)s_dyn;
+	uint32_t *sbm = (uint32_t*)(s_dyn + (size_t)slots * 8);
+	const uint32_t bw = KhReplay::fw(slots);
+	uint64_t *stage = (uint64_t*)(s_dyn + (size_t)slots * 8 + (size_t)bw * 8);
+	KhReplay R;
+	R.K = sK; R.used = sbm; R.occ = sbm + bw;
+	if (lane == 0) { R.used[0] = 0; if (pre_flag[t]) R.resize(pre_val[t]); }
+	const uint64_t *src = cat + catoff[t];
+	const uint64_t m = catoff[t + 1] - catoff[t];
+	for (uint64_t e0 = 0; e0 < m; e0 += 512) {
+		const uint32_t c = (uint32_t)(m - e0 < 512 ? m - e0 : 512);
+		__syncwarp();
+		for (uint32_t i = lane; i < c; i += 32) stage[i] = src[e0 + i]; // coalesced staging of the next 512 entries
+		__syncwarp();
+		if (lane == 0) for (uint32_t i = 0; i < c; ++i) R.entry(stage[i]);
+	}
+	if (lane == 0) {
+		if (trailing[t]) R.check();
+		out_cap[t] = R.n; out_size[t] = R.count;
+	}
+	// export in slot order with all lanes: every lane needs the final state of lane 0
+	const uint32_t n = __shfl_sync(0xffffffffu, R.n, 0);
+	const int swapped = __shfl_sync(0xffffffffu, (int)(R.used != sbm), 0);
+	const uint32_t *used = swapped ? sbm + bw : sbm;
+	__syncwarp();
+	uint64_t *dst = outkeys + catoff[t];
+	uint32_t r = 0;
+	for (uint32_t base = 0; base < n; base += 32) {
+		const uint32_t i = base + lane;
+		const bool u = i < n && (used[i >> 5] >> (i & 31) & 1);
+		const uint32_t mask = __ballot_sync(0xffffffffu, u);
+		if (u) dst[r + __popc(mask & ((1u << lane) - 1))] = sK[i];
+		r += __popc(mask);
+	}
 }
 
 // attach the current counts to slot-ordered keys of sub-tables s0.. (off[] local to the range)
@@ -726,7 +785,8 @@ Engine::~Engine()
 	if (last_new) cudaFree(last_new);
 	journal_free_all();
 	DBuf *all[] = {&b_w2, &b_wm, &b_flags, &b_tilecnt, &b_tileoff, &b_pv, &b_ppos, &b_sv, &b_sj, &b_sv2, &b_sj2, &b_pflag, &b_newv,
-	               &b_newsorted, &b_tmp, &b_pend, &b_lput, &b_lnew, &b_stats, &b_misc, &b_rs[0], &b_rs[1], &b_rs[2], &b_rs[3], &b_rs[4]};
+	               &b_newsorted, &b_tmp, &b_pend, &b_lput, &b_lnew, &b_stats, &b_misc, &b_rs[0], &b_rs[1], &b_rs[2], &b_rs[3], &b_rs[4],
+	               &b_lay[0], &b_lay[1], &b_lay[2], &b_lay[3], &b_lay[4], &b_lay[5], &b_lay[6], &b_lay[7], &b_lay[8], &b_lay[9], &b_lay[10], &b_lay[11]};
 	for (DBuf *b : all) b->release();
 	if (stream) cudaStreamDestroy(stream);
 }
@@ -736,7 +796,7 @@ void *Engine::journal_alloc(size_t bytes)
 	bytes = (bytes + 255) & ~(size_t)255;
 	if (slabs.empty() || slabs.back().used + bytes > slabs.back().cap) {
 		Slab sl;
-		sl.cap = std::max<size_t>(bytes, (size_t)1 << 30);
+		sl.cap = std::max<size_t>(bytes, (size_t)2 << 30);
 		sl.used = 0;
 		YAKB_CUDA(cudaMalloc((void**)&sl.p, sl.cap));
 		slabs.push_back(sl);
@@ -1014,18 +1074,19 @@ static uint32_t final_capacity(bool pflag, uint32_t pval, uint64_t m, bool trail
 	return (uint32_t)n;
 }
 
-void Engine::layout(int s0, int s1, LayoutOut &out, bool with_counts)
+// Rebuild the khashl layout of sub-tables [s0, s1) batch by batch (scratch-bounded).  For every batch
+// `fn(b0, ns, catoff, d_out, cap, size)` sees: the first sub-table (relative to s0), their number, the
+// host offsets of each sub-table's run inside d_out (run t holds size[t] stored keys in slot order,
+// counts attached when asked), and the khashl capacity / size of each.  Scratch is grow-only.
+template<class F> void Engine::layout_batches(int s0, int s1, bool with_counts, F &&fn)
 {
 	const int nsub = s1 - s0;
-	out.cap.assign(nsub, 0); out.size.assign(nsub, 0); out.off.assign(nsub + 1, 0); out.keys.clear();
-	// per-sub-table journal lengths and trailing flags
 	std::vector<uint32_t> h_nkeys(nsub);
 	std::vector<uint64_t> h_lp(nsub), h_ln(nsub);
 	YAKB_CUDA(cudaMemcpyAsync(h_nkeys.data(), nkeys + s0, nsub * 4, cudaMemcpyDeviceToHost, stream));
 	YAKB_CUDA(cudaMemcpyAsync(h_lp.data(), last_put + s0, nsub * 8, cudaMemcpyDeviceToHost, stream));
 	YAKB_CUDA(cudaMemcpyAsync(h_ln.data(), last_new + s0, nsub * 8, cudaMemcpyDeviceToHost, stream));
 	YAKB_CUDA(cudaStreamSynchronize(stream));
-	// process in batches bounded by scratch memory
 	const uint64_t budget = 6ull << 30;
 	int b0 = 0;
 	while (b0 < nsub) {
@@ -1045,30 +1106,28 @@ void Engine::layout(int s0, int s1, LayoutOut &out, bool with_counts)
 				capf = (uint32_t)std::min<uint64_t>(bound * 2, 0x80000000ull);
 			}
 			const uint64_t jlen = (uint64_t)h_nkeys[b1] + nops[s];
-			const uint64_t bw = 2 * (uint64_t)(capf < 32 ? 1 : capf >> 5);
-			const uint64_t add = (uint64_t)capf * 8 + bw * 4 + jlen * 16;
+			const bool small = capf <= 16384; // replayed in shared memory: no global scratch
+			const uint64_t bw = small ? 2 : 2 * (uint64_t)(capf < 32 ? 1 : capf >> 5);
+			const uint64_t add = (small ? 0 : (uint64_t)capf * 8 + bw * 4) + jlen * 16;
 			if (b1 > b0 && bytes + add > budget) break;
 			bytes += add;
 			catoff.push_back(catoff.back() + jlen);
-			koff.push_back(koff.back() + std::max<uint32_t>(capf, 4));
-			boff.push_back(boff.back() + std::max<uint64_t>(bw, 2));
+			koff.push_back(koff.back() + (small ? 0 : std::max<uint32_t>(capf, 4)));
+			boff.push_back(boff.back() + (small ? 0 : std::max<uint64_t>(bw, 2)));
 			trail.push_back(tr); pf.push_back(presize_flag[s]); pvv.push_back(presize_val[s]);
+			caps_scratch_.push_back(capf);
 			++b1;
 		}
 		const int ns = b1 - b0;
 		const uint64_t ncat = catoff.back();
-		uint64_t *d_cat, *d_out, *d_keys, *d_catoff, *d_koff, *d_boff, *d_run;
-		uint32_t *d_bm, *d_pv, *d_ocap, *d_osize;
-		uint8_t *d_trail, *d_pf;
-		YAKB_CUDA(cudaMalloc(&d_cat, std::max<uint64_t>(ncat, 1) * 8));
-		YAKB_CUDA(cudaMalloc(&d_out, std::max<uint64_t>(ncat, 1) * 8));
+		uint64_t *d_cat = b_lay[0].as<uint64_t>(std::max<uint64_t>(ncat, 1)), *d_out = b_lay[1].as<uint64_t>(std::max<uint64_t>(ncat, 1));
+		uint64_t *d_keys = b_lay[2].as<uint64_t>(std::max<uint64_t>(koff.back(), 1));
+		uint32_t *d_bm = b_lay[3].as<uint32_t>(std::max<uint64_t>(boff.back(), 1));
+		uint64_t *d_catoff = b_lay[4].as<uint64_t>(ns + 1), *d_koff = b_lay[5].as<uint64_t>(ns + 1), *d_boff = b_lay[6].as<uint64_t>(ns + 1);
+		uint64_t *d_run = b_lay[7].as<uint64_t>(ns);
+		uint32_t *d_pv = b_lay[8].as<uint32_t>(ns), *d_ocap = b_lay[9].as<uint32_t>(ns), *d_osize = b_lay[10].as<uint32_t>(ns);
+		uint8_t *d_trail = b_lay[11].as<uint8_t>(2 * (size_t)ns), *d_pf = d_trail + ns;
 		YAKB_CUDA(cudaMemsetAsync(d_out, 0, std::max<uint64_t>(ncat, 1) * 8, stream));
-		YAKB_CUDA(cudaMalloc(&d_keys, koff.back() * 8));
-		YAKB_CUDA(cudaMalloc(&d_bm, boff.back() * 4));
-		YAKB_CUDA(cudaMalloc(&d_catoff, (ns + 1) * 8)); YAKB_CUDA(cudaMalloc(&d_koff, (ns + 1) * 8)); YAKB_CUDA(cudaMalloc(&d_boff, (ns + 1) * 8));
-		YAKB_CUDA(cudaMalloc(&d_run, ns * 8));
-		YAKB_CUDA(cudaMalloc(&d_pv, ns * 4)); YAKB_CUDA(cudaMalloc(&d_ocap, ns * 4)); YAKB_CUDA(cudaMalloc(&d_osize, ns * 4));
-		YAKB_CUDA(cudaMalloc(&d_trail, ns)); YAKB_CUDA(cudaMalloc(&d_pf, ns));
 		YAKB_CUDA(cudaMemcpyAsync(d_catoff, catoff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
 		YAKB_CUDA(cudaMemcpyAsync(d_koff, koff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
 		YAKB_CUDA(cudaMemcpyAsync(d_boff, boff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
@@ -1076,37 +1135,73 @@ void Engine::layout(int s0, int s1, LayoutOut &out, bool with_counts)
 		YAKB_CUDA(cudaMemcpyAsync(d_trail, trail.data(), ns, cudaMemcpyHostToDevice, stream));
 		YAKB_CUDA(cudaMemcpyAsync(d_pf, pf.data(), ns, cudaMemcpyHostToDevice, stream));
 		YAKB_CUDA(cudaMemsetAsync(d_run, 0, ns * 8, stream));
-		double t_a = getenv("YAKB_TIMING") ? (cudaStreamSynchronize(stream), wall_s()) : 0;
 		for (auto &seg : journal) {
 			gather_seg_kernel<<<std::max<uint32_t>(1, cdiv(seg.n, 256)), 256, 0, stream>>>(seg.keys, seg.off, s0 + b0, ns, d_catoff, d_run, d_cat);
 			advance_run_kernel<<<cdiv(ns, 256), 256, 0, stream>>>(seg.off, s0 + b0, ns, d_run);
 		}
 		YAKB_CUDA(cudaGetLastError());
-		double t_b = getenv("YAKB_TIMING") ? (cudaStreamSynchronize(stream), wall_s()) : 0;
-		build_layout_kernel<<<cdiv(ns, 32), 32, 0, stream>>>(d_cat, d_catoff, d_pf, d_pv, d_trail, d_keys, d_koff, d_bm, d_boff, ns, d_ocap, d_osize, d_out);
-		YAKB_CUDA(cudaGetLastError());
-		double t_c = getenv("YAKB_TIMING") ? (cudaStreamSynchronize(stream), wall_s()) : 0;
+		{ // small tables replay in shared memory (three size classes), the rest in global scratch
+			const uint32_t cls[3] = {1024, 4096, 16384};
+			std::vector<int> lists[4];
+			for (int t = 0; t < ns; ++t) {
+				const uint32_t c = caps_scratch_[t];
+				int k = 3;
+				for (int i = 2; i >= 0; --i) if (c <= cls[i]) k = i;
+				lists[k].push_back(t);
+			}
+			caps_scratch_.clear();
+			std::vector<int> all;
+			size_t start[5] = {0, 0, 0, 0, 0};
+			for (int k = 0; k < 4; ++k) { start[k] = all.size(); all.insert(all.end(), lists[k].begin(), lists[k].end()); }
+			start[4] = all.size();
+			int *d_list = (int*)b_misc.need(std::max<size_t>(all.size(), 1) * sizeof(int));
+			YAKB_CUDA(cudaMemcpyAsync(d_list, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+			for (int k = 0; k < 3; ++k) {
+				if (lists[k].empty()) continue;
+				const size_t sm = (size_t)cls[k] * 8 + (size_t)(cls[k] < 32 ? 1 : cls[k] >> 5) * 8 + 512 * 8;
+				YAKB_CUDA(cudaFuncSetAttribute(build_layout_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+				build_layout_smem_kernel<<<(uint32_t)lists[k].size(), 32, sm, stream>>>(d_list + start[k], cls[k], d_cat, d_catoff, d_pf, d_pv, d_trail,
+				                                                                          d_ocap, d_osize, d_out);
+			}
+			if (!lists[3].empty())
+				build_layout_kernel<<<cdiv(lists[3].size(), 32), 32, 0, stream>>>(d_list + start[3], (int)lists[3].size(), d_cat, d_catoff, d_pf, d_pv, d_trail,
+				                                                                  d_keys, d_koff, d_bm, d_boff, d_ocap, d_osize, d_out);
+			YAKB_CUDA(cudaGetLastError());
+			YAKB_CUDA(cudaStreamSynchronize(stream)); // `all` must outlive the copy
+		}
 		if (with_counts && ncat && cap)
 			fill_counts_kernel<<<cdiv(ncat, 256), 256, 0, stream>>>(d_out, d_catoff, ns, s0 + b0, ncat, slots, cap);
 		YAKB_CUDA(cudaGetLastError());
-		std::vector<uint64_t> tmp(ncat);
-		if (ncat) YAKB_CUDA(cudaMemcpyAsync(tmp.data(), d_out, ncat * 8, cudaMemcpyDeviceToHost, stream));
-		YAKB_CUDA(cudaMemcpyAsync(out.cap.data() + b0, d_ocap, ns * 4, cudaMemcpyDeviceToHost, stream));
-		YAKB_CUDA(cudaMemcpyAsync(out.size.data() + b0, d_osize, ns * 4, cudaMemcpyDeviceToHost, stream));
+		std::vector<uint32_t> h_cap(ns), h_size(ns);
+		YAKB_CUDA(cudaMemcpyAsync(h_cap.data(), d_ocap, ns * 4, cudaMemcpyDeviceToHost, stream));
+		YAKB_CUDA(cudaMemcpyAsync(h_size.data(), d_osize, ns * 4, cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaStreamSynchronize(stream));
-		for (int t = 0; t < ns; ++t) { // a sub-table's run may be shorter than its journal (operation entries)
-			if (out.size[b0 + t] > catoff[t + 1] - catoff[t]) throw CudaError("[yakb] layout: inconsistent journal");
-			out.keys.insert(out.keys.end(), tmp.begin() + catoff[t], tmp.begin() + catoff[t] + out.size[b0 + t]);
-			out.off[b0 + t + 1] = out.keys.size();
-		}
-		if (getenv("YAKB_TIMING")) fprintf(stderr, "[T::layout] %d sub-tables %llu keys: gather %.4f build %.4f fill+copy %.4f s\n", ns, (unsigned long long)ncat, t_b - t_a, t_c - t_b, wall_s() - t_c);
-		cudaFree(d_cat); cudaFree(d_out); cudaFree(d_keys); cudaFree(d_bm); cudaFree(d_catoff); cudaFree(d_koff); cudaFree(d_boff);
-		cudaFree(d_run); cudaFree(d_pv); cudaFree(d_ocap); cudaFree(d_osize); cudaFree(d_trail); cudaFree(d_pf);
+		for (int t = 0; t < ns; ++t)
+			if (h_size[t] > catoff[t + 1] - catoff[t]) throw CudaError("[yakb] layout: inconsistent journal");
+		fn(b0, ns, catoff, d_catoff, d_out, d_osize, h_cap, h_size);
 		b0 = b1;
 	}
 }
 
-void Engine::load_subtables(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys)
+void Engine::layout(int s0, int s1, LayoutOut &out, bool with_counts)
+{
+	const int nsub = s1 - s0;
+	out.cap.assign(nsub, 0); out.size.assign(nsub, 0); out.off.assign(nsub + 1, 0); out.keys.clear();
+	layout_batches(s0, s1, with_counts, [&](int b0, int ns, const std::vector<uint64_t> &catoff, const uint64_t *, const uint64_t *d_out,
+	                                          const uint32_t *, const std::vector<uint32_t> &h_cap, const std::vector<uint32_t> &h_size) {
+		const uint64_t ncat = catoff.back();
+		std::vector<uint64_t> tmp(ncat);
+		if (ncat) YAKB_CUDA(cudaMemcpyAsync(tmp.data(), d_out, ncat * 8, cudaMemcpyDeviceToHost, stream));
+		YAKB_CUDA(cudaStreamSynchronize(stream));
+		for (int t = 0; t < ns; ++t) { // a sub-table's run may be shorter than its journal (operation entries)
+			out.cap[b0 + t] = h_cap[t]; out.size[b0 + t] = h_size[t];
+			out.keys.insert(out.keys.end(), tmp.begin() + catoff[t], tmp.begin() + catoff[t] + h_size[t]);
+			out.off[b0 + t + 1] = out.keys.size();
+		}
+	});
+}
+
+void Engine::load_subtables(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys, bool keys_on_device)
 {
 	const uint64_t n = off[P];
 	uint32_t mx = 0;
@@ -1119,7 +1214,7 @@ void Engine::load_subtables(const std::vector<uint32_t> &caps, const std::vector
 	seg.off = (uint64_t*)journal_alloc((uint64_t)(P + 1) * 8);
 	YAKB_CUDA(cudaMemcpyAsync(seg.off, off.data(), (uint64_t)(P + 1) * 8, cudaMemcpyHostToDevice, stream));
 	if (n) {
-		YAKB_CUDA(cudaMemcpyAsync(seg.keys, keys, n * 8, cudaMemcpyHostToDevice, stream));
+		YAKB_CUDA(cudaMemcpyAsync(seg.keys, keys, n * 8, keys_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
 		bulk_insert_kernel<<<cdiv(n, 256), 256, 0, stream>>>(seg.keys, seg.off, P, n, slots, cap);
 		clear_kernel<<<cdiv(n, 256), 256, 0, stream>>>(seg.keys, n); // journal keeps keys without counts
 		YAKB_CUDA(cudaGetLastError());
@@ -1130,24 +1225,54 @@ void Engine::load_subtables(const std::vector<uint32_t> &caps, const std::vector
 	tot = n;
 }
 
+// flag[i] = 1 if entry i of a layout batch is a real key (inside its sub-table's run) whose count is in [lo, hi]
+__global__ void shrink_flag_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ catoff, const uint32_t *__restrict__ size,
+                                   int ns, uint64_t n, uint32_t lo_c, uint32_t hi_c, uint8_t *__restrict__ flag, uint32_t *kept)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t lo = 0, hi = ns;
+	while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (catoff[mid] <= i) lo = mid; else hi = mid; }
+	const uint32_t c = (uint32_t)keys[i] & YAKB_MAX_COUNT;
+	const bool keep = i - catoff[lo] < size[lo] && c >= lo_c && c <= hi_c;
+	flag[i] = keep;
+	if (keep) atomicAdd(&kept[lo], 1u);
+}
+
 void Engine::shrink(int min, int max)
 {
 	if (!(max >= min && max <= 1023)) max = 1023;
-	// htab.c:183-193: old slots upward, keep min<=count<=max, into a set pre-sized to the OLD size
-	LayoutOut lo;
-	layout(0, P, lo, true);
-	std::vector<uint64_t> kept; kept.reserve(lo.keys.size());
+	if (min < 0) min = 0;
+	// htab.c:183-193: old slots upward, keep min<=count<=max, into a set pre-sized to the OLD size.
+	// Layout, filter and compaction stay on the device; only per-sub-table counts come back.
+	RadixScratch &rs = *reinterpret_cast<RadixScratch*>(b_rs);
 	std::vector<uint64_t> off(P + 1, 0);
-	std::vector<uint32_t> caps(P);
-	for (int s = 0; s < P; ++s) {
-		for (uint64_t i = lo.off[s]; i < lo.off[s + 1]; ++i) {
-			int c = (int)(lo.keys[i] & YAKB_MAX_COUNT);
-			if (c >= min && c <= max) kept.push_back(lo.keys[i]);
+	std::vector<uint32_t> caps(P, 0);
+	uint64_t total = 0;
+	{ std::vector<uint32_t> z; sizes(z); for (uint32_t v : z) total += v; }
+	uint64_t *d_kept = b_newv.as<uint64_t>(std::max<uint64_t>(total, 1)); // every batch appends here
+	uint64_t n_kept = 0;
+	layout_batches(0, P, true, [&](int b0, int ns, const std::vector<uint64_t> &catoff, const uint64_t *d_catoff, const uint64_t *d_out,
+	                                const uint32_t *d_osize, const std::vector<uint32_t> &, const std::vector<uint32_t> &h_size) {
+		const uint64_t ncat = catoff.back();
+		uint8_t *flag = b_pflag.as<uint8_t>(std::max<uint64_t>(ncat, 1));
+		uint32_t *d_cnt = b_pend.as<uint32_t>(ns + 1);
+		YAKB_CUDA(cudaMemsetAsync(d_cnt, 0, (ns + 1) * 4, stream));
+		std::vector<uint32_t> h_cnt(ns, 0);
+		if (ncat) {
+			shrink_flag_kernel<<<cdiv(ncat, 256), 256, 0, stream>>>(d_out, d_catoff, d_osize, ns, ncat, (uint32_t)min, (uint32_t)max, flag, d_cnt);
+			compact_flagged_u64(d_out, flag, ncat, d_kept + n_kept, d_cnt + ns, stream, rs);
+			YAKB_CUDA(cudaGetLastError());
 		}
-		off[s + 1] = kept.size();
-		caps[s] = lo.size[s]; // yak_ht_resize(f, kh_size(g))
-	}
-	rebuild(caps, off, kept.data());
+		YAKB_CUDA(cudaMemcpyAsync(h_cnt.data(), d_cnt, ns * 4, cudaMemcpyDeviceToHost, stream));
+		YAKB_CUDA(cudaStreamSynchronize(stream));
+		for (int t = 0; t < ns; ++t) {
+			n_kept += h_cnt[t];
+			off[b0 + t + 1] = n_kept;
+			caps[b0 + t] = h_size[t]; // yak_ht_resize(f, kh_size(g))
+		}
+	});
+	rebuild_dev(caps, off, d_kept);
 }
 
 void Engine::rebuild(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys)
@@ -1158,6 +1283,16 @@ void Engine::rebuild(const std::vector<uint32_t> &caps, const std::vector<uint64
 	YAKB_CUDA(cudaMemsetAsync(last_put, 0, P * 8, stream));
 	YAKB_CUDA(cudaMemsetAsync(last_new, 0, P * 8, stream));
 	load_subtables(caps, off, keys);
+}
+
+// same as rebuild() with the keys already on the device (d_keys may live in a scratch buffer)
+void Engine::rebuild_dev(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *d_keys)
+{
+	journal_free_all();
+	if (slots) { YAKB_CUDA(cudaFree(slots)); slots = nullptr; cap = 0; }
+	YAKB_CUDA(cudaMemsetAsync(last_put, 0, P * 8, stream));
+	YAKB_CUDA(cudaMemsetAsync(last_new, 0, P * 8, stream));
+	load_subtables(caps, off, d_keys, true);
 }
 
 void Engine::sizes(std::vector<uint32_t> &out)
