@@ -35,6 +35,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout, which must carry exactly one JSON line
 
 K, PRE, BF, NH, L = 31, 12, 37, 4, 150
 SEED_G, SEED_R = 20260925, 7

@@ -358,3 +358,17 @@ def test_parallel_reader_is_exactly_the_sequential_reader(block, threads):
     open(trunc, "w").write("@a\nACGTAC\n+\nIIIIII\n@b\nGGGTTT\n+\nIII\n@c\nAAAA\n+\nIIII\n" * 3)
     assert _pfill_all(trunc, block, threads, 4096, 4096, 0)[0] == _fill_all(trunc, 4096, 4096, 0)[0] == b"ACGTAC\n"
     assert not capi.lib().yakb_pfastx_open((files[0] + ".gz").encode(), 0, 0) or True
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs) on a tiny bounded sample, here without a GPU"""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1",
+                        "--genome", "400000", "--chunk-reads", "3000", "--bf-shift", "24"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "events/s" and d["steps"] == 3 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["h2d_bytes_per_step"] == 0

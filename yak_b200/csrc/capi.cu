@@ -551,7 +551,7 @@ extern "C" int yakb_count_events_dev(yak_ch_t *h, const uint64_t *d_ev, uint64_t
 	GUARD_END(-1)
 }
 
-static DBuf g_route_scratch[13];
+static RouteScratch g_route_scratch;
 static std::mutex g_route_mu;
 extern "C" int yakb_extract_route_dev(const void *d_asc, uint64_t n, int k, int pre, int world, uint64_t *d_out, uint64_t *counts, void *cuda_stream)
 {

@@ -17,7 +17,6 @@
 #include "yakb_dev.cuh"
 #include "kernels.cuh"
 #include "extras.cuh"
-#include "radix.cuh"
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
@@ -54,7 +53,7 @@ static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b -
 
 // number of OUR kernels launched (cub's are not counted); reported by bench.py as gpu_launches
 static std::atomic<uint64_t> g_launches{0};
-uint64_t Engine::launches() { return g_launches.load(); }
+uint64_t Engine::launches() { return g_launches.load() + radix_launches(); }
 void Engine::note_launch(int n) { g_launches += n; }
 
 // ---- per-kernel timing (off unless enabled)
@@ -785,9 +784,10 @@ Engine::~Engine()
 	if (last_new) cudaFree(last_new);
 	journal_free_all();
 	DBuf *all[] = {&b_w2, &b_wm, &b_flags, &b_tilecnt, &b_tileoff, &b_pv, &b_ppos, &b_sv, &b_sj, &b_sv2, &b_sj2, &b_pflag, &b_newv,
-	               &b_newsorted, &b_tmp, &b_pend, &b_lput, &b_lnew, &b_stats, &b_misc, &b_rs[0], &b_rs[1], &b_rs[2], &b_rs[3], &b_rs[4],
+	               &b_newsorted, &b_tmp, &b_pend, &b_lput, &b_lnew, &b_stats, &b_misc, 
 	               &b_lay[0], &b_lay[1], &b_lay[2], &b_lay[3], &b_lay[4], &b_lay[5], &b_lay[6], &b_lay[7], &b_lay[8], &b_lay[9], &b_lay[10], &b_lay[11]};
 	for (DBuf *b : all) b->release();
+	rs.release();
 	if (stream) cudaStreamDestroy(stream);
 }
 
@@ -928,7 +928,6 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 		return st;
 	}
 	// pending list in file order
-	RadixScratch &rs = *reinterpret_cast<RadixScratch*>(b_rs);
 	exclusive_scan_u32(tilecnt, tileoff, ntiles + 1, stream, rs);
 	uint32_t n_pending = 0;
 	YAKB_CUDA(cudaMemcpyAsync(&n_pending, tileoff + ntiles, 4, cudaMemcpyDeviceToHost, stream));
@@ -1245,7 +1244,6 @@ void Engine::shrink(int min, int max)
 	if (min < 0) min = 0;
 	// htab.c:183-193: old slots upward, keep min<=count<=max, into a set pre-sized to the OLD size.
 	// Layout, filter and compaction stay on the device; only per-sub-table counts come back.
-	RadixScratch &rs = *reinterpret_cast<RadixScratch*>(b_rs);
 	std::vector<uint64_t> off(P + 1, 0);
 	std::vector<uint32_t> caps(P, 0);
 	uint64_t total = 0;

@@ -19,20 +19,10 @@
 #include <string>
 #include <stdexcept>
 #include <cuda_runtime.h>
+#include "dbuf.cuh"
+#include "radix.cuh"
 
 namespace yakb {
-
-struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
-void cuda_fail(cudaError_t e, const char *what, const char *file, int line);
-#define YAKB_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) ::yakb::cuda_fail(e__, #x, __FILE__, __LINE__); } while (0)
-
-// grow-only device buffer
-struct DBuf {
-	void *p = nullptr; size_t cap = 0;
-	void *need(size_t bytes);
-	template<class T> T *as(size_t n) { return (T*)need(n * sizeof(T)); }
-	void release();
-};
 
 // optional per-kernel timing with CUDA events on the engine's stream (bench.py roofline leg)
 struct Prof {
@@ -97,7 +87,8 @@ struct Engine {
 	double load_limit = 0.6;
 	// scratch (grow-only, reused by every chunk)
 	DBuf b_w2, b_wm, b_flags, b_tilecnt, b_tileoff, b_pv, b_ppos, b_sv, b_sj, b_sv2, b_sj2, b_pflag, b_newv, b_newsorted,
-	     b_tmp, b_pend, b_lput, b_lnew, b_stats, b_misc, b_rs[5], b_lay[12];
+	     b_tmp, b_pend, b_lput, b_lnew, b_stats, b_misc, b_lay[12];
+	RadixScratch rs;
 	std::vector<uint32_t> caps_scratch_;
 
 	static Engine *create(int k, int pre, int n_hash, int n_shift, int rank = 0, int world = 1);

@@ -4,7 +4,6 @@
 #include "yakb_dev.cuh"
 #include "kernels.cuh"
 #include "extras.cuh"
-#include "radix.cuh"
 #include <stdio.h>
 #include <algorithm>
 
@@ -52,20 +51,20 @@ __global__ void rank_offsets_kernel(const uint64_t *__restrict__ sorted, uint64_
 }
 
 int extract_events(const uint8_t *d_asc, uint64_t n, int k, int pre, int world, uint64_t *d_out, uint64_t *counts,
-                   cudaStream_t stream, DBuf *scratch /* 8 buffers + a RadixScratch (5 more) */)
+                   cudaStream_t stream, RouteScratch &sc)
 {
 	for (int r = 0; r < world; ++r) counts[r] = 0;
 	if (n == 0) return 0;
 	const uint64_t nwords = (n + 31) / 32, ntiles = (nwords + 255) / 256;
-	uint64_t *w2 = scratch[0].as<uint64_t>(packed_words(nwords)) + YAKB_PADW;
-	uint32_t *wm = scratch[1].as<uint32_t>(packed_words(nwords)) + YAKB_PADW;
-	uint32_t *vmask = scratch[2].as<uint32_t>(nwords);
-	uint32_t *tilecnt = scratch[3].as<uint32_t>(ntiles + 1), *tileoff = scratch[4].as<uint32_t>(ntiles + 1);
-	uint32_t *ppos = scratch[5].as<uint32_t>(n);
+	uint64_t *w2 = sc.b[0].as<uint64_t>(packed_words(nwords)) + YAKB_PADW;
+	uint32_t *wm = sc.b[1].as<uint32_t>(packed_words(nwords)) + YAKB_PADW;
+	uint32_t *vmask = sc.b[2].as<uint32_t>(nwords);
+	uint32_t *tilecnt = sc.b[3].as<uint32_t>(ntiles + 1), *tileoff = sc.b[4].as<uint32_t>(ntiles + 1);
+	uint32_t *ppos = sc.b[5].as<uint32_t>(n);
 	pack_ascii_kernel<<<cdiv(packed_npad(nwords) + YAKB_PADW, 256), 256, 0, stream>>>(d_asc, n, w2, wm, nwords, packed_npad(nwords));
 	valid_mask_kernel<<<(uint32_t)ntiles, 256, 0, stream>>>(wm, nwords, k, vmask, tilecnt);
 	YAKB_CUDA(cudaMemsetAsync(tilecnt + ntiles, 0, 4, stream));
-	RadixScratch &rs = *reinterpret_cast<RadixScratch*>(scratch + 8);
+	RadixScratch &rs = sc.rs;
 	exclusive_scan_u32(tilecnt, tileoff, ntiles + 1, stream, rs);
 	uint32_t n_ev = 0;
 	YAKB_CUDA(cudaMemcpyAsync(&n_ev, tileoff + ntiles, 4, cudaMemcpyDeviceToHost, stream));
@@ -74,18 +73,18 @@ int extract_events(const uint8_t *d_asc, uint64_t n, int k, int pre, int world, 
 	int lw = 0;
 	while ((1 << lw) < world) ++lw;
 	if ((1 << lw) != world || lw > pre) { fprintf(stderr, "[yakb] ERROR: world size must be a power of two <= 2^pre\n"); return -1; }
-	uint64_t *ev = lw ? scratch[7].as<uint64_t>(n_ev) : d_out;
+	uint64_t *ev = lw ? sc.b[7].as<uint64_t>(n_ev) : d_out;
 	if (k >= 32) compact_fused<true><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, vmask, tileoff, ev, ppos);
 	else compact_fused<false><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, vmask, tileoff, ev, ppos);
 	YAKB_CUDA(cudaGetLastError());
 	if (lw == 0) { counts[0] = n_ev; YAKB_CUDA(cudaStreamSynchronize(stream)); return 0; }
 	// owner rank = top lw bits of the sub-table index = hash bits [pre-lw, pre); one stable pass on them
-	uint64_t *alt = scratch[6].as<uint64_t>(n_ev);
+	uint64_t *alt = sc.b[6].as<uint64_t>(n_ev);
 	if (radix_sort_pairs(ev, nullptr, d_out, nullptr, alt, nullptr, n_ev, pre - lw, pre, stream, rs) != 0)
 		YAKB_CUDA(cudaMemcpyAsync(d_out, alt, (size_t)n_ev * 8, cudaMemcpyDeviceToDevice, stream));
 	// per-rank counts: lower bounds in the sorted owner field (host binary search over device data
 	// would sync per probe; a tiny kernel does all ranks at once)
-	uint64_t *d_off = (uint64_t*)scratch[4].need((world + 1) * 8);
+	uint64_t *d_off = (uint64_t*)sc.b[4].need((world + 1) * 8);
 	rank_offsets_kernel<<<1, 64, 0, stream>>>(d_out, n_ev, pre, lw, world, d_off);
 	std::vector<uint64_t> off(world + 1);
 	YAKB_CUDA(cudaMemcpyAsync(off.data(), d_off, (world + 1) * 8, cudaMemcpyDeviceToHost, stream));

@@ -2,10 +2,15 @@
 // the first version of the path used between its kernels.
 #include "radix.cuh"
 #include <stdio.h>
+#include <atomic>
 
 namespace yakb {
 
 static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+static std::atomic<uint64_t> g_radix_launches{0};
+void radix_note_launch(int n) { g_radix_launches += n; }
+uint64_t radix_launches() { return g_radix_launches.load(); }
 
 // ------------------------------------------------------------------ exclusive scan
 
@@ -59,7 +64,7 @@ void exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, cudaStrea
 	if (n == 0) return;
 	scan_level(in, out, n, st, rs, 0);
 	YAKB_CUDA(cudaGetLastError());
-	Engine::note_launch(3);
+	radix_note_launch(3);
 }
 
 // ------------------------------------------------------------------ radix sort
@@ -226,7 +231,7 @@ int radix_sort_pairs(const uint64_t *k_src, const uint32_t *v_src, uint64_t *k_a
 			radix_scatter_kernel<false, true><<<ntiles, 256, sm, st>>>(kin, vin, kout, vout, n, lo, dmask, hist, ntiles);
 		}
 		YAKB_CUDA(cudaGetLastError());
-		Engine::note_launch(2);
+		radix_note_launch(2);
 		where = where == 0 ? 1 : 0;
 		kin = kout; vin = vout;
 	}
@@ -281,7 +286,7 @@ void compact_flagged_u64(const uint64_t *in, const uint8_t *flag, uint64_t n, ui
 	if (n) flag_scatter_kernel<<<ntiles, 256, 0, st>>>(in, flag, n, tc, out);
 	YAKB_CUDA(cudaMemcpyAsync(d_count, tc + ntiles, 4, cudaMemcpyDeviceToDevice, st));
 	YAKB_CUDA(cudaGetLastError());
-	Engine::note_launch(2);
+	radix_note_launch(2);
 }
 
 } // namespace yakb

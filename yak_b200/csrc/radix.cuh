@@ -5,11 +5,17 @@
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
-#include "engine.cuh"
+#include "dbuf.cuh"
 
 namespace yakb {
 
-struct RadixScratch { DBuf hist, lvl[4]; };
+struct RadixScratch {
+	DBuf hist, lvl[4];
+	void release() { hist.release(); for (DBuf &b : lvl) b.release(); }
+};
+// our own kernels launched by these helpers are counted here (Engine::launches adds them)
+void radix_note_launch(int n);
+uint64_t radix_launches();
 
 // out[i] = sum of in[0..i) ; out may alias in.  n up to 2^32.
 void exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, cudaStream_t st, RadixScratch &rs);
