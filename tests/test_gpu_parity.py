@@ -211,3 +211,22 @@ def test_restore_roundtrip_and_qv(oracle, yakb, reads_fa):
         assert list(c1) == list(c2)
         assert sum(c1) > 0 or min_frac > 0.9
     L.yak_ch_destroy(hg); OL.yo_ch_destroy(ho); OL.yo_ch_destroy(ho2)
+
+
+@pytest.mark.parametrize("smem_max,warp", [("0", "1"), ("0", "0"), ("1024", "1")])
+def test_layout_replay_variants_agree(oracle, yakb, reads_fa, monkeypatch, smem_max, warp):
+    """the khashl layout rebuild has three code paths (shared memory, one thread, one warp per sub-table);
+    force the large-table paths on small data: count, two-pass bloom, restore and shrink must stay byte-exact"""
+    monkeypatch.setenv("YAKB_LAYOUT_SMEM_MAX", smem_max)
+    monkeypatch.setenv("YAKB_LAYOUT_WARP", warp)
+    for k, pre, b in ((31, 10, 0), (31, 10, 20), (21, 11, 0)):
+        ho, hg, ref, mine, _ = _count_both(oracle, yakb, reads_fa, k, pre, b)
+        try:
+            assert mine == ref, util.explain_diff(mine, ref)
+            oracle.lib().yo_ch_shrink(ho, 3, 900)
+            yakb.lib().yak_ch_shrink(hg, 3, 900, 1)
+            a, bb = yakb.dump_bytes(hg), oracle.dump_bytes(ho)
+            assert a == bb, util.explain_diff(a, bb)
+        finally:
+            yakb.lib().yak_ch_destroy(hg)
+            oracle.lib().yo_ch_destroy(ho)

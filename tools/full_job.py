@@ -1,0 +1,44 @@
+"""The complete config-2 job on one GPU with device-generated reads: pass 1, destroy_bf, clear, pass 2,
+shrink (layout of every sub-table), hist.  Prints stage times; optional partial dump."""
+import ctypes as C, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from yak_b200 import capi
+lib = capi.lib()
+G = int(float(sys.argv[1])) if len(sys.argv) > 1 else 3_000_000_000
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+bf = int(sys.argv[3]) if len(sys.argv) > 3 else 37
+nr, L = 2_000_000, 150
+cur = torch.cuda.current_stream().cuda_stream
+g2 = torch.empty((G + 31) // 32 + 1, dtype=torch.int64, device="cuda")
+lib.yakb_synth_genome_dev(bench.SEED_G, G, g2.data_ptr(), cur)
+buf = torch.empty(nr * (L + 1), dtype=torch.uint8, device="cuda")
+h = lib.yak_ch_init(31, 12, 4, bf)
+stats = (C.c_uint64 * 4)()
+out = {}
+def one_pass(create_new):
+    t_dev, ev = 0.0, 0
+    for i in range(steps):
+        lib.yakb_synth_reads_dev(g2.data_ptr(), G, bench.SEED_R, i * nr, nr, L, bench.ERR, bench.NPCT, 0, buf.data_ptr(), cur)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        assert lib.yakb_count_ascii_dev(h, buf.data_ptr(), nr * (L + 1), create_new, stats) == 0
+        t_dev += time.time() - t0
+        ev += stats[0]
+    return t_dev, ev
+t, ev = one_pass(1); out["pass1_s"] = t; out["events"] = ev; out["distinct_pass1"] = int(h.contents.tot)
+out["dev_GB_after_pass1"] = lib.yakb_ch_device_bytes(h) / 1e9
+print(json.dumps(out), flush=True)
+t0 = time.time(); lib.yak_ch_destroy_bf(h); lib.yak_ch_clear(h, 1); out["destroy_bf_clear_s"] = time.time() - t0
+t, ev = one_pass(0); out["pass2_s"] = t
+print(json.dumps(out), flush=True)
+t0 = time.time(); lib.yak_ch_shrink(h, 2, 1023, 1); out["shrink_s"] = time.time() - t0; out["distinct_final"] = int(h.contents.tot)
+print(json.dumps(out), flush=True)
+hist = (C.c_int64 * 1024)()
+t0 = time.time(); lib.yak_ch_hist(h, hist, 1); out["hist_s"] = time.time() - t0
+out["hist_peak"] = max(range(2, 1024), key=lambda i: hist[i]); out["hist_sum"] = sum(hist)
+out["total_s"] = out["pass1_s"] + out["destroy_bf_clear_s"] + out["pass2_s"] + out["shrink_s"]
+out["input_events_per_s"] = out["events"] / out["total_s"]
+print(json.dumps(out), flush=True)
+lib.yak_ch_destroy(h)

@@ -623,41 +623,44 @@ struct KhReplay {
 	}
 };
 
-// global-scratch variant: one thread per listed sub-table
-__global__ void build_layout_kernel(const int *__restrict__ list, int nlist,
-                                    const uint64_t *__restrict__ cat, const uint64_t *__restrict__ catoff,
+// the journal of one sub-table = its runs in every segment, in segment order
+struct SegView { const uint64_t *const *keys; const uint64_t *const *off; int n; };
+
+// global-scratch variant: one thread per listed sub-table.  The sub-table's output region (reg) is
+// also its working key array; the slot-ordered keys end up compacted at its front.
+__global__ void build_layout_kernel(const int *__restrict__ list, int nlist, SegView sv, int s_first,
                                     const uint8_t *__restrict__ pre_flag, const uint32_t *__restrict__ pre_val,
                                     const uint8_t *__restrict__ trailing,
-                                    uint64_t *keys_all, const uint64_t *__restrict__ koff,
+                                    uint64_t *out_all, const uint64_t *__restrict__ ooff,
                                     uint32_t *bm_all, const uint64_t *__restrict__ boff,
-                                    uint32_t *out_cap, uint32_t *out_size, uint64_t *outkeys)
+                                    uint32_t *out_cap, uint32_t *out_size)
 {
 	const int li = blockIdx.x * blockDim.x + threadIdx.x;
 	if (li >= nlist) return;
 	const int t = list[li];
 	KhReplay R;
-	R.K = keys_all + koff[t];
+	R.K = out_all + ooff[t];
 	const uint64_t bwords = (boff[t + 1] - boff[t]) / 2;
 	R.used = bm_all + boff[t]; R.occ = R.used + bwords;
 	R.used[0] = 0;
-	const uint64_t *src = cat + catoff[t];
-	const uint64_t m = catoff[t + 1] - catoff[t];
 	if (pre_flag[t]) R.resize(pre_val[t]);
-	for (uint64_t e = 0; e < m; ++e) R.entry(src[e]);
+	for (int c = 0; c < sv.n; ++c) {
+		const uint64_t *k = sv.keys[c];
+		for (uint64_t e = sv.off[c][s_first + t], e1 = sv.off[c][s_first + t + 1]; e < e1; ++e) R.entry(k[e]);
+	}
 	if (trailing[t]) R.check(); // a later put of an existing key (quirk Q3)
 	out_cap[t] = R.n; out_size[t] = R.count;
-	uint64_t *dst = outkeys + catoff[t];
 	uint64_t r = 0;
-	for (uint32_t i = 0; i < R.n; ++i) if (R.is_used(i)) dst[r++] = R.K[i];
+	for (uint32_t i = 0; i < R.n; ++i) if (R.is_used(i)) R.K[r++] = R.K[i]; // r <= i: in-place compaction
 }
 
 // shared-memory variant: one warp per listed sub-table whose table never exceeds `slots` entries.
 // dynamic smem: slots*8 (keys) + 2*fw(slots)*4 (bitmaps) + 512*8 (journal staging)
-__global__ void __launch_bounds__(32) build_layout_smem_kernel(const int *__restrict__ list, uint32_t slots,
-                                    const uint64_t *__restrict__ cat, const uint64_t *__restrict__ catoff,
+__global__ void __launch_bounds__(32) build_layout_smem_kernel(const int *__restrict__ list, uint32_t slots, SegView sv, int s_first,
                                     const uint8_t *__restrict__ pre_flag, const uint32_t *__restrict__ pre_val,
                                     const uint8_t *__restrict__ trailing,
-                                    uint32_t *out_cap, uint32_t *out_size, uint64_t *outkeys)
+                                    uint64_t *out_all, const uint64_t *__restrict__ ooff,
+                                    uint32_t *out_cap, uint32_t *out_size)
 {
 	extern __shared__ unsigned char s_dyn[];
 	const int t = list[blockIdx.x], lane = threadIdx.x;
@@ -668,14 +671,16 @@ __global__ void __launch_bounds__(32) build_layout_smem_kernel(const int *__rest
 	KhReplay R;
 	R.K = sK; R.used = sbm; R.occ = sbm + bw;
 	if (lane == 0) { R.used[0] = 0; if (pre_flag[t]) R.resize(pre_val[t]); }
-	const uint64_t *src = cat + catoff[t];
-	const uint64_t m = catoff[t + 1] - catoff[t];
-	for (uint64_t e0 = 0; e0 < m; e0 += 512) {
-		const uint32_t c = (uint32_t)(m - e0 < 512 ? m - e0 : 512);
-		__syncwarp();
-		for (uint32_t i = lane; i < c; i += 32) stage[i] = src[e0 + i]; // coalesced staging of the next 512 entries
-		__syncwarp();
-		if (lane == 0) for (uint32_t i = 0; i < c; ++i) R.entry(stage[i]);
+	for (int c = 0; c < sv.n; ++c) {
+		const uint64_t *src = sv.keys[c] + sv.off[c][s_first + t];
+		const uint64_t m = sv.off[c][s_first + t + 1] - sv.off[c][s_first + t];
+		for (uint64_t e0 = 0; e0 < m; e0 += 512) {
+			const uint32_t cc = (uint32_t)(m - e0 < 512 ? m - e0 : 512);
+			__syncwarp();
+			for (uint32_t i = lane; i < cc; i += 32) stage[i] = src[e0 + i]; // coalesced staging of the next 512 entries
+			__syncwarp();
+			if (lane == 0) for (uint32_t i = 0; i < cc; ++i) R.entry(stage[i]);
+		}
 	}
 	if (lane == 0) {
 		if (trailing[t]) R.check();
@@ -686,7 +691,7 @@ __global__ void __launch_bounds__(32) build_layout_smem_kernel(const int *__rest
 	const int swapped = __shfl_sync(0xffffffffu, (int)(R.used != sbm), 0);
 	const uint32_t *used = swapped ? sbm + bw : sbm;
 	__syncwarp();
-	uint64_t *dst = outkeys + catoff[t];
+	uint64_t *dst = out_all + ooff[t];
 	uint32_t r = 0;
 	for (uint32_t base = 0; base < n; base += 32) {
 		const uint32_t i = base + lane;
@@ -695,6 +700,114 @@ __global__ void __launch_bounds__(32) build_layout_smem_kernel(const int *__rest
 		if (u) dst[r + __popc(mask & ((1u << lane) - 1))] = sK[i];
 		r += __popc(mask);
 	}
+}
+
+// warp variant for large sub-tables whose journal holds puts only (counting, shrink, restore):
+// the FCFS put phases between two doublings run on all 32 lanes - a slot belongs to the lowest
+// journal rank that probes it (atomicMin), a displaced rank moves on, which is exactly first-come
+// first-served linear probing - while the kick-out rehash (khashl.h:152-195) stays with lane 0.
+// cat = the sub-table's journal made contiguous, own = one u32 per slot (all ones = free).
+__global__ void __launch_bounds__(32) build_layout_warp_kernel(const int *__restrict__ list,
+                                    const uint64_t *__restrict__ cat_all, const uint64_t *__restrict__ catoff,
+                                    const uint8_t *__restrict__ pre_flag, const uint32_t *__restrict__ pre_val,
+                                    const uint8_t *__restrict__ trailing,
+                                    uint64_t *out_all, const uint64_t *__restrict__ ooff,
+                                    uint32_t *bm_all, const uint64_t *__restrict__ boff,
+                                    uint32_t *own_all, uint32_t *out_cap, uint32_t *out_size)
+{
+	const int t = list[blockIdx.x], lane = threadIdx.x;
+	const uint64_t *cat = cat_all + catoff[t];
+	const uint64_t m = catoff[t + 1] - catoff[t];
+	uint32_t *own = own_all + ooff[t]; // same geometry as the key region
+	KhReplay R;
+	R.K = out_all + ooff[t];
+	const uint64_t bwords = (boff[t + 1] - boff[t]) / 2;
+	R.used = bm_all + boff[t]; R.occ = R.used + bwords;
+	if (lane == 0) { R.used[0] = 0; if (pre_flag[t]) R.resize(pre_val[t]); }
+	__syncwarp();
+	uint64_t e0 = 0;
+	while (e0 < m) {
+		if (lane == 0) R.check(); // doubling when the load limit is reached (khashl.h:202-205)
+		__syncwarp(); // lane 0's writes to the table are visible to the other lanes from here
+		// broadcast the table state of lane 0
+		const uint32_t n = __shfl_sync(0xffffffffu, R.n, 0), bits = __shfl_sync(0xffffffffu, R.bits, 0), count = __shfl_sync(0xffffffffu, R.count, 0);
+		const int swapped = __shfl_sync(0xffffffffu, (int)(R.used != bm_all + boff[t]), 0);
+		uint32_t *used = swapped ? bm_all + boff[t] + bwords : bm_all + boff[t];
+		const uint32_t mask = n - 1, room = (n >> 1) + (n >> 2) - count; // puts until the next load check fires
+		const uint64_t e1 = m - e0 < room ? m : e0 + room;
+		for (uint32_t i = lane; i < n; i += 32) own[i] = 0xFFFFFFFFu;
+		__syncwarp();
+		for (uint64_t eb = e0; eb < e1; eb += 32) { // 32 keys at a time, ranks = journal positions
+			const uint64_t e = eb + lane;
+			bool active = e < e1;
+			uint32_t rank = (uint32_t)(e - e0), pos = active ? kh_home(cat[e], bits) : 0;
+			while (active) {
+				if (used[pos >> 5] >> (pos & 31) & 1) { pos = (pos + 1) & mask; continue; } // an older key
+				const uint32_t old = atomicMin(&own[pos], rank);
+				if (old == 0xFFFFFFFFu) active = false;              // free slot taken
+				else { if (old > rank) rank = old; pos = (pos + 1) & mask; } // the later of the two moves on
+			}
+		}
+		__syncwarp();
+		// materialise the phase: keys into their slots, occupancy bits; a lane owns whole bitmap words,
+		// and reads the owners from L2 where the atomics put them
+		for (uint32_t w = lane; w < (n < 32 ? 1u : n >> 5); w += 32) {
+			uint32_t bitsw = used[w];
+			for (uint32_t b = 0; b < 32 && w * 32 + b < n; ++b) {
+				const uint32_t r = __ldcg(&own[w * 32 + b]);
+				if (r != 0xFFFFFFFFu) { R.K[w * 32 + b] = cat[e0 + r]; bitsw |= 1u << b; }
+			}
+			used[w] = bitsw;
+		}
+		__syncwarp();
+		if (lane == 0) R.count += (uint32_t)(e1 - e0);
+		e0 = e1;
+	}
+	if (lane == 0) {
+		if (trailing[t]) R.check();
+		out_cap[t] = R.n; out_size[t] = R.count;
+	}
+	__syncwarp();
+	// in-place compaction to slot order (r <= i), cooperatively
+	const uint32_t n = __shfl_sync(0xffffffffu, R.n, 0);
+	const int swapped = __shfl_sync(0xffffffffu, (int)(R.used != bm_all + boff[t]), 0);
+	const uint32_t *used = swapped ? bm_all + boff[t] + bwords : bm_all + boff[t];
+	__syncwarp();
+	uint32_t r = 0;
+	for (uint32_t base = 0; base < n; base += 32) {
+		const uint32_t i = base + lane;
+		const bool u = i < n && (used[i >> 5] >> (i & 31) & 1);
+		const uint64_t kv = u ? R.K[i] : 0;
+		const uint32_t mk = __ballot_sync(0xffffffffu, u);
+		__syncwarp();
+		if (u) R.K[r + __popc(mk & ((1u << lane) - 1))] = kv; // r + rank <= i: never overtakes unread slots of later rounds
+		r += __popc(mk);
+		__syncwarp();
+	}
+}
+
+// copy the runs of sub-tables given by `sub` (indices relative to s_first) of one journal segment to cat, behind earlier segments
+__global__ void gather_seg_kernel(const uint64_t *__restrict__ seg_keys, const uint64_t *__restrict__ seg_off, int s_first,
+                                  const int *__restrict__ sub, int nsub, const uint64_t *__restrict__ catoff, uint64_t *run, uint64_t *__restrict__ cat)
+{
+	// one block per listed sub-table
+	const int t = sub[blockIdx.x];
+	const uint64_t b = seg_off[s_first + t], n = seg_off[s_first + t + 1] - b;
+	uint64_t *dst = cat + catoff[t] + run[t];
+	for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = seg_keys[b + i];
+	__syncthreads();
+	if (threadIdx.x == 0) run[t] += n;
+}
+
+// dense[i] = the j-th key of sub-table t's run, for i = voff[t] + j, j < voff[t+1]-voff[t]
+__global__ void densify_kernel(const uint64_t *__restrict__ out_all, const uint64_t *__restrict__ ooff, const uint64_t *__restrict__ voff,
+                               int ns, uint64_t n, uint64_t *__restrict__ dense)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t lo = 0, hi = ns;
+	while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (voff[mid] <= i) lo = mid; else hi = mid; }
+	dense[i] = out_all[ooff[lo] + (i - voff[lo])];
 }
 
 // attach the current counts to slot-ordered keys of sub-tables s0.. (off[] local to the range)
@@ -709,23 +822,6 @@ __global__ void fill_counts_kernel(uint64_t *keys, const uint64_t *__restrict__ 
 	uint64_t key = keys[i];
 	int64_t q = tab_find(reg, cap, key >> YAKB_COUNTER_BITS);
 	if (q >= 0) keys[i] = (key & ~(uint64_t)YAKB_MAX_COUNT) | (reg[q] & YAKB_MAX_COUNT);
-}
-
-// copy the runs of sub-tables [s0, s0+ns) of one journal segment behind what earlier segments put
-__global__ void gather_seg_kernel(const uint64_t *__restrict__ seg_keys, const uint64_t *__restrict__ seg_off, int s0, int ns,
-                                  const uint64_t *__restrict__ catoff, const uint64_t *__restrict__ run, uint64_t *__restrict__ cat)
-{
-	const uint64_t base = seg_off[s0], n = seg_off[s0 + ns] - base;
-	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	uint32_t lo = 0, hi = ns;
-	while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (seg_off[s0 + mid] - base <= i) lo = mid; else hi = mid; }
-	cat[catoff[lo] + run[lo] + (i - (seg_off[s0 + lo] - base))] = seg_keys[base + i];
-}
-__global__ void advance_run_kernel(const uint64_t *__restrict__ seg_off, int s0, int ns, uint64_t *run)
-{
-	int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t < ns) run[t] += seg_off[s0 + t + 1] - seg_off[s0 + t];
 }
 
 // ============================================================ host side
@@ -788,6 +884,7 @@ Engine::~Engine()
 	               &b_lay[0], &b_lay[1], &b_lay[2], &b_lay[3], &b_lay[4], &b_lay[5], &b_lay[6], &b_lay[7], &b_lay[8], &b_lay[9], &b_lay[10], &b_lay[11]};
 	for (DBuf *b : all) b->release();
 	rs.release();
+	b_segp.release();
 	if (stream) cudaStreamDestroy(stream);
 }
 
@@ -1074,10 +1171,10 @@ static uint32_t final_capacity(bool pflag, uint32_t pval, uint64_t m, bool trail
 }
 
 // Rebuild the khashl layout of sub-tables [s0, s1) batch by batch (scratch-bounded).  For every batch
-// `fn(b0, ns, catoff, d_out, cap, size)` sees: the first sub-table (relative to s0), their number, the
-// host offsets of each sub-table's run inside d_out (run t holds size[t] stored keys in slot order,
-// counts attached when asked), and the khashl capacity / size of each.  Scratch is grow-only.
-template<class F> void Engine::layout_batches(int s0, int s1, bool with_counts, F &&fn)
+// `fn(b0, ns, voff, d_voff, d_dense, cap, size)` sees: the first sub-table (relative to s0), their
+// number, and a dense device array holding each sub-table's stored keys in slot order (run t =
+// [voff[t], voff[t+1]), counts attached when asked), plus the khashl capacity / size of each.
+template<class F> void Engine::layout_batches(int s0, int s1, bool with_counts, uint64_t reserve_bytes, F &&fn)
 {
 	const int nsub = s1 - s0;
 	std::vector<uint32_t> h_nkeys(nsub);
@@ -1085,13 +1182,32 @@ template<class F> void Engine::layout_batches(int s0, int s1, bool with_counts, 
 	YAKB_CUDA(cudaMemcpyAsync(h_nkeys.data(), nkeys + s0, nsub * 4, cudaMemcpyDeviceToHost, stream));
 	YAKB_CUDA(cudaMemcpyAsync(h_lp.data(), last_put + s0, nsub * 8, cudaMemcpyDeviceToHost, stream));
 	YAKB_CUDA(cudaMemcpyAsync(h_ln.data(), last_new + s0, nsub * 8, cudaMemcpyDeviceToHost, stream));
+	// the journal as arrays of segment pointers
+	std::vector<const uint64_t*> hk, ho;
+	for (auto &seg : journal) { hk.push_back(seg.keys); ho.push_back(seg.off); }
+	const uint64_t **d_segk = (const uint64_t**)b_segp.need(std::max<size_t>(hk.size(), 1) * 2 * sizeof(void*));
+	const uint64_t **d_sego = d_segk + std::max<size_t>(hk.size(), 1);
+	if (!hk.empty()) {
+		YAKB_CUDA(cudaMemcpyAsync(d_segk, hk.data(), hk.size() * sizeof(void*), cudaMemcpyHostToDevice, stream));
+		YAKB_CUDA(cudaMemcpyAsync(d_sego, ho.data(), ho.size() * sizeof(void*), cudaMemcpyHostToDevice, stream));
+	}
 	YAKB_CUDA(cudaStreamSynchronize(stream));
-	const uint64_t budget = 6ull << 30;
+	SegView sv; sv.keys = d_segk; sv.off = d_sego; sv.n = (int)hk.size();
+	// scratch budget: most of what is free now (large sub-tables replay one thread each, so the more
+	// of them run at once the better), but never less than 2 GB
+	size_t mem_free = 0, mem_total = 0;
+	cudaMemGetInfo(&mem_free, &mem_total);
+	mem_free += b_lay[0].cap + b_lay[1].cap + b_lay[2].cap + b_lay[3].cap + b_lay[7].cap; // our own grow-only scratch is reusable
+	uint64_t budget = mem_free > reserve_bytes ? (uint64_t)((mem_free - reserve_bytes) * 0.8) : 0;
+	budget = std::max<uint64_t>(budget, 2ull << 30);
+	const char *env_sm = getenv("YAKB_LAYOUT_SMEM_MAX"), *env_wp = getenv("YAKB_LAYOUT_WARP"); // test knobs
+	const uint32_t smem_max = env_sm ? (uint32_t)atoi(env_sm) : 16384;
+	const bool use_warp = env_wp ? atoi(env_wp) != 0 : true;
 	int b0 = 0;
 	while (b0 < nsub) {
-		std::vector<uint64_t> catoff(1, 0), koff(1, 0), boff(1, 0);
-		std::vector<uint8_t> trail, pf;
-		std::vector<uint32_t> pvv;
+		std::vector<uint64_t> ooff(1, 0), boff(1, 0), catoff(1, 0);
+		std::vector<uint8_t> trail, pf, kind;
+		std::vector<uint32_t> pvv, capb;
 		int b1 = b0;
 		uint64_t bytes = 0;
 		while (b1 < nsub) {
@@ -1104,80 +1220,87 @@ template<class F> void Engine::layout_batches(int s0, int s1, bool with_counts, 
 				while (bound < want) bound *= 2;
 				capf = (uint32_t)std::min<uint64_t>(bound * 2, 0x80000000ull);
 			}
-			const uint64_t jlen = (uint64_t)h_nkeys[b1] + nops[s];
-			const bool small = capf <= 16384; // replayed in shared memory: no global scratch
+			const bool small = capf <= smem_max; // replayed in shared memory: its region only receives the result
+			const bool warp = !small && use_warp && nops[s] == 0; // large, puts only: 32 lanes per sub-table
+			const uint64_t region = small ? std::max<uint64_t>(h_nkeys[b1], 1) : std::max<uint32_t>(capf, 4);
 			const uint64_t bw = small ? 2 : 2 * (uint64_t)(capf < 32 ? 1 : capf >> 5);
-			const uint64_t add = (small ? 0 : (uint64_t)capf * 8 + bw * 4) + jlen * 16;
+			const uint64_t add = region * 8 + bw * 4 + (uint64_t)h_nkeys[b1] * 8 + (warp ? region * 4 + (uint64_t)h_nkeys[b1] * 8 : 0);
 			if (b1 > b0 && bytes + add > budget) break;
 			bytes += add;
-			catoff.push_back(catoff.back() + jlen);
-			koff.push_back(koff.back() + (small ? 0 : std::max<uint32_t>(capf, 4)));
-			boff.push_back(boff.back() + (small ? 0 : std::max<uint64_t>(bw, 2)));
-			trail.push_back(tr); pf.push_back(presize_flag[s]); pvv.push_back(presize_val[s]);
-			caps_scratch_.push_back(capf);
+			ooff.push_back(ooff.back() + region);
+			boff.push_back(boff.back() + std::max<uint64_t>(bw, 2));
+			trail.push_back(tr); pf.push_back(presize_flag[s]); pvv.push_back(presize_val[s]); capb.push_back(capf);
+			kind.push_back(small ? 0 : warp ? 2 : 1);
+			catoff.push_back(catoff.back() + (warp ? h_nkeys[b1] : 0));
 			++b1;
 		}
 		const int ns = b1 - b0;
-		const uint64_t ncat = catoff.back();
-		uint64_t *d_cat = b_lay[0].as<uint64_t>(std::max<uint64_t>(ncat, 1)), *d_out = b_lay[1].as<uint64_t>(std::max<uint64_t>(ncat, 1));
-		uint64_t *d_keys = b_lay[2].as<uint64_t>(std::max<uint64_t>(koff.back(), 1));
+		uint64_t *d_out = b_lay[1].as<uint64_t>(std::max<uint64_t>(ooff.back(), 1));
 		uint32_t *d_bm = b_lay[3].as<uint32_t>(std::max<uint64_t>(boff.back(), 1));
-		uint64_t *d_catoff = b_lay[4].as<uint64_t>(ns + 1), *d_koff = b_lay[5].as<uint64_t>(ns + 1), *d_boff = b_lay[6].as<uint64_t>(ns + 1);
-		uint64_t *d_run = b_lay[7].as<uint64_t>(ns);
+		uint64_t *d_ooff = b_lay[4].as<uint64_t>(ns + 1), *d_boff = b_lay[6].as<uint64_t>(ns + 1), *d_voff = b_lay[5].as<uint64_t>(ns + 1);
 		uint32_t *d_pv = b_lay[8].as<uint32_t>(ns), *d_ocap = b_lay[9].as<uint32_t>(ns), *d_osize = b_lay[10].as<uint32_t>(ns);
 		uint8_t *d_trail = b_lay[11].as<uint8_t>(2 * (size_t)ns), *d_pf = d_trail + ns;
-		YAKB_CUDA(cudaMemsetAsync(d_out, 0, std::max<uint64_t>(ncat, 1) * 8, stream));
-		YAKB_CUDA(cudaMemcpyAsync(d_catoff, catoff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
-		YAKB_CUDA(cudaMemcpyAsync(d_koff, koff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
+		YAKB_CUDA(cudaMemcpyAsync(d_ooff, ooff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
 		YAKB_CUDA(cudaMemcpyAsync(d_boff, boff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
 		YAKB_CUDA(cudaMemcpyAsync(d_pv, pvv.data(), ns * 4, cudaMemcpyHostToDevice, stream));
 		YAKB_CUDA(cudaMemcpyAsync(d_trail, trail.data(), ns, cudaMemcpyHostToDevice, stream));
 		YAKB_CUDA(cudaMemcpyAsync(d_pf, pf.data(), ns, cudaMemcpyHostToDevice, stream));
-		YAKB_CUDA(cudaMemsetAsync(d_run, 0, ns * 8, stream));
-		for (auto &seg : journal) {
-			gather_seg_kernel<<<std::max<uint32_t>(1, cdiv(seg.n, 256)), 256, 0, stream>>>(seg.keys, seg.off, s0 + b0, ns, d_catoff, d_run, d_cat);
-			advance_run_kernel<<<cdiv(ns, 256), 256, 0, stream>>>(seg.off, s0 + b0, ns, d_run);
-		}
-		YAKB_CUDA(cudaGetLastError());
 		{ // small tables replay in shared memory (three size classes), the rest in global scratch
 			const uint32_t cls[3] = {1024, 4096, 16384};
-			std::vector<int> lists[4];
+			std::vector<int> lists[5]; // 0-2 shared-memory classes, 3 one thread each, 4 one warp each
 			for (int t = 0; t < ns; ++t) {
-				const uint32_t c = caps_scratch_[t];
-				int k = 3;
-				for (int i = 2; i >= 0; --i) if (c <= cls[i]) k = i;
+				int k = kind[t] == 2 ? 4 : 3;
+				if (kind[t] == 0) for (int i = 2; i >= 0; --i) if (capb[t] <= cls[i]) k = i;
 				lists[k].push_back(t);
 			}
-			caps_scratch_.clear();
 			std::vector<int> all;
-			size_t start[5] = {0, 0, 0, 0, 0};
-			for (int k = 0; k < 4; ++k) { start[k] = all.size(); all.insert(all.end(), lists[k].begin(), lists[k].end()); }
-			start[4] = all.size();
+			size_t start[6] = {0, 0, 0, 0, 0, 0};
+			for (int k = 0; k < 5; ++k) { start[k] = all.size(); all.insert(all.end(), lists[k].begin(), lists[k].end()); }
 			int *d_list = (int*)b_misc.need(std::max<size_t>(all.size(), 1) * sizeof(int));
 			YAKB_CUDA(cudaMemcpyAsync(d_list, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
 			for (int k = 0; k < 3; ++k) {
 				if (lists[k].empty()) continue;
 				const size_t sm = (size_t)cls[k] * 8 + (size_t)(cls[k] < 32 ? 1 : cls[k] >> 5) * 8 + 512 * 8;
 				YAKB_CUDA(cudaFuncSetAttribute(build_layout_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-				build_layout_smem_kernel<<<(uint32_t)lists[k].size(), 32, sm, stream>>>(d_list + start[k], cls[k], d_cat, d_catoff, d_pf, d_pv, d_trail,
-				                                                                          d_ocap, d_osize, d_out);
+				build_layout_smem_kernel<<<(uint32_t)lists[k].size(), 32, sm, stream>>>(d_list + start[k], cls[k], sv, s0 + b0, d_pf, d_pv, d_trail,
+				                                                                          d_out, d_ooff, d_ocap, d_osize);
 			}
 			if (!lists[3].empty())
-				build_layout_kernel<<<cdiv(lists[3].size(), 32), 32, 0, stream>>>(d_list + start[3], (int)lists[3].size(), d_cat, d_catoff, d_pf, d_pv, d_trail,
-				                                                                  d_keys, d_koff, d_bm, d_boff, d_ocap, d_osize, d_out);
+				build_layout_kernel<<<cdiv(lists[3].size(), 32), 32, 0, stream>>>(d_list + start[3], (int)lists[3].size(), sv, s0 + b0, d_pf, d_pv, d_trail,
+				                                                                  d_out, d_ooff, d_bm, d_boff, d_ocap, d_osize);
+			if (!lists[4].empty()) {
+				uint64_t *d_cat = b_lay[0].as<uint64_t>(std::max<uint64_t>(catoff.back(), 1));
+				uint32_t *d_own = b_lay[7].as<uint32_t>(std::max<uint64_t>(ooff.back(), 1));
+				uint64_t *d_catoff = (uint64_t*)b_tmp.need((size_t)(2 * ns + 2) * 8), *d_run = d_catoff + ns + 1;
+				YAKB_CUDA(cudaMemcpyAsync(d_catoff, catoff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
+				YAKB_CUDA(cudaMemsetAsync(d_run, 0, (size_t)ns * 8, stream));
+				for (auto &seg : journal)
+					gather_seg_kernel<<<(uint32_t)lists[4].size(), 256, 0, stream>>>(seg.keys, seg.off, s0 + b0, d_list + start[4], (int)lists[4].size(), d_catoff, d_run, d_cat);
+				build_layout_warp_kernel<<<(uint32_t)lists[4].size(), 32, 0, stream>>>(d_list + start[4], d_cat, d_catoff, d_pf, d_pv, d_trail,
+				                                                                       d_out, d_ooff, d_bm, d_boff, d_own, d_ocap, d_osize);
+			}
 			YAKB_CUDA(cudaGetLastError());
 			YAKB_CUDA(cudaStreamSynchronize(stream)); // `all` must outlive the copy
 		}
-		if (with_counts && ncat && cap)
-			fill_counts_kernel<<<cdiv(ncat, 256), 256, 0, stream>>>(d_out, d_catoff, ns, s0 + b0, ncat, slots, cap);
-		YAKB_CUDA(cudaGetLastError());
 		std::vector<uint32_t> h_cap(ns), h_size(ns);
 		YAKB_CUDA(cudaMemcpyAsync(h_cap.data(), d_ocap, ns * 4, cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaMemcpyAsync(h_size.data(), d_osize, ns * 4, cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaStreamSynchronize(stream));
-		for (int t = 0; t < ns; ++t)
-			if (h_size[t] > catoff[t + 1] - catoff[t]) throw CudaError("[yakb] layout: inconsistent journal");
-		fn(b0, ns, catoff, d_catoff, d_out, d_osize, h_cap, h_size);
+		std::vector<uint64_t> voff(ns + 1, 0);
+		for (int t = 0; t < ns; ++t) {
+			if (h_size[t] > ooff[t + 1] - ooff[t]) throw CudaError("[yakb] layout: inconsistent journal");
+			voff[t + 1] = voff[t] + h_size[t];
+		}
+		const uint64_t nv = voff.back();
+		uint64_t *d_dense = b_lay[2].as<uint64_t>(std::max<uint64_t>(nv, 1));
+		YAKB_CUDA(cudaMemcpyAsync(d_voff, voff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
+		if (nv) {
+			densify_kernel<<<cdiv(nv, 256), 256, 0, stream>>>(d_out, d_ooff, d_voff, ns, nv, d_dense);
+			if (with_counts && cap) fill_counts_kernel<<<cdiv(nv, 256), 256, 0, stream>>>(d_dense, d_voff, ns, s0 + b0, nv, slots, cap);
+		}
+		YAKB_CUDA(cudaGetLastError());
+		fn(b0, ns, voff, d_voff, d_dense, h_cap, h_size);
+		YAKB_CUDA(cudaStreamSynchronize(stream)); // voff is read by the copy above until here
 		b0 = b1;
 	}
 }
@@ -1186,16 +1309,15 @@ void Engine::layout(int s0, int s1, LayoutOut &out, bool with_counts)
 {
 	const int nsub = s1 - s0;
 	out.cap.assign(nsub, 0); out.size.assign(nsub, 0); out.off.assign(nsub + 1, 0); out.keys.clear();
-	layout_batches(s0, s1, with_counts, [&](int b0, int ns, const std::vector<uint64_t> &catoff, const uint64_t *, const uint64_t *d_out,
-	                                          const uint32_t *, const std::vector<uint32_t> &h_cap, const std::vector<uint32_t> &h_size) {
-		const uint64_t ncat = catoff.back();
-		std::vector<uint64_t> tmp(ncat);
-		if (ncat) YAKB_CUDA(cudaMemcpyAsync(tmp.data(), d_out, ncat * 8, cudaMemcpyDeviceToHost, stream));
+	layout_batches(s0, s1, with_counts, 0, [&](int b0, int ns, const std::vector<uint64_t> &voff, const uint64_t *, const uint64_t *d_dense,
+	                                             const std::vector<uint32_t> &h_cap, const std::vector<uint32_t> &h_size) {
+		const uint64_t nv = voff.back(), base = out.keys.size();
+		out.keys.resize(base + nv);
+		if (nv) YAKB_CUDA(cudaMemcpyAsync(out.keys.data() + base, d_dense, nv * 8, cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaStreamSynchronize(stream));
-		for (int t = 0; t < ns; ++t) { // a sub-table's run may be shorter than its journal (operation entries)
+		for (int t = 0; t < ns; ++t) {
 			out.cap[b0 + t] = h_cap[t]; out.size[b0 + t] = h_size[t];
-			out.keys.insert(out.keys.end(), tmp.begin() + catoff[t], tmp.begin() + catoff[t] + h_size[t]);
-			out.off[b0 + t + 1] = out.keys.size();
+			out.off[b0 + t + 1] = base + voff[t + 1];
 		}
 	});
 }
@@ -1224,16 +1346,16 @@ void Engine::load_subtables(const std::vector<uint32_t> &caps, const std::vector
 	tot = n;
 }
 
-// flag[i] = 1 if entry i of a layout batch is a real key (inside its sub-table's run) whose count is in [lo, hi]
-__global__ void shrink_flag_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ catoff, const uint32_t *__restrict__ size,
-                                   int ns, uint64_t n, uint32_t lo_c, uint32_t hi_c, uint8_t *__restrict__ flag, uint32_t *kept)
+// flag[i] = 1 if key i of a dense layout batch has its count in [lo, hi]; kept[t] counts them per sub-table
+__global__ void shrink_flag_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ voff, int ns, uint64_t n,
+                                   uint32_t lo_c, uint32_t hi_c, uint8_t *__restrict__ flag, uint32_t *kept)
 {
 	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	uint32_t lo = 0, hi = ns;
-	while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (catoff[mid] <= i) lo = mid; else hi = mid; }
+	while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (voff[mid] <= i) lo = mid; else hi = mid; }
 	const uint32_t c = (uint32_t)keys[i] & YAKB_MAX_COUNT;
-	const bool keep = i - catoff[lo] < size[lo] && c >= lo_c && c <= hi_c;
+	const bool keep = c >= lo_c && c <= hi_c;
 	flag[i] = keep;
 	if (keep) atomicAdd(&kept[lo], 1u);
 }
@@ -1250,16 +1372,16 @@ void Engine::shrink(int min, int max)
 	{ std::vector<uint32_t> z; sizes(z); for (uint32_t v : z) total += v; }
 	uint64_t *d_kept = b_newv.as<uint64_t>(std::max<uint64_t>(total, 1)); // every batch appends here
 	uint64_t n_kept = 0;
-	layout_batches(0, P, true, [&](int b0, int ns, const std::vector<uint64_t> &catoff, const uint64_t *d_catoff, const uint64_t *d_out,
-	                                const uint32_t *d_osize, const std::vector<uint32_t> &, const std::vector<uint32_t> &h_size) {
-		const uint64_t ncat = catoff.back();
-		uint8_t *flag = b_pflag.as<uint8_t>(std::max<uint64_t>(ncat, 1));
+	layout_batches(0, P, true, 0, [&](int b0, int ns, const std::vector<uint64_t> &voff, const uint64_t *d_voff, const uint64_t *d_dense,
+	                                   const std::vector<uint32_t> &, const std::vector<uint32_t> &h_size) {
+		const uint64_t nv = voff.back();
+		uint8_t *flag = b_pflag.as<uint8_t>(std::max<uint64_t>(nv, 1));
 		uint32_t *d_cnt = b_pend.as<uint32_t>(ns + 1);
 		YAKB_CUDA(cudaMemsetAsync(d_cnt, 0, (ns + 1) * 4, stream));
 		std::vector<uint32_t> h_cnt(ns, 0);
-		if (ncat) {
-			shrink_flag_kernel<<<cdiv(ncat, 256), 256, 0, stream>>>(d_out, d_catoff, d_osize, ns, ncat, (uint32_t)min, (uint32_t)max, flag, d_cnt);
-			compact_flagged_u64(d_out, flag, ncat, d_kept + n_kept, d_cnt + ns, stream, rs);
+		if (nv) {
+			shrink_flag_kernel<<<cdiv(nv, 256), 256, 0, stream>>>(d_dense, d_voff, ns, nv, (uint32_t)min, (uint32_t)max, flag, d_cnt);
+			compact_flagged_u64(d_dense, flag, nv, d_kept + n_kept, d_cnt + ns, stream, rs);
 			YAKB_CUDA(cudaGetLastError());
 		}
 		YAKB_CUDA(cudaMemcpyAsync(h_cnt.data(), d_cnt, ns * 4, cudaMemcpyDeviceToHost, stream));

@@ -87,9 +87,8 @@ struct Engine {
 	double load_limit = 0.6;
 	// scratch (grow-only, reused by every chunk)
 	DBuf b_w2, b_wm, b_flags, b_tilecnt, b_tileoff, b_pv, b_ppos, b_sv, b_sj, b_sv2, b_sj2, b_pflag, b_newv, b_newsorted,
-	     b_tmp, b_pend, b_lput, b_lnew, b_stats, b_misc, b_lay[12];
+	     b_tmp, b_pend, b_lput, b_lnew, b_stats, b_misc, b_lay[12], b_segp;
 	RadixScratch rs;
-	std::vector<uint32_t> caps_scratch_;
 
 	static Engine *create(int k, int pre, int n_hash, int n_shift, int rank = 0, int world = 1);
 	~Engine();
@@ -118,7 +117,7 @@ struct Engine {
 	// restore: sub-table s gets `keys` (stored form, with counts) in file order, khashl pre-sized to cap
 	void load_subtables(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys, bool keys_on_device = false);
 	void rebuild_dev(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *d_keys);
-	template<class F> void layout_batches(int s0, int s1, bool with_counts, F &&fn);
+	template<class F> void layout_batches(int s0, int s1, bool with_counts, uint64_t reserve_bytes, F &&fn);
 	uint64_t device_bytes() const;
 	static uint64_t launches();
 	static void note_launch(int n);
