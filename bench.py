@@ -223,7 +223,7 @@ def run_reference_arm(args):
             pass
     ev_per_step = n_ev / (W + KS)
     val = ev_per_step * KS / (ms_total / 1000.0)
-    line = {"impl": "reference", "metric": "k-mer events/s (k=31, pass 1 of `yak count -b37`, chunk steps)", "value": val,
+    line = {"impl": "reference", "metric": f"k-mer events/s (k={K}, pass 1 of `yak count -b{args.bf_shift}`, chunk steps)", "value": val,
             "unit": "events/s", "n_gpus": args.gpus, "steps": KS, "warmup": W, "ms_per_step": ms_total / KS,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "cfg2", "k": K, "pre": PRE, "bf_shift": bf, "bf_n_hash": NH, "read_len": L, "genome_bp": G,
@@ -241,6 +241,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome", type=int, default=3_000_000_000)
+    ap.add_argument("--k", type=int, default=K, help="k-mer length (configs[4] sweeps 21/31/47/63)")
     ap.add_argument("--chunk-reads", type=int, default=2_000_000)
     ap.add_argument("--bf-shift", type=int, default=BF)
     ap.add_argument("--e2e-reads", type=int, default=4_000_000)
@@ -248,6 +249,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
+    globals()["K"] = args.k
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -379,7 +381,7 @@ def main():
                 "peak_source": peak_kind, "launches": nl, "kernel_ms_total": tms,
                 "algorithmic_bytes_per_launch": ab / max(nl, 1),
                 "share_of_step": tms / ms if ms > 0 else None}
-    line = {"metric": "k-mer events/s (k=31, pass 1 of `yak count -b37`, chunk steps)", "value": value, "unit": "events/s",
+    line = {"metric": f"k-mer events/s (k={K}, pass 1 of `yak count -b{args.bf_shift}`, chunk steps)", "value": value, "unit": "events/s",
             "n_gpus": world, "steps": KS, "warmup": W, "ms_per_step": ms / KS, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "cfg2", "k": K, "pre": PRE, "bf_shift": args.bf_shift, "bf_n_hash": NH, "read_len": L,

@@ -237,7 +237,16 @@ size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len,
 			});
 		}
 		for (auto &th : pool) th.join();
+		// stitch in order with the true state; big block outputs that fit the caller's buffer are
+		// copied there by the workers in parallel afterwards (the single stitching thread would
+		// otherwise spend most of the round in memcpy)
+		struct CopyTask { const uint8_t *src; size_t len, dst_off; };
+		std::vector<CopyTask> tasks;
 		std::vector<uint8_t> gap;
+		auto emit_big = [&](const uint8_t *p, size_t len, int64_t recs) {
+			if (len >= (1u << 16) && spill_.empty() && n + len <= cap) { tasks.push_back({p, len, n}); n += len; *n_seq += recs; }
+			else emit(p, len, recs);
+		};
 		for (int t = 0; t < nb; ++t) {
 			BlockJob &j = jobs_[t];
 			int64_t gs = 0;
@@ -248,7 +257,7 @@ size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len,
 				if (true_.at_record_boundary()) { // the guess was a real record start: adopt the speculative result
 					if (true_.st == FastxCore::S_SEQ) close_carried(true_, true, min_len, gap, &gs);
 					emit(gap.data(), gap.size(), gs);
-					emit(j.out.data(), j.out.size(), j.nseq);
+					emit_big(j.out.data(), j.out.size(), j.nseq);
 					true_ = std::move(j.spec);
 				} else { // wrong guess: this block again, sequentially, from the true state
 					true_.feed(j.raw.get() + j.q, j.n - j.q, min_len, gap, &gs);
@@ -256,6 +265,12 @@ size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len,
 					++n_redo_;
 				}
 			} else emit(gap.data(), gap.size(), gs);
+		}
+		if (!tasks.empty()) {
+			std::vector<std::thread> cp;
+			for (size_t k = 1; k < tasks.size(); ++k) cp.emplace_back([&, k]() { memcpy(dst + tasks[k].dst_off, tasks[k].src, tasks[k].len); });
+			memcpy(dst + tasks[0].dst_off, tasks[0].src, tasks[0].len);
+			for (auto &th : cp) th.join();
 		}
 		next_off_ = base + (uint64_t)nb * block_;
 		if (next_off_ >= size_ || nb == 0) {
