@@ -367,9 +367,10 @@ def main():
         "compact": 8.0 * n_pending,
         "pack_ascii": 1.375 * nr * rec * KS,
     }
-    # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r01_top_kernels_ncu.md,
-    # step ~10 of this workload; dram__bytes_read.sum + dram__bytes_write.sum)
-    ncu_traffic = {"k1_fused": 7.852583e9 + 1.164658e9, "group_insert": 20.139495e9 + 15.937980e9}
+    # DRAM bytes per launch from the committed `ncu --set full` captures (dram__bytes_read.sum + dram__bytes_write.sum):
+    # k1_fused in the steady state (profiles/r01_k1_fused_steady.md), group_insert at step ~10 (profiles/r01_top_kernels_ncu.md)
+    ncu_traffic = {"k1_fused": 8.218429e9 + 7.537115e9, "group_insert": 20.139495e9 + 15.937980e9}
+    ncu_source = {"k1_fused": "profiles/r01_k1_fused_steady.md", "group_insert": "profiles/r01_top_kernels_ncu.md"}
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, [0, 0])
     roof = None
     if dom[0]:
@@ -377,9 +378,13 @@ def main():
         ab = alg_bytes.get(nm, 0.0)
         ach = ab / (tms / 1000.0) / 1e9 if tms > 0 else 0.0
         roof = {"bound": "hbm", "kernel": nm, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": ncu_traffic.get(nm), "traffic_source": "profiles/r01_top_kernels_ncu.md" if nm in ncu_traffic else None,
+                "traffic": ncu_traffic.get(nm), "traffic_source": ncu_source.get(nm),
                 "peak_source": peak_kind, "launches": nl, "kernel_ms_total": tms,
                 "algorithmic_bytes_per_launch": ab / max(nl, 1),
+                # the binding limit of a hash-table update is the random 32-byte read-modify-write rate, not bytes:
+                # measured with tools/gups.cu on this pool (profiles/r01_gups_random_access.txt, 64 GiB footprint)
+                "random_rmw": {"achieved_gops": (ev_total / (tms / 1000.0) / 1e9) if nm.startswith("k1_") and tms > 0 else None,
+                               "peak_gops": 14.7, "unit": "G read-modify-writes/s"},
                 "share_of_step": tms / ms if ms > 0 else None}
     line = {"metric": f"k-mer events/s (k={K}, pass 1 of `yak count -b{args.bf_shift}`, chunk steps)", "value": value, "unit": "events/s",
             "n_gpus": world, "steps": KS, "warmup": W, "ms_per_step": ms / KS, "higher_is_better": True, "scaling": "weak",

@@ -41,4 +41,9 @@ out["hist_peak"] = max(range(2, 1024), key=lambda i: hist[i]); out["hist_sum"] =
 out["total_s"] = out["pass1_s"] + out["destroy_bf_clear_s"] + out["pass2_s"] + out["shrink_s"]
 out["input_events_per_s"] = out["events"] / out["total_s"]
 print(json.dumps(out), flush=True)
+if len(sys.argv) > 4 and sys.argv[4] == "dump":
+    t0 = time.time(); rc = lib.yak_ch_dump(h, b"/dev/shm/yakb_full.yak"); out["dump_s"] = time.time() - t0
+    out["dump_bytes"] = os.path.getsize("/dev/shm/yakb_full.yak") if rc == 0 else -1
+    os.unlink("/dev/shm/yakb_full.yak")
+    print(json.dumps(out), flush=True)
 lib.yak_ch_destroy(h)
