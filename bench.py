@@ -351,9 +351,10 @@ def main():
         be.close()
     del buf
     torch.cuda.empty_cache()
+    if world > 1:  # every rank leaves the process group together; the legs below are rank 0's alone
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel (live CUDA-event times from inside the library)
@@ -419,7 +420,7 @@ def main():
         dt = time.time() - t0
         osz = os.path.getsize(out)
         lib.yak_ch_destroy(hh)
-        line["e2e"] = {"value": n_ev / dt1, "unit": "events/s", "h2d_bytes_per_step": args.e2e_reads * (L + 1),
+        line["e2e"] = {"value": n_ev / dt1, "unit": "events/s", "n_gpus_used": 1, "h2d_bytes_per_step": args.e2e_reads * (L + 1),
                        "d2h_bytes_per_step": 8, "seconds": dt1, "distinct_after_pass1": tot1,
                        "what": f"yak_count(pass 1, -b{args.bf_shift}) of {args.e2e_reads} FASTQ reads ({fsz} B in tmpfs): parse + H2D + kernels, {n_ev} events"}
         line["e2e_full_job"] = {"value": n_ev / dt, "unit": "input events/s", "seconds": dt, "h2d_bytes": 2 * args.e2e_reads * (L + 1),
@@ -437,8 +438,6 @@ def main():
     if args.verbose:
         sys.stderr.write(json.dumps(per_step) + "\n")
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
