@@ -35,7 +35,17 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout, which must carry exactly one JSON line
+
+# stdout must carry exactly ONE JSON line, but libraries print there too (NCCL's version banner, for one):
+# keep a private handle on the real stdout for the result and point fd 1 at stderr for everybody else.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit_result(line: dict) -> None:
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 
 K, PRE, BF, NH, L = 31, 12, 37, 4, 150
 SEED_G, SEED_R = 20260925, 7
@@ -231,7 +241,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": val, "unit": "events/s", "cores": threads, "kind": kind,
                              "sample": f"yak count -k{K} -p{PRE} -b{bf} -t{threads} -K{per * L}: pass-1 batches {W + 1}..{W + KS} of {per} reads ({int(ev_per_step)} events each), timed from the reference's own progress lines"},
             "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit_result(line)
 
 
 def main():
@@ -437,7 +447,7 @@ def main():
                 pass
     if args.verbose:
         sys.stderr.write(json.dumps(per_step) + "\n")
-    print(json.dumps(line))
+    emit_result(line)
 
 
 if __name__ == "__main__":
