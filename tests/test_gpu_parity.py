@@ -30,7 +30,8 @@ def reads_fq():
 
 
 @pytest.mark.parametrize("k,pre,b", [(31, 12, 0), (31, 10, 0), (21, 11, 0), (15, 10, 0), (47, 12, 0), (63, 10, 0),
-                                     (31, 12, 22), (31, 10, 20), (31, 12, 24), (27, 11, 21), (63, 10, 21), (31, 12, 12)])
+                                     (31, 12, 22), (31, 10, 20), (31, 12, 24), (27, 11, 21), (63, 10, 21), (31, 12, 12),
+                                     (31, 14, 0), (31, 14, 25), (31, 16, 0), (31, 16, 26), (32, 10, 0), (4, 10, 0)])
 def test_count_matches_oracle(oracle, yakb, reads_fa, k, pre, b):
     ho, hg, ref, mine, ne = _count_both(oracle, yakb, reads_fa, k, pre, b)
     try:
