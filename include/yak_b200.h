@@ -64,6 +64,10 @@ void *yakb_ch_stream(const yak_ch_t *h);
 uint64_t yakb_ch_device_bytes(const yak_ch_t *h);
 /* number of kernels this library launched so far in this process */
 uint64_t yakb_kernel_launches(void);
+/* The library keeps device blocks of destroyed tables for the next table (csrc/dbuf.cuh; bounded by
+ * YAKB_CACHE_GB, default 48): bytes held idle right now, and a call that hands them all back. */
+uint64_t yakb_device_cache_bytes(void);
+void yakb_device_cache_trim(void);
 
 /* the host-side FASTA/FASTQ record reader yak_count/yak_qv use (reference kseq.h:192-232
  * semantics; plain or gzip; NULL or "-" = stdin).  next() returns the sequence length, -1 at EOF,

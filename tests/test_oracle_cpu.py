@@ -360,6 +360,20 @@ def test_parallel_reader_is_exactly_the_sequential_reader(block, threads):
     assert not capi.lib().yakb_pfastx_open((files[0] + ".gz").encode(), 0, 0) or True
 
 
+def test_parallel_reader_pool_copies_and_parse_ahead():
+    """the streaming pool: block outputs >= 64 KB are copied into the caller's buffer by the workers while other
+    blocks are parsed ahead; many small fills and few large ones must both reproduce the sequential reader"""
+    from yak_b200 import synth
+    p = os.path.join(util.TMP, "yakb_par_big.fq")
+    with open(p, "wb") as f:
+        f.write(synth.reads_file_bytes(5, 200_000, 9, 60_000, 150, 0.01, 3, fastq=True))
+    want, wn = _fill_all(p, 1 << 22, 1 << 22, 31)
+    for block, threads, cap, target in [(256 << 10, 8, 3 << 20, 2 << 20), (128 << 10, 5, 1 << 20, 300_000), (1 << 20, 3, 40 << 20, 40 << 20)]:
+        for _ in range(3):
+            got, gn, redo = _pfill_all(p, block, threads, cap, target, 31)
+            assert got == want and gn == wn, (block, threads, cap, target, redo)
+
+
 def test_bench_reference_arm_prints_one_json_line():
     """`bench.py --impl reference` (the CPU arm the driver runs) on a tiny bounded sample, here without a GPU"""
     import json

@@ -33,11 +33,11 @@ template<int MODE,int ILP> void run(uint64_t* a, uint64_t n, const char* name){
   cudaFree(sink);
 }
 int main(){
-  for (double gb : {1.0, 8.0, 32.0, 64.0, 120.0}){
+  for (double gb : {0.008, 0.03125, 0.0625, 0.25, 1.0, 8.0, 32.0, 64.0, 120.0}){
     uint64_t n=(uint64_t)(gb*(1ull<<30)/8); uint64_t* a;
     if (cudaMalloc(&a,n*8)!=cudaSuccess){ printf("alloc %.0f GB failed\n",gb); continue; }
     cudaMemset(a,0,n*8);
-    printf("footprint %.0f GiB\n",gb);
+    printf("footprint %.4g GiB\n",gb);
     run<0,1>(a,n,"load");
     run<0,8>(a,n,"load");
     run<1,8>(a,n,"load+CAS");

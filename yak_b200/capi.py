@@ -91,6 +91,8 @@ def lib() -> C.CDLL:
         "yakb_ch_stream": (vp, [ChP]),
         "yakb_ch_device_bytes": (u64, [ChP]),
         "yakb_kernel_launches": (u64, []),
+        "yakb_device_cache_bytes": (u64, []),
+        "yakb_device_cache_trim": (None, []),
         "yakb_fastx_open": (vp, [C.c_char_p]),
         "yakb_fastx_next": (i64, [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]),
         "yakb_fastx_close": (None, [vp]),

@@ -36,9 +36,8 @@ struct ChBox {
 	std::vector<yak_ht_t> handles;
 	std::vector<yak_bf_t> filters;
 	std::mutex mu;
-	DBuf d_in, d_aux, d_aux2;
-	uint8_t *pinned[2] = {nullptr, nullptr};
-	size_t pinned_cap = 0;
+	DBuf d_in, d_in2, d_aux, d_aux2;
+	cudaStream_t copy_stream = nullptr; // host->device copies of yak_count batches, overlapping the kernels
 };
 static const uint32_t kMagic = 0x59414B42; // "YAKB"
 
@@ -149,8 +148,8 @@ extern "C" void yak_ch_destroy(yak_ch_t *h) // htab.c:41-49
 	ChBox *b = box_of(h);
 	delete b->eng;
 	free(b->pub.h);
-	for (int i = 0; i < 2; ++i) if (b->pinned[i]) cudaFreeHost(b->pinned[i]);
-	b->d_in.release(); b->d_aux.release(); b->d_aux2.release();
+	if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+	b->d_in.release(); b->d_in2.release(); b->d_aux.release(); b->d_aux2.release();
 	b->magic = 0;
 	delete b;
 }
@@ -576,6 +575,8 @@ extern "C" uint64_t yakb_ch_device_bytes(const yak_ch_t *h) { return box_of(h)->
 extern "C" const char *yakb_version(void) { return YAKS_VERSION; }
 extern "C" int yakb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 extern "C" uint64_t yakb_kernel_launches(void) { return Engine::launches(); }
+extern "C" uint64_t yakb_device_cache_bytes(void) { return (uint64_t)dev_pool_idle(); }
+extern "C" void yakb_device_cache_trim(void) { dev_trim(); }
 extern "C" void yakb_prof_enable(int on) { Prof::enable(on != 0); if (on) Prof::reset(); }
 extern "C" int yakb_prof_json(char *buf, uint64_t cap)
 {
@@ -691,8 +692,35 @@ static uint64_t batch_bases(int64_t chunk_size)
 	return b;
 }
 
+// Pinned staging buffers are process-wide and outlive a table: cudaMallocHost of two batch-sized
+// buffers costs more than counting a small file, and yak_count is called once per pass.
+namespace {
+struct PinnedPool {
+	std::mutex mu;
+	std::vector<std::pair<uint8_t*, size_t>> idle;
+	uint8_t *get(size_t bytes, size_t *cap)
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		int best = -1;
+		for (int i = 0; i < (int)idle.size(); ++i)
+			if (idle[i].second >= bytes && (best < 0 || idle[i].second < idle[best].second)) best = i;
+		if (best >= 0) { uint8_t *p = idle[best].first; *cap = idle[best].second; idle.erase(idle.begin() + best); return p; }
+		if (idle.size() >= 2) { cudaFreeHost(idle.back().first); idle.pop_back(); } // too small to be useful: do not hoard
+		uint8_t *p = nullptr;
+		YAKB_CUDA(cudaMallocHost(&p, bytes));
+		*cap = bytes;
+		return p;
+	}
+	void put(uint8_t *p, size_t cap) { if (p) { std::lock_guard<std::mutex> lk(mu); idle.push_back({p, cap}); } }
+};
+PinnedPool g_pinned;
+}
+
 // count.c:147-166 with 85-145 folded in: read records, drop those shorter than k (count.c:95),
 // concatenate with '\n' separators into pinned memory, ship the batch, run the device path.
+// Three things overlap: the reader's pool parses ahead of the consumer, the producer thread stitches
+// batch i+1 into pinned memory and copies it to the device on its own stream, the main thread runs
+// the kernels of batch i.
 extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *h0)
 {
 	GUARD_BEGIN
@@ -709,45 +737,70 @@ extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *
 	std::lock_guard<std::mutex> lk(b->mu);
 	const int create_new = h0 == 0;
 	const uint64_t cap = batch_bases(opt->chunk_size);
-	size_t need = cap + (cap >> 4) + 4096;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (!b->copy_stream) YAKB_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+	uint8_t *pinned[2] = {nullptr, nullptr};
+	size_t pinned_cap[2] = {0, 0};
 	auto ensure_pinned = [&](size_t bytes) {
-		if (b->pinned_cap >= bytes) return;
-		for (int i = 0; i < 2; ++i) { if (b->pinned[i]) cudaFreeHost(b->pinned[i]); b->pinned[i] = nullptr; }
-		for (int i = 0; i < 2; ++i) YAKB_CUDA(cudaMallocHost(&b->pinned[i], bytes));
-		b->pinned_cap = bytes;
+		for (int i = 0; i < 2; ++i)
+			if (pinned_cap[i] < bytes) { g_pinned.put(pinned[i], pinned_cap[i]); pinned[i] = g_pinned.get(bytes, &pinned_cap[i]); }
 	};
-	{ StageTimer tp("yak_count:pinned"); ensure_pinned(need); }
-	// producer thread parses the next batch into one pinned buffer while the device works on the other
-	struct Batch { size_t n = 0; int64_t n_seq = 0; bool done = false; size_t need = 0; };
+	struct Release { uint8_t **p; size_t *c; ~Release() { for (int i = 0; i < 2; ++i) g_pinned.put(p[i], c[i]); } } release{pinned, pinned_cap};
+	{ StageTimer tp("yak_count:pinned"); ensure_pinned(cap + (cap >> 4) + 4096); }
+	struct Batch { size_t n = 0; int64_t n_seq = 0; bool done = false; size_t need = 0; std::string err; };
 	Batch batch[2];
-	auto parse = [&](int slot) {
+	DBuf *d_in[2] = {&b->d_in, &b->d_in2};
+	auto produce = [&](int slot, uint64_t target) {
 		Batch &t = batch[slot];
 		t = Batch();
-		t.n = par ? prd.fill(b->pinned[slot], b->pinned_cap, cap, opt->k, &t.n_seq, &t.done, &t.need)
-		          : rd.fill(b->pinned[slot], b->pinned_cap, cap, opt->k, &t.n_seq, &t.done, &t.need);
+		try {
+			cudaSetDevice(dev);
+			const size_t pc = std::min(pinned_cap[0], pinned_cap[1]);
+			t.n = par ? prd.fill(pinned[slot], pc, target, opt->k, &t.n_seq, &t.done, &t.need)
+			          : rd.fill(pinned[slot], pc, target, opt->k, &t.n_seq, &t.done, &t.need);
+			if (t.n && !t.need) {
+				uint8_t *d = d_in[slot]->as<uint8_t>(t.n + 64);
+				YAKB_CUDA(cudaMemcpyAsync(d, pinned[slot], t.n, cudaMemcpyHostToDevice, b->copy_stream));
+				YAKB_CUDA(cudaStreamSynchronize(b->copy_stream));
+			}
+		} catch (const std::exception &e) { t.err = e.what(); t.done = true; }
 	};
 	int slot = 0;
-	parse(0);
+	// (YAKB_RAMP=<bases> makes the first batch that small and doubles from there; with the pooled parser the
+	// first full batch is ready within ~10 ms, so the default is no ramp)
+	const char *env_ramp = getenv("YAKB_RAMP");
+	uint64_t target = env_ramp && atoll(env_ramp) > 0 ? std::min<uint64_t>(cap, (uint64_t)atoll(env_ramp)) : cap;
+	double t_first = wall_now(), t_dev = 0, t_wait = 0;
+	int n_batches = 0;
+	produce(0, target);
+	t_first = wall_now() - t_first;
 	for (;;) {
 		Batch cur = batch[slot];
+		if (!cur.err.empty()) throw CudaError(cur.err);
 		if (cur.need) { // one record larger than the staging buffers: grow them and parse again
 			ensure_pinned(cur.need + (cur.need >> 3) + 4096);
-			parse(slot);
+			produce(slot, target);
 			continue;
 		}
+		const uint64_t next_target = std::min<uint64_t>(cap, target * 2);
 		std::thread producer;
-		if (!cur.done) producer = std::thread(parse, slot ^ 1);
+		if (!cur.done) producer = std::thread(produce, slot ^ 1, next_target);
+		struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_on_unwind{producer};
 		if (cur.n) {
-			uint8_t *d = b->d_in.as<uint8_t>(cur.n + 64);
-			YAKB_CUDA(cudaMemcpyAsync(d, b->pinned[slot], cur.n, cudaMemcpyHostToDevice, b->eng->stream));
-			run_ascii_dev(b, d, cur.n, create_new, nullptr);
+			const double td = wall_now();
+			run_ascii_dev(b, (const uint8_t*)d_in[slot]->p, cur.n, create_new, nullptr);
+			t_dev += wall_now() - td; ++n_batches;
+			if (timing_on()) fprintf(stderr, "[T::yak_count] batch %d: %zu bytes, kernels %.4f s\n", n_batches, cur.n, wall_now() - td);
 			fprintf(stderr, "[M::%s::%.3f*%.2f] processed %d sequences; %ld distinct k-mers in the hash table\n", __func__,
 			        wall_now() - g_t0, cpu_now() / (wall_now() - g_t0 + 1e-9), (int)cur.n_seq, (long)h->tot);
 		}
-		if (producer.joinable()) producer.join();
+		{ const double tw = wall_now(); if (producer.joinable()) producer.join(); t_wait += wall_now() - tw; }
 		if (cur.done) break;
 		slot ^= 1;
+		target = next_target;
 	}
+	if (timing_on()) fprintf(stderr, "[T::yak_count] %d batches: first batch ready after %.3f s, kernels %.3f s, waiting for the producer %.3f s\n", n_batches, t_first, t_dev, t_wait);
 	return h;
 	GUARD_END(0)
 }
@@ -889,12 +942,12 @@ extern "C" yak_bf_t *yak_bf_init(int n_shift, int n_hashes) // bbf.c:5-18
 	if (yakb_device_count() == 0) { fprintf(stderr, "[yakb] ERROR: no CUDA device; this library has no CPU path\n"); return 0; }
 	yak_bf_t *b = (yak_bf_t*)calloc(1, sizeof(yak_bf_t));
 	b->n_shift = n_shift; b->n_hashes = n_hashes;
-	YAKB_CUDA(cudaMalloc((void**)&b->b, (size_t)1 << (n_shift - 3)));
+	b->b = (uint8_t*)dev_alloc((size_t)1 << (n_shift - 3));
 	YAKB_CUDA(cudaMemset(b->b, 0, (size_t)1 << (n_shift - 3)));
 	return b;
 	GUARD_END(0)
 }
-extern "C" void yak_bf_destroy(yak_bf_t *b) { if (b == 0) return; cudaFree(b->b); free(b); } // bbf.c:20-24
+extern "C" void yak_bf_destroy(yak_bf_t *b) { if (b == 0) return; dev_free(b->b); free(b); } // bbf.c:20-24
 extern "C" int yak_bf_insert(yak_bf_t *b, uint64_t hash) // bbf.c:25-42
 {
 	GUARD_BEGIN

@@ -23,6 +23,7 @@
 #include <map>
 #include <string>
 #include <atomic>
+#include <mutex>
 #include <time.h>
 #include <stdlib.h>
 
@@ -36,18 +37,87 @@ void cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 	throw CudaError(buf);
 }
 
+// ---- cached device memory (see dbuf.cuh)
+namespace {
+struct DevCache {
+	std::mutex mu;
+	std::map<void*, size_t> live;                    // size of every block handed out
+	std::multimap<size_t, void*> idle;               // freed blocks by size
+	size_t idle_bytes = 0;
+	size_t limit() { static size_t v = 0; if (!v) { const char *e = getenv("YAKB_CACHE_GB"); v = (size_t)(e ? atof(e) : 48.0) << 30; if (!v) v = 1; } return v; }
+	bool enabled() { static int v = -1; if (v < 0) v = getenv("YAKB_NO_POOL") ? 0 : 1; return v != 0; }
+	void drop_all() { for (auto &kv : idle) cudaFree(kv.second); idle.clear(); idle_bytes = 0; }
+};
+DevCache g_dc;
+}
+void *dev_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+	if (!g_dc.enabled()) { YAKB_CUDA(cudaMalloc(&p, bytes)); return p; }
+	std::lock_guard<std::mutex> lk(g_dc.mu);
+	auto it = g_dc.idle.lower_bound(bytes); // smallest idle block that is large enough, if it is not wastefully large
+	if (it != g_dc.idle.end() && it->first <= bytes + (bytes >> 2) + (1u << 20)) {
+		p = it->second;
+		g_dc.live[p] = it->first;
+		g_dc.idle_bytes -= it->first;
+		g_dc.idle.erase(it);
+		return p;
+	}
+	cudaError_t e = cudaMalloc(&p, bytes);
+	if (e == cudaErrorMemoryAllocation && !g_dc.idle.empty()) { // idle blocks of the wrong sizes are in the way
+		(void)cudaGetLastError();
+		cudaDeviceSynchronize();
+		g_dc.drop_all();
+		e = cudaMalloc(&p, bytes);
+	}
+	YAKB_CUDA(e);
+	g_dc.live[p] = bytes;
+	return p;
+}
+void dev_free(void *p)
+{
+	if (p == nullptr) return;
+	if (!g_dc.enabled()) { cudaFree(p); return; }
+	cudaDeviceSynchronize(); // like cudaFree: nothing on the device uses the block any more
+	std::lock_guard<std::mutex> lk(g_dc.mu);
+	auto it = g_dc.live.find(p);
+	if (it == g_dc.live.end()) { cudaFree(p); return; }
+	const size_t bytes = it->second;
+	g_dc.live.erase(it);
+	g_dc.idle.insert({bytes, p});
+	g_dc.idle_bytes += bytes;
+	while (g_dc.idle_bytes > g_dc.limit() && !g_dc.idle.empty()) { // keep the hoard bounded: largest blocks go first
+		auto last = std::prev(g_dc.idle.end());
+		cudaFree(last->second);
+		g_dc.idle_bytes -= last->first;
+		g_dc.idle.erase(last);
+	}
+}
+size_t dev_pool_idle()
+{
+	std::lock_guard<std::mutex> lk(g_dc.mu);
+	return g_dc.idle_bytes;
+}
+void dev_trim()
+{
+	cudaDeviceSynchronize();
+	std::lock_guard<std::mutex> lk(g_dc.mu);
+	g_dc.drop_all();
+}
+
 void *DBuf::need(size_t bytes)
 {
 	if (bytes > cap) {
-		if (p) YAKB_CUDA(cudaFree(p));
+		if (p) dev_free(p);
 		p = nullptr;
 		size_t want = bytes + (bytes >> 3) + 256;
-		YAKB_CUDA(cudaMalloc(&p, want));
+		p = dev_alloc(want);
 		cap = want;
 	}
 	return p;
 }
-void DBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+void DBuf::release() { if (p) dev_free(p); p = nullptr; cap = 0; }
 
 static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
@@ -846,9 +916,9 @@ Engine *Engine::create(int k, int pre, int n_hash, int n_shift, int rank, int wo
 	Engine *g = new Engine;
 	g->k = k, g->pre = pre, g->P = 1 << (pre - lw), g->lw = lw, g->rank = rank;
 	YAKB_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
-	YAKB_CUDA(cudaMalloc(&g->nkeys, g->P * sizeof(uint32_t)));
-	YAKB_CUDA(cudaMalloc(&g->last_put, g->P * sizeof(uint64_t)));
-	YAKB_CUDA(cudaMalloc(&g->last_new, g->P * sizeof(uint64_t)));
+	g->nkeys = (uint32_t*)dev_alloc(g->P * sizeof(uint32_t));
+	g->last_put = (uint64_t*)dev_alloc(g->P * sizeof(uint64_t));
+	g->last_new = (uint64_t*)dev_alloc(g->P * sizeof(uint64_t));
 	YAKB_CUDA(cudaMemsetAsync(g->nkeys, 0, g->P * sizeof(uint32_t), g->stream));
 	YAKB_CUDA(cudaMemsetAsync(g->last_put, 0, g->P * sizeof(uint64_t), g->stream));
 	YAKB_CUDA(cudaMemsetAsync(g->last_new, 0, g->P * sizeof(uint64_t), g->stream));
@@ -863,7 +933,7 @@ Engine *Engine::create(int k, int pre, int n_hash, int n_shift, int rank, int wo
 		if (sub >= 9 && sub + 9 <= 64) {
 			g->nb = sub - 9;
 			size_t bytes = (size_t)1 << (n_shift - 3 - lw);
-			YAKB_CUDA(cudaMalloc(&g->bloom, bytes));
+			g->bloom = (uint8_t*)dev_alloc(bytes);
 			YAKB_CUDA(cudaMemsetAsync(g->bloom, 0, bytes, g->stream));
 		}
 	}
@@ -873,11 +943,7 @@ Engine *Engine::create(int k, int pre, int n_hash, int n_shift, int rank, int wo
 
 Engine::~Engine()
 {
-	if (slots) cudaFree(slots);
-	if (nkeys) cudaFree(nkeys);
-	if (bloom) cudaFree(bloom);
-	if (last_put) cudaFree(last_put);
-	if (last_new) cudaFree(last_new);
+	dev_free(slots); dev_free(nkeys); dev_free(bloom); dev_free(last_put); dev_free(last_new);
 	journal_free_all();
 	DBuf *all[] = {&b_w2, &b_wm, &b_flags, &b_tilecnt, &b_tileoff, &b_pv, &b_ppos, &b_sv, &b_sj, &b_sv2, &b_sj2, &b_pflag, &b_newv,
 	               &b_newsorted, &b_tmp, &b_pend, &b_lput, &b_lnew, &b_stats, &b_misc, 
@@ -895,7 +961,7 @@ void *Engine::journal_alloc(size_t bytes)
 		Slab sl;
 		sl.cap = std::max<size_t>(bytes, (size_t)2 << 30);
 		sl.used = 0;
-		YAKB_CUDA(cudaMalloc((void**)&sl.p, sl.cap));
+		sl.p = (char*)dev_alloc(sl.cap);
 		slabs.push_back(sl);
 	}
 	void *r = slabs.back().p + slabs.back().used;
@@ -905,12 +971,12 @@ void *Engine::journal_alloc(size_t bytes)
 
 void Engine::journal_free_all()
 {
-	for (auto &sl : slabs) cudaFree(sl.p);
+	for (auto &sl : slabs) dev_free(sl.p);
 	slabs.clear();
 	journal.clear();
 }
 
-void Engine::destroy_bloom() { if (bloom) { cudaFree(bloom); bloom = nullptr; } }
+void Engine::destroy_bloom() { if (bloom) { dev_free(bloom); bloom = nullptr; } }
 
 uint64_t Engine::device_bytes() const
 {
@@ -923,14 +989,14 @@ void Engine::grow(uint32_t new_cap)
 {
 	uint64_t *ns = nullptr;
 	const uint64_t total_new = (uint64_t)P * new_cap;
-	YAKB_CUDA(cudaMalloc(&ns, total_new * 8));
+	ns = (uint64_t*)dev_alloc(total_new * 8);
 	YAKB_CUDA(cudaMemsetAsync(ns, 0xFF, total_new * 8, stream));
 	if (slots && cap) {
 		const uint64_t total_old = (uint64_t)P * cap;
 		rehash_kernel<<<cdiv(total_old, 256), 256, 0, stream>>>(slots, cap, total_old, ns, new_cap);
 		YAKB_CUDA(cudaGetLastError());
 		YAKB_CUDA(cudaStreamSynchronize(stream));
-		YAKB_CUDA(cudaFree(slots));
+		dev_free(slots);
 	}
 	slots = ns; cap = new_cap;
 }
@@ -1197,6 +1263,7 @@ template<class F> void Engine::layout_batches(int s0, int s1, bool with_counts, 
 	// of them run at once the better), but never less than 2 GB
 	size_t mem_free = 0, mem_total = 0;
 	cudaMemGetInfo(&mem_free, &mem_total);
+	mem_free += dev_pool_idle(); // idle pool blocks are ours to take
 	mem_free += b_lay[0].cap + b_lay[1].cap + b_lay[2].cap + b_lay[3].cap + b_lay[7].cap; // our own grow-only scratch is reusable
 	uint64_t budget = mem_free > reserve_bytes ? (uint64_t)((mem_free - reserve_bytes) * 0.8) : 0;
 	budget = std::max<uint64_t>(budget, 2ull << 30);
@@ -1399,7 +1466,7 @@ void Engine::rebuild(const std::vector<uint32_t> &caps, const std::vector<uint64
 {
 	// drop the old table and journal, start again from the given keys
 	journal_free_all();
-	if (slots) { YAKB_CUDA(cudaFree(slots)); slots = nullptr; cap = 0; }
+	if (slots) { dev_free(slots); slots = nullptr; cap = 0; }
 	YAKB_CUDA(cudaMemsetAsync(last_put, 0, P * 8, stream));
 	YAKB_CUDA(cudaMemsetAsync(last_new, 0, P * 8, stream));
 	load_subtables(caps, off, keys);
@@ -1409,7 +1476,7 @@ void Engine::rebuild(const std::vector<uint32_t> &caps, const std::vector<uint64
 void Engine::rebuild_dev(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *d_keys)
 {
 	journal_free_all();
-	if (slots) { YAKB_CUDA(cudaFree(slots)); slots = nullptr; cap = 0; }
+	if (slots) { dev_free(slots); slots = nullptr; cap = 0; }
 	YAKB_CUDA(cudaMemsetAsync(last_put, 0, P * 8, stream));
 	YAKB_CUDA(cudaMemsetAsync(last_new, 0, P * 8, stream));
 	load_subtables(caps, off, d_keys, true);

@@ -187,10 +187,10 @@ __global__ void bf_insert_one_kernel(uint32_t *bits, int n_shift, int n_hashes, 
 int bf_insert_one(uint8_t *d_bits, int n_shift, int n_hashes, uint64_t hash)
 {
 	int *d = nullptr, h = 0;
-	YAKB_CUDA(cudaMalloc(&d, 4));
+	d = (int*)dev_alloc(4);
 	bf_insert_one_kernel<<<1, 1>>>((uint32_t*)d_bits, n_shift, n_hashes, hash, d);
 	YAKB_CUDA(cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost));
-	cudaFree(d);
+	dev_free(d);
 	return h;
 }
 

@@ -5,7 +5,11 @@
 #include <fcntl.h>
 #include <unistd.h>
 #include <sys/stat.h>
+#include <sys/mman.h>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <deque>
 #include <algorithm>
 
 namespace yakb {
@@ -143,6 +147,25 @@ static size_t guess_record_start(const unsigned char *p, size_t n, bool first_bl
 	return n;
 }
 
+// ---------------------------------------------------------------- the pool
+
+struct CopyTask { const uint8_t *src; uint8_t *dst; size_t len; BlockJob *slot; };
+
+struct ParallelFastx::Impl {
+	std::mutex mu;
+	std::condition_variable cv;          // one condition for everything: the events are rare (one per block)
+	std::vector<BlockJob> ring;
+	std::deque<CopyTask> copyq;
+	std::vector<std::thread> workers;
+	uint64_t next_parse = 0;             // next block a worker may take
+	int copies_open = 0;                 // copy tasks queued or running
+	int min_len = 0;
+	bool started = false, stop = false;
+};
+
+ParallelFastx::ParallelFastx() {}
+ParallelFastx::~ParallelFastx() { close(); }
+
 bool ParallelFastx::open(const char *fn, size_t block_bytes, int threads)
 {
 	close();
@@ -156,36 +179,111 @@ bool ParallelFastx::open(const char *fn, size_t block_bytes, int threads)
 		return false;
 	}
 	size_ = (uint64_t)sb.st_size;
-	block_ = block_bytes ? block_bytes : (8u << 20);
+	if (size_ > 0) {
+		void *m = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+		if (m == MAP_FAILED) { close(); return false; }
+		map_ = (const unsigned char*)m;
+		madvise(m, size_, MADV_SEQUENTIAL);
+	}
+	block_ = block_bytes ? block_bytes : (2u << 20);
+	nblocks_ = (size_ + block_ - 1) / block_;
 	if (threads <= 0) {
 		const char *e = getenv("YAKB_PARSE_THREADS");
-		threads = e && atoi(e) > 0 ? atoi(e) : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+		threads = e && atoi(e) > 0 ? atoi(e) : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
 	}
 	threads_ = threads;
-	next_off_ = 0; eof_ = size_ == 0; finished_ = false; n_redo_ = 0;
+	finished_ = false; n_redo_ = 0; true_blocks_ = 0;
 	true_ = FastxCore();
 	spill_.clear(); spill_pos_ = 0; spill_seq_ = 0;
+	im_ = new Impl;
+	im_->ring.resize((size_t)std::max(4 * threads_, 16));
 	return true;
 }
 
 void ParallelFastx::close()
 {
+	if (im_) {
+		{ std::lock_guard<std::mutex> lk(im_->mu); im_->stop = true; }
+		im_->cv.notify_all();
+		for (auto &th : im_->workers) th.join();
+		delete im_;
+		im_ = nullptr;
+	}
+	if (map_) munmap((void*)map_, size_);
+	map_ = nullptr;
 	if (fd_ >= 0) ::close(fd_);
 	fd_ = -1;
 }
 
+// One unit of pool work, lock held on entry and on exit; false if there was nothing to do.
+// Copies come first: they free ring slots, which is what parsing waits for.
+bool ParallelFastx::work_one(std::unique_lock<std::mutex> &lk, bool may_parse)
+{
+	Impl &im = *im_;
+	if (!im.copyq.empty()) {
+		CopyTask t = im.copyq.front(); im.copyq.pop_front();
+		lk.unlock();
+		memcpy(t.dst, t.src, t.len);
+		lk.lock();
+		t.slot->state = 0; --im.copies_open;
+		im.cv.notify_all();
+		return true;
+	}
+	if (may_parse && im.next_parse < nblocks_) {
+		BlockJob &j = im.ring[im.next_parse % im.ring.size()];
+		if (j.state == 0) {
+			const uint64_t b = im.next_parse++;
+			const int ml = im.min_len;
+			j.state = 1; j.blk = b;
+			lk.unlock();
+			const uint64_t off = b * (uint64_t)block_;
+			const unsigned char *raw = map_ + off;
+			j.n = (size_t)std::min<uint64_t>(block_, size_ - off);
+			j.q = guess_record_start(raw, j.n, off == 0);
+			j.spec = FastxCore();
+			j.out.clear();
+			j.nseq = 0; j.min_len = ml;
+			if (j.q < j.n) j.spec.feed(raw + j.q, j.n - j.q, ml, j.out, &j.nseq);
+			lk.lock();
+			j.state = 2;
+			im.cv.notify_all();
+			return true;
+		}
+	}
+	return false;
+}
+
 size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len, int64_t *n_seq, bool *done, size_t *need)
 {
+	Impl &im = *im_;
 	size_t n = 0;
 	*done = false;
 	if (need) *need = 0;
 	if (target > cap) target = cap;
+	const size_t W = im.ring.size();
+
+	if (!im.started) { // the record-length filter is known from here on: start the pool
+		std::lock_guard<std::mutex> lk(im.mu);
+		im.started = true; im.min_len = min_len;
+		for (int t = 0; t < threads_; ++t)
+			im.workers.emplace_back([this]() {
+				std::unique_lock<std::mutex> lk(im_->mu);
+				while (!im_->stop) if (!work_one(lk, true)) im_->cv.wait(lk);
+			});
+	} else if (im.min_len != min_len) { std::lock_guard<std::mutex> lk(im.mu); im.min_len = min_len; } // blocks parsed with the old value are redone below
+
 	// parsed bytes go straight to the caller's buffer while they fit, else to spill_
 	auto emit = [&](const uint8_t *p, size_t len, int64_t recs) {
 		if (len == 0) return;
 		if (spill_.empty() && n + len <= cap) { memcpy(dst + n, p, len); n += len; *n_seq += recs; }
 		else { spill_.insert(spill_.end(), p, p + len); spill_seq_ += recs; }
 	};
+	auto wait_copies = [&]() { // the caller may read dst only after every copy into it has landed
+		std::unique_lock<std::mutex> lk(im.mu);
+		while (im.copies_open > 0) if (!work_one(lk, false)) im.cv.wait(lk);
+	};
+	uint64_t consumed = true_blocks_;
+	std::vector<uint8_t> gap;
 	for (;;) {
 		// hand over what a previous call could not place, whole records only
 		if (spill_pos_ < spill_.size()) {
@@ -200,6 +298,7 @@ size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len,
 				const uint8_t *b = spill_.data() + spill_pos_;
 				const uint8_t *nl = (const uint8_t*)memchr(b, '\n', avail);
 				if (need) *need = (nl ? (size_t)(nl - b) : avail) + 1;
+				true_blocks_ = consumed;
 				return 0;
 			}
 			memcpy(dst + n, spill_.data() + spill_pos_, take);
@@ -210,77 +309,58 @@ size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len,
 				*n_seq += c; spill_seq_ -= c;
 			}
 			n += take; spill_pos_ += take;
-			if (spill_pos_ < spill_.size()) return n; // caller's buffer is full
+			if (spill_pos_ < spill_.size()) break; // caller's buffer is full
 			spill_.clear(); spill_pos_ = 0;
 		}
-		if (n >= target) return n;
-		if (finished_) { *done = true; return n; }
-		// one round: up to threads_ blocks parsed in parallel, stitched in order
-		const int nb = (int)std::min<uint64_t>((uint64_t)threads_, (size_ - next_off_ + block_ - 1) / block_);
-		if ((int)jobs_.size() < nb) jobs_.resize(nb);
-		std::vector<std::thread> pool;
-		const uint64_t base = next_off_;
-		for (int t = 0; t < nb; ++t) {
-			pool.emplace_back([&, t]() {
-				BlockJob &j = jobs_[t];
-				const uint64_t off = base + (uint64_t)t * block_;
-				const size_t len = (size_t)std::min<uint64_t>(block_, size_ - off);
-				if (!j.raw) j.raw.reset(new unsigned char[block_]);
-				size_t got = 0;
-				while (got < len) { ssize_t r = pread(fd_, j.raw.get() + got, len - got, off + got); if (r <= 0) break; got += r; }
-				j.n = got;
-				j.q = guess_record_start(j.raw.get(), j.n, off == 0);
-				j.spec = FastxCore();
-				j.out.clear();
-				j.nseq = 0;
-				if (j.q < j.n) j.spec.feed(j.raw.get() + j.q, j.n - j.q, min_len, j.out, &j.nseq);
-			});
-		}
-		for (auto &th : pool) th.join();
-		// stitch in order with the true state; big block outputs that fit the caller's buffer are
-		// copied there by the workers in parallel afterwards (the single stitching thread would
-		// otherwise spend most of the round in memcpy)
-		struct CopyTask { const uint8_t *src; size_t len, dst_off; };
-		std::vector<CopyTask> tasks;
-		std::vector<uint8_t> gap;
-		auto emit_big = [&](const uint8_t *p, size_t len, int64_t recs) {
-			if (len >= (1u << 16) && spill_.empty() && n + len <= cap) { tasks.push_back({p, len, n}); n += len; *n_seq += recs; }
-			else emit(p, len, recs);
-		};
-		for (int t = 0; t < nb; ++t) {
-			BlockJob &j = jobs_[t];
-			int64_t gs = 0;
-			gap.clear();
-			true_.feed(j.raw.get(), j.q, min_len, gap, &gs); // the gap, with the true state
-			if (j.q < j.n) {
-				true_.settle(min_len, gap, &gs);
-				if (true_.at_record_boundary()) { // the guess was a real record start: adopt the speculative result
-					if (true_.st == FastxCore::S_SEQ) close_carried(true_, true, min_len, gap, &gs);
-					emit(gap.data(), gap.size(), gs);
-					emit_big(j.out.data(), j.out.size(), j.nseq);
-					true_ = std::move(j.spec);
-				} else { // wrong guess: this block again, sequentially, from the true state
-					true_.feed(j.raw.get() + j.q, j.n - j.q, min_len, gap, &gs);
-					emit(gap.data(), gap.size(), gs);
-					++n_redo_;
-				}
-			} else emit(gap.data(), gap.size(), gs);
-		}
-		if (!tasks.empty()) {
-			std::vector<std::thread> cp;
-			for (size_t k = 1; k < tasks.size(); ++k) cp.emplace_back([&, k]() { memcpy(dst + tasks[k].dst_off, tasks[k].src, tasks[k].len); });
-			memcpy(dst + tasks[0].dst_off, tasks[0].src, tasks[0].len);
-			for (auto &th : cp) th.join();
-		}
-		next_off_ = base + (uint64_t)nb * block_;
-		if (next_off_ >= size_ || nb == 0) {
+		if (n >= target) break;
+		if (finished_) { *done = true; break; }
+		if (consumed == nblocks_) { // end of input: close the open record
 			int64_t gs = 0;
 			gap.clear();
 			true_.finish(min_len, gap, &gs);
 			emit(gap.data(), gap.size(), gs);
 			finished_ = true;
+			continue;
 		}
+		// the next block in file order, parsed by the pool (the caller helps while it waits)
+		BlockJob &j = im.ring[consumed % W];
+		{
+			std::unique_lock<std::mutex> lk(im.mu);
+			while (!(j.state == 2 && j.blk == consumed)) if (!work_one(lk, true)) im.cv.wait(lk);
+		}
+		const unsigned char *raw = map_ + consumed * (uint64_t)block_;
+		int64_t gs = 0;
+		bool queued = false;
+		gap.clear();
+		true_.feed(raw, j.q, min_len, gap, &gs); // the gap before the guess, with the true state
+		if (j.q < j.n) {
+			true_.settle(min_len, gap, &gs);
+			if (j.min_len == min_len && true_.at_record_boundary()) { // the guess was a real record start: adopt the speculative result
+				if (true_.st == FastxCore::S_SEQ) close_carried(true_, true, min_len, gap, &gs);
+				emit(gap.data(), gap.size(), gs);
+				true_ = std::move(j.spec); // before the slot can be handed back (a finished copy frees it)
+				if (j.out.size() >= (1u << 16) && spill_.empty() && n + j.out.size() <= cap) { // big: copied by the pool
+					std::lock_guard<std::mutex> lk(im.mu);
+					im.copyq.push_back({j.out.data(), dst + n, j.out.size(), &j});
+					++im.copies_open; j.state = 3; queued = true;
+					n += j.out.size(); *n_seq += j.nseq;
+				} else emit(j.out.data(), j.out.size(), j.nseq);
+			} else { // wrong guess: this block again, sequentially, from the true state
+				true_.feed(raw + j.q, j.n - j.q, min_len, gap, &gs);
+				emit(gap.data(), gap.size(), gs);
+				++n_redo_;
+			}
+		} else emit(gap.data(), gap.size(), gs);
+		{
+			std::lock_guard<std::mutex> lk(im.mu);
+			if (!queued) j.state = 0;
+		}
+		im.cv.notify_all();
+		++consumed;
 	}
+	true_blocks_ = consumed;
+	wait_copies();
+	return n;
 }
 
 } // namespace yakb

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include <memory>
+#include <mutex>
 
 namespace yakb {
 
@@ -32,35 +33,46 @@ struct FastxCore {
 };
 
 struct BlockJob {
-	std::unique_ptr<unsigned char[]> raw;
+	uint64_t blk = ~0ull;         // block number this slot holds
+	int state = 0;                // 0 free, 1 being parsed, 2 parsed, 3 stitched, its output still being copied out
+	int min_len = 0;              // the record-length filter it was parsed with
 	size_t n = 0, q = 0;
 	FastxCore spec;               // state after the speculative parse
 	std::vector<uint8_t> out;     // its output
 	int64_t nseq = 0;
 };
 
+// Streaming design: the file is memory-mapped; a pool of workers parses blocks ahead of the consumer
+// (a ring of slots bounds the distance) for the whole life of the reader, and also carries out the big
+// copies into the caller's buffer.  fill() is the in-order stitcher.
 class ParallelFastx {
 public:
-	~ParallelFastx() { close(); }
+	ParallelFastx();
+	~ParallelFastx();
+	ParallelFastx(const ParallelFastx&) = delete;
+	ParallelFastx &operator=(const ParallelFastx&) = delete;
 	// false if the file cannot be opened or is not a plain regular file (gzip, stdin): use FastxReader
-	bool open(const char *fn, size_t block_bytes = 8u << 20, int threads = 0);
+	bool open(const char *fn, size_t block_bytes = 0, int threads = 0);
 	void close();
 	// same contract as FastxReader::fill
 	size_t fill(uint8_t *dst, size_t cap, size_t target, int min_len, int64_t *n_seq, bool *done, size_t *need);
 	uint64_t mis_speculations() const { return n_redo_; }
 
 private:
+	struct Impl;
+	bool work_one(std::unique_lock<std::mutex> &lk, bool may_parse);
+	Impl *im_ = nullptr;
 	int fd_ = -1;
-	uint64_t size_ = 0, next_off_ = 0;
+	const unsigned char *map_ = nullptr;
+	uint64_t size_ = 0, nblocks_ = 0, true_blocks_ = 0; // true_blocks_: blocks stitched so far
 	size_t block_ = 0;
 	int threads_ = 1;
 	FastxCore true_;                 // exact parser state at the end of the last stitched block
 	std::vector<uint8_t> spill_;     // parsed output that did not fit the caller's buffer yet
 	size_t spill_pos_ = 0;
 	int64_t spill_seq_ = 0;          // records inside spill_ not yet reported
-	bool eof_ = false, finished_ = false;
+	bool finished_ = false;
 	uint64_t n_redo_ = 0;
-	std::vector<BlockJob> jobs_;     // reused every round
 };
 
 } // namespace yakb
