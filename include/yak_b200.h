@@ -54,6 +54,12 @@ int yakb_ch_get_batch_dev(const yak_ch_t *h, uint64_t n, const uint64_t *d_x, in
 int yakb_qv_seqs(const yak_ch_t *h, int64_t n_seq, const int64_t *lens, const char *cat,
                  int min_len, double min_frac, int64_t cnt[YAK_N_COUNTS], int32_t *tot, int32_t *non0);
 
+/* The lookup loop shared by the reference's other scanners (triobin.c:62-86, trioeval.c:61-89,
+ * chkerr.c:35-56, sexchr.c:42-66; any k < 64) as one batched device call over sequences in host memory
+ * (`cat` back to back, lens[i] each): out[j] for the k-mer ENDING at base j of `cat` = yak_ch_get's
+ * value (-1 absent), or -2 where no k-mer ends.  yak_b200/cli/scan_logic.c does the per-sequence part. */
+int yakb_scan_seqs(const yak_ch_t *h, int64_t n_seq, const int64_t *lens, const char *cat, int16_t *out);
+
 /* serialise exactly the bytes yak_ch_dump writes into a malloc'd buffer; returns the length */
 int64_t yakb_ch_dump_mem(const yak_ch_t *h, uint8_t **out);
 /* make room for this many distinct keys per sub-table up front (optional) */

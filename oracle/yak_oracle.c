@@ -492,6 +492,82 @@ yo_ch_t *yo_ch_restore(const char *fn)
 	return h;
 }
 
+/* htab.c:396-476 with the variadic (min_cnt, mid_cnt) made explicit.  mode: 1 ALL, 2/3 TRIOBIN1/2
+ * (count -> 2-bit class, second file in bits 2-3), 4/5/6 SEXCHR1/2/3 (membership bits 0/1/2).
+ * n_io (may be NULL) receives {#put calls, #new keys} as printed at htab.c:474. */
+yo_ch_t *yo_ch_restore_core(yo_ch_t *ch0, const char *fn, int mode, int min_cnt, int mid_cnt, int64_t n_io[2])
+{
+	FILE *fp;
+	char magic[4];
+	uint32_t t[3], j;
+	int w, absent;
+	const uint64_t mask = YO_MAX_COUNT;
+	int64_t n_ins = 0, n_new = 0;
+	yo_ch_t *h;
+	if (mode < 1 || mode > 6) return 0;                                        /* htab.c:419 */
+	if (ch0 == 0 && (mode == 3 || mode == 5 || mode == 6)) return 0;          /* htab.c:412-418 */
+	if ((fp = fopen(fn, "rb")) == 0) return 0;
+	if (fread(magic, 1, 4, fp) != 4) { fclose(fp); return 0; }
+	if (memcmp(magic, "YAK\2", 4) != 0) { fprintf(stderr, "ERROR: wrong file magic.\n"); fclose(fp); return 0; }
+	if (fread(t, 4, 3, fp) != 3 || t[2] != YO_COUNTER_BITS) { fclose(fp); return 0; }
+	h = ch0 ? ch0 : yo_ch_init(t[0], t[1], 0, 0);
+	for (w = 0; w < 1 << h->pre; ++w) {
+		if (fread(t, 4, 2, fp) != 2) break;
+		yo_set_resize(&h->h[w], t[0]);                                         /* htab.c:438 */
+		for (j = 0; j < t[1]; ++j) {
+			uint64_t key;
+			uint32_t it;
+			if (fread(&key, 8, 1, fp) != 1) break;
+			if (mode == 1) {
+				++n_ins;
+				yo_set_put(&h->h[w], key, &absent);
+				if (absent) ++n_new;
+			} else {
+				int x;
+				if (mode == 2 || mode == 3) {                                  /* htab.c:448-452 */
+					const int cnt = key & mask, shift = mode == 2 ? 0 : 2;
+					x = cnt >= mid_cnt ? 2 << shift : cnt >= min_cnt ? 1 << shift : -1;
+				} else x = 1 << (mode - 4);                                    /* htab.c:462 */
+				if (x < 0) continue;
+				key = (key & ~mask) | x;
+				++n_ins;
+				it = yo_set_put(&h->h[w], key, &absent);
+				if (absent) ++n_new;
+				else h->h[w].keys[it] |= x;                                    /* htab.c:459, 468 */
+			}
+		}
+	}
+	fclose(fp);
+	if (n_io) n_io[0] = n_ins, n_io[1] = n_new;
+	return h;
+}
+
+/* the loop every scanner shares (triobin.c:62-86, trioeval.c:61-89, chkerr.c:35-56, sexchr.c:42-66):
+ * out[i] = yak_ch_get of the k-mer ending at base i (-1 absent), or -2 where no k-mer ends */
+void yo_scan_seq(const yo_ch_t *ch, int64_t len, const char *seq, int16_t *out)
+{
+	const int k = ch->k;
+	int64_t i;
+	int l = 0;
+	uint64_t x[4] = {0, 0, 0, 0}, mask = k < 32 ? (1ULL << 2 * k) - 1 : (1ULL << k) - 1;
+	const int shift = k < 32 ? 2 * (k - 1) : k - 1;
+	for (i = 0; i < len; ++i) {
+		int c = yo_nt4[(uint8_t)seq[i]];
+		out[i] = -2;
+		if (c >= 4) { l = 0, x[0] = x[1] = x[2] = x[3] = 0; continue; }
+		if (k < 32) {
+			x[0] = (x[0] << 2 | c) & mask;
+			x[1] = x[1] >> 2 | (uint64_t)(3 - c) << shift;
+		} else {
+			x[0] = (x[0] << 1 | (c & 1)) & mask;
+			x[1] = (x[1] << 1 | (c >> 1)) & mask;
+			x[2] = x[2] >> 1 | (uint64_t)(1 - (c & 1)) << shift;
+			x[3] = x[3] >> 1 | (uint64_t)(1 - (c >> 1)) << shift;
+		}
+		if (++l >= k) out[i] = (int16_t)yo_ch_get(ch, k < 32 ? yo_hash64(x[0] < x[1] ? x[0] : x[1], mask) : yo_hash_long(x));
+	}
+}
+
 /* ------------------------------------------------------------------ event stream */
 
 /* count.c:28-43 (k < 32) and count.c:45-60 (32 <= k < 64) */

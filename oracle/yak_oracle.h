@@ -79,6 +79,10 @@ void yo_ch_subtract(yo_ch_t *h0, const yo_ch_t *h1);
 void yo_ch_isec(yo_ch_t *h0, const yo_ch_t *h1);
 int  yo_ch_dump(const yo_ch_t *h, const char *fn);
 yo_ch_t *yo_ch_restore(const char *fn);
+/* htab.c:396-476: load into ch0 (or a new table) with the count -> flag remapping of `mode` */
+yo_ch_t *yo_ch_restore_core(yo_ch_t *ch0, const char *fn, int mode, int min_cnt, int mid_cnt, int64_t n_io[2]);
+/* per-position lookups of one sequence, the loop shared by triobin/trioeval/chkerr/sexchr */
+void yo_scan_seq(const yo_ch_t *ch, int64_t len, const char *seq, int16_t *out);
 /* serialise into a malloc'd buffer (same bytes as yo_ch_dump); returns length */
 int64_t yo_ch_dump_mem(const yo_ch_t *h, uint8_t **out);
 

@@ -1,0 +1,187 @@
+"""CPU checks of the scanner path against the UNMODIFIED reference's stdout
+(tests/golden/scan_*.txt): the oracle's restatements of yak_ch_restore_core's flag modes and of the shared lookup
+loop feed yak_b200/cli/scan_logic.c - the per-sequence logic the CLI runs behind the batched device lookup - and
+the text must equal the reference's byte for byte.  The GPU side of the same cases is tests/test_gpu_scan.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib
+import scan_inputs as S
+import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+CHUNK = {"triobin": 200_000_000, "trioeval": 1_000_000_000, "chkerr": 1_000_000_000, "sexchr": 1_000_000_000}
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_seq", C.c_int64), ("names", C.POINTER(C.c_char_p)), ("lens", C.POINTER(C.c_int64)), ("vals", C.POINTER(C.c_int16))]
+
+
+class TbOpt(C.Structure):
+    _fields_ = [("k", C.c_int), ("print_diff", C.c_int), ("ratio_thres", C.c_double)]
+
+
+class TeOpt(C.Structure):
+    _fields_ = [("k", C.c_int), ("min_n", C.c_int), ("print_err", C.c_int), ("print_frag", C.c_int)]
+
+
+class TeSum(C.Structure):
+    _fields_ = [("v", C.c_int64 * 6)]
+
+
+class CeOpt(C.Structure):
+    _fields_ = [("k", C.c_int), ("min_cnt", C.c_int), ("min_streak", C.c_int)]
+
+
+@pytest.fixture(scope="module")
+def env():
+    oracle_lib.build()
+    so = os.path.join(util.TMP, "yakb_scan_logic_test.so")
+    subprocess.run(["gcc", "-O2", "-Wall", "-fPIC", "-shared", "-o", so, os.path.join(ROOT, "yak_b200", "cli", "scan_logic.c")], check=True)
+    logic = C.CDLL(so)
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p; libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    for f in ("yakb_triobin_batch", "yakb_chkerr_batch"):
+        getattr(logic, f).argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Batch)]
+    logic.yakb_trioeval_batch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Batch), C.POINTER(TeSum)]
+    logic.yakb_trioeval_header.argtypes = [C.c_void_p]
+    logic.yakb_trioeval_footer.argtypes = [C.c_void_p, C.POINTER(TeSum)]
+    logic.yakb_sexchr_header.argtypes = [C.c_void_p]
+    logic.yakb_sexchr_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Batch)]
+    O = oracle_lib.lib()
+    O.yo_ch_restore_core.restype = C.POINTER(oracle_lib.YoCh)
+    O.yo_ch_restore_core.argtypes = [C.POINTER(oracle_lib.YoCh), C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+    O.yo_scan_seq.argtypes = [C.POINTER(oracle_lib.YoCh), C.c_int64, C.c_char_p, C.POINTER(C.c_int16)]
+    O.yo_reader_open.restype = C.c_void_p; O.yo_reader_open.argtypes = [C.c_char_p]
+    O.yo_reader_next.restype = C.c_int64; O.yo_reader_next.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
+    O.yo_reader_close.argtypes = [C.c_void_p]
+    paths = S.write_all(util.TMP)
+    for y, (fa, k) in S.COUNTS.items():   # the oracle's count is byte-exact against the reference (test_oracle_cpu.py)
+        paths[y] = os.path.join(util.TMP, "yakb_scan_" + y)
+        h, _ = oracle_lib.count_file(paths[fa], k=k, pre=10, bf_shift=0)
+        assert O.yo_ch_dump(h, paths[y].encode()) == 0
+        O.yo_ch_destroy(h)
+    return logic, libc, O, paths
+
+
+def batches(O, fn, chunk):
+    """bseq.c:33-57: records until the batch holds >= chunk bases"""
+    r = O.yo_reader_open(fn.encode())
+    assert r
+    names, seqs, size = [], [], 0
+    seq, name = C.c_char_p(), C.c_char_p()
+    while True:
+        ln = O.yo_reader_next(r, C.byref(seq), C.byref(name))
+        if ln >= 0:
+            names.append(name.value)
+            seqs.append(C.string_at(seq, ln))
+            size += ln
+        if ln < 0 or size >= chunk:
+            if names:
+                yield names, seqs
+            names, seqs, size = [], [], 0
+            if ln < 0:
+                break
+    O.yo_reader_close(r)
+
+
+def make_batch(O, ch, names, seqs):
+    lens = (C.c_int64 * len(seqs))(*[len(s) for s in seqs])
+    tot = sum(len(s) for s in seqs)
+    vals = (C.c_int16 * max(tot, 1))()
+    off = 0
+    for s in seqs:
+        O.yo_scan_seq(ch, len(s), s, C.cast(C.byref(vals, off * 2), C.POINTER(C.c_int16)))
+        off += len(s)
+    nm = (C.c_char_p * len(names))(*names)
+    b = Batch(len(seqs), nm, lens, vals)
+    b._keep = (nm, lens, vals)
+    return b
+
+
+def getopt(args, spec):
+    """tiny getopt for the -xVALUE / -x forms the cases use; returns (dict, positional)"""
+    o, pos = {}, []
+    for a in args:
+        if a.startswith("-") and len(a) > 1:
+            o[a[1]] = a[2:] if spec[a[1]] else True
+        else:
+            pos.append(a)
+    return o, pos
+
+
+def parse_num(s):
+    mul = {"k": 1e3, "m": 1e6, "g": 1e9}.get(s[-1].lower())
+    return int(float(s[:-1]) * mul + .499) if mul else int(float(s) + .499)
+
+
+def run_case(env, cmd):
+    logic, libc, O, paths = env
+    name, args = cmd[0], S.argv(cmd[1:], paths)
+    out_path = os.path.join(util.TMP, "yakb_scan_out.txt")
+    fp = libc.fopen(out_path.encode(), b"w")
+    if name in ("triobin", "trioeval"):
+        o, pos = getopt(args, {"c": 1, "d": 1, "t": 1, "p": 0, "r": 1, "n": 1, "e": 0, "F": 0})
+        mn, md = int(o.get("c", 2)), int(o.get("d", 5))
+        ch = O.yo_ch_restore_core(None, pos[0].encode(), 2, mn, md, None)
+        assert ch and O.yo_ch_restore_core(ch, pos[1].encode(), 3, mn, md, None)
+        if name == "triobin":
+            opt = TbOpt(ch.contents.k, 1 if "p" in o else 0, float(o.get("r", 0.33)))
+            for names, seqs in batches(O, pos[2], CHUNK[name]):
+                logic.yakb_triobin_batch(fp, C.byref(opt), C.byref(make_batch(O, ch, names, seqs)))
+        else:
+            opt = TeOpt(ch.contents.k, int(o.get("n", 2)), 1 if "e" in o else 0, 0 if "F" in o else 1)
+            sm = TeSum()
+            logic.yakb_trioeval_header(fp)
+            for names, seqs in batches(O, pos[2], CHUNK[name]):
+                logic.yakb_trioeval_batch(fp, C.byref(opt), C.byref(make_batch(O, ch, names, seqs)), C.byref(sm))
+            logic.yakb_trioeval_footer(fp, C.byref(sm))
+    elif name == "chkerr":
+        o, pos = getopt(args, {"t": 1, "c": 1, "s": 1})
+        ch = O.yo_ch_restore_core(None, pos[0].encode(), 1, 0, 0, None)
+        opt = CeOpt(ch.contents.k, int(o.get("c", 3)), int(o.get("s", 5)))
+        for names, seqs in batches(O, pos[1], CHUNK[name]):
+            logic.yakb_chkerr_batch(fp, C.byref(opt), C.byref(make_batch(O, ch, names, seqs)))
+    else:
+        o, pos = getopt(args, {"t": 1, "K": 1})
+        ch = O.yo_ch_restore_core(None, pos[0].encode(), 4, 0, 0, None)
+        assert ch and O.yo_ch_restore_core(ch, pos[1].encode(), 5, 0, 0, None) and O.yo_ch_restore_core(ch, pos[2].encode(), 6, 0, 0, None)
+        logic.yakb_sexchr_header(fp)
+        for hap in (1, 2):
+            for names, seqs in batches(O, pos[2 + hap], parse_num(o["K"]) if "K" in o else CHUNK[name]):
+                logic.yakb_sexchr_batch(fp, hap, C.byref(make_batch(O, ch, names, seqs)))
+    libc.fclose(fp)
+    O.yo_ch_destroy(ch)
+    return open(out_path, "rb").read()
+
+
+@pytest.mark.parametrize("gold,cmd", S.CASES, ids=[c[0] for c in S.CASES])
+def test_scan_logic_on_oracle_lookups_equals_reference_stdout(env, gold, cmd):
+    got = run_case(env, cmd)
+    want = open(os.path.join(GOLD, gold), "rb").read()
+    assert got == want
+
+
+def test_restore_core_modes_of_the_oracle(env):
+    """flag bits after TRIOBIN1+2 and SEXCHR1+2+3 loads (htab.c:448-470) and the mode errors (htab.c:412-419)"""
+    _, _, O, paths = env
+    n_io = (C.c_int64 * 2)()
+    assert not O.yo_ch_restore_core(None, paths["pat.yak"].encode(), 3, 2, 5, None)   # TRIOBIN2 needs a table
+    assert not O.yo_ch_restore_core(None, paths["pat.yak"].encode(), 5, 0, 0, None)
+    assert not O.yo_ch_restore_core(None, paths["pat.yak"].encode(), 7, 0, 0, None)
+    ch = O.yo_ch_restore_core(None, paths["pat.yak"].encode(), 2, 2, 5, n_io)
+    first = n_io[1]
+    assert first == n_io[0] > 0
+    assert O.yo_ch_restore_core(ch, paths["mat.yak"].encode(), 3, 2, 5, n_io)
+    assert 0 < n_io[1] < n_io[0]                       # most maternal k-mers are shared with the father
+    hist = (C.c_int64 * 1024)()
+    O.yo_ch_hist(ch, hist)
+    assert sum(hist) == first + n_io[1] and all(hist[i] == 0 for i in range(16, 1024)) and hist[0] == 0
+    assert hist[2] > 0 and hist[8] > 0 and hist[10] > hist[2]   # specific to one parent / class 2 in both
+    O.yo_ch_destroy(ch)

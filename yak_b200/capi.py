@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
         "yakb_ch_get_batch_dev": (C.c_int, [ChP, u64, vp, vp]),
         "yakb_qv_seqs": (C.c_int, [ChP, i64, C.POINTER(i64), C.c_char_p, C.c_int, C.c_double, C.POINTER(i64),
                                    C.POINTER(i32), C.POINTER(i32)]),
+        "yakb_scan_seqs": (C.c_int, [ChP, i64, C.POINTER(i64), C.c_char_p, C.POINTER(C.c_int16)]),
         "yakb_ch_dump_mem": (i64, [ChP, C.POINTER(vp)]),
         "yakb_ch_init_shard": (ChP, [C.c_int] * 6),
         "yakb_ch_dump_shard_mem": (i64, [ChP, C.c_int, C.POINTER(vp)]),

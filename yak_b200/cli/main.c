@@ -12,6 +12,11 @@
 #include "yak.h"
 
 int yak_qv_solve(const int64_t *hist, const int64_t *cnt, int kmer, double fpr, yak_qstat_t *qs); /* qv_solve.c */
+int yakb_cmd_triobin(int argc, char *argv[]);  /* scan.c */
+int yakb_cmd_trioeval(int argc, char *argv[]);
+int yakb_cmd_chkerr(int argc, char *argv[]);
+int yakb_cmd_sexchr(int argc, char *argv[]);
+int64_t yakb_cli_parse_num(const char *s);
 
 static double t_real0;
 static double realtime(void) { struct timeval tv; gettimeofday(&tv, 0); return tv.tv_sec + tv.tv_usec * 1e-6; }
@@ -19,7 +24,7 @@ static double cputime(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); retur
 static long peakrss(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return r.ru_maxrss * 1024; }
 
 /* "10k" / "1.5g" style numbers (reference yak-priv.h:75-84) */
-static int64_t parse_num(const char *s)
+int64_t yakb_cli_parse_num(const char *s)
 {
 	char *p;
 	double x = strtod(s, &p);
@@ -39,10 +44,10 @@ static int cmd_count(int argc, char *argv[])
 	while ((c = getopt(argc, argv, "k:p:K:t:b:H:o:")) >= 0) {
 		if (c == 'k') opt.k = atoi(optarg);
 		else if (c == 'p') opt.pre = atoi(optarg);
-		else if (c == 'K') opt.chunk_size = parse_num(optarg);
+		else if (c == 'K') opt.chunk_size = yakb_cli_parse_num(optarg);
 		else if (c == 't') opt.n_thread = atoi(optarg);
 		else if (c == 'b') opt.bf_shift = atoi(optarg);
-		else if (c == 'H') opt.bf_n_hash = (int)parse_num(optarg);
+		else if (c == 'H') opt.bf_n_hash = (int)yakb_cli_parse_num(optarg);
 		else if (c == 'o') fn_out = optarg;
 	}
 	if (argc - optind < 1) {
@@ -84,8 +89,8 @@ static int cmd_qv(int argc, char *argv[])
 	int c, i, kmer;
 	yak_qopt_init(&opt);
 	while ((c = getopt(argc, argv, "K:t:l:f:pe:E")) >= 0) {
-		if (c == 'K') opt.chunk_size = parse_num(optarg);
-		else if (c == 'l') opt.min_len = (int)parse_num(optarg);
+		if (c == 'K') opt.chunk_size = yakb_cli_parse_num(optarg);
+		else if (c == 'l') opt.min_len = (int)yakb_cli_parse_num(optarg);
 		else if (c == 'f') opt.min_frac = atof(optarg);
 		else if (c == 't') opt.n_threads = atoi(optarg);
 		else if (c == 'p') opt.print_each = 1;
@@ -240,6 +245,10 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "  isec      intersect k-mer sets\n");
 		fprintf(stderr, "  print     print k-mers for k<=31\n");
 		fprintf(stderr, "  qv        evaluate quality values\n");
+		fprintf(stderr, "  triobin   trio binning\n");
+		fprintf(stderr, "  trioeval  evaluate phasing accuracy with trio\n");
+		fprintf(stderr, "  chkerr    find streaks of low-count k-mers\n");
+		fprintf(stderr, "  sexchr    sex-chromosome k-mer content of two haplotype assemblies\n");
 		fprintf(stderr, "  inspect   k-mer hash tables\n");
 		fprintf(stderr, "  version   print version number\n");
 		return 1;
@@ -250,6 +259,10 @@ int main(int argc, char *argv[])
 	else if (strcmp(argv[1], "isec") == 0) ret = cmd_setop(argc - 1, argv + 1, 1);
 	else if (strcmp(argv[1], "print") == 0) ret = cmd_print(argc - 1, argv + 1);
 	else if (strcmp(argv[1], "qv") == 0) ret = cmd_qv(argc - 1, argv + 1);
+	else if (strcmp(argv[1], "triobin") == 0) ret = yakb_cmd_triobin(argc - 1, argv + 1);
+	else if (strcmp(argv[1], "trioeval") == 0) ret = yakb_cmd_trioeval(argc - 1, argv + 1);
+	else if (strcmp(argv[1], "chkerr") == 0) ret = yakb_cmd_chkerr(argc - 1, argv + 1);
+	else if (strcmp(argv[1], "sexchr") == 0) ret = yakb_cmd_sexchr(argc - 1, argv + 1);
 	else if (strcmp(argv[1], "inspect") == 0) ret = cmd_inspect(argc - 1, argv + 1);
 	else if (strcmp(argv[1], "version") == 0) { puts(YAKS_VERSION); return 0; }
 	else { fprintf(stderr, "[E::%s] unknown command\n", __func__); return 1; }

@@ -272,12 +272,6 @@ extern "C" yak_knt_t *yak_ch_getseq(const yak_ch_t *h, int w, uint32_t *n) // ht
 	GUARD_END(0)
 }
 
-static void unsupported(const char *fn)
-{
-	fprintf(stderr, "[yakb] ERROR: %s is not implemented by the B200 library yet (SURVEY 8(f))\n", fn);
-	abort();
-}
-
 // htab.c:102-110: per sub-table `if (size*3 < capacity) resize(size*3)`; the condition needs the khashl
 // capacity, so it is recorded as an operation and evaluated when the layout is replayed
 extern "C" void yak_ch_tighten(yak_ch_t *h)
@@ -465,10 +459,21 @@ extern "C" int64_t yakb_ch_dump_shard_mem(const yak_ch_t *h, int with_header, ui
 extern "C" yak_ch_t *yak_ch_restore_core(yak_ch_t *ch0, const char *fn, int mode, ...) // htab.c:396-476
 {
 	GUARD_BEGIN
-	if (mode != YAK_LOAD_ALL) {
-		if (mode < YAK_LOAD_ALL || mode > YAK_LOAD_SEXCHR3) return 0;
-		unsupported("yak_ch_restore_core(mode != YAK_LOAD_ALL)");
+	int min_cnt = 0, mid_cnt = 0, mode_err = 0;
+	{
+		va_list ap;
+		va_start(ap, mode);
+		if (mode == YAK_LOAD_ALL) {
+		} else if (mode == YAK_LOAD_TRIOBIN1 || mode == YAK_LOAD_TRIOBIN2) {
+			min_cnt = va_arg(ap, int);
+			mid_cnt = va_arg(ap, int);
+			if (ch0 == 0 && mode == YAK_LOAD_TRIOBIN2) mode_err = 1;
+		} else if (mode == YAK_LOAD_SEXCHR1 || mode == YAK_LOAD_SEXCHR2 || mode == YAK_LOAD_SEXCHR3) {
+			if (ch0 == 0 && mode != YAK_LOAD_SEXCHR1) mode_err = 1;
+		} else mode_err = 1;
+		va_end(ap);
 	}
+	if (mode_err) return 0;
 	FILE *fp;
 	char magic[4];
 	uint32_t t[3];
@@ -481,27 +486,42 @@ extern "C" yak_ch_t *yak_ch_restore_core(yak_ch_t *ch0, const char *fn, int mode
 		fclose(fp);
 		return 0;
 	}
-	if (ch0) unsupported("yak_ch_restore_core(ch0 != NULL)");
-	yak_ch_t *ch = yak_ch_init(t[0], t[1], 0, 0);
+	yak_ch_t *ch = ch0 ? ch0 : yak_ch_init(t[0], t[1], 0, 0);
 	if (!ch) { fclose(fp); return 0; }
+	assert((int)t[0] == ch->k && (int)t[1] == ch->pre); // htab.c:437
 	ChBox *b = box_of(ch);
+	std::lock_guard<std::mutex> lk(b->mu);
 	const int P = 1 << ch->pre;
+	const uint64_t cmask = YAK_MAX_COUNT;
 	std::vector<uint32_t> caps(P, 0);
 	std::vector<uint64_t> off(P + 1, 0), keys;
+	std::vector<uint64_t> buf;
 	for (int s = 0; s < P; ++s) {
 		uint32_t u[2] = {0, 0};
 		if (fread(u, 4, 2, fp) != 2) u[0] = u[1] = 0;
 		caps[s] = u[0];
-		const size_t base = keys.size();
-		keys.resize(base + u[1]);
-		size_t got = u[1] ? fread(keys.data() + base, 8, u[1], fp) : 0;
-		keys.resize(base + got);
+		buf.resize(u[1]);
+		const size_t got = u[1] ? fread(buf.data(), 8, u[1], fp) : 0;
+		for (size_t j = 0; j < got; ++j) {
+			uint64_t key = buf[j];
+			if (mode == YAK_LOAD_TRIOBIN1 || mode == YAK_LOAD_TRIOBIN2) { // htab.c:448-460: count -> class bits
+				const int cnt = (int)(key & cmask), shift = mode == YAK_LOAD_TRIOBIN1 ? 0 : 2;
+				if (cnt >= mid_cnt) key = (key & ~cmask) | (uint64_t)(2 << shift);
+				else if (cnt >= min_cnt) key = (key & ~cmask) | (uint64_t)(1 << shift);
+				else continue;
+			} else if (mode != YAK_LOAD_ALL) key = (key & ~cmask) | (uint64_t)(1 << (mode - YAK_LOAD_SEXCHR1)); // htab.c:461-469
+			keys.push_back(key);
+		}
 		off[s + 1] = keys.size();
 	}
 	fclose(fp);
-	b->eng->load_subtables(caps, off, keys.data());
-	ch->tot = 0; // the reference leaves tot untouched on restore (htab.c:441)
-	fprintf(stderr, "[M::%s] inserted %ld k-mers, of which %ld are new\n", __func__, (long)keys.size(), (long)keys.size());
+	uint64_t n_new = keys.size();
+	const bool engine_sharded = b->eng->P != P; // shards hold part of the sub-tables: not a restore target
+	if (engine_sharded) throw CudaError("yak_ch_restore_core on a shard of a multi-GPU table");
+	if (ch0 == 0 && mode == YAK_LOAD_ALL) b->eng->load_subtables(caps, off, keys.data());
+	else n_new = b->eng->upsert(caps, off, keys.data(), mode != YAK_LOAD_ALL);
+	if (ch0 == 0) ch->tot = 0; // the reference leaves tot untouched on restore (htab.c:441)
+	fprintf(stderr, "[M::%s] inserted %ld k-mers, of which %ld are new\n", __func__, (long)keys.size(), (long)n_new);
 	return ch;
 	GUARD_END(0)
 }
@@ -870,6 +890,43 @@ extern "C" int yakb_qv_seqs(const yak_ch_t *h, int64_t n_seq, const int64_t *len
 	}
 	YAKB_CUDA(cudaMemcpyAsync(cnt, d_hist, 1024 * 8, cudaMemcpyDeviceToHost, b->eng->stream));
 	YAKB_CUDA(cudaStreamSynchronize(b->eng->stream));
+	return 0;
+	GUARD_END(-1)
+}
+
+// the lookups of the other scanners (triobin.c:62-86, trioeval.c:61-89, chkerr.c:35-56, sexchr.c:42-66), batched
+extern "C" int yakb_scan_seqs(const yak_ch_t *h, int64_t n_seq, const int64_t *lens, const char *cat, int16_t *out)
+{
+	GUARD_BEGIN
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	Engine *e = b->eng;
+	const uint64_t cap = batch_bases(0);
+	int64_t s = 0, src = 0;
+	std::vector<uint8_t> buf;
+	std::vector<int16_t> back;
+	while (s < n_seq) {
+		buf.clear();
+		const int64_t s_first = s, src_first = src;
+		while (s < n_seq && (buf.empty() || buf.size() + lens[s] + 1 <= cap)) {
+			buf.insert(buf.end(), cat + src, cat + src + lens[s]);
+			buf.push_back('\n'); // a separator byte: no k-mer spans two sequences
+			src += lens[s]; ++s;
+		}
+		const uint64_t n = buf.size();
+		uint8_t *d = b->d_in.as<uint8_t>(n + 64);
+		int16_t *d_cnt = (int16_t*)b->d_aux.need(n * 2 + 16);
+		YAKB_CUDA(cudaMemcpyAsync(d, buf.data(), n, cudaMemcpyHostToDevice, e->stream));
+		qv_scan_ascii(e, d, n, d_cnt, 1);
+		back.resize(n);
+		YAKB_CUDA(cudaMemcpyAsync(back.data(), d_cnt, n * 2, cudaMemcpyDeviceToHost, e->stream));
+		YAKB_CUDA(cudaStreamSynchronize(e->stream));
+		int64_t o = src_first, p = 0;
+		for (int64_t i = s_first; i < s; ++i) { // drop the separators again
+			memcpy(out + o, back.data() + p, (size_t)lens[i] * 2);
+			o += lens[i]; p += lens[i] + 1;
+		}
+	}
 	return 0;
 	GUARD_END(-1)
 }

@@ -612,18 +612,20 @@ __global__ void get_batch_kernel(const uint64_t *__restrict__ xs, uint64_t n, in
 }
 
 // qv.c:48-66: per position the count of its k-mer (absent -> 0), or -1 where no k-mer ends
+// raw = 1 (the other scanners: triobin.c:76, trioeval.c:75, chkerr.c:55, sexchr.c:61): yak_ch_get's own value,
+// -1 for an absent k-mer, and -2 where no k-mer ends
 template<bool LONGK>
 __global__ void __launch_bounds__(256) qv_scan_kernel(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords, uint64_t n,
                                                       int k, int pre, uint32_t Pmask, Own own, const uint64_t *__restrict__ slots, uint32_t cap,
-                                                      int16_t *__restrict__ out)
+                                                      int16_t *__restrict__ out, int raw)
 {
 	const uint64_t W = blockIdx.x * 256ull + threadIdx.x;
 	if (W >= nwords) return;
 	int16_t res[32];
 #pragma unroll
-	for (int r = 0; r < 32; ++r) res[r] = -1;
+	for (int r = 0; r < 32; ++r) res[r] = raw ? -2 : -1;
 	roll_word<LONGK>(w2, wm, W, k, [&](int r, uint64_t v) {
-		int16_t c = 0;
+		int16_t c = raw ? -1 : 0;
 		if (cap && ((uint32_t)(v >> own.shift) & own.mask) == own.rank) {
 			const uint64_t *reg = slots + (uint64_t)((uint32_t)v & Pmask) * cap;
 			int64_t q = tab_find(reg, cap, v >> pre);
@@ -1189,6 +1191,90 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 	return st;
 }
 
+// ---- restore into an existing table (htab.c:436-472): key i (stored form, its low bits are the bits to
+//      set) is put into its sub-table; an existing key gets the bits OR-ed in when `or_bits`, else stays as
+//      it is.  isnew[i] = the put inserted the key; newcnt[s] / lnew[s] = new keys / last new position (+1).
+__global__ void upsert_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ off, uint32_t P, uint64_t n,
+                              uint64_t *slots, uint32_t cap, int or_bits, uint8_t *__restrict__ isnew, uint32_t *newcnt, uint32_t *lnew)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t lo = 0, hi = P; // sub-table s with off[s] <= i < off[s+1]
+	while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
+	const uint64_t val = keys[i];
+	uint64_t *slot, cur;
+	if (tab_insert(slots + (uint64_t)lo * cap, cap, val, &slot, &cur)) {
+		isnew[i] = 1;
+		atomicAdd(&newcnt[lo], 1u);
+		atomicMax(&lnew[lo], (uint32_t)(i - off[lo]) + 1);
+	} else {
+		isnew[i] = 0;
+		if (or_bits && (val & YAKB_MAX_COUNT)) atomicOr((unsigned long long*)slot, (unsigned long long)(val & YAKB_MAX_COUNT));
+	}
+}
+
+__global__ void upsert_times_kernel(uint32_t P, uint32_t seq, const uint64_t *__restrict__ off, const uint32_t *__restrict__ lnew,
+                                    const uint32_t *__restrict__ newcnt, uint64_t *last_put, uint64_t *last_new, uint32_t *nkeys)
+{
+	uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= P) return;
+	const uint64_t m = off[s + 1] - off[s];
+	if (m) last_put[s] = (uint64_t)(seq + 1) << 32 | m;            // every key of the file is a put
+	if (lnew[s]) last_new[s] = (uint64_t)(seq + 1) << 32 | lnew[s];
+	nkeys[s] += newcnt[s];
+}
+
+uint64_t Engine::upsert(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys, bool or_bits)
+{
+	// yak_ht_resize(h, capacity in the file) on every sub-table first (htab.c:438), as journal operations
+	std::vector<uint64_t> ops(P);
+	for (int s = 0; s < P; ++s) ops[s] = (uint64_t)caps[s] << YAKB_COUNTER_BITS | OP_RESIZE;
+	append_ops(ops);
+	const uint64_t n = off[P];
+	if (n == 0) return 0;
+	std::vector<uint32_t> have;
+	sizes(have);
+	uint64_t mx = 8;
+	for (int s = 0; s < P; ++s) mx = std::max<uint64_t>(mx, (uint64_t)have[s] + (off[s + 1] - off[s]));
+	reserve(mx);
+	uint64_t *d_keys = b_pv.as<uint64_t>(n), *d_off = b_tmp.as<uint64_t>(P + 1), *d_new = b_newv.as<uint64_t>(n);
+	uint8_t *isnew = b_pflag.as<uint8_t>(n);
+	uint32_t *newcnt = b_pend.as<uint32_t>(P + 1), *lnew = b_lnew.as<uint32_t>(P);
+	unsigned long long *stats = b_stats.as<unsigned long long>(4);
+	YAKB_CUDA(cudaMemcpyAsync(d_keys, keys, n * 8, cudaMemcpyHostToDevice, stream));
+	YAKB_CUDA(cudaMemcpyAsync(d_off, off.data(), (uint64_t)(P + 1) * 8, cudaMemcpyHostToDevice, stream));
+	YAKB_CUDA(cudaMemsetAsync(newcnt, 0, (P + 1) * 4, stream));
+	YAKB_CUDA(cudaMemsetAsync(lnew, 0, P * 4, stream));
+	YAKB_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned long long), stream));
+	upsert_kernel<<<cdiv(n, 256), 256, 0, stream>>>(d_keys, d_off, P, n, slots, cap, or_bits ? 1 : 0, isnew, newcnt, lnew);
+	YAKB_CUDA(cudaGetLastError());
+	compact_flagged_u64(d_keys, isnew, n, d_new, (uint32_t*)(stats + 2), stream, rs); // new keys, file order = sub-table order
+	std::vector<uint32_t> h_newcnt(P);
+	YAKB_CUDA(cudaMemcpyAsync(h_newcnt.data(), newcnt, P * 4, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+	std::vector<uint64_t> noff(P + 1, 0);
+	for (int s = 0; s < P; ++s) noff[s + 1] = noff[s] + h_newcnt[s];
+	const uint64_t n_new = noff[P];
+	if (n_new) {
+		Segment seg;
+		seg.n = n_new;
+		seg.keys = (uint64_t*)journal_alloc(n_new * 8);
+		seg.off = (uint64_t*)journal_alloc((uint64_t)(P + 1) * 8);
+		YAKB_CUDA(cudaMemcpyAsync(seg.keys, d_new, n_new * 8, cudaMemcpyDeviceToDevice, stream));
+		YAKB_CUDA(cudaMemcpyAsync(seg.off, noff.data(), (uint64_t)(P + 1) * 8, cudaMemcpyHostToDevice, stream));
+		clear_kernel<<<cdiv(n_new, 256), 256, 0, stream>>>(seg.keys, n_new); // journal entries are puts: no low bits
+		YAKB_CUDA(cudaGetLastError());
+		journal.push_back(seg);
+	}
+	upsert_times_kernel<<<cdiv(P, 256), 256, 0, stream>>>(P, chunk_seq, d_off, lnew, newcnt, last_put, last_new, nkeys);
+	YAKB_CUDA(cudaGetLastError());
+	YAKB_CUDA(cudaStreamSynchronize(stream)); // noff is read by the copy above until here
+	note_launch(4);
+	++chunk_seq;
+	tot += n_new;
+	return n_new;
+}
+
 void Engine::clear()
 {
 	const uint64_t total = (uint64_t)P * cap;
@@ -1519,15 +1605,15 @@ void Engine::append_ops(const std::vector<uint64_t> &op)
 	journal.push_back(seg);
 }
 
-void qv_scan_ascii(Engine *e, const uint8_t *d_asc, uint64_t n, int16_t *d_cnt)
+void qv_scan_ascii(Engine *e, const uint8_t *d_asc, uint64_t n, int16_t *d_cnt, int raw)
 {
 	if (n == 0) return;
 	const uint64_t nwords = (n + 31) / 32;
 	uint64_t *w2 = e->b_w2.as<uint64_t>(packed_words(nwords)) + YAKB_PADW;
 	uint32_t *wm = e->b_wm.as<uint32_t>(packed_words(nwords)) + YAKB_PADW;
 	pack_ascii_kernel<<<cdiv(packed_npad(nwords) + YAKB_PADW, 256), 256, 0, e->stream>>>(d_asc, n, w2, wm, nwords, packed_npad(nwords));
-	if (e->k >= 32) qv_scan_kernel<true><<<cdiv(nwords, 256), 256, 0, e->stream>>>(w2, wm, nwords, n, e->k, e->pre, e->P - 1, e->own(), e->slots, e->cap, d_cnt);
-	else qv_scan_kernel<false><<<cdiv(nwords, 256), 256, 0, e->stream>>>(w2, wm, nwords, n, e->k, e->pre, e->P - 1, e->own(), e->slots, e->cap, d_cnt);
+	if (e->k >= 32) qv_scan_kernel<true><<<cdiv(nwords, 256), 256, 0, e->stream>>>(w2, wm, nwords, n, e->k, e->pre, e->P - 1, e->own(), e->slots, e->cap, d_cnt, raw);
+	else qv_scan_kernel<false><<<cdiv(nwords, 256), 256, 0, e->stream>>>(w2, wm, nwords, n, e->k, e->pre, e->P - 1, e->own(), e->slots, e->cap, d_cnt, raw);
 	YAKB_CUDA(cudaGetLastError());
 	YAKB_CUDA(cudaStreamSynchronize(e->stream));
 }

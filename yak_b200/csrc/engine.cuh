@@ -116,6 +116,10 @@ struct Engine {
 	void layout(int s0, int s1, LayoutOut &out, bool with_counts = true);
 	// restore: sub-table s gets `keys` (stored form, with counts) in file order, khashl pre-sized to cap
 	void load_subtables(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys, bool keys_on_device = false);
+	// restore into the table as it is (htab.c:436-472): resize every sub-table to caps[s], then put the keys
+	// (stored form; low bits = bits to set) in file order; existing keys get the bits OR-ed in when or_bits.
+	// Returns the number of keys that were new.
+	uint64_t upsert(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys, bool or_bits);
 	void rebuild_dev(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *d_keys);
 	template<class F> void layout_batches(int s0, int s1, bool with_counts, uint64_t reserve_bytes, F &&fn);
 	uint64_t device_bytes() const;
@@ -129,6 +133,6 @@ private:
 };
 
 // lookups for qv (qv.c:34-86): per position count (-1 = no k-mer event there), device in/out
-void qv_scan_ascii(Engine *e, const uint8_t *d_asc, uint64_t n, int16_t *d_cnt);
+void qv_scan_ascii(Engine *e, const uint8_t *d_asc, uint64_t n, int16_t *d_cnt, int raw = 0);
 
 } // namespace yakb
