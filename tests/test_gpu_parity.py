@@ -231,3 +231,44 @@ def test_layout_replay_variants_agree(oracle, yakb, reads_fa, monkeypatch, smem_
         finally:
             yakb.lib().yak_ch_destroy(hg)
             oracle.lib().yo_ch_destroy(ho)
+
+
+ZONE_SNIPPET = r"""
+import sys, os
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np
+import oracle_lib
+from yak_b200 import capi, synth
+capi.require_gpu()
+fn = {fn!r}
+rng = np.random.default_rng(11)
+with open(fn, "wb") as f:
+    f.write(synth.reads_file_bytes(3, 300_000, 4, 30_000, 150, 0.01, 2))
+    for i in range(3000):                      # skew: one k-mer (and its neighbours) thousands of times -> zone lists overflow
+        f.write(b">pa%d\n" % i + b"A" * int(rng.integers(31, 200)) + b"\n")
+    f.write(synth.reads_file_bytes(3, 300_000, 5, 20_000, 150, 0.01, 2))
+for k, pre, b in ((31, 10, 0), (31, 12, 24), (47, 11, 23), (21, 10, 22)):
+    hg = capi.count_file(fn, k=k, pre=pre, bf_shift=b, chunk_size=1_500_000)
+    ho, _ = oracle_lib.count_file(fn, k=k, pre=pre, bf_shift=b)
+    assert capi.dump_bytes(hg) == oracle_lib.dump_bytes(ho), (k, pre, b)
+    capi.lib().yak_ch_destroy(hg); oracle_lib.lib().yo_ch_destroy(ho)
+print("zone ok")
+"""
+
+
+@pytest.mark.parametrize("env", [
+    {"YAKB_ZONE": "1", "YAKB_ZONE_MB": "0.02"},                              # several sub-tables per zone
+    {"YAKB_ZONE": "1", "YAKB_ZONE_MB": "0.0001"},                            # one sub-table per zone
+    {"YAKB_ZONE": "1", "YAKB_ZONE_MB": "0.02", "YAKB_ZONE_SLACK": "0"},      # zone lists overflow into the spill list
+    {"YAKB_ZONE": "1", "YAKB_ZONE_MB": "4"},                                 # few zones
+], ids=["zones", "zone-per-subtable", "spill", "few-zones"])
+def test_zone_blocked_front_end_is_bit_exact(env):
+    """the zone-blocked probe path (engine.cu: zone_scatter / zone_probe) is chosen for tables of gigabytes; force it
+    on small inputs - both passes, several chunks, skewed k-mers - and compare the .yak bytes with the oracle"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, YAKB_BATCH="1500000", **env)
+    r = subprocess.run([sys.executable, "-c", ZONE_SNIPPET.format(root=root, fn=os.path.join(util.TMP, "yakb_zone.fa"))],
+                       env=e, capture_output=True, text=True)
+    assert r.returncode == 0 and "zone ok" in r.stdout, r.stderr[-3000:]

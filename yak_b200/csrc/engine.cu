@@ -327,6 +327,191 @@ __global__ void __launch_bounds__(256, 3) k1_fused(const uint64_t *__restrict__ 
 		for (uint32_t i = threadIdx.x; i < P; i += 256) if (s_lp[i]) atomicMax(&glob_lput[i], s_lp[i]);
 }
 
+// ---- K1, zone-blocked front end for large tables.  Random 32-byte read-modify-writes spread over tens of
+//      gigabytes run at ~12 G/s on this part; the same operations confined to ~100 MB of the table at a time
+//      run 2-4 times faster (DRAM row locality + L2 merging; tools/zone_sweep.cu).  So the events of a chunk
+//      are first scattered into per-zone lists (zone = a group of neighbouring sub-tables), then the table
+//      is probed zone by zone.  Counter updates commute, and the pending flag / last-put bookkeeping are
+//      per position, so the order in which events reach the table is free.
+//
+//      zone_scatter: one pass over the packed reads, each CTA a tile of `ztile` words: roll + hash every
+//      k-mer twice - once to count the tile's events per zone (shared-memory bins), once, after reserving the
+//      tile's ranges in the zone lists with one global atomic per zone, to write (hash, position) there.
+//      Zone lists have a fixed capacity (mean + 25 %); what does not fit goes to a spill list (skewed input).
+//      Ranks inside a (tile, zone) run come from warp votes, not from shared-memory atomics with a return
+//      value (those cost ~200 cycles per warp instruction here): every warp keeps private per-zone counters;
+//      the lanes of a step that hit the same zone find each other with match.any, the first of them bumps
+//      the warp's counter for all, the others take consecutive places behind it.
+template<bool LONGK, int PASS, class F>
+__device__ __forceinline__ void zone_roll(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t W, bool live, int k,
+                                          uint32_t Pmask, Own own, int zshift, uint32_t *wc, uint32_t &my_ev, F &&place)
+{
+	const int lane = threadIdx.x & 31;
+	Roller<LONGK> ro;
+	if (live) ro.init(w2, wm, (int64_t)W, k);
+#pragma unroll 4
+	for (int r = 0; r < 32; ++r) {
+		uint64_t v = 0;
+		const bool e = live && ro.step(r, v) && ((uint32_t)(v >> own.shift) & own.mask) == own.rank;
+		const uint32_t z = e ? ((uint32_t)v & Pmask) >> zshift : 0xFFFFFFFFu;
+		const uint32_t m = __match_any_sync(0xffffffffu, z);
+		const int leader = __ffs(m) - 1;
+		uint32_t base = 0;
+		if (e && lane == leader) { base = wc[z]; wc[z] = base + __popc(m); }
+		__syncwarp();
+		if (PASS == 1) {
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (e) place(r, v, z, base + __popc(m & ((1u << lane) - 1)));
+		} else if (e) ++my_ev;
+	}
+}
+
+template<bool LONGK>
+__global__ void __launch_bounds__(256) zone_scatter(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords, int k, uint32_t ztile,
+                                                    uint32_t Pmask, Own own, int zshift, uint32_t Z, uint32_t zcap, unsigned int *zfill,
+                                                    uint64_t *__restrict__ zev, uint32_t *__restrict__ zpos,
+                                                    uint64_t *__restrict__ spill_ev, uint32_t *__restrict__ spill_pos, unsigned int *n_spill,
+                                                    unsigned long long *stats)
+{
+	extern __shared__ uint32_t s_z[]; // [8 warps][Z]: events per (warp, zone), then each warp's cursor into the zone lists
+	uint32_t *wc = s_z + (threadIdx.x >> 5) * Z;
+	const uint64_t ntiles = (nwords + ztile - 1) / ztile;
+	uint32_t my_ev = 0;
+	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		for (uint32_t i = threadIdx.x; i < 8 * Z; i += 256) s_z[i] = 0;
+		__syncthreads();
+		for (uint32_t j = 0; j < ztile / 256; ++j) {
+			const uint64_t W = tile * ztile + j * 256 + threadIdx.x;
+			zone_roll<LONGK, 0>(w2, wm, W, W < nwords, k, Pmask, own, zshift, wc, my_ev, [](int, uint64_t, uint32_t, uint32_t) {});
+		}
+		__syncthreads();
+		for (uint32_t z = threadIdx.x; z < Z; z += 256) { // one reservation per zone for the whole tile, split among the warps
+			uint32_t c[8], tot = 0;
+#pragma unroll
+			for (int w = 0; w < 8; ++w) { c[w] = s_z[w * Z + z]; tot += c[w]; }
+			uint32_t base = tot ? atomicAdd(&zfill[z], tot) : 0;
+#pragma unroll
+			for (int w = 0; w < 8; ++w) { s_z[w * Z + z] = base; base += c[w]; }
+		}
+		__syncthreads();
+		for (uint32_t j = 0; j < ztile / 256; ++j) {
+			const uint64_t W = tile * ztile + j * 256 + threadIdx.x;
+			zone_roll<LONGK, 1>(w2, wm, W, W < nwords, k, Pmask, own, zshift, wc, my_ev, [&](int r, uint64_t v, uint32_t z, uint32_t i) {
+				const uint32_t pos = (uint32_t)(W * 32 + r);
+				if (i < zcap) { zev[(uint64_t)z * zcap + i] = v; zpos[(uint64_t)z * zcap + i] = pos; }
+				else { const uint32_t q = atomicAdd(n_spill, 1u); spill_ev[q] = v; spill_pos[q] = pos; }
+			});
+		}
+		__syncthreads();
+	}
+#pragma unroll
+	for (int d = 16; d; d >>= 1) my_ev += __shfl_xor_sync(0xffffffffu, my_ev, d);
+	if ((threadIdx.x & 31) == 0 && my_ev) atomicAdd(&stats[0], (unsigned long long)my_ev);
+}
+
+//      zone_probe: persistent CTAs take slices of 2048 events from a global work counter, in zone order, so
+//      at any moment the whole grid works on one or two zones.  Per event the same bucket probe + counter
+//      CAS as k1_fused; a miss sets the position's bit in flags[] (pass 1).  n_list = Z zone lists of zcap
+//      entries each (fill counts in zfill[]), or one list (the spill).
+#define YAKB_ZSLICE 2048
+__global__ void __launch_bounds__(256, 3) zone_probe(const uint64_t *__restrict__ zev, const uint32_t *__restrict__ zpos, uint32_t n_list, uint32_t zcap,
+                                                    const unsigned int *__restrict__ zfill, int pre, uint32_t Pmask,
+                                                    uint64_t *slots, uint32_t cap, int create_new, uint32_t *flags,
+                                                    uint32_t *glob_lput, int smem_lp, unsigned int *work)
+{
+	extern __shared__ uint32_t s_lp[];
+	__shared__ uint32_t s_item;
+	const uint32_t P = Pmask + 1, nbk = cap / YAKB_BUCKET;
+	if (smem_lp) for (uint32_t i = threadIdx.x; i < P; i += 256) s_lp[i] = 0;
+	// slices per list; a single list (the spill) is cut by its actual fill, which is usually zero
+	const uint32_t spz = ((n_list == 1 ? min(zfill[0], zcap) : zcap) + YAKB_ZSLICE - 1) / YAKB_ZSLICE;
+	const uint64_t n_items = (uint64_t)n_list * spz;
+	for (;;) {
+		__syncthreads();
+		if (threadIdx.x == 0) s_item = atomicAdd(work, 1u);
+		__syncthreads();
+		const uint64_t item = s_item;
+		if (item >= n_items) break;
+		const uint32_t z = (uint32_t)(item / spz), sl = (uint32_t)(item % spz);
+		const uint32_t nz = min(zfill[z], zcap), start = sl * YAKB_ZSLICE;
+		if (start >= nz) continue; // an empty tail slice of this list
+		const uint64_t *ev = zev + (uint64_t)z * zcap;
+		const uint32_t *ep = zpos + (uint64_t)z * zcap;
+#pragma unroll 1
+		for (uint32_t g = 0; g < YAKB_ZSLICE / 1024; ++g) { // 4 events per thread at a time, lanes on consecutive entries
+			uint64_t v[4];
+			Bucket bk[4];
+			uint32_t bi[4], pos[4], vm = 0;
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const uint32_t i = start + g * 1024 + j * 256 + threadIdx.x;
+				bi[j] = 0; v[j] = 0; pos[j] = 0;
+				if (i < nz) {
+					v[j] = ev[i]; pos[j] = ep[i];
+					vm |= 1u << j;
+					bi[j] = tab_home(v[j] >> pre, nbk);
+					bk[j] = load_bucket(slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET);
+				}
+			}
+			uint64_t expect[4], prev[4];
+			uint32_t todo = 0, hit = 0;
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				expect[j] = prev[j] = 0;
+				if (vm >> j & 1) {
+					int f, m = bucket_match(bk[j], v[j] >> pre, &f);
+					if (m >= 0) {
+						const uint64_t c = bucket_get(bk[j], m);
+						hit |= 1u << j;
+						if ((c & YAKB_MAX_COUNT) != YAKB_MAX_COUNT) {
+							uint64_t *q = slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET + m;
+							expect[j] = c;
+							prev[j] = atomicCAS((unsigned long long*)q, (unsigned long long)c, (unsigned long long)(c + 1));
+						}
+					} else if (f < 0) todo |= 1u << j;
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < 4; ++j) if (prev[j] != expect[j]) { todo |= 1u << j; hit &= ~(1u << j); }
+			if (__any_sync(0xffffffffu, todo != 0)) {
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const bool redo = todo >> j & 1;
+					if (__any_sync(0xffffffffu, redo)) {
+						uint64_t *reg = slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap;
+						Bucket bb = bk[j];
+						if (redo && prev[j] != expect[j]) bb = load_bucket(reg + (uint64_t)bi[j] * YAKB_BUCKET);
+						if (probe_inc_warp(reg, nbk, v[j] >> pre, bi[j], bb, redo)) hit |= 1u << j;
+					}
+				}
+			}
+			if (create_new) {
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					if (!(vm >> j & 1)) continue;
+					if (hit >> j & 1) {
+						const uint32_t s = (uint32_t)v[j] & Pmask, t = pos[j] + 1;
+						if (smem_lp) atomicMax(&s_lp[s], t); else atomicMax(&glob_lput[s], t);
+					} else atomicOr(&flags[pos[j] >> 5], 1u << (pos[j] & 31));
+				}
+			}
+		}
+	}
+	__syncthreads();
+	if (smem_lp && create_new)
+		for (uint32_t i = threadIdx.x; i < P; i += 256) if (s_lp[i]) atomicMax(&glob_lput[i], s_lp[i]);
+}
+
+// pending events per 256-word tile from the flag words (what k1_fused accumulates as it goes)
+__global__ void __launch_bounds__(256) flag_tilecnt_kernel(const uint32_t *__restrict__ flags, uint64_t nwords, uint32_t *__restrict__ tilecnt)
+{
+	const uint64_t W = blockIdx.x * 256ull + threadIdx.x;
+	uint32_t c = W < nwords ? __popc(flags[W]) : 0;
+	uint32_t tot;
+	block_excl_scan_256(c, &tot);
+	if (threadIdx.x == 0) tilecnt[blockIdx.x] = tot;
+}
+
 // ---- K1, array front end (events already hashed: yak_ch_insert_list, multi-GPU receive side).
 //      word W = events 32W..32W+31, lane = bit.
 __global__ void __launch_bounds__(256) k1_array(const uint64_t *__restrict__ ev, uint64_t n, int pre, uint32_t Pmask, Own own,
@@ -948,7 +1133,7 @@ Engine::~Engine()
 	dev_free(slots); dev_free(nkeys); dev_free(bloom); dev_free(last_put); dev_free(last_new);
 	journal_free_all();
 	DBuf *all[] = {&b_w2, &b_wm, &b_flags, &b_tilecnt, &b_tileoff, &b_pv, &b_ppos, &b_sv, &b_sj, &b_sv2, &b_sj2, &b_pflag, &b_newv,
-	               &b_newsorted, &b_tmp, &b_pend, &b_lput, &b_lnew, &b_stats, &b_misc, 
+	               &b_newsorted, &b_tmp, &b_pend, &b_lput, &b_lnew, &b_stats, &b_misc, &b_zev, &b_zpos, &b_zsp, &b_zspp, &b_zfill,
 	               &b_lay[0], &b_lay[1], &b_lay[2], &b_lay[3], &b_lay[4], &b_lay[5], &b_lay[6], &b_lay[7], &b_lay[8], &b_lay[9], &b_lay[10], &b_lay[11]};
 	for (DBuf *b : all) b->release();
 	rs.release();
@@ -1067,6 +1252,56 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 	const int smem1 = create_new && smem_lp_ok(P, 1);
 	const size_t sm1 = smem1 ? (size_t)P * 4 : 0;
 	const uint32_t grid1 = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)nsm * 4);
+	// zone-blocked probing, EXPERIMENTAL and off unless YAKB_ZONE is set (1 = always, 2 = for tables >= 2 GB;
+	// YAKB_ZONE_MB = zone size, default 128).  Measured on cfg2 (profiles/r01_zone_blocking.md): the probe itself
+	// gets 1.6x faster at 240 M events per chunk, but the scatter that feeds it costs as much as it saves - its
+	// per-event 8-byte stores are bound by L2 write transactions (~38 G/s), not bytes - so k1_fused stays the default.
+	int zshift = 0;
+	uint32_t Z = 0;
+	if (d_ev == nullptr && cap) {
+		static const int zmode = getenv("YAKB_ZONE") ? atoi(getenv("YAKB_ZONE")) : 0;
+		static const double zmb = getenv("YAKB_ZONE_MB") ? atof(getenv("YAKB_ZONE_MB")) : 128.0;
+		const double table_bytes = (double)P * cap * 8;
+		if (zmode == 1 || (zmode == 2 && table_bytes >= 2e9)) {
+			while ((1 << zshift) < P && (double)cap * 8 * (2 << zshift) <= zmb * 1048576.0) ++zshift;
+			Z = (uint32_t)P >> zshift;
+			while (Z > 2048) { ++zshift; Z >>= 1; } // 8 warps x Z counters must fit shared memory
+			if (Z < 2) Z = 0;
+		}
+	}
+	if (Z) {
+		const uint64_t n_pos = nwords * 32;
+		static const uint64_t zslack = getenv("YAKB_ZONE_SLACK") ? (uint64_t)atoll(getenv("YAKB_ZONE_SLACK")) : 4096; // test knob: 0 forces spills
+		const uint32_t zcap = (uint32_t)std::min<uint64_t>(n_pos, n_pos / Z + n_pos / Z / 4 + zslack);
+		uint64_t *zev = b_zev.as<uint64_t>((uint64_t)Z * zcap), *sp_ev = b_zsp.as<uint64_t>(n_pos);
+		uint32_t *zpos = b_zpos.as<uint32_t>((uint64_t)Z * zcap), *sp_pos = b_zspp.as<uint32_t>(n_pos);
+		unsigned int *zfill = b_zfill.as<unsigned int>(Z + 4); // [Z] fills, n_spill, work, work2
+		YAKB_CUDA(cudaMemsetAsync(zfill, 0, (Z + 4) * 4, stream));
+		if (create_new) YAKB_CUDA(cudaMemsetAsync(flags, 0, nwords * 4, stream));
+		const size_t smz = (size_t)Z * 8 * 4;
+		// events in flight between a tile's reservation and its last store must stay well inside L2, or half-written
+		// sectors of the zone lists are evicted and written twice: small tiles, few CTAs
+		static const uint32_t ztile = getenv("YAKB_ZTILE_WORDS") ? (uint32_t)atoi(getenv("YAKB_ZTILE_WORDS")) / 256 * 256 : 1024;
+		static const int zgrid = getenv("YAKB_ZGRID") ? atoi(getenv("YAKB_ZGRID")) : 4;
+		const uint64_t nzt = (nwords + ztile - 1) / ztile;
+		const uint32_t gridz = (uint32_t)std::min<uint64_t>(nzt, (uint64_t)nsm * zgrid);
+		{ ProfScope ps("zone_scatter", stream);
+		if (longk) {
+			set_smem(zone_scatter<true>, smz);
+			zone_scatter<true><<<gridz, 256, smz, stream>>>(w2, wm, nwords, k, ztile, Pmask, own(), zshift, Z, zcap, zfill, zev, zpos, sp_ev, sp_pos, zfill + Z, stats);
+		} else {
+			set_smem(zone_scatter<false>, smz);
+			zone_scatter<false><<<gridz, 256, smz, stream>>>(w2, wm, nwords, k, ztile, Pmask, own(), zshift, Z, zcap, zfill, zev, zpos, sp_ev, sp_pos, zfill + Z, stats);
+		} }
+		{ ProfScope ps("zone_probe", stream);
+		set_smem(zone_probe, sm1);
+		zone_probe<<<nsm * 3, 256, sm1, stream>>>(zev, zpos, Z, zcap, zfill, pre, Pmask, slots, cap, create_new, flags, lput, smem1, zfill + Z + 1);
+		// the spill list: one more list whose fill count is n_spill (normally 0: its slices are all empty)
+		zone_probe<<<nsm * 3, 256, sm1, stream>>>(sp_ev, sp_pos, 1, (uint32_t)std::min<uint64_t>(n_pos, 0xFFFFFFFFu), zfill + Z, pre, Pmask, slots, cap, create_new, flags, lput, smem1, zfill + Z + 2);
+		if (create_new) flag_tilecnt_kernel<<<(uint32_t)ntiles, 256, 0, stream>>>(flags, nwords, tilecnt); }
+		YAKB_CUDA(cudaGetLastError());
+		note_launch(create_new ? 3 : 2);
+	} else
 	{ ProfScope ps(d_ev ? "k1_array" : "k1_fused", stream);
 	if (d_ev == nullptr) {
 		if (longk) {

@@ -87,7 +87,7 @@ struct Engine {
 	double load_limit = 0.6;
 	// scratch (grow-only, reused by every chunk)
 	DBuf b_w2, b_wm, b_flags, b_tilecnt, b_tileoff, b_pv, b_ppos, b_sv, b_sj, b_sv2, b_sj2, b_pflag, b_newv, b_newsorted,
-	     b_tmp, b_pend, b_lput, b_lnew, b_stats, b_misc, b_lay[12], b_segp;
+	     b_tmp, b_pend, b_lput, b_lnew, b_stats, b_misc, b_lay[12], b_segp, b_zev, b_zpos, b_zsp, b_zspp, b_zfill;
 	RadixScratch rs;
 
 	static Engine *create(int k, int pre, int n_hash, int n_shift, int rank = 0, int world = 1);
