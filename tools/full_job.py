@@ -33,7 +33,10 @@ print(json.dumps(out), flush=True)
 t0 = time.time(); lib.yak_ch_destroy_bf(h); lib.yak_ch_clear(h, 1); out["destroy_bf_clear_s"] = time.time() - t0
 t, ev = one_pass(0); out["pass2_s"] = t
 print(json.dumps(out), flush=True)
+lib.yakb_prof_enable(1)
 t0 = time.time(); lib.yak_ch_shrink(h, 2, 1023, 1); out["shrink_s"] = time.time() - t0; out["distinct_final"] = int(h.contents.tot)
+pj = C.create_string_buffer(1 << 16); lib.yakb_prof_json(pj, 1 << 16); lib.yakb_prof_enable(0)
+out["shrink_kernels_ms"] = {k: round(v[0], 1) for k, v in json.loads(pj.value.decode()).items()}
 print(json.dumps(out), flush=True)
 hist = (C.c_int64 * 1024)()
 t0 = time.time(); lib.yak_ch_hist(h, hist, 1); out["hist_s"] = time.time() - t0
@@ -41,7 +44,24 @@ out["hist_peak"] = max(range(2, 1024), key=lambda i: hist[i]); out["hist_sum"] =
 out["total_s"] = out["pass1_s"] + out["destroy_bf_clear_s"] + out["pass2_s"] + out["shrink_s"]
 out["input_events_per_s"] = out["events"] / out["total_s"]
 print(json.dumps(out), flush=True)
-if len(sys.argv) > 4 and sys.argv[4] == "dump":
+if "qv" in sys.argv[4:]:
+    # BASELINE configs[2]: yak qv of 50 x 1 Mbp contigs (1e-4 substitutions) against the resident table, through
+    # yak_qv(opt, file, ch, cnt): parse + H2D + batched device lookups + histogram
+    nctg, lctg = 50, 1_000_000
+    cbuf = torch.empty(nctg * (lctg + 4), dtype=torch.uint8, device="cuda")
+    lib.yakb_synth_reads_dev(g2.data_ptr(), G, 99, 0, nctg, lctg, 1e-4, 0, 1, cbuf.data_ptr(), cur)
+    torch.cuda.synchronize()
+    fn = "/dev/shm/yakb_ctg.fa"
+    cbuf.cpu().numpy().tofile(fn)
+    qo = capi.YakQopt()
+    lib.yak_qopt_init(C.byref(qo))
+    cnt = (C.c_int64 * 1024)()
+    for rep in range(2):
+        t0 = time.time(); lib.yak_qv(C.byref(qo), fn.encode(), h, cnt); out["qv_s"] = time.time() - t0
+    out["qv_lookups"] = sum(cnt); out["qv_lookups_per_s"] = sum(cnt) / out["qv_s"]; out["qv_absent_or_zero"] = cnt[0]
+    os.unlink(fn)
+    print(json.dumps(out), flush=True)
+if "dump" in sys.argv[4:]:
     t0 = time.time(); rc = lib.yak_ch_dump(h, b"/dev/shm/yakb_full.yak"); out["dump_s"] = time.time() - t0
     out["dump_bytes"] = os.path.getsize("/dev/shm/yakb_full.yak") if rc == 0 else -1
     os.unlink("/dev/shm/yakb_full.yak")

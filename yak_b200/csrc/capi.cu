@@ -600,6 +600,7 @@ extern "C" void yakb_device_cache_trim(void) { dev_trim(); }
 extern "C" void yakb_prof_enable(int on) { Prof::enable(on != 0); if (on) Prof::reset(); }
 extern "C" int yakb_prof_json(char *buf, uint64_t cap)
 {
+	Prof::resolve(); // event pairs recorded outside the per-chunk path (layout, shrink); waits for their completion
 	std::string j = Prof::json();
 	if (j.size() + 1 > cap) return -1;
 	memcpy(buf, j.c_str(), j.size() + 1);

@@ -1648,22 +1648,27 @@ template<class F> void Engine::layout_batches(int s0, int s1, bool with_counts, 
 			YAKB_CUDA(cudaMemcpyAsync(d_list, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
 			for (int k = 0; k < 3; ++k) {
 				if (lists[k].empty()) continue;
+				ProfScope ps("layout(smem replay)", stream);
 				const size_t sm = (size_t)cls[k] * 8 + (size_t)(cls[k] < 32 ? 1 : cls[k] >> 5) * 8 + 512 * 8;
 				YAKB_CUDA(cudaFuncSetAttribute(build_layout_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
 				build_layout_smem_kernel<<<(uint32_t)lists[k].size(), 32, sm, stream>>>(d_list + start[k], cls[k], sv, s0 + b0, d_pf, d_pv, d_trail,
 				                                                                          d_out, d_ooff, d_ocap, d_osize);
 			}
-			if (!lists[3].empty())
+			if (!lists[3].empty()) {
+				ProfScope ps("layout(thread replay)", stream);
 				build_layout_kernel<<<cdiv(lists[3].size(), 32), 32, 0, stream>>>(d_list + start[3], (int)lists[3].size(), sv, s0 + b0, d_pf, d_pv, d_trail,
 				                                                                  d_out, d_ooff, d_bm, d_boff, d_ocap, d_osize);
+			}
 			if (!lists[4].empty()) {
 				uint64_t *d_cat = b_lay[0].as<uint64_t>(std::max<uint64_t>(catoff.back(), 1));
 				uint32_t *d_own = b_lay[7].as<uint32_t>(std::max<uint64_t>(ooff.back(), 1));
 				uint64_t *d_catoff = (uint64_t*)b_tmp.need((size_t)(2 * ns + 2) * 8), *d_run = d_catoff + ns + 1;
 				YAKB_CUDA(cudaMemcpyAsync(d_catoff, catoff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
 				YAKB_CUDA(cudaMemsetAsync(d_run, 0, (size_t)ns * 8, stream));
+				{ ProfScope ps("layout(gather journal)", stream);
 				for (auto &seg : journal)
-					gather_seg_kernel<<<(uint32_t)lists[4].size(), 256, 0, stream>>>(seg.keys, seg.off, s0 + b0, d_list + start[4], (int)lists[4].size(), d_catoff, d_run, d_cat);
+					gather_seg_kernel<<<(uint32_t)lists[4].size(), 256, 0, stream>>>(seg.keys, seg.off, s0 + b0, d_list + start[4], (int)lists[4].size(), d_catoff, d_run, d_cat); }
+				ProfScope ps("layout(warp replay)", stream);
 				build_layout_warp_kernel<<<(uint32_t)lists[4].size(), 32, 0, stream>>>(d_list + start[4], d_cat, d_catoff, d_pf, d_pv, d_trail,
 				                                                                       d_out, d_ooff, d_bm, d_boff, d_own, d_ocap, d_osize);
 			}
@@ -1683,6 +1688,7 @@ template<class F> void Engine::layout_batches(int s0, int s1, bool with_counts, 
 		uint64_t *d_dense = b_lay[2].as<uint64_t>(std::max<uint64_t>(nv, 1));
 		YAKB_CUDA(cudaMemcpyAsync(d_voff, voff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, stream));
 		if (nv) {
+			ProfScope ps("layout(densify+counts)", stream);
 			densify_kernel<<<cdiv(nv, 256), 256, 0, stream>>>(d_out, d_ooff, d_voff, ns, nv, d_dense);
 			if (with_counts && cap) fill_counts_kernel<<<cdiv(nv, 256), 256, 0, stream>>>(d_dense, d_voff, ns, s0 + b0, nv, slots, cap);
 		}
@@ -1723,6 +1729,7 @@ void Engine::load_subtables(const std::vector<uint32_t> &caps, const std::vector
 	seg.off = (uint64_t*)journal_alloc((uint64_t)(P + 1) * 8);
 	YAKB_CUDA(cudaMemcpyAsync(seg.off, off.data(), (uint64_t)(P + 1) * 8, cudaMemcpyHostToDevice, stream));
 	if (n) {
+		ProfScope ps("load(bulk insert)", stream);
 		YAKB_CUDA(cudaMemcpyAsync(seg.keys, keys, n * 8, keys_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
 		bulk_insert_kernel<<<cdiv(n, 256), 256, 0, stream>>>(seg.keys, seg.off, P, n, slots, cap);
 		clear_kernel<<<cdiv(n, 256), 256, 0, stream>>>(seg.keys, n); // journal keeps keys without counts
@@ -1745,7 +1752,11 @@ __global__ void shrink_flag_kernel(const uint64_t *__restrict__ keys, const uint
 	const uint32_t c = (uint32_t)keys[i] & YAKB_MAX_COUNT;
 	const bool keep = c >= lo_c && c <= hi_c;
 	flag[i] = keep;
-	if (keep) atomicAdd(&kept[lo], 1u);
+	// one atomic per (warp, sub-table): neighbours almost always share the sub-table, and three billion atomics on a few
+	// thousand addresses take seconds
+	const uint32_t am = __activemask(), peers = __match_any_sync(am, lo);
+	const uint32_t votes = __ballot_sync(am, keep) & peers;
+	if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1) && votes) atomicAdd(&kept[lo], (uint32_t)__popc(votes));
 }
 
 void Engine::shrink(int min, int max)
@@ -1768,6 +1779,7 @@ void Engine::shrink(int min, int max)
 		YAKB_CUDA(cudaMemsetAsync(d_cnt, 0, (ns + 1) * 4, stream));
 		std::vector<uint32_t> h_cnt(ns, 0);
 		if (nv) {
+			ProfScope ps("shrink(filter)", stream);
 			shrink_flag_kernel<<<cdiv(nv, 256), 256, 0, stream>>>(d_dense, d_voff, ns, nv, (uint32_t)min, (uint32_t)max, flag, d_cnt);
 			compact_flagged_u64(d_dense, flag, nv, d_kept + n_kept, d_cnt + ns, stream, rs);
 			YAKB_CUDA(cudaGetLastError());
