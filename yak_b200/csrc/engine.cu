@@ -959,6 +959,97 @@ __global__ void __launch_bounds__(32) build_layout_smem_kernel(const int *__rest
 	}
 }
 
+// ---- the kick-out rehash (khashl.h:152-195) is one sequential walk per table, and on a table of megabytes every
+//      step of it is a round trip to L2 or DRAM (~1 us per key when one lane does it alone).  Its accesses are two
+//      streams, though - old slots upward, new homes at about twice that - so a few cache lines per array in shared
+//      memory catch nearly all of them.  All 32 lanes run the walk in lock step on identical values (free under
+//      SIMT); a missing line is fetched by the whole warp as one 128-byte load.  Write-through, and a write updates
+//      the cached copy, so the cache never holds anything the table does not.
+struct WarpCache {
+	uint64_t k[64][16];  // key lines (16 slots)
+	uint32_t u[16][32];  // lines of the old occupancy bitmap (1024 slots)
+	uint32_t o[16][32];  // lines of the new one
+	uint32_t kt[64], ut[16], ot[16];
+};
+
+__device__ __forceinline__ uint64_t wc_key(WarpCache &c, const uint64_t *K, uint32_t i, int lane)
+{
+	const uint32_t tag = i >> 4, s = tag & 63;
+	if (c.kt[s] != tag) {
+		__syncwarp();
+		if (lane < 16) c.k[s][lane] = __ldcg(K + (uint64_t)tag * 16 + lane);
+		c.kt[s] = tag;
+		__syncwarp();
+	}
+	return c.k[s][i & 15];
+}
+__device__ __forceinline__ void wc_key_put(WarpCache &c, uint64_t *K, uint32_t i, uint64_t v)
+{
+	const uint32_t tag = i >> 4, s = tag & 63;
+	K[i] = v;                                           // every lane, same address and value: one transaction
+	if (c.kt[s] == tag) c.k[s][i & 15] = v;
+}
+// word w of a bitmap through its line cache (lines[16][32], tags[16])
+__device__ __forceinline__ uint32_t wc_word(uint32_t (*lines)[32], uint32_t *tags, const uint32_t *bm, uint32_t w, int lane)
+{
+	const uint32_t tag = w >> 5, s = tag & 15;
+	if (tags[s] != tag) {
+		__syncwarp();
+		lines[s][lane] = __ldcg(bm + (uint64_t)tag * 32 + lane);
+		tags[s] = tag;
+		__syncwarp();
+	}
+	return lines[s][w & 31];
+}
+__device__ __forceinline__ void wc_word_put(uint32_t (*lines)[32], uint32_t *tags, uint32_t *bm, uint32_t w, uint32_t v)
+{
+	const uint32_t tag = w >> 5, s = tag & 15;
+	bm[w] = v;
+	if (tags[s] == tag) lines[s][w & 31] = v;
+}
+
+// khashl.h:152-195 for a table that grows, run by the whole warp on identical state (R is the same in every lane)
+__device__ void warp_resize(KhReplay &R, uint32_t request, WarpCache &c, int lane)
+{
+	uint32_t lg = 0, q = request;
+	while ((q >>= 1) != 0) ++lg;
+	if (request & (request - 1)) ++lg;
+	const uint32_t new_bits = lg > 2 ? lg : 2, new_n = 1u << new_bits, new_mask = new_n - 1, n = R.n;
+	if (R.count > (new_n >> 1) + (new_n >> 2)) return;
+	if (new_n < n) { // shrinking is not on this kernel's path (puts only); keep the plain walk for it
+		if (lane == 0) R.resize(request);
+		__syncwarp();
+		const int sw = __shfl_sync(0xffffffffu, (int)(R.bits != 0 && R.n != n), 0);
+		if (sw && lane != 0) { uint32_t *tmp = R.used; R.used = R.occ; R.occ = tmp; }
+		R.bits = __shfl_sync(0xffffffffu, R.bits, 0); R.n = __shfl_sync(0xffffffffu, R.n, 0);
+		return;
+	}
+	for (uint32_t w = lane; w < KhReplay::fw(new_n); w += 32) R.occ[w] = 0;
+	for (int i = lane; i < 64; i += 32) c.kt[i] = 0xFFFFFFFFu;
+	if (lane < 16) c.ut[lane] = c.ot[lane] = 0xFFFFFFFFu;
+	__syncwarp();
+	for (uint32_t j = 0; j != n; ++j) {
+		uint32_t uw = wc_word(c.u, c.ut, R.used, j >> 5, lane);
+		if (!(uw >> (j & 31) & 1)) continue;
+		uint64_t key = wc_key(c, R.K, j, lane);
+		wc_word_put(c.u, c.ut, R.used, j >> 5, uw & ~(1u << (j & 31)));
+		for (;;) {
+			uint32_t i = kh_home(key, new_bits), ow;
+			while ((ow = wc_word(c.o, c.ot, R.occ, i >> 5, lane)) >> (i & 31) & 1) i = (i + 1) & new_mask;
+			wc_word_put(c.o, c.ot, R.occ, i >> 5, ow | 1u << (i & 31));
+			if (i < n && ((uw = wc_word(c.u, c.ut, R.used, i >> 5, lane)) >> (i & 31) & 1)) { // an old key not moved yet: kick it out
+				const uint64_t ev = wc_key(c, R.K, i, lane);
+				wc_key_put(c, R.K, i, key);
+				key = ev;
+				wc_word_put(c.u, c.ut, R.used, i >> 5, uw & ~(1u << (i & 31)));
+			} else { wc_key_put(c, R.K, i, key); break; }
+		}
+	}
+	__syncwarp();
+	uint32_t *tmp = R.used; R.used = R.occ; R.occ = tmp;
+	R.bits = new_bits; R.n = new_n;
+}
+
 // warp variant for large sub-tables whose journal holds puts only (counting, shrink, restore):
 // the FCFS put phases between two doublings run on all 32 lanes - a slot belongs to the lowest
 // journal rank that probes it (atomicMin), a displaced rank moves on, which is exactly first-come
@@ -970,7 +1061,7 @@ __global__ void __launch_bounds__(32) build_layout_warp_kernel(const int *__rest
                                     const uint8_t *__restrict__ trailing,
                                     uint64_t *out_all, const uint64_t *__restrict__ ooff,
                                     uint32_t *bm_all, const uint64_t *__restrict__ boff,
-                                    uint32_t *own_all, uint32_t *out_cap, uint32_t *out_size)
+                                    uint32_t *own_all, uint32_t *out_cap, uint32_t *out_size, unsigned long long *phase_clk)
 {
 	const int t = list[blockIdx.x], lane = threadIdx.x;
 	const uint64_t *cat = cat_all + catoff[t];
@@ -980,12 +1071,17 @@ __global__ void __launch_bounds__(32) build_layout_warp_kernel(const int *__rest
 	R.K = out_all + ooff[t];
 	const uint64_t bwords = (boff[t + 1] - boff[t]) / 2;
 	R.used = bm_all + boff[t]; R.occ = R.used + bwords;
-	if (lane == 0) { R.used[0] = 0; if (pre_flag[t]) R.resize(pre_val[t]); }
+	__shared__ WarpCache wcache;
+	if (lane == 0) R.used[0] = 0;
+	__syncwarp();
+	if (pre_flag[t]) warp_resize(R, pre_val[t], wcache, lane); // R stays identical in all lanes throughout
 	__syncwarp();
 	uint64_t e0 = 0;
+	long long t_rehash = 0, t_init = 0, t_put = 0, t_mat = 0, t0 = clock64(), t1;
 	while (e0 < m) {
-		if (lane == 0) R.check(); // doubling when the load limit is reached (khashl.h:202-205)
-		__syncwarp(); // lane 0's writes to the table are visible to the other lanes from here
+		if (R.count >= (R.n >> 1) + (R.n >> 2)) warp_resize(R, R.n + 1, wcache, lane); // doubling at the load limit (khashl.h:202-205)
+		__syncwarp(); // the table as the rehash left it is visible to every lane from here
+		t1 = clock64(); t_rehash += t1 - t0; t0 = t1;
 		// broadcast the table state of lane 0
 		const uint32_t n = __shfl_sync(0xffffffffu, R.n, 0), bits = __shfl_sync(0xffffffffu, R.bits, 0), count = __shfl_sync(0xffffffffu, R.count, 0);
 		const int swapped = __shfl_sync(0xffffffffu, (int)(R.used != bm_all + boff[t]), 0);
@@ -994,6 +1090,7 @@ __global__ void __launch_bounds__(32) build_layout_warp_kernel(const int *__rest
 		const uint64_t e1 = m - e0 < room ? m : e0 + room;
 		for (uint32_t i = lane; i < n; i += 32) own[i] = 0xFFFFFFFFu;
 		__syncwarp();
+		t1 = clock64(); t_init += t1 - t0; t0 = t1;
 		for (uint64_t eb = e0; eb < e1; eb += 32) { // 32 keys at a time, ranks = journal positions
 			const uint64_t e = eb + lane;
 			bool active = e < e1;
@@ -1006,6 +1103,7 @@ __global__ void __launch_bounds__(32) build_layout_warp_kernel(const int *__rest
 			}
 		}
 		__syncwarp();
+		t1 = clock64(); t_put += t1 - t0; t0 = t1;
 		// materialise the phase: keys into their slots, occupancy bits; a lane owns whole bitmap words,
 		// and reads the owners from L2 where the atomics put them
 		for (uint32_t w = lane; w < (n < 32 ? 1u : n >> 5); w += 32) {
@@ -1017,13 +1115,16 @@ __global__ void __launch_bounds__(32) build_layout_warp_kernel(const int *__rest
 			used[w] = bitsw;
 		}
 		__syncwarp();
-		if (lane == 0) R.count += (uint32_t)(e1 - e0);
+		R.count += (uint32_t)(e1 - e0);
 		e0 = e1;
+		t1 = clock64(); t_mat += t1 - t0; t0 = t1;
 	}
-	if (lane == 0) {
-		if (trailing[t]) R.check();
-		out_cap[t] = R.n; out_size[t] = R.count;
+	if (phase_clk && lane == 0) {
+		atomicAdd(&phase_clk[0], (unsigned long long)t_rehash); atomicAdd(&phase_clk[1], (unsigned long long)t_init);
+		atomicAdd(&phase_clk[2], (unsigned long long)t_put); atomicAdd(&phase_clk[3], (unsigned long long)t_mat);
 	}
+	if (trailing[t] && R.count >= (R.n >> 1) + (R.n >> 2)) warp_resize(R, R.n + 1, wcache, lane); // quirk Q3
+	if (lane == 0) { out_cap[t] = R.n; out_size[t] = R.count; }
 	__syncwarp();
 	// in-place compaction to slot order (r <= i), cooperatively
 	const uint32_t n = __shfl_sync(0xffffffffu, R.n, 0);
@@ -1669,8 +1770,18 @@ template<class F> void Engine::layout_batches(int s0, int s1, bool with_counts, 
 				for (auto &seg : journal)
 					gather_seg_kernel<<<(uint32_t)lists[4].size(), 256, 0, stream>>>(seg.keys, seg.off, s0 + b0, d_list + start[4], (int)lists[4].size(), d_catoff, d_run, d_cat); }
 				ProfScope ps("layout(warp replay)", stream);
+				unsigned long long *d_clk = nullptr; // YAKB_LAYOUT_CLOCKS=1: cycles per phase of the warp replay, summed over sub-tables
+				static const bool want_clk = getenv("YAKB_LAYOUT_CLOCKS") != nullptr;
+				if (want_clk) { d_clk = (unsigned long long*)b_stats.need(8 * sizeof(unsigned long long)) + 4; YAKB_CUDA(cudaMemsetAsync(d_clk, 0, 32, stream)); }
 				build_layout_warp_kernel<<<(uint32_t)lists[4].size(), 32, 0, stream>>>(d_list + start[4], d_cat, d_catoff, d_pf, d_pv, d_trail,
-				                                                                       d_out, d_ooff, d_bm, d_boff, d_own, d_ocap, d_osize);
+				                                                                       d_out, d_ooff, d_bm, d_boff, d_own, d_ocap, d_osize, d_clk);
+				if (want_clk) {
+					unsigned long long h_clk[4];
+					YAKB_CUDA(cudaMemcpyAsync(h_clk, d_clk, 32, cudaMemcpyDeviceToHost, stream));
+					YAKB_CUDA(cudaStreamSynchronize(stream));
+					fprintf(stderr, "[T::layout warp replay] %zu sub-tables, cycles per sub-table: rehash %.0f, init %.0f, put %.0f, materialise %.0f\n", lists[4].size(),
+					        (double)h_clk[0] / lists[4].size(), (double)h_clk[1] / lists[4].size(), (double)h_clk[2] / lists[4].size(), (double)h_clk[3] / lists[4].size());
+				}
 			}
 			YAKB_CUDA(cudaGetLastError());
 			YAKB_CUDA(cudaStreamSynchronize(stream)); // `all` must outlive the copy
@@ -1795,11 +1906,22 @@ void Engine::shrink(int min, int max)
 	rebuild_dev(caps, off, d_kept);
 }
 
+// empty the count table for a rebuild; the allocation is kept when it is large enough for the new content
+// (freeing and re-allocating tens of gigabytes costs more than the rebuild itself)
+void Engine::reset_table(const std::vector<uint64_t> &off)
+{
+	uint64_t mx = 8;
+	for (int s = 0; s < P; ++s) mx = std::max<uint64_t>(mx, off[s + 1] - off[s]);
+	const uint64_t want = ((uint64_t)(mx / load_limit) + 16 + 3) & ~3ull;
+	if (slots && cap >= want) YAKB_CUDA(cudaMemsetAsync(slots, 0xFF, (uint64_t)P * cap * 8, stream));
+	else if (slots) { dev_free(slots); slots = nullptr; cap = 0; }
+}
+
 void Engine::rebuild(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys)
 {
 	// drop the old table and journal, start again from the given keys
 	journal_free_all();
-	if (slots) { dev_free(slots); slots = nullptr; cap = 0; }
+	reset_table(off);
 	YAKB_CUDA(cudaMemsetAsync(last_put, 0, P * 8, stream));
 	YAKB_CUDA(cudaMemsetAsync(last_new, 0, P * 8, stream));
 	load_subtables(caps, off, keys);
@@ -1809,7 +1931,7 @@ void Engine::rebuild(const std::vector<uint32_t> &caps, const std::vector<uint64
 void Engine::rebuild_dev(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *d_keys)
 {
 	journal_free_all();
-	if (slots) { dev_free(slots); slots = nullptr; cap = 0; }
+	reset_table(off);
 	YAKB_CUDA(cudaMemsetAsync(last_put, 0, P * 8, stream));
 	YAKB_CUDA(cudaMemsetAsync(last_new, 0, P * 8, stream));
 	load_subtables(caps, off, d_keys, true);

@@ -130,6 +130,7 @@ private:
 	ChunkStats finish_chunk(uint64_t n_words, int create_new, const uint64_t *w2, const uint32_t *wm,
 	                        const uint64_t *d_ev, uint64_t n_units, int only_s, bool ignore_bloom = false);
 	void grow(uint32_t new_cap);
+	void reset_table(const std::vector<uint64_t> &off);
 };
 
 // lookups for qv (qv.c:34-86): per position count (-1 = no k-mer event there), device in/out
