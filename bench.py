@@ -359,6 +359,7 @@ def main():
         lib.yak_ch_destroy(h)
     else:
         be.close()
+    lib.yakb_device_cache_trim()   # the library keeps freed device blocks for its next table; the legs below start clean
     del buf
     torch.cuda.empty_cache()
     if world > 1:  # every rank leaves the process group together; the legs below are rank 0's alone
@@ -397,6 +398,12 @@ def main():
                 "random_rmw": {"achieved_gops": (ev_total / (tms / 1000.0) / 1e9) if nm.startswith("k1_") and tms > 0 else None,
                                "peak_gops": 14.7, "unit": "G read-modify-writes/s"},
                 "share_of_step": tms / ms if ms > 0 else None}
+    # the whole step against the same peak, by SURVEY 8(d)'s fixed accounting for pass 1 with a filter
+    # (extract 8.31 + insert 24 + bloom block 128 = 160.3 B per k-mer event, whatever the implementation skips)
+    roof_step = {"bound": "hbm", "achieved": ALG["pass1_bloom"] * ev_all / (ms / 1000.0) / 1e9 / world, "peak": peak, "unit": "GB/s",
+                 "algorithmic_bytes_per_event": ALG["pass1_bloom"], "per": "GPU"} if args.bf_shift > PRE else None
+    if roof_step:
+        roof_step["frac"] = roof_step["achieved"] / peak
     line = {"metric": f"k-mer events/s (k={K}, pass 1 of `yak count -b{args.bf_shift}`, chunk steps)", "value": value, "unit": "events/s",
             "n_gpus": world, "steps": KS, "warmup": W, "ms_per_step": ms / KS, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -406,7 +413,7 @@ def main():
                        "device_bytes": int(dev_bytes)},
             "input_gbp_per_s": (nr * L * KS * world) / (ms / 1000.0) / 1e9,
             "gpu_launches": int(launches), "kernels_ms": {k: round(v[0], 3) for k, v in prof.items()},
-            "clocks": clk, "roofline": roof}
+            "clocks": clk, "roofline": roof, "roofline_step": roof_step}
 
     # ---- e2e: the same metric (pass-1 events/s) through the reference-facing C call on a HOST file:
     #      yak_count(fn, opt, NULL) = parse + H2D + every kernel of the pass, result (h->tot) read back.

@@ -40,13 +40,20 @@ void cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 // ---- cached device memory (see dbuf.cuh)
 namespace {
 struct DevCache {
+	struct Key { int dev; size_t bytes; bool operator<(const Key &o) const { return dev != o.dev ? dev < o.dev : bytes < o.bytes; } };
 	std::mutex mu;
-	std::map<void*, size_t> live;                    // size of every block handed out
-	std::multimap<size_t, void*> idle;               // freed blocks by size
+	std::map<void*, Key> live;                       // device and size of every block handed out
+	std::multimap<Key, void*> idle;                  // freed blocks by (device, size)
 	size_t idle_bytes = 0;
 	size_t limit() { static size_t v = 0; if (!v) { const char *e = getenv("YAKB_CACHE_GB"); v = (size_t)(e ? atof(e) : 48.0) << 30; if (!v) v = 1; } return v; }
 	bool enabled() { static int v = -1; if (v < 0) v = getenv("YAKB_NO_POOL") ? 0 : 1; return v != 0; }
-	void drop_all() { for (auto &kv : idle) cudaFree(kv.second); idle.clear(); idle_bytes = 0; }
+	void drop(std::multimap<Key, void*>::iterator it) // cudaFree works on any device's pointer
+	{
+		cudaFree(it->second);
+		idle_bytes -= it->first.bytes;
+		idle.erase(it);
+	}
+	void drop_all() { while (!idle.empty()) drop(idle.begin()); }
 };
 DevCache g_dc;
 }
@@ -55,12 +62,14 @@ void *dev_alloc(size_t bytes)
 	void *p = nullptr;
 	bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
 	if (!g_dc.enabled()) { YAKB_CUDA(cudaMalloc(&p, bytes)); return p; }
+	int dev = 0;
+	cudaGetDevice(&dev);
 	std::lock_guard<std::mutex> lk(g_dc.mu);
-	auto it = g_dc.idle.lower_bound(bytes); // smallest idle block that is large enough, if it is not wastefully large
-	if (it != g_dc.idle.end() && it->first <= bytes + (bytes >> 2) + (1u << 20)) {
+	auto it = g_dc.idle.lower_bound({dev, bytes}); // smallest idle block of this device that is large enough, if it is not wastefully large
+	if (it != g_dc.idle.end() && it->first.dev == dev && it->first.bytes <= bytes + (bytes >> 2) + (1u << 20)) {
 		p = it->second;
 		g_dc.live[p] = it->first;
-		g_dc.idle_bytes -= it->first;
+		g_dc.idle_bytes -= it->first.bytes;
 		g_dc.idle.erase(it);
 		return p;
 	}
@@ -72,7 +81,7 @@ void *dev_alloc(size_t bytes)
 		e = cudaMalloc(&p, bytes);
 	}
 	YAKB_CUDA(e);
-	g_dc.live[p] = bytes;
+	g_dc.live[p] = {dev, bytes};
 	return p;
 }
 void dev_free(void *p)
@@ -83,15 +92,14 @@ void dev_free(void *p)
 	std::lock_guard<std::mutex> lk(g_dc.mu);
 	auto it = g_dc.live.find(p);
 	if (it == g_dc.live.end()) { cudaFree(p); return; }
-	const size_t bytes = it->second;
+	const DevCache::Key key = it->second;
 	g_dc.live.erase(it);
-	g_dc.idle.insert({bytes, p});
-	g_dc.idle_bytes += bytes;
-	while (g_dc.idle_bytes > g_dc.limit() && !g_dc.idle.empty()) { // keep the hoard bounded: largest blocks go first
-		auto last = std::prev(g_dc.idle.end());
-		cudaFree(last->second);
-		g_dc.idle_bytes -= last->first;
-		g_dc.idle.erase(last);
+	g_dc.idle.insert({key, p});
+	g_dc.idle_bytes += key.bytes;
+	while (g_dc.idle_bytes > g_dc.limit() && !g_dc.idle.empty()) { // keep the hoard bounded: the largest block goes first
+		auto big = g_dc.idle.begin();
+		for (auto i = g_dc.idle.begin(); i != g_dc.idle.end(); ++i) if (i->first.bytes > big->first.bytes) big = i;
+		g_dc.drop(big);
 	}
 }
 size_t dev_pool_idle()
