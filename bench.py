@@ -362,6 +362,40 @@ def main():
     lib.yakb_device_cache_trim()   # the library keeps freed device blocks for its next table; the legs below start clean
     del buf
     torch.cuda.empty_cache()
+    e2e_multi = None
+    if world > 1 and not args.no_e2e:
+        # e2e at N GPUs: the same pass-1 metric from a FASTQ file on the host through the sharded file path
+        # (yak_b200/dist.py count_file_sharded: every rank parses the file with the library's parser pool, keeps its
+        # contiguous part of every batch, H2D, extraction, one NCCL all-to-all per batch, count on its shard)
+        from yak_b200 import dist as ydist
+        fn = os.path.join(shm_dir(), f"yakb_bench_e2e_{os.environ.get('MASTER_PORT', '0')}.fq")
+        nev = torch.zeros(1, dtype=torch.int64, device="cuda")
+        if rank == 0:
+            nev[0] = make_sample_file(torch, lib, genome2, G, args.e2e_reads, 0, fn)
+        dist.broadcast(nev, 0)
+        batch = min(64 << 20, (512 << 20) // world) * world
+        os.environ.setdefault("YAKB_PARSE_THREADS", str(max(2, (os.cpu_count() or 2) // world)))  # N parser pools share the host
+        dt = 0.0
+        for rep in range(2):            # warm-up (pinned buffers, page cache), then the timed run
+            be2 = ydist.GpuBackend(K, PRE, args.bf_shift, NH, rank, world)
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.time()
+            sc2 = ydist.count_file_sharded(fn, be2, k=K, batch_bases=batch)
+            tot2 = sc2.total_distinct()  # the result every rank reads back
+            torch.cuda.synchronize()
+            dt = time.time() - t0
+            be2.close()
+        tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        if rank == 0:
+            os.unlink(fn)
+            e2e_multi = {"value": int(nev[0]) / float(tmax[0]), "unit": "events/s", "n_gpus_used": world,
+                         "h2d_bytes_per_step": args.e2e_reads * (L + 1), "d2h_bytes_per_step": 8 * world, "seconds": float(tmax[0]),
+                         "distinct_after_pass1": tot2,
+                         "what": f"pass 1 (-b{args.bf_shift}) of {args.e2e_reads} FASTQ reads in tmpfs on {world} GPUs: parse + H2D + extract + all-to-all + count, {int(nev[0])} events (max over ranks)"}
+        lib.yakb_device_cache_trim()
     if world > 1:  # every rank leaves the process group together; the legs below are rank 0's alone
         dist.barrier()
         dist.destroy_process_group()
@@ -419,7 +453,9 @@ def main():
     #      yak_count(fn, opt, NULL) = parse + H2D + every kernel of the pass, result (h->tot) read back.
     #      The whole `yak count -b37` job (both passes + shrink + dump) on the same file is reported next
     #      to it together with the unmodified reference's time for that job (cpu_baseline).
-    if not args.no_e2e:
+    if e2e_multi:
+        line["e2e"] = e2e_multi
+    elif not args.no_e2e:
         fn = os.path.join(shm_dir(), f"yakb_bench_{os.getpid()}.fq")
         n_ev = make_sample_file(torch, lib, genome2, G, args.e2e_reads, 0, fn)
         out = os.path.join(shm_dir(), f"yakb_bench_{os.getpid()}.yak")

@@ -76,12 +76,12 @@ class OracleBackend:
         return (full[:16] if with_header else b"") + full[start:off]
 
 
-def _worker(rank, world, port, fn, k, pre, b, out):
+def _worker(rank, world, port, fn, k, pre, b, out, batch_bases=0):
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     from yak_b200 import dist as yd
     be = OracleBackend(k, pre, b, 4, rank, world)
-    sc = yd.count_file_sharded(fn, be, records_per_chunk=1000, k=k, two_pass=b > 0)
+    sc = yd.count_file_sharded(fn, be, records_per_chunk=1000, k=k, two_pass=b > 0, batch_bases=batch_bases)
     tot = sc.total_distinct()
     data = sc.dump_bytes()
     if rank == 0:
@@ -109,3 +109,17 @@ def test_sharded_count_equals_single_table(world, k, pre, b):
     assert got == want, util.explain_diff(got, want)
     assert int(open(out + ".tot").read()) == h.contents.tot
     O.lib().yo_ch_destroy(h)
+
+
+@pytest.mark.parametrize("world,k,pre,b,batch", [(2, 31, 12, 0, 5000), (2, 31, 10, 20, 100_000), (4, 21, 11, 21, 20_000)])
+def test_sharded_count_through_the_parser_pool(world, k, pre, b, batch):
+    """the fast file path of N>1 (bench.py's e2e at N GPUs): every rank parses the same batches with the library's
+    parser pool and keeps its contiguous part of each; same bytes as a single-table count"""
+    fn = G.input_path("reads_q")
+    out = os.path.join(util.TMP, f"yakb_distpool_{world}_{k}_{pre}_{b}.yak")
+    mp.spawn(_worker, args=(world, _free_port(), fn, k, pre, b, out, batch), nprocs=world, join=True)
+    h, _ = O.count_file(fn, k=k, pre=pre, bf_shift=b)
+    want = O.dump_bytes(h)
+    got = open(out, "rb").read()
+    assert got == want, util.explain_diff(got, want)
+    assert int(open(out + ".tot").read()) == h.contents.tot

@@ -12,7 +12,7 @@ import util
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, fn, k, pre, b, out):
+def _worker(rank, world, port, fn, k, pre, b, out, batch_bases=0):
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(rank)
@@ -20,7 +20,7 @@ def _worker(rank, world, port, fn, k, pre, b, out):
                             device_id=torch.device("cuda", rank))
     from yak_b200 import dist as yd
     be = yd.GpuBackend(k, pre, b, 4, rank, world)
-    sc = yd.count_file_sharded(fn, be, records_per_chunk=2000, k=k, two_pass=b > 0)
+    sc = yd.count_file_sharded(fn, be, records_per_chunk=2000, k=k, two_pass=b > 0, batch_bases=batch_bases)
     tot = sc.total_distinct()
     data = sc.dump_bytes()
     if rank == 0:
@@ -30,8 +30,8 @@ def _worker(rank, world, port, fn, k, pre, b, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,pre,b", [(31, 12, 0), (31, 10, 20), (47, 12, 0)])
-def test_nccl_sharded_count_equals_oracle(yakb, k, pre, b):
+@pytest.mark.parametrize("k,pre,b,batch", [(31, 12, 0, 0), (31, 10, 20, 0), (47, 12, 0, 0), (31, 12, 22, 60_000), (31, 10, 0, 1 << 20)])
+def test_nccl_sharded_count_equals_oracle(yakb, k, pre, b, batch):
     import torch
     import torch.multiprocessing as mp
     world = 1
@@ -42,7 +42,7 @@ def test_nccl_sharded_count_equals_oracle(yakb, k, pre, b):
     fn = G.input_path("reads_q")
     out = os.path.join(util.TMP, f"yakb_nccl_{k}_{pre}_{b}.yak")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(world, port, fn, k, pre, b, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, fn, k, pre, b, out, batch), nprocs=world, join=True)
     h, _ = O.count_file(fn, k=k, pre=pre, bf_shift=b)
     want = O.dump_bytes(h)
     got = open(out, "rb").read()

@@ -131,9 +131,77 @@ class ShardedCounter:
         return b"".join(parts) if self.rank == 0 else None
 
 
+def _slice_bounds(view: np.ndarray, n: int, G: int) -> list[int]:
+    """cut [0, n) of a "SEQ\nSEQ\n..." buffer into G contiguous parts at record boundaries, about equal in bytes"""
+    b = [0]
+    for r in range(1, G):
+        p = max(b[-1], r * n // G)
+        w = 1 << 12
+        while True:                       # last newline before p (records can be long: widen the window)
+            lo = max(b[-1], p - w)
+            hit = np.flatnonzero(view[lo:p] == 10)
+            if hit.size or lo == b[-1]:
+                break
+            w <<= 2
+        b.append(lo + int(hit[-1]) + 1 if hit.size else b[-1])
+    b.append(n)
+    return b
+
+
+def _count_file_sharded_pool(fn, sc: ShardedCounter, k, create_new, batch_bases, pinned):
+    """One pass over a plain file with the library's parser pool (csrc/fastx_par.cpp): every rank parses the same
+    batches (the parse is deterministic, so no message is needed to agree on them), keeps the r-th of G contiguous
+    parts of each, and ships only that part to its GPU.  False if the pool cannot read this file (gzip, stdin)."""
+    import threading
+    from . import capi
+    L = capi.lib()
+    rd = L.yakb_pfastx_open(fn.encode(), 0, 0)
+    if not rd:
+        return False
+    cap = batch_bases + (batch_bases >> 4) + 4096
+    bufs = []
+    for _ in range(2):
+        t = torch.empty(cap, dtype=torch.uint8, pin_memory=True) if pinned else torch.empty(cap, dtype=torch.uint8)
+        bufs.append(t)
+    state = [None, None]
+
+    def fill(slot):
+        ns, done, need = C.c_int64(), C.c_int(), C.c_uint64()
+        n = L.yakb_pfastx_fill(rd, bufs[slot].data_ptr(), cap, batch_bases, k, C.byref(ns), C.byref(done), C.byref(need))
+        state[slot] = (int(n), bool(done.value), int(need.value))
+
+    try:
+        slot = 0
+        fill(0)
+        while True:
+            n, done, need = state[slot]
+            if need:
+                raise RuntimeError("a record larger than the staging buffer; raise batch_bases")
+            th = None
+            if not done:                  # the pool parses the next batch while this one is on the device
+                th = threading.Thread(target=fill, args=(slot ^ 1,))
+                th.start()
+            src = bufs[slot] if pinned else bufs[slot].numpy()     # a pinned tensor slice goes to the device by DMA
+            if n:
+                b = _slice_bounds(bufs[slot].numpy(), n, sc.world)
+                sc.count_chunk(src[b[sc.rank]:b[sc.rank + 1]], create_new)
+            elif sc.world > 1:
+                sc.count_chunk(src[:0], create_new)   # an empty last batch still takes part in the all-to-all
+            if th:
+                th.join()
+            if done:
+                break
+            slot ^= 1
+    finally:
+        L.yakb_pfastx_close(rd)
+    return True
+
+
 def count_file_sharded(fn: str, backend, records_per_chunk: int = 1 << 20, k: int = 31, two_pass: bool = False,
-                       fn2: str | None = None, group=None) -> ShardedCounter:
-    """`yak count` of one shared file on all ranks: every rank walks the file and keeps its slice."""
+                       fn2: str | None = None, group=None, batch_bases: int = 0) -> ShardedCounter:
+    """`yak count` of one shared file on all ranks.  batch_bases > 0: plain files go through the parser pool, each
+    rank keeping its contiguous part of every batch (the fast path, bench.py's e2e at N GPUs); otherwise, and for
+    gzip / stdin, every rank walks the file record by record and keeps its slice of every chunk."""
     from . import capi
     L = capi.lib()
     sc = ShardedCounter(backend, group)
@@ -141,6 +209,8 @@ def count_file_sharded(fn: str, backend, records_per_chunk: int = 1 << 20, k: in
     per = max(1, records_per_chunk // G)
 
     def one_pass(path, create_new):
+        if batch_bases > 0 and _count_file_sharded_pool(path, sc, k, create_new, batch_bases, sc._dev().type == "cuda"):
+            return
         rd = L.yakb_fastx_open(path.encode())
         if not rd:
             raise FileNotFoundError(path)
