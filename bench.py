@@ -365,8 +365,8 @@ def main():
     e2e_multi = None
     if world > 1 and not args.no_e2e:
         # e2e at N GPUs: the same pass-1 metric from a FASTQ file on the host through the sharded file path
-        # (yak_b200/dist.py count_file_sharded: every rank parses the file with the library's parser pool, keeps its
-        # contiguous part of every batch, H2D, extraction, one NCCL all-to-all per batch, count on its shard)
+        # (yak_b200/dist.py count_file_sharded: rank 0's parser pool fills a shared-memory staging buffer, every rank takes
+        # its contiguous part of every batch: H2D, extraction, one NCCL all-to-all per batch, count on its shard)
         from yak_b200 import dist as ydist
         fn = os.path.join(shm_dir(), f"yakb_bench_e2e_{os.environ.get('MASTER_PORT', '0')}.fq")
         nev = torch.zeros(1, dtype=torch.int64, device="cuda")
@@ -374,7 +374,6 @@ def main():
             nev[0] = make_sample_file(torch, lib, genome2, G, args.e2e_reads, 0, fn)
         dist.broadcast(nev, 0)
         batch = min(64 << 20, (512 << 20) // world) * world
-        os.environ.setdefault("YAKB_PARSE_THREADS", str(max(2, (os.cpu_count() or 2) // world)))  # N parser pools share the host
         dt = 0.0
         for rep in range(2):            # warm-up (pinned buffers, page cache), then the timed run
             be2 = ydist.GpuBackend(K, PRE, args.bf_shift, NH, rank, world)

@@ -131,6 +131,9 @@ class ShardedCounter:
         return b"".join(parts) if self.rank == 0 else None
 
 
+_STAGES: dict = {}
+
+
 def _slice_bounds(view: np.ndarray, n: int, G: int) -> list[int]:
     """cut [0, n) of a "SEQ\nSEQ\n..." buffer into G contiguous parts at record boundaries, about equal in bytes"""
     b = [0]
@@ -148,60 +151,88 @@ def _slice_bounds(view: np.ndarray, n: int, G: int) -> list[int]:
     return b
 
 
-def _count_file_sharded_pool(fn, sc: ShardedCounter, k, create_new, batch_bases, pinned):
-    """One pass over a plain file with the library's parser pool (csrc/fastx_par.cpp): every rank parses the same
-    batches (the parse is deterministic, so no message is needed to agree on them), keeps the r-th of G contiguous
-    parts of each, and ships only that part to its GPU.  False if the pool cannot read this file (gzip, stdin)."""
+def _count_file_sharded_pool(fn, sc: ShardedCounter, k, create_new, batch_bases, group):
+    """One pass over a plain file with the library's parser pool (csrc/fastx_par.cpp).  Rank 0 parses - once, with all
+    the host's cores - into a staging buffer in shared memory that every rank of the node maps; per batch it broadcasts
+    the batch length, every rank cuts the batch into G contiguous parts at record boundaries (same arithmetic
+    everywhere), and ships only ITS part to its GPU.  While the ranks work on batch i, rank 0's pool already fills the
+    other half of the buffer with batch i+1 (a rank has read its part of batch i-1 before it entered that batch's
+    all-to-all, so the half is free).  False if the pool cannot read this file (gzip, stdin): the caller falls back."""
+    import os
+    import tempfile
     import threading
     from . import capi
     L = capi.lib()
-    rd = L.yakb_pfastx_open(fn.encode(), 0, 0)
-    if not rd:
-        return False
+    G, r, dev = sc.world, sc.rank, sc._dev()
     cap = batch_bases + (batch_bases >> 4) + 4096
-    bufs = []
-    for _ in range(2):
-        t = torch.empty(cap, dtype=torch.uint8, pin_memory=True) if pinned else torch.empty(cap, dtype=torch.uint8)
-        bufs.append(t)
+    rd = L.yakb_pfastx_open(fn.encode(), 0, 0) if r == 0 else None
+    ok = torch.tensor([1 if (r != 0 or rd) else 0], dtype=torch.int64, device=dev)
+    if G > 1:
+        dist.broadcast(ok, 0, group=group)
+    if int(ok[0]) == 0:
+        return False
+    stage_dir = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    stage = os.path.join(stage_dir, "yakb_stage_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getuid()))
+    mm = _STAGES.get((stage, cap))            # mapped (and page-locked for DMA) once per process, reused by later passes
+    fresh = torch.tensor([0 if mm is not None else 1], dtype=torch.int64, device=dev)
+    if G > 1:
+        dist.all_reduce(fresh, op=dist.ReduceOp.MAX, group=group)
+    if int(fresh[0]):
+        if r == 0:
+            with open(stage, "wb") as f:
+                f.truncate(2 * cap)
+        if G > 1:
+            dist.barrier(group=group)
+        mm = np.memmap(stage, dtype=np.uint8, mode="r+", shape=(2 * cap,))
+        if dev.type == "cuda":
+            torch.cuda.cudart().cudaHostRegister(mm.ctypes.data, 2 * cap, 0)   # best effort: pageable copies work too
+        _STAGES[(stage, cap)] = mm
+        if G > 1:
+            dist.barrier(group=group)
+        if r == 0:
+            os.unlink(stage)                  # the mappings keep the memory alive; nothing is left behind in /dev/shm
     state = [None, None]
 
     def fill(slot):
         ns, done, need = C.c_int64(), C.c_int(), C.c_uint64()
-        n = L.yakb_pfastx_fill(rd, bufs[slot].data_ptr(), cap, batch_bases, k, C.byref(ns), C.byref(done), C.byref(need))
-        state[slot] = (int(n), bool(done.value), int(need.value))
+        n = L.yakb_pfastx_fill(rd, mm.ctypes.data + slot * cap, cap, batch_bases, k, C.byref(ns), C.byref(done), C.byref(need))
+        state[slot] = (int(n), 1 if done.value else 0, int(need.value))
 
     try:
         slot = 0
-        fill(0)
+        if r == 0:
+            fill(0)
         while True:
-            n, done, need = state[slot]
+            hdr = torch.tensor(list(state[slot]) if r == 0 else [0, 0, 0], dtype=torch.int64, device=dev)
+            if G > 1:
+                dist.broadcast(hdr, 0, group=group)
+            n, done, need = (int(x) for x in hdr.tolist())
             if need:
                 raise RuntimeError("a record larger than the staging buffer; raise batch_bases")
             th = None
-            if not done:                  # the pool parses the next batch while this one is on the device
+            if r == 0 and not done:       # the pool parses the next batch while this one is on the devices
                 th = threading.Thread(target=fill, args=(slot ^ 1,))
                 th.start()
-            src = bufs[slot] if pinned else bufs[slot].numpy()     # a pinned tensor slice goes to the device by DMA
-            if n:
-                b = _slice_bounds(bufs[slot].numpy(), n, sc.world)
-                sc.count_chunk(src[b[sc.rank]:b[sc.rank + 1]], create_new)
-            elif sc.world > 1:
-                sc.count_chunk(src[:0], create_new)   # an empty last batch still takes part in the all-to-all
+            view = mm[slot * cap: slot * cap + n]
+            b = _slice_bounds(view, n, G)
+            sc.count_chunk(view[b[r]:b[r + 1]], create_new)   # also for an empty part: every rank joins every all-to-all
             if th:
                 th.join()
             if done:
                 break
             slot ^= 1
     finally:
-        L.yakb_pfastx_close(rd)
+        if rd:
+            L.yakb_pfastx_close(rd)
     return True
 
 
 def count_file_sharded(fn: str, backend, records_per_chunk: int = 1 << 20, k: int = 31, two_pass: bool = False,
                        fn2: str | None = None, group=None, batch_bases: int = 0) -> ShardedCounter:
-    """`yak count` of one shared file on all ranks.  batch_bases > 0: plain files go through the parser pool, each
-    rank keeping its contiguous part of every batch (the fast path, bench.py's e2e at N GPUs); otherwise, and for
-    gzip / stdin, every rank walks the file record by record and keeps its slice of every chunk."""
+    """`yak count` of one shared file on all ranks of ONE node.  batch_bases > 0: plain files are parsed once by rank 0's
+    parser pool into shared memory, each rank taking its contiguous part of every batch (the fast path, bench.py's e2e
+    at N GPUs); otherwise, and for gzip / stdin, every rank walks the file record by record and keeps its slice of
+    every chunk."""
     from . import capi
     L = capi.lib()
     sc = ShardedCounter(backend, group)
@@ -209,7 +240,7 @@ def count_file_sharded(fn: str, backend, records_per_chunk: int = 1 << 20, k: in
     per = max(1, records_per_chunk // G)
 
     def one_pass(path, create_new):
-        if batch_bases > 0 and _count_file_sharded_pool(path, sc, k, create_new, batch_bases, sc._dev().type == "cuda"):
+        if batch_bases > 0 and _count_file_sharded_pool(path, sc, k, create_new, batch_bases, group):
             return
         rd = L.yakb_fastx_open(path.encode())
         if not rd:
