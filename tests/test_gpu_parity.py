@@ -211,6 +211,25 @@ def test_restore_roundtrip_and_qv(oracle, yakb, reads_fa):
         assert list(t1) == list(t2) and list(z1) == list(z2)
         assert list(c1) == list(c2)
         assert sum(c1) > 0 or min_frac > 0.9
+    # yak_qv(file) without per-sequence output reads plain files through the parser pool, gzip through the sequential reader
+    import gzip
+    fa = os.path.join(util.TMP, "yakb_qv_ctg.fa")
+    with open(fa, "wb") as f:
+        f.write(synth.contigs_bytes(7, 200_000, 5, 40, 9_000, sub=2e-3, width=60) + b">short\nACGTACGT\n>n\n" + b"N" * 200 + b"\n")
+    with gzip.open(fa + ".gz", "wb") as f:
+        f.write(open(fa, "rb").read())
+    recs = [b"".join(r.split(b"\n")[1:]) for r in open(fa, "rb").read().split(b">")[1:]]
+    lens = (C.c_int64 * len(recs))(*[len(s) for s in recs])
+    for min_len in (0, 5000):
+        qo = yakb.YakQopt()
+        L.yak_qopt_init(C.byref(qo))
+        qo.min_len = min_len
+        want = (C.c_int64 * 1024)()
+        OL.yo_qv_seqs(ho2, len(recs), lens, b"".join(recs), min_len, qo.min_frac, want, None, None)
+        for path in (fa, fa + ".gz"):
+            got = (C.c_int64 * 1024)()
+            L.yak_qv(C.byref(qo), path.encode(), hg, got)
+            assert list(got) == list(want) and sum(want) > 100_000, (path, min_len)
     L.yak_ch_destroy(hg); OL.yo_ch_destroy(ho); OL.yo_ch_destroy(ho2)
 
 

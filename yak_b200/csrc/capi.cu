@@ -22,6 +22,7 @@
 #include <thread>
 #include <atomic>
 #include <chrono>
+#include <memory>
 #include <sys/resource.h>
 #include <sys/time.h>
 
@@ -857,8 +858,12 @@ static void qv_batch(ChBox *b, const uint8_t *cat, uint64_t n, const std::vector
 	int32_t *d_tot = (int32_t*)(base + o_tot), *d_non0 = (int32_t*)(base + o_non0);
 	uint8_t *d_pass = base + o_pass;
 	YAKB_CUDA(cudaMemcpyAsync(d_off, seq_off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+	const double tb0 = wall_now();
+	if (timing_on()) YAKB_CUDA(cudaStreamSynchronize(e->stream));
+	const double tb1 = wall_now();
 	qv_scan_ascii(e, d, n, d_cnt);
-	qv_stats(d_cnt, d_off, n_seq, min_len, min_frac, d_tot, d_non0, d_pass, d_hist, e->stream);
+	if (timing_on()) fprintf(stderr, "[T::qv_batch] H2D %.4f s, pack + scan %.4f s\n", tb1 - tb0, wall_now() - tb1);
+	qv_stats(d_cnt, d_off, n_seq, n, min_len, min_frac, d_tot, d_non0, d_pass, d_hist, e->stream);
 	if (tot) YAKB_CUDA(cudaMemcpyAsync(tot, d_tot, n_seq * 4, cudaMemcpyDeviceToHost, e->stream));
 	if (non0) YAKB_CUDA(cudaMemcpyAsync(non0, d_non0, n_seq * 4, cudaMemcpyDeviceToHost, e->stream));
 	if (cnt_back) { cnt_back->resize(n); YAKB_CUDA(cudaMemcpyAsync(cnt_back->data(), d_cnt, n * 2, cudaMemcpyDeviceToHost, e->stream)); }
@@ -940,11 +945,44 @@ extern "C" void yak_qv(const yak_qopt_t *opt, const char *fn, const yak_ch_t *ch
 	std::lock_guard<std::mutex> lk(b->mu);
 	assert(ch->k < 32); // qv.c:43
 	memset(cnt, 0, YAK_N_COUNTS * sizeof(int64_t));
-	FastxReader rd;
-	if (!rd.open(fn)) return;
 	unsigned long long *d_hist = (unsigned long long*)b->d_aux2.need(1024 * 8);
 	YAKB_CUDA(cudaMemsetAsync(d_hist, 0, 1024 * 8, b->eng->stream));
 	const uint64_t cap = std::min<uint64_t>(batch_bases(0), (uint64_t)std::max<int64_t>(opt->chunk_size, 1));
+	// Without per-sequence output nothing needs the names: plain files then come through the parser pool as
+	// "SEQ\n" batches (sequences shorter than min_len take no part in anything, qv.c:44, so the pool may drop them)
+	ParallelFastx prd;
+	if (!opt->print_each && !opt->print_err_kmer && !getenv("YAKB_SERIAL_PARSE") && prd.open(fn)) {
+		size_t pcap = cap + (cap >> 4) + 4096;
+		std::unique_ptr<uint8_t[]> pbuf(new uint8_t[pcap]); // not a vector: no need to zero 68 MB first
+		bool pdone = false;
+		const int min_len = std::max(opt->min_len, 0);
+		while (!pdone) {
+			int64_t n_seq = 0;
+			size_t need = 0;
+			const double tq0 = wall_now();
+			const size_t n = prd.fill(pbuf.get(), pcap, cap, min_len, &n_seq, &pdone, &need);
+			const double tq1 = wall_now();
+			if (need) { pcap = need + (need >> 3) + 4096; pbuf.reset(new uint8_t[pcap]); continue; }
+			if (n == 0) continue;
+			std::vector<uint64_t> off(1, 0);
+			off.reserve((size_t)n_seq + 1);
+			for (const uint8_t *p = pbuf.get(), *e = p + n; p < e; ) { // one '\n' ends every sequence
+				const uint8_t *nl = (const uint8_t*)memchr(p, '\n', e - p);
+				p = nl ? nl + 1 : e;
+				off.push_back((uint64_t)(p - pbuf.get()));
+			}
+			fprintf(stderr, "[M::%s] read %d sequences\n", "yak_qv_cb", (int)n_seq);
+			const double tq2 = wall_now();
+			qv_batch(b, pbuf.get(), n, off, opt->min_len, opt->min_frac, d_hist, nullptr, nullptr, nullptr);
+			if (timing_on()) fprintf(stderr, "[T::yak_qv] batch of %zu bytes: parse %.4f s, offsets %.4f s, device %.4f s\n", n, tq1 - tq0, tq2 - tq1, wall_now() - tq2);
+			fprintf(stderr, "[M::%s@%.2f*%.2f] processed %d sequences\n", "yak_qv_cb", wall_now() - g_t0, cpu_now() / (wall_now() - g_t0 + 1e-6), (int)n_seq);
+		}
+		YAKB_CUDA(cudaMemcpyAsync(cnt, d_hist, 1024 * 8, cudaMemcpyDeviceToHost, b->eng->stream));
+		YAKB_CUDA(cudaStreamSynchronize(b->eng->stream));
+		return;
+	}
+	FastxReader rd;
+	if (!rd.open(fn)) return;
 	bool done = false;
 	std::vector<uint8_t> buf;
 	std::vector<std::string> names;

@@ -95,47 +95,77 @@ int extract_events(const uint8_t *d_asc, uint64_t n, int k, int pre, int world, 
 
 // ---- qv.c:44-85 per sequence: tot / non0 and the min_frac gate.  One warp per sequence.
 //      seq_off[s] = offset of sequence s in the position array; its last position is a separator.
-__global__ void __launch_bounds__(256) qv_seq_stats_kernel(const int16_t *__restrict__ cnt, const uint64_t *__restrict__ seq_off, uint64_t n_seq,
-                                                           int min_len, double min_frac, int32_t *__restrict__ tot, int32_t *__restrict__ non0,
-                                                           uint8_t *__restrict__ pass)
+// Both kernels walk POSITIONS, not sequences (a warp per sequence leaves 50 warps busy on an assembly of 50 contigs):
+// a warp takes 1024 consecutive positions, every lane tracks the sequence its position lies in, and lanes of the
+// same sequence combine their flags with votes before one atomic per (warp step, sequence).
+__device__ __forceinline__ uint64_t seq_of(const uint64_t *__restrict__ seq_off, uint64_t n_seq, uint64_t p)
 {
-	const uint64_t s = (blockIdx.x * 256ull + threadIdx.x) >> 5;
+	uint64_t lo = 0, hi = n_seq; // sequence s with seq_off[s] <= p < seq_off[s+1]
+	while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (seq_off[mid] <= p) lo = mid; else hi = mid; }
+	return lo;
+}
+
+__global__ void __launch_bounds__(256) qv_pos_stats_kernel(const int16_t *__restrict__ cnt, const uint64_t *__restrict__ seq_off, uint64_t n_seq,
+                                                           uint64_t n, int min_len, int32_t *tot, int32_t *non0)
+{
 	const int lane = threadIdx.x & 31;
-	if (s >= n_seq) return;
-	const uint64_t b = seq_off[s], e = seq_off[s + 1] - 1;
-	int t = 0, z = 0;
-	if ((int64_t)(e - b) >= min_len)
-		for (uint64_t p = b + lane; p < e; p += 32) { int c = cnt[p]; t += c >= 0; z += c > 0; }
-#pragma unroll
-	for (int d = 16; d; d >>= 1) { t += __shfl_xor_sync(0xffffffffu, t, d); z += __shfl_xor_sync(0xffffffffu, z, d); }
-	if (lane == 0) {
-		tot[s] = t; non0[s] = z;
-		pass[s] = (int64_t)(e - b) >= min_len && !((double)z < (double)t * min_frac);
+	const uint64_t base = ((blockIdx.x * 256ull + threadIdx.x) >> 5) * 1024;
+	if (base >= n) return;
+	uint64_t s = seq_of(seq_off, n_seq, min(base + lane, n - 1));
+	for (int it = 0; it < 32; ++it) {
+		const uint64_t p = base + it * 32 + lane;
+		const bool in = p < n;
+		if (in) while (p >= seq_off[s + 1]) ++s;
+		int c = -1;
+		if (in && p + 1 < seq_off[s + 1] && (int64_t)(seq_off[s + 1] - 1 - seq_off[s]) >= min_len) c = cnt[p]; // not the separator; qv.c:44
+		const uint32_t peers = __match_any_sync(0xffffffffu, in ? s : ~0ull);
+		const uint32_t tb = __ballot_sync(0xffffffffu, c >= 0) & peers, zb = __ballot_sync(0xffffffffu, c > 0) & peers;
+		if (in && lane == __ffs(peers) - 1) {
+			if (tb) atomicAdd(&tot[s], __popc(tb));
+			if (zb) atomicAdd(&non0[s], __popc(zb));
+		}
 	}
 }
 
-__global__ void __launch_bounds__(256) qv_hist_kernel(const int16_t *__restrict__ cnt, const uint64_t *__restrict__ seq_off, uint64_t n_seq,
-                                                      const uint8_t *__restrict__ pass, unsigned long long *hist)
+__global__ void qv_pass_kernel(const uint64_t *__restrict__ seq_off, uint64_t n_seq, int min_len, double min_frac,
+                               const int32_t *__restrict__ tot, const int32_t *__restrict__ non0, uint8_t *__restrict__ pass)
+{
+	const uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (s >= n_seq) return;
+	const int64_t len = (int64_t)(seq_off[s + 1] - 1 - seq_off[s]);
+	pass[s] = len >= min_len && !((double)non0[s] < (double)tot[s] * min_frac); // qv.c:83
+}
+
+__global__ void __launch_bounds__(256) qv_pos_hist_kernel(const int16_t *__restrict__ cnt, const uint64_t *__restrict__ seq_off, uint64_t n_seq,
+                                                          uint64_t n, const uint8_t *__restrict__ pass, unsigned long long *hist)
 {
 	__shared__ uint32_t s_h[1024];
 	for (int i = threadIdx.x; i < 1024; i += 256) s_h[i] = 0;
 	__syncthreads();
 	const int lane = threadIdx.x & 31;
-	for (uint64_t s = (blockIdx.x * 256ull + threadIdx.x) >> 5; s < n_seq; s += (gridDim.x * 256ull) >> 5) {
-		if (!pass[s]) continue;
-		const uint64_t b = seq_off[s], e = seq_off[s + 1] - 1;
-		for (uint64_t p = b + lane; p < e; p += 32) { int c = cnt[p]; if (c >= 0) atomicAdd(&s_h[c], 1u); }
+	for (uint64_t base = ((blockIdx.x * 256ull + threadIdx.x) >> 5) * 1024; base < n; base += ((gridDim.x * 256ull) >> 5) * 1024) {
+		uint64_t s = seq_of(seq_off, n_seq, min(base + lane, n - 1));
+		for (int it = 0; it < 32; ++it) {
+			const uint64_t p = base + it * 32 + lane;
+			if (p >= n) break;
+			while (p >= seq_off[s + 1]) ++s;
+			if (p + 1 < seq_off[s + 1] && pass[s]) { const int c = cnt[p]; if (c >= 0) atomicAdd(&s_h[c], 1u); }
+		}
 	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < 1024; i += 256) if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
 }
 
-void qv_stats(const int16_t *d_cnt, const uint64_t *d_seq_off, uint64_t n_seq, int min_len, double min_frac,
+void qv_stats(const int16_t *d_cnt, const uint64_t *d_seq_off, uint64_t n_seq, uint64_t n, int min_len, double min_frac,
               int32_t *d_tot, int32_t *d_non0, uint8_t *d_pass, unsigned long long *d_hist, cudaStream_t stream)
 {
-	if (n_seq == 0) return;
-	qv_seq_stats_kernel<<<cdiv(n_seq * 32, 256), 256, 0, stream>>>(d_cnt, d_seq_off, n_seq, min_len, min_frac, d_tot, d_non0, d_pass);
-	qv_hist_kernel<<<std::min<uint32_t>(cdiv(n_seq * 32, 256), 148 * 8), 256, 0, stream>>>(d_cnt, d_seq_off, n_seq, d_pass, d_hist);
+	if (n_seq == 0 || n == 0) return;
+	YAKB_CUDA(cudaMemsetAsync(d_tot, 0, n_seq * 4, stream));
+	YAKB_CUDA(cudaMemsetAsync(d_non0, 0, n_seq * 4, stream));
+	const uint64_t n_warps = (n + 1023) / 1024;
+	qv_pos_stats_kernel<<<cdiv(n_warps * 32, 256), 256, 0, stream>>>(d_cnt, d_seq_off, n_seq, n, min_len, d_tot, d_non0);
+	qv_pass_kernel<<<cdiv(n_seq, 256), 256, 0, stream>>>(d_seq_off, n_seq, min_len, min_frac, d_tot, d_non0, d_pass);
+	qv_pos_hist_kernel<<<std::min<uint32_t>(cdiv(n_warps * 32, 256), 148 * 8), 256, 0, stream>>>(d_cnt, d_seq_off, n_seq, n, d_pass, d_hist);
 	YAKB_CUDA(cudaGetLastError());
 }
 
