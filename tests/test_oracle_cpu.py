@@ -374,6 +374,23 @@ def test_parallel_reader_pool_copies_and_parse_ahead():
             assert got == want and gn == wn, (block, threads, cap, target, redo)
 
 
+def test_parallel_reader_long_records_stay_linear():
+    """a chromosome-sized record spans hundreds of blocks; the open record is carried, not re-copied, block after block"""
+    import time
+    rng = np.random.default_rng(8)
+    big = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 24_000_000)])
+    p = os.path.join(util.TMP, "yakb_par_long.fa")
+    with open(p, "wb") as f:
+        f.write(b">one line\n" + big + b"\n>wrapped\r\n" + b"\r\n".join(big[i:i + 80] for i in range(0, 3_000_000, 80)) + b"\r\n>tail\nACGT")
+    want = big + b"\n" + big[:3_000_000] + b"\nACGT\n"
+    t0 = time.time()
+    got, gn, _ = _pfill_all(p, 64 << 10, 8, 64 << 20, 64 << 20, 0)
+    dt = time.time() - t0
+    assert got == want and gn == 3
+    assert _fill_all(p, 64 << 20, 64 << 20, 0)[0] == want
+    assert dt < 5.0, dt      # 24 MB in 64 KB blocks: quadratic re-copying took many seconds
+
+
 def test_bench_reference_arm_prints_one_json_line():
     """`bench.py --impl reference` (the CPU arm the driver runs) on a tiny bounded sample, here without a GPU"""
     import json

@@ -15,14 +15,20 @@
 namespace yakb {
 
 // ---------------------------------------------------------------- the grammar (kseq.h:192-232)
-// Sequence bytes go straight into `out`; `rs` marks where the open record starts there.  Between
-// calls the open record's bytes live in `rec` (they are few: at most one record per block).
+// Sequence bytes go straight into `out`; `rs` marks where this call's part of the open record starts there.
+// Between calls the open record's bytes live in `rec`, and they stay there while later calls add to the
+// record (a chromosome-sized sequence spans hundreds of blocks: moving it back and forth would be quadratic);
+// `rec` is spliced in front of out[rs..] once, when the record is closed.
 
-// close the record whose bytes are out[rs..]: keep it (terminator appended) or drop it
+// close the record whose bytes are rec + out[rs..]: keep it (terminator appended) or drop it
 static inline void close_in_out(FastxCore &c, size_t &rs, bool keep, int min_len, std::vector<uint8_t> &out, int64_t *n_seq)
 {
-	if (keep && c.cur_len >= min_len) { out.push_back('\n'); ++*n_seq; }
-	else out.resize(rs);
+	if (keep && c.cur_len >= min_len) {
+		if (!c.rec.empty()) out.insert(out.begin() + rs, c.rec.begin(), c.rec.end());
+		out.push_back('\n');
+		++*n_seq;
+	} else out.resize(rs);
+	c.rec.clear();
 	rs = out.size();
 	c.cur_len = 0;
 }
@@ -42,7 +48,6 @@ static inline void close_carried(FastxCore &c, bool keep, int min_len, std::vect
 void FastxCore::feed(const unsigned char *p, size_t n, int min_len, std::vector<uint8_t> &out, int64_t *n_seq)
 {
 	size_t i = 0, rs = out.size();
-	if (!rec.empty()) { out.insert(out.end(), rec.begin(), rec.end()); rec.clear(); }
 	while (i < n && !stopped) {
 		if (st == S_FIND) {
 			if (last) { st = S_NAME; last = 0; rs = out.size(); cur_len = 0; continue; } // header character consumed already
@@ -66,7 +71,13 @@ void FastxCore::feed(const unsigned char *p, size_t n, int min_len, std::vector<
 			out.insert(out.end(), p + i, p + i + len);
 			cur_len += (int64_t)len;
 			i += len + (nl ? 1 : 0);
-			if (nl) { if (cur_len > 1 && out.back() == '\r') { out.pop_back(); --cur_len; } bol = true; } // kseq.h:146
+			if (nl) { // kseq.h:146: a CR before the line end goes; the line's last byte may have arrived in an earlier call
+				if (cur_len > 1) {
+					if (out.size() > rs) { if (out.back() == '\r') { out.pop_back(); --cur_len; } }
+					else if (!rec.empty() && rec.back() == '\r') { rec.pop_back(); --cur_len; }
+				}
+				bol = true;
+			}
 		} else { // S_QUAL: only lengths matter
 			if (bol && qual_lines > 0 && qual_len >= cur_len) { // kseq.h:224
 				const bool ok = qual_len == cur_len;
@@ -87,10 +98,10 @@ void FastxCore::feed(const unsigned char *p, size_t n, int min_len, std::vector<
 		}
 	}
 	// park the open record's bytes until the next call
-	if (out.size() > rs) {
-		if (!stopped && (st == S_SEQ || st == S_PLUS || st == S_QUAL)) rec.assign((const char*)out.data() + rs, out.size() - rs);
-		out.resize(rs);
-	}
+	const bool open = !stopped && (st == S_SEQ || st == S_PLUS || st == S_QUAL);
+	if (open) { if (out.size() > rs) rec.append((const char*)out.data() + rs, out.size() - rs); }
+	else rec.clear();
+	out.resize(rs);
 }
 
 void FastxCore::settle(int min_len, std::vector<uint8_t> &out, int64_t *n_seq)
