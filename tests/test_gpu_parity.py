@@ -10,10 +10,10 @@ import util
 pytestmark = pytest.mark.gpu
 
 
-def _count_both(oracle, yakb, fn, k, pre, b, fn2=None):
+def _count_both(oracle, yakb, fn, k, pre, b, fn2=None, chunk_size=10_000_000):
     ho, ne = oracle.count_file(fn, k=k, pre=pre, bf_shift=b, fn2=fn2)
     ref = oracle.dump_bytes(ho)
-    hg = yakb.count_file(fn, k=k, pre=pre, bf_shift=b, fn2=fn2)
+    hg = yakb.count_file(fn, k=k, pre=pre, bf_shift=b, fn2=fn2, chunk_size=chunk_size)
     assert hg
     mine = yakb.dump_bytes(hg)
     return ho, hg, ref, mine, ne
@@ -55,8 +55,10 @@ def test_count_fastq_two_files(oracle, yakb, reads_fa, reads_fq):
 @pytest.mark.parametrize("b", [0, 22])
 def test_many_small_chunks(oracle, yakb, reads_fa, b, monkeypatch):
     # results must not depend on how the input is cut into batches
+    # (a batch is max(YAKB_BATCH, opt->chunk_size) bases: both must be small; 1 Mbp of reads in 20+ batches, and the
+    # parser pool hands each out in pieces of the staging buffer)
     monkeypatch.setenv("YAKB_BATCH", "50000")
-    ho, hg, ref, mine, _ = _count_both(oracle, yakb, reads_fa, 31, 12, b)
+    ho, hg, ref, mine, _ = _count_both(oracle, yakb, reads_fa, 31, 12, b, chunk_size=40_000)
     try:
         assert mine == ref, util.explain_diff(mine, ref)
     finally:
@@ -100,6 +102,23 @@ def test_edge_case_records(oracle, yakb, k, pre, b):
     finally:
         yakb.lib().yak_ch_destroy(hg)
         oracle.lib().yo_ch_destroy(ho)
+
+
+def test_record_larger_than_staging_buffer(oracle, yakb, monkeypatch):
+    """batches of 1000 bases against records of 20 and 45 kbp: yak_count grows its staging buffers and parses again"""
+    monkeypatch.setenv("YAKB_BATCH", "1000")
+    rng = np.random.default_rng(6)
+    fn = os.path.join(util.TMP, "yakb_bigrec.fa")
+    with open(fn, "w") as f:
+        for i, n in enumerate((300, 20_000, 150, 45_000, 31, 6000)):
+            f.write(f">r{i}\n" + "".join("ACGT"[j] for j in rng.integers(0, 4, n)) + "\n")
+    for b in (0, 20):
+        ho, hg, ref, mine, _ = _count_both(oracle, yakb, fn, 31, 10, b, chunk_size=1000)
+        try:
+            assert mine == ref, util.explain_diff(mine, ref)
+        finally:
+            yakb.lib().yak_ch_destroy(hg)
+            oracle.lib().yo_ch_destroy(ho)
 
 
 def test_empty_and_missing_input(yakb):
