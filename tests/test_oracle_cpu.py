@@ -389,6 +389,24 @@ def test_parallel_reader_long_records_stay_linear():
     assert got == want and gn == 3
     assert _fill_all(p, 64 << 20, 64 << 20, 0)[0] == want
     assert dt < 5.0, dt      # 24 MB in 64 KB blocks: quadratic re-copying took many seconds
+    # long FASTQ reads: blocks that lie inside a quality string look like sequence to the mid-record speculation and
+    # must be refused by the true state; quality characters include every character the grammar cares about
+    q = os.path.join(util.TMP, "yakb_par_long.fq")
+    with open(q, "wb") as f:
+        for i, n in enumerate((300_000, 70_000, 500, 1_000_000)):
+            seq = big[i * 1000:i * 1000 + n]
+            qual = bytes(np.frombuffer(b"@+>I#", dtype=np.uint8)[rng.integers(0, 5, n)])
+            if i == 1:   # multi-line sequence and quality (kseq allows both)
+                seq_txt = b"\n".join(seq[j:j + 100] for j in range(0, n, 100))
+                qual_txt = b"\n".join(qual[j:j + 7000] for j in range(0, n, 7000))
+            else:
+                seq_txt, qual_txt = seq, qual
+            f.write(b"@r%d\n" % i + seq_txt + b"\n+\n" + qual_txt + b"\n")
+    want_q, wn = _fill_all(q, 64 << 20, 64 << 20, 0)
+    assert wn == 4 and len(want_q) == 300_000 + 70_000 + 500 + 1_000_000 + 4
+    for block, threads in ((16 << 10, 8), (64 << 10, 3), (5000, 4)):
+        got, gn, _ = _pfill_all(q, block, threads, 64 << 20, 64 << 20, 0)
+        assert got == want_q and gn == wn, (block, threads)
 
 
 def test_bench_reference_arm_prints_one_json_line():

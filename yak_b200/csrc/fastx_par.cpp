@@ -158,6 +158,33 @@ static size_t guess_record_start(const unsigned char *p, size_t n, bool first_bl
 	return n;
 }
 
+// The bytes of p[0..n) read as the inside of a sequence (state S_SEQ of the grammar, kseq.h:206-213): line ends dropped,
+// a CR before a line end dropped too (kseq.h:146; the caller checks that the record already held two bases, the rule's
+// other condition).  False when anything else shows up - a line starting with '>', '@' or '+' - or when the first line
+// end's CR would sit in the previous block.
+static bool mid_sequence_parse(const unsigned char *p, size_t n, bool bol, BlockJob &j)
+{
+	j.mid.clear();
+	j.mid_bol_in = bol;
+	size_t i = 0;
+	while (i < n) {
+		if (bol) {
+			const unsigned char c = p[i];
+			if (c == '>' || c == '@' || c == '+') return false;
+			if (c == '\n') { ++i; continue; }
+			bol = false;
+		}
+		const unsigned char *nl = (const unsigned char*)memchr(p + i, '\n', n - i);
+		const size_t len = nl ? (size_t)(nl - (p + i)) : n - i;
+		if (len == 0 && i == 0) return false; // the line ended in the previous block: its CR, if any, is not ours to see
+		j.mid.insert(j.mid.end(), p + i, p + i + len);
+		i += len + (nl ? 1 : 0);
+		if (nl) { if (len > 0 && j.mid.back() == '\r') j.mid.pop_back(); bol = true; }
+	}
+	j.mid_bol_out = bol;
+	return true;
+}
+
 // ---------------------------------------------------------------- the pool
 
 struct CopyTask { const uint8_t *src; uint8_t *dst; size_t len; BlockJob *slot; };
@@ -255,6 +282,7 @@ bool ParallelFastx::work_one(std::unique_lock<std::mutex> &lk, bool may_parse)
 			j.out.clear();
 			j.nseq = 0; j.min_len = ml;
 			if (j.q < j.n) j.spec.feed(raw + j.q, j.n - j.q, ml, j.out, &j.nseq);
+			j.mid_ok = off > 0 && j.q >= 4096 && mid_sequence_parse(raw, j.q, raw[-1] == '\n', j);
 			lk.lock();
 			j.state = 2;
 			im.cv.notify_all();
@@ -294,7 +322,7 @@ size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len,
 		while (im.copies_open > 0) if (!work_one(lk, false)) im.cv.wait(lk);
 	};
 	uint64_t consumed = true_blocks_;
-	std::vector<uint8_t> gap;
+	std::vector<uint8_t> &gap = gap_; // a member: its capacity (a whole chromosome, at times) survives the call
 	for (;;) {
 		// hand over what a previous call could not place, whole records only
 		if (spill_pos_ < spill_.size()) {
@@ -343,13 +371,34 @@ size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len,
 		int64_t gs = 0;
 		bool queued = false;
 		gap.clear();
-		true_.feed(raw, j.q, min_len, gap, &gs); // the gap before the guess, with the true state
+		if (j.mid_ok && !true_.stopped && true_.st == FastxCore::S_SEQ && true_.bol == j.mid_bol_in && true_.cur_len >= 2) {
+			// the bytes before the guess continue an open sequence, as the worker assumed: take its bases
+			true_.rec.append((const char*)j.mid.data(), j.mid.size());
+			true_.cur_len += (int64_t)j.mid.size();
+			true_.bol = j.mid_bol_out;
+		} else true_.feed(raw, j.q, min_len, gap, &gs); // the gap before the guess, with the true state
 		if (j.q < j.n) {
 			true_.settle(min_len, gap, &gs);
 			if (j.min_len == min_len && true_.at_record_boundary()) { // the guess was a real record start: adopt the speculative result
-				if (true_.st == FastxCore::S_SEQ) close_carried(true_, true, min_len, gap, &gs);
+				if (true_.st == FastxCore::S_SEQ && true_.rec.size() >= (1u << 16) && true_.cur_len >= min_len && spill_.empty() &&
+				    n + gap.size() + true_.rec.size() + 1 <= cap) {
+					// a long carried record ends here: straight from the carry buffer to the caller's, not through `gap`
+					emit(gap.data(), gap.size(), gs);
+					gap.clear(); gs = 0;
+					memcpy(dst + n, true_.rec.data(), true_.rec.size());
+					n += true_.rec.size();
+					dst[n++] = '\n';
+					++*n_seq;
+					true_.rec.clear(); true_.cur_len = 0;
+				} else if (true_.st == FastxCore::S_SEQ) close_carried(true_, true, min_len, gap, &gs);
 				emit(gap.data(), gap.size(), gs);
-				true_ = std::move(j.spec); // before the slot can be handed back (a finished copy frees it)
+				{ // take over the speculative end state, but keep the carry buffer's capacity (it is freed otherwise, and the
+				  // next chromosome grows it again page fault by page fault)
+					std::string keep = std::move(true_.rec);
+					keep.assign(j.spec.rec);
+					true_ = std::move(j.spec); // before the slot can be handed back (a finished copy frees it)
+					true_.rec = std::move(keep);
+				}
 				if (j.out.size() >= (1u << 16) && spill_.empty() && n + j.out.size() <= cap) { // big: copied by the pool
 					std::lock_guard<std::mutex> lk(im.mu);
 					im.copyq.push_back({j.out.data(), dst + n, j.out.size(), &j});

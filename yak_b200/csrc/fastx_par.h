@@ -40,6 +40,11 @@ struct BlockJob {
 	FastxCore spec;               // state after the speculative parse
 	std::vector<uint8_t> out;     // its output
 	int64_t nseq = 0;
+	// second speculation, for the bytes before the guess (all of the block when it holds no record start, as inside a
+	// chromosome-sized sequence): "the block starts in the middle of a sequence".  mid_ok: [0, q) is nothing but sequence
+	// lines; mid = their bases; mid_bol_in / mid_bol_out = at a line start before / after them.
+	bool mid_ok = false, mid_bol_in = false, mid_bol_out = false;
+	std::vector<uint8_t> mid;
 };
 
 // Streaming design: the file is memory-mapped; a pool of workers parses blocks ahead of the consumer
@@ -69,6 +74,7 @@ private:
 	int threads_ = 1;
 	FastxCore true_;                 // exact parser state at the end of the last stitched block
 	std::vector<uint8_t> spill_;     // parsed output that did not fit the caller's buffer yet
+	std::vector<uint8_t> gap_;       // the stitcher's scratch
 	size_t spill_pos_ = 0;
 	int64_t spill_seq_ = 0;          // records inside spill_ not yet reported
 	bool finished_ = false;
