@@ -24,7 +24,7 @@ namespace yakb {
 static inline void close_in_out(FastxCore &c, size_t &rs, bool keep, int min_len, std::vector<uint8_t> &out, int64_t *n_seq)
 {
 	if (keep && c.cur_len >= min_len) {
-		if (!c.rec.empty()) out.insert(out.begin() + rs, c.rec.begin(), c.rec.end());
+		if (!c.rec.empty()) out.insert(out.begin() + rs, (const uint8_t*)c.rec.data(), (const uint8_t*)c.rec.data() + c.rec.size());
 		out.push_back('\n');
 		++*n_seq;
 	} else out.resize(rs);
@@ -37,7 +37,7 @@ static inline void close_in_out(FastxCore &c, size_t &rs, bool keep, int min_len
 static inline void close_carried(FastxCore &c, bool keep, int min_len, std::vector<uint8_t> &out, int64_t *n_seq)
 {
 	if (keep && c.cur_len >= min_len) {
-		out.insert(out.end(), c.rec.begin(), c.rec.end());
+		out.insert(out.end(), (const uint8_t*)c.rec.data(), (const uint8_t*)c.rec.data() + c.rec.size()); // same element type: one memmove
 		out.push_back('\n');
 		++*n_seq;
 	}
@@ -380,15 +380,14 @@ size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len,
 		if (j.q < j.n) {
 			true_.settle(min_len, gap, &gs);
 			if (j.min_len == min_len && true_.at_record_boundary()) { // the guess was a real record start: adopt the speculative result
-				if (true_.st == FastxCore::S_SEQ && true_.rec.size() >= (1u << 16) && true_.cur_len >= min_len && spill_.empty() &&
-				    n + gap.size() + true_.rec.size() + 1 <= cap) {
-					// a long carried record ends here: straight from the carry buffer to the caller's, not through `gap`
+				if (true_.st == FastxCore::S_SEQ && true_.rec.size() >= (1u << 16) && true_.cur_len >= min_len) {
+					// a long carried record ends here: straight from the carry buffer to where it goes, not through `gap`
 					emit(gap.data(), gap.size(), gs);
 					gap.clear(); gs = 0;
-					memcpy(dst + n, true_.rec.data(), true_.rec.size());
-					n += true_.rec.size();
-					dst[n++] = '\n';
-					++*n_seq;
+					const uint8_t *r = (const uint8_t*)true_.rec.data();
+					const size_t len = true_.rec.size();
+					if (spill_.empty() && n + len + 1 <= cap) { memcpy(dst + n, r, len); n += len; dst[n++] = '\n'; ++*n_seq; }
+					else { spill_.insert(spill_.end(), r, r + len); spill_.push_back('\n'); ++spill_seq_; }
 					true_.rec.clear(); true_.cur_len = 0;
 				} else if (true_.st == FastxCore::S_SEQ) close_carried(true_, true, min_len, gap, &gs);
 				emit(gap.data(), gap.size(), gs);
