@@ -54,11 +54,17 @@ ERR, NPCT = 0.005, 1
 ALG = {"extract": 0.31 + 8.0, "insert": 24.0, "bloom": 128.0, "pass1_bloom": 160.3, "plain": 32.3, "lookup": 8.31}
 
 
-def shm_dir():
+def shm_dir(need_bytes: int = 4 << 30):
+    """a directory in memory for the e2e sample file (and the reference's output), with room for it"""
     for d in ("/dev/shm", tempfile.gettempdir()):
-        if os.path.isdir(d) and os.access(d, os.W_OK):
-            return d
-    return "."
+        try:
+            if os.path.isdir(d) and os.access(d, os.W_OK):
+                st = os.statvfs(d)
+                if st.f_bavail * st.f_frsize >= need_bytes:
+                    return d
+        except OSError:
+            pass
+    return tempfile.gettempdir()
 
 
 class ClockSampler:

@@ -171,7 +171,17 @@ def _count_file_sharded_pool(fn, sc: ShardedCounter, k, create_new, batch_bases,
         dist.broadcast(ok, 0, group=group)
     if int(ok[0]) == 0:
         return False
-    stage_dir = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    use_shm = 0
+    if r == 0:
+        try:
+            st = os.statvfs("/dev/shm")
+            use_shm = int(os.access("/dev/shm", os.W_OK) and st.f_bavail * st.f_frsize >= 2 * cap + (64 << 20))
+        except OSError:
+            pass
+    where = torch.tensor([use_shm], dtype=torch.int64, device=dev)
+    if G > 1:
+        dist.broadcast(where, 0, group=group)     # one decision for the node
+    stage_dir = "/dev/shm" if int(where[0]) else tempfile.gettempdir()
     stage = os.path.join(stage_dir, "yakb_stage_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getuid()))
     mm = _STAGES.get((stage, cap))            # mapped (and page-locked for DMA) once per process, reused by later passes
     fresh = torch.tensor([0 if mm is not None else 1], dtype=torch.int64, device=dev)
