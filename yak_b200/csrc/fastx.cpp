@@ -9,10 +9,25 @@
 #include "fastx.h"
 #include <string.h>
 #include <ctype.h>
+#include <stdlib.h>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
 
 namespace yakb {
 
 static const size_t kBuf = 4u << 20;
+
+struct FastxReader::Ahead {
+	static const int N = 3;
+	std::vector<unsigned char> blk[N];
+	int64_t len[N];
+	int head = 0, count = 0;
+	bool done = false, stop = false; // done: the producer has delivered its last block
+	std::mutex mu;
+	std::condition_variable cv;
+	std::thread th;
+};
 
 bool FastxReader::open(const char *fn)
 {
@@ -22,13 +37,61 @@ bool FastxReader::open(const char *fn)
 	gzbuffer(fp_, 1u << 20);
 	buf_.resize(kBuf);
 	beg_ = end_ = 0; eof_ = false; last_ = 0;
+	if (!getenv("YAKB_NO_READAHEAD")) {
+		ahead_ = new Ahead;
+		Ahead *a = ahead_;
+		gzFile fp = fp_;
+		a->th = std::thread([a, fp]() {
+			for (int slot = 0;; slot = (slot + 1) % Ahead::N) {
+				{
+					std::unique_lock<std::mutex> lk(a->mu);
+					a->cv.wait(lk, [a] { return a->stop || a->count < Ahead::N; });
+					if (a->stop) return;
+				}
+				std::vector<unsigned char> &b = a->blk[slot];
+				b.resize(kBuf);
+				const int got = gzread(fp, b.data(), (unsigned)kBuf);
+				std::lock_guard<std::mutex> lk(a->mu);
+				a->len[slot] = got > 0 ? got : 0;
+				++a->count;
+				if (got < (int)kBuf) a->done = true; // a short read is the end (the same rule as the direct reads)
+				a->cv.notify_all();
+				if (a->done) return;
+			}
+		});
+	}
 	return true;
 }
 
 void FastxReader::close()
 {
+	if (ahead_) {
+		{ std::lock_guard<std::mutex> lk(ahead_->mu); ahead_->stop = true; }
+		ahead_->cv.notify_all();
+		if (ahead_->th.joinable()) ahead_->th.join();
+		delete ahead_;
+		ahead_ = nullptr;
+	}
 	if (fp_) gzclose(fp_);
 	fp_ = nullptr;
+}
+
+int64_t FastxReader::read_block_()
+{
+	if (!ahead_) {
+		const int got = gzread(fp_, buf_.data(), (unsigned)buf_.size());
+		return got > 0 ? got : 0;
+	}
+	Ahead *a = ahead_;
+	std::unique_lock<std::mutex> lk(a->mu);
+	a->cv.wait(lk, [a] { return a->count > 0 || a->done; });
+	if (a->count == 0) return 0;
+	buf_.swap(a->blk[a->head]);      // the parser owns the block now; the producer refills the other vector
+	const int64_t n = a->len[a->head];
+	a->head = (a->head + 1) % Ahead::N;
+	--a->count;
+	a->cv.notify_all();
+	return n;
 }
 
 int FastxReader::getc_()
@@ -36,9 +99,8 @@ int FastxReader::getc_()
 	if (beg_ >= end_) {
 		if (eof_) return -1;
 		beg_ = 0;
-		int got = gzread(fp_, buf_.data(), (unsigned)buf_.size());
-		end_ = got > 0 ? got : 0;
-		if (end_ < (int64_t)buf_.size()) eof_ = true;
+		end_ = read_block_();
+		if (end_ < (int64_t)kBuf) eof_ = true;
 		if (end_ == 0) return -1;
 	}
 	return buf_[beg_++];
@@ -51,9 +113,8 @@ bool FastxReader::line_(std::string &s, int64_t *count_only)
 		if (beg_ >= end_) {
 			if (eof_) break;
 			beg_ = 0;
-			int r = gzread(fp_, buf_.data(), (unsigned)buf_.size());
-			end_ = r > 0 ? r : 0;
-			if (end_ < (int64_t)buf_.size()) eof_ = true;
+			end_ = read_block_();
+			if (end_ < (int64_t)kBuf) eof_ = true;
 			if (end_ == 0) break;
 		}
 		got = true;
@@ -75,9 +136,8 @@ bool FastxReader::refill_()
 	if (beg_ < end_) return true;
 	if (eof_) return false;
 	beg_ = 0;
-	int got = gzread(fp_, buf_.data(), (unsigned)buf_.size());
-	end_ = got > 0 ? got : 0;
-	if (end_ < (int64_t)buf_.size()) eof_ = true;
+	end_ = read_block_();
+	if (end_ < (int64_t)kBuf) eof_ = true;
 	return end_ > 0;
 }
 

@@ -28,6 +28,11 @@ public:
 	size_t fill(uint8_t *dst, size_t cap, size_t target, int min_len, int64_t *n_seq, bool *done, size_t *need);
 
 private:
+	// gzip / stdin input is read (and inflated) by a helper thread a few blocks ahead of the parser, so that
+	// inflating and parsing overlap; YAKB_NO_READAHEAD=1 reads in the parsing thread
+	struct Ahead;
+	Ahead *ahead_ = nullptr;
+	int64_t read_block_();     // next block into buf_; returns its length, 0 at the end of the input
 	int getc_();
 	// append the rest of the current line to s (without the '\n'); false if nothing was left
 	bool line_(std::string &s, int64_t *count_only);
