@@ -91,6 +91,10 @@ void *yakb_pfastx_open(const char *fn, uint64_t block_bytes, int threads);
 int64_t yakb_pfastx_fill(void *reader, char *buf, uint64_t cap, uint64_t target, int min_len,
                          int64_t *n_seq, int *done, uint64_t *need);
 uint64_t yakb_pfastx_redo(void *reader);   /* blocks that had to be re-parsed sequentially */
+/* The reference's -K (count.c:106) for the bulk forms: whether `yak count` reads on behind a FASTQ record with a
+ * truncated quality string depends on it (count.c:93,109,162; kthread.c:119).  Default 10 M (misc.c:31). */
+void yakb_fastx_set_chunk(void *reader, int64_t chunk_size);
+void yakb_pfastx_set_chunk(void *reader, int64_t chunk_size);
 void yakb_pfastx_close(void *reader);
 /* skip n_skip records, then append up to n_take records (those of length >= min_len) to buf as
  * "SEQ\n"; returns the records consumed (-1: buf too small).  Lets each rank of a multi-GPU job

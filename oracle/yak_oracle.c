@@ -631,21 +631,45 @@ yo_ch_t *yo_count_seqs(int64_t n_seq, const int64_t *lens, const char *cat, int 
 	return h;
 }
 
-yo_ch_t *yo_count_file(const char *fn, int k, int pre, int bf_shift, int bf_n_hash, yo_ch_t *h0, int64_t *n_events)
+/* count.c:88-110: step 0 of the pipeline collects records until they hold chunk_size bases (records shorter than k do not
+ * count) or kseq_read fails; a failure that is a truncated FASTQ record (kseq's -2) only ends that chunk, the next call
+ * resumes at the next header character (kseq.h:192-199).  A call that collects nothing returns NULL, which retires the
+ * pipeline worker that made it (kthread.c:119); count.c:162 starts 3 workers, so reading goes on until the third empty
+ * call - the end of the file gives three in a row, a truncated record that is the first thing a call meets costs one. */
+yo_ch_t *yo_count_file_chunked(const char *fn, int k, int pre, int bf_shift, int bf_n_hash, yo_ch_t *h0, int64_t *n_events,
+                               int64_t chunk_size)
 {
 	feeder_t f;
 	yo_reader_t *r = yo_reader_open(fn);
 	yo_ch_t *h;
 	const char *seq;
-	int64_t len;
+	int64_t len, sum_len = 0;
+	int workers = 3;                                           /* count.c:162 */
 	if (r == 0) return 0;                                      /* count.c:152 */
 	h = h0 ? h0 : yo_ch_init(k, pre, bf_n_hash, bf_shift);
 	memset(&f, 0, sizeof(f));
 	if (n_events) *n_events = 0;
-	while ((len = yo_reader_next(r, &seq, 0)) >= 0) feed_seq(h, h0 == 0, &f, len, seq, n_events);
+	for (;;) {
+		len = yo_reader_next(r, &seq, 0);
+		if (len < 0) {                                         /* the call ends here */
+			if (len == -1) break;                              /* end of file: every later call is empty as well */
+			if (sum_len == 0 && --workers == 0) break;         /* count.c:109 + kthread.c:119 */
+			sum_len = 0;                                       /* the next call starts a new chunk */
+			continue;
+		}
+		feed_seq(h, h0 == 0, &f, len, seq, n_events);
+		if (len < k) continue;                                 /* count.c:95 */
+		sum_len += len;
+		if (sum_len >= chunk_size) sum_len = 0;                /* count.c:106 */
+	}
 	free(f.ev);
 	yo_reader_close(r);
 	return h;
+}
+
+yo_ch_t *yo_count_file(const char *fn, int k, int pre, int bf_shift, int bf_n_hash, yo_ch_t *h0, int64_t *n_events)
+{
+	return yo_count_file_chunked(fn, k, pre, bf_shift, bf_n_hash, h0, n_events, 10000000); /* misc.c:31 */
 }
 
 /* ------------------------------------------------------------------ qv scan */

@@ -92,7 +92,10 @@ int64_t yo_extract(int k, int64_t len, const char *seq, uint64_t *out);
 
 /* ---- whole-file driver: count.c:85-166 + main.c:53-60, sequential ---- */
 yo_ch_t *yo_count_file(const char *fn, int k, int pre, int bf_shift, int bf_n_hash, yo_ch_t *h0,
-                       int64_t *n_events);
+                       int64_t *n_events);            /* chunk_size = 10 M, yak_copt_init's default */
+/* the -K chunk size decides what happens after a truncated FASTQ record (count.c:93,109) */
+yo_ch_t *yo_count_file_chunked(const char *fn, int k, int pre, int bf_shift, int bf_n_hash, yo_ch_t *h0,
+                               int64_t *n_events, int64_t chunk_size);
 /* same over sequences already in memory (concatenated, lens[] gives each length) */
 yo_ch_t *yo_count_seqs(int64_t n_seq, const int64_t *lens, const char *cat, int k, int pre,
                        int bf_shift, int bf_n_hash, yo_ch_t *h0, int64_t *n_events);

@@ -85,11 +85,14 @@ def dump_bytes(h) -> bytes:
     return data
 
 
-def count_file(fn: str, k=31, pre=12, bf_shift=0, bf_n_hash=4, two_pass=None, fn2=None):
-    """The `yak count` protocol of main.c:53-60 on the oracle; returns (handle, n_events)."""
+def count_file(fn: str, k=31, pre=12, bf_shift=0, bf_n_hash=4, two_pass=None, fn2=None, chunk_size=10_000_000):
+    """The `yak count` protocol of main.c:53-60 on the oracle; returns (handle, n_events).  chunk_size = the reference's -K
+    (it only matters behind a truncated FASTQ record, count.c:93,109)."""
     L = lib()
     ne = C.c_int64()
-    h = L.yo_count_file(fn.encode(), k, pre, bf_shift, bf_n_hash, None, C.byref(ne))
+    L.yo_count_file_chunked.restype = C.POINTER(YoCh)
+    L.yo_count_file_chunked.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(YoCh), C.POINTER(C.c_int64), C.c_int64]
+    h = L.yo_count_file_chunked(fn.encode(), k, pre, bf_shift, bf_n_hash, None, C.byref(ne), chunk_size)
     if not h:
         return None, 0
     if two_pass is None:
@@ -97,7 +100,7 @@ def count_file(fn: str, k=31, pre=12, bf_shift=0, bf_n_hash=4, two_pass=None, fn
     if two_pass:
         L.yo_ch_destroy_bf(h)
         L.yo_ch_clear(h)
-        L.yo_count_file((fn2 or fn).encode(), k, pre, bf_shift, bf_n_hash, h, None)
+        L.yo_count_file_chunked((fn2 or fn).encode(), k, pre, bf_shift, bf_n_hash, h, None, chunk_size)
         L.yo_ch_shrink(h, 2, 1023)
     return h, ne.value
 

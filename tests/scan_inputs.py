@@ -59,11 +59,25 @@ def child_contigs(a, b, seed=9, n=6):
     return bytes(out)
 
 
+def bad_fastq(a, b):
+    """FASTQ contigs with truncated-quality records between the good ones (quality one character too long, so the bad
+    record does not swallow the next header): good bad good bad bad good bad bad good.  The reference's two-worker
+    pipeline (kt_pipeline(2, ...)) reads on behind a bad record, loses a worker on every batch that starts with one, and
+    never reaches the last record."""
+    def rec(name, codes, ok=True):
+        s = synth.codes_to_ascii(codes).tobytes()
+        return b"@" + name + b"\n" + s + b"\n+\n" + b"I" * (len(s) + (0 if ok else 1)) + b"\n"
+    parts = [rec(b"g1", a[100:3100]), rec(b"b1", a[5000:5100], False), rec(b"g2", b[7000:9500]), rec(b"b2", b[100:200], False),
+             rec(b"b3", a[300:400], False), rec(b"g3", a[12000:15000]), rec(b"b4", b[400:500], False), rec(b"b5", a[600:700], False),
+             rec(b"g4", b[20000:22000])]
+    return b"".join(parts)
+
+
 def write_all(d):
-    """writes pat.fa mat.fa third.fa child.fa hapA.fa hapB.fa into d; returns their paths"""
+    """writes pat.fa mat.fa third.fa child.fa hapA.fa hapB.fa bad.fq into d; returns their paths"""
     a, b, c = genomes()
     files = {"pat.fa": reads_fasta(a, 31), "mat.fa": reads_fasta(b, 32), "third.fa": reads_fasta(c, 33),
-             "child.fa": child_contigs(a, b),
+             "child.fa": child_contigs(a, b), "bad.fq": bad_fastq(a, b),
              "hapA.fa": _fa(b"hA1", a[1000:9000]) + _fa(b"hA2", c[500:4500], 60) + _fa(b"hA3", b[20000:26000]),
              "hapB.fa": _fa(b"hB1", b[30000:38000]) + _fa(b"hB2", c[10000:13000])}
     paths = {}
@@ -89,6 +103,10 @@ CASES = [
     ("scan_chkerr_c.txt", ["chkerr", "-t1", "-c8", "-s2", "{mat47.yak}", "{child.fa}"]),
     ("scan_sexchr.txt", ["sexchr", "-t1", "{pat.yak}", "{mat.yak}", "{third.yak}", "{hapA.fa}", "{hapB.fa}"]),
     ("scan_sexchr_K.txt", ["sexchr", "-t1", "-K5k", "{third.yak}", "{pat.yak}", "{mat.yak}", "{hapB.fa}", "{hapA.fa}"]),
+    # truncated FASTQ records: which records are still read depends on the reference's pipeline (bseq.c:40, kthread.c:119)
+    ("scan_chkerr_badq.txt", ["chkerr", "-t1", "{pat.yak}", "{bad.fq}"]),
+    ("scan_triobin_badq.txt", ["triobin", "-t1", "{pat.yak}", "{mat.yak}", "{bad.fq}"]),
+    ("scan_sexchr_badq.txt", ["sexchr", "-t1", "-K2k", "{pat.yak}", "{mat.yak}", "{third.yak}", "{bad.fq}", "{hapB.fa}"]),
 ]
 
 

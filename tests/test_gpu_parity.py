@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _count_both(oracle, yakb, fn, k, pre, b, fn2=None, chunk_size=10_000_000):
-    ho, ne = oracle.count_file(fn, k=k, pre=pre, bf_shift=b, fn2=fn2)
+    ho, ne = oracle.count_file(fn, k=k, pre=pre, bf_shift=b, fn2=fn2, chunk_size=chunk_size)
     ref = oracle.dump_bytes(ho)
     hg = yakb.count_file(fn, k=k, pre=pre, bf_shift=b, fn2=fn2, chunk_size=chunk_size)
     assert hg
@@ -119,6 +119,27 @@ def test_record_larger_than_staging_buffer(oracle, yakb, monkeypatch):
         finally:
             yakb.lib().yak_ch_destroy(hg)
             oracle.lib().yo_ch_destroy(ho)
+
+
+@pytest.mark.parametrize("seed,chunk", [(1, 10_000_000), (1, 3000), (2, 200), (5, 10_000_000), (7, 700)])
+def test_truncated_fastq_records_like_the_reference(oracle, yakb, seed, chunk, monkeypatch):
+    """behind a FASTQ record with a truncated quality the reference reads on or stops depending on its pipeline state and -K
+    (count.c:93,109,162; kthread.c:119; the oracle's restatement is checked against the reference binary on the CPU)"""
+    import test_oracle_cpu as T
+    rng = np.random.default_rng(4000 + seed)
+    fn = os.path.join(util.TMP, f"yakb_badq{seed}.fq")
+    with open(fn, "wb") as f:
+        f.write(T._random_fastx(rng, 150, long_lines=seed == 5, bad=0.3))
+    for serial in ("", "1"):
+        if serial:
+            monkeypatch.setenv("YAKB_SERIAL_PARSE", "1")
+        for b in (0, 19):
+            ho, hg, ref, mine, _ = _count_both(oracle, yakb, fn, 15, 10, b, chunk_size=chunk)
+            try:
+                assert mine == ref, (serial, b, util.explain_diff(mine, ref))
+            finally:
+                yakb.lib().yak_ch_destroy(hg)
+                oracle.lib().yo_ch_destroy(ho)
 
 
 def test_empty_and_missing_input(yakb):

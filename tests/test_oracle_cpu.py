@@ -198,6 +198,37 @@ def _records_oracle(path):
     return out
 
 
+def _ref_flow(path, min_len, chunk=10_000_000, workers=3):
+    """the sequences `yak count` processes, in order: count.c:88-110 over kseq_read (the oracle's restatement of it) -
+    a truncated FASTQ record ends the step-0 call, the third call that collects nothing ends the input (kthread.c:119)"""
+    L = O.lib()
+    L.yo_reader_open.restype = C.c_void_p; L.yo_reader_open.argtypes = [C.c_char_p]
+    L.yo_reader_next.restype = C.c_int64; L.yo_reader_next.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
+    L.yo_reader_close.argtypes = [C.c_void_p]
+    r = L.yo_reader_open(path.encode())
+    out, sum_len = [], 0
+    seq, name = C.c_char_p(), C.c_char_p()
+    while True:
+        n = L.yo_reader_next(r, C.byref(seq), C.byref(name))
+        if n == -1:
+            break
+        if n == -2:
+            if sum_len == 0:
+                workers -= 1
+                if workers == 0:
+                    break
+            sum_len = 0
+            continue
+        if n < min_len:
+            continue
+        out.append(seq.value)
+        sum_len += n
+        if sum_len >= chunk:
+            sum_len = 0
+    L.yo_reader_close(r)
+    return out
+
+
 def test_fastx_reader_matches_kseq_semantics():
     import gzip
     import test_gpu_parity as T
@@ -260,11 +291,13 @@ def test_qv_solver_matches_reference_output():
     assert lines == want
 
 
-def _fill_all(path, cap, target, min_len):
+def _fill_all(path, cap, target, min_len, chunk=0):
     """Drive yakb_fastx_fill the way yak_count does; returns the concatenated 'SEQ\\n' stream."""
     from yak_b200 import capi
     L = capi.lib()
     r = L.yakb_fastx_open(path.encode())
+    if chunk:
+        L.yakb_fastx_set_chunk(r, chunk)
     out, nseq = bytearray(), 0
     buf = C.create_string_buffer(cap)
     while True:
@@ -302,18 +335,26 @@ def test_bulk_fill_equals_record_reader(cap, target):
     open(p, "w").write("@a\nACGTAC\n+\nIIIIII\n@b\nGGGTTT\n+\nIIIIII")
     assert _fill_all(p, cap, target, 0)[0] == b"ACGTAC\nGGGTTT\n"
     open(p, "w").write("@a\nACGTAC\n+\nIIIIII\n@b\nGGGTTT\n+\nIII\n@c\nAAAA\n+\nIIII\n")
-    want = b"".join(s + b"\n" for _, s in (r for r in _records_oracle(p) if not isinstance(r, int)))
+    want = b"".join(s + b"\n" for s in _ref_flow(p, 0))     # the short quality of b swallows the header of c (kseq.h:224)
     assert _fill_all(p, cap, target, 0)[0] == want == b"ACGTAC\n"
+    # reading goes on behind a truncated record the way the reference's pipeline does (count.c:93,109; kthread.c:119)
+    open(p, "w").write("@a\nACGTAC\n+\nIIIIII\n@b\nGGGTTT\n+\nIIIIIIII\n@c\nAAAA\n+\nIIII\n@d\nCC\n+\nI\n@e\nTTTT\n+\nIIII\n")
+    for chunk in (10_000_000, 6, 4):
+        want = b"".join(s + b"\n" for s in _ref_flow(p, 0, chunk))
+        assert _fill_all(p, cap, target, 0, chunk)[0] == want, chunk
+    assert _ref_flow(p, 0) == [b"ACGTAC", b"AAAA"]    # b is dropped, c follows; d's short quality swallows the header of e
     big = G.input_path("reads_q")
     want = b"".join(s + b"\n" for _, s in (r for r in _records_oracle(big) if not isinstance(r, int)))
     assert _fill_all(big, max(cap, 4096), target, 0)[0] == want
 
 
-def _pfill_all(path, block, threads, cap, target, min_len):
+def _pfill_all(path, block, threads, cap, target, min_len, chunk=0):
     from yak_b200 import capi
     L = capi.lib()
     r = L.yakb_pfastx_open(path.encode(), block, threads)
     assert r
+    if chunk:
+        L.yakb_pfastx_set_chunk(r, chunk)
     out, nseq = bytearray(), 0
     buf = C.create_string_buffer(cap)
     while True:
@@ -356,7 +397,8 @@ def test_parallel_reader_is_exactly_the_sequential_reader(block, threads):
             assert got == want and gn == wn, (fn, block, threads, min_len, redo)
     trunc = os.path.join(util.TMP, "yakb_par_trunc.fq")
     open(trunc, "w").write("@a\nACGTAC\n+\nIIIIII\n@b\nGGGTTT\n+\nIII\n@c\nAAAA\n+\nIIII\n" * 3)
-    assert _pfill_all(trunc, block, threads, 4096, 4096, 0)[0] == _fill_all(trunc, 4096, 4096, 0)[0] == b"ACGTAC\n"
+    want = b"".join(s + b"\n" for s in _ref_flow(trunc, 0))      # every b is dropped, reading goes on behind it
+    assert _pfill_all(trunc, block, threads, 4096, 4096, 0)[0] == _fill_all(trunc, 4096, 4096, 0)[0] == want == b"ACGTAC\n" * 3
     assert not capi.lib().yakb_pfastx_open((files[0] + ".gz").encode(), 0, 0) or True
 
 
@@ -421,3 +463,65 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "events/s" and d["steps"] == 3 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def _random_fastx(rng, n_rec, long_lines=False, bad=0.0):
+    """adversarial FASTA/FASTQ text: multi-line records, CRLF, blank lines, quality lines starting with '>' '@' '+',
+    lower case / IUPAC, empty sequences, optional missing final newline"""
+    out = []
+    for i in range(n_rec):
+        eol = "\r\n" if rng.random() < 0.2 else "\n"
+        n = int(rng.integers(0, 60000 if long_lines and rng.random() < 0.3 else 400))
+        seq = "".join("ACGTNacgtRY"[j] for j in rng.integers(0, 11, n))
+        width = int(rng.integers(20, 5000 if long_lines else 120)) if rng.random() < 0.5 else max(n, 1)
+        lines = [seq[j:j + width] for j in range(0, max(n, 1), width)]
+        if rng.random() < 0.1:
+            lines.insert(int(rng.integers(0, len(lines) + 1)), "")          # a blank line inside the sequence
+        if rng.random() < 0.5:
+            out.append(f">r{i} c{eol}" + eol.join(lines) + eol)
+        else:
+            qual = "".join("I>@+#"[j] for j in rng.integers(0, 5, n))
+            if bad and n > 3 and rng.random() < bad:
+                qual = qual[:int(rng.integers(1, n))] if rng.random() < 0.6 else qual + "I" * int(rng.integers(1, 9))   # truncated / too long
+            qw = int(rng.integers(20, 5000 if long_lines else 120)) if rng.random() < 0.4 else max(n, 1)
+            qlines = [qual[j:j + qw] for j in range(0, max(n, 1), qw)]
+            out.append(f"@q{i}{eol}" + eol.join(lines) + eol + "+" + ("x" if rng.random() < 0.3 else "") + eol + eol.join(qlines) + eol)
+    txt = "".join(out)
+    if rng.random() < 0.3:
+        txt = txt.rstrip("\r\n")
+    if rng.random() < 0.15:
+        txt = "\n\n" + txt
+    return txt.encode()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_parallel_reader_randomised_against_sequential(seed):
+    """differential test of the parser pool (speculative record starts, mid-sequence speculation, carried records,
+    pool copies, spill) against the sequential reader on adversarial inputs, block sizes and buffer sizes"""
+    rng = np.random.default_rng(1000 + seed)
+    long_lines = seed % 3 == 0
+    p = os.path.join(util.TMP, f"yakb_par_rand{seed}.fx")
+    with open(p, "wb") as f:
+        f.write(_random_fastx(rng, int(rng.integers(5, 120)), long_lines, bad=(0.0, 0.1, 0.5)[seed % 3 if seed % 2 else 0]))
+    for min_len in (0, 31):
+        chunk = int(rng.choice([10_000_000, 3000, 200]))     # the reference's -K: decides what follows a truncated record
+        want = b"".join(s + b"\n" for s in _ref_flow(p, min_len, chunk))
+        wn = len(_ref_flow(p, min_len, chunk))
+        assert _fill_all(p, 1 << 22, 1 << 22, min_len, chunk) == (want, wn), (seed, min_len, chunk)
+        for _ in range(4):
+            block = int(rng.choice([16, 61, 300, 4096, 9000, 70000])) if not long_lines else int(rng.choice([4096, 6000, 20000, 70000]))
+            threads = int(rng.integers(1, 9))
+            cap = int(rng.choice([1 << 22, 1 << 17, 70000]))
+            target = int(rng.integers(1, cap + 1))
+            got, gn, redo = _pfill_all(p, block, threads, cap, target, min_len, chunk)
+            assert got == want and gn == wn, (seed, block, threads, cap, target, min_len, chunk, redo)
+    # the record readers themselves on the same adversarial file: product == oracle (kseq restatement) record by record,
+    # and the oracle's whole count == the UNMODIFIED reference binary's .yak (where oracle/_ref is built), for several -K
+    assert _records_product(p) == _records_oracle(p)
+    if os.path.exists(O.REF_YAK):
+        y = os.path.join(util.TMP, f"yakb_par_rand{seed}.yak")
+        for chunk in (10_000_000, 3000, 200):
+            O.ref_count(p, y, k=15, pre=10, extra=(f"-K{chunk}",))
+            h, _ = O.count_file(p, k=15, pre=10, bf_shift=0, chunk_size=chunk)
+            assert O.dump_bytes(h) == open(y, "rb").read(), (seed, chunk)
+            O.lib().yo_ch_destroy(h)

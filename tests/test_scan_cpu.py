@@ -70,8 +70,9 @@ def env():
     return logic, libc, O, paths
 
 
-def batches(O, fn, chunk):
-    """bseq.c:33-57: records until the batch holds >= chunk bases"""
+def batches(O, fn, chunk, workers=2):
+    """bseq.c:33-57 under kt_pipeline(2, ...): records until the batch holds >= chunk bases or kseq_read fails; a truncated
+    FASTQ record (-2) only ends the batch, and a batch that read nothing retires one pipeline worker (kthread.c:119)"""
     r = O.yo_reader_open(fn.encode())
     assert r
     names, seqs, size = [], [], 0
@@ -85,8 +86,10 @@ def batches(O, fn, chunk):
         if ln < 0 or size >= chunk:
             if names:
                 yield names, seqs
+            elif ln == -2:
+                workers -= 1
             names, seqs, size = [], [], 0
-            if ln < 0:
+            if ln == -1 or workers == 0:
                 break
     O.yo_reader_close(r)
 

@@ -14,6 +14,7 @@ int64_t yakb_cli_parse_num(const char *s); /* main.c */
 
 typedef struct {
 	void *rd;
+	int ref_workers;          /* pipeline workers the reference has left (2 at the start: kt_pipeline(2, ...)) */
 	int64_t n_seq, m_seq;
 	char **names;
 	int64_t *lens;
@@ -27,6 +28,7 @@ static int br_open(batch_reader_t *br, const char *fn)
 {
 	memset(br, 0, sizeof(*br));
 	br->rd = yakb_fastx_open(fn);
+	br->ref_workers = 2;
 	return br->rd != 0;
 }
 
@@ -43,7 +45,16 @@ static int br_next(batch_reader_t *br, int64_t chunk_size, const char *who)
 	const char *seq, *name;
 	int64_t len;
 	br_reset(br);
-	while ((len = yakb_fastx_next(br->rd, &seq, &name)) >= 0) {
+	if (br->ref_workers == 0) return 0;
+	for (;;) {
+		len = yakb_fastx_next(br->rd, &seq, &name);
+		if (len == -2) { /* a truncated FASTQ record ends bseq_read's batch (bseq.c:40); a call that read nothing retires one
+		                    of the reference's two pipeline workers (kthread.c:119), the second ends the input */
+			if (br->n_seq > 0) break;
+			if (--br->ref_workers == 0) break;
+			continue;
+		}
+		if (len < 0) { br->ref_workers = 0; break; }
 		if (br->n_seq == br->m_seq) {
 			br->m_seq = br->m_seq ? br->m_seq << 1 : 256;
 			br->names = (char**)realloc(br->names, br->m_seq * sizeof(char*));

@@ -654,6 +654,9 @@ extern "C" int64_t yakb_fastx_fill(void *reader, char *buf, uint64_t cap, uint64
 	return (int64_t)n;
 }
 
+extern "C" void yakb_fastx_set_chunk(void *reader, int64_t chunk_size) { ((FastxReader*)reader)->set_ref_chunk(chunk_size); }
+extern "C" void yakb_pfastx_set_chunk(void *reader, int64_t chunk_size) { ((ParallelFastx*)reader)->set_ref_chunk(chunk_size); }
+
 extern "C" void *yakb_pfastx_open(const char *fn, uint64_t block_bytes, int threads)
 {
 	ParallelFastx *r = new ParallelFastx;
@@ -751,6 +754,7 @@ extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *
 	ParallelFastx prd; // plain regular files are parsed by several threads; gzip / stdin by the sequential reader
 	const bool par = !getenv("YAKB_SERIAL_PARSE") && prd.open(fn);
 	if (!par && !rd.open(fn)) return 0;
+	prd.set_ref_chunk(opt->chunk_size); rd.set_ref_chunk(opt->chunk_size); // -K decides what follows a truncated FASTQ record
 	yak_ch_t *h = h0;
 	if (h0) assert(h0->k == opt->k && h0->pre == opt->pre);
 	else h = yak_ch_init(opt->k, opt->pre, opt->bf_n_hash, opt->bf_shift);
@@ -952,6 +956,7 @@ extern "C" void yak_qv(const yak_qopt_t *opt, const char *fn, const yak_ch_t *ch
 	// "SEQ\n" batches (sequences shorter than min_len take no part in anything, qv.c:44, so the pool may drop them)
 	ParallelFastx prd;
 	if (!opt->print_each && !opt->print_err_kmer && !getenv("YAKB_SERIAL_PARSE") && prd.open(fn)) {
+		prd.set_ref_flow(opt->chunk_size, 2, 0); // behind a truncated FASTQ record: bseq_read's batches, two pipeline workers (qv.c:94,126)
 		size_t pcap = cap + (cap >> 4) + 4096;
 		std::unique_ptr<uint8_t[]> pbuf(new uint8_t[pcap]); // not a vector: no need to zero 68 MB first
 		bool pdone = false;
@@ -984,6 +989,8 @@ extern "C" void yak_qv(const yak_qopt_t *opt, const char *fn, const yak_ch_t *ch
 	FastxReader rd;
 	if (!rd.open(fn)) return;
 	bool done = false;
+	int64_t ref_n = 0, ref_size = 0;
+	int ref_workers = 2;
 	std::vector<uint8_t> buf;
 	std::vector<std::string> names;
 	std::vector<int32_t> tot, non0;
@@ -993,7 +1000,14 @@ extern "C" void yak_qv(const yak_qopt_t *opt, const char *fn, const yak_ch_t *ch
 		buf.clear(); names.clear();
 		while (buf.size() < cap) { // bseq.c:33-57: a batch closes once it holds >= chunk_size bases
 			int64_t len = rd.next();
+			if (len == -2) { // a truncated FASTQ record ends the reference's bseq_read call; an empty call retires one of the two pipeline workers (qv.c:126, kthread.c:119)
+				if (ref_n == 0 && --ref_workers == 0) { done = true; break; }
+				ref_n = ref_size = 0;
+				continue;
+			}
 			if (len < 0) { done = true; break; }
+			++ref_n; ref_size += len;
+			if (ref_size >= std::max<int64_t>(opt->chunk_size, 1)) ref_n = ref_size = 0;
 			buf.insert(buf.end(), rd.seq().begin(), rd.seq().end());
 			buf.push_back('\n');
 			off.push_back(buf.size());

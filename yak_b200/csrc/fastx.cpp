@@ -37,6 +37,7 @@ bool FastxReader::open(const char *fn)
 	gzbuffer(fp_, 1u << 20);
 	buf_.resize(kBuf);
 	beg_ = end_ = 0; eof_ = false; last_ = 0;
+	ref_sum_ = 0; ref_workers_ = 3;
 	if (!getenv("YAKB_NO_READAHEAD")) {
 		ahead_ = new Ahead;
 		Ahead *a = ahead_;
@@ -155,6 +156,7 @@ size_t FastxReader::fill(uint8_t *dst, size_t cap, size_t target, int min_len, i
 	}
 	// close the record being parsed: keep it (terminator appended) or drop it
 	auto finish_record = [&](bool keep) {
+		if (keep && cur_len_ >= min_len) { ref_sum_ += cur_len_; if (ref_sum_ >= ref_chunk_) ref_sum_ = 0; } // count.c:105-106
 		if (in_carry_) {
 			if (keep && cur_len_ >= min_len) carry_ready_ = true; else carry_.clear();
 			in_carry_ = false;
@@ -219,7 +221,10 @@ size_t FastxReader::fill(uint8_t *dst, size_t cap, size_t target, int min_len, i
 				const bool ok = qual_len_ == cur_len_;
 				finish_record(ok);
 				st_ = S_FIND; last_ = 0;
-				if (!ok) { eof_ = true; beg_ = end_; *done = true; break; } // kseq's -2: the caller's loop ends
+				if (!ok) { // kseq's -2 ends the reference's step-0 call; see set_ref_chunk()
+					if (ref_sum_ == 0 && --ref_workers_ <= 0) { eof_ = true; beg_ = end_; *done = true; break; }
+					ref_sum_ = 0; // the next call resumes at the next header character (state S_FIND, last_ 0)
+				}
 				continue;
 			}
 			const unsigned char *nl = (const unsigned char*)memchr(p, '\n', avail);

@@ -26,6 +26,11 @@ public:
 	// A record that does not fit is carried over to the next call; if it can never fit, *need is
 	// set to the dst size required.
 	size_t fill(uint8_t *dst, size_t cap, size_t target, int min_len, int64_t *n_seq, bool *done, size_t *need);
+	// fill() goes on behind a FASTQ record with a truncated quality string exactly where the reference's `yak count`
+	// does: its step-0 call ends at such a record; a call that had collected nothing (records >= min_len bases; a call
+	// is also full at chunk_size bases, count.c:106) retires one of the pipeline's three workers, the third ends the
+	// input (count.c:109,162; kthread.c:119).  chunk_size is the reference's -K.
+	void set_ref_chunk(int64_t chunk_size) { ref_chunk_ = chunk_size > 0 ? chunk_size : 1; }
 
 private:
 	// gzip / stdin input is read (and inflated) by a helper thread a few blocks ahead of the parser, so that
@@ -51,6 +56,8 @@ private:
 	std::string carry_;        // a record that did not fit the caller's buffer
 	bool carry_ready_ = false; // carry_ holds a COMPLETE record waiting for the next fill()
 	bool in_carry_ = false;    // the current record is being collected in carry_
+	int64_t ref_chunk_ = 10000000, ref_sum_ = 0; // yak_copt_init's default (misc.c:31); bases the reference's current call holds
+	int ref_workers_ = 3;
 };
 
 } // namespace yakb

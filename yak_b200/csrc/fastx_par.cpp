@@ -83,7 +83,7 @@ void FastxCore::feed(const unsigned char *p, size_t n, int min_len, std::vector<
 				const bool ok = qual_len == cur_len;
 				close_in_out(*this, rs, ok, min_len, out, n_seq);
 				st = S_FIND; last = 0;
-				if (!ok) stopped = true; // kseq's -2: the caller's read loop ends here
+				if (!ok) { stopped = true; bad_at = (int64_t)i; } // kseq's -2: the caller decides whether reading goes on
 				continue;
 			}
 			const unsigned char *nl = (const unsigned char*)memchr(p + i, '\n', n - i);
@@ -110,7 +110,7 @@ void FastxCore::settle(int min_len, std::vector<uint8_t> &out, int64_t *n_seq)
 		const bool ok = qual_len == cur_len;
 		close_carried(*this, ok, min_len, out, n_seq);
 		st = S_FIND; last = 0;
-		if (!ok) stopped = true;
+		if (!ok) { stopped = true; bad_at = 0; }
 	}
 }
 
@@ -231,6 +231,7 @@ bool ParallelFastx::open(const char *fn, size_t block_bytes, int threads)
 	}
 	threads_ = threads;
 	finished_ = false; n_redo_ = 0; true_blocks_ = 0;
+	ref_workers_ = ref_workers0_; anchor_off_ = 0;
 	true_ = FastxCore();
 	spill_.clear(); spill_pos_ = 0; spill_seq_ = 0;
 	im_ = new Impl;
@@ -290,6 +291,51 @@ bool ParallelFastx::work_one(std::unique_lock<std::mutex> &lk, bool may_parse)
 		}
 	}
 	return false;
+}
+
+// What the reference does behind a truncated FASTQ record (kseq's -2) depends on its pipeline (count.c:88-110, 162;
+// kthread.c:119): the step-0 call that met the record ends there; if it had collected records (>= k bases each) they are
+// processed and the next call resumes at the next header character; a call that collected nothing retires one of the three
+// pipeline workers, and the third such call (the end of the file makes three at once) ends the input.  "Collected nothing"
+// needs the lengths of the records since the call began (a call also ends once it holds chunk_size bases), which the block
+// outputs do not keep - so on a bad record, and only then, the stretch since the last decision is parsed again, sequentially.
+bool ParallelFastx::ref_resumes(uint64_t bad_off, int min_len)
+{
+	FastxCore e;
+	std::vector<uint8_t> scratch;
+	int64_t sum = 0, cnt = 0; // bases and records the reference's current call holds
+	const int fml = flow_min_len_ >= 0 ? flow_min_len_ : min_len;
+	for (uint64_t off = anchor_off_; off < bad_off; ) {
+		const size_t len = (size_t)std::min<uint64_t>(1u << 20, bad_off - off);
+		int64_t ns = 0;
+		scratch.clear();
+		e.feed(map_ + off, len, fml, scratch, &ns);
+		for (const uint8_t *p = scratch.data(), *end = p + scratch.size(); p < end; ) { // "SEQ\n" of every record the call counts
+			const uint8_t *nl = (const uint8_t*)memchr(p, '\n', end - p);
+			sum += nl - p; ++cnt;
+			if (sum >= ref_chunk_) sum = cnt = 0; // count.c:106 / bseq.c:53: that call is full, the next one starts
+			p = nl + 1;
+		}
+		off += len;
+	}
+	anchor_off_ = bad_off;
+	if (cnt == 0 && --ref_workers_ <= 0) return false;
+	return true;
+}
+
+// true_.feed() over a stretch of the file, going on behind truncated records where the reference does
+void ParallelFastx::feed_true(const unsigned char *buf, size_t len, uint64_t file_off, int min_len, std::vector<uint8_t> &out, int64_t *ns)
+{
+	size_t pos = 0;
+	for (;;) {
+		true_.feed(buf + pos, len - pos, min_len, out, ns);
+		if (!(true_.stopped && true_.bad_at >= 0)) return;
+		const size_t at = pos + (size_t)true_.bad_at;
+		true_.bad_at = -1;
+		if (!ref_resumes(file_off + at, min_len)) return; // the input ends here for the reference too
+		true_.stopped = false;
+		pos = at;
+	}
 }
 
 size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len, int64_t *n_seq, bool *done, size_t *need)
@@ -367,7 +413,9 @@ size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len,
 			std::unique_lock<std::mutex> lk(im.mu);
 			while (!(j.state == 2 && j.blk == consumed)) if (!work_one(lk, true)) im.cv.wait(lk);
 		}
-		const unsigned char *raw = map_ + consumed * (uint64_t)block_;
+		const uint64_t blk_off = consumed * (uint64_t)block_;
+		const unsigned char *raw = map_ + blk_off;
+		const size_t jq = j.q, jn = j.n; // the slot may be handed back (and refilled) as soon as its copy is queued
 		int64_t gs = 0;
 		bool queued = false;
 		gap.clear();
@@ -376,9 +424,13 @@ size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len,
 			true_.rec.append((const char*)j.mid.data(), j.mid.size());
 			true_.cur_len += (int64_t)j.mid.size();
 			true_.bol = j.mid_bol_out;
-		} else true_.feed(raw, j.q, min_len, gap, &gs); // the gap before the guess, with the true state
-		if (j.q < j.n) {
+		} else feed_true(raw, jq, blk_off, min_len, gap, &gs); // the gap before the guess, with the true state
+		if (jq < jn) {
 			true_.settle(min_len, gap, &gs);
+			if (true_.stopped && true_.bad_at >= 0) { // the record that ends right at the guess has a truncated quality
+				true_.bad_at = -1;
+				if (ref_resumes(blk_off + jq, min_len)) true_.stopped = false;
+			}
 			if (j.min_len == min_len && true_.at_record_boundary()) { // the guess was a real record start: adopt the speculative result
 				if (true_.st == FastxCore::S_SEQ && true_.rec.size() >= (1u << 16) && true_.cur_len >= min_len) {
 					// a long carried record ends here: straight from the carry buffer to where it goes, not through `gap`
@@ -398,14 +450,26 @@ size_t ParallelFastx::fill(uint8_t *dst, size_t cap, size_t target, int min_len,
 					true_ = std::move(j.spec); // before the slot can be handed back (a finished copy frees it)
 					true_.rec = std::move(keep);
 				}
+				const int64_t spec_bad = true_.stopped ? true_.bad_at : -1; // the worker stopped at a truncated record
 				if (j.out.size() >= (1u << 16) && spill_.empty() && n + j.out.size() <= cap) { // big: copied by the pool
 					std::lock_guard<std::mutex> lk(im.mu);
 					im.copyq.push_back({j.out.data(), dst + n, j.out.size(), &j});
 					++im.copies_open; j.state = 3; queued = true;
 					n += j.out.size(); *n_seq += j.nseq;
 				} else emit(j.out.data(), j.out.size(), j.nseq);
+				if (spec_bad >= 0) { // the rest of the block, with the true state, if the reference reads on
+					true_.bad_at = -1;
+					const size_t at = jq + (size_t)spec_bad;
+					if (ref_resumes(blk_off + at, min_len)) {
+						true_.stopped = false;
+						int64_t rs = 0;
+						gap.clear();
+						feed_true(raw + at, jn - at, blk_off + at, min_len, gap, &rs);
+						emit(gap.data(), gap.size(), rs);
+					}
+				}
 			} else { // wrong guess: this block again, sequentially, from the true state
-				true_.feed(raw + j.q, j.n - j.q, min_len, gap, &gs);
+				feed_true(raw + jq, jn - jq, blk_off + jq, min_len, gap, &gs);
 				emit(gap.data(), gap.size(), gs);
 				++n_redo_;
 			}

@@ -21,6 +21,10 @@ struct FastxCore {
 	enum { S_FIND, S_NAME, S_SEQ, S_PLUS, S_QUAL };
 	int st = S_FIND, last = 0, last_qual = 0;
 	bool bol = true, stopped = false, qline_nonempty = false;
+	// stopped by a FASTQ record with a truncated quality string (kseq's -2): index into the buffer of that feed() call
+	// where kseq would go on (just behind the quality lines it read), or 0 after settle(); -1 otherwise.  To resume the
+	// way a later kseq_read call does (kseq.h:192-199), clear `stopped` and feed from there: the state is S_FIND, last 0.
+	int64_t bad_at = -1;
 	int64_t qual_len = 0, qual_lines = 0, cur_len = 0; // cur_len: sequence length of the open record
 	std::string rec;            // bytes of the open record carried between feed() calls
 	// consume n bytes; completed records of length >= min_len are appended to out as "SEQ\n"
@@ -62,10 +66,21 @@ public:
 	// same contract as FastxReader::fill
 	size_t fill(uint8_t *dst, size_t cap, size_t target, int min_len, int64_t *n_seq, bool *done, size_t *need);
 	uint64_t mis_speculations() const { return n_redo_; }
+	// the reference's -K (count.c:106): it decides whether reading goes on behind a truncated FASTQ record, see ref_resumes()
+	void set_ref_chunk(int64_t chunk_size) { ref_chunk_ = chunk_size > 0 ? chunk_size : 1; }
+	// the general form: `workers` pipeline threads (3 in yak count, count.c:162; 2 in qv and the other scanners, qv.c:126),
+	// and which records a step-0 call counts: those of at least flow_min_len bases (k in count.c:95; 0 for bseq_read,
+	// bseq.c:33-57, which keeps every record), or fill()'s own min_len when flow_min_len < 0
+	void set_ref_flow(int64_t chunk_size, int workers, int flow_min_len) { set_ref_chunk(chunk_size); ref_workers_ = ref_workers0_ = workers; flow_min_len_ = flow_min_len; }
 
 private:
 	struct Impl;
 	bool work_one(std::unique_lock<std::mutex> &lk, bool may_parse);
+	bool ref_resumes(uint64_t bad_off, int min_len);
+	void feed_true(const unsigned char *buf, size_t len, uint64_t file_off, int min_len, std::vector<uint8_t> &out, int64_t *ns);
+	int64_t ref_chunk_ = 10000000;   // yak_copt_init's default (misc.c:31)
+	int ref_workers_ = 3, ref_workers0_ = 3, flow_min_len_ = -1; // count.c:162
+	uint64_t anchor_off_ = 0;        // where the reference's current step-0 call (or an earlier one) began: file start, or behind the last bad record
 	Impl *im_ = nullptr;
 	int fd_ = -1;
 	const unsigned char *map_ = nullptr;
