@@ -525,3 +525,37 @@ def test_parallel_reader_randomised_against_sequential(seed):
             h, _ = O.count_file(p, k=15, pre=10, bf_shift=0, chunk_size=chunk)
             assert O.dump_bytes(h) == open(y, "rb").read(), (seed, chunk)
             O.lib().yo_ch_destroy(h)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_oracle_randomised_parameters_against_reference_binary(seed):
+    """the checker itself, checked: random k / -p / -b / -H / -K, one- and two-file runs, clean and adversarial reads -
+    the oracle's .yak must be the unmodified reference's, byte for byte"""
+    if not os.path.exists(O.REF_YAK):
+        pytest.skip("oracle/_ref not built")
+    from yak_b200 import synth
+    rng = np.random.default_rng(7000 + seed)
+    k = int(rng.choice([5, 13, 21, 27, 31, 32, 33, 47, 63]))
+    pre = int(rng.integers(10, 15))
+    b = int(rng.choice([0, 0, pre - 1, pre + 9, pre + 10, pre + 12, pre + 14]))
+    nh = int(rng.choice([1, 2, 4, 4, 7, 8]))
+    chunk = int(rng.choice([10_000_000, 50_000, 4000]))
+    f1 = os.path.join(util.TMP, f"yakb_rnd{seed}_1.fx")
+    f2 = os.path.join(util.TMP, f"yakb_rnd{seed}_2.fx")
+    G_, n = 30_000, int(rng.integers(200, 1500))
+    with open(f1, "wb") as f:
+        f.write(synth.reads_file_bytes(50 + seed, G_, 60 + seed, n, 150, 0.01, 3, fastq=bool(seed % 2)))
+        if seed % 3 == 0:
+            f.write(_random_fastx(rng, 40, bad=0.2))
+    with open(f2, "wb") as f:
+        f.write(synth.reads_file_bytes(50 + seed, G_, 80 + seed, n // 2, 150, 0.02, 3, fastq=not seed % 2))
+    two = b > 0 and seed % 2 == 0
+    y = os.path.join(util.TMP, f"yakb_rnd{seed}.yak")
+    O.ref_count(f1, y, k=k, pre=pre, bf_shift=b, bf_n_hash=nh, extra=(f"-K{chunk}",))
+    if two:   # second input for pass 2 (main.c:57)
+        cmd = [O.REF_YAK, "count", f"-k{k}", f"-p{pre}", "-t3", f"-H{nh}", f"-b{b}", f"-K{chunk}", "-o", y, f1, f2]
+        subprocess.run(cmd, check=True, capture_output=True)
+    h, _ = O.count_file(f1, k=k, pre=pre, bf_shift=b, bf_n_hash=nh, fn2=f2 if two else None, chunk_size=chunk)
+    got, want = O.dump_bytes(h), open(y, "rb").read()
+    assert got == want, (k, pre, b, nh, chunk, two, util.explain_diff(got, want))
+    O.lib().yo_ch_destroy(h)
