@@ -94,6 +94,9 @@ uint64_t yakb_pfastx_redo(void *reader);   /* blocks that had to be re-parsed se
 /* The reference's -K (count.c:106) for the bulk forms: whether `yak count` reads on behind a FASTQ record with a
  * truncated quality string depends on it (count.c:93,109,162; kthread.c:119).  Default 10 M (misc.c:31). */
 void yakb_fastx_set_chunk(void *reader, int64_t chunk_size);
+/* the rule itself (csrc/ref_flow.h), for tests: lens[i] = length of record i, or -2 for a truncated FASTQ record;
+ * read_out[i] = 1 if the reference reads record i with `workers` pipeline threads (3 for count, 2 for the scanners) */
+void yakb_ref_flow_sim(const int64_t *lens, int64_t n, int workers, int64_t chunk_size, int min_len, uint8_t *read_out);
 void yakb_pfastx_set_chunk(void *reader, int64_t chunk_size);
 void yakb_pfastx_close(void *reader);
 /* skip n_skip records, then append up to n_take records (those of length >= min_len) to buf as

@@ -559,3 +559,38 @@ def test_oracle_randomised_parameters_against_reference_binary(seed):
     got, want = O.dump_bytes(h), open(y, "rb").read()
     assert got == want, (k, pre, b, nh, chunk, two, util.explain_diff(got, want))
     O.lib().yo_ch_destroy(h)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_ref_flow_rule_of_the_library(seed):
+    """csrc/ref_flow.h (used by the sequential reader and yak_qv) against the flows pinned to the reference: `_ref_flow`
+    (count.c, checked against the reference binary above) and test_scan_cpu.batches (bseq_read, checked against the
+    reference's scanner stdout), on random streams of good and truncated FASTQ records"""
+    import test_scan_cpu as TS
+    from yak_b200 import capi
+    L = capi.lib()
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.integers(5, 60))
+    lens = [(-2 if rng.random() < (0.15, 0.4, 0.7)[seed % 3] else int(rng.integers(1, 80))) for _ in range(n)]
+    p = os.path.join(util.TMP, f"yakb_flow{seed}.fq")
+    with open(p, "w") as f:
+        for i, ln in enumerate(lens):
+            m = ln if ln > 0 else int(rng.integers(4, 40))
+            s = "".join("ACGT"[j] for j in rng.integers(0, 4, m))
+            f.write(f"@r{i}\n{s}\n+\n" + "I" * (m + (1 if ln < 0 else 0)) + "\n")     # one quality character too many = kseq's -2
+    seqs = [ln.strip() for ln in open(p).read().split("\n")[1::4]]
+    arr = (C.c_int64 * n)(*lens)
+    for chunk in (10_000_000, 150, 40):
+        for min_len in (0, 31):
+            out = (C.c_uint8 * n)()
+            L.yakb_ref_flow_sim(arr, n, 3, chunk, min_len, out)
+            mine = [seqs[i].encode() for i in range(n) if out[i] and lens[i] >= min_len]
+            assert mine == _ref_flow(p, min_len, chunk), (seed, chunk, min_len)
+        out = (C.c_uint8 * n)()
+        L.yakb_ref_flow_sim(arr, n, 2, chunk, 0, out)
+        O_ = O.lib()
+        O_.yo_reader_open.restype = C.c_void_p; O_.yo_reader_open.argtypes = [C.c_char_p]
+        O_.yo_reader_next.restype = C.c_int64; O_.yo_reader_next.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
+        O_.yo_reader_close.argtypes = [C.c_void_p]
+        want = [s for _, ss in TS.batches(O_, p, chunk) for s in ss]
+        assert [seqs[i].encode() for i in range(n) if out[i]] == want, (seed, chunk)

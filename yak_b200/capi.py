@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
         "yakb_pfastx_fill": (i64, [vp, vp, u64, u64, C.c_int, C.POINTER(i64), C.POINTER(C.c_int), C.POINTER(u64)]),
         "yakb_pfastx_redo": (u64, [vp]),
         "yakb_fastx_set_chunk": (None, [vp, i64]),
+        "yakb_ref_flow_sim": (None, [C.POINTER(i64), i64, C.c_int, i64, C.c_int, C.POINTER(C.c_uint8)]),
         "yakb_pfastx_set_chunk": (None, [vp, i64]),
         "yakb_pfastx_close": (None, [vp]),
         "yakb_fastx_read_slice": (i64, [vp, i64, i64, C.c_int, vp, u64, C.POINTER(u64), C.POINTER(i64)]),

@@ -21,6 +21,7 @@
 #include <mutex>
 #include <thread>
 #include <atomic>
+#include "ref_flow.h"
 #include <chrono>
 #include <memory>
 #include <sys/resource.h>
@@ -654,6 +655,19 @@ extern "C" int64_t yakb_fastx_fill(void *reader, char *buf, uint64_t cap, uint64
 	return (int64_t)n;
 }
 
+// which records of a stream the reference reads: lens[i] = record length, or -2 for a truncated FASTQ record (csrc/ref_flow.h)
+extern "C" void yakb_ref_flow_sim(const int64_t *lens, int64_t n, int workers, int64_t chunk_size, int min_len, uint8_t *read_out)
+{
+	yakb_ref_flow_t f;
+	yakb_ref_flow_init(&f, workers, chunk_size, min_len);
+	int64_t i = 0;
+	for (; i < n; ++i) {
+		if (lens[i] == -2) { read_out[i] = 0; if (!yakb_ref_flow_bad(&f)) { ++i; break; } }
+		else { read_out[i] = 1; yakb_ref_flow_record(&f, lens[i]); }
+	}
+	for (; i < n; ++i) read_out[i] = 0;
+}
+
 extern "C" void yakb_fastx_set_chunk(void *reader, int64_t chunk_size) { ((FastxReader*)reader)->set_ref_chunk(chunk_size); }
 extern "C" void yakb_pfastx_set_chunk(void *reader, int64_t chunk_size) { ((ParallelFastx*)reader)->set_ref_chunk(chunk_size); }
 
@@ -989,8 +1003,8 @@ extern "C" void yak_qv(const yak_qopt_t *opt, const char *fn, const yak_ch_t *ch
 	FastxReader rd;
 	if (!rd.open(fn)) return;
 	bool done = false;
-	int64_t ref_n = 0, ref_size = 0;
-	int ref_workers = 2;
+	yakb_ref_flow_t flow;
+	yakb_ref_flow_init(&flow, 2, opt->chunk_size, 0); // bseq_read under kt_pipeline(2, ...): qv.c:94,126
 	std::vector<uint8_t> buf;
 	std::vector<std::string> names;
 	std::vector<int32_t> tot, non0;
@@ -1000,14 +1014,12 @@ extern "C" void yak_qv(const yak_qopt_t *opt, const char *fn, const yak_ch_t *ch
 		buf.clear(); names.clear();
 		while (buf.size() < cap) { // bseq.c:33-57: a batch closes once it holds >= chunk_size bases
 			int64_t len = rd.next();
-			if (len == -2) { // a truncated FASTQ record ends the reference's bseq_read call; an empty call retires one of the two pipeline workers (qv.c:126, kthread.c:119)
-				if (ref_n == 0 && --ref_workers == 0) { done = true; break; }
-				ref_n = ref_size = 0;
+			if (len == -2) { // a truncated FASTQ record: csrc/ref_flow.h
+				if (!yakb_ref_flow_bad(&flow)) { done = true; break; }
 				continue;
 			}
 			if (len < 0) { done = true; break; }
-			++ref_n; ref_size += len;
-			if (ref_size >= std::max<int64_t>(opt->chunk_size, 1)) ref_n = ref_size = 0;
+			yakb_ref_flow_record(&flow, len);
 			buf.insert(buf.end(), rd.seq().begin(), rd.seq().end());
 			buf.push_back('\n');
 			off.push_back(buf.size());

@@ -37,7 +37,7 @@ bool FastxReader::open(const char *fn)
 	gzbuffer(fp_, 1u << 20);
 	buf_.resize(kBuf);
 	beg_ = end_ = 0; eof_ = false; last_ = 0;
-	ref_sum_ = 0; ref_workers_ = 3;
+	yakb_ref_flow_init(&flow_, 3, ref_chunk_, 0);
 	if (!getenv("YAKB_NO_READAHEAD")) {
 		ahead_ = new Ahead;
 		Ahead *a = ahead_;
@@ -156,7 +156,7 @@ size_t FastxReader::fill(uint8_t *dst, size_t cap, size_t target, int min_len, i
 	}
 	// close the record being parsed: keep it (terminator appended) or drop it
 	auto finish_record = [&](bool keep) {
-		if (keep && cur_len_ >= min_len) { ref_sum_ += cur_len_; if (ref_sum_ >= ref_chunk_) ref_sum_ = 0; } // count.c:105-106
+		if (keep && cur_len_ >= min_len) yakb_ref_flow_record(&flow_, cur_len_); // count.c:95,105-106
 		if (in_carry_) {
 			if (keep && cur_len_ >= min_len) carry_ready_ = true; else carry_.clear();
 			in_carry_ = false;
@@ -222,8 +222,8 @@ size_t FastxReader::fill(uint8_t *dst, size_t cap, size_t target, int min_len, i
 				finish_record(ok);
 				st_ = S_FIND; last_ = 0;
 				if (!ok) { // kseq's -2 ends the reference's step-0 call; see set_ref_chunk()
-					if (ref_sum_ == 0 && --ref_workers_ <= 0) { eof_ = true; beg_ = end_; *done = true; break; }
-					ref_sum_ = 0; // the next call resumes at the next header character (state S_FIND, last_ 0)
+					if (!yakb_ref_flow_bad(&flow_)) { eof_ = true; beg_ = end_; *done = true; break; }
+					// else the next call resumes at the next header character (state S_FIND, last_ 0)
 				}
 				continue;
 			}

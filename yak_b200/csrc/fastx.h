@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 #include <zlib.h>
+#include "ref_flow.h"
 
 namespace yakb {
 
@@ -30,7 +31,7 @@ public:
 	// does: its step-0 call ends at such a record; a call that had collected nothing (records >= min_len bases; a call
 	// is also full at chunk_size bases, count.c:106) retires one of the pipeline's three workers, the third ends the
 	// input (count.c:109,162; kthread.c:119).  chunk_size is the reference's -K.
-	void set_ref_chunk(int64_t chunk_size) { ref_chunk_ = chunk_size > 0 ? chunk_size : 1; }
+	void set_ref_chunk(int64_t chunk_size) { ref_chunk_ = chunk_size > 0 ? chunk_size : 1; flow_.chunk = ref_chunk_; }
 
 private:
 	// gzip / stdin input is read (and inflated) by a helper thread a few blocks ahead of the parser, so that
@@ -56,8 +57,8 @@ private:
 	std::string carry_;        // a record that did not fit the caller's buffer
 	bool carry_ready_ = false; // carry_ holds a COMPLETE record waiting for the next fill()
 	bool in_carry_ = false;    // the current record is being collected in carry_
-	int64_t ref_chunk_ = 10000000, ref_sum_ = 0; // yak_copt_init's default (misc.c:31); bases the reference's current call holds
-	int ref_workers_ = 3;
+	int64_t ref_chunk_ = 10000000;               // yak_copt_init's default (misc.c:31)
+	yakb_ref_flow_t flow_ = {3, 0, 0, 0, 10000000}; // count.c:162; min_len 0: fill() only reports records it keeps
 };
 
 } // namespace yakb
