@@ -594,3 +594,53 @@ def test_ref_flow_rule_of_the_library(seed):
         O_.yo_reader_close.argtypes = [C.c_void_p]
         want = [s for _, ss in TS.batches(O_, p, chunk) for s in ss]
         assert [seqs[i].encode() for i in range(n) if out[i]] == want, (seed, chunk)
+
+
+def test_qv_solver_randomised_against_reference_function():
+    """cli/qv_solve.c against the reference's own yak_qv_solve (qv.c:146-244, called through oracle/_ref/libyakref.so) on
+    random k-mer spectra: every printed figure identical, every double within 1e-9 relative"""
+    if not os.path.exists(O.REF_LIB):
+        pytest.skip("oracle/_ref not built")
+    src = os.path.join(ROOT, "yak_b200", "cli", "qv_solve.c")
+    so = os.path.join(util.TMP, "yakb_qvsolve2.so")
+    subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), "-o", so, src, "-lm"], check=True)
+
+    class Qs(C.Structure):
+        _fields_ = [("tot", C.c_int64), ("qv_raw", C.c_double), ("qv", C.c_double), ("cov", C.c_double), ("err", C.c_double),
+                    ("fpr_lower", C.c_double), ("fpr_upper", C.c_double), ("adj_cnt", C.c_double * 1024)]
+    libs = [C.CDLL(so), C.CDLL(O.REF_LIB)]
+    for S in libs:
+        S.yak_qv_solve.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int, C.c_double, C.POINTER(Qs)]
+        S.yak_qv_solve.restype = C.c_int
+    rng = np.random.default_rng(77)
+    for trial in range(60):
+        cov = float(rng.choice([4, 12, 21, 35, 80, 300]))
+        G_ = int(rng.choice([1e5, 3e6, 2e8]))
+        x = np.arange(1024)
+        with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+            logp = x * np.log(cov) - cov - np.array([float(np.sum(np.log(np.arange(1, i + 1)))) for i in x])
+        peak = np.exp(logp)
+        hist = (G_ * peak + G_ * 0.02 * 0.5 ** x * (x > 0)).astype(np.int64)     # genomic peak + error k-mers
+        hist[1023] += int(G_ * 1e-4)
+        if trial % 7 == 0:
+            hist = hist // int(rng.choice([1000, 100000]))                       # thin spectra too (an all-zero one makes the reference read cnt[-1])
+        if trial % 11 == 0:
+            hist[int(rng.integers(2, 1000))] = 0
+        cnt = (hist * float(rng.uniform(0.5, 1.2))).astype(np.int64)
+        cnt[0] = int(rng.integers(0, max(2, G_ // 1000)))
+        if cnt[2:1023].max() <= 0:
+            continue
+        k = int(rng.choice([15, 21, 31]))
+        fpr = float(rng.choice([0.00004, 0.001, 0.0]))
+        res = []
+        for S in libs:
+            qs = Qs()
+            rc = S.yak_qv_solve((C.c_int64 * 1024)(*hist.tolist()), (C.c_int64 * 1024)(*cnt.tolist()), k, fpr, C.byref(qs))
+            res.append((rc, qs))
+        (r0, a), (r1, b) = res
+        assert r0 == r1, trial
+        fa = ["%.3f" % a.adj_cnt[i] for i in range(1024)] + ["%.3g %.3g" % (a.fpr_lower, a.fpr_upper), "%d %.3f" % (a.tot, a.err), "%.3f" % a.cov, "%.3f %.3f" % (a.qv_raw, a.qv)]
+        fb = ["%.3f" % b.adj_cnt[i] for i in range(1024)] + ["%.3g %.3g" % (b.fpr_lower, b.fpr_upper), "%d %.3f" % (b.tot, b.err), "%.3f" % b.cov, "%.3f %.3f" % (b.qv_raw, b.qv)]
+        assert fa == fb, trial
+        for u, v in zip([a.qv_raw, a.qv, a.cov, a.err, a.fpr_lower, a.fpr_upper] + list(a.adj_cnt), [b.qv_raw, b.qv, b.cov, b.err, b.fpr_lower, b.fpr_upper] + list(b.adj_cnt)):
+            assert (u == v) or (np.isnan(u) and np.isnan(v)) or abs(u - v) <= 1e-9 * max(abs(u), abs(v)), (trial, u, v)
