@@ -644,3 +644,34 @@ def test_qv_solver_randomised_against_reference_function():
         assert fa == fb, trial
         for u, v in zip([a.qv_raw, a.qv, a.cov, a.err, a.fpr_lower, a.fpr_upper] + list(a.adj_cnt), [b.qv_raw, b.qv, b.cov, b.err, b.fpr_lower, b.fpr_upper] + list(b.adj_cnt)):
             assert (u == v) or (np.isnan(u) and np.isnan(v)) or abs(u - v) <= 1e-9 * max(abs(u), abs(v)), (trial, u, v)
+
+
+def test_cli_inspect_randomised_against_reference_binary():
+    """`yak-b200 inspect x.yak` (inspect.c:8-106, single-file mode: no table, no GPU) against the reference binary's stdout on
+    tables of random k / -p / -b"""
+    if not os.path.exists(O.REF_YAK):
+        pytest.skip("oracle/_ref not built")
+    from yak_b200 import synth
+    exe = os.path.join(ROOT, "yak_b200", "bin", "yak-b200")
+    rng = np.random.default_rng(31)
+    fa = os.path.join(util.TMP, "yakb_insp.fa")
+    with open(fa, "wb") as f:
+        f.write(synth.reads_file_bytes(3, 20_000, 4, 3000, 150, 0.01, 2))
+    for trial in range(6):
+        k, pre = int(rng.choice([15, 31, 47, 63])), int(rng.integers(10, 14))
+        b = int(rng.choice([0, pre + 10]))
+        y = os.path.join(util.TMP, "yakb_insp.yak")
+        h, _ = O.count_file(fa, k=k, pre=pre, bf_shift=b)
+        assert O.lib().yo_ch_dump(h, y.encode()) == 0
+        O.lib().yo_ch_destroy(h)
+        mine = subprocess.run([exe, "inspect", y], capture_output=True)
+        ref = subprocess.run([O.REF_YAK, "inspect", y], capture_output=True)
+        assert mine.returncode == ref.returncode == 0
+        assert mine.stdout == ref.stdout and len(ref.stdout) > 100, (k, pre, b)
+    # error paths: missing file, wrong magic (inspect.c:18-30)
+    bad = os.path.join(util.TMP, "yakb_insp_bad.yak")
+    open(bad, "wb").write(b"NOPE" + b"\0" * 64)
+    for args in (["inspect"], ["inspect", "/nonexistent.yak"], ["inspect", bad]):
+        m = subprocess.run([exe] + args, capture_output=True)
+        r = subprocess.run([O.REF_YAK] + args, capture_output=True)
+        assert (m.returncode != 0) == (r.returncode != 0) and m.stdout == r.stdout, args
