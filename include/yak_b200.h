@@ -98,6 +98,10 @@ void yakb_fastx_set_chunk(void *reader, int64_t chunk_size);
  * read_out[i] = 1 if the reference reads record i with `workers` pipeline threads (3 for count, 2 for the scanners) */
 void yakb_ref_flow_sim(const int64_t *lens, int64_t n, int workers, int64_t chunk_size, int min_len, uint8_t *read_out);
 void yakb_pfastx_set_chunk(void *reader, int64_t chunk_size);
+/* the reference's pipeline threads for the caller being served (csrc/ref_flow.h): 3 = yak count (the default), 2 = qv and the
+ * scanners (with flow_min_len 0: bseq_read keeps every record), 0 = yak_recount's plain loop, which ends at the first such record */
+void yakb_fastx_set_workers(void *reader, int workers);
+void yakb_pfastx_set_flow(void *reader, int64_t chunk_size, int workers, int flow_min_len);
 void yakb_pfastx_close(void *reader);
 /* skip n_skip records, then append up to n_take records (those of length >= min_len) to buf as
  * "SEQ\n"; returns the records consumed (-1: buf too small).  Lets each rank of a multi-GPU job

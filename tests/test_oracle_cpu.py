@@ -291,13 +291,15 @@ def test_qv_solver_matches_reference_output():
     assert lines == want
 
 
-def _fill_all(path, cap, target, min_len, chunk=0):
+def _fill_all(path, cap, target, min_len, chunk=0, workers=None):
     """Drive yakb_fastx_fill the way yak_count does; returns the concatenated 'SEQ\\n' stream."""
     from yak_b200 import capi
     L = capi.lib()
     r = L.yakb_fastx_open(path.encode())
     if chunk:
         L.yakb_fastx_set_chunk(r, chunk)
+    if workers is not None:
+        L.yakb_fastx_set_workers(r, workers)
     out, nseq = bytearray(), 0
     buf = C.create_string_buffer(cap)
     while True:
@@ -348,13 +350,15 @@ def test_bulk_fill_equals_record_reader(cap, target):
     assert _fill_all(big, max(cap, 4096), target, 0)[0] == want
 
 
-def _pfill_all(path, block, threads, cap, target, min_len, chunk=0):
+def _pfill_all(path, block, threads, cap, target, min_len, chunk=0, workers=None):
     from yak_b200 import capi
     L = capi.lib()
     r = L.yakb_pfastx_open(path.encode(), block, threads)
     assert r
     if chunk:
         L.yakb_pfastx_set_chunk(r, chunk)
+    if workers is not None:
+        L.yakb_pfastx_set_flow(r, chunk or 10_000_000, workers, -1)
     out, nseq = bytearray(), 0
     buf = C.create_string_buffer(cap)
     while True:
@@ -515,6 +519,10 @@ def test_parallel_reader_randomised_against_sequential(seed):
             target = int(rng.integers(1, cap + 1))
             got, gn, redo = _pfill_all(p, block, threads, cap, target, min_len, chunk)
             assert got == want and gn == wn, (seed, block, threads, cap, target, min_len, chunk, redo)
+    # yak_recount's plain loop (count.c:176) ends at the first truncated record: workers = 0
+    plain = b"".join(s + b"\n" for _, s in (r for r in _records_oracle(p) if not isinstance(r, int)))
+    assert _fill_all(p, 1 << 22, 1 << 22, 0, workers=0)[0] == plain
+    assert _pfill_all(p, 4096, 4, 1 << 22, 1 << 22, 0, workers=0)[0] == plain
     # the record readers themselves on the same adversarial file: product == oracle (kseq restatement) record by record,
     # and the oracle's whole count == the UNMODIFIED reference binary's .yak (where oracle/_ref is built), for several -K
     assert _records_product(p) == _records_oracle(p)

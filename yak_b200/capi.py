@@ -104,6 +104,8 @@ def lib() -> C.CDLL:
         "yakb_fastx_set_chunk": (None, [vp, i64]),
         "yakb_ref_flow_sim": (None, [C.POINTER(i64), i64, C.c_int, i64, C.c_int, C.POINTER(C.c_uint8)]),
         "yakb_pfastx_set_chunk": (None, [vp, i64]),
+        "yakb_fastx_set_workers": (None, [vp, C.c_int]),
+        "yakb_pfastx_set_flow": (None, [vp, i64, C.c_int, C.c_int]),
         "yakb_pfastx_close": (None, [vp]),
         "yakb_fastx_read_slice": (i64, [vp, i64, i64, C.c_int, vp, u64, C.POINTER(u64), C.POINTER(i64)]),
         "yakb_prof_enable": (None, [C.c_int]),

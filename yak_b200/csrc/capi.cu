@@ -670,6 +670,8 @@ extern "C" void yakb_ref_flow_sim(const int64_t *lens, int64_t n, int workers, i
 
 extern "C" void yakb_fastx_set_chunk(void *reader, int64_t chunk_size) { ((FastxReader*)reader)->set_ref_chunk(chunk_size); }
 extern "C" void yakb_pfastx_set_chunk(void *reader, int64_t chunk_size) { ((ParallelFastx*)reader)->set_ref_chunk(chunk_size); }
+extern "C" void yakb_fastx_set_workers(void *reader, int workers) { ((FastxReader*)reader)->set_ref_workers(workers); }
+extern "C" void yakb_pfastx_set_flow(void *reader, int64_t chunk_size, int workers, int flow_min_len) { ((ParallelFastx*)reader)->set_ref_flow(chunk_size, workers, flow_min_len); }
 
 extern "C" void *yakb_pfastx_open(const char *fn, uint64_t block_bytes, int threads)
 {
@@ -760,7 +762,12 @@ PinnedPool g_pinned;
 // Three things overlap: the reader's pool parses ahead of the consumer, the producer thread stitches
 // batch i+1 into pinned memory and copies it to the device on its own stream, the main thread runs
 // the kernels of batch i.
-extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *h0)
+static yak_ch_t *count_impl(const char *fn, const yak_copt_t *opt, yak_ch_t *h0, int ref_workers);
+extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *h0) { return count_impl(fn, opt, h0, 3); } // count.c:162
+
+// ref_workers: the reference's pipeline threads for this entry point (what follows a truncated FASTQ record depends on them,
+// csrc/ref_flow.h); 0 = yak_recount's plain read loop
+static yak_ch_t *count_impl(const char *fn, const yak_copt_t *opt, yak_ch_t *h0, int ref_workers)
 {
 	GUARD_BEGIN
 	StageTimer tm("yak_count");
@@ -768,7 +775,8 @@ extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *
 	ParallelFastx prd; // plain regular files are parsed by several threads; gzip / stdin by the sequential reader
 	const bool par = !getenv("YAKB_SERIAL_PARSE") && prd.open(fn);
 	if (!par && !rd.open(fn)) return 0;
-	prd.set_ref_chunk(opt->chunk_size); rd.set_ref_chunk(opt->chunk_size); // -K decides what follows a truncated FASTQ record
+	prd.set_ref_flow(opt->chunk_size, ref_workers, -1); // -K and the pipeline decide what follows a truncated FASTQ record
+	rd.set_ref_chunk(opt->chunk_size); rd.set_ref_workers(ref_workers);
 	yak_ch_t *h = h0;
 	if (h0) assert(h0->k == opt->k && h0->pre == opt->pre);
 	else h = yak_ch_init(opt->k, opt->pre, opt->bf_n_hash, opt->bf_shift);
@@ -854,8 +862,9 @@ extern "C" void yak_recount(const char *fn, yak_ch_t *h) // count.c:168-193: cle
 	if (probe == 0) return; // count.c:172
 	if (probe != stdin) fclose(probe);
 	yak_ch_clear(h, 1);
-	// NB the reference does not drop reads shorter than k here, which changes nothing: they hold no k-mer
-	yak_count(fn, &o, h);
+	// NB the reference does not drop reads shorter than k here, which changes nothing: they hold no k-mer.  Its loop is a
+	// plain `while (kseq_read(ks) >= 0)` (count.c:176): the first truncated FASTQ record ends it.
+	count_impl(fn, &o, h, 0);
 }
 
 // ------------------------------------------------------------------ qv

@@ -32,6 +32,8 @@ public:
 	// is also full at chunk_size bases, count.c:106) retires one of the pipeline's three workers, the third ends the
 	// input (count.c:109,162; kthread.c:119).  chunk_size is the reference's -K.
 	void set_ref_chunk(int64_t chunk_size) { ref_chunk_ = chunk_size > 0 ? chunk_size : 1; flow_.chunk = ref_chunk_; }
+	// workers = 3 is `yak count`; workers = 0 a plain read loop that ends at the first truncated record (yak_recount, count.c:176)
+	void set_ref_workers(int workers) { flow_.workers = workers; }
 
 private:
 	// gzip / stdin input is read (and inflated) by a helper thread a few blocks ahead of the parser, so that

@@ -301,6 +301,7 @@ bool ParallelFastx::work_one(std::unique_lock<std::mutex> &lk, bool may_parse)
 // outputs do not keep - so on a bad record, and only then, the stretch since the last decision is parsed again, sequentially.
 bool ParallelFastx::ref_resumes(uint64_t bad_off, int min_len)
 {
+	if (ref_workers0_ <= 0) return false; // a plain read loop (yak_recount, count.c:176): the first truncated record ends it
 	FastxCore e;
 	std::vector<uint8_t> scratch;
 	int64_t sum = 0, cnt = 0; // bases and records the reference's current call holds

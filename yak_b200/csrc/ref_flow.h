@@ -29,6 +29,7 @@ static inline void yakb_ref_flow_record(yakb_ref_flow_t *f, int64_t len)
 /* kseq_read returned -2: 1 = reading goes on behind the record, 0 = the input ends here */
 static inline int yakb_ref_flow_bad(yakb_ref_flow_t *f)
 {
+	if (f->workers <= 0) return 0; /* initialised with 0 workers: a plain `while (kseq_read(ks) >= 0)` loop (yak_recount, count.c:176) */
 	if (f->n == 0 && --f->workers <= 0) return 0;
 	f->n = f->size = 0;
 	return 1;
