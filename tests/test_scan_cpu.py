@@ -188,3 +188,65 @@ def test_restore_core_modes_of_the_oracle(env):
     assert sum(hist) == first + n_io[1] and all(hist[i] == 0 for i in range(16, 1024)) and hist[0] == 0
     assert hist[2] > 0 and hist[8] > 0 and hist[10] > hist[2]   # specific to one parent / class 2 in both
     O.yo_ch_destroy(ch)
+
+
+def _random_contigs(rng, a, b, c, path):
+    """contigs cut from the three genomes, mixed within a contig, with Ns / lower case / short ones, FASTA or FASTQ"""
+    from yak_b200 import synth
+    fastq = rng.random() < 0.3
+    out = bytearray()
+    for i in range(int(rng.integers(2, 9))):
+        segs = []
+        for _ in range(int(rng.integers(1, 5))):
+            g = (a, b, c)[int(rng.integers(0, 3))]
+            st, ln = int(rng.integers(0, S.G - 4000)), int(rng.integers(10, 4000))
+            segs.append(g[st:st + ln])
+        x = np.concatenate(segs).copy()
+        m = rng.random(x.size) < 0.002
+        x[m] = (x[m] + 1) & 3
+        asc = bytearray(synth.codes_to_ascii(x).tobytes())
+        for _ in range(int(rng.integers(0, 3))):
+            p = int(rng.integers(0, len(asc)))
+            asc[p:p + int(rng.integers(1, 30))] = b"N" * min(int(rng.integers(1, 30)), len(asc) - p)
+        if rng.random() < 0.3:
+            asc = asc.lower()
+        if fastq:
+            out += b"@c%d x\n" % i + bytes(asc) + b"\n+\n" + b"I" * len(asc) + b"\n"
+        else:
+            w = int(rng.choice([0, 60, 1000]))
+            body = bytes(asc) if not w else b"\n".join(bytes(asc[q:q + w]) for q in range(0, len(asc), w))
+            out += b">c%d x\n" % i + body + b"\n"
+    open(path, "wb").write(bytes(out))
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_scan_logic_randomised_against_reference_binary(env, seed):
+    """random contigs and random options: the reference binary's stdout (-t1) against oracle lookups + cli/scan_logic.c"""
+    if not os.path.exists(oracle_lib.REF_YAK):
+        pytest.skip("oracle/_ref not built")
+    logic, libc, O, paths = env
+    rng = np.random.default_rng(500 + seed)
+    a, b, c = S.genomes()
+    paths = dict(paths)
+    for tag in ("rc1.fx", "rc2.fx"):
+        paths[tag] = os.path.join(util.TMP, f"yakb_scan_rnd{seed}_{tag}")
+        _random_contigs(rng, a, b, c, paths[tag])
+    k47 = rng.random() < 0.25
+    pat, mat = ("{pat47.yak}", "{mat47.yak}") if k47 else ("{pat.yak}", "{mat.yak}")
+    which = seed % 4
+    if which == 0:
+        cmd = ["triobin", "-t1", f"-c{int(rng.integers(1, 5))}", f"-d{int(rng.integers(2, 12))}", f"-r{float(rng.choice([0.1, 0.33, 0.9]))}"]
+        cmd += (["-p"] if rng.random() < 0.5 else []) + [pat, mat, "{rc1.fx}"]
+    elif which == 1:
+        cmd = ["trioeval", "-t1", f"-c{int(rng.integers(1, 5))}", f"-d{int(rng.integers(2, 12))}", f"-n{int(rng.integers(1, 6))}"]
+        cmd += (["-e"] if rng.random() < 0.5 else []) + (["-F"] if rng.random() < 0.3 else []) + [pat, mat, "{rc1.fx}"]
+    elif which == 2:
+        cmd = ["chkerr", "-t1", f"-c{int(rng.integers(0, 9))}", f"-s{int(rng.integers(0, 9))}", mat if rng.random() < 0.5 else pat, "{rc1.fx}"]
+    else:
+        cmd = ["sexchr", "-t1"] + ([f"-K{int(rng.choice([500, 3000, 100000]))}"] if rng.random() < 0.6 else [])
+        cmd += ["{pat.yak}", "{third.yak}", "{mat.yak}", "{rc1.fx}", "{rc2.fx}"]
+    ref = subprocess.run([oracle_lib.REF_YAK] + S.argv(cmd, paths), capture_output=True)
+    assert ref.returncode == 0, ref.stderr.decode()[-500:]
+    env2 = (logic, libc, O, paths)
+    got = run_case(env2, cmd)
+    assert got == ref.stdout, (cmd, len(got), len(ref.stdout))
