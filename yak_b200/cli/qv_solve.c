@@ -63,7 +63,9 @@ int yak_qv_solve(const int64_t *hist, const int64_t *cnt, int kmer, double fpr, 
 		if (peak_cnt < cnt[c]) peak_cnt = cnt[c], peak = c;
 	for (c = 2, valley_cnt = peak_cnt; c < peak; ++c)
 		if (valley_cnt > cnt[c]) valley_cnt = cnt[c], valley = c;
-	qs->cov = (double)cnt[peak] / hist[peak];
+	/* no query k-mer with a count in 2..1022: the reference evaluates cnt[-1] / hist[-1] here (undefined; its binary prints
+	 * -nan, i.e. 0/0, unless the table holds saturated k-mers).  Say 0/0 and be deterministic. */
+	qs->cov = peak >= 0 ? (double)cnt[peak] / hist[peak] : 0.0 / (peak + 1.0);
 
 	qs->fpr_upper = 1.0;
 	for (c = 2; c < peak; ++c) {
