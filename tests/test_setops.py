@@ -166,3 +166,61 @@ def test_cli_setop_commands_equal_reference_binary():
         r1 = subprocess.run([O.REF_YAK, "print"] + flags + [fc], check=True, capture_output=True).stdout
         r2 = subprocess.run([exe, "print"] + flags + [fc], check=True, capture_output=True).stdout
         assert r1 == r2 and len(r1) > 1000
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_LIB), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_random_scripts_equal_reference_functions(seed):
+    """random sequences of table operations - tighten / setcnt / shrink / merge / subtract / isec and yak_ch_restore_core
+    into the table in every mode - on the reference's own functions and on the oracle: same .yak bytes after every step"""
+    import numpy as np
+    from yak_b200.capi import YakCh
+    rng = np.random.default_rng(300 + seed)
+    R = C.CDLL(O.REF_LIB)
+    ChP = C.POINTER(YakCh)
+    R.yak_ch_restore.restype = ChP; R.yak_ch_restore.argtypes = [C.c_char_p]
+    R.yak_ch_restore_core.restype = ChP
+    R.yak_ch_dump.argtypes = [ChP, C.c_char_p]
+    R.yak_ch_destroy.argtypes = [ChP]
+    R.yak_ch_tighten.argtypes = [ChP]
+    R.yak_ch_setcnt.argtypes = [ChP, C.c_int, C.c_int]
+    R.yak_ch_shrink.argtypes = [ChP, C.c_int, C.c_int, C.c_int]
+    R.yak_ch_merge.argtypes = [ChP, ChP, C.c_int, C.c_int, C.c_int, C.c_int]
+    R.yak_ch_subtract.argtypes = [ChP, ChP, C.c_int]
+    R.yak_ch_isec.argtypes = [ChP, ChP, C.c_int]
+    L = O.lib()
+    L.yo_ch_restore_core.restype = C.POINTER(O.YoCh)
+    L.yo_ch_restore_core.argtypes = [C.POINTER(O.YoCh), C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+    files = dict(zip("ABC", _yak_files()))
+    tmp = os.path.join(util.TMP, "yakb_setops_rnd.yak")
+    start = str(rng.choice(list("ABC")))
+    hr, ho = R.yak_ch_restore(files[start].encode()), L.yo_ch_restore(files[start].encode())
+    for step in range(int(rng.integers(2, 7))):
+        op = str(rng.choice(["tighten", "setcnt", "shrink", "merge", "subtract", "isec", "load"]))
+        x = files[str(rng.choice(list("ABC")))].encode()
+        if op == "tighten":
+            R.yak_ch_tighten(hr); L.yo_ch_tighten(ho)
+        elif op == "setcnt":
+            c = int(rng.integers(0, 1024))
+            R.yak_ch_setcnt(hr, c, 2); L.yo_ch_setcnt(ho, c)
+        elif op == "shrink":
+            lo, hi = int(rng.integers(0, 6)), int(rng.choice([3, 20, 1023]))
+            R.yak_ch_shrink(hr, lo, hi, 2); L.yo_ch_shrink(ho, lo, hi)
+        elif op == "merge":
+            lo, hi, pr = int(rng.integers(0, 4)), int(rng.choice([5, 1023])), int(rng.integers(0, 2))
+            R.yak_ch_merge(hr, R.yak_ch_restore(x), lo, hi, 2, pr); L.yo_ch_merge(ho, L.yo_ch_restore(x), lo, hi, pr)
+        elif op in ("subtract", "isec"):
+            a, b = R.yak_ch_restore(x), L.yo_ch_restore(x)
+            (R.yak_ch_subtract if op == "subtract" else R.yak_ch_isec)(hr, a, 2)
+            (L.yo_ch_subtract if op == "subtract" else L.yo_ch_isec)(ho, b)
+            R.yak_ch_destroy(a); L.yo_ch_destroy(b)
+        else:   # yak_ch_restore_core(ch0 != NULL, mode): htab.c:436-472
+            mode = int(rng.integers(1, 7))
+            mn, md = int(rng.integers(1, 4)), int(rng.integers(3, 9))
+            R.yak_ch_restore_core.argtypes = [ChP, C.c_char_p, C.c_int, C.c_int, C.c_int]
+            assert R.yak_ch_restore_core(hr, x, mode, mn, md)
+            assert L.yo_ch_restore_core(ho, x, mode, mn, md, None)
+        R.yak_ch_dump(hr, tmp.encode())
+        got, want = O.dump_bytes(ho), open(tmp, "rb").read()
+        assert got == want, f"seed {seed} step {step} {op}: " + util.explain_diff(got, want)
+    R.yak_ch_destroy(hr); L.yo_ch_destroy(ho)
