@@ -8,7 +8,8 @@ synthetic stream as yak_b200/synth.py generated on the device.  A *step* is one 
 (pack -> fused extract+probe -> ordered bloom/insert of pending events -> journal).  Steps are
 consecutive batches from the start of the job; the table, bloom and journal persist across steps.
 The default 3 + 297 steps are the WHOLE first pass of cfg2 (600 M reads = 90 Gbp = 30x of 3 Gbp),
-table growth and rehash included.
+table growth and rehash included (N ranks take N batches per step, so the default is 300 / N steps there:
+the -b37 filter is sized for 90 Gbp, not for N times that).
 Each step is bracketed by its own pair of CUDA events; the step's input batch is generated on the
 device just before it, outside the timed region (max over ranks of the summed step times).
 
@@ -253,7 +254,8 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=297)
+    ap.add_argument("--steps", type=int, default=None,
+                    help="timed steps; default = the whole first pass of cfg2 (600 M reads): 300 / gpus batches per rank, minus the warm-up")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome", type=int, default=3_000_000_000)
@@ -266,6 +268,9 @@ def main():
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     globals()["K"] = args.k
+    if args.steps is None:   # N ranks consume N batches per step: the default job stays cfg2's 600 M reads at every N
+        world_env = max(1, int(os.environ.get("WORLD_SIZE", str(args.gpus))))
+        args.steps = max(1, 300 // world_env - args.warmup)
     if args.impl == "reference":
         return run_reference_arm(args)
 

@@ -224,3 +224,94 @@ def test_oracle_random_scripts_equal_reference_functions(seed):
         got, want = O.dump_bytes(ho), open(tmp, "rb").read()
         assert got == want, f"seed {seed} step {step} {op}: " + util.explain_diff(got, want)
     R.yak_ch_destroy(hr); L.yo_ch_destroy(ho)
+
+
+CNTASM_CASES = [
+    # (options, number of inputs, start from the table of an earlier run via -i)
+    ([], 3, False),
+    (["-c1", "-x3", "-e1", "-s2"], 4, False),
+    (["-c1", "-x2", "-r", "-e0", "-s1", "-k27", "-p11"], 3, False),
+    (["-c2", "-x1023", "-e2", "-s1"], 4, True),
+]
+
+
+def _cntasm_inputs(n):
+    """n small 'assemblies' sharing most of their sequence: windows of one seeded genome, a few bases changed in each"""
+    import numpy as np
+    from yak_b200 import synth
+    g = synth.genome_codes(4242, 60_000)
+    out = []
+    for i in range(n):
+        p = os.path.join(util.TMP, f"yakb_cntasm_{i}.fa")
+        rng = np.random.default_rng(900 + i)
+        s = g[i * 2000: 40_000 + i * 5000].copy()
+        pos = rng.integers(0, len(s), 150)
+        s[pos] = (s[pos] + rng.integers(1, 4, 150)) & 3
+        seq = np.frombuffer(b"ACGT", dtype=np.uint8)[s]
+        with open(p, "wb") as f:
+            for j, a in enumerate(range(0, len(seq), 9000)):   # a few contigs, a duplicated one so that counts above 1 occur
+                f.write(b">c%d\n" % j + seq[a:a + 9000].tobytes() + b"\n")
+            f.write(b">dup\n" + seq[100:3100].tobytes() + b"\n")
+        out.append(p)
+    return out
+
+
+def _cntasm_oracle(opts, fns, fn_in):
+    """main.c:90-162 on the oracle's functions"""
+    import getopt
+    L = O.lib()
+    o = dict(getopt.getopt(opts, "k:p:c:x:e:s:r")[0])
+    k, pre = int(o.get("-k", 31)), int(o.get("-p", 10))
+    mn, mx, max_out, check_n, pr = int(o.get("-c", 1)), int(o.get("-x", 1)), int(o.get("-e", 0)), int(o.get("-s", 10)), int("-r" in o)
+    h = L.yo_ch_restore(fn_in.encode()) if fn_in else None
+    for n, fn in enumerate(fns, 1):
+        h1, _ = O.count_file(fn, k=k, pre=pre, bf_shift=0)
+        if not h:
+            h = h1
+            L.yo_ch_shrink(h, mn, mx); L.yo_ch_setcnt(h, 1)
+        else:
+            L.yo_ch_merge(h, h1, mn, mx, pr)
+        if n == len(fns) or (n > max_out and n % check_n == 0):
+            L.yo_ch_shrink(h, n - max_out, 1023)
+    L.yo_ch_tighten(h)
+    b = O.dump_bytes(h)
+    L.yo_ch_destroy(h)
+    return b
+
+
+def _cntasm_run(exe, opts, fns, fn_in, out):
+    import subprocess
+    cmd = [exe, "cntasm", "-o", out] + (opts if any(x.startswith("-p") for x in opts) else opts + ["-p10"]) + (["-i", fn_in] if fn_in else []) + fns
+    subprocess.run(cmd, check=True, capture_output=True)
+    return open(out, "rb").read()
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_YAK), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", CNTASM_CASES, ids=lambda c: "cntasm" + "".join(c[0]))
+def test_oracle_cntasm_flow_equals_reference_binary(case):
+    """`yak cntasm` of the reference binary against the same sequence of operations on the oracle"""
+    opts, n, chain = case
+    fns = _cntasm_inputs(n)
+    prev = os.path.join(util.TMP, "yakb_cntasm_prev.yak")
+    if chain:
+        _cntasm_run(O.REF_YAK, ["-c1", "-x1"], fns[:2], None, prev)
+    want = _cntasm_run(O.REF_YAK, opts, fns, prev if chain else None, os.path.join(util.TMP, "yakb_cntasm_ref.yak"))
+    got = _cntasm_oracle(opts, fns, prev if chain else None)
+    assert len(want) > 16 + 8 * 1024 + 8 * 1000          # the case keeps k-mers
+    assert got == want, util.explain_diff(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(O.REF_YAK), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", CNTASM_CASES, ids=lambda c: "cntasm" + "".join(c[0]))
+def test_cli_cntasm_equals_reference_binary(case):
+    opts, n, chain = case
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "yak_b200", "bin", "yak-b200")
+    fns = _cntasm_inputs(n)
+    prev = os.path.join(util.TMP, "yakb_cntasm_prev.yak")
+    if chain:
+        _cntasm_run(O.REF_YAK, ["-c1", "-x1"], fns[:2], None, prev)
+    want = _cntasm_run(O.REF_YAK, opts, fns, prev if chain else None, os.path.join(util.TMP, "yakb_cntasm_ref.yak"))
+    got = _cntasm_run(exe, opts, fns, prev if chain else None, os.path.join(util.TMP, "yakb_cntasm_cli.yak"))
+    assert got == want, util.explain_diff(got, want)

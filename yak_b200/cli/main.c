@@ -1,4 +1,4 @@
-/* yak-b200: the `yak` command line (count / qv / inspect / version) over libyakb200.so.
+/* yak-b200: the `yak` command line (count / recount / cntasm / subtract / isec / print / qv / inspect / version; scanners in scan.c) over libyakb200.so.
  * Plain host C calling the C ABI of include/yak.h; flags, defaults, messages and the two-pass
  * bloom protocol follow the reference CLI (main.c:13-64 count, 163-215 qv, 325-379 dispatch;
  * inspect.c:8-106).  Nothing here touches the GPU directly. */
@@ -184,6 +184,77 @@ static int cmd_recount(int argc, char *argv[])
 	return 0;
 }
 
+/* reference main.c:90-162: one table over several assemblies - count each input, keep its k-mers with min <= count <= max as
+ * "seen once", add the samples up (yak_ch_merge), drop k-mers absent from more than -e samples every -s samples and at the end */
+static int cmd_cntasm(int argc, char *argv[])
+{
+	yak_ch_t *h = 0, *h1;
+	char *fn_in = 0, *fn_out = 0;
+	int c, i, min_cnt = 1, max_cnt = 1, max_out = 0, check_n = 10, pre_resize = 0;
+	yak_copt_t opt;
+	yak_copt_init(&opt);
+	opt.chunk_size = yakb_cli_parse_num("1.9g");
+	while ((c = getopt(argc, argv, "k:p:K:t:i:o:c:x:e:s:r")) >= 0) {
+		if (c == 'k') opt.k = atoi(optarg);
+		else if (c == 'c') min_cnt = atoi(optarg);
+		else if (c == 'x') max_cnt = atoi(optarg);
+		else if (c == 'e') max_out = atoi(optarg);
+		else if (c == 's') check_n = atoi(optarg);
+		else if (c == 'r') pre_resize = 1;
+		else if (c == 'p') opt.pre = atoi(optarg);
+		else if (c == 'K') opt.chunk_size = yakb_cli_parse_num(optarg);
+		else if (c == 't') opt.n_thread = atoi(optarg);
+		else if (c == 'i') fn_in = optarg;
+		else if (c == 'o') fn_out = optarg;
+	}
+	if (argc - optind < 1) {
+		fprintf(stderr, "Usage: yak-b200 cntasm [options] <in1.fa> [in2.fa [...]]\n");
+		fprintf(stderr, "Options:\n");
+		fprintf(stderr, "  -k INT     k-mer size [%d]\n", opt.k);
+		fprintf(stderr, "  -c INT     min count [%d]\n", min_cnt);
+		fprintf(stderr, "  -x INT     max count [%d]\n", max_cnt);
+		fprintf(stderr, "  -p INT     prefix length [%d]\n", opt.pre);
+		fprintf(stderr, "  -r         resize before merging (same result bytes as the reference's -r)\n");
+		fprintf(stderr, "  -t INT     number of worker threads (accepted, unused on the GPU) [%d]\n", opt.n_thread);
+		fprintf(stderr, "  -e INT     exclude a k-mer if absent from INT samples [%d]\n", max_out);
+		fprintf(stderr, "  -s INT     shrink the hash table every INT samples [%d]\n", check_n);
+		fprintf(stderr, "  -K INT     chunk size [1.9g]\n");
+		fprintf(stderr, "  -i FILE    input k-mer dump []\n");
+		fprintf(stderr, "  -o FILE    output k-mer dump []\n");
+		fprintf(stderr, "Note: if input and output file names are identical, input is overwritten\n");
+		return 1;
+	}
+	if (opt.pre < YAK_COUNTER_BITS) { fprintf(stderr, "ERROR: -p should be at least %d\n", YAK_COUNTER_BITS); return 1; }
+	if (opt.k >= 32) { fprintf(stderr, "ERROR: -k must be <=31\n"); return 1; }
+	if (check_n <= 0) check_n = 1; /* the reference divides by -s (main.c:154) */
+	if (fn_in) {
+		h = yak_ch_restore(fn_in);
+		if (h == 0) fprintf(stderr, "WARNING: failed to read %s. Continue anyway\n", fn_in);
+	}
+	for (i = optind; i < argc; ++i) {
+		int n = i - optind + 1; /* samples so far */
+		h1 = yak_count(argv[i], &opt, 0);
+		if (h1 == 0) { /* the reference goes on with a null table here (quirk Q8) and crashes */
+			fprintf(stderr, "ERROR: failed to count '%s' (no such file, or no CUDA device)\n", argv[i]);
+			yak_ch_destroy(h);
+			return 1;
+		}
+		if (h == 0) {
+			h = h1;
+			yak_ch_shrink(h, min_cnt, max_cnt, opt.n_thread);
+			yak_ch_setcnt(h, 1, opt.n_thread);
+		} else yak_ch_merge(h, h1, min_cnt, max_cnt, opt.n_thread, pre_resize); /* frees h1 */
+		if (i == argc - 1 || (n > max_out && n % check_n == 0))
+			yak_ch_shrink(h, n - max_out, YAK_MAX_COUNT, opt.n_thread);
+		fprintf(stderr, "[M::%s::%.3f*%.2f] processed file %s; %ld distinct k-mers in the hash table\n", "main_cntasm",
+		        realtime() - t_real0, cputime() / (realtime() - t_real0), argv[i], (long)h->tot);
+	}
+	yak_ch_tighten(h);
+	if (fn_out) yak_ch_dump(h, fn_out);
+	yak_ch_destroy(h);
+	return 0;
+}
+
 /* reference main.c:217-284: k-mers of the first table absent from (subtract) / present in (isec) the others */
 static int cmd_setop(int argc, char *argv[], int isec)
 {
@@ -241,6 +312,7 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "Command:\n");
 		fprintf(stderr, "  count     count k-mers\n");
 		fprintf(stderr, "  recount   count existing k-mers\n");
+		fprintf(stderr, "  cntasm    collate counts per dataset\n");
 		fprintf(stderr, "  subtract  subtract k-mer sets\n");
 		fprintf(stderr, "  isec      intersect k-mer sets\n");
 		fprintf(stderr, "  print     print k-mers for k<=31\n");
@@ -255,6 +327,7 @@ int main(int argc, char *argv[])
 	}
 	if (strcmp(argv[1], "count") == 0) ret = cmd_count(argc - 1, argv + 1);
 	else if (strcmp(argv[1], "recount") == 0) ret = cmd_recount(argc - 1, argv + 1);
+	else if (strcmp(argv[1], "cntasm") == 0) ret = cmd_cntasm(argc - 1, argv + 1);
 	else if (strcmp(argv[1], "subtract") == 0) ret = cmd_setop(argc - 1, argv + 1, 0);
 	else if (strcmp(argv[1], "isec") == 0) ret = cmd_setop(argc - 1, argv + 1, 1);
 	else if (strcmp(argv[1], "print") == 0) ret = cmd_print(argc - 1, argv + 1);

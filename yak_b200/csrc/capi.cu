@@ -19,6 +19,7 @@
 #include <math.h>
 #include <algorithm>
 #include <mutex>
+#include <sys/stat.h>
 #include <thread>
 #include <atomic>
 #include "ref_flow.h"
@@ -784,7 +785,10 @@ static yak_ch_t *count_impl(const char *fn, const yak_copt_t *opt, yak_ch_t *h0,
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
 	const int create_new = h0 == 0;
-	const uint64_t cap = batch_bases(opt->chunk_size);
+	uint64_t cap = batch_bases(opt->chunk_size);
+	struct stat st;
+	if (par && stat(fn, &st) == 0 && S_ISREG(st.st_mode)) // a batch never holds more than the file: no 2 x 1.9 GB of pinned memory for `cntasm -K1.9g` on a small assembly
+		cap = std::min<uint64_t>(cap, std::max<uint64_t>((uint64_t)st.st_size + 4096, 1u << 20));
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (!b->copy_stream) YAKB_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
