@@ -81,6 +81,11 @@ void yakb_device_cache_trim(void);
 void *yakb_fastx_open(const char *fn);
 int64_t yakb_fastx_next(void *reader, const char **seq, const char **name);
 void yakb_fastx_close(void *reader);
+/* A regular file made of BGZF blocks (bgzip, samtools, most sequencer pipelines) is inflated by a pool of threads
+ * (csrc/bgzf.h; same byte stream as zlib's gzread, reference count.c:150-151).  yakb_fastx_open uses one thread per
+ * core; here bgzf_threads < 0 keeps zlib's sequential reader, job_bytes = inflated bytes per unit of work. */
+void *yakb_fastx_open_bgzf(const char *fn, int bgzf_threads, uint64_t job_bytes);
+int yakb_fastx_bgzf_threads(void *reader);   /* 0 when the input does not go through the pool */
 /* bulk form used by yak_count: append whole records (length >= min_len) as "SEQ\n" until `target`
  * bytes; returns bytes appended; *done = input exhausted; *need != 0: grow buf to that size */
 int64_t yakb_fastx_fill(void *reader, char *buf, uint64_t cap, uint64_t target, int min_len,

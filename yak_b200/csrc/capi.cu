@@ -634,6 +634,14 @@ extern "C" void *yakb_fastx_open(const char *fn)
 	if (!r->open(fn)) { delete r; return 0; }
 	return r;
 }
+// bgzf_threads < 0: zlib's sequential reader even for a BGZF file; 0: one inflating thread per core (csrc/bgzf.h)
+extern "C" void *yakb_fastx_open_bgzf(const char *fn, int bgzf_threads, uint64_t job_bytes)
+{
+	FastxReader *r = new FastxReader;
+	if (!r->open(fn, bgzf_threads, (size_t)job_bytes)) { delete r; return 0; }
+	return r;
+}
+extern "C" int yakb_fastx_bgzf_threads(void *reader) { return ((FastxReader*)reader)->bgzf_threads(); }
 extern "C" int64_t yakb_fastx_next(void *reader, const char **seq, const char **name)
 {
 	FastxReader *r = (FastxReader*)reader;

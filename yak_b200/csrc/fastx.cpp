@@ -29,15 +29,23 @@ struct FastxReader::Ahead {
 	std::thread th;
 };
 
-bool FastxReader::open(const char *fn)
+int FastxReader::bgzf_threads() const { return bgzf_ ? bgzf_->threads() : 0; }
+
+bool FastxReader::open(const char *fn, int bgzf_threads, size_t bgzf_job_bytes)
 {
 	close();
+	buf_.resize(kBuf);
+	beg_ = end_ = 0; eof_ = src_last_ = false; last_ = 0;
+	yakb_ref_flow_init(&flow_, 3, ref_chunk_, 0);
+	if (fn != nullptr && strcmp(fn, "-") != 0 && bgzf_threads >= 0 && !getenv("YAKB_NO_PBGZF")) {
+		bgzf_ = new BgzfPool;
+		if (bgzf_->open(fn, bgzf_threads, bgzf_job_bytes)) return true; // the pool runs ahead of the parser by itself
+		delete bgzf_;
+		bgzf_ = nullptr;
+	}
 	fp_ = (fn == nullptr || strcmp(fn, "-") == 0) ? gzdopen(0, "r") : gzopen(fn, "r");
 	if (!fp_) return false;
 	gzbuffer(fp_, 1u << 20);
-	buf_.resize(kBuf);
-	beg_ = end_ = 0; eof_ = false; last_ = 0;
-	yakb_ref_flow_init(&flow_, 3, ref_chunk_, 0);
 	if (!getenv("YAKB_NO_READAHEAD")) {
 		ahead_ = new Ahead;
 		Ahead *a = ahead_;
@@ -75,22 +83,27 @@ void FastxReader::close()
 	}
 	if (fp_) gzclose(fp_);
 	fp_ = nullptr;
+	delete bgzf_;
+	bgzf_ = nullptr;
 }
 
 int64_t FastxReader::read_block_()
 {
+	if (bgzf_) return bgzf_->next(buf_, &src_last_);
 	if (!ahead_) {
-		const int got = gzread(fp_, buf_.data(), (unsigned)buf_.size());
+		const int got = gzread(fp_, buf_.data(), (unsigned)kBuf);
+		src_last_ = got < (int)kBuf; // a short read is the end
 		return got > 0 ? got : 0;
 	}
 	Ahead *a = ahead_;
 	std::unique_lock<std::mutex> lk(a->mu);
 	a->cv.wait(lk, [a] { return a->count > 0 || a->done; });
-	if (a->count == 0) return 0;
+	if (a->count == 0) { src_last_ = true; return 0; }
 	buf_.swap(a->blk[a->head]);      // the parser owns the block now; the producer refills the other vector
 	const int64_t n = a->len[a->head];
 	a->head = (a->head + 1) % Ahead::N;
 	--a->count;
+	src_last_ = a->done && a->count == 0; // the producer flags its last block in the same critical section that delivers it
 	a->cv.notify_all();
 	return n;
 }
@@ -101,7 +114,7 @@ int FastxReader::getc_()
 		if (eof_) return -1;
 		beg_ = 0;
 		end_ = read_block_();
-		if (end_ < (int64_t)kBuf) eof_ = true;
+		if (src_last_) eof_ = true;
 		if (end_ == 0) return -1;
 	}
 	return buf_[beg_++];
@@ -115,7 +128,7 @@ bool FastxReader::line_(std::string &s, int64_t *count_only)
 			if (eof_) break;
 			beg_ = 0;
 			end_ = read_block_();
-			if (end_ < (int64_t)kBuf) eof_ = true;
+			if (src_last_) eof_ = true;
 			if (end_ == 0) break;
 		}
 		got = true;
@@ -138,7 +151,7 @@ bool FastxReader::refill_()
 	if (eof_) return false;
 	beg_ = 0;
 	end_ = read_block_();
-	if (end_ < (int64_t)kBuf) eof_ = true;
+	if (src_last_) eof_ = true;
 	return end_ > 0;
 }
 

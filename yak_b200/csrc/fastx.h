@@ -6,6 +6,7 @@
 #include <vector>
 #include <zlib.h>
 #include "ref_flow.h"
+#include "bgzf.h"
 
 namespace yakb {
 
@@ -13,7 +14,10 @@ class FastxReader {
 public:
 	FastxReader() {}
 	~FastxReader() { close(); }
-	bool open(const char *fn); // NULL or "-" = stdin (count.c:151)
+	// NULL or "-" = stdin (count.c:151).  A regular file made of BGZF blocks is inflated by a pool of threads (bgzf.h):
+	// bgzf_threads 0 = one per core, < 0 = zlib's sequential reader as for any other gzip file (also YAKB_NO_PBGZF=1)
+	bool open(const char *fn, int bgzf_threads = 0, size_t bgzf_job_bytes = 4u << 20);
+	int bgzf_threads() const;   // 0 when the input is not read through the BGZF pool
 	void close();
 	// next record: sequence bytes (line ends removed) in seq(); returns length, -1 at EOF,
 	// -2 on a truncated quality string (kseq.h:189-191)
@@ -40,7 +44,9 @@ private:
 	// inflating and parsing overlap; YAKB_NO_READAHEAD=1 reads in the parsing thread
 	struct Ahead;
 	Ahead *ahead_ = nullptr;
-	int64_t read_block_();     // next block into buf_; returns its length, 0 at the end of the input
+	BgzfPool *bgzf_ = nullptr;
+	bool src_last_ = false;    // the block read_block_() just returned is the last one
+	int64_t read_block_();     // next block into buf_; returns its length (0 possible at the end of the input), sets src_last_
 	int getc_();
 	// append the rest of the current line to s (without the '\n'); false if nothing was left
 	bool line_(std::string &s, int64_t *count_only);
