@@ -683,3 +683,54 @@ def test_cli_inspect_randomised_against_reference_binary():
         m = subprocess.run([exe] + args, capture_output=True)
         r = subprocess.run([O.REF_YAK] + args, capture_output=True)
         assert (m.returncode != 0) == (r.returncode != 0) and m.stdout == r.stdout, args
+
+
+def test_inspect_two_file_logic_against_reference_binary():
+    """`yak inspect [-m] in1.yak in2.yak` (inspect.c:31-95, stored keys passed to yak_ch_get: quirk Q7): cli/inspect_logic.c over
+    the oracle's yak_ch_get equals the reference binary's stdout on tables of different inputs, k, -p and -m"""
+    if not os.path.exists(O.REF_YAK):
+        pytest.skip("oracle/_ref not built")
+    from yak_b200 import synth
+    so = os.path.join(util.TMP, "yakb_inspect_logic_test.so")
+    cli = os.path.join(ROOT, "yak_b200", "cli")
+    subprocess.run(["gcc", "-O2", "-Wall", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-o", so,
+                    os.path.join(cli, "inspect_logic.c"), os.path.join(cli, "qv_solve.c"), "-lm"], check=True)
+    logic = C.CDLL(so)
+    LOOKUP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int32))
+    logic.yakb_inspect_run.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), LOOKUP, C.c_void_p, C.c_int64]
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p; libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    L = O.lib()
+    rng = np.random.default_rng(77)
+    fa, fb = os.path.join(util.TMP, "yakb_insp2_a.fa"), os.path.join(util.TMP, "yakb_insp2_b.fa")
+    with open(fa, "wb") as f:
+        f.write(synth.reads_file_bytes(3, 8_000, 4, 1200, 150, 0.01, 2))
+    with open(fb, "wb") as f:
+        f.write(synth.reads_file_bytes(3, 8_000, 5, 900, 150, 0.02, 2))
+    y1, y2, outp = (os.path.join(util.TMP, n) for n in ("yakb_insp2_1.yak", "yakb_insp2_2.yak", "yakb_insp2.out"))
+    for trial in range(6):
+        k = int(rng.choice([15, 21, 31]))
+        p1, p2 = int(rng.integers(10, 13)), int(rng.integers(10, 13))
+        for fn, y, pre in ((fa, y1, p1), (fb, y2, p2)):
+            h, _ = O.count_file(fn, k=k, pre=pre, bf_shift=0)
+            assert L.yo_ch_dump(h, y.encode()) == 0
+            L.yo_ch_destroy(h)
+        h2 = L.yo_ch_restore(y2.encode())
+        hist = (C.c_int64 * 1024)()
+        L.yo_ch_hist(h2, hist)
+
+        def lookup(ctx, n, x, out):
+            for i in range(n):
+                out[i] = L.yo_ch_get(h2, x[i])
+            return 0
+        flags = [] if trial % 2 == 0 else ["-m%d" % int(rng.integers(1, 40))]
+        m = int(flags[0][2:]) if flags else 20
+        fp = libc.fopen(outp.encode(), b"w")
+        assert logic.yakb_inspect_run(fp, y1.encode(), m, hist, LOOKUP(lookup), None, int(rng.choice([1, 1000, 1 << 20]))) == 0
+        libc.fclose(fp)
+        L.yo_ch_destroy(h2)
+        ref = subprocess.run([O.REF_YAK, "inspect"] + flags + [y1, y2], capture_output=True)
+        assert ref.returncode == 0
+        got = open(outp, "rb").read()
+        assert got == ref.stdout and got.count(b"\n") > 3, (trial, k, p1, p2, flags)

@@ -315,3 +315,17 @@ def test_cli_cntasm_equals_reference_binary(case):
     want = _cntasm_run(O.REF_YAK, opts, fns, prev if chain else None, os.path.join(util.TMP, "yakb_cntasm_ref.yak"))
     got = _cntasm_run(exe, opts, fns, prev if chain else None, os.path.join(util.TMP, "yakb_cntasm_cli.yak"))
     assert got == want, util.explain_diff(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(O.REF_YAK), reason="oracle/_ref not built")
+def test_cli_inspect_two_files_equals_reference_binary():
+    """`inspect [-m] in1.yak in2.yak`: the lookups of stored keys (quirk Q7) as batched device lookups, stdout of the reference"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "yak_b200", "bin", "yak-b200")
+    fa, fb, fc = _yak_files()
+    for args in ([fa, fb], ["-m7", fb, fa], ["-m40", fc, fa], [fa, fa]):
+        r = subprocess.run([O.REF_YAK, "inspect"] + args, check=True, capture_output=True).stdout
+        m = subprocess.run([exe, "inspect"] + args, check=True, capture_output=True).stdout
+        assert m == r and r.count(b"\n") > 3, args

@@ -10,6 +10,7 @@
 #include <sys/time.h>
 #include <sys/resource.h>
 #include "yak.h"
+#include "yak_b200.h"
 
 int yak_qv_solve(const int64_t *hist, const int64_t *cnt, int kmer, double fpr, yak_qstat_t *qs); /* qv_solve.c */
 int yakb_cmd_triobin(int argc, char *argv[]);  /* scan.c */
@@ -131,40 +132,32 @@ static int cmd_qv(int argc, char *argv[])
 	return 0;
 }
 
-/* single-file mode of the reference's inspect (inspect.c:40-62, 96-103): stream the file, print
- * the count histogram high to low.  (Two-file mode: SURVEY quirk Q7, not implemented.) */
+/* reference inspect.c:8-106; the logic is cli/inspect_logic.c, the lookups of the two-file mode one batched call each */
+typedef int (*yakb_lookup_f)(void *ctx, uint64_t n, const uint64_t *x, int32_t *out);
+int yakb_inspect_run(FILE *out, const char *fn1, int max_cnt, const int64_t *hist2, yakb_lookup_f lookup, void *ctx, int64_t batch);
+static int inspect_lookup(void *ctx, uint64_t n, const uint64_t *x, int32_t *out) { return yakb_ch_get_batch((const yak_ch_t*)ctx, n, x, out); }
+
 static int cmd_inspect(int argc, char *argv[])
 {
-	FILE *fp;
-	char magic[4];
-	uint32_t t[3], u[2], j;
-	int64_t tot[YAK_N_COUNTS], acc = 0;
-	int i, n_sub;
-	if (argc < 2) { fprintf(stderr, "Usage: yak-b200 inspect <in1.yak>\n"); return 1; }
-	if (argc > 2) { fprintf(stderr, "ERROR: two-file inspect is not implemented by yak-b200\n"); return 1; }
-	if ((fp = fopen(argv[1], "rb")) == 0) { fprintf(stderr, "ERROR: failed to open '%s'\n", argv[1]); return 1; }
-	if (fread(magic, 1, 4, fp) != 4 || memcmp(magic, YAK_MAGIC, 4) != 0 || fread(t, 4, 3, fp) != 3 || t[2] != YAK_COUNTER_BITS) {
-		fprintf(stderr, "ERROR: not a .yak file\n");
-		fclose(fp);
+	int c, max_cnt = 20, rc;
+	int64_t hist[YAK_N_COUNTS];
+	yak_ch_t *ch;
+	while ((c = getopt(argc, argv, "m:")) >= 0)
+		if (c == 'm') max_cnt = atoi(optarg);
+	if (argc - optind < 1) {
+		fprintf(stderr, "Usage: yak-b200 inspect [options] <in1.yak> [in2.yak]\n");
+		fprintf(stderr, "Options:\n");
+		fprintf(stderr, "  -m INT    max count (effective with in2.yak) [%d]\n", max_cnt);
+		fprintf(stderr, "Notes: when in2.yak is present, inspect evaluates the k-mer QV of in1.yak and\n");
+		fprintf(stderr, "  the k-mer sensitivity of in2.yak.\n");
 		return 1;
 	}
-	memset(tot, 0, sizeof(tot));
-	n_sub = 1 << t[1];
-	for (i = 0; i < n_sub; ++i) {
-		if (fread(u, 4, 2, fp) != 2) break;
-		for (j = 0; j < u[1]; ++j) {
-			uint64_t key;
-			if (fread(&key, 8, 1, fp) != 1) break;
-			++tot[key & YAK_MAX_COUNT];
-		}
-	}
-	fclose(fp);
-	for (i = YAK_N_COUNTS - 1; i >= 0; --i) {
-		acc += tot[i];
-		if (acc == 0) continue;
-		printf("HS\t%d\t%ld\t%ld\t%ld\n", i, 0L, (long)tot[i], (long)acc);
-	}
-	return 0;
+	if (argc - optind < 2) return yakb_inspect_run(stdout, argv[optind], max_cnt, 0, 0, 0, 1);
+	if ((ch = yak_ch_restore(argv[optind + 1])) == 0) { fprintf(stderr, "ERROR: failed to load '%s'\n", argv[optind + 1]); return 1; }
+	yak_ch_hist(ch, hist, 1);
+	rc = yakb_inspect_run(stdout, argv[optind], max_cnt, hist, inspect_lookup, ch, 16 << 20);
+	yak_ch_destroy(ch);
+	return rc;
 }
 
 /* reference main.c:66-88: tighten, count the k-mers of a table again from other reads */
