@@ -331,3 +331,20 @@ def test_zone_blocked_front_end_is_bit_exact(env):
     r = subprocess.run([sys.executable, "-c", ZONE_SNIPPET.format(root=root, fn=os.path.join(util.TMP, "yakb_zone.fa"))],
                        env=e, capture_output=True, text=True)
     assert r.returncode == 0 and "zone ok" in r.stdout, r.stderr[-3000:]
+
+
+@pytest.mark.skipif(os.environ.get("YAKB_TEST_UNVERIFIED") != "1",
+                    reason="zone_scatter_staged was written without GPU access (end of round 1); set YAKB_TEST_UNVERIFIED=1 to run")
+@pytest.mark.parametrize("env", [
+    {"YAKB_ZONE_MB": "0.02"}, {"YAKB_ZONE_MB": "0.0001"}, {"YAKB_ZONE_MB": "0.02", "YAKB_ZONE_SLACK": "0"}, {"YAKB_ZONE_MB": "4"},
+    {"YAKB_ZONE_MB": "0.02", "YAKB_ZTILE_WORDS": "512"},
+], ids=["zones", "zone-per-subtable", "spill", "few-zones", "tile512"])
+def test_zone_staged_scatter_is_bit_exact(env):
+    """the same cases through the shared-memory staged scatter (engine.cu: zone_scatter_staged, YAKB_ZONE_STAGED=1)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, YAKB_BATCH="1500000", YAKB_ZONE="1", YAKB_ZONE_STAGED="1", **env)
+    r = subprocess.run([sys.executable, "-c", ZONE_SNIPPET.format(root=root, fn=os.path.join(util.TMP, "yakb_zone_s.fa"))],
+                       env=e, capture_output=True, text=True)
+    assert r.returncode == 0 and "zone ok" in r.stdout, r.stderr[-3000:]

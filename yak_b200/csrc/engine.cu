@@ -417,6 +417,94 @@ __global__ void __launch_bounds__(256) zone_scatter(const uint64_t *__restrict__
 	if ((threadIdx.x & 31) == 0 && my_ev) atomicAdd(&stats[0], (unsigned long long)my_ev);
 }
 
+//      zone_scatter_staged (YAKB_ZONE_STAGED=1; written after the measurements above, NOT yet run on a GPU - see
+//      DESIGN.md section 9): the same two rolls per tile, but the second one places (hash, position) into a
+//      shared-memory staging area in zone order; the tile is then copied out by consecutive threads, so every
+//      (tile, zone) run leaves the SM as a few whole sectors instead of one 8-byte and one 4-byte store per event.
+//      Shared memory: [TMAX] u64 hashes | [TMAX] u32 positions | [8][Z] per-warp counters / cursors |
+//      [Z] place of the tile's run in the zone list | [Z + 1] place of the run in the staging area.
+template<bool LONGK>
+__global__ void __launch_bounds__(256) zone_scatter_staged(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords, int k, uint32_t ztile,
+                                                           uint32_t Pmask, Own own, int zshift, uint32_t Z, uint32_t zcap, unsigned int *zfill,
+                                                           uint64_t *__restrict__ zev, uint32_t *__restrict__ zpos,
+                                                           uint64_t *__restrict__ spill_ev, uint32_t *__restrict__ spill_pos, unsigned int *n_spill,
+                                                           unsigned long long *stats)
+{
+	extern __shared__ uint64_t s_stage_ev[];
+	const uint32_t tmax = ztile * 32;
+	uint32_t *s_stage_pos = (uint32_t*)(s_stage_ev + tmax);
+	uint32_t *s_cnt = s_stage_pos + tmax;   // [8][Z]
+	uint32_t *s_goff = s_cnt + 8 * Z;       // [Z]
+	uint32_t *s_toff = s_goff + Z;          // [Z + 1]
+	__shared__ uint32_t s_wsum[8];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t *wc = s_cnt + warp * Z;
+	const uint32_t zpt = (Z + 255) / 256;   // zones per thread in the offsets step, <= 8 (Z <= 2048)
+	const uint64_t ntiles = (nwords + ztile - 1) / ztile;
+	uint32_t my_ev = 0;
+	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		for (uint32_t i = threadIdx.x; i < 8 * Z; i += 256) s_cnt[i] = 0;
+		__syncthreads();
+		for (uint32_t j = 0; j < ztile / 256; ++j) {
+			const uint64_t W = tile * ztile + j * 256 + threadIdx.x;
+			zone_roll<LONGK, 0>(w2, wm, W, W < nwords, k, Pmask, own, zshift, wc, my_ev, [](int, uint64_t, uint32_t, uint32_t) {});
+		}
+		__syncthreads();
+		// per zone: events of the tile, their place in the staging area (exclusive scan over the zones) and in the zone list
+		uint32_t tot[8], sum = 0;
+#pragma unroll
+		for (uint32_t q = 0; q < 8; ++q) {
+			const uint32_t z = threadIdx.x * zpt + q;
+			tot[q] = 0;
+			if (q < zpt && z < Z) {
+#pragma unroll
+				for (int w = 0; w < 8; ++w) tot[q] += s_cnt[w * Z + z];
+			}
+			sum += tot[q];
+		}
+		uint32_t incl = sum;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+		if (lane == 31) s_wsum[warp] = incl;
+		__syncthreads();
+		uint32_t run = incl - sum;
+		for (int w = 0; w < warp; ++w) run += s_wsum[w];
+#pragma unroll
+		for (uint32_t q = 0; q < 8; ++q) {
+			const uint32_t z = threadIdx.x * zpt + q;
+			if (q < zpt && z < Z) {
+				s_toff[z] = run;
+				s_goff[z] = tot[q] ? atomicAdd(&zfill[z], tot[q]) : 0;
+				uint32_t b = run;
+#pragma unroll
+				for (int w = 0; w < 8; ++w) { const uint32_t c = s_cnt[w * Z + z]; s_cnt[w * Z + z] = b; b += c; }
+				run += tot[q];
+			}
+		}
+		if (threadIdx.x == 255) s_toff[Z] = run; // the last thread's running sum is the tile's total
+		__syncthreads();
+		for (uint32_t j = 0; j < ztile / 256; ++j) {
+			const uint64_t W = tile * ztile + j * 256 + threadIdx.x;
+			zone_roll<LONGK, 1>(w2, wm, W, W < nwords, k, Pmask, own, zshift, wc, my_ev, [&](int r, uint64_t v, uint32_t, uint32_t i) {
+				s_stage_ev[i] = v; s_stage_pos[i] = (uint32_t)(W * 32 + r);
+			});
+		}
+		__syncthreads();
+		const uint32_t T = s_toff[Z];
+		for (uint32_t i = threadIdx.x; i < T; i += 256) {
+			const uint64_t v = s_stage_ev[i];
+			const uint32_t pos = s_stage_pos[i], z = ((uint32_t)v & Pmask) >> zshift;
+			const uint32_t li = s_goff[z] + (i - s_toff[z]);
+			if (li < zcap) { zev[(uint64_t)z * zcap + li] = v; zpos[(uint64_t)z * zcap + li] = pos; }
+			else { const uint32_t q = atomicAdd(n_spill, 1u); spill_ev[q] = v; spill_pos[q] = pos; }
+		}
+		__syncthreads();
+	}
+#pragma unroll
+	for (int d = 16; d; d >>= 1) my_ev += __shfl_xor_sync(0xffffffffu, my_ev, d);
+	if (lane == 0 && my_ev) atomicAdd(&stats[0], (unsigned long long)my_ev);
+}
+
 //      zone_probe: persistent CTAs take slices of 2048 events from a global work counter, in zone order, so
 //      at any moment the whole grid works on one or two zones.  Per event the same bucket probe + counter
 //      CAS as k1_fused; a miss sets the position's bit in flags[] (pass 1).  n_list = Z zone lists of zcap
@@ -1394,6 +1482,21 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 		static const int zgrid = getenv("YAKB_ZGRID") ? atoi(getenv("YAKB_ZGRID")) : 4;
 		const uint64_t nzt = (nwords + ztile - 1) / ztile;
 		const uint32_t gridz = (uint32_t)std::min<uint64_t>(nzt, (uint64_t)nsm * zgrid);
+		// YAKB_ZONE_STAGED=1: the shared-memory staged scatter (zone_scatter_staged); tiles of YAKB_ZTILE_WORDS (default 256) words
+		static const int zstaged = getenv("YAKB_ZONE_STAGED") ? atoi(getenv("YAKB_ZONE_STAGED")) : 0;
+		const uint32_t stile = getenv("YAKB_ZTILE_WORDS") ? std::max(256u, ztile) : 256u;
+		const size_t sms = (size_t)stile * 32 * 12 + ((size_t)Z * 10 + 1) * 4;
+		if (zstaged && sms <= 200 * 1024) {
+			ProfScope ps("zone_scatter", stream);
+			const uint32_t grids = (uint32_t)std::min<uint64_t>((nwords + stile - 1) / stile, (uint64_t)nsm * std::max<size_t>(1, (220 * 1024) / (sms + 1024)));
+			if (longk) {
+				set_smem(zone_scatter_staged<true>, sms);
+				zone_scatter_staged<true><<<grids, 256, sms, stream>>>(w2, wm, nwords, k, stile, Pmask, own(), zshift, Z, zcap, zfill, zev, zpos, sp_ev, sp_pos, zfill + Z, stats);
+			} else {
+				set_smem(zone_scatter_staged<false>, sms);
+				zone_scatter_staged<false><<<grids, 256, sms, stream>>>(w2, wm, nwords, k, stile, Pmask, own(), zshift, Z, zcap, zfill, zev, zpos, sp_ev, sp_pos, zfill + Z, stats);
+			}
+		} else
 		{ ProfScope ps("zone_scatter", stream);
 		if (longk) {
 			set_smem(zone_scatter<true>, smz);
