@@ -84,9 +84,11 @@ def _worker(rank, world, port, fn, k, pre, b, out, batch_bases=0):
     sc = yd.count_file_sharded(fn, be, records_per_chunk=1000, k=k, two_pass=b > 0, batch_bases=batch_bases)
     tot = sc.total_distinct()
     data = sc.dump_bytes()
+    assert sc.dump_file(out + ".par") == os.path.getsize(out + ".par")     # every rank writes its part of the file itself
     if rank == 0:
         open(out, "wb").write(data)
         open(out + ".tot", "w").write(str(tot))
+        assert open(out + ".par", "rb").read() == data
     dist.destroy_process_group()
 
 
@@ -123,3 +125,24 @@ def test_sharded_count_through_the_parser_pool(world, k, pre, b, batch):
     got = open(out, "rb").read()
     assert got == want, util.explain_diff(got, want)
     assert int(open(out + ".tot").read()) == h.contents.tot
+
+
+@pytest.mark.parametrize("kind", ["bgzf", "gzip"])
+def test_sharded_count_of_compressed_input_is_read_once_by_rank0(kind):
+    """gzip / blocked-gzip input on N > 1: rank 0 inflates and parses (csrc/bgzf.cpp, fastx.cpp) into the shared staging
+    buffer, every rank takes its part; same bytes as a single-table count of the plain file"""
+    import gzip
+    import test_bgzf_cpu as B
+    world, k, pre, b = 2, 31, 10, 20
+    plain = G.input_path("reads_q")
+    text = open(plain, "rb").read()
+    fn = os.path.join(util.TMP, f"yakb_dist_{kind}.fq.gz")
+    with open(fn, "wb") as f:
+        f.write(B.bgzf_bytes(text, 40_000) if kind == "bgzf" else gzip.compress(text))
+    out = os.path.join(util.TMP, f"yakb_dist_{kind}.yak")
+    mp.spawn(_worker, args=(world, _free_port(), fn, k, pre, b, out, 50_000), nprocs=world, join=True)
+    h, _ = O.count_file(plain, k=k, pre=pre, bf_shift=b)
+    want = O.dump_bytes(h)
+    got = open(out, "rb").read()
+    assert got == want, util.explain_diff(got, want)
+    O.lib().yo_ch_destroy(h)

@@ -131,6 +131,35 @@ class ShardedCounter:
         return b"".join(parts) if self.rank == 0 else None
 
 
+    def dump_file(self, path: str) -> int:
+        """The .yak file written by all ranks of one node side by side: every rank writes its shard image at its own offset
+        (rank-ordered concatenation, htab.c:373-394); returns the file size.  No shard travels between processes."""
+        import os
+        part = self.b.dump_shard(self.rank == 0)
+        if self.world == 1:
+            with open(path, "wb") as f:
+                f.write(part)
+            return len(part)
+        lens = torch.zeros(self.world, dtype=torch.int64, device=self._dev())
+        lens[self.rank] = len(part)
+        dist.all_reduce(lens, group=self.group)
+        off = [0] + [int(x) for x in torch.cumsum(lens, 0).tolist()]
+        if self.rank == 0:
+            with open(path, "wb") as f:
+                f.truncate(off[-1])
+        dist.barrier(group=self.group)
+        fd = os.open(path, os.O_WRONLY)
+        try:
+            done = 0
+            view = memoryview(part)
+            while done < len(part):
+                done += os.pwrite(fd, view[done:done + (1 << 30)], off[self.rank] + done)
+        finally:
+            os.close(fd)
+        dist.barrier(group=self.group)
+        return off[-1]
+
+
 _STAGES: dict = {}
 
 
@@ -152,12 +181,13 @@ def _slice_bounds(view: np.ndarray, n: int, G: int) -> list[int]:
 
 
 def _count_file_sharded_pool(fn, sc: ShardedCounter, k, create_new, batch_bases, group):
-    """One pass over a plain file with the library's parser pool (csrc/fastx_par.cpp).  Rank 0 parses - once, with all
-    the host's cores - into a staging buffer in shared memory that every rank of the node maps; per batch it broadcasts
-    the batch length, every rank cuts the batch into G contiguous parts at record boundaries (same arithmetic
-    everywhere), and ships only ITS part to its GPU.  While the ranks work on batch i, rank 0's pool already fills the
-    other half of the buffer with batch i+1 (a rank has read its part of batch i-1 before it entered that batch's
-    all-to-all, so the half is free).  False if the pool cannot read this file (gzip, stdin): the caller falls back."""
+    """One pass over a file read ONCE, by rank 0: a plain file with the library's parser pool (csrc/fastx_par.cpp, all the
+    host's cores), gzip / blocked gzip with the sequential reader (csrc/fastx.cpp; BGZF blocks inflated by a pool of
+    threads, csrc/bgzf.cpp).  Rank 0 parses into a staging buffer in shared memory that every rank of the node maps; per
+    batch it broadcasts the batch length, every rank cuts the batch into G contiguous parts at record boundaries (same
+    arithmetic everywhere), and ships only ITS part to its GPU.  While the ranks work on batch i, rank 0 already fills
+    the other half of the buffer with batch i+1 (a rank has read its part of batch i-1 before it entered that batch's
+    all-to-all, so the half is free).  False if rank 0 cannot open the file: the caller falls back (and reports it)."""
     import os
     import tempfile
     import threading
@@ -165,7 +195,11 @@ def _count_file_sharded_pool(fn, sc: ShardedCounter, k, create_new, batch_bases,
     L = capi.lib()
     G, r, dev = sc.world, sc.rank, sc._dev()
     cap = batch_bases + (batch_bases >> 4) + 4096
-    rd = L.yakb_pfastx_open(fn.encode(), 0, 0) if r == 0 else None
+    rd, fill_fn, close_fn = None, L.yakb_pfastx_fill, L.yakb_pfastx_close
+    if r == 0:
+        rd = L.yakb_pfastx_open(fn.encode(), 0, 0)
+        if not rd and fn != "-":          # gzip / BGZF: the sequential reader has the same bulk call
+            rd, fill_fn, close_fn = L.yakb_fastx_open(fn.encode()), L.yakb_fastx_fill, L.yakb_fastx_close
     ok = torch.tensor([1 if (r != 0 or rd) else 0], dtype=torch.int64, device=dev)
     if G > 1:
         dist.broadcast(ok, 0, group=group)
@@ -205,7 +239,7 @@ def _count_file_sharded_pool(fn, sc: ShardedCounter, k, create_new, batch_bases,
 
     def fill(slot):
         ns, done, need = C.c_int64(), C.c_int(), C.c_uint64()
-        n = L.yakb_pfastx_fill(rd, mm.ctypes.data + slot * cap, cap, batch_bases, k, C.byref(ns), C.byref(done), C.byref(need))
+        n = fill_fn(rd, mm.ctypes.data + slot * cap, cap, batch_bases, k, C.byref(ns), C.byref(done), C.byref(need))
         state[slot] = (int(n), 1 if done.value else 0, int(need.value))
 
     try:
@@ -233,7 +267,7 @@ def _count_file_sharded_pool(fn, sc: ShardedCounter, k, create_new, batch_bases,
             slot ^= 1
     finally:
         if rd:
-            L.yakb_pfastx_close(rd)
+            close_fn(rd)
     return True
 
 
@@ -280,3 +314,56 @@ def count_file_sharded(fn: str, backend, records_per_chunk: int = 1 << 20, k: in
         one_pass(fn2 or fn, 0)
         sc.shrink(2, 1023)
     return sc
+
+
+def main(argv=None) -> int:
+    """`yak count` on all GPUs of one node: torchrun --nproc-per-node N -m yak_b200.dist count [options] in.fq [in2.fq]
+    (options and two-pass protocol of the reference's main_count, main.c:13-64; one process per GPU, sub-tables sharded,
+    one all-to-all per batch, every rank writes its part of the .yak file)."""
+    import argparse
+    import os
+    import sys
+    ap = argparse.ArgumentParser(prog="yak_b200.dist")
+    ap.add_argument("command", choices=["count"])
+    ap.add_argument("-k", type=int, default=31)
+    ap.add_argument("-p", type=int, default=10)
+    ap.add_argument("-b", type=int, default=0)
+    ap.add_argument("-H", type=int, default=4)
+    ap.add_argument("-t", type=int, default=4, help="accepted, unused")
+    ap.add_argument("-K", default="100m", help="accepted; batches are sized for the GPUs")
+    ap.add_argument("-o", default=None)
+    ap.add_argument("files", nargs="+")
+    a = ap.parse_args(argv)
+    if a.p < 10:
+        print("ERROR: -p should be at least 10", file=sys.stderr)
+        return 1
+    if a.k >= 64:
+        print("ERROR: -k must be smaller than 64", file=sys.stderr)
+        return 1
+    rank, world, local = (int(os.environ.get(v, d)) for v, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    if world & (world - 1) or world > (1 << a.p):
+        print("ERROR: the number of ranks must be a power of two", file=sys.stderr)
+        return 1
+    from . import capi
+    capi.require_gpu()                    # no CPU path: fail loudly
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    be = GpuBackend(a.k, a.p, a.b, a.H, rank, world)
+    try:
+        batch = min(64 << 20, (512 << 20) // world) * world
+        sc = count_file_sharded(a.files[0], be, k=a.k, two_pass=a.b > 0, fn2=a.files[1] if len(a.files) > 1 else None, batch_bases=batch)
+        tot = sc.total_distinct()
+        if rank == 0:
+            print("[M::%s] %d distinct k-mers%s on %d GPUs" % ("yak_b200.dist", tot, " after shrinking" if a.b > 0 else "", world), file=sys.stderr)
+        if a.o:
+            sc.dump_file(a.o)
+    finally:
+        be.close()
+        if world > 1:
+            dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
