@@ -207,6 +207,33 @@ size_t FastxReader::fill(uint8_t *dst, size_t cap, size_t target, int min_len, i
 		const int64_t avail = end_ - beg_;
 		if (st_ == S_FIND) {
 			if (last_) { st_ = S_NAME; bol_ = false; rec_start = n; cur_len_ = 0; in_carry_ = false; last_ = 0; continue; }
+			// Fast path for what sequencers write: a four-line FASTQ record that lies whole in the buffer - header, one
+			// sequence line, '+' line, one quality line of the same length, no CR.  Anything else (multi-line, FASTA,
+			// empty or over-long lines, a record cut by the buffer's end or too big for dst) goes through the state
+			// machine below, which this shortcut reproduces step for step.
+			if (p[0] == '@') {
+				const unsigned char *e = p + avail;
+				const unsigned char *nl1 = (const unsigned char*)memchr(p, '\n', avail);
+				const unsigned char *sq = nl1 ? nl1 + 1 : e;
+				if (sq < e && *sq != '\n' && *sq != '>' && *sq != '@' && *sq != '+') {
+					const unsigned char *nl2 = (const unsigned char*)memchr(sq, '\n', e - sq);
+					if (nl2 && nl2 + 1 < e && nl2[1] == '+' && nl2[-1] != '\r') {
+						const unsigned char *nl3 = (const unsigned char*)memchr(nl2 + 1, '\n', e - (nl2 + 1));
+						const unsigned char *ql = nl3 ? nl3 + 1 : e;
+						const int64_t len = nl2 - sq;
+						if (ql + len < e && ql[len] == '\n' && ql[len - 1] != '\r' && memchr(ql, '\n', len) == nullptr) {
+							if (len < min_len) { beg_ = ql + len + 1 - buf_.data(); bol_ = true; continue; } // dropped (count.c:95)
+							if (n + (size_t)len + 1 <= cap) {
+								memcpy(dst + n, sq, len);
+								n += len; dst[n++] = '\n'; ++*n_seq;
+								yakb_ref_flow_record(&flow_, len);
+								beg_ = ql + len + 1 - buf_.data(); bol_ = true;
+								continue;
+							}
+						}
+					}
+				}
+			}
 			int64_t i = 0;
 			while (i < avail && p[i] != '>' && p[i] != '@') ++i;
 			beg_ += i;
