@@ -734,3 +734,64 @@ def test_inspect_two_file_logic_against_reference_binary():
         assert ref.returncode == 0
         got = open(outp, "rb").read()
         assert got == ref.stdout and got.count(b"\n") > 3, (trial, k, p1, p2, flags)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fill_shortcut_for_four_line_fastq_equals_the_state_machine(seed):
+    """fill()'s shortcut for whole four-line FASTQ records (fastx.cpp) against the oracle's record reader: records of random
+    length next to everything that must NOT take the shortcut (CRLF, multi-line, blank lines, short / long qualities that
+    are legal, FASTA records in between), small destination buffers, the length filter"""
+    rng = np.random.default_rng(900 + seed)
+    recs = []
+    for i in range(3000):
+        ln = int(rng.integers(1, 260))
+        s = bytes(rng.choice(np.frombuffer(b"ACGTNacgtn", dtype=np.uint8), ln))
+        kind = int(rng.integers(0, 12))
+        if kind == 0:      # CRLF
+            recs.append(b"@r%d x\r\n" % i + s + b"\r\n+\r\n" + b"I" * ln + b"\r\n")
+        elif kind == 1:    # two sequence lines, two quality lines
+            h = ln // 2
+            recs.append(b"@r%d\n" % i + s[:h] + b"\n" + s[h:] + b"\n+\n" + b"I" * h + b"\n" + b"I" * (ln - h) + b"\n")
+        elif kind == 2:    # blank line before the sequence
+            recs.append(b"@r%d\n\n" % i + s + b"\n+r%d\n" % i + b"I" * ln + b"\n")
+        elif kind == 3:    # FASTA
+            recs.append(b">f%d\n" % i + s + b"\n")
+        elif kind == 4:    # quality characters that look like headers
+            recs.append(b"@r%d\n" % i + s + b"\n+\n" + b"@" * ln + b"\n")
+        else:
+            recs.append(b"@r%d some comment\n" % i + s + b"\n+\n" + b"I" * ln + b"\n")
+    fn = os.path.join(util.TMP, "yakb_fastpath.fq")
+    with open(fn, "wb") as f:
+        f.write(b"".join(recs))
+    want_recs = [r for r in _records_oracle(fn) if not isinstance(r, int)]
+    assert len(want_recs) == 3000
+    for min_len in (0, 31, 200):
+        want = b"".join(q + b"\n" for _, q in want_recs if len(q) >= min_len)
+        for cap, target in ((1 << 20, 1 << 20), (300, 100), (5000, 5000)):
+            got, nseq = _fill_all(fn, cap, target, min_len)
+            assert got == want, (min_len, cap)
+            assert nseq == sum(1 for _, q in want_recs if len(q) >= min_len)
+            got, nseq, _ = _pfill_all(fn, 3000, 3, cap, target, min_len)
+            assert got == want, ("pool", min_len, cap)
+
+
+@pytest.mark.parametrize("tail", [b"\n", b"", b"\r\n"])
+def test_last_record_waiting_in_the_carry_is_not_lost(tail):
+    """a last record that does not fit what is left of the caller's buffer is closed by the end of the input while it sits in the
+    reader's carry buffer: fill() must not report `done` before it has handed it over (FASTA and FASTQ, both readers, gzip)"""
+    import gzip
+    rng = np.random.default_rng(5)
+    big = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 9000))
+    for text in (b">a\nACGTACGT\n>b\n" + big + tail, b"@a\nACGTACGT\n+\nIIIIIIII\n@b\n" + big + b"\n+\n" + b"I" * 9000 + tail,
+                 b">only\n" + big[:5000] + b"\n" + big[5000:] + tail):
+        fn = os.path.join(util.TMP, "yakb_lastcarry.fx")
+        with open(fn, "wb") as f:
+            f.write(text)
+        with gzip.open(fn + ".gz", "wb") as f:
+            f.write(text)
+        want = b"".join(q + b"\n" for _, q in (r for r in _records_oracle(fn) if not isinstance(r, int)))
+        assert want.endswith(big + b"\n")
+        for cap, target in ((9004, 9004), (9010, 100), (1 << 20, 1 << 20), (9001, 9001)):
+            assert _fill_all(fn, cap, target, 0)[0] == want, (cap, "sequential")
+            assert _fill_all(fn + ".gz", cap, target, 0)[0] == want, (cap, "gzip")
+            assert _pfill_all(fn, 2000, 3, cap, target, 0)[0] == want, (cap, "pool")

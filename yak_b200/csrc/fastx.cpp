@@ -200,7 +200,7 @@ size_t FastxReader::fill(uint8_t *dst, size_t cap, size_t target, int min_len, i
 				finish_record(qual_len_ == cur_len_);
 			} else if (st_ == S_PLUS) finish_record(false); // kseq.h:222: no quality string at all
 			st_ = S_FIND; last_ = 0;
-			*done = true;
+			*done = !carry_ready_; // a last record that did not fit dst waits in carry_: the caller must come back for it
 			break;
 		}
 		const unsigned char *p = buf_.data() + beg_;
