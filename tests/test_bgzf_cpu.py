@@ -217,3 +217,44 @@ def test_bgzf_truncated_and_corrupted_files(seed):
         assert got == want, (seed, trial, kind)
         if kind in (0, 3):   # nothing is dropped by gzread either when the file is merely cut short / mislabelled
             assert read_all(fn, -1) == want
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_sequential_reader_buffer_boundaries_on_adversarial_input(seed):
+    """the sequential reader's block buffer is 4 MB, so small test files never put a record across two buffers.  BGZF members
+    of a few bytes with one member per job do: every member becomes one parser buffer.  Adversarial FASTA/FASTQ (CRLF, blank
+    lines, multi-line, truncated qualities) read that way must equal the same text read from a plain file: the bulk path
+    (shortcut included), the record path, and what follows truncated records for several -K"""
+    import test_oracle_cpu as T
+    rng = np.random.default_rng(4000 + seed)
+    text = T._random_fastx(rng, int(rng.integers(20, 150)), False, bad=(0.0, 0.15)[seed % 2])
+    plain = _write("yakb_bgzf_adv.fx", text)
+    fn = _write("yakb_bgzf_adv.fx.gz", bgzf_bytes(text, int(rng.choice([1, 2, 7, 33, 150, 1000])), rng if seed % 3 else None))
+    L = lib()
+    L.yakb_fastx_set_chunk.argtypes = [C.c_void_p, C.c_int64]
+
+    def fill_all(path, threads, job, cap, target, min_len, chunk):
+        r = L.yakb_fastx_open_bgzf(path.encode(), threads, job)
+        L.yakb_fastx_set_chunk(r, chunk)
+        out, nseq = bytearray(), 0
+        buf = C.create_string_buffer(cap)
+        while True:
+            ns, done, need = C.c_int64(), C.c_int(), C.c_uint64()
+            n = L.yakb_fastx_fill(r, buf, cap, target, min_len, C.byref(ns), C.byref(done), C.byref(need))
+            if need.value:
+                cap = need.value + 5
+                buf = C.create_string_buffer(cap)
+                continue
+            out += buf.raw[:n]
+            nseq += ns.value
+            if done.value:
+                break
+        L.yakb_fastx_close(r)
+        return bytes(out), nseq
+    for min_len in (0, 31):
+        for chunk in (10_000_000, 3000, 200):
+            want = fill_all(plain, 0, 1, 1 << 22, 1 << 22, min_len, chunk)
+            assert want[0] == b"".join(s + b"\n" for s in T._ref_flow(plain, min_len, chunk))     # the plain read is the pinned one
+            for cap, target in ((1 << 22, 1 << 22), (700, 300), (64, 64)):
+                assert fill_all(fn, int(rng.integers(1, 5)), 1, cap, target, min_len, chunk) == want, (seed, min_len, chunk, cap)
+    assert records(fn, 3, 1) == records(plain, 0)
