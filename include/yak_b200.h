@@ -75,6 +75,13 @@ uint64_t yakb_kernel_launches(void);
 uint64_t yakb_device_cache_bytes(void);
 void yakb_device_cache_trim(void);
 
+/* test hook, no GPU: the host side of yak_ch_restore_core (reference htab.c:419-472) - header checks, then the sub-table
+ * capacities, offsets and keys (counts mapped to flag bits for the TRIOBIN / SEXCHR modes) as the device receives them; the
+ * 2^pre key arrays are read by `threads` threads (0 = one per core, at most 16).  Arrays are malloc'd for the caller.
+ * Returns 0, -1 unreadable, -2 wrong magic, -3 wrong counter bits. */
+int yakb_yak_file_read(const char *fn, int mode, int min_cnt, int mid_cnt, int threads, uint32_t *k, uint32_t *pre,
+                       uint32_t **caps, uint64_t **off, uint64_t **keys);
+
 /* the host-side FASTA/FASTQ record reader yak_count/yak_qv use (reference kseq.h:192-232
  * semantics; plain or gzip; NULL or "-" = stdin).  next() returns the sequence length, -1 at EOF,
  * -2 on a truncated quality string; *seq / *name stay valid until the following call. */

@@ -3,6 +3,7 @@ import ctypes as C
 import hashlib
 import os
 import re
+import struct
 import subprocess
 
 import numpy as np
@@ -795,3 +796,104 @@ def test_last_record_waiting_in_the_carry_is_not_lost(tail):
             assert _fill_all(fn, cap, target, 0)[0] == want, (cap, "sequential")
             assert _fill_all(fn + ".gz", cap, target, 0)[0] == want, (cap, "gzip")
             assert _pfill_all(fn, 2000, 3, cap, target, 0)[0] == want, (cap, "pool")
+
+
+def _parse_yak_like_the_reference(data: bytes, mode, min_cnt, mid_cnt):
+    """htab.c:419-472 on bytes, with its unchecked freads: a missing header is an empty sub-table, a short key array ends the file"""
+    if len(data) < 4:
+        return -1
+    if data[:4] != b"YAK\x02":
+        return -2
+    if len(data) < 16:
+        return -1
+    k, pre, cb = struct.unpack_from("<III", data, 4)
+    if cb != 10:
+        return -3
+    caps, off, keys, o = [], [0], [], 16
+    for s in range(1 << pre):
+        cap = size = 0
+        if o + 8 <= len(data):
+            cap, size = struct.unpack_from("<II", data, o)
+            o += 8
+        else:
+            o = len(data)
+        got = min(size, (len(data) - o) // 8)
+        ks = np.frombuffer(data, dtype="<u8", count=got, offset=o).copy()
+        o = o + 8 * got if got == size else len(data)
+        if mode in (2, 3):        # YAK_LOAD_TRIOBIN1/2
+            cnt = (ks & np.uint64(1023)).astype(np.int64)
+            shift = 0 if mode == 2 else 2
+            x = np.where(cnt >= mid_cnt, 2 << shift, np.where(cnt >= min_cnt, 1 << shift, -1))
+            keep = x >= 0
+            ks = (ks[keep] & ~np.uint64(1023)) | x[keep].astype(np.uint64)
+        elif mode in (4, 5, 6):   # YAK_LOAD_SEXCHR1/2/3
+            ks = (ks & ~np.uint64(1023)) | np.uint64(1 << (mode - 4))
+        caps.append(cap)
+        keys.append(ks)
+        off.append(off[-1] + len(ks))
+    return k, pre, caps, off, np.concatenate(keys) if keys else np.zeros(0, np.uint64)
+
+
+def test_yak_file_reader_of_restore_equals_a_plain_parse():
+    """the host side of yak_ch_restore_core (header walk + key arrays read by several threads, capi.cu) against a plain parse:
+    whole files, every load mode, files cut anywhere, a pipe"""
+    import threading
+    from yak_b200 import capi, synth
+    L = capi.lib()
+    L.yakb_yak_file_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                     C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.POINTER(C.c_uint64))]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+
+    def read(fn, mode=1, mn=0, md=0, threads=0):
+        k, pre = C.c_uint32(), C.c_uint32()
+        caps, off, keys = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint64)()
+        rc = L.yakb_yak_file_read(fn.encode(), mode, mn, md, threads, C.byref(k), C.byref(pre), C.byref(caps), C.byref(off), C.byref(keys))
+        if rc != 0:
+            return rc
+        P = 1 << pre.value
+        o = [off[i] for i in range(P + 1)]
+        out = (k.value, pre.value, [caps[i] for i in range(P)], o, np.ctypeslib.as_array(keys, shape=(max(o[-1], 1),))[:o[-1]].copy())
+        for p in (caps, off, keys):
+            libc.free(p)
+        return out
+
+    def same(a, b):
+        if isinstance(a, int) or isinstance(b, int):
+            return a == b
+        return a[:4] == b[:4] and np.array_equal(a[4], b[4])
+    rng = np.random.default_rng(17)
+    fa = os.path.join(util.TMP, "yakb_yfr.fa")
+    with open(fa, "wb") as f:
+        f.write(synth.reads_file_bytes(3, 400_000, 4, 60_000, 150, 0.01, 2))
+    y = os.path.join(util.TMP, "yakb_yfr.yak")
+    for k, pre in ((31, 10), (21, 12)):
+        h, _ = O.count_file(fa, k=k, pre=pre, bf_shift=0)
+        assert O.lib().yo_ch_dump(h, y.encode()) == 0
+        O.lib().yo_ch_destroy(h)
+        data = open(y, "rb").read()
+        assert len(data) > (8 << 20)          # several threads take part
+        for mode, mn, md in ((1, 0, 0), (2, 2, 5), (3, 1, 3), (4, 0, 0), (5, 0, 0), (6, 0, 0)):
+            want = _parse_yak_like_the_reference(data, mode, mn, md)
+            assert same(read(y, mode, mn, md, 0), want) and same(read(y, mode, mn, md, 1), want) and same(read(y, mode, mn, md, 5), want)
+        cut = os.path.join(util.TMP, "yakb_yfr_cut.yak")
+        for n in [0, 3, 4, 15, 16, 20, 24, 31] + [int(x) for x in rng.integers(16, len(data), 12)]:
+            open(cut, "wb").write(data[:n])
+            assert same(read(cut, 1, 0, 0, 3), _parse_yak_like_the_reference(data[:n], 1, 0, 0)), n
+        open(cut, "wb").write(b"NOPE" + data[4:100]);
+        assert read(cut) == -2
+        open(cut, "wb").write(data[:12] + struct.pack("<I", 9) + data[16:100])
+        assert read(cut) == -3
+        assert read("/nonexistent/x.yak") == -1
+    # a pipe cannot be read by offsets: front to back, same result
+    fifo = os.path.join(util.TMP, "yakb_yfr.fifo")
+    if os.path.exists(fifo):
+        os.unlink(fifo)
+    os.mkfifo(fifo)
+    small = data[:16 + 8 * 4096 + 200_000]
+    t = threading.Thread(target=lambda: open(fifo, "wb").write(small))
+    t.start()
+    got = read(fifo, 1, 0, 0, 4)
+    t.join()
+    os.unlink(fifo)
+    assert same(got, _parse_yak_like_the_reference(small, 1, 0, 0))
