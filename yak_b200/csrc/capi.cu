@@ -413,9 +413,9 @@ template<class Sink> static void serialise(ChBox *b, Sink &&sink, bool header = 
 	}
 	const int step = 1024;
 	double t_lay = 0, t_sink = 0;
+	LayoutOut lo; // one for all steps: Engine::layout resets it, and its key array (gigabytes) keeps its pages
 	for (int s0 = 0; s0 < P; s0 += step) {
 		const int s1 = std::min(P, s0 + step);
-		LayoutOut lo;
 		double t0 = wall_now();
 		b->eng->layout(s0, s1, lo, true);
 		double t1 = wall_now();
