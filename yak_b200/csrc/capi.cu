@@ -10,6 +10,7 @@
 #include "extras.cuh"
 #include "fastx.h"
 #include "fastx_par.h"
+#include "yakfile.h"
 #include "yakb_dev.cuh"
 #include <stdio.h>
 #include <stdlib.h>
@@ -438,8 +439,8 @@ extern "C" int yak_ch_dump(const yak_ch_t *h, const char *fn)
 	if (b->eng->lw) { fprintf(stderr, "[yakb] ERROR: yak_ch_dump on one shard of a multi-GPU table; use yakb_ch_dump_shard_mem\n"); return -1; }
 	FILE *fp = strcmp(fn, "-") ? fopen(fn, "wb") : stdout;
 	if (fp == 0) return -1;
-	static char iobuf[1 << 20];
-	setvbuf(fp, iobuf, _IOFBF, sizeof(iobuf));
+	std::unique_ptr<char[]> iobuf(new char[1 << 20]); // per call: tables may be dumped from several threads at once
+	setvbuf(fp, iobuf.get(), _IOFBF, 1 << 20);
 	serialise(b, [&](const void *p, size_t n) { fwrite(p, 1, n, fp); });
 	fprintf(stderr, "[M::%s] dumpped the hash table to file '%s'.\n", __func__, fn);
 	if (fp != stdout) fclose(fp); else { fflush(fp); setvbuf(fp, nullptr, _IOLBF, 0); }
@@ -461,162 +462,6 @@ static int64_t dump_mem(const yak_ch_t *h, uint8_t **out, bool header)
 }
 extern "C" int64_t yakb_ch_dump_mem(const yak_ch_t *h, uint8_t **out) { return dump_mem(h, out, true); }
 extern "C" int64_t yakb_ch_dump_shard_mem(const yak_ch_t *h, int with_header, uint8_t **out) { return dump_mem(h, out, with_header != 0); }
-
-// The host side of yak_ch_restore_core (htab.c:419-472): header checks, then per sub-table {capacity, size, keys}.  The
-// reference reads key by key; a table of human reads is 25 GB, so here the 2^pre headers are walked first (each tells where
-// the next one lies) and the key arrays are then read by several threads straight to their place in one dense array.
-// Short files read like the reference's unchecked freads leave things: a sub-table whose header is missing is empty, one
-// whose keys are cut short has the whole keys that are there.  Flag modes map the counts (htab.c:448-469) afterwards.
-// Returns 0, -1 (cannot open / shorter than the header), -2 (magic), -3 (counter bits).
-namespace {
-// the keys of a table file: anonymous memory that is never zeroed by us and is backed by huge pages where the kernel gives
-// them (a std::vector of 3 G keys spends seconds on first-touch page faults in one thread before a byte is read; here the
-// reading threads touch their own parts)
-struct KeyBuf {
-	uint64_t *p = nullptr;
-	size_t n = 0, bytes = 0;
-	KeyBuf() {}
-	KeyBuf(const KeyBuf&) = delete;
-	KeyBuf &operator=(const KeyBuf&) = delete;
-	~KeyBuf() { if (p) munmap(p, bytes); }
-	bool alloc(size_t count)
-	{
-		if (p) munmap(p, bytes);
-		p = nullptr; n = count;
-		bytes = (std::max<size_t>(count, 1) * 8 + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
-		void *m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-		if (m == MAP_FAILED) { n = 0; return false; }
-		madvise(m, bytes, MADV_HUGEPAGE);
-		p = (uint64_t*)m;
-		return true;
-	}
-	uint64_t *data() { return p; }
-	size_t size() const { return n; }
-	uint64_t &operator[](size_t i) { return p[i]; }
-	void shrink(size_t count) { n = count; }
-};
-struct YakFile {
-	uint32_t k = 0, pre = 0, counter_bits = 0;
-	std::vector<uint32_t> caps;
-	std::vector<uint64_t> off;
-	KeyBuf keys;
-};
-static bool pread_all(int fd, void *dst, size_t n, uint64_t at)
-{
-	char *p = (char*)dst;
-	while (n) {
-		const ssize_t r = pread(fd, p, std::min<size_t>(n, 1u << 30), (off_t)at);
-		if (r <= 0) return false;
-		p += r; at += (uint64_t)r; n -= (size_t)r;
-	}
-	return true;
-}
-static int read_yak_file(const char *fn, int mode, int min_cnt, int mid_cnt, YakFile &yf, int threads, bool header_only = false)
-{
-	const int fd = open(fn, O_RDONLY);
-	if (fd < 0) return -1;
-	struct Close { int fd; ~Close() { close(fd); } } closer{fd};
-	struct stat st;
-	if (fstat(fd, &st) != 0) return -1;
-	const bool regular = S_ISREG(st.st_mode);
-	char head[16];
-	if (!regular) { // a pipe (`yak qv <(...)`): no offsets to jump to - read it front to back
-		FILE *fp = fdopen(dup(fd), "rb");
-		if (!fp) return -1;
-		struct FClose { FILE *f; ~FClose() { fclose(f); } } fcloser{fp};
-		if (fread(head, 1, 4, fp) != 4) return -1;
-		if (strncmp(head, YAK_MAGIC, 4) != 0) return -2;
-		uint32_t t[3];
-		if (fread(t, 4, 3, fp) != 3) return -1;
-		yf.k = t[0]; yf.pre = t[1]; yf.counter_bits = t[2];
-		if (t[2] != YAK_COUNTER_BITS) return -3;
-		if (yf.pre > 30) return -1;
-		const int P = 1 << yf.pre; // (a pipe cannot be opened twice: header_only is not honoured here, the body comes along)
-		yf.caps.assign(P, 0); yf.off.assign(P + 1, 0);
-		std::vector<uint64_t> tmp;
-		for (int s = 0; s < P; ++s) {
-			uint32_t u[2] = {0, 0};
-			if (fread(u, 4, 2, fp) != 2) u[0] = u[1] = 0;
-			yf.caps[s] = u[0];
-			const size_t base = tmp.size();
-			tmp.resize(base + u[1]);
-			const size_t got = u[1] ? fread(tmp.data() + base, 8, u[1], fp) : 0;
-			tmp.resize(base + got);
-			yf.off[s + 1] = tmp.size();
-		}
-		if (!yf.keys.alloc(tmp.size())) return -1;
-		if (!tmp.empty()) memcpy(yf.keys.data(), tmp.data(), tmp.size() * 8);
-	} else {
-		const uint64_t fsize = (uint64_t)st.st_size;
-		if (fsize < 4 || !pread_all(fd, head, 4, 0)) return -1;
-		if (strncmp(head, YAK_MAGIC, 4) != 0) return -2;
-		if (fsize < 16 || !pread_all(fd, head + 4, 12, 4)) return -1;
-		uint32_t t[3];
-		memcpy(t, head + 4, 12);
-		yf.k = t[0]; yf.pre = t[1]; yf.counter_bits = t[2];
-		if (t[2] != YAK_COUNTER_BITS) return -3;
-		if (header_only) return 0;
-		if (yf.pre > 30) return -1;
-		const int P = 1 << yf.pre;
-		yf.caps.assign(P, 0); yf.off.assign(P + 1, 0);
-		std::vector<uint64_t> at(P, 0); // file offset of each sub-table's keys
-		uint64_t o = 16;
-		for (int s = 0; s < P; ++s) {
-			uint32_t u[2] = {0, 0};
-			if (o + 8 <= fsize && pread_all(fd, u, 8, o)) o += 8; else { u[0] = u[1] = 0; o = fsize; }
-			const uint64_t got = std::min<uint64_t>(u[1], (fsize - o) / 8);
-			yf.caps[s] = u[0];
-			at[s] = o;
-			yf.off[s + 1] = yf.off[s] + got;
-			o = got == u[1] ? o + got * 8 : fsize; // a short array is the end of the file
-		}
-		const uint64_t n = yf.off[P];
-		const double t_hdr = wall_now();
-		if (!yf.keys.alloc(n)) return -1;
-		const double t_alloc = wall_now();
-		if (threads <= 0) threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
-		if (n < (1u << 20)) threads = 1;
-		std::atomic<int> next{0}, failed{0};
-		auto work = [&]() {
-			for (;;) {
-				const int s0 = next.fetch_add(16);
-				if (s0 >= P) break;
-				for (int s = s0; s < std::min(P, s0 + 16); ++s) {
-					const uint64_t m = yf.off[s + 1] - yf.off[s];
-					if (m && !pread_all(fd, yf.keys.data() + yf.off[s], m * 8, at[s])) failed = 1;
-				}
-			}
-		};
-		std::vector<std::thread> th;
-		for (int i = 1; i < threads; ++i) th.emplace_back(work);
-		work();
-		for (auto &x : th) x.join();
-		if (timing_on()) fprintf(stderr, "[T::read_yak_file] %.2f GB: allocation %.3f s, key arrays %.3f s on %d threads\n", n * 8e-9, t_alloc - t_hdr, wall_now() - t_alloc, threads);
-		if (failed) return -1;
-	}
-	if (mode != YAK_LOAD_ALL) { // counts -> flag bits, in place; TRIOBIN drops the k-mers below min_cnt (htab.c:448-469)
-		const uint64_t cmask = YAK_MAX_COUNT;
-		const int P = 1 << yf.pre;
-		uint64_t w = 0, r = 0;
-		for (int s = 0; s < P; ++s) {
-			const uint64_t end = yf.off[s + 1];
-			for (; r < end; ++r) {
-				uint64_t key = yf.keys[r];
-				if (mode == YAK_LOAD_TRIOBIN1 || mode == YAK_LOAD_TRIOBIN2) {
-					const int cnt = (int)(key & cmask), shift = mode == YAK_LOAD_TRIOBIN1 ? 0 : 2;
-					if (cnt >= mid_cnt) key = (key & ~cmask) | (uint64_t)(2 << shift);
-					else if (cnt >= min_cnt) key = (key & ~cmask) | (uint64_t)(1 << shift);
-					else continue;
-				} else key = (key & ~cmask) | (uint64_t)(1 << (mode - YAK_LOAD_SEXCHR1));
-				yf.keys[w++] = key;
-			}
-			yf.off[s + 1] = w;
-		}
-		yf.keys.shrink(w);
-	}
-	return 0;
-}
-}
 
 // test hook (no GPU): the arrays yak_ch_restore_core hands to the device, malloc'd for the caller
 extern "C" int yakb_yak_file_read(const char *fn, int mode, int min_cnt, int mid_cnt, int threads, uint32_t *k, uint32_t *pre,
