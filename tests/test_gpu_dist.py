@@ -72,7 +72,7 @@ def test_multi_gpu_count_command_equals_oracle(yakb, b, compressed):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), "-m", "yak_b200.dist", "count", "-k31", "-p12", f"-b{b}", "-o", out, gz if compressed else fn]
-    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True)
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     h, _ = O.count_file(fn, k=31, pre=12, bf_shift=b)
     want = O.dump_bytes(h)
