@@ -4,16 +4,16 @@
 # 1. the GPU suite as the driver runs it; 2. the parity cases of code that has never run on a GPU; 3. the default bench line;
 # 4. the zone-blocked front end with the direct and the staged scatter over zone sizes and chunk sizes.
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/n_pytest.log 2>&1; echo "pytest gpu rc=$?"
-YAKB_TEST_UNVERIFIED=1 python -m pytest tests/test_gpu_parity.py tests/test_gpu_dist.py -k "zone_staged or count_command" -q > gpurun_out/n_pytest_unverified.log 2>&1; echo "unverified rc=$?"
-python bench.py > gpurun_out/n_bench_default.json 2> gpurun_out/n_bench_default.err; echo "bench rc=$?"
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/n_pytest.log 2>&1; echo "pytest gpu rc=$?"
+YAKB_TEST_UNVERIFIED=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_dist.py -k "zone_staged or count_command" -q > gpurun_out/n_pytest_unverified.log 2>&1; echo "unverified rc=$?"
+timeout 900 python bench.py > gpurun_out/n_bench_default.json 2> gpurun_out/n_bench_default.err; echo "bench rc=$?"
 for mb in 32 64 128; do
 	for st in 0 1; do
-		YAKB_ZONE=2 YAKB_ZONE_MB=$mb YAKB_ZONE_STAGED=$st python bench.py --no-e2e --no-cpu > gpurun_out/n_zone${mb}_s${st}.json 2> gpurun_out/n_zone${mb}_s${st}.err
-		YAKB_ZONE=2 YAKB_ZONE_MB=$mb YAKB_ZONE_STAGED=$st python bench.py --no-e2e --no-cpu --chunk-reads 5000000 --steps 117 > gpurun_out/n_zone${mb}_s${st}_5m.json 2> gpurun_out/n_zone${mb}_s${st}_5m.err
+		YAKB_ZONE=2 YAKB_ZONE_MB=$mb YAKB_ZONE_STAGED=$st timeout 600 python bench.py --no-e2e --no-cpu > gpurun_out/n_zone${mb}_s${st}.json 2> gpurun_out/n_zone${mb}_s${st}.err
+		YAKB_ZONE=2 YAKB_ZONE_MB=$mb YAKB_ZONE_STAGED=$st timeout 600 python bench.py --no-e2e --no-cpu --chunk-reads 5000000 --steps 117 > gpurun_out/n_zone${mb}_s${st}_5m.json 2> gpurun_out/n_zone${mb}_s${st}_5m.err
 	done
 done
-python bench.py --no-e2e --no-cpu --chunk-reads 5000000 --steps 117 > gpurun_out/n_bench_5m.json 2> gpurun_out/n_bench_5m.err
+timeout 600 python bench.py --no-e2e --no-cpu --chunk-reads 5000000 --steps 117 > gpurun_out/n_bench_5m.json 2> gpurun_out/n_bench_5m.err
 tail -n 3 gpurun_out/n_pytest.log gpurun_out/n_pytest_unverified.log
 for f in gpurun_out/n_*.json; do python - "$f" <<'PY'
 import json, sys
