@@ -146,3 +146,29 @@ def test_sharded_count_of_compressed_input_is_read_once_by_rank0(kind):
     got = open(out, "rb").read()
     assert got == want, util.explain_diff(got, want)
     O.lib().yo_ch_destroy(h)
+
+
+def test_slice_bounds_cut_at_record_boundaries():
+    """_slice_bounds (the per-rank cut of a parsed batch): parts are contiguous, cover the batch, and every cut is right behind a
+    newline - for short reads, for records longer than a part, for a batch that is one record, for an empty batch"""
+    from yak_b200.dist import _slice_bounds
+    rng = np.random.default_rng(9)
+    for trial in range(300):
+        G_ = int(rng.choice([1, 2, 4, 8]))
+        kind = trial % 4
+        if kind == 0:
+            lens = rng.integers(1, 300, int(rng.integers(0, 400)))
+        elif kind == 1:
+            lens = rng.integers(1, 200_000, int(rng.integers(1, 6)))           # records longer than a part and than the search window
+        elif kind == 2:
+            lens = np.array([int(rng.integers(1, 100_000))])
+        else:
+            lens = np.concatenate([rng.integers(1, 50, 200), [150_000], rng.integers(1, 50, 3)])
+        buf = np.concatenate([np.concatenate([np.full(int(n), 65, np.uint8), [10]]) for n in lens]) if len(lens) else np.zeros(0, np.uint8)
+        buf = buf.astype(np.uint8)
+        n = len(buf)
+        b = _slice_bounds(buf, n, G_)
+        assert len(b) == G_ + 1 and b[0] == 0 and b[-1] == n
+        assert all(b[i] <= b[i + 1] for i in range(G_))
+        for x in b[1:-1]:
+            assert x == 0 or buf[x - 1] == 10, (trial, x)
