@@ -283,3 +283,34 @@ def test_readers_under_thread_sanitizer():
         pytest.skip("no ThreadSanitizer runtime here: " + cc.stderr[-300:])
     r = subprocess.run([exe, d], capture_output=True, text=True, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1"))
     assert r.returncode == 0 and r.stdout.startswith("ok") and "ThreadSanitizer" not in r.stderr, (r.stdout + r.stderr)[-3000:]
+
+
+def test_inputs_of_many_parser_buffers():
+    """20 MB of FASTQ (five 4 MB parser buffers; records across every buffer end): plain file, plain gzip through the read-ahead
+    thread, BGZF through the pool, and the parser pool - one stream"""
+    from yak_b200 import synth
+    text = synth.reads_file_bytes(1, 500_000, 2, 64_000, fastq=True)
+    assert len(text) > (18 << 20)
+    plain = _write("yakb_big.fq", text)
+    want = read_all(plain, 0, cap=8 << 20)
+    assert want[1] == 64_000
+    gz = _write("yakb_big.fq.gz", gzip.compress(text, 1))
+    assert read_all(gz, 0, cap=8 << 20, expect_pool=False) == want
+    bz = _write("yakb_big.bgzf.fq.gz", bgzf_bytes(text, 65280, level=1))
+    assert read_all(bz, 4, cap=8 << 20, expect_pool=True) == want
+    assert read_all(bz, 3, job=300_000, cap=3 << 20) == want
+    L = capi.lib()
+    r = L.yakb_pfastx_open(plain.encode(), 1 << 20, 4)
+    out, nseq = bytearray(), 0
+    buf = C.create_string_buffer(8 << 20)
+    while True:
+        ns, done, need = C.c_int64(), C.c_int(), C.c_uint64()
+        n = L.yakb_pfastx_fill(r, buf, 8 << 20, 8 << 20, 0, C.byref(ns), C.byref(done), C.byref(need))
+        out += buf.raw[:n]
+        nseq += ns.value
+        if done.value:
+            break
+    L.yakb_pfastx_close(r)
+    assert (bytes(out), nseq) == want
+    for p in (plain, gz, bz):
+        os.unlink(p)
