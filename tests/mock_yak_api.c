@@ -1,0 +1,48 @@
+/* mock_yak_api.c - TEST INFRASTRUCTURE ONLY.  The yak.h entry points the CLI's host code (yak_b200/cli/main.c) calls, answered
+ * by the CPU oracle (oracle/yak_oracle.c), so that the command flows - option parsing, the two-pass protocol, cntasm's
+ * merge/shrink schedule, two-file inspect - can be run here, without a GPU, against the reference binary
+ * (tests/test_cli_flows_cpu.py).  It is linked into a throw-away executable under the test's temp directory and never into
+ * the product: libyakb200.so has no CPU path. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "yak.h"
+#include "yak_b200.h"
+#include "../oracle/yak_oracle.h"
+
+int yak_verbose = 3;
+#define O(h) ((yo_ch_t*)(h))
+
+void yak_copt_init(yak_copt_t *o) { o->bf_shift = 0; o->bf_n_hash = 4; o->k = 31; o->pre = 10; o->n_thread = 4; o->chunk_size = 10000000; } /* misc.c:23-32 */
+void yak_qopt_init(yak_qopt_t *o) { memset(o, 0, sizeof(*o)); o->chunk_size = 1000000000; o->n_threads = 4; o->min_frac = 0.5; o->fpr = 0.00004; }
+
+yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *h0)
+{
+	return (yak_ch_t*)yo_count_file_chunked(fn, opt->k, opt->pre, opt->bf_shift, opt->bf_n_hash, O(h0), 0, opt->chunk_size);
+}
+void yak_recount(const char *fn, yak_ch_t *h) { yo_ch_clear(O(h)); yo_count_file_chunked(fn, h->k, h->pre, 0, 4, O(h), 0, 1LL << 62); }
+void yak_ch_destroy(yak_ch_t *h) { if (h) yo_ch_destroy(O(h)); }
+void yak_ch_destroy_bf(yak_ch_t *h) { yo_ch_destroy_bf(O(h)); }
+void yak_ch_clear(yak_ch_t *h, int n) { (void)n; yo_ch_clear(O(h)); }
+void yak_ch_hist(const yak_ch_t *h, int64_t cnt[YAK_N_COUNTS], int n) { (void)n; yo_ch_hist(O(h), cnt); }
+void yak_ch_shrink(yak_ch_t *h, int min, int max, int n) { (void)n; yo_ch_shrink(O(h), min, max); }
+void yak_ch_setcnt(yak_ch_t *h, int cnt, int n) { (void)n; yo_ch_setcnt(O(h), cnt); }
+void yak_ch_merge(yak_ch_t *h0, yak_ch_t *h1, int min, int max, int n, int pre_resize) { (void)n; yo_ch_merge(O(h0), O(h1), min, max, pre_resize); }
+void yak_ch_tighten(yak_ch_t *h) { yo_ch_tighten(O(h)); }
+void yak_ch_subtract(yak_ch_t *h0, const yak_ch_t *h1, int n) { (void)n; yo_ch_subtract(O(h0), O(h1)); }
+void yak_ch_isec(yak_ch_t *h0, const yak_ch_t *h1, int n) { (void)n; yo_ch_isec(O(h0), O(h1)); }
+int yak_ch_dump(const yak_ch_t *h, const char *fn) { return yo_ch_dump(O(h), fn); }
+yak_ch_t *yak_ch_restore(const char *fn) { return (yak_ch_t*)yo_ch_restore(fn); }
+int yakb_ch_get_batch(const yak_ch_t *h, uint64_t n, const uint64_t *x, int32_t *out)
+{
+	uint64_t i;
+	for (i = 0; i < n; ++i) out[i] = yo_ch_get(O(h), x[i]);
+	return 0;
+}
+/* not exercised by the flow tests */
+yak_knt_t *yak_ch_getseq(const yak_ch_t *h, int w, uint32_t *n) { (void)h; (void)w; *n = 0; return 0; }
+void yak_qv(const yak_qopt_t *opt, const char *fn, const yak_ch_t *ch, int64_t *cnt) { (void)opt; (void)fn; (void)ch; memset(cnt, 0, YAK_N_COUNTS * sizeof(int64_t)); }
+int yakb_cmd_triobin(int argc, char *argv[]) { (void)argc; (void)argv; return 1; }
+int yakb_cmd_trioeval(int argc, char *argv[]) { (void)argc; (void)argv; return 1; }
+int yakb_cmd_chkerr(int argc, char *argv[]) { (void)argc; (void)argv; return 1; }
+int yakb_cmd_sexchr(int argc, char *argv[]) { (void)argc; (void)argv; return 1; }
