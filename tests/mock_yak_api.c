@@ -42,7 +42,27 @@ int yakb_ch_get_batch(const yak_ch_t *h, uint64_t n, const uint64_t *x, int32_t 
 /* not exercised by the flow tests */
 yak_knt_t *yak_ch_getseq(const yak_ch_t *h, int w, uint32_t *n) { (void)h; (void)w; *n = 0; return 0; }
 void yak_qv(const yak_qopt_t *opt, const char *fn, const yak_ch_t *ch, int64_t *cnt) { (void)opt; (void)fn; (void)ch; memset(cnt, 0, YAK_N_COUNTS * sizeof(int64_t)); }
+#ifdef MOCK_STUB_SCANNERS
 int yakb_cmd_triobin(int argc, char *argv[]) { (void)argc; (void)argv; return 1; }
 int yakb_cmd_trioeval(int argc, char *argv[]) { (void)argc; (void)argv; return 1; }
 int yakb_cmd_chkerr(int argc, char *argv[]) { (void)argc; (void)argv; return 1; }
 int yakb_cmd_sexchr(int argc, char *argv[]) { (void)argc; (void)argv; return 1; }
+#else
+/* the scanners of cli/scan.c: table loads with flag modes, one lookup call per batch of sequences */
+#include <stdarg.h>
+yak_ch_t *yak_ch_restore_core(yak_ch_t *ch0, const char *fn, int mode, ...)
+{
+	int min_cnt = 0, mid_cnt = 0;
+	va_list ap;
+	va_start(ap, mode);
+	if (mode == YAK_LOAD_TRIOBIN1 || mode == YAK_LOAD_TRIOBIN2) { min_cnt = va_arg(ap, int); mid_cnt = va_arg(ap, int); }
+	va_end(ap);
+	return (yak_ch_t*)yo_ch_restore_core(O(ch0), fn, mode, min_cnt, mid_cnt, 0);
+}
+int yakb_scan_seqs(const yak_ch_t *h, int64_t n_seq, const int64_t *lens, const char *cat, int16_t *out)
+{
+	int64_t i, off = 0;
+	for (i = 0; i < n_seq; off += lens[i++]) yo_scan_seq(O(h), lens[i], cat + off, out + off);
+	return 0;
+}
+#endif

@@ -24,7 +24,11 @@ def exe():
     cli = os.path.join(ROOT, "yak_b200", "cli")
     subprocess.run(["gcc", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", out,
                     os.path.join(cli, "main.c"), os.path.join(cli, "qv_solve.c"), os.path.join(cli, "inspect_logic.c"),
-                    os.path.join(ROOT, "tests", "mock_yak_api.c"), "-L" + O.ORACLE_DIR, "-loracle", "-Wl,-rpath," + O.ORACLE_DIR, "-lm", "-lz"], check=True)
+                    os.path.join(cli, "scan.c"), os.path.join(cli, "scan_logic.c"),
+                    os.path.join(ROOT, "tests", "mock_yak_api.c"), "-L" + O.ORACLE_DIR, "-loracle", "-Wl,-rpath," + O.ORACLE_DIR,
+                    # the record reader of the scanners is the library's own host code (no device involved); every yak.h symbol
+                    # resolves to the mock, which the linker sees first
+                    "-L" + os.path.join(ROOT, "yak_b200", "lib"), "-lyakb200", "-Wl,-rpath," + os.path.join(ROOT, "yak_b200", "lib"), "-lm", "-lz"], check=True)
     return out
 
 
@@ -77,3 +81,19 @@ def test_setop_and_inspect_command_lines(exe):
     for args in (["inspect", ya], ["inspect", ya, yb], ["inspect", "-m7", yb, ya], ["inspect", "-m", "40", yc, ya], ["inspect", ya, ya]):
         m, r = _both(exe, args, out_flag=False)
         assert m[0] == r[0] == 0 and m[1] == r[1] and r[1].count(b"\n") > 3, args
+
+
+def test_scanner_command_lines(exe):
+    """triobin / trioeval / chkerr / sexchr of cli/scan.c - options, table loads, batching, what follows truncated records -
+    against the reference binary's committed stdout (tests/golden/scan_*.txt)"""
+    import scan_inputs as S
+    paths = S.write_all(util.TMP)
+    for y, (fa, k) in S.COUNTS.items():
+        paths[y] = os.path.join(util.TMP, "yakb_flow_" + y)
+        h, _ = O.count_file(paths[fa], k=k, pre=10, bf_shift=0)
+        assert O.lib().yo_ch_dump(h, paths[y].encode()) == 0
+        O.lib().yo_ch_destroy(h)
+    for gold, cmd in S.CASES:
+        r = subprocess.run([exe] + S.argv(cmd, paths), capture_output=True)
+        assert r.returncode == 0, (gold, r.stderr.decode()[-500:])
+        assert r.stdout == open(os.path.join(ROOT, "tests", "golden", gold), "rb").read(), gold
