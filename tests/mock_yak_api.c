@@ -41,7 +41,25 @@ int yakb_ch_get_batch(const yak_ch_t *h, uint64_t n, const uint64_t *x, int32_t 
 }
 /* not exercised by the flow tests */
 yak_knt_t *yak_ch_getseq(const yak_ch_t *h, int w, uint32_t *n) { (void)h; (void)w; *n = 0; return 0; }
-void yak_qv(const yak_qopt_t *opt, const char *fn, const yak_ch_t *ch, int64_t *cnt) { (void)opt; (void)fn; (void)ch; memset(cnt, 0, YAK_N_COUNTS * sizeof(int64_t)); }
+/* qv.c:88-135 without -p / -E (those lines are printed inside the library): every record of the file in one batch */
+void yak_qv(const yak_qopt_t *opt, const char *fn, const yak_ch_t *ch, int64_t *cnt)
+{
+	yo_reader_t *r = yo_reader_open(fn);
+	const char *seq, *name;
+	char *cat = 0;
+	int64_t *lens = 0, n = 0, m = 0, tot = 0, cap = 0, len;
+	memset(cnt, 0, YAK_N_COUNTS * sizeof(int64_t));
+	if (r == 0) return;
+	while ((len = yo_reader_next(r, &seq, &name)) >= 0) {
+		if (n == m) { m = m ? m * 2 : 256; lens = (int64_t*)realloc(lens, m * sizeof(int64_t)); }
+		if (tot + len + 1 > cap) { cap = (tot + len + 1) * 2; cat = (char*)realloc(cat, cap); }
+		memcpy(cat + tot, seq, len);
+		tot += len; lens[n++] = len;
+	}
+	yo_reader_close(r);
+	yo_qv_seqs(O(ch), n, lens, cat ? cat : "", opt->min_len, opt->min_frac, cnt, 0, 0);
+	free(cat); free(lens);
+}
 #ifdef MOCK_STUB_SCANNERS
 int yakb_cmd_triobin(int argc, char *argv[]) { (void)argc; (void)argv; return 1; }
 int yakb_cmd_trioeval(int argc, char *argv[]) { (void)argc; (void)argv; return 1; }

@@ -97,3 +97,19 @@ def test_scanner_command_lines(exe):
         r = subprocess.run([exe] + S.argv(cmd, paths), capture_output=True)
         assert r.returncode == 0, (gold, r.stderr.decode()[-500:])
         assert r.stdout == open(os.path.join(ROOT, "tests", "golden", gold), "rb").read(), gold
+
+
+def test_qv_command_lines(exe):
+    """`qv` without -p / -E: option parsing, the hist of the table, the solver and the CT / FR / ER / CV / QV lines"""
+    import scan_inputs as S
+    paths = S.write_all(util.TMP)
+    y = os.path.join(util.TMP, "yakb_flow_qv.yak")
+    h, _ = O.count_file(G.input_path("reads_q"), k=31, pre=10, bf_shift=0)
+    assert O.lib().yo_ch_dump(h, y.encode()) == 0
+    O.lib().yo_ch_destroy(h)
+    asm = G.input_path("reads_a")
+    for args in (["qv", y, asm], ["qv", "-l", "100", "-f", "0.3", "-e", "0.0001", "-t2", y, asm], ["qv", "-K", "20k", y, asm], ["qv", y, paths["child.fa"]]):
+        m, r = _both(exe, args, out_flag=False)
+        assert m[0] == r[0] == 0 and m[1] == r[1] and r[1].count(b"\n") > 1000, args
+    m, r = _both(exe, ["qv", y], out_flag=False)
+    assert m[0] == r[0] == 1
