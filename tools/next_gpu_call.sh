@@ -14,6 +14,10 @@ for mb in 32 64 128; do
 	done
 done
 timeout 600 python bench.py --no-e2e --no-cpu --chunk-reads 5000000 --steps 117 > gpurun_out/n_bench_5m.json 2> gpurun_out/n_bench_5m.err
+# 5. the kernels under compute-sanitizer: the smoke run, memcheck then racecheck
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/n_memcheck.log 2>&1; echo "memcheck rc=$?"
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/n_racecheck.log 2>&1; echo "racecheck rc=$?"
+tail -n 5 gpurun_out/n_memcheck.log gpurun_out/n_racecheck.log
 tail -n 3 gpurun_out/n_pytest.log gpurun_out/n_pytest_unverified.log
 for f in gpurun_out/n_*.json; do python - "$f" <<'PY'
 import json, sys
