@@ -93,6 +93,14 @@ void yakb_fastx_close(void *reader);
  * core; here bgzf_threads < 0 keeps zlib's sequential reader, job_bytes = inflated bytes per unit of work. */
 void *yakb_fastx_open_bgzf(const char *fn, int bgzf_threads, uint64_t job_bytes);
 int yakb_fastx_bgzf_threads(void *reader);   /* 0 when the input does not go through the pool */
+/* `yak count -b` reads its input twice (reference main.c:53-60).  With YAKB_TEXT_CACHE_GB=<GB> (off by default) the first
+ * pass over a compressed file keeps the inflated text in an anonymous memory file and the second pass parses that with the
+ * parser pool instead of inflating again (csrc/textcache.h).  Test hooks for the two halves, no GPU involved:
+ * open a reader that keeps the text, commit after the last fill (1 = kept), ask for the path a second pass would open. */
+void *yakb_fastx_open_tee(const char *fn);
+int yakb_fastx_tee_commit(void *reader);
+int yakb_text_cache_path(const char *fn, char *buf, int len);
+void yakb_text_cache_release(void);
 /* bulk form used by yak_count: append whole records (length >= min_len) as "SEQ\n" until `target`
  * bytes; returns bytes appended; *done = input exhausted; *need != 0: grow buf to that size */
 int64_t yakb_fastx_fill(void *reader, char *buf, uint64_t cap, uint64_t target, int min_len,

@@ -314,3 +314,76 @@ def test_inputs_of_many_parser_buffers():
     assert (bytes(out), nseq) == want
     for p in (plain, gz, bz):
         os.unlink(p)
+
+
+def test_text_cache_for_the_second_pass(monkeypatch):
+    """csrc/textcache.h: the first pass over a compressed file keeps the inflated text in a memfd, the second pass maps it and
+    parses it with the parser pool - same records as reading the file again; nothing is kept when the text exceeds the budget,
+    when the cache is off, or for a file that changed in between"""
+    import time
+    L = lib()
+    L.yakb_fastx_open_tee.restype = C.c_void_p
+    L.yakb_fastx_open_tee.argtypes = [C.c_char_p]
+    L.yakb_fastx_tee_commit.argtypes = [C.c_void_p]
+    L.yakb_text_cache_path.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    L.yakb_pfastx_open.restype = C.c_void_p
+    L.yakb_pfastx_open.argtypes = [C.c_char_p, C.c_uint64, C.c_int]
+    L.yakb_pfastx_fill.restype = C.c_int64
+    L.yakb_pfastx_fill.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    L.yakb_pfastx_close.argtypes = [C.c_void_p]
+
+    def drain(r, fill, cap=1 << 20):
+        out, nseq = bytearray(), 0
+        buf = C.create_string_buffer(cap)
+        while True:
+            ns, done, need = C.c_int64(), C.c_int(), C.c_uint64()
+            n = fill(r, buf, cap, cap, 0, C.byref(ns), C.byref(done), C.byref(need))
+            assert not need.value
+            out += buf.raw[:n]
+            nseq += ns.value
+            if done.value:
+                return bytes(out), nseq
+
+    def first_pass(fn):
+        r = L.yakb_fastx_open_tee(fn.encode())
+        assert r
+        got = drain(r, L.yakb_fastx_fill)
+        kept = L.yakb_fastx_tee_commit(r)
+        L.yakb_fastx_close(r)
+        return got, kept
+
+    def cache_path(fn):
+        buf = C.create_string_buffer(256)
+        assert L.yakb_text_cache_path(fn.encode(), buf, 256) >= 0
+        return buf.value.decode()
+
+    rng = np.random.default_rng(21)
+    text = fastq_text(rng, 9000) + fastq_text(rng, 500, fasta=True)
+    plain = _write("yakb_tc.fx", text)
+    want = read_all(plain, 0)
+    gz = _write("yakb_tc.fx.gz", gzip.compress(text))
+    bz = _write("yakb_tc.bgzf.gz", bgzf_bytes(text, 20000, rng))
+    monkeypatch.delenv("YAKB_TEXT_CACHE_GB", raising=False)
+    assert first_pass(gz) == (want, 0) and cache_path(gz) == ""                    # off by default
+    monkeypatch.setenv("YAKB_TEXT_CACHE_GB", "0.5")
+    for fn in (gz, bz):
+        got, kept = first_pass(fn)
+        assert got == want and kept == 1
+        p = cache_path(fn)
+        assert p.startswith("/proc/self/fd/") and cache_path(plain) == ""
+        assert open(p, "rb").read() == text                                      # the inflated text, byte for byte
+        r = L.yakb_pfastx_open(p.encode(), 50_000, 3)                              # what the second pass does
+        assert r
+        L.yakb_text_cache_release()
+        assert cache_path(fn) == ""                                               # one use
+        assert drain(r, L.yakb_pfastx_fill) == want
+        L.yakb_pfastx_close(r)
+    monkeypatch.setenv("YAKB_TEXT_CACHE_GB", "0.000001")                         # 1 KB: the text does not fit
+    assert first_pass(gz) == (want, 0) and cache_path(gz) == ""
+    monkeypatch.setenv("YAKB_TEXT_CACHE_GB", "0.5")
+    assert first_pass(gz)[1] == 1 and cache_path(gz) != ""
+    time.sleep(0.01)
+    with open(gz, "wb") as f:                                                     # the file changed: the copy is not its text any more
+        f.write(gzip.compress(text[:100_000]))
+    assert cache_path(gz) == ""
+    L.yakb_text_cache_release()

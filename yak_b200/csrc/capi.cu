@@ -11,6 +11,7 @@
 #include "fastx.h"
 #include "fastx_par.h"
 #include "yakfile.h"
+#include "textcache.h"
 #include "yakb_dev.cuh"
 #include <stdio.h>
 #include <stdlib.h>
@@ -19,6 +20,7 @@
 #include <assert.h>
 #include <math.h>
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <sys/stat.h>
 #include <sys/mman.h>
@@ -634,6 +636,34 @@ extern "C" void *yakb_fastx_open_bgzf(const char *fn, int bgzf_threads, uint64_t
 	return r;
 }
 extern "C" int yakb_fastx_bgzf_threads(void *reader) { return ((FastxReader*)reader)->bgzf_threads(); }
+// test hooks (no GPU) for csrc/textcache.h: what yak_count does around its first pass over a compressed file ...
+namespace { std::mutex g_tee_mu; std::map<void*, std::pair<std::string, int>> g_tee; }
+extern "C" void *yakb_fastx_open_tee(const char *fn)
+{
+	FastxReader *r = new FastxReader;
+	if (!r->open(fn)) { delete r; return 0; }
+	std::string key;
+	const int fd = text_cache_begin(fn, &key);
+	if (fd >= 0) { r->tee_to(fd, text_cache_budget()); std::lock_guard<std::mutex> lk(g_tee_mu); g_tee[r] = {key, fd}; }
+	return r;
+}
+extern "C" int yakb_fastx_tee_commit(void *reader) // after the last fill(): 1 if the text was kept
+{
+	std::pair<std::string, int> t;
+	{ std::lock_guard<std::mutex> lk(g_tee_mu); auto it = g_tee.find(reader); if (it == g_tee.end()) return 0; t = it->second; g_tee.erase(it); }
+	const uint64_t n = ((FastxReader*)reader)->tee_bytes();
+	text_cache_end(t.first, t.second, n);
+	return n != UINT64_MAX;
+}
+// ... and before its second: the path that maps the kept text ("" if none), and the release that follows the open
+extern "C" int yakb_text_cache_path(const char *fn, char *buf, int len)
+{
+	const std::string p = text_cache_lookup(fn);
+	if ((int)p.size() + 1 > len) return -1;
+	memcpy(buf, p.c_str(), p.size() + 1);
+	return (int)p.size();
+}
+extern "C" void yakb_text_cache_release(void) { text_cache_release(); }
 extern "C" int64_t yakb_fastx_next(void *reader, const char **seq, const char **name)
 {
 	FastxReader *r = (FastxReader*)reader;
@@ -774,8 +804,14 @@ static yak_ch_t *count_impl(const char *fn, const yak_copt_t *opt, yak_ch_t *h0,
 	StageTimer tm("yak_count");
 	FastxReader rd;
 	ParallelFastx prd; // plain regular files are parsed by several threads; gzip / stdin by the sequential reader
-	const bool par = !getenv("YAKB_SERIAL_PARSE") && prd.open(fn);
+	// the second pass over a compressed file reads the text the first pass kept (csrc/textcache.h; YAKB_TEXT_CACHE_GB, off by default)
+	const std::string cached = h0 ? text_cache_lookup(fn) : std::string();
+	const char *src = cached.empty() ? fn : cached.c_str();
+	const bool par = !getenv("YAKB_SERIAL_PARSE") && prd.open(src);
+	if (!cached.empty()) text_cache_release(); // one use: the mapping keeps the text alive until prd closes
 	if (!par && !rd.open(fn)) return 0;
+	struct Tee { std::string key; int fd = -1; ~Tee() { if (fd >= 0) close(fd); } } tee;
+	if (!par && !h0 && (tee.fd = text_cache_begin(fn, &tee.key)) >= 0) rd.tee_to(tee.fd, text_cache_budget());
 	prd.set_ref_flow(opt->chunk_size, ref_workers, -1); // -K and the pipeline decide what follows a truncated FASTQ record
 	rd.set_ref_chunk(opt->chunk_size); rd.set_ref_workers(ref_workers);
 	yak_ch_t *h = h0;
@@ -787,7 +823,7 @@ static yak_ch_t *count_impl(const char *fn, const yak_copt_t *opt, yak_ch_t *h0,
 	const int create_new = h0 == 0;
 	uint64_t cap = batch_bases(opt->chunk_size);
 	struct stat st;
-	if (par && stat(fn, &st) == 0 && S_ISREG(st.st_mode)) // a batch never holds more than the file: no 2 x 1.9 GB of pinned memory for `cntasm -K1.9g` on a small assembly
+	if (par && stat(src, &st) == 0 && S_ISREG(st.st_mode)) // a batch never holds more than the file: no 2 x 1.9 GB of pinned memory for `cntasm -K1.9g` on a small assembly
 		cap = std::min<uint64_t>(cap, std::max<uint64_t>((uint64_t)st.st_size + 4096, 1u << 20));
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -852,6 +888,7 @@ static yak_ch_t *count_impl(const char *fn, const yak_copt_t *opt, yak_ch_t *h0,
 		slot ^= 1;
 		target = next_target;
 	}
+	if (tee.fd >= 0) { text_cache_end(tee.key, tee.fd, rd.tee_bytes()); tee.fd = -1; }
 	if (timing_on()) fprintf(stderr, "[T::yak_count] %d batches: first batch ready after %.3f s, kernels %.3f s, waiting for the producer %.3f s\n", n_batches, t_first, t_dev, t_wait);
 	return h;
 	GUARD_END(0)

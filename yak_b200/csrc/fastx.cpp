@@ -10,6 +10,7 @@
 #include <string.h>
 #include <ctype.h>
 #include <stdlib.h>
+#include <unistd.h>
 #include <thread>
 #include <mutex>
 #include <condition_variable>
@@ -35,7 +36,7 @@ bool FastxReader::open(const char *fn, int bgzf_threads, size_t bgzf_job_bytes)
 {
 	close();
 	buf_.resize(kBuf);
-	beg_ = end_ = 0; eof_ = src_last_ = false; last_ = 0;
+	beg_ = end_ = 0; eof_ = src_last_ = src_end_seen_ = false; last_ = 0;
 	yakb_ref_flow_init(&flow_, 3, ref_chunk_, 0);
 	if (fn != nullptr && strcmp(fn, "-") != 0 && bgzf_threads >= 0 && !getenv("YAKB_NO_PBGZF")) {
 		bgzf_ = new BgzfPool;
@@ -88,6 +89,25 @@ void FastxReader::close()
 }
 
 int64_t FastxReader::read_block_()
+{
+	const int64_t n = read_source_();
+	if (src_last_) src_end_seen_ = true;
+	if (tee_ok_ && n > 0) { // the second pass of a compressed file reads this copy instead of inflating again
+		if (tee_bytes_ + (uint64_t)n > tee_budget_) tee_ok_ = false;
+		else {
+			int64_t done = 0;
+			while (done < n) {
+				const ssize_t w = write(tee_fd_, buf_.data() + done, (size_t)(n - done));
+				if (w <= 0) { tee_ok_ = false; break; }
+				done += w;
+			}
+			tee_bytes_ += (uint64_t)n;
+		}
+	}
+	return n;
+}
+
+int64_t FastxReader::read_source_()
 {
 	if (bgzf_) return bgzf_->next(buf_, &src_last_);
 	if (!ahead_) {

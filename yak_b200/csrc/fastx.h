@@ -18,6 +18,10 @@ public:
 	// bgzf_threads 0 = one per core, < 0 = zlib's sequential reader as for any other gzip file (also YAKB_NO_PBGZF=1)
 	bool open(const char *fn, int bgzf_threads = 0, size_t bgzf_job_bytes = 4u << 20);
 	int bgzf_threads() const;   // 0 when the input is not read through the BGZF pool
+	// keep a copy of every block of (inflated) text the source delivers in fd, up to budget bytes (csrc/textcache.h);
+	// tee_bytes(): the size of the copy once the source has delivered its last block and everything fit, else UINT64_MAX
+	void tee_to(int fd, uint64_t budget) { tee_fd_ = fd; tee_budget_ = budget; tee_bytes_ = 0; tee_ok_ = fd >= 0; }
+	uint64_t tee_bytes() const { return tee_ok_ && src_end_seen_ ? tee_bytes_ : UINT64_MAX; }
 	void close();
 	// next record: sequence bytes (line ends removed) in seq(); returns length, -1 at EOF,
 	// -2 on a truncated quality string (kseq.h:189-191)
@@ -46,6 +50,11 @@ private:
 	Ahead *ahead_ = nullptr;
 	BgzfPool *bgzf_ = nullptr;
 	bool src_last_ = false;    // the block read_block_() just returned is the last one
+	bool src_end_seen_ = false; // the source has delivered its last block (the parse may stop earlier: truncated-record rule)
+	int tee_fd_ = -1;
+	uint64_t tee_budget_ = 0, tee_bytes_ = 0;
+	bool tee_ok_ = false;
+	int64_t read_source_();    // read_block_ without the tee
 	int64_t read_block_();     // next block into buf_; returns its length (0 possible at the end of the input), sets src_last_
 	int getc_();
 	// append the rest of the current line to s (without the '\n'); false if nothing was left
