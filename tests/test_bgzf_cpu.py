@@ -219,7 +219,7 @@ def test_bgzf_truncated_and_corrupted_files(seed):
             assert read_all(fn, -1) == want
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", list(range(12)) + [27, 53, 73])
 def test_sequential_reader_buffer_boundaries_on_adversarial_input(seed):
     """the sequential reader's block buffer is 4 MB, so small test files never put a record across two buffers.  BGZF members
     of a few bytes with one member per job do: every member becomes one parser buffer.  Adversarial FASTA/FASTQ (CRLF, blank
