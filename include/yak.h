@@ -24,8 +24,8 @@ extern "C" {
 #define YAK_BLK_SHIFT    9
 #define YAK_BLK_MASK     ((1<<(YAK_BLK_SHIFT)) - 1)
 
-/* reference yak.h:16-21 - yak_ch_restore_core() modes (only YAK_LOAD_ALL is implemented; the
- * trio/sex-chromosome remaps are SURVEY 8(f) rank 2 and abort with a message) */
+/* reference yak.h:16-21 - yak_ch_restore_core() modes; all six are implemented (htab.c:396-476: the
+ * trio / sex-chromosome modes remap counts to flag bits while loading, csrc/capi.cu yak_ch_restore_core) */
 #define YAK_LOAD_ALL       1
 #define YAK_LOAD_TRIOBIN1  2
 #define YAK_LOAD_TRIOBIN2  3

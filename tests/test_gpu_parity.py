@@ -294,6 +294,7 @@ def test_layout_replay_variants_agree(oracle, yakb, reads_fa, monkeypatch, smem_
 
 ZONE_SNIPPET = r"""
 import sys, os
+import ctypes as C
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
 import numpy as np
 import oracle_lib
@@ -311,40 +312,99 @@ for k, pre, b in ((31, 10, 0), (31, 12, 24), (47, 11, 23), (21, 10, 22)):
     ho, _ = oracle_lib.count_file(fn, k=k, pre=pre, bf_shift=b)
     assert capi.dump_bytes(hg) == oracle_lib.dump_bytes(ho), (k, pre, b)
     capi.lib().yak_ch_destroy(hg); oracle_lib.lib().yo_ch_destroy(ho)
+# the array front end (yak_ch_insert_list, count.c:82; the multi-GPU receive side) through the same partition
+OL, L = oracle_lib.lib(), capi.lib()
+k, pre = 31, 10
+seqs = [ln.strip() for ln in open(fn, "rb") if not ln.startswith(b">")][:4000]
+ev = []
+for s in seqs:
+    buf = (C.c_uint64 * len(s))()
+    n = OL.yo_extract(k, len(s), s, buf)
+    ev.append(np.frombuffer(buf, dtype=np.uint64, count=n).copy())
+ev = np.concatenate(ev)
+for b in (0, 21):
+    ho, hg = OL.yo_ch_init(k, pre, 4, b), L.yak_ch_init(k, pre, 4, b)
+    for part in np.array_split(ev, 3):
+        sub = (part & np.uint64((1 << pre) - 1)).astype(np.int64)
+        order = np.argsort(sub, kind="stable")
+        part_s, sub_s = part[order], sub[order]
+        for lst in np.split(part_s, np.flatnonzero(np.diff(sub_s)) + 1):
+            a = np.ascontiguousarray(lst, dtype=np.uint64)
+            p = a.ctypes.data_as(C.POINTER(C.c_uint64))
+            assert OL.yo_ch_insert_list(ho, 1, len(a), p) == L.yak_ch_insert_list(hg, 1, len(a), p)
+    a = np.ascontiguousarray(ev[:50_000], dtype=np.uint64)         # a long list with foreign elements (htab.c:61)
+    p = a.ctypes.data_as(C.POINTER(C.c_uint64))
+    assert OL.yo_ch_insert_list(ho, 1, len(a), p) == L.yak_ch_insert_list(hg, 1, len(a), p)
+    assert capi.dump_bytes(hg) == oracle_lib.dump_bytes(ho), ("insert_list", b)
+    L.yak_ch_destroy(hg); OL.yo_ch_destroy(ho)
 print("zone ok")
 """
 
 
 @pytest.mark.parametrize("env", [
-    {"YAKB_ZONE": "1", "YAKB_ZONE_MB": "0.02"},                              # several sub-tables per zone
-    {"YAKB_ZONE": "1", "YAKB_ZONE_MB": "0.0001"},                            # one sub-table per zone
-    {"YAKB_ZONE": "1", "YAKB_ZONE_MB": "0.02", "YAKB_ZONE_SLACK": "0"},      # zone lists overflow into the spill list
-    {"YAKB_ZONE": "1", "YAKB_ZONE_MB": "4"},                                 # few zones
-], ids=["zones", "zone-per-subtable", "spill", "few-zones"])
-def test_zone_blocked_front_end_is_bit_exact(env):
-    """the zone-blocked probe path (engine.cu: zone_scatter / zone_probe) is chosen for tables of gigabytes; force it
-    on small inputs - both passes, several chunks, skewed k-mers - and compare the .yak bytes with the oracle"""
+    {"YAKB_ZONE_MB": "0.02"},                                  # several sub-tables per zone
+    {"YAKB_ZONE_MB": "0.0001"},                                # one sub-table per zone (2048 zones at -p12: the maximum)
+    {"YAKB_ZONE_MB": "0.02", "YAKB_ZONE_SLACK": "0"},          # zone lists overflow into the spill list, the spill list into the fallback
+    {"YAKB_ZONE_MB": "4"},                                     # few zones
+    {"YAKB_ZONE_MB": "0.02", "YAKB_PEND_MAX": "20000"},        # the pending events of a chunk in many ranges
+    {"YAKB_ZONE": "0", "YAKB_PEND_MAX": "5000"},               # ranges behind the unpartitioned probe
+], ids=["zones", "zone-per-subtable", "spill", "few-zones", "pending-ranges", "ranges-unpartitioned"])
+def test_partitioned_front_end_is_bit_exact(env):
+    """the partitioned probe path (partition.cuh: part_scatter, engine.cu: zone_probe) is chosen for tables of gigabytes and
+    chunks of tens of millions of positions; force it on small inputs - both passes, several chunks, skewed k-mers, packed
+    reads and event arrays - and compare the .yak bytes with the oracle"""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    e = dict(os.environ, YAKB_BATCH="1500000", **env)
+    e = dict(os.environ, YAKB_BATCH="1500000", YAKB_ZONE="1")
+    e.update(env)
     r = subprocess.run([sys.executable, "-c", ZONE_SNIPPET.format(root=root, fn=os.path.join(util.TMP, "yakb_zone.fa"))],
-                       env=e, capture_output=True, text=True)
+                       env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "zone ok" in r.stdout, r.stderr[-3000:]
 
 
-@pytest.mark.skipif(os.environ.get("YAKB_TEST_UNVERIFIED") != "1",
-                    reason="zone_scatter_staged was written without GPU access (end of round 1); set YAKB_TEST_UNVERIFIED=1 to run")
-@pytest.mark.parametrize("env", [
-    {"YAKB_ZONE_MB": "0.02"}, {"YAKB_ZONE_MB": "0.0001"}, {"YAKB_ZONE_MB": "0.02", "YAKB_ZONE_SLACK": "0"}, {"YAKB_ZONE_MB": "4"},
-    {"YAKB_ZONE_MB": "0.02", "YAKB_ZTILE_WORDS": "512"},
-], ids=["zones", "zone-per-subtable", "spill", "few-zones", "tile512"])
-def test_zone_staged_scatter_is_bit_exact(env):
-    """the same cases through the shared-memory staged scatter (engine.cu: zone_scatter_staged, YAKB_ZONE_STAGED=1)"""
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    e = dict(os.environ, YAKB_BATCH="1500000", YAKB_ZONE="1", YAKB_ZONE_STAGED="1", **env)
-    r = subprocess.run([sys.executable, "-c", ZONE_SNIPPET.format(root=root, fn=os.path.join(util.TMP, "yakb_zone_s.fa"))],
-                       env=e, capture_output=True, text=True, timeout=300)   # never-run kernel: do not let it hold the box
-    assert r.returncode == 0 and "zone ok" in r.stdout, r.stderr[-3000:]
+def test_ch_inc_matches_oracle(oracle, yakb, reads_fa):
+    """yak_ch_inc (htab.c:80-91): saturating ++ of an existing key, -1 for an absent one; then the bytes"""
+    OL, L = oracle.lib(), yakb.lib()
+    OL.yo_ch_inc.restype = C.c_int
+    OL.yo_ch_inc.argtypes = [C.POINTER(oracle.YoCh), C.c_uint64]
+    k, pre = 31, 10
+    ho, _ = oracle.count_file(reads_fa, k=k, pre=pre, bf_shift=0)
+    hg = yakb.count_file(reads_fa, k=k, pre=pre, bf_shift=0)
+    seqs = [ln.strip() for ln in open(reads_fa) if not ln.startswith(">")][:40]
+    ev = []
+    for s in seqs:
+        buf = (C.c_uint64 * len(s))()
+        n = OL.yo_extract(k, len(s), s.encode(), buf)
+        ev.append(np.frombuffer(buf, dtype=np.uint64, count=n).copy())
+    ev = np.concatenate(ev)[:600]
+    absent = ev[:50] ^ np.uint64(0x2AAAAAAAAAAA)
+    for x in np.concatenate([ev, absent, ev[:20]]):
+        assert L.yak_ch_inc(hg, int(x)) == OL.yo_ch_inc(ho, int(x))
+    # a counter at the cap stays there (htab.c:88): polyA-like saturation by repeated increments of one key
+    x0 = int(ev[0])
+    for _ in range(1030):
+        OL.yo_ch_inc(ho, x0)
+    OL.yo_ch_inc.restype = C.c_int
+    a, p = util.u64_array(np.full(1030, x0, dtype=np.uint64))
+    L.yak_ch_insert_list(hg, 0, len(a), p)               # the batched form of the same increments
+    assert L.yak_ch_inc(hg, x0) == OL.yo_ch_inc(ho, x0) == 1023
+    assert yakb.dump_bytes(hg) == oracle.dump_bytes(ho)
+    L.yak_ch_destroy(hg); OL.yo_ch_destroy(ho)
+
+
+@pytest.mark.parametrize("n_shift,n_hashes", [(9, 4), (12, 4), (20, 2), (16, 12), (24, 40)])
+def test_public_bloom_filter_matches_oracle(oracle, yakb, n_shift, n_hashes):
+    """yak_bf_init / yak_bf_insert / yak_bf_destroy (bbf.c:5-42) as a stand-alone device filter: the same return value
+    (number of bits already set) for every insert of a stream with repeats; init refuses n_shift < 9 and > 55"""
+    OL, L = oracle.lib(), yakb.lib()
+    assert not L.yak_bf_init(8, 4) and not L.yak_bf_init(56, 4)          # bbf.c:9
+    bo, bg = OL.yo_bloom_init(n_shift, n_hashes), L.yak_bf_init(n_shift, n_hashes)
+    assert bo and bg
+    rng = np.random.default_rng(n_shift * 100 + n_hashes)
+    xs = rng.integers(0, 1 << 62, 400, dtype=np.uint64)
+    xs = np.concatenate([xs, xs[::3], (xs[:64] & np.uint64((1 << n_shift) - 1)) | np.uint64(32 << n_shift)])  # h2 a multiple of 32: bbf.c:33
+    for x in xs:
+        assert L.yak_bf_insert(bg, int(x)) == OL.yo_bloom_insert(bo, int(x))
+    L.yak_bf_destroy(bg); OL.yo_bloom_destroy(bo)
+    L.yak_bf_destroy(None)                                                 # bbf.c:22: NULL-safe

@@ -293,15 +293,31 @@ extern "C" void yak_ch_tighten(yak_ch_t *h)
 	GUARD_END_VOID
 }
 
+// Sub-table ranges [s0, s1) whose key totals stay below `max_keys` (one sub-table at least): the slices in which
+// a table is brought to the host.  A fixed 1024 sub-tables was the whole table at -p10, i.e. tens of gigabytes
+// of host memory and more than 2^31 events in one count_events() call for human-size assemblies.
+static std::vector<int> slice_bounds(Engine *e, uint64_t max_keys = 1ull << 28)
+{
+	std::vector<uint32_t> z;
+	e->sizes(z);
+	std::vector<int> b(1, 0);
+	uint64_t acc = 0;
+	for (int s = 0; s < e->P; ++s) {
+		if (s > b.back() && (acc + z[s] > max_keys || s - b.back() >= 1024)) { b.push_back(s); acc = 0; }
+		acc += z[s];
+	}
+	if (e->P > b.back()) b.push_back(e->P);
+	return b;
+}
+
 // all sub-tables of a table in slot order with counts, brought to the host in slices
 template<class F> static void for_each_slice(Engine *e, F &&fn)
 {
-	const int step = 1024;
-	for (int s0 = 0; s0 < e->P; s0 += step) {
-		const int s1 = std::min(e->P, s0 + step);
+	const std::vector<int> b = slice_bounds(e);
+	for (size_t i = 0; i + 1 < b.size(); ++i) {
 		LayoutOut lo;
-		e->layout(s0, s1, lo, true);
-		fn(s0, s1, lo);
+		e->layout(b[i], b[i + 1], lo, true);
+		fn(b[i], b[i + 1], lo);
 	}
 }
 
@@ -408,17 +424,16 @@ extern "C" void yak_ch_isec(yak_ch_t *h0, const yak_ch_t *h1, int n_thread)
 template<class Sink> static void serialise(ChBox *b, Sink &&sink, bool header = true)
 {
 	const yak_ch_t *h = &b->pub;
-	const int P = b->eng->P; // a shard writes its own contiguous range of sub-tables
 	uint32_t t[3] = {(uint32_t)h->k, (uint32_t)h->pre, YAK_COUNTER_BITS};
 	if (header) {
 		sink(YAK_MAGIC, 4);
 		sink(t, 12);
 	}
-	const int step = 1024;
 	double t_lay = 0, t_sink = 0;
 	LayoutOut lo; // one for all steps: Engine::layout resets it, and its key array (gigabytes) keeps its pages
-	for (int s0 = 0; s0 < P; s0 += step) {
-		const int s1 = std::min(P, s0 + step);
+	const std::vector<int> bounds = slice_bounds(b->eng, 1ull << 30);
+	for (size_t bi = 0; bi + 1 < bounds.size(); ++bi) {
+		const int s0 = bounds[bi], s1 = bounds[bi + 1];
 		double t0 = wall_now();
 		b->eng->layout(s0, s1, lo, true);
 		double t1 = wall_now();

@@ -17,6 +17,7 @@
 #include "yakb_dev.cuh"
 #include "kernels.cuh"
 #include "extras.cuh"
+#include "partition.cuh"
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
@@ -139,9 +140,11 @@ static bool g_prof_on = false;
 struct ProfPair { const char *name; cudaEvent_t a, b; };
 static std::vector<ProfPair> g_prof_open, g_prof_done;
 static std::map<std::string, std::pair<double, uint64_t>> g_prof_acc;
+static std::map<std::string, uint64_t> g_prof_units; // work items (events, pending events, positions) a kernel name processed
 void Prof::enable(bool on) { g_prof_on = on; }
 bool Prof::on() { return g_prof_on; }
-void Prof::reset() { g_prof_acc.clear(); }
+void Prof::reset() { g_prof_acc.clear(); g_prof_units.clear(); }
+void Prof::units(const char *name, uint64_t n) { if (g_prof_on) g_prof_units[name] += n; }
 void Prof::begin(const char *name, cudaStream_t s)
 {
 	ProfPair p; p.name = name;
@@ -172,7 +175,9 @@ std::string Prof::json()
 	char buf[256];
 	bool first = true;
 	for (auto &kv : g_prof_acc) {
-		snprintf(buf, sizeof(buf), "%s\"%s\": [%.6f, %llu]", first ? "" : ", ", kv.first.c_str(), kv.second.first, (unsigned long long)kv.second.second);
+		auto u = g_prof_units.find(kv.first);
+		snprintf(buf, sizeof(buf), "%s\"%s\": [%.6f, %llu, %llu]", first ? "" : ", ", kv.first.c_str(), kv.second.first, (unsigned long long)kv.second.second,
+		         (unsigned long long)(u == g_prof_units.end() ? 0 : u->second));
 		o += buf; first = false;
 	}
 	return o + "}";
@@ -335,176 +340,14 @@ __global__ void __launch_bounds__(256, 3) k1_fused(const uint64_t *__restrict__ 
 		for (uint32_t i = threadIdx.x; i < P; i += 256) if (s_lp[i]) atomicMax(&glob_lput[i], s_lp[i]);
 }
 
-// ---- K1, zone-blocked front end for large tables.  Random 32-byte read-modify-writes spread over tens of
-//      gigabytes run at ~12 G/s on this part; the same operations confined to ~100 MB of the table at a time
-//      run 2-4 times faster (DRAM row locality + L2 merging; tools/zone_sweep.cu).  So the events of a chunk
-//      are first scattered into per-zone lists (zone = a group of neighbouring sub-tables), then the table
-//      is probed zone by zone.  Counter updates commute, and the pending flag / last-put bookkeeping are
-//      per position, so the order in which events reach the table is free.
+// ---- K1, partitioned front end for large tables.  Random 32-byte read-modify-writes spread over tens of
+//      gigabytes run at ~12-15 G/s on this part; the same operations confined to tens of megabytes of the table
+//      at a time run 2-4 times faster (DRAM row locality + L2 merging; tools/zone_sweep.cu).  So the events of a
+//      chunk are first partitioned into per-zone lists (zone = a group of neighbouring sub-tables; part_scatter in
+//      partition.cuh - the reference's ch_insert_buf, count.c:17-26), then the table is probed zone by zone.
+//      Counter updates commute, and the pending flag / last-put bookkeeping are per position, so the order in
+//      which events reach the table is free.
 //
-//      zone_scatter: one pass over the packed reads, each CTA a tile of `ztile` words: roll + hash every
-//      k-mer twice - once to count the tile's events per zone (shared-memory bins), once, after reserving the
-//      tile's ranges in the zone lists with one global atomic per zone, to write (hash, position) there.
-//      Zone lists have a fixed capacity (mean + 25 %); what does not fit goes to a spill list (skewed input).
-//      Ranks inside a (tile, zone) run come from warp votes, not from shared-memory atomics with a return
-//      value (those cost ~200 cycles per warp instruction here): every warp keeps private per-zone counters;
-//      the lanes of a step that hit the same zone find each other with match.any, the first of them bumps
-//      the warp's counter for all, the others take consecutive places behind it.
-template<bool LONGK, int PASS, class F>
-__device__ __forceinline__ void zone_roll(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t W, bool live, int k,
-                                          uint32_t Pmask, Own own, int zshift, uint32_t *wc, uint32_t &my_ev, F &&place)
-{
-	const int lane = threadIdx.x & 31;
-	Roller<LONGK> ro;
-	if (live) ro.init(w2, wm, (int64_t)W, k);
-#pragma unroll 4
-	for (int r = 0; r < 32; ++r) {
-		uint64_t v = 0;
-		const bool e = live && ro.step(r, v) && ((uint32_t)(v >> own.shift) & own.mask) == own.rank;
-		const uint32_t z = e ? ((uint32_t)v & Pmask) >> zshift : 0xFFFFFFFFu;
-		const uint32_t m = __match_any_sync(0xffffffffu, z);
-		const int leader = __ffs(m) - 1;
-		uint32_t base = 0;
-		if (e && lane == leader) { base = wc[z]; wc[z] = base + __popc(m); }
-		__syncwarp();
-		if (PASS == 1) {
-			base = __shfl_sync(0xffffffffu, base, leader);
-			if (e) place(r, v, z, base + __popc(m & ((1u << lane) - 1)));
-		} else if (e) ++my_ev;
-	}
-}
-
-template<bool LONGK>
-__global__ void __launch_bounds__(256) zone_scatter(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords, int k, uint32_t ztile,
-                                                    uint32_t Pmask, Own own, int zshift, uint32_t Z, uint32_t zcap, unsigned int *zfill,
-                                                    uint64_t *__restrict__ zev, uint32_t *__restrict__ zpos,
-                                                    uint64_t *__restrict__ spill_ev, uint32_t *__restrict__ spill_pos, unsigned int *n_spill,
-                                                    unsigned long long *stats)
-{
-	extern __shared__ uint32_t s_z[]; // [8 warps][Z]: events per (warp, zone), then each warp's cursor into the zone lists
-	uint32_t *wc = s_z + (threadIdx.x >> 5) * Z;
-	const uint64_t ntiles = (nwords + ztile - 1) / ztile;
-	uint32_t my_ev = 0;
-	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-		for (uint32_t i = threadIdx.x; i < 8 * Z; i += 256) s_z[i] = 0;
-		__syncthreads();
-		for (uint32_t j = 0; j < ztile / 256; ++j) {
-			const uint64_t W = tile * ztile + j * 256 + threadIdx.x;
-			zone_roll<LONGK, 0>(w2, wm, W, W < nwords, k, Pmask, own, zshift, wc, my_ev, [](int, uint64_t, uint32_t, uint32_t) {});
-		}
-		__syncthreads();
-		for (uint32_t z = threadIdx.x; z < Z; z += 256) { // one reservation per zone for the whole tile, split among the warps
-			uint32_t c[8], tot = 0;
-#pragma unroll
-			for (int w = 0; w < 8; ++w) { c[w] = s_z[w * Z + z]; tot += c[w]; }
-			uint32_t base = tot ? atomicAdd(&zfill[z], tot) : 0;
-#pragma unroll
-			for (int w = 0; w < 8; ++w) { s_z[w * Z + z] = base; base += c[w]; }
-		}
-		__syncthreads();
-		for (uint32_t j = 0; j < ztile / 256; ++j) {
-			const uint64_t W = tile * ztile + j * 256 + threadIdx.x;
-			zone_roll<LONGK, 1>(w2, wm, W, W < nwords, k, Pmask, own, zshift, wc, my_ev, [&](int r, uint64_t v, uint32_t z, uint32_t i) {
-				const uint32_t pos = (uint32_t)(W * 32 + r);
-				if (i < zcap) { zev[(uint64_t)z * zcap + i] = v; zpos[(uint64_t)z * zcap + i] = pos; }
-				else { const uint32_t q = atomicAdd(n_spill, 1u); spill_ev[q] = v; spill_pos[q] = pos; }
-			});
-		}
-		__syncthreads();
-	}
-#pragma unroll
-	for (int d = 16; d; d >>= 1) my_ev += __shfl_xor_sync(0xffffffffu, my_ev, d);
-	if ((threadIdx.x & 31) == 0 && my_ev) atomicAdd(&stats[0], (unsigned long long)my_ev);
-}
-
-//      zone_scatter_staged (YAKB_ZONE_STAGED=1; written after the measurements above, NOT yet run on a GPU - see
-//      DESIGN.md section 9): the same two rolls per tile, but the second one places (hash, position) into a
-//      shared-memory staging area in zone order; the tile is then copied out by consecutive threads, so every
-//      (tile, zone) run leaves the SM as a few whole sectors instead of one 8-byte and one 4-byte store per event.
-//      Shared memory: [TMAX] u64 hashes | [TMAX] u32 positions | [8][Z] per-warp counters / cursors |
-//      [Z] place of the tile's run in the zone list | [Z + 1] place of the run in the staging area.
-template<bool LONGK>
-__global__ void __launch_bounds__(256) zone_scatter_staged(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords, int k, uint32_t ztile,
-                                                           uint32_t Pmask, Own own, int zshift, uint32_t Z, uint32_t zcap, unsigned int *zfill,
-                                                           uint64_t *__restrict__ zev, uint32_t *__restrict__ zpos,
-                                                           uint64_t *__restrict__ spill_ev, uint32_t *__restrict__ spill_pos, unsigned int *n_spill,
-                                                           unsigned long long *stats)
-{
-	extern __shared__ uint64_t s_stage_ev[];
-	const uint32_t tmax = ztile * 32;
-	uint32_t *s_stage_pos = (uint32_t*)(s_stage_ev + tmax);
-	uint32_t *s_cnt = s_stage_pos + tmax;   // [8][Z]
-	uint32_t *s_goff = s_cnt + 8 * Z;       // [Z]
-	uint32_t *s_toff = s_goff + Z;          // [Z + 1]
-	__shared__ uint32_t s_wsum[8];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t *wc = s_cnt + warp * Z;
-	const uint32_t zpt = (Z + 255) / 256;   // zones per thread in the offsets step, <= 8 (Z <= 2048)
-	const uint64_t ntiles = (nwords + ztile - 1) / ztile;
-	uint32_t my_ev = 0;
-	for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-		for (uint32_t i = threadIdx.x; i < 8 * Z; i += 256) s_cnt[i] = 0;
-		__syncthreads();
-		for (uint32_t j = 0; j < ztile / 256; ++j) {
-			const uint64_t W = tile * ztile + j * 256 + threadIdx.x;
-			zone_roll<LONGK, 0>(w2, wm, W, W < nwords, k, Pmask, own, zshift, wc, my_ev, [](int, uint64_t, uint32_t, uint32_t) {});
-		}
-		__syncthreads();
-		// per zone: events of the tile, their place in the staging area (exclusive scan over the zones) and in the zone list
-		uint32_t tot[8], sum = 0;
-#pragma unroll
-		for (uint32_t q = 0; q < 8; ++q) {
-			const uint32_t z = threadIdx.x * zpt + q;
-			tot[q] = 0;
-			if (q < zpt && z < Z) {
-#pragma unroll
-				for (int w = 0; w < 8; ++w) tot[q] += s_cnt[w * Z + z];
-			}
-			sum += tot[q];
-		}
-		uint32_t incl = sum;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-		if (lane == 31) s_wsum[warp] = incl;
-		__syncthreads();
-		uint32_t run = incl - sum;
-		for (int w = 0; w < warp; ++w) run += s_wsum[w];
-#pragma unroll
-		for (uint32_t q = 0; q < 8; ++q) {
-			const uint32_t z = threadIdx.x * zpt + q;
-			if (q < zpt && z < Z) {
-				s_toff[z] = run;
-				s_goff[z] = tot[q] ? atomicAdd(&zfill[z], tot[q]) : 0;
-				uint32_t b = run;
-#pragma unroll
-				for (int w = 0; w < 8; ++w) { const uint32_t c = s_cnt[w * Z + z]; s_cnt[w * Z + z] = b; b += c; }
-				run += tot[q];
-			}
-		}
-		if (threadIdx.x == 255) s_toff[Z] = run; // the last thread's running sum is the tile's total
-		__syncthreads();
-		for (uint32_t j = 0; j < ztile / 256; ++j) {
-			const uint64_t W = tile * ztile + j * 256 + threadIdx.x;
-			zone_roll<LONGK, 1>(w2, wm, W, W < nwords, k, Pmask, own, zshift, wc, my_ev, [&](int r, uint64_t v, uint32_t, uint32_t i) {
-				s_stage_ev[i] = v; s_stage_pos[i] = (uint32_t)(W * 32 + r);
-			});
-		}
-		__syncthreads();
-		const uint32_t T = s_toff[Z];
-		for (uint32_t i = threadIdx.x; i < T; i += 256) {
-			const uint64_t v = s_stage_ev[i];
-			const uint32_t pos = s_stage_pos[i], z = ((uint32_t)v & Pmask) >> zshift;
-			const uint32_t li = s_goff[z] + (i - s_toff[z]);
-			if (li < zcap) { zev[(uint64_t)z * zcap + li] = v; zpos[(uint64_t)z * zcap + li] = pos; }
-			else { const uint32_t q = atomicAdd(n_spill, 1u); spill_ev[q] = v; spill_pos[q] = pos; }
-		}
-		__syncthreads();
-	}
-#pragma unroll
-	for (int d = 16; d; d >>= 1) my_ev += __shfl_xor_sync(0xffffffffu, my_ev, d);
-	if (lane == 0 && my_ev) atomicAdd(&stats[0], (unsigned long long)my_ev);
-}
-
 //      zone_probe: persistent CTAs take slices of 2048 events from a global work counter, in zone order, so
 //      at any moment the whole grid works on one or two zones.  Per event the same bucket probe + counter
 //      CAS as k1_fused; a miss sets the position's bit in flags[] (pass 1).  n_list = Z zone lists of zcap
@@ -669,11 +512,11 @@ __global__ void __launch_bounds__(256) k1_array(const uint64_t *__restrict__ ev,
 
 __global__ void __launch_bounds__(256) compact_array(const uint64_t *__restrict__ ev, uint64_t nwords,
                                                      const uint32_t *__restrict__ flags, const uint32_t *__restrict__ tileoff,
-                                                     uint64_t *__restrict__ pv, uint32_t *__restrict__ ppos)
+                                                     uint64_t tile0, uint32_t off0, uint64_t *__restrict__ pv, uint32_t *__restrict__ ppos)
 {
-	const uint64_t W = blockIdx.x * 256ull + threadIdx.x;
+	const uint64_t W = (tile0 + blockIdx.x) * 256ull + threadIdx.x;
 	uint32_t f = W < nwords ? flags[W] : 0;
-	uint32_t o = tileoff[blockIdx.x] + block_excl_scan_256(__popc(f), nullptr);
+	uint32_t o = tileoff[tile0 + blockIdx.x] - off0 + block_excl_scan_256(__popc(f), nullptr);
 	while (f) {
 		int r = __ffs(f) - 1;
 		f &= f - 1;
@@ -1373,6 +1216,10 @@ void Engine::grow(uint32_t new_cap)
 {
 	uint64_t *ns = nullptr;
 	const uint64_t total_new = (uint64_t)P * new_cap;
+	if (total_new * 8 >= (4ull << 30)) { // old + new table live side by side: the partition lists (dead here) make room
+		YAKB_CUDA(cudaStreamSynchronize(stream));
+		b_zev.release(); b_zpos.release(); b_zsp.release(); b_zspp.release();
+	}
 	ns = (uint64_t*)dev_alloc(total_new * 8);
 	YAKB_CUDA(cudaMemsetAsync(ns, 0xFF, total_new * 8, stream));
 	if (slots && cap) {
@@ -1409,6 +1256,7 @@ ChunkStats Engine::count_ascii(const uint8_t *d_asc, uint64_t n, int create_new)
 	uint32_t *wm = b_wm.as<uint32_t>(packed_words(nwords)) + YAKB_PADW;
 	{ ProfScope ps("pack_ascii", stream);
 	pack_ascii_kernel<<<cdiv(packed_npad(nwords) + YAKB_PADW, 256), 256, 0, stream>>>(d_asc, n, w2, wm, nwords, packed_npad(nwords)); }
+	Prof::units("pack_ascii", n);
 	YAKB_CUDA(cudaGetLastError());
 	note_launch(1);
 	return finish_chunk(nwords, create_new, w2, wm, nullptr, n, -1);
@@ -1420,6 +1268,177 @@ ChunkStats Engine::count_events(const uint64_t *d_ev, uint64_t n, int create_new
 	if (n == 0) return st;
 	if (n >= 0x7FFFFF00ull) throw CudaError("[yakb] chunk too large (positions are 31-bit)");
 	return finish_chunk((n + 31) / 32, create_new, nullptr, nullptr, d_ev, n, only_s, ignore_bloom);
+}
+
+// ---- stage 1 of a chunk, partitioned (count.c:17-26): every event is written to the list of its zone (part_scatter),
+//      then the table is probed zone by zone (zone_probe).  Returns false - having touched neither the table nor flags -
+//      when the lists overflowed (heavily repeated k-mers): the caller then probes unpartitioned.
+bool Engine::probe_partitioned(uint64_t nwords, int create_new, const uint64_t *w2, const uint32_t *wm, const uint64_t *d_ev, uint64_t n_units,
+                               int only_s, uint32_t *flags, uint32_t *tilecnt, uint32_t *lput, unsigned long long *stats, int nsm)
+{
+	if (cap == 0) return false;
+	// YAKB_ZONE: 0 = never, 1 = always (tests), unset / 2 = when it pays: a table far beyond L2 and a chunk large enough
+	// that the scatter's fixed costs (Z reservations per tile) are amortised.  YAKB_ZONE_MB = size of a zone's table slice.
+	static const int zmode = getenv("YAKB_ZONE") ? atoi(getenv("YAKB_ZONE")) : 2;
+	static const double zmb = getenv("YAKB_ZONE_MB") ? atof(getenv("YAKB_ZONE_MB")) : 64.0;
+	static const uint64_t zmin_pos = getenv("YAKB_ZONE_MIN_POS") ? (uint64_t)atoll(getenv("YAKB_ZONE_MIN_POS")) : (32ull << 20);
+	const uint64_t n_pos = d_ev ? n_units : nwords * 32;
+	const double table_bytes = (double)P * cap * 8;
+	if (zmode == 0 || (zmode != 1 && (table_bytes < 2e9 || n_pos < zmin_pos))) return false;
+	int zshift = 0;
+	while ((1 << zshift) < P && (double)cap * 8 * (2 << zshift) <= zmb * 1048576.0) ++zshift;
+	uint32_t Z = (uint32_t)P >> zshift;
+	while (Z > 2048) { ++zshift; Z >>= 1; } // the reserve step of part_scatter gives a thread at most 8 zones
+	if (Z < 2) return false;
+	// list capacity: the events this chunk is expected to hold (positions x the events-per-position ratio of the chunks
+	// before it; 1 until one was seen), spread evenly, plus 12.5 % and a constant; the rest spills
+	static const uint64_t zslack = getenv("YAKB_ZONE_SLACK") ? (uint64_t)atoll(getenv("YAKB_ZONE_SLACK")) : 2048; // test knob: 0 forces spills
+	const double ratio = d_ev ? 1.0 : ev_ratio;
+	const uint64_t est = (uint64_t)((double)n_pos * ratio) + 1;
+	const uint32_t zcap = (uint32_t)std::min<uint64_t>(n_pos, est / Z + est / Z / 8 + zslack);
+	const uint32_t spill_cap = (uint32_t)std::min<uint64_t>(n_pos, est / 16 + 65536);
+	uint64_t *zev = b_zev.as<uint64_t>((uint64_t)Z * zcap), *sp_ev = b_zsp.as<uint64_t>(spill_cap);
+	uint32_t *zpos = b_zpos.as<uint32_t>((uint64_t)Z * zcap), *sp_pos = b_zspp.as<uint32_t>(spill_cap);
+	unsigned int *zfill = b_zfill.as<unsigned int>(Z + 4); // [Z] fills, n_spill, work, work2
+	YAKB_CUDA(cudaMemsetAsync(zfill, 0, (Z + 4) * 4, stream));
+	const size_t sms = part_smem_bytes(Z);
+	const uint64_t ntiles = (nwords + 255) / 256;
+	const uint32_t grids = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)nsm * std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (sms + 1024))));
+	const bool longk = k >= 32;
+	{ ProfScope ps("part_scatter", stream);
+	if (d_ev) {
+		set_smem(part_scatter<false, true>, sms);
+		part_scatter<false, true><<<grids, 256, sms, stream>>>(nullptr, nullptr, nwords, k, d_ev, n_units, only_s, P - 1, own(), zshift, Z, zcap, zfill,
+		                                                        zev, zpos, sp_ev, sp_pos, zfill + Z, spill_cap, stats);
+	} else if (longk) {
+		set_smem(part_scatter<true, false>, sms);
+		part_scatter<true, false><<<grids, 256, sms, stream>>>(w2, wm, nwords, k, nullptr, 0, -1, P - 1, own(), zshift, Z, zcap, zfill,
+		                                                        zev, zpos, sp_ev, sp_pos, zfill + Z, spill_cap, stats);
+	} else {
+		set_smem(part_scatter<false, false>, sms);
+		part_scatter<false, false><<<grids, 256, sms, stream>>>(w2, wm, nwords, k, nullptr, 0, -1, P - 1, own(), zshift, Z, zcap, zfill,
+		                                                         zev, zpos, sp_ev, sp_pos, zfill + Z, spill_cap, stats);
+	} }
+	YAKB_CUDA(cudaGetLastError());
+	note_launch(1);
+	unsigned int n_spill = 0;
+	YAKB_CUDA(cudaMemcpyAsync(&n_spill, zfill + Z, 4, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+	if (n_spill > spill_cap) { // events were dropped: start over without the partition (nothing but stats[0] was written)
+		YAKB_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned long long), stream));
+		return false;
+	}
+	const int smem1 = create_new && smem_lp_ok(P, 1);
+	const size_t sm1 = smem1 ? (size_t)P * 4 : 0;
+	if (create_new) YAKB_CUDA(cudaMemsetAsync(flags, 0, nwords * 4, stream));
+	{ ProfScope ps("zone_probe", stream);
+	set_smem(zone_probe, sm1);
+	zone_probe<<<nsm * 3, 256, sm1, stream>>>(zev, zpos, Z, zcap, zfill, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 1);
+	// the spill list: one more list whose fill count is n_spill
+	if (n_spill) zone_probe<<<nsm * 3, 256, sm1, stream>>>(sp_ev, sp_pos, 1, spill_cap, zfill + Z, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 2);
+	if (create_new) flag_tilecnt_kernel<<<(uint32_t)ntiles, 256, 0, stream>>>(flags, nwords, tilecnt); }
+	YAKB_CUDA(cudaGetLastError());
+	note_launch(1 + (n_spill ? 1 : 0) + (create_new ? 1 : 0));
+	return true;
+}
+
+// ---- stage 2 of a pass-1 chunk for the pending events of tiles [t0, t1) (n_pending of them, the first at index off0 of
+//      the chunk's pending order): file-order list -> stable sort by group -> group_insert -> bookkeeping -> journal segment.
+//      Returns the number of new keys.  Pending events see the table as the ranges before them left it, so cutting a chunk
+//      into ranges changes nothing; it bounds the scratch memory of a large chunk in the filling phase.
+uint64_t Engine::pending_range(uint64_t t0, uint64_t t1, uint32_t off0, uint32_t n_pending, uint64_t nwords, const uint64_t *w2, const uint32_t *wm,
+                               const uint64_t *d_ev, const uint32_t *flags, const uint32_t *tileoff, uint32_t *lput, uint32_t *lnew,
+                               unsigned long long *stats, uint8_t *bloom, int nsm)
+{
+	if (n_pending == 0) return 0;
+	const uint32_t Pmask = P - 1;
+	const bool longk = k >= 32;
+	uint64_t *pv = b_pv.as<uint64_t>(n_pending);
+	uint32_t *ppos = b_ppos.as<uint32_t>(n_pending);
+	{ ProfScope ps("compact", stream);
+	if (d_ev == nullptr) {
+		if (longk) compact_fused<true><<<(uint32_t)(t1 - t0), 256, 0, stream>>>(w2, wm, nwords, k, flags, tileoff, t0, off0, pv, ppos);
+		else compact_fused<false><<<(uint32_t)(t1 - t0), 256, 0, stream>>>(w2, wm, nwords, k, flags, tileoff, t0, off0, pv, ppos);
+	} else compact_array<<<(uint32_t)(t1 - t0), 256, 0, stream>>>(d_ev, nwords, flags, tileoff, t0, off0, pv, ppos);
+	}
+	YAKB_CUDA(cudaGetLastError());
+	// make room: every pending event may be a new key of its sub-table
+	const int smem1h = smem_lp_ok(P, 1);
+	const size_t sm1h = smem1h ? (size_t)P * 4 : 0;
+	uint32_t *pend = b_pend.as<uint32_t>(P + 1);
+	YAKB_CUDA(cudaMemsetAsync(pend, 0, (P + 1) * 4, stream));
+	{ ProfScope ps("pend_hist", stream);
+	set_smem(pend_hist_kernel, sm1h);
+	pend_hist_kernel<<<std::min<uint32_t>(cdiv(n_pending, 256), nsm * 4), 256, sm1h, stream>>>(pv, n_pending, Pmask, pend, smem1h);
+	max_need_kernel<<<1, 1024, 0, stream>>>(nkeys, pend, P, pend + P); }
+	uint32_t need = 0;
+	YAKB_CUDA(cudaMemcpyAsync(&need, pend + P, 4, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+	if ((double)need > load_limit * cap) {
+		uint64_t want = (std::max<uint64_t>((uint64_t)(need / load_limit) + 16, (uint64_t)cap * 2) + 3) & ~3ull;
+		if (want > 0xFFFFFFF0ull) throw CudaError("[yakb] sub-table capacity overflow");
+		ProfScope ps("grow", stream);
+		grow((uint32_t)want);
+	}
+	// group key: the bloom block (bbf.c:27-28: low n_shift-9 bits of the hash, sub-table included)
+	// or, without a filter, enough low hash bits to keep groups short
+	int G;
+	const int vbits = longk ? 64 : 2 * k;
+	if (bloom) G = n_shift - 9;
+	else { G = pre; while (G < vbits && (1ull << G) < (uint64_t)n_pending / 2) ++G; }
+	if (G > vbits) G = vbits;
+	uint64_t *sv = b_sv.as<uint64_t>(n_pending), *sv2 = b_sv2.as<uint64_t>(n_pending);
+	uint32_t *sj = b_sj.as<uint32_t>(n_pending), *sj2 = b_sj2.as<uint32_t>(n_pending);
+	{ ProfScope ps("group_sort", stream);
+	if (radix_sort_pairs(pv, nullptr, sv, sj, sv2, sj2, n_pending, 0, G, stream, rs)) { sv = sv2; sj = sj2; } }
+	uint8_t *pflag = b_pflag.as<uint8_t>(2 * (size_t)n_pending); // [0,n): put/new bits, [n,2n): new-key flag
+	{ ProfScope ps("group_insert", stream);
+	group_insert<<<cdiv(n_pending, 256), 256, 0, stream>>>(sv, sj, n_pending, G, pre, Pmask, lw, slots, cap,
+	                                                       (uint32_t*)bloom, nb, n_shift - pre, n_hash, pflag); }
+	YAKB_CUDA(cudaGetLastError());
+	const int smem2 = smem_lp_ok(P, 2);
+	const size_t sm2 = smem2 ? (size_t)P * 8 : 0;
+	set_smem(post_pending, sm2);
+	{ ProfScope ps("post_pending", stream);
+	post_pending<<<std::min<uint32_t>(cdiv(n_pending, 256), nsm * 4), 256, sm2, stream>>>(pv, ppos, pflag, n_pending, Pmask, lput, lnew, smem2, stats); }
+	YAKB_CUDA(cudaGetLastError());
+	note_launch(5); // compact, pend_hist, max_need, group_insert, post_pending
+	// new keys in file order, then stably by sub-table -> journal segment
+	uint64_t *newv = b_newv.as<uint64_t>(n_pending);
+	uint32_t *d_nsel = (uint32_t*)(stats + 2);
+	const uint8_t *isnew = pflag + n_pending; // written by post_pending
+	{ ProfScope ps("journal(compact)", stream);
+	compact_flagged_u64(pv, isnew, n_pending, newv, d_nsel, stream, rs); }
+	uint32_t n_new = 0;
+	YAKB_CUDA(cudaMemcpyAsync(&n_new, d_nsel, 4, cudaMemcpyDeviceToHost, stream));
+	YAKB_CUDA(cudaStreamSynchronize(stream));
+	if (n_new) {
+		// stable by sub-table (the low pre-lw bits): newv is in file order, so each run is in first-put order
+		uint64_t *sorted = b_newsorted.as<uint64_t>(n_new), *sorted2 = b_sv.as<uint64_t>(n_new);
+		Segment seg;
+		seg.n = n_new;
+		seg.keys = (uint64_t*)journal_alloc((uint64_t)n_new * 8);
+		seg.off = (uint64_t*)journal_alloc((uint64_t)(P + 1) * 8);
+		ProfScope ps("journal(sort+seg)", stream);
+		if (radix_sort_pairs(newv, nullptr, sorted, nullptr, sorted2, nullptr, n_new, 0, pre - lw, stream, rs)) sorted = sorted2;
+		seg_offsets_kernel<<<cdiv(P + 1, 256), 256, 0, stream>>>(sorted, n_new, Pmask, seg.off, nkeys);
+		seg_addkeys_kernel<<<cdiv(P, 256), 256, 0, stream>>>(seg.off, P, nkeys);
+		seg_keys_kernel<<<cdiv(n_new, 256), 256, 0, stream>>>(sorted, n_new, pre, seg.keys);
+		YAKB_CUDA(cudaGetLastError());
+		journal.push_back(seg);
+		note_launch(3);
+	}
+	return n_new;
+}
+
+// work items per kernel name of one chunk, for the roofline accounting of bench.py (SURVEY 8(d) bytes are per event)
+static void note_units(bool parted, bool array, const ChunkStats &st)
+{
+	if (!Prof::on()) return;
+	if (parted) { Prof::units("part_scatter", st.n_events); Prof::units("zone_probe", st.n_events); }
+	else Prof::units(array ? "k1_array" : "k1_fused", st.n_events);
+	for (const char *nm : {"compact", "pend_hist", "group_sort", "group_insert", "post_pending", "journal(compact)"}) Prof::units(nm, st.n_pending);
+	Prof::units("journal(sort+seg)", st.n_new);
 }
 
 // common tail of both front ends.  n_units: #bases (ASCII) or #events (array front end)
@@ -1446,100 +1465,40 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 	int dev = 0, nsm = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-	const int smem1 = create_new && smem_lp_ok(P, 1);
-	const size_t sm1 = smem1 ? (size_t)P * 4 : 0;
-	const uint32_t grid1 = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)nsm * 4);
-	// zone-blocked probing, EXPERIMENTAL and off unless YAKB_ZONE is set (1 = always, 2 = for tables >= 2 GB;
-	// YAKB_ZONE_MB = zone size, default 128).  Measured on cfg2 (profiles/r01_zone_blocking.md): the probe itself
-	// gets 1.6x faster at 240 M events per chunk, but the scatter that feeds it costs as much as it saves - its
-	// per-event 8-byte stores are bound by L2 write transactions (~38 G/s), not bytes - so k1_fused stays the default.
-	int zshift = 0;
-	uint32_t Z = 0;
-	if (d_ev == nullptr && cap) {
-		static const int zmode = getenv("YAKB_ZONE") ? atoi(getenv("YAKB_ZONE")) : 0;
-		static const double zmb = getenv("YAKB_ZONE_MB") ? atof(getenv("YAKB_ZONE_MB")) : 128.0;
-		const double table_bytes = (double)P * cap * 8;
-		if (zmode == 1 || (zmode == 2 && table_bytes >= 2e9)) {
-			while ((1 << zshift) < P && (double)cap * 8 * (2 << zshift) <= zmb * 1048576.0) ++zshift;
-			Z = (uint32_t)P >> zshift;
-			while (Z > 2048) { ++zshift; Z >>= 1; } // 8 warps x Z counters must fit shared memory
-			if (Z < 2) Z = 0;
-		}
-	}
-	if (Z) {
-		const uint64_t n_pos = nwords * 32;
-		static const uint64_t zslack = getenv("YAKB_ZONE_SLACK") ? (uint64_t)atoll(getenv("YAKB_ZONE_SLACK")) : 4096; // test knob: 0 forces spills
-		const uint32_t zcap = (uint32_t)std::min<uint64_t>(n_pos, n_pos / Z + n_pos / Z / 4 + zslack);
-		uint64_t *zev = b_zev.as<uint64_t>((uint64_t)Z * zcap), *sp_ev = b_zsp.as<uint64_t>(n_pos);
-		uint32_t *zpos = b_zpos.as<uint32_t>((uint64_t)Z * zcap), *sp_pos = b_zspp.as<uint32_t>(n_pos);
-		unsigned int *zfill = b_zfill.as<unsigned int>(Z + 4); // [Z] fills, n_spill, work, work2
-		YAKB_CUDA(cudaMemsetAsync(zfill, 0, (Z + 4) * 4, stream));
-		if (create_new) YAKB_CUDA(cudaMemsetAsync(flags, 0, nwords * 4, stream));
-		const size_t smz = (size_t)Z * 8 * 4;
-		// events in flight between a tile's reservation and its last store must stay well inside L2, or half-written
-		// sectors of the zone lists are evicted and written twice: small tiles, few CTAs
-		static const uint32_t ztile = getenv("YAKB_ZTILE_WORDS") ? (uint32_t)atoi(getenv("YAKB_ZTILE_WORDS")) / 256 * 256 : 1024;
-		static const int zgrid = getenv("YAKB_ZGRID") ? atoi(getenv("YAKB_ZGRID")) : 4;
-		const uint64_t nzt = (nwords + ztile - 1) / ztile;
-		const uint32_t gridz = (uint32_t)std::min<uint64_t>(nzt, (uint64_t)nsm * zgrid);
-		// YAKB_ZONE_STAGED=1: the shared-memory staged scatter (zone_scatter_staged); tiles of YAKB_ZTILE_WORDS (default 256) words
-		static const int zstaged = getenv("YAKB_ZONE_STAGED") ? atoi(getenv("YAKB_ZONE_STAGED")) : 0;
-		const uint32_t stile = getenv("YAKB_ZTILE_WORDS") ? std::max(256u, ztile) : 256u;
-		const size_t sms = (size_t)stile * 32 * 12 + ((size_t)Z * 10 + 1) * 4;
-		if (zstaged && sms <= 200 * 1024) {
-			ProfScope ps("zone_scatter", stream);
-			const uint32_t grids = (uint32_t)std::min<uint64_t>((nwords + stile - 1) / stile, (uint64_t)nsm * std::max<size_t>(1, (220 * 1024) / (sms + 1024)));
+	// ---- stage 1: every event meets the table (hit: counter++; miss: the position is flagged pending)
+	const bool parted = probe_partitioned(nwords, create_new, w2, wm, d_ev, n_units, only_s, flags, tilecnt, lput, stats, nsm);
+	if (!parted) {
+		const int smem1 = create_new && smem_lp_ok(P, 1);
+		const size_t sm1 = smem1 ? (size_t)P * 4 : 0;
+		const uint32_t grid1 = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)nsm * 4);
+		ProfScope ps(d_ev ? "k1_array" : "k1_fused", stream);
+		if (d_ev == nullptr) {
 			if (longk) {
-				set_smem(zone_scatter_staged<true>, sms);
-				zone_scatter_staged<true><<<grids, 256, sms, stream>>>(w2, wm, nwords, k, stile, Pmask, own(), zshift, Z, zcap, zfill, zev, zpos, sp_ev, sp_pos, zfill + Z, stats);
+				set_smem(k1_fused<true>, sm1);
+				k1_fused<true><<<grid1, 256, sm1, stream>>>(w2, wm, nwords, k, pre, Pmask, own(), slots, cap, create_new, flags, tilecnt, lput, smem1, stats);
 			} else {
-				set_smem(zone_scatter_staged<false>, sms);
-				zone_scatter_staged<false><<<grids, 256, sms, stream>>>(w2, wm, nwords, k, stile, Pmask, own(), zshift, Z, zcap, zfill, zev, zpos, sp_ev, sp_pos, zfill + Z, stats);
+				set_smem(k1_fused<false>, sm1);
+				k1_fused<false><<<grid1, 256, sm1, stream>>>(w2, wm, nwords, k, pre, Pmask, own(), slots, cap, create_new, flags, tilecnt, lput, smem1, stats);
 			}
-		} else
-		{ ProfScope ps("zone_scatter", stream);
-		if (longk) {
-			set_smem(zone_scatter<true>, smz);
-			zone_scatter<true><<<gridz, 256, smz, stream>>>(w2, wm, nwords, k, ztile, Pmask, own(), zshift, Z, zcap, zfill, zev, zpos, sp_ev, sp_pos, zfill + Z, stats);
 		} else {
-			set_smem(zone_scatter<false>, smz);
-			zone_scatter<false><<<gridz, 256, smz, stream>>>(w2, wm, nwords, k, ztile, Pmask, own(), zshift, Z, zcap, zfill, zev, zpos, sp_ev, sp_pos, zfill + Z, stats);
-		} }
-		{ ProfScope ps("zone_probe", stream);
-		set_smem(zone_probe, sm1);
-		zone_probe<<<nsm * 3, 256, sm1, stream>>>(zev, zpos, Z, zcap, zfill, pre, Pmask, slots, cap, create_new, flags, lput, smem1, zfill + Z + 1);
-		// the spill list: one more list whose fill count is n_spill (normally 0: its slices are all empty)
-		zone_probe<<<nsm * 3, 256, sm1, stream>>>(sp_ev, sp_pos, 1, (uint32_t)std::min<uint64_t>(n_pos, 0xFFFFFFFFu), zfill + Z, pre, Pmask, slots, cap, create_new, flags, lput, smem1, zfill + Z + 2);
-		if (create_new) flag_tilecnt_kernel<<<(uint32_t)ntiles, 256, 0, stream>>>(flags, nwords, tilecnt); }
-		YAKB_CUDA(cudaGetLastError());
-		note_launch(create_new ? 3 : 2);
-	} else
-	{ ProfScope ps(d_ev ? "k1_array" : "k1_fused", stream);
-	if (d_ev == nullptr) {
-		if (longk) {
-			set_smem(k1_fused<true>, sm1);
-			k1_fused<true><<<grid1, 256, sm1, stream>>>(w2, wm, nwords, k, pre, Pmask, own(), slots, cap, create_new, flags, tilecnt, lput, smem1, stats);
-		} else {
-			set_smem(k1_fused<false>, sm1);
-			k1_fused<false><<<grid1, 256, sm1, stream>>>(w2, wm, nwords, k, pre, Pmask, own(), slots, cap, create_new, flags, tilecnt, lput, smem1, stats);
+			set_smem(k1_array, sm1);
+			k1_array<<<grid1, 256, sm1, stream>>>(d_ev, n_ev_in, pre, Pmask, own(), slots, cap, create_new, only_s, flags, tilecnt, lput, smem1, stats);
 		}
-	} else {
-		set_smem(k1_array, sm1);
-		k1_array<<<grid1, 256, sm1, stream>>>(d_ev, n_ev_in, pre, Pmask, own(), slots, cap, create_new, only_s, flags, tilecnt, lput, smem1, stats);
+		YAKB_CUDA(cudaGetLastError());
+		note_launch(1);
 	}
-	}
-	YAKB_CUDA(cudaGetLastError());
-	note_launch(1); // k1
 	unsigned long long h_stats[4] = {0, 0, 0, 0};
 	if (!create_new) {
 		YAKB_CUDA(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
 		YAKB_CUDA(cudaStreamSynchronize(stream));
 		Prof::resolve();
 		st.n_events = h_stats[0];
+		note_ratio(st.n_events, d_ev ? 0 : nwords * 32);
+		note_units(parted, d_ev != nullptr, st);
 		++chunk_seq;
 		return st;
 	}
-	// pending list in file order
+	// ---- stage 2: the pending events in file order, in ranges of tiles of about pend_max events
 	exclusive_scan_u32(tilecnt, tileoff, ntiles + 1, stream, rs);
 	uint32_t n_pending = 0;
 	YAKB_CUDA(cudaMemcpyAsync(&n_pending, tileoff + ntiles, 4, cudaMemcpyDeviceToHost, stream));
@@ -1547,84 +1506,20 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 	st.n_pending = n_pending;
 	uint64_t n_new = 0;
 	if (n_pending) {
-		uint64_t *pv = b_pv.as<uint64_t>(n_pending);
-		uint32_t *ppos = b_ppos.as<uint32_t>(n_pending);
-		{ ProfScope ps("compact", stream);
-		if (d_ev == nullptr) {
-			if (longk) compact_fused<true><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, flags, tileoff, pv, ppos);
-			else compact_fused<false><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, flags, tileoff, pv, ppos);
-		} else compact_array<<<(uint32_t)ntiles, 256, 0, stream>>>(d_ev, nwords, flags, tileoff, pv, ppos);
+		static const uint64_t pend_max = getenv("YAKB_PEND_MAX") ? (uint64_t)atoll(getenv("YAKB_PEND_MAX")) : (256ull << 20);
+		const uint64_t nsub = std::min<uint64_t>(ntiles, (n_pending + pend_max - 1) / pend_max);
+		std::vector<uint64_t> tb(nsub + 1);
+		std::vector<uint32_t> to(nsub + 1, 0);
+		for (uint64_t i = 0; i <= nsub; ++i) tb[i] = ntiles * i / nsub;
+		to[nsub] = n_pending;
+		if (nsub > 1) {
+			for (uint64_t i = 1; i < nsub; ++i) YAKB_CUDA(cudaMemcpyAsync(&to[i], tileoff + tb[i], 4, cudaMemcpyDeviceToHost, stream));
+			YAKB_CUDA(cudaStreamSynchronize(stream));
 		}
-		YAKB_CUDA(cudaGetLastError());
-		// make room: every pending event may be a new key of its sub-table
-		const int smem1h = smem_lp_ok(P, 1);
-		const size_t sm1h = smem1h ? (size_t)P * 4 : 0;
-		uint32_t *pend = b_pend.as<uint32_t>(P + 1);
-		YAKB_CUDA(cudaMemsetAsync(pend, 0, (P + 1) * 4, stream));
-		{ ProfScope ps("pend_hist", stream);
-		set_smem(pend_hist_kernel, sm1h);
-		pend_hist_kernel<<<std::min<uint32_t>(cdiv(n_pending, 256), nsm * 4), 256, sm1h, stream>>>(pv, n_pending, Pmask, pend, smem1h);
-		max_need_kernel<<<1, 1024, 0, stream>>>(nkeys, pend, P, pend + P); }
-		uint32_t need = 0;
-		YAKB_CUDA(cudaMemcpyAsync(&need, pend + P, 4, cudaMemcpyDeviceToHost, stream));
-		YAKB_CUDA(cudaStreamSynchronize(stream));
-		if ((double)need > load_limit * cap) {
-			uint64_t want = (std::max<uint64_t>((uint64_t)(need / load_limit) + 16, (uint64_t)cap * 2) + 3) & ~3ull;
-			if (want > 0xFFFFFFF0ull) throw CudaError("[yakb] sub-table capacity overflow");
-			grow((uint32_t)want);
-		}
-		// group key: the bloom block (bbf.c:27-28: low n_shift-9 bits of the hash, sub-table included)
-		// or, without a filter, enough low hash bits to keep groups short
-		int G;
-		const int vbits = longk ? 64 : 2 * k;
-		if (bloom) G = n_shift - 9;
-		else { G = pre; while (G < vbits && (1ull << G) < (uint64_t)n_pending / 2) ++G; }
-		if (G > vbits) G = vbits;
-		uint64_t *sv = b_sv.as<uint64_t>(n_pending), *sv2 = b_sv2.as<uint64_t>(n_pending);
-		uint32_t *sj = b_sj.as<uint32_t>(n_pending), *sj2 = b_sj2.as<uint32_t>(n_pending);
-		{ ProfScope ps("group_sort", stream);
-		if (radix_sort_pairs(pv, nullptr, sv, sj, sv2, sj2, n_pending, 0, G, stream, rs)) { sv = sv2; sj = sj2; } }
-		uint8_t *pflag = b_pflag.as<uint8_t>(2 * (size_t)n_pending); // [0,n): put/new bits, [n,2n): new-key flag
-		{ ProfScope ps("group_insert", stream);
-		group_insert<<<cdiv(n_pending, 256), 256, 0, stream>>>(sv, sj, n_pending, G, pre, Pmask, lw, slots, cap,
-		                                                       (uint32_t*)bloom, nb, n_shift - pre, n_hash, pflag); }
-		YAKB_CUDA(cudaGetLastError());
-		const int smem2 = smem_lp_ok(P, 2);
-		const size_t sm2 = smem2 ? (size_t)P * 8 : 0;
-		set_smem(post_pending, sm2);
-		{ ProfScope ps("post_pending", stream);
-		post_pending<<<std::min<uint32_t>(cdiv(n_pending, 256), nsm * 4), 256, sm2, stream>>>(pv, ppos, pflag, n_pending, Pmask, lput, lnew, smem2, stats); }
-		YAKB_CUDA(cudaGetLastError());
-		note_launch(5); // compact, pend_hist, max_need, group_insert, post_pending
-		// new keys in file order, then stably by sub-table -> journal segment
-		uint64_t *newv = b_newv.as<uint64_t>(n_pending);
-		uint32_t *d_nsel = (uint32_t*)(stats + 2);
-		const uint8_t *isnew = pflag + n_pending; // written by post_pending
-		{ ProfScope ps("journal(compact)", stream);
-		compact_flagged_u64(pv, isnew, n_pending, newv, d_nsel, stream, rs); }
-		YAKB_CUDA(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
-		YAKB_CUDA(cudaStreamSynchronize(stream));
-		n_new = (uint32_t)h_stats[2];
-		if (n_new) {
-			// stable by sub-table (the low pre-lw bits): newv is in file order, so each run is in first-put order
-			uint64_t *sorted = b_newsorted.as<uint64_t>(n_new), *sorted2 = b_sv.as<uint64_t>(n_new);
-			ProfScope ps("journal(sort+seg)", stream);
-			if (radix_sort_pairs(newv, nullptr, sorted, nullptr, sorted2, nullptr, n_new, 0, pre - lw, stream, rs)) sorted = sorted2;
-			Segment seg;
-			seg.n = n_new;
-			seg.keys = (uint64_t*)journal_alloc(n_new * 8);
-			seg.off = (uint64_t*)journal_alloc((uint64_t)(P + 1) * 8);
-			seg_offsets_kernel<<<cdiv(P + 1, 256), 256, 0, stream>>>(sorted, n_new, Pmask, seg.off, nkeys);
-			seg_addkeys_kernel<<<cdiv(P, 256), 256, 0, stream>>>(seg.off, P, nkeys);
-			seg_keys_kernel<<<cdiv(n_new, 256), 256, 0, stream>>>(sorted, n_new, pre, seg.keys);
-			YAKB_CUDA(cudaGetLastError());
-			journal.push_back(seg);
-			note_launch(3);
-		}
-	} else {
-		YAKB_CUDA(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
-		YAKB_CUDA(cudaStreamSynchronize(stream));
+		for (uint64_t i = 0; i < nsub; ++i)
+			n_new += pending_range(tb[i], tb[i + 1], to[i], to[i + 1] - to[i], nwords, w2, wm, d_ev, flags, tileoff, lput, lnew, stats, bloom, nsm);
 	}
+	YAKB_CUDA(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
 	merge_times_kernel<<<cdiv(P, 256), 256, 0, stream>>>(P, chunk_seq, lput, lnew, last_put, last_new);
 	YAKB_CUDA(cudaGetLastError());
 	note_launch(1);
@@ -1634,6 +1529,8 @@ ChunkStats Engine::finish_chunk(uint64_t nwords, int create_new, const uint64_t 
 	st.n_put = h_stats[1] + (st.n_events - st.n_pending);
 	st.n_new = n_new;
 	tot += n_new;
+	note_ratio(st.n_events, d_ev ? 0 : nwords * 32);
+	note_units(parted, d_ev != nullptr, st);
 	++chunk_seq;
 	return st;
 }

@@ -18,6 +18,7 @@
 #include <vector>
 #include <string>
 #include <stdexcept>
+#include <algorithm>
 #include <cuda_runtime.h>
 #include "dbuf.cuh"
 #include "radix.cuh"
@@ -31,8 +32,9 @@ struct Prof {
 	static void reset();
 	static void begin(const char *name, cudaStream_t s);
 	static void end(cudaStream_t s);
+	static void units(const char *name, uint64_t n);   // work items processed under this name (events, positions)
 	static void resolve();                       // call after the stream was synchronised
-	static std::string json();                   // {"name": [total_ms, launches], ...}
+	static std::string json();                   // {"name": [total_ms, launches, units], ...}
 };
 struct ProfScope {
 	cudaStream_t s; bool live;
@@ -129,6 +131,14 @@ struct Engine {
 private:
 	ChunkStats finish_chunk(uint64_t n_words, int create_new, const uint64_t *w2, const uint32_t *wm,
 	                        const uint64_t *d_ev, uint64_t n_units, int only_s, bool ignore_bloom = false);
+	bool probe_partitioned(uint64_t nwords, int create_new, const uint64_t *w2, const uint32_t *wm, const uint64_t *d_ev, uint64_t n_units,
+	                       int only_s, uint32_t *flags, uint32_t *tilecnt, uint32_t *lput, unsigned long long *stats, int nsm);
+	uint64_t pending_range(uint64_t t0, uint64_t t1, uint32_t off0, uint32_t n_pending, uint64_t nwords, const uint64_t *w2, const uint32_t *wm,
+	                       const uint64_t *d_ev, const uint32_t *flags, const uint32_t *tileoff, uint32_t *lput, uint32_t *lnew,
+	                       unsigned long long *stats, uint8_t *bloom, int nsm);
+	// k-mer events per input position of the last large chunk (sizes the partition lists of the next one)
+	double ev_ratio = 1.0;
+	void note_ratio(uint64_t n_events, uint64_t n_pos) { if (n_pos >= (1u << 20)) ev_ratio = std::min(1.0, (double)n_events / (double)n_pos * 1.03 + 0.01); }
 	void grow(uint32_t new_cap);
 	void reset_table(const std::vector<uint64_t> &off);
 };

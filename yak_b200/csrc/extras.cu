@@ -74,8 +74,8 @@ int extract_events(const uint8_t *d_asc, uint64_t n, int k, int pre, int world, 
 	while ((1 << lw) < world) ++lw;
 	if ((1 << lw) != world || lw > pre) { fprintf(stderr, "[yakb] ERROR: world size must be a power of two <= 2^pre\n"); return -1; }
 	uint64_t *ev = lw ? sc.b[7].as<uint64_t>(n_ev) : d_out;
-	if (k >= 32) compact_fused<true><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, vmask, tileoff, ev, ppos);
-	else compact_fused<false><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, vmask, tileoff, ev, ppos);
+	if (k >= 32) compact_fused<true><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, vmask, tileoff, 0, 0, ev, ppos);
+	else compact_fused<false><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, vmask, tileoff, 0, 0, ev, ppos);
 	YAKB_CUDA(cudaGetLastError());
 	if (lw == 0) { counts[0] = n_ev; YAKB_CUDA(cudaStreamSynchronize(stream)); return 0; }
 	// owner rank = top lw bits of the sub-table index = hash bits [pre-lw, pre); one stable pass on them

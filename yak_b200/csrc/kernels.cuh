@@ -172,11 +172,12 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t *to
 template<bool LONGK>
 __global__ void __launch_bounds__(256) compact_fused(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords, int k,
                                                      const uint32_t *__restrict__ flags, const uint32_t *__restrict__ tileoff,
-                                                     uint64_t *__restrict__ pv, uint32_t *__restrict__ ppos)
+                                                     uint64_t tile0, uint32_t off0, uint64_t *__restrict__ pv, uint32_t *__restrict__ ppos)
 {
-	const uint64_t W = blockIdx.x * 256ull + threadIdx.x;
+	// tiles [tile0, tile0 + gridDim.x) of the chunk; off0 = tileoff[tile0], so the list starts at index 0
+	const uint64_t W = (tile0 + blockIdx.x) * 256ull + threadIdx.x;
 	uint32_t f = W < nwords ? flags[W] : 0;
-	uint32_t o = tileoff[blockIdx.x] + block_excl_scan_256(__popc(f), nullptr);
+	uint32_t o = tileoff[tile0 + blockIdx.x] - off0 + block_excl_scan_256(__popc(f), nullptr);
 	if (f) roll_word<LONGK>(w2, wm, W, k, [&](int r, uint64_t h) {
 		if (f >> r & 1) { pv[o] = h; ppos[o] = (uint32_t)(W * 32 + r); ++o; }
 	});
