@@ -35,6 +35,10 @@ int yakb_count_events_dev(yak_ch_t *h, const uint64_t *d_ev, uint64_t n, int cre
  * d_out must hold n entries; counts[world] (host) receives the per-rank counts. */
 int yakb_extract_route_dev(const void *d_asc, uint64_t n, int k, int pre, int world,
                            uint64_t *d_out, uint64_t *counts, void *cuda_stream);
+/* the same without waiting for the device: d_counts[world] is DEVICE memory (the caller exchanges the counts
+ * of all ranks with one collective and reads them back once); world is a power of two <= 16 */
+int yakb_extract_route_async(const void *d_asc, uint64_t n, int k, int pre, int world,
+                             uint64_t *d_out, uint64_t *d_counts, void *cuda_stream);
 
 /* Multi-GPU: one shard of a table whose 2^pre sub-tables are split over `world` (power of two)
  * GPUs; shard `rank` owns sub-tables [rank*2^pre/world, (rank+1)*2^pre/world) and ignores events
@@ -70,6 +74,12 @@ void *yakb_ch_stream(const yak_ch_t *h);
 uint64_t yakb_ch_device_bytes(const yak_ch_t *h);
 /* number of kernels this library launched so far in this process */
 uint64_t yakb_kernel_launches(void);
+/* GPUs a table lives on: 1, or the G of a table yak_count() spread over the GPUs of this process (environment YAKB_GPUS = a
+ * power of two: shard r on device r owns sub-tables [r*2^pre/G, (r+1)*2^pre/G); per batch one host thread per GPU copies its
+ * part of the reads, extracts and groups the k-mers by owner, and every GPU pulls its runs from its peers over NVLink).
+ * Such a table supports the `yak count` flow: yak_count, yak_ch_destroy_bf / clear / shrink / hist / get / insert_list /
+ * dump / destroy; the other entry points report an error. */
+int yakb_ch_gpus(const yak_ch_t *h);
 /* The library keeps device blocks of destroyed tables for the next table (csrc/dbuf.cuh; bounded by
  * YAKB_CACHE_GB, default 48): bytes held idle right now, and a call that hands them all back. */
 uint64_t yakb_device_cache_bytes(void);

@@ -47,7 +47,7 @@ class OracleBackend:
         owner = ((ev & np.uint64((1 << self.pre) - 1)) >> np.uint64(self.pre - self.lw)).astype(np.int64)
         order = np.argsort(owner, kind="stable")
         counts = np.bincount(owner, minlength=self.world).tolist()
-        return torch.from_numpy(ev[order].view(np.int64).copy()), [int(c) for c in counts]
+        return torch.from_numpy(ev[order].view(np.int64).copy()), torch.tensor([int(c) for c in counts], dtype=torch.int64)
 
     def count_events(self, ev, create_new):
         a = np.ascontiguousarray(ev.numpy().view(np.uint64))

@@ -51,8 +51,6 @@ def test_nccl_sharded_count_equals_oracle(yakb, k, pre, b, batch):
     O.lib().yo_ch_destroy(h)
 
 
-@pytest.mark.skipif(os.environ.get("YAKB_TEST_UNVERIFIED") != "1",
-                    reason="the torchrun entry point was written without GPU access (end of round 1); set YAKB_TEST_UNVERIFIED=1 to run")
 @pytest.mark.parametrize("b,compressed", [(0, False), (22, False), (20, True)])
 def test_multi_gpu_count_command_equals_oracle(yakb, b, compressed):
     """`torchrun -m yak_b200.dist count ...` on every GPU of the box (1 works too): the .yak file the ranks write side by side"""
@@ -79,3 +77,133 @@ def test_multi_gpu_count_command_equals_oracle(yakb, b, compressed):
     got = open(out, "rb").read()
     assert got == want, util.explain_diff(got, want)
     O.lib().yo_ch_destroy(h)
+
+
+@pytest.mark.parametrize("k,pre", [(31, 12), (21, 10), (47, 11), (63, 12)])
+def test_route_extraction_is_the_oracles_stable_grouping(yakb, k, pre):
+    """yakb_extract_route_dev on ONE GPU for world = 1..16 owners (csrc/extras.cu route_tile_kernel / route_gather_kernel): the
+    hashed k-mers of a read batch grouped by owner rank, file order inside a group (count.c:120,133 is what that order
+    protects) - against the oracle's event stream of the same reads"""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from yak_b200 import synth
+    L, OL = yakb.lib(), O.lib()
+    rng = np.random.default_rng(k * 100 + pre)
+    reads = synth.codes_to_ascii(synth.read_codes(5, 400_000, 9, 0, 5000, 150, 0.01, 3))
+    seqs = [bytes(r) for r in reads] + [b"ACGT" * 5, b"", b"A" * 700, bytes(rng.choice(list(b"ACGTN"), 3000).astype(np.uint8))]
+    asc = b"\n".join(seqs) + b"\n"
+    want = []
+    for s in seqs:
+        for part in s.split(b"N"):
+            if len(part) >= k:
+                buf = (C.c_uint64 * len(part))()
+                n = OL.yo_extract(k, len(part), part, buf)
+                want.append(np.frombuffer(buf, dtype=np.uint64, count=n).copy())
+    want = np.concatenate(want)
+    d_asc = torch.frombuffer(bytearray(asc), dtype=torch.uint8).cuda()
+    for world in (1, 2, 4, 8, 16):
+        lw = world.bit_length() - 1
+        out = torch.zeros(len(asc), dtype=torch.int64, device="cuda")
+        counts = (C.c_uint64 * world)()
+        torch.cuda.synchronize()
+        assert L.yakb_extract_route_dev(d_asc.data_ptr(), len(asc), k, pre, world, out.data_ptr(), counts, torch.cuda.current_stream().cuda_stream) == 0
+        owner = ((want & np.uint64((1 << pre) - 1)) >> np.uint64(pre - lw)).astype(np.int64)
+        order = np.argsort(owner, kind="stable")
+        assert [int(c) for c in counts] == np.bincount(owner, minlength=world).tolist(), world
+        got = out[:len(want)].cpu().numpy().view(np.uint64)
+        assert np.array_equal(got, want[order]), world
+    assert L.yakb_extract_route_dev(d_asc.data_ptr(), len(asc), k, pre, 32, out.data_ptr(), (C.c_uint64 * 32)(), torch.cuda.current_stream().cuda_stream) != 0
+    assert L.yakb_extract_route_dev(d_asc.data_ptr(), len(asc), k, pre, 3, out.data_ptr(), (C.c_uint64 * 3)(), torch.cuda.current_stream().cuda_stream) != 0
+
+
+def _gpus_pow2():
+    import torch
+    world = 1
+    while world * 2 <= min(torch.cuda.device_count(), 8):
+        world *= 2
+    return world
+
+
+@pytest.mark.parametrize("b,batch", [(0, "0"), (22, "70000"), (20, "1500")])
+def test_in_library_multi_gpu_count_command_equals_oracle(yakb, b, batch):
+    """`yak-b200 count -g G` (YAKB_GPUS): ONE process, one host thread per GPU, the routed k-mers pulled from the peers'
+    buffers with peer copies (csrc/capi.cu multi_batch) - the plain-C boundary on several GPUs, no Python, no torchrun.
+    Batches of 70 kB and 1.5 kB of bases cut the input into hundreds of exchanges."""
+    import subprocess
+    world = _gpus_pow2()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    fn = G.input_path("reads_q")
+    out = os.path.join(util.TMP, f"yakb_multi_cli_{b}.yak")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    if batch != "0":
+        env["YAKB_BATCH"] = batch
+    r = subprocess.run([os.path.join(root, "yak_b200", "bin", "yak-b200"), "count", "-k31", "-p12", f"-b{b}", "-g", str(world), "-K", "1000", "-o", out, fn],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert f"on {world} GPUs" in r.stderr
+    h, _ = O.count_file(fn, k=31, pre=12, bf_shift=b)
+    want = O.dump_bytes(h)
+    got = open(out, "rb").read()
+    assert got == want, util.explain_diff(got, want)
+    O.lib().yo_ch_destroy(h)
+
+
+MULTI_SNIPPET = r"""
+import sys, os
+import ctypes as C
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np
+import oracle_lib as O
+from yak_b200 import capi
+capi.require_gpu()
+L, OL = capi.lib(), O.lib()
+fn = {fn!r}
+for k, pre, b in ((31, 10, 0), (47, 12, 21)):
+    hg = capi.count_file(fn, k=k, pre=pre, bf_shift=b)
+    assert L.yakb_ch_gpus(hg) == {world}
+    ho, _ = O.count_file(fn, k=k, pre=pre, bf_shift=b)
+    assert hg.contents.tot == ho.contents.tot
+    assert capi.dump_bytes(hg) == O.dump_bytes(ho), (k, pre, b)
+    h1, h2 = (C.c_int64 * 1024)(), (C.c_int64 * 1024)()
+    OL.yo_ch_hist(ho, h1); L.yak_ch_hist(hg, h2, 4)
+    assert list(h1) == list(h2)
+    # lookups across the shards, present and absent (htab.c:93-100)
+    seqs = [ln.strip() for ln in open(fn, "rb") if ln[:1] in b"ACGT"][:300]
+    ev = []
+    for s in seqs:
+        buf = (C.c_uint64 * len(s))()
+        n = OL.yo_extract(k, len(s), s, buf)
+        ev.append(np.frombuffer(buf, dtype=np.uint64, count=n).copy())
+    ev = np.concatenate(ev)
+    probe = np.ascontiguousarray(np.concatenate([ev[::7], ev[::11] ^ np.uint64(0x5555555555)]), dtype=np.uint64)
+    got = np.zeros(len(probe), dtype=np.int32)
+    assert L.yakb_ch_get_batch(hg, len(probe), probe.ctypes.data_as(C.POINTER(C.c_uint64)), got.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+    want = np.array([OL.yo_ch_get(ho, int(x)) for x in probe], dtype=np.int32)
+    assert np.array_equal(got, want)
+    assert L.yak_ch_get(hg, int(probe[0])) == want[0]
+    OL.yo_ch_shrink(ho, 3, 900); L.yak_ch_shrink(hg, 3, 900, 1)
+    assert capi.dump_bytes(hg) == O.dump_bytes(ho), ("shrink", k, pre, b)
+    assert hg.contents.tot == ho.contents.tot
+    OL.yo_ch_clear(ho); L.yak_ch_clear(hg, 1)
+    assert capi.dump_bytes(hg) == O.dump_bytes(ho), ("clear", k, pre, b)
+    L.yak_ch_destroy(hg); OL.yo_ch_destroy(ho)
+print("multi ok")
+"""
+
+
+def test_in_library_multi_gpu_table_operations(yakb):
+    """the `yak count` flow of the C API on a table spread over the GPUs of one process (YAKB_GPUS): tot, dump, hist, get across
+    shards, shrink, clear - against the oracle's single table"""
+    import subprocess
+    import sys
+    world = _gpus_pow2()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, YAKB_GPUS=str(world), YAKB_BATCH="200000")
+    r = subprocess.run([sys.executable, "-c", MULTI_SNIPPET.format(root=root, fn=G.input_path("reads_q"), world=world)],
+                       env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "multi ok" in r.stdout, r.stderr[-3000:]

@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
         "yakb_count_ascii_host": (C.c_int, [ChP, C.c_char_p, u64, C.c_int, C.POINTER(u64)]),
         "yakb_count_events_dev": (C.c_int, [ChP, vp, u64, C.c_int, C.POINTER(u64)]),
         "yakb_extract_route_dev": (C.c_int, [vp, u64, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u64), vp]),
+        "yakb_extract_route_async": (C.c_int, [vp, u64, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
         "yakb_ch_get_batch": (C.c_int, [ChP, u64, C.POINTER(u64), C.POINTER(i32)]),
         "yakb_ch_get_batch_dev": (C.c_int, [ChP, u64, vp, vp]),
         "yakb_qv_seqs": (C.c_int, [ChP, i64, C.POINTER(i64), C.c_char_p, C.c_int, C.c_double, C.POINTER(i64),
@@ -92,6 +93,7 @@ def lib() -> C.CDLL:
         "yakb_ch_stream": (vp, [ChP]),
         "yakb_ch_device_bytes": (u64, [ChP]),
         "yakb_kernel_launches": (u64, []),
+        "yakb_ch_gpus": (C.c_int, [ChP]),
         "yakb_device_cache_bytes": (u64, []),
         "yakb_device_cache_trim": (None, []),
         "yakb_fastx_open": (vp, [C.c_char_p]),

@@ -42,8 +42,9 @@ static int cmd_count(int argc, char *argv[])
 	char *fn_out = 0;
 	int c;
 	yak_copt_init(&opt);
-	while ((c = getopt(argc, argv, "k:p:K:t:b:H:o:")) >= 0) {
-		if (c == 'k') opt.k = atoi(optarg);
+	while ((c = getopt(argc, argv, "k:p:K:t:b:H:o:g:")) >= 0) {
+		if (c == 'g') setenv("YAKB_GPUS", optarg, 1); /* ours: spread the table over this many GPUs (the library reads YAKB_GPUS) */
+		else if (c == 'k') opt.k = atoi(optarg);
 		else if (c == 'p') opt.pre = atoi(optarg);
 		else if (c == 'K') opt.chunk_size = yakb_cli_parse_num(optarg);
 		else if (c == 't') opt.n_thread = atoi(optarg);
@@ -61,6 +62,7 @@ static int cmd_count(int argc, char *argv[])
 		fprintf(stderr, "  -t INT     number of worker threads (accepted, unused on the GPU) [%d]\n", opt.n_thread);
 		fprintf(stderr, "  -o FILE    dump the count hash table to FILE []\n");
 		fprintf(stderr, "  -K INT     chunk size [100m]\n");
+		fprintf(stderr, "  -g INT     number of GPUs to spread the sub-tables over (a power of two; also YAKB_GPUS) [1]\n");
 		fprintf(stderr, "Note: -b37 is recommended for human reads\n");
 		return 1;
 	}

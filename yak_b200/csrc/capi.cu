@@ -28,6 +28,7 @@
 #include <fcntl.h>
 #include <thread>
 #include <atomic>
+#include <condition_variable>
 #include "ref_flow.h"
 #include <chrono>
 #include <memory>
@@ -38,10 +39,22 @@ using namespace yakb;
 
 struct yak_ht_t { struct ChBox *owner; int idx; };
 
+// One GPU's part of a table that yak_count spread over several GPUs of this process: shard r lives on
+// device `dev` and owns sub-tables [r*P/G, (r+1)*P/G).  Its buffers belong to that device.
+struct Shard {
+	int dev = 0;
+	Engine *eng = nullptr;
+	RouteScratch route;
+	DBuf d_in, d_ev, d_recv;
+	cudaStream_t stream = nullptr;      // host->device copy + extraction of this shard's slice of a batch
+};
+
 struct ChBox {
 	yak_ch_t pub;          // must stay first: yak_ch_t* <-> ChBox*
 	uint32_t magic;
-	Engine *eng;
+	Engine *eng;           // the table; shard 0 of a multi-GPU table
+	std::vector<Shard*> shards; // empty for a table on one GPU
+	int dev = 0;           // device of `eng`
 	std::vector<yak_ht_t> handles;
 	std::vector<yak_bf_t> filters;
 	std::mutex mu;
@@ -55,6 +68,38 @@ static ChBox *box_of(const yak_ch_t *h)
 	ChBox *b = (ChBox*)h;
 	if (b == nullptr || b->magic != kMagic) { fprintf(stderr, "[yakb] ERROR: yak_ch_t was not created by this library\n"); abort(); }
 	return b;
+}
+// for the entry points that work on one-GPU tables only: a multi-GPU table (yak_count with YAKB_GPUS > 1) supports the
+// `yak count` flow - yak_count, yak_ch_destroy_bf / clear / shrink / hist / get / insert_list / dump / destroy
+static ChBox *box_single(const yak_ch_t *h, const char *func)
+{
+	ChBox *b = box_of(h);
+	if (!b->shards.empty()) throw CudaError(std::string(func) + " is not available on a multi-GPU table (YAKB_GPUS > 1): dump it and restore it on one GPU");
+	return b;
+}
+struct DevGuard {
+	int prev = 0;
+	explicit DevGuard(int d) { cudaGetDevice(&prev); if (d != prev) cudaSetDevice(d); }
+	~DevGuard() { int cur = 0; cudaGetDevice(&cur); if (cur != prev) cudaSetDevice(prev); }
+};
+// fn(engine, rank) for the table's engine, or for every shard on its own device (side by side when `parallel`)
+template<class F> static void each_shard(ChBox *b, bool parallel, F &&fn)
+{
+	if (b->shards.empty()) { fn(b->eng, 0); return; }
+	const int G = (int)b->shards.size();
+	if (!parallel) {
+		for (int r = 0; r < G; ++r) { DevGuard g(b->shards[r]->dev); fn(b->shards[r]->eng, r); }
+		return;
+	}
+	std::vector<std::thread> th;
+	std::vector<std::string> err(G);
+	for (int r = 0; r < G; ++r)
+		th.emplace_back([&, r] {
+			try { cudaSetDevice(b->shards[r]->dev); fn(b->shards[r]->eng, r); }
+			catch (const std::exception &e) { err[r] = e.what(); }
+		});
+	for (auto &t : th) t.join();
+	for (auto &e : err) if (!e.empty()) throw CudaError(e);
 }
 
 #define GUARD_BEGIN try {
@@ -107,9 +152,10 @@ static void attach_handles(ChBox *b)
 		b->handles[i].owner = b; b->handles[i].idx = i;
 		b->pub.h[i].h = &b->handles[i];
 		if (b->eng->bloom) {
-			b->filters[i].n_shift = b->eng->n_shift - b->eng->pre;
-			b->filters[i].n_hashes = b->eng->n_hash;
-			b->filters[i].b = b->eng->bloom + (size_t)(i & (b->eng->P - 1)) * 64; // first block of sub-filter i (blocks interleave by sub-table)
+			const Engine *e = b->shards.empty() ? b->eng : b->shards[i / b->eng->P]->eng; // the engine that holds sub-table i
+			b->filters[i].n_shift = e->n_shift - e->pre;
+			b->filters[i].n_hashes = e->n_hash;
+			b->filters[i].b = e->bloom + (size_t)(i & (e->P - 1)) * 64; // first block of sub-filter i (blocks interleave by sub-table)
 			b->pub.h[i].b = &b->filters[i];
 		}
 	}
@@ -125,8 +171,57 @@ static yak_ch_t *ch_init_shard(int k, int pre, int n_hash, int n_shift, int rank
 	ChBox *b = new ChBox;
 	memset(&b->pub, 0, sizeof(b->pub));
 	b->magic = kMagic; b->eng = e;
+	cudaGetDevice(&b->dev);
 	b->pub.k = k; b->pub.pre = pre; b->pub.n_hash = e->n_hash; b->pub.n_shift = e->n_shift; b->pub.tot = 0;
 	attach_handles(b);
+	return &b->pub;
+	GUARD_END(0)
+}
+
+// how many GPUs yak_count spreads a NEW table over: YAKB_GPUS (default 1), a power of two, at most the devices present and 16
+static int multi_gpus_wanted()
+{
+	const char *e = getenv("YAKB_GPUS");
+	int g = e ? atoi(e) : 1, n = 0;
+	if (g <= 1) return 1;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 1;
+	while (g > n || (g & (g - 1))) --g;
+	return g > 16 ? 16 : (g < 1 ? 1 : g);
+}
+
+// a table of G shards, shard r on device r (the devices CUDA_VISIBLE_DEVICES leaves visible)
+static yak_ch_t *ch_init_multi(int k, int pre, int n_hash, int n_shift, int G)
+{
+	GUARD_BEGIN
+	StageTimer tm("yak_ch_init(multi)");
+	if (pre < YAK_COUNTER_BITS) return 0;
+	ChBox *b = new ChBox;
+	memset(&b->pub, 0, sizeof(b->pub));
+	b->magic = kMagic; b->eng = nullptr;
+	int dev0 = 0;
+	cudaGetDevice(&dev0);
+	bool ok = true;
+	for (int r = 0; r < G && ok; ++r) {
+		Shard *sh = new Shard;
+		sh->dev = r;
+		b->shards.push_back(sh);
+		DevGuard g(r);
+		for (int q = 0; q < G; ++q) // peers read each other's routed events directly over NVLink; without peer access the copies are staged
+			if (q != r) { int can = 0; cudaDeviceCanAccessPeer(&can, r, q); if (can && cudaDeviceEnablePeerAccess(q, 0) != cudaSuccess) (void)cudaGetLastError(); }
+		sh->eng = Engine::create(k, pre, n_hash, n_shift, r, G);
+		if (!sh->eng) { ok = false; break; }
+		YAKB_CUDA(cudaStreamCreateWithFlags(&sh->stream, cudaStreamNonBlocking));
+	}
+	cudaSetDevice(dev0);
+	if (!ok) {
+		for (Shard *sh : b->shards) { DevGuard g(sh->dev); delete sh->eng; if (sh->stream) cudaStreamDestroy(sh->stream); delete sh; }
+		delete b;
+		return 0;
+	}
+	b->eng = b->shards[0]->eng; b->dev = b->shards[0]->dev;
+	b->pub.k = k; b->pub.pre = pre; b->pub.n_hash = b->eng->n_hash; b->pub.n_shift = b->eng->n_shift; b->pub.tot = 0;
+	attach_handles(b);
+	fprintf(stderr, "[M::%s] table of 2^%d sub-tables on %d GPUs (%d sub-tables each)\n", __func__, pre, G, b->eng->P);
 	return &b->pub;
 	GUARD_END(0)
 }
@@ -145,7 +240,7 @@ extern "C" void yak_ch_destroy_bf(yak_ch_t *h) // htab.c:31-39
 {
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
-	b->eng->destroy_bloom();
+	each_shard(b, false, [](Engine *e, int) { e->destroy_bloom(); });
 	for (int i = 0; i < 1 << h->pre; ++i) h->h[i].b = 0;
 	b->filters.clear();
 }
@@ -155,7 +250,17 @@ extern "C" void yak_ch_destroy(yak_ch_t *h) // htab.c:41-49
 	if (h == 0) return;
 	StageTimer tm("yak_ch_destroy");
 	ChBox *b = box_of(h);
-	delete b->eng;
+	if (b->shards.empty()) delete b->eng;
+	else
+		for (Shard *sh : b->shards) {
+			DevGuard g(sh->dev);
+			delete sh->eng;
+			sh->d_in.release(); sh->d_ev.release(); sh->d_recv.release();
+			for (DBuf &d : sh->route.b) d.release();
+			sh->route.rs.release();
+			if (sh->stream) cudaStreamDestroy(sh->stream);
+			delete sh;
+		}
 	free(b->pub.h);
 	if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
 	b->d_in.release(); b->d_in2.release(); b->d_aux.release(); b->d_aux2.release();
@@ -169,9 +274,16 @@ extern "C" int yak_ch_insert_list(yak_ch_t *h, int create_new, int n, const uint
 	if (n <= 0) return 0;
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
+	const int only = (int)(a[0] & (uint64_t)(b->eng->P - 1)); // region index; foreign shards are filtered by owner
+	if (!b->shards.empty()) { // the shard that owns a[0]'s sub-table takes the list
+		Shard *sh = b->shards[(a[0] & (((uint64_t)1 << h->pre) - 1)) / (uint64_t)b->eng->P];
+		DevGuard g(sh->dev);
+		uint64_t *d = sh->d_in.as<uint64_t>(n);
+		YAKB_CUDA(cudaMemcpyAsync(d, a, (size_t)n * 8, cudaMemcpyHostToDevice, sh->eng->stream));
+		return (int)sh->eng->count_events(d, n, create_new, only).n_new;
+	}
 	uint64_t *d = b->d_in.as<uint64_t>(n);
 	YAKB_CUDA(cudaMemcpyAsync(d, a, (size_t)n * 8, cudaMemcpyHostToDevice, b->eng->stream));
-	const int only = (int)(a[0] & (uint64_t)(b->eng->P - 1)); // region index; foreign shards are filtered by owner
 	ChunkStats st = b->eng->count_events(d, n, create_new, only);
 	return (int)st.n_new; // the caller adds this to h->tot (count.c:138)
 	GUARD_END(0)
@@ -183,6 +295,21 @@ extern "C" int yakb_ch_get_batch(const yak_ch_t *h, uint64_t n, const uint64_t *
 	if (n == 0) return 0;
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
+	if (!b->shards.empty()) { // every shard answers for its own sub-tables (-1 elsewhere): the maximum is the table's answer
+		std::vector<int32_t> part(n);
+		for (uint64_t i = 0; i < n; ++i) out[i] = -1;
+		for (Shard *sh : b->shards) {
+			DevGuard g(sh->dev);
+			uint64_t *dx = sh->d_in.as<uint64_t>(n);
+			int32_t *dout = sh->d_recv.as<int32_t>(n);
+			YAKB_CUDA(cudaMemcpyAsync(dx, x, n * 8, cudaMemcpyHostToDevice, sh->eng->stream));
+			sh->eng->get_batch(dx, n, dout);
+			YAKB_CUDA(cudaMemcpyAsync(part.data(), dout, n * 4, cudaMemcpyDeviceToHost, sh->eng->stream));
+			YAKB_CUDA(cudaStreamSynchronize(sh->eng->stream));
+			for (uint64_t i = 0; i < n; ++i) if (part[i] > out[i]) out[i] = part[i];
+		}
+		return 0;
+	}
 	uint64_t *dx = b->d_in.as<uint64_t>(n);
 	int32_t *dout = b->d_aux.as<int32_t>(n);
 	YAKB_CUDA(cudaMemcpyAsync(dx, x, n * 8, cudaMemcpyHostToDevice, b->eng->stream));
@@ -196,7 +323,7 @@ extern "C" int yakb_ch_get_batch(const yak_ch_t *h, uint64_t n, const uint64_t *
 extern "C" int yakb_ch_get_batch_dev(const yak_ch_t *h, uint64_t n, const uint64_t *d_x, int32_t *d_out)
 {
 	GUARD_BEGIN
-	ChBox *b = box_of(h);
+	ChBox *b = box_single(h, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
 	b->eng->get_batch(d_x, n, d_out);
 	return 0;
@@ -213,7 +340,7 @@ extern "C" int yak_ch_get(const yak_ch_t *h, uint64_t x) // htab.c:93-100
 extern "C" int yak_ch_inc(yak_ch_t *h, uint64_t x) // htab.c:80-91
 {
 	GUARD_BEGIN
-	ChBox *b = box_of(h);
+	ChBox *b = box_single(h, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
 	return inc_one(b->eng, x);
 	GUARD_END(-1)
@@ -225,7 +352,7 @@ extern "C" void yak_ch_clear(yak_ch_t *h, int n_thread) // htab.c:116-130
 	(void)n_thread;
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
-	b->eng->clear();
+	each_shard(b, true, [](Engine *e, int) { e->clear(); });
 	GUARD_END_VOID
 }
 
@@ -235,7 +362,11 @@ extern "C" void yak_ch_hist(const yak_ch_t *h, int64_t cnt[YAK_N_COUNTS], int n_
 	(void)n_thread;
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
-	b->eng->hist(cnt);
+	if (b->shards.empty()) b->eng->hist(cnt);
+	else {
+		for (int i = 0; i < YAK_N_COUNTS; ++i) cnt[i] = 0;
+		each_shard(b, false, [&](Engine *e, int) { int64_t part[YAK_N_COUNTS]; e->hist(part); for (int i = 0; i < YAK_N_COUNTS; ++i) cnt[i] += part[i]; });
+	}
 	GUARD_END_VOID
 }
 
@@ -246,8 +377,10 @@ extern "C" void yak_ch_shrink(yak_ch_t *h, int min, int max, int n_thread) // ht
 	StageTimer tm("yak_ch_shrink");
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
-	b->eng->shrink(min, max);
-	h->tot = b->eng->tot;
+	each_shard(b, true, [&](Engine *e, int) { e->shrink(min, max); });
+	uint64_t tot = 0;
+	each_shard(b, false, [&](Engine *e, int) { tot += e->tot; });
+	h->tot = tot;
 	GUARD_END_VOID
 }
 
@@ -256,7 +389,7 @@ extern "C" void yak_ch_setcnt(yak_ch_t *h, int cnt, int n_thread) // htab.c:229-
 	GUARD_BEGIN
 	(void)n_thread;
 	assert(cnt >= 0 && cnt <= YAK_MAX_COUNT);
-	ChBox *b = box_of(h);
+	ChBox *b = box_single(h, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
 	setcnt(b->eng, cnt);
 	GUARD_END_VOID
@@ -266,7 +399,7 @@ extern "C" yak_knt_t *yak_ch_getseq(const yak_ch_t *h, int w, uint32_t *n) // ht
 {
 	GUARD_BEGIN
 	assert(h->k < 32 && w < 1 << h->pre);
-	ChBox *b = box_of(h);
+	ChBox *b = box_single(h, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
 	LayoutOut lo;
 	b->eng->layout(w, w + 1, lo, true);
@@ -286,7 +419,7 @@ extern "C" yak_knt_t *yak_ch_getseq(const yak_ch_t *h, int w, uint32_t *n) // ht
 extern "C" void yak_ch_tighten(yak_ch_t *h)
 {
 	GUARD_BEGIN
-	ChBox *b = box_of(h);
+	ChBox *b = box_single(h, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
 	std::vector<uint64_t> op(b->eng->P, (uint64_t)Engine::OP_TIGHTEN);
 	b->eng->append_ops(op);
@@ -328,7 +461,7 @@ extern "C" void yak_ch_merge(yak_ch_t *h0, yak_ch_t *h1, int min, int max, int n
 {
 	GUARD_BEGIN
 	(void)n_thread;
-	ChBox *b0 = box_of(h0), *b1 = box_of(h1);
+	ChBox *b0 = box_single(h0, __func__), *b1 = box_single(h1, __func__);
 	assert(h0->k == h1->k && h0->pre == h1->pre && b0->eng->P == b1->eng->P);
 	if (!(max >= min && max <= YAK_MAX_COUNT)) max = YAK_MAX_COUNT;
 	{
@@ -371,7 +504,7 @@ extern "C" void yak_ch_merge(yak_ch_t *h0, yak_ch_t *h1, int min, int max, int n
 // (subtract) / present in (isec) h1, re-put into sets pre-sized to h0's old sizes
 static void filter_by_membership(yak_ch_t *h0, const yak_ch_t *h1, bool keep_present)
 {
-	ChBox *b0 = box_of(h0), *b1 = box_of(h1);
+	ChBox *b0 = box_single(h0, __func__), *b1 = box_single(h1, __func__);
 	assert(h0->k == h1->k && h0->pre == h1->pre && b0->eng->P == b1->eng->P);
 	std::lock_guard<std::mutex> lk(b0->mu);
 	Engine *e0 = b0->eng, *e1 = b1->eng;
@@ -421,7 +554,14 @@ extern "C" void yak_ch_isec(yak_ch_t *h0, const yak_ch_t *h1, int n_thread)
 // ------------------------------------------------------------------ dump / restore
 
 // htab.c:373-394; sink(ptr,len) receives the bytes in order
+template<class Sink> static void serialise_engine(ChBox *b, Engine *eng, Sink &&sink, bool header);
+// a multi-GPU table is the rank-ordered concatenation of its shards (the header from the first)
 template<class Sink> static void serialise(ChBox *b, Sink &&sink, bool header = true)
+{
+	if (b->shards.empty()) { serialise_engine(b, b->eng, sink, header); return; }
+	for (size_t r = 0; r < b->shards.size(); ++r) { DevGuard g(b->shards[r]->dev); serialise_engine(b, b->shards[r]->eng, sink, header && r == 0); }
+}
+template<class Sink> static void serialise_engine(ChBox *b, Engine *eng, Sink &&sink, bool header)
 {
 	const yak_ch_t *h = &b->pub;
 	uint32_t t[3] = {(uint32_t)h->k, (uint32_t)h->pre, YAK_COUNTER_BITS};
@@ -431,11 +571,11 @@ template<class Sink> static void serialise(ChBox *b, Sink &&sink, bool header = 
 	}
 	double t_lay = 0, t_sink = 0;
 	LayoutOut lo; // one for all steps: Engine::layout resets it, and its key array (gigabytes) keeps its pages
-	const std::vector<int> bounds = slice_bounds(b->eng, 1ull << 30);
+	const std::vector<int> bounds = slice_bounds(eng, 1ull << 30);
 	for (size_t bi = 0; bi + 1 < bounds.size(); ++bi) {
 		const int s0 = bounds[bi], s1 = bounds[bi + 1];
 		double t0 = wall_now();
-		b->eng->layout(s0, s1, lo, true);
+		eng->layout(s0, s1, lo, true);
 		double t1 = wall_now();
 		for (int s = s0; s < s1; ++s) {
 			uint32_t u[2] = {lo.cap[s - s0], lo.size[s - s0]};
@@ -453,7 +593,7 @@ extern "C" int yak_ch_dump(const yak_ch_t *h, const char *fn)
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
 	StageTimer tm("yak_ch_dump");
-	if (b->eng->lw) { fprintf(stderr, "[yakb] ERROR: yak_ch_dump on one shard of a multi-GPU table; use yakb_ch_dump_shard_mem\n"); return -1; }
+	if (b->eng->lw && b->shards.empty()) { fprintf(stderr, "[yakb] ERROR: yak_ch_dump on one shard of a multi-GPU table; use yakb_ch_dump_shard_mem\n"); return -1; }
 	FILE *fp = strcmp(fn, "-") ? fopen(fn, "wb") : stdout;
 	if (fp == 0) return -1;
 	std::unique_ptr<char[]> iobuf(new char[1 << 20]); // per call: tables may be dumped from several threads at once
@@ -521,7 +661,7 @@ extern "C" yak_ch_t *yak_ch_restore_core(yak_ch_t *ch0, const char *fn, int mode
 	if (!ch) return 0;
 	assert((int)yf.k == ch->k && (int)yf.pre == ch->pre); // htab.c:437
 	if (yf.caps.empty() && read_yak_file(fn, mode, min_cnt, mid_cnt, yf, 0) != 0) { if (!ch0) yak_ch_destroy(ch); return 0; }
-	ChBox *b = box_of(ch);
+	ChBox *b = box_single(ch, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
 	const int P = 1 << ch->pre;
 	std::vector<uint32_t> &caps = yf.caps;
@@ -553,7 +693,7 @@ static int run_ascii_dev(ChBox *b, const uint8_t *d_asc, uint64_t n, int create_
 extern "C" int yakb_count_ascii_dev(yak_ch_t *h, const void *d_asc, uint64_t n, int create_new, uint64_t stats[4])
 {
 	GUARD_BEGIN
-	ChBox *b = box_of(h);
+	ChBox *b = box_single(h, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
 	return run_ascii_dev(b, (const uint8_t*)d_asc, n, create_new, stats);
 	GUARD_END(-1)
@@ -562,7 +702,7 @@ extern "C" int yakb_count_ascii_dev(yak_ch_t *h, const void *d_asc, uint64_t n, 
 extern "C" int yakb_count_ascii_host(yak_ch_t *h, const char *asc, uint64_t n, int create_new, uint64_t stats[4])
 {
 	GUARD_BEGIN
-	ChBox *b = box_of(h);
+	ChBox *b = box_single(h, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
 	uint8_t *d = b->d_in.as<uint8_t>(n + 64);
 	YAKB_CUDA(cudaMemcpyAsync(d, asc, n, cudaMemcpyHostToDevice, b->eng->stream));
@@ -573,7 +713,7 @@ extern "C" int yakb_count_ascii_host(yak_ch_t *h, const char *asc, uint64_t n, i
 extern "C" int yakb_count_events_dev(yak_ch_t *h, const uint64_t *d_ev, uint64_t n, int create_new, uint64_t stats[4])
 {
 	GUARD_BEGIN
-	ChBox *b = box_of(h);
+	ChBox *b = box_single(h, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
 	ChunkStats st = b->eng->count_events(d_ev, n, create_new, -1);
 	b->pub.tot = b->eng->tot;
@@ -592,10 +732,18 @@ extern "C" int yakb_extract_route_dev(const void *d_asc, uint64_t n, int k, int 
 	GUARD_END(-1)
 }
 
+extern "C" int yakb_extract_route_async(const void *d_asc, uint64_t n, int k, int pre, int world, uint64_t *d_out, uint64_t *d_counts, void *cuda_stream)
+{
+	GUARD_BEGIN
+	std::lock_guard<std::mutex> lk(g_route_mu);
+	return extract_events_async((const uint8_t*)d_asc, n, k, pre, world, d_out, d_counts, (cudaStream_t)cuda_stream, g_route_scratch);
+	GUARD_END(-1)
+}
+
 extern "C" int yakb_ch_reserve(yak_ch_t *h, uint64_t keys_per_subtable)
 {
 	GUARD_BEGIN
-	ChBox *b = box_of(h);
+	ChBox *b = box_single(h, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
 	b->eng->reserve(keys_per_subtable);
 	return 0;
@@ -603,7 +751,13 @@ extern "C" int yakb_ch_reserve(yak_ch_t *h, uint64_t keys_per_subtable)
 }
 
 extern "C" void *yakb_ch_stream(const yak_ch_t *h) { return (void*)box_of(h)->eng->stream; }
-extern "C" uint64_t yakb_ch_device_bytes(const yak_ch_t *h) { return box_of(h)->eng->device_bytes(); }
+extern "C" uint64_t yakb_ch_device_bytes(const yak_ch_t *h)
+{
+	uint64_t tot = 0;
+	each_shard(box_of(h), false, [&](Engine *e, int) { tot += e->device_bytes(); });
+	return tot;
+}
+extern "C" int yakb_ch_gpus(const yak_ch_t *h) { ChBox *b = box_of(h); return b->shards.empty() ? 1 : (int)b->shards.size(); }
 extern "C" const char *yakb_version(void) { return YAKS_VERSION; }
 extern "C" int yakb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 extern "C" uint64_t yakb_kernel_launches(void) { return Engine::launches(); }
@@ -808,6 +962,77 @@ PinnedPool g_pinned;
 // Three things overlap: the reader's pool parses ahead of the consumer, the producer thread stitches
 // batch i+1 into pinned memory and copies it to the device on its own stream, the main thread runs
 // the kernels of batch i.
+// ---- one batch on a multi-GPU table (inside one process: one host thread per GPU).
+//      The batch ("SEQ\nSEQ\n..." in pinned host memory) is cut into G contiguous parts at record boundaries.  Thread r
+//      copies part r to GPU r and extracts its k-mers grouped by owner (extract_events: count.c:28-60 + the stable
+//      partition); after a barrier every GPU pulls the runs it owns from its peers' buffers - source ranks in order, i.e.
+//      file order per sub-table (count.c:120,133) - with peer copies over NVLink, and counts them on its shard.
+namespace {
+struct Barrier {
+	std::mutex mu; std::condition_variable cv; int n, waiting = 0; uint64_t gen = 0;
+	explicit Barrier(int n_) : n(n_) {}
+	void wait()
+	{
+		std::unique_lock<std::mutex> lk(mu);
+		const uint64_t g = gen;
+		if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); }
+		else cv.wait(lk, [&] { return gen != g; });
+	}
+};
+}
+
+static void multi_batch(ChBox *b, const uint8_t *host, size_t n, int create_new)
+{
+	const int G = (int)b->shards.size(), k = b->pub.k, pre = b->pub.pre;
+	std::vector<size_t> cut(G + 1, 0);
+	cut[G] = n;
+	for (int r = 1; r < G; ++r) { // the last record boundary at or before r*n/G
+		size_t p = std::max(cut[r - 1], n * (size_t)r / G);
+		while (p > cut[r - 1] && host[p - 1] != '\n') --p;
+		cut[r] = p;
+	}
+	std::vector<std::vector<uint64_t>> counts(G, std::vector<uint64_t>(G, 0)); // counts[s][d]: events of part s owned by GPU d
+	std::vector<const uint64_t*> d_ev(G, nullptr);
+	std::vector<std::string> err(G);
+	std::atomic<int> failed{0};
+	Barrier mid(G);
+	std::vector<uint64_t> n_new(G, 0);
+	auto work = [&](int r) {
+		Shard *sh = b->shards[r];
+		cudaSetDevice(sh->dev);
+		try {
+			const size_t nr = cut[r + 1] - cut[r];
+			uint8_t *d_in = sh->d_in.as<uint8_t>(nr + 64);
+			uint64_t *ev = sh->d_ev.as<uint64_t>(std::max<size_t>(nr, 1));
+			if (nr) YAKB_CUDA(cudaMemcpyAsync(d_in, host + cut[r], nr, cudaMemcpyHostToDevice, sh->stream));
+			if (extract_events(d_in, nr, k, pre, G, ev, counts[r].data(), sh->stream, sh->route) != 0) throw CudaError("extract_events failed");
+			YAKB_CUDA(cudaStreamSynchronize(sh->stream));
+			d_ev[r] = ev;
+		} catch (const std::exception &e) { err[r] = e.what(); failed = 1; }
+		mid.wait(); // every part is extracted, every count is known
+		if (failed) { mid.wait(); return; }
+		try {
+			uint64_t total = 0;
+			for (int s = 0; s < G; ++s) total += counts[s][r];
+			uint64_t *recv = sh->d_recv.as<uint64_t>(std::max<uint64_t>(total, 1));
+			uint64_t off = 0;
+			for (int s = 0; s < G; ++s) {
+				uint64_t src_off = 0;
+				for (int d = 0; d < r; ++d) src_off += counts[s][d];
+				if (counts[s][r]) YAKB_CUDA(cudaMemcpyPeerAsync(recv + off, sh->dev, d_ev[s] + src_off, b->shards[s]->dev, counts[s][r] * 8, sh->eng->stream));
+				off += counts[s][r];
+			}
+			n_new[r] = sh->eng->count_events(recv, total, create_new, -1).n_new; // on the same stream, behind the copies
+		} catch (const std::exception &e) { err[r] = e.what(); failed = 1; }
+		mid.wait(); // nobody reuses its event buffer before every peer has pulled from it
+	};
+	std::vector<std::thread> th;
+	for (int r = 0; r < G; ++r) th.emplace_back(work, r);
+	for (auto &t : th) t.join();
+	for (auto &e : err) if (!e.empty()) throw CudaError(e);
+	for (int r = 0; r < G; ++r) b->pub.tot += n_new[r];
+}
+
 static yak_ch_t *count_impl(const char *fn, const yak_copt_t *opt, yak_ch_t *h0, int ref_workers);
 extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *h0) { return count_impl(fn, opt, h0, 3); } // count.c:162
 
@@ -831,15 +1056,25 @@ static yak_ch_t *count_impl(const char *fn, const yak_copt_t *opt, yak_ch_t *h0,
 	rd.set_ref_chunk(opt->chunk_size); rd.set_ref_workers(ref_workers);
 	yak_ch_t *h = h0;
 	if (h0) assert(h0->k == opt->k && h0->pre == opt->pre);
-	else h = yak_ch_init(opt->k, opt->pre, opt->bf_n_hash, opt->bf_shift);
+	else {
+		const int gpus = multi_gpus_wanted(); // YAKB_GPUS > 1: the new table is spread over that many GPUs of this process
+		h = gpus > 1 && (1 << opt->pre) >= gpus ? ch_init_multi(opt->k, opt->pre, opt->bf_n_hash, opt->bf_shift, gpus)
+		                                          : yak_ch_init(opt->k, opt->pre, opt->bf_n_hash, opt->bf_shift);
+	}
 	if (!h) return 0;
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
+	const bool multi = !b->shards.empty();
 	const int create_new = h0 == 0;
 	uint64_t cap = batch_bases(opt->chunk_size);
 	struct stat st;
-	if (par && stat(src, &st) == 0 && S_ISREG(st.st_mode)) // a batch never holds more than the file: no 2 x 1.9 GB of pinned memory for `cntasm -K1.9g` on a small assembly
+	if (par && stat(src, &st) == 0 && S_ISREG(st.st_mode)) {
+		// large files get large batches (the partitioned probe gains with the events per chunk; ~32 batches keep parser,
+		// copies and kernels overlapped), and a batch never holds more than the file: no 2 x 1.9 GB of pinned memory for
+		// `cntasm -K1.9g` on a small assembly
+		if (!getenv("YAKB_BATCH")) cap = std::max<uint64_t>(cap, std::min<uint64_t>((uint64_t)st.st_size / 32, 1ull << 30));
 		cap = std::min<uint64_t>(cap, std::max<uint64_t>((uint64_t)st.st_size + 4096, 1u << 20));
+	}
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (!b->copy_stream) YAKB_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
@@ -862,7 +1097,7 @@ static yak_ch_t *count_impl(const char *fn, const yak_copt_t *opt, yak_ch_t *h0,
 			const size_t pc = std::min(pinned_cap[0], pinned_cap[1]);
 			t.n = par ? prd.fill(pinned[slot], pc, target, opt->k, &t.n_seq, &t.done, &t.need)
 			          : rd.fill(pinned[slot], pc, target, opt->k, &t.n_seq, &t.done, &t.need);
-			if (t.n && !t.need) {
+			if (t.n && !t.need && !multi) {
 				uint8_t *d = d_in[slot]->as<uint8_t>(t.n + 64);
 				YAKB_CUDA(cudaMemcpyAsync(d, pinned[slot], t.n, cudaMemcpyHostToDevice, b->copy_stream));
 				YAKB_CUDA(cudaStreamSynchronize(b->copy_stream));
@@ -892,7 +1127,8 @@ static yak_ch_t *count_impl(const char *fn, const yak_copt_t *opt, yak_ch_t *h0,
 		struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_on_unwind{producer};
 		if (cur.n) {
 			const double td = wall_now();
-			run_ascii_dev(b, (const uint8_t*)d_in[slot]->p, cur.n, create_new, nullptr);
+			if (multi) multi_batch(b, pinned[slot], cur.n, create_new);
+			else run_ascii_dev(b, (const uint8_t*)d_in[slot]->p, cur.n, create_new, nullptr);
 			t_dev += wall_now() - td; ++n_batches;
 			if (timing_on()) fprintf(stderr, "[T::yak_count] batch %d: %zu bytes, kernels %.4f s\n", n_batches, cur.n, wall_now() - td);
 			fprintf(stderr, "[M::%s::%.3f*%.2f] processed %d sequences; %ld distinct k-mers in the hash table\n", __func__,
@@ -957,7 +1193,7 @@ extern "C" int yakb_qv_seqs(const yak_ch_t *h, int64_t n_seq, const int64_t *len
                             int min_len, double min_frac, int64_t cnt[YAK_N_COUNTS], int32_t *tot, int32_t *non0)
 {
 	GUARD_BEGIN
-	ChBox *b = box_of(h);
+	ChBox *b = box_single(h, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
 	assert(h->k < 32); // qv.c:43
 	unsigned long long *d_hist = (unsigned long long*)b->d_aux2.need(1024 * 8);
@@ -987,7 +1223,7 @@ extern "C" int yakb_qv_seqs(const yak_ch_t *h, int64_t n_seq, const int64_t *len
 extern "C" int yakb_scan_seqs(const yak_ch_t *h, int64_t n_seq, const int64_t *lens, const char *cat, int16_t *out)
 {
 	GUARD_BEGIN
-	ChBox *b = box_of(h);
+	ChBox *b = box_single(h, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
 	Engine *e = b->eng;
 	const uint64_t cap = batch_bases(0);
@@ -1024,7 +1260,7 @@ extern "C" int yakb_scan_seqs(const yak_ch_t *h, int64_t n_seq, const int64_t *l
 extern "C" void yak_qv(const yak_qopt_t *opt, const char *fn, const yak_ch_t *ch, int64_t *cnt)
 {
 	GUARD_BEGIN
-	ChBox *b = box_of(ch);
+	ChBox *b = box_single(ch, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
 	assert(ch->k < 32); // qv.c:43
 	memset(cnt, 0, YAK_N_COUNTS * sizeof(int64_t));

@@ -141,12 +141,14 @@ struct ProfPair { const char *name; cudaEvent_t a, b; };
 static std::vector<ProfPair> g_prof_open, g_prof_done;
 static std::map<std::string, std::pair<double, uint64_t>> g_prof_acc;
 static std::map<std::string, uint64_t> g_prof_units; // work items (events, pending events, positions) a kernel name processed
+static std::mutex g_prof_mu; // engines of a multi-GPU table run on one host thread each
 void Prof::enable(bool on) { g_prof_on = on; }
 bool Prof::on() { return g_prof_on; }
-void Prof::reset() { g_prof_acc.clear(); g_prof_units.clear(); }
-void Prof::units(const char *name, uint64_t n) { if (g_prof_on) g_prof_units[name] += n; }
+void Prof::reset() { std::lock_guard<std::mutex> lk(g_prof_mu); g_prof_acc.clear(); g_prof_units.clear(); }
+void Prof::units(const char *name, uint64_t n) { if (g_prof_on) { std::lock_guard<std::mutex> lk(g_prof_mu); g_prof_units[name] += n; } }
 void Prof::begin(const char *name, cudaStream_t s)
 {
+	std::lock_guard<std::mutex> lk(g_prof_mu);
 	ProfPair p; p.name = name;
 	cudaEventCreate(&p.a); cudaEventCreate(&p.b);
 	cudaEventRecord(p.a, s);
@@ -154,12 +156,14 @@ void Prof::begin(const char *name, cudaStream_t s)
 }
 void Prof::end(cudaStream_t s)
 {
+	std::lock_guard<std::mutex> lk(g_prof_mu);
 	ProfPair p = g_prof_open.back(); g_prof_open.pop_back();
 	cudaEventRecord(p.b, s);
 	g_prof_done.push_back(p);
 }
 void Prof::resolve()
 {
+	std::lock_guard<std::mutex> lk(g_prof_mu);
 	for (auto &p : g_prof_done) {
 		float ms = 0;
 		if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
@@ -171,6 +175,7 @@ void Prof::resolve()
 }
 std::string Prof::json()
 {
+	std::lock_guard<std::mutex> lk(g_prof_mu);
 	std::string o = "{";
 	char buf[256];
 	bool first = true;
@@ -212,6 +217,51 @@ __device__ __forceinline__ int probe_inc_warp(uint64_t *reg, uint32_t nbk, uint6
 		}
 	}
 	return found;
+}
+
+// Probe up to four events of one thread at once (vm = which of v[0..3] are live; bi / bk = their home buckets, already
+// loaded by the caller so that the loads overlap whatever it did in between).  Returns the mask of events found in the
+// table (counter bumped by one, saturating).  All 32 lanes call it together.  Every round handles ALL unfinished events
+// of the thread: match, issue the counter CAS of every match, then look at the results; events whose bucket was full
+// without the key move on to the next bucket, events that lost a CAS race look at the same bucket again - the follow-up
+// loads of a round are issued together, so a warp pays one extra round trip per additional bucket, not one per event.
+__device__ __forceinline__ uint32_t probe_inc4(uint64_t *slots, uint32_t cap, uint32_t nbk, int pre, uint32_t Pmask,
+                                               const uint64_t (&v)[4], uint32_t vm, uint32_t (&bi)[4], Bucket (&bk)[4])
+{
+	uint32_t todo = vm, hit = 0;
+	for (;;) {
+		uint64_t expect[4], prev[4];
+		uint32_t cas = 0, adv = 0;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			expect[j] = prev[j] = 0;
+			if (todo >> j & 1) {
+				int f, m = bucket_match(bk[j], v[j] >> pre, &f);
+				if (m >= 0) {
+					const uint64_t c = bucket_get(bk[j], m);
+					if ((c & YAKB_MAX_COUNT) == YAKB_MAX_COUNT) { hit |= 1u << j; todo &= ~(1u << j); } // htab.c:69: stays at the cap
+					else {
+						uint64_t *q = slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET + m;
+						expect[j] = c;
+						prev[j] = atomicCAS((unsigned long long*)q, (unsigned long long)c, (unsigned long long)(c + 1));
+						cas |= 1u << j;
+					}
+				} else if (f >= 0) todo &= ~(1u << j);  // a free slot and no key: absent
+				else adv |= 1u << j;                    // full without the key: the next bucket
+			}
+		}
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			if ((cas >> j & 1) && prev[j] == expect[j]) { hit |= 1u << j; todo &= ~(1u << j); }
+		if (!__any_sync(0xffffffffu, todo != 0)) break;
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			if (todo >> j & 1) {
+				if (adv >> j & 1) { if (++bi[j] == nbk) bi[j] = 0; }
+				bk[j] = load_bucket(slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET);
+			}
+	}
+	return hit;
 }
 
 // ---- K1, fused front end: extraction + table probe.  One thread per 32-position word, persistent
@@ -281,39 +331,7 @@ __global__ void __launch_bounds__(256, 3) k1_fused(const uint64_t *__restrict__ 
 			__syncwarp();
 			my_ev += __popc(vm);
 			if (cap == 0) { pend |= vm << b; continue; }
-			// first look at the 4 home buckets: issue every counter CAS before waiting for any result
-			uint64_t expect[4], prev[4];
-			uint32_t todo = 0, hit = 0; // todo: needs the slow path (next bucket / lost CAS); hit: found
-#pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				expect[j] = prev[j] = 0;
-				if (vm >> j & 1) {
-					int f, m = bucket_match(bk[j], v[j] >> pre, &f);
-					if (m >= 0) {
-						const uint64_t c = bucket_get(bk[j], m);
-						hit |= 1u << j;
-						if ((c & YAKB_MAX_COUNT) != YAKB_MAX_COUNT) {
-							uint64_t *q = slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET + m;
-							expect[j] = c;
-							prev[j] = atomicCAS((unsigned long long*)q, (unsigned long long)c, (unsigned long long)(c + 1));
-						}
-					} else if (f < 0) todo |= 1u << j; // home bucket full without the key: keep probing
-				}
-			}
-#pragma unroll
-			for (int j = 0; j < 4; ++j) if (prev[j] != expect[j]) { todo |= 1u << j; hit &= ~(1u << j); } // lost a race: redo
-			if (__any_sync(0xffffffffu, todo != 0)) {
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					const bool redo = todo >> j & 1;
-					if (__any_sync(0xffffffffu, redo)) {
-						uint64_t *reg = slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap;
-						Bucket bb = bk[j];
-						if (redo && prev[j] != expect[j]) bb = load_bucket(reg + (uint64_t)bi[j] * YAKB_BUCKET);
-						if (probe_inc_warp(reg, nbk, v[j] >> pre, bi[j], bb, redo)) hit |= 1u << j;
-					}
-				}
-			}
+			const uint32_t hit = probe_inc4(slots, cap, nbk, pre, Pmask, v, vm, bi, bk);
 			if (create_new) {
 				pend |= (vm & ~hit) << b;
 #pragma unroll
@@ -353,10 +371,14 @@ __global__ void __launch_bounds__(256, 3) k1_fused(const uint64_t *__restrict__ 
 //      CAS as k1_fused; a miss sets the position's bit in flags[] (pass 1).  n_list = Z zone lists of zcap
 //      entries each (fill counts in zfill[]), or one list (the spill).
 #define YAKB_ZSLICE 2048
-__global__ void __launch_bounds__(256, 3) zone_probe(const uint64_t *__restrict__ zev, const uint32_t *__restrict__ zpos, uint32_t n_list, uint32_t zcap,
+//      zsub = sub-tables per zone when that is at most 8 (0 otherwise, and for the spill list): the last-put times of a
+//      slice's hits are then reduced per sub-table inside the warp - one shared-memory atomic per (warp, slice, sub-table)
+//      instead of one per hit, which in a zone list all fall on the same few counters and serialise.
+template<int MINB>
+__global__ void __launch_bounds__(256, MINB) zone_probe(const uint64_t *__restrict__ zev, const uint32_t *__restrict__ zpos, uint32_t n_list, uint32_t zcap,
                                                     const unsigned int *__restrict__ zfill, int pre, uint32_t Pmask,
                                                     uint64_t *slots, uint32_t cap, int create_new, uint32_t *flags,
-                                                    uint32_t *glob_lput, int smem_lp, unsigned int *work)
+                                                    uint32_t *glob_lput, int smem_lp, unsigned int *work, uint32_t zsub)
 {
 	extern __shared__ uint32_t s_lp[];
 	__shared__ uint32_t s_item;
@@ -376,6 +398,10 @@ __global__ void __launch_bounds__(256, 3) zone_probe(const uint64_t *__restrict_
 		if (start >= nz) continue; // an empty tail slice of this list
 		const uint64_t *ev = zev + (uint64_t)z * zcap;
 		const uint32_t *ep = zpos + (uint64_t)z * zcap;
+		const uint32_t s0 = z * zsub; // first sub-table of the zone
+		uint32_t tm[8];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) tm[i] = 0;
 #pragma unroll 1
 		for (uint32_t g = 0; g < YAKB_ZSLICE / 1024; ++g) { // 4 events per thread at a time, lanes on consecutive entries
 			uint64_t v[4];
@@ -392,48 +418,30 @@ __global__ void __launch_bounds__(256, 3) zone_probe(const uint64_t *__restrict_
 					bk[j] = load_bucket(slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET);
 				}
 			}
-			uint64_t expect[4], prev[4];
-			uint32_t todo = 0, hit = 0;
-#pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				expect[j] = prev[j] = 0;
-				if (vm >> j & 1) {
-					int f, m = bucket_match(bk[j], v[j] >> pre, &f);
-					if (m >= 0) {
-						const uint64_t c = bucket_get(bk[j], m);
-						hit |= 1u << j;
-						if ((c & YAKB_MAX_COUNT) != YAKB_MAX_COUNT) {
-							uint64_t *q = slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET + m;
-							expect[j] = c;
-							prev[j] = atomicCAS((unsigned long long*)q, (unsigned long long)c, (unsigned long long)(c + 1));
-						}
-					} else if (f < 0) todo |= 1u << j;
-				}
-			}
-#pragma unroll
-			for (int j = 0; j < 4; ++j) if (prev[j] != expect[j]) { todo |= 1u << j; hit &= ~(1u << j); }
-			if (__any_sync(0xffffffffu, todo != 0)) {
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					const bool redo = todo >> j & 1;
-					if (__any_sync(0xffffffffu, redo)) {
-						uint64_t *reg = slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap;
-						Bucket bb = bk[j];
-						if (redo && prev[j] != expect[j]) bb = load_bucket(reg + (uint64_t)bi[j] * YAKB_BUCKET);
-						if (probe_inc_warp(reg, nbk, v[j] >> pre, bi[j], bb, redo)) hit |= 1u << j;
-					}
-				}
-			}
+			const uint32_t hit = probe_inc4(slots, cap, nbk, pre, Pmask, v, vm, bi, bk);
 			if (create_new) {
 #pragma unroll
 				for (int j = 0; j < 4; ++j) {
 					if (!(vm >> j & 1)) continue;
 					if (hit >> j & 1) {
 						const uint32_t s = (uint32_t)v[j] & Pmask, t = pos[j] + 1;
-						if (smem_lp) atomicMax(&s_lp[s], t); else atomicMax(&glob_lput[s], t);
+						if (zsub) {
+							const uint32_t sl = s - s0;
+#pragma unroll
+							for (int i = 0; i < 8; ++i) if (sl == (uint32_t)i) tm[i] = max(tm[i], t);
+						} else if (smem_lp) atomicMax(&s_lp[s], t);
+						else atomicMax(&glob_lput[s], t);
 					} else atomicOr(&flags[pos[j] >> 5], 1u << (pos[j] & 31));
 				}
 			}
+		}
+		if (create_new && zsub) {
+#pragma unroll
+			for (int i = 0; i < 8; ++i)
+				if ((uint32_t)i < zsub) { // warp-uniform
+					const uint32_t t = __reduce_max_sync(0xffffffffu, tm[i]);
+					if ((threadIdx.x & 31) == 0 && t) { if (smem_lp) atomicMax(&s_lp[s0 + i], t); else atomicMax(&glob_lput[s0 + i], t); }
+				}
 		}
 	}
 	__syncthreads();
@@ -1332,10 +1340,18 @@ bool Engine::probe_partitioned(uint64_t nwords, int create_new, const uint64_t *
 	const size_t sm1 = smem1 ? (size_t)P * 4 : 0;
 	if (create_new) YAKB_CUDA(cudaMemsetAsync(flags, 0, nwords * 4, stream));
 	{ ProfScope ps("zone_probe", stream);
-	set_smem(zone_probe, sm1);
-	zone_probe<<<nsm * 3, 256, sm1, stream>>>(zev, zpos, Z, zcap, zfill, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 1);
+	const uint32_t zsub = (1u << zshift) <= 8 ? (1u << zshift) : 0;
+	static const int zocc = getenv("YAKB_ZPROBE_OCC") ? atoi(getenv("YAKB_ZPROBE_OCC")) : 3; // resident CTAs per SM (2: no register spills)
+	if (zocc == 2) {
+		set_smem(zone_probe<2>, sm1);
+		zone_probe<2><<<nsm * 2, 256, sm1, stream>>>(zev, zpos, Z, zcap, zfill, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 1, zsub);
+	} else {
+		set_smem(zone_probe<3>, sm1);
+		zone_probe<3><<<nsm * 3, 256, sm1, stream>>>(zev, zpos, Z, zcap, zfill, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 1, zsub);
+	}
 	// the spill list: one more list whose fill count is n_spill
-	if (n_spill) zone_probe<<<nsm * 3, 256, sm1, stream>>>(sp_ev, sp_pos, 1, spill_cap, zfill + Z, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 2);
+	if (n_spill) set_smem(zone_probe<3>, sm1);
+	if (n_spill) zone_probe<3><<<nsm * 3, 256, sm1, stream>>>(sp_ev, sp_pos, 1, spill_cap, zfill + Z, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 2, 0);
 	if (create_new) flag_tilecnt_kernel<<<(uint32_t)ntiles, 256, 0, stream>>>(flags, nwords, tilecnt); }
 	YAKB_CUDA(cudaGetLastError());
 	note_launch(1 + (n_spill ? 1 : 0) + (create_new ? 1 : 0));

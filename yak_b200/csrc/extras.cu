@@ -12,84 +12,171 @@ namespace yakb {
 static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
 
-// bit r of vmask[W] = a k-mer ends at position 32W+r (depends on the invalid mask only); tile counts
-__global__ void __launch_bounds__(256) valid_mask_kernel(const uint32_t *__restrict__ wm, uint64_t nwords, int k,
-                                                         uint32_t *__restrict__ vmask, uint32_t *__restrict__ tilecnt)
+// ---- multi-GPU routing: the hashed k-mers of a rank's reads, in file order, stably grouped by the rank
+//      that owns their sub-table (owner = top lw bits of the sub-table index = hash bits [pre-lw, pre)).
+//
+//      route_tile_kernel: ONE roll.  A CTA takes a tile of 256 words (8192 positions), a thread one word; the thread keeps
+//      its up to 32 hashes in registers, counts them per owner (four 16-bit counters to a u64), a block scan of those packed
+//      counters gives every thread its stable place inside the tile's owner runs, and the tile leaves the SM sorted by
+//      owner (file order inside an owner) as one coalesced copy.  cnt[owner][tile] = events of that owner in the tile.
+//      An exclusive scan over cnt (owner-major) is the final place of every (owner, tile) run;
+//      route_gather_kernel copies the runs there (coalesced reads, runs of ~8192/world events written contiguously).
+#define YAKB_RT_POS 8192
+#define YAKB_RT_MAXW 16
+
+template<bool LONGK>
+__global__ void __launch_bounds__(256, 2) route_tile_kernel(const uint64_t *__restrict__ w2, const uint32_t *__restrict__ wm, uint64_t nwords, int k,
+                                                           int oshift, uint32_t omask, int world, uint64_t *__restrict__ tile_ev,
+                                                           uint32_t *__restrict__ cnt, uint32_t ntiles)
 {
-	__shared__ uint32_t s_cnt;
-	if (threadIdx.x == 0) s_cnt = 0;
-	__syncthreads();
-	const uint64_t W = blockIdx.x * 256ull + threadIdx.x;
+	extern __shared__ __align__(16) uint64_t s_ev[];  // [8192]
+	__shared__ unsigned long long s_w[8][4];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint64_t tile = blockIdx.x;
+	const uint64_t W = tile * 256 + threadIdx.x;
+	uint64_t h[32];
+	uint32_t vm = 0;
 	if (W < nwords) {
-		int l = 0;
-		for (int64_t p = (int64_t)(W * 32) - (k - 1); p < (int64_t)(W * 32); ++p) {
-			if (p < 0) continue;
-			l = (wm[p >> 5] >> (31 - (p & 31)) & 1) ? 0 : l + 1;
-		}
-		const uint32_t cm = wm[W];
-		uint32_t m = 0;
+		Roller<LONGK> ro;
+		ro.init(w2, wm, (int64_t)W, k);
 #pragma unroll
-		for (int r = 0; r < 32; ++r) {
-			l = (cm >> (31 - r) & 1) ? 0 : (l < 64 ? l + 1 : l);
-			if (l >= k) m |= 1u << r;
+		for (int r = 0; r < 32; ++r) { h[r] = 0; if (ro.step(r, h[r])) vm |= 1u << r; }
+	} else {
+#pragma unroll
+		for (int r = 0; r < 32; ++r) h[r] = 0;
+	}
+	// this thread's events per owner, packed
+	unsigned long long a[4] = {0, 0, 0, 0};
+#pragma unroll
+	for (int r = 0; r < 32; ++r)
+		if (vm >> r & 1) {
+			const uint32_t o = (uint32_t)(h[r] >> oshift) & omask;
+			const unsigned long long one = 1ull << (16 * (o & 3));
+#pragma unroll
+			for (int g = 0; g < 4; ++g) if ((o >> 2) == (uint32_t)g) a[g] += one;
 		}
-		vmask[W] = m;
-		if (m) atomicAdd(&s_cnt, __popc(m));
+	// block-wide exclusive scan of the packed counters (fields never carry: a tile holds at most 8192 events)
+	unsigned long long inc[4];
+#pragma unroll
+	for (int g = 0; g < 4; ++g) {
+		inc[g] = a[g];
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc[g], d); if (lane >= d) inc[g] += t; }
+		if (lane == 31) s_w[warp][g] = inc[g];
 	}
 	__syncthreads();
-	if (threadIdx.x == 0) tilecnt[blockIdx.x] = s_cnt;
+	unsigned long long cur[4], tot[4];
+#pragma unroll
+	for (int g = 0; g < 4; ++g) {
+		unsigned long long before = 0, all = 0;
+#pragma unroll
+		for (int w = 0; w < 8; ++w) { const unsigned long long t = s_w[w][g]; if (w < warp) before += t; all += t; }
+		cur[g] = before + inc[g] - a[g];
+		tot[g] = all;
+	}
+	// start of every owner's run inside the tile, added to the thread's place (packed again)
+	uint32_t acc = 0;
+#pragma unroll
+	for (int o = 0; o < YAKB_RT_MAXW; ++o) {
+		cur[o >> 2] += (unsigned long long)acc << (16 * (o & 3));
+		const uint32_t c = (uint32_t)(tot[o >> 2] >> (16 * (o & 3))) & 0xFFFFu;
+		if (threadIdx.x == 0 && o < world) cnt[(uint64_t)o * ntiles + tile] = c;
+		acc += c;
+	}
+	// place, in position order
+#pragma unroll
+	for (int r = 0; r < 32; ++r)
+		if (vm >> r & 1) {
+			const uint32_t o = (uint32_t)(h[r] >> oshift) & omask;
+			const int sh = 16 * (o & 3);
+			uint32_t pos = 0;
+#pragma unroll
+			for (int g = 0; g < 4; ++g) if ((o >> 2) == (uint32_t)g) { pos = (uint32_t)(cur[g] >> sh) & 0xFFFFu; cur[g] += 1ull << sh; }
+			s_ev[pos] = h[r];
+		}
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < acc; i += 256) tile_ev[tile * YAKB_RT_POS + i] = s_ev[i];
 }
 
-__global__ void rank_offsets_kernel(const uint64_t *__restrict__ sorted, uint64_t n, int pre, int lw, int world, uint64_t *off)
+// goff = exclusive scan of cnt (owner-major, world*ntiles + 1 entries)
+__global__ void __launch_bounds__(256) route_gather_kernel(const uint64_t *__restrict__ tile_ev, const uint32_t *__restrict__ goff, uint32_t ntiles,
+                                                           int world, uint64_t *__restrict__ out)
 {
-	int r = threadIdx.x;
-	if (r > world) return;
-	const uint32_t fmask = (1u << lw) - 1;
-	uint64_t lo = 0, hi = n;
-	while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if ((uint32_t)((sorted[mid] >> (pre - lw)) & fmask) < (uint32_t)r) lo = mid + 1; else hi = mid; }
-	off[r] = lo;
+	__shared__ uint32_t s_toff[YAKB_RT_MAXW + 1], s_g[YAKB_RT_MAXW];
+	const uint64_t tile = blockIdx.x;
+	if (threadIdx.x == 0) {
+		uint32_t acc = 0;
+		for (int o = 0; o < world; ++o) {
+			const uint64_t idx = (uint64_t)o * ntiles + tile;
+			s_toff[o] = acc; s_g[o] = goff[idx];
+			acc += goff[idx + 1] - goff[idx];
+		}
+		for (int o = world; o <= YAKB_RT_MAXW; ++o) s_toff[o] = acc;
+	}
+	__syncthreads();
+	const uint32_t T = s_toff[world];
+	for (uint32_t i = threadIdx.x; i < T; i += 256) {
+		int o = 0;
+#pragma unroll
+		for (int q = 1; q < YAKB_RT_MAXW; ++q) if (q < world && s_toff[q] <= i) o = q;
+		out[(uint64_t)s_g[o] + (i - s_toff[o])] = tile_ev[tile * YAKB_RT_POS + i];
+	}
+}
+
+__global__ void route_counts_kernel(const uint32_t *__restrict__ goff, uint32_t ntiles, int world, uint64_t *__restrict__ counts)
+{
+	const int o = threadIdx.x;
+	if (o < world) counts[o] = (uint64_t)goff[(uint64_t)(o + 1) * ntiles] - (uint64_t)goff[(uint64_t)o * ntiles];
+}
+
+// d_counts (device, world entries) receives the events per owner; nothing here waits for the device
+int extract_events_async(const uint8_t *d_asc, uint64_t n, int k, int pre, int world, uint64_t *d_out, uint64_t *d_counts,
+                         cudaStream_t stream, RouteScratch &sc)
+{
+	int lw = 0;
+	while ((1 << lw) < world) ++lw;
+	if ((1 << lw) != world || lw > pre || world > YAKB_RT_MAXW) {
+		fprintf(stderr, "[yakb] ERROR: world size must be a power of two <= %d\n", YAKB_RT_MAXW);
+		return -1;
+	}
+	YAKB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)world * 8, stream));
+	if (n == 0) return 0;
+	if (n >= 0x7FFFFF00ull) { fprintf(stderr, "[yakb] ERROR: chunk too large (positions are 31-bit)\n"); return -1; }
+	const uint64_t nwords = (n + 31) / 32, ntiles = (nwords + 255) / 256;
+	uint64_t *w2 = sc.b[0].as<uint64_t>(packed_words(nwords)) + YAKB_PADW;
+	uint32_t *wm = sc.b[1].as<uint32_t>(packed_words(nwords)) + YAKB_PADW;
+	uint64_t *tile_ev = sc.b[2].as<uint64_t>(ntiles * YAKB_RT_POS);
+	uint32_t *cnt = sc.b[3].as<uint32_t>((uint64_t)world * ntiles + 1);
+	ProfScope ps("extract_route", stream);
+	pack_ascii_kernel<<<cdiv(packed_npad(nwords) + YAKB_PADW, 256), 256, 0, stream>>>(d_asc, n, w2, wm, nwords, packed_npad(nwords));
+	YAKB_CUDA(cudaMemsetAsync(cnt + (uint64_t)world * ntiles, 0, 4, stream));
+	const size_t sm = (size_t)YAKB_RT_POS * 8;
+	if (k >= 32) {
+		YAKB_CUDA(cudaFuncSetAttribute(route_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+		route_tile_kernel<true><<<(uint32_t)ntiles, 256, sm, stream>>>(w2, wm, nwords, k, pre - lw, (uint32_t)world - 1, world, tile_ev, cnt, (uint32_t)ntiles);
+	} else {
+		YAKB_CUDA(cudaFuncSetAttribute(route_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+		route_tile_kernel<false><<<(uint32_t)ntiles, 256, sm, stream>>>(w2, wm, nwords, k, pre - lw, (uint32_t)world - 1, world, tile_ev, cnt, (uint32_t)ntiles);
+	}
+	exclusive_scan_u32(cnt, cnt, (uint64_t)world * ntiles + 1, stream, sc.rs);
+	route_gather_kernel<<<(uint32_t)ntiles, 256, 0, stream>>>(tile_ev, cnt, (uint32_t)ntiles, world, d_out);
+	route_counts_kernel<<<1, 32, 0, stream>>>(cnt, (uint32_t)ntiles, world, d_counts);
+	YAKB_CUDA(cudaGetLastError());
+	Engine::note_launch(4);
+	Prof::units("extract_route", n);
+	return 0;
 }
 
 int extract_events(const uint8_t *d_asc, uint64_t n, int k, int pre, int world, uint64_t *d_out, uint64_t *counts,
                    cudaStream_t stream, RouteScratch &sc)
 {
 	for (int r = 0; r < world; ++r) counts[r] = 0;
-	if (n == 0) return 0;
-	const uint64_t nwords = (n + 31) / 32, ntiles = (nwords + 255) / 256;
-	uint64_t *w2 = sc.b[0].as<uint64_t>(packed_words(nwords)) + YAKB_PADW;
-	uint32_t *wm = sc.b[1].as<uint32_t>(packed_words(nwords)) + YAKB_PADW;
-	uint32_t *vmask = sc.b[2].as<uint32_t>(nwords);
-	uint32_t *tilecnt = sc.b[3].as<uint32_t>(ntiles + 1), *tileoff = sc.b[4].as<uint32_t>(ntiles + 1);
-	uint32_t *ppos = sc.b[5].as<uint32_t>(n);
-	pack_ascii_kernel<<<cdiv(packed_npad(nwords) + YAKB_PADW, 256), 256, 0, stream>>>(d_asc, n, w2, wm, nwords, packed_npad(nwords));
-	valid_mask_kernel<<<(uint32_t)ntiles, 256, 0, stream>>>(wm, nwords, k, vmask, tilecnt);
-	YAKB_CUDA(cudaMemsetAsync(tilecnt + ntiles, 0, 4, stream));
-	RadixScratch &rs = sc.rs;
-	exclusive_scan_u32(tilecnt, tileoff, ntiles + 1, stream, rs);
-	uint32_t n_ev = 0;
-	YAKB_CUDA(cudaMemcpyAsync(&n_ev, tileoff + ntiles, 4, cudaMemcpyDeviceToHost, stream));
+	uint64_t *d_counts = (uint64_t*)sc.b[4].need((size_t)std::max(world, 1) * 8);
+	const int rc = extract_events_async(d_asc, n, k, pre, world, d_out, d_counts, stream, sc);
+	if (rc != 0 || n == 0) return rc;
+	YAKB_CUDA(cudaMemcpyAsync(counts, d_counts, (size_t)world * 8, cudaMemcpyDeviceToHost, stream));
 	YAKB_CUDA(cudaStreamSynchronize(stream));
-	if (n_ev == 0) return 0;
-	int lw = 0;
-	while ((1 << lw) < world) ++lw;
-	if ((1 << lw) != world || lw > pre) { fprintf(stderr, "[yakb] ERROR: world size must be a power of two <= 2^pre\n"); return -1; }
-	uint64_t *ev = lw ? sc.b[7].as<uint64_t>(n_ev) : d_out;
-	if (k >= 32) compact_fused<true><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, vmask, tileoff, 0, 0, ev, ppos);
-	else compact_fused<false><<<(uint32_t)ntiles, 256, 0, stream>>>(w2, wm, nwords, k, vmask, tileoff, 0, 0, ev, ppos);
-	YAKB_CUDA(cudaGetLastError());
-	if (lw == 0) { counts[0] = n_ev; YAKB_CUDA(cudaStreamSynchronize(stream)); return 0; }
-	// owner rank = top lw bits of the sub-table index = hash bits [pre-lw, pre); one stable pass on them
-	uint64_t *alt = sc.b[6].as<uint64_t>(n_ev);
-	if (radix_sort_pairs(ev, nullptr, d_out, nullptr, alt, nullptr, n_ev, pre - lw, pre, stream, rs) != 0)
-		YAKB_CUDA(cudaMemcpyAsync(d_out, alt, (size_t)n_ev * 8, cudaMemcpyDeviceToDevice, stream));
-	// per-rank counts: lower bounds in the sorted owner field (host binary search over device data
-	// would sync per probe; a tiny kernel does all ranks at once)
-	uint64_t *d_off = (uint64_t*)sc.b[4].need((world + 1) * 8);
-	rank_offsets_kernel<<<1, 64, 0, stream>>>(d_out, n_ev, pre, lw, world, d_off);
-	std::vector<uint64_t> off(world + 1);
-	YAKB_CUDA(cudaMemcpyAsync(off.data(), d_off, (world + 1) * 8, cudaMemcpyDeviceToHost, stream));
-	YAKB_CUDA(cudaStreamSynchronize(stream));
-	for (int r = 0; r < world; ++r) counts[r] = off[r + 1] - off[r];
+	Prof::resolve();
 	return 0;
 }
 

@@ -30,6 +30,18 @@ class GpuBackend:
             raise RuntimeError("yakb_ch_init_shard failed")
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.stats = (C.c_uint64 * 4)()
+        self._out = self._recv = None          # grow-only exchange buffers: NCCL sees the same addresses every chunk
+
+    def _buf(self, name: str, n: int) -> torch.Tensor:
+        cur = getattr(self, name)
+        if cur is None or cur.numel() < n:
+            setattr(self, name, None)
+            cur = torch.empty(int(n * 1.1) + 1024, dtype=torch.int64, device=self.device)
+            setattr(self, name, cur)
+        return cur
+
+    def recv_buffer(self, n: int) -> torch.Tensor:
+        return self._buf("_recv", n)[:n]
 
     def to_device(self, asc: bytes | np.ndarray | torch.Tensor) -> torch.Tensor:
         if isinstance(asc, torch.Tensor):
@@ -38,16 +50,16 @@ class GpuBackend:
         return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
 
     def extract_route(self, asc: torch.Tensor):
+        """hashed k-mers of `asc` grouped by owner rank (file order inside a group) and the events per owner as a DEVICE
+        tensor: nothing here waits for the GPU (the host learns the counts once, from the all-gather of the exchange)"""
         n = asc.numel()
-        out = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
-        counts = (C.c_uint64 * self.world)()
-        torch.cuda.current_stream().synchronize()
-        rc = self.lib.yakb_extract_route_dev(asc.data_ptr(), n, self.k, self.pre, self.world, out.data_ptr(), counts,
-                                             torch.cuda.current_stream().cuda_stream)
+        out = self._buf("_out", max(n, 1))
+        counts = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        rc = self.lib.yakb_extract_route_async(asc.data_ptr(), n, self.k, self.pre, self.world, out.data_ptr(), counts.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream)
         if rc != 0:
-            raise RuntimeError("yakb_extract_route_dev failed")
-        cl = [int(c) for c in counts]
-        return out[:sum(cl)], cl
+            raise RuntimeError("yakb_extract_route_async failed")
+        return out, counts
 
     def count_events(self, ev: torch.Tensor, create_new: int) -> int:
         torch.cuda.current_stream().synchronize()
@@ -71,6 +83,7 @@ class GpuBackend:
         return data
 
     def close(self):
+        self._out = self._recv = None
         if self.h:
             self.lib.yak_ch_destroy(self.h)
             self.h = None
@@ -85,24 +98,60 @@ class ShardedCounter:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.events = 0
+        self._a2a_events, self._a2a_total, self.a2a_bytes = [], 0.0, 0
 
     def count_chunk(self, asc_local, create_new: int = 1) -> int:
         """asc_local: this rank's contiguous slice of the chunk (ASCII, any non-ACGTU byte separates reads)."""
-        ev, counts = self.b.extract_route(self.b.to_device(asc_local))
+        import os
+        import time
+        dbg = self.rank == 0 and os.environ.get("YAKB_DIST_TIMING") == "1"
+        t = [time.time()]
+
+        def mark():
+            if dbg:
+                torch.cuda.synchronize()
+                t.append(time.time())
+        ev, c_out = self.b.extract_route(self.b.to_device(asc_local))
+        mark()
         if self.world == 1:
-            recv = ev
+            recv = ev[:int(c_out[0])]
         else:
             dev = ev.device
-            c_out = torch.tensor(counts, dtype=torch.int64, device=dev)
-            c_in = torch.empty_like(c_out)
-            dist.all_to_all_single(c_in, c_out, group=self.group)          # tiny count exchange
-            in_splits = [int(x) for x in c_in.tolist()]
-            recv = torch.empty(sum(in_splits), dtype=torch.int64, device=dev)
-            dist.all_to_all_single(recv, ev.contiguous(), output_split_sizes=in_splits, input_split_sizes=counts,
+            cuda = dev.type == "cuda"
+            # every rank's per-owner counts in one small all-gather; its copy to the host is the only point of the
+            # exchange where the host waits for the device.  m[s][d] = events rank s sends to rank d
+            allc = torch.empty(self.world * self.world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allc, c_out.contiguous(), group=self.group)
+            m = allc.view(self.world, self.world).cpu()
+            mark()
+            out_splits = [int(x) for x in m[self.rank].tolist()]
+            in_splits = [int(x) for x in m[:, self.rank].tolist()]
+            recv = self.b.recv_buffer(sum(in_splits)) if hasattr(self.b, "recv_buffer") else torch.empty(sum(in_splits), dtype=torch.int64, device=dev)
+            if cuda:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            dist.all_to_all_single(recv, ev[:sum(out_splits)], output_split_sizes=in_splits, input_split_sizes=out_splits,
                                    group=self.group)                        # the one payload all-to-all of the chunk
+            if cuda:
+                e1.record()
+                self._a2a_events.append((e0, e1))
+                self.a2a_bytes += 8 * (sum(out_splits) - out_splits[self.rank])
+            mark()
         n = self.b.count_events(recv, create_new)
+        mark()
+        if dbg:
+            import sys
+            print("[T::count_chunk] extract %.1f ms, counts %.1f ms, all-to-all %.1f ms, count %.1f ms (%d events in)" %
+                  tuple([(b - a) * 1e3 for a, b in zip(t, t[1:])] + [recv.numel()]), file=sys.stderr)
         self.events += n
         return n
+
+    def a2a_ms(self) -> float:
+        """device time of the payload all-to-alls so far (call after a synchronize)"""
+        t = sum(a.elapsed_time(b) for a, b in self._a2a_events)
+        self._a2a_events.clear()
+        self._a2a_total += t
+        return self._a2a_total
 
     def second_pass_prepare(self):
         """main.c:55-56 on every shard."""
@@ -216,21 +265,25 @@ def _count_file_sharded_pool(fn, sc: ShardedCounter, k, create_new, batch_bases,
     if G > 1:
         dist.broadcast(where, 0, group=group)     # one decision for the node
     stage_dir = "/dev/shm" if int(where[0]) else tempfile.gettempdir()
-    stage = os.path.join(stage_dir, "yakb_stage_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getuid()))
-    mm = _STAGES.get((stage, cap))            # mapped (and page-locked for DMA) once per process, reused by later passes
+    mm = _STAGES.get((id(group), cap))        # mapped (and page-locked for DMA) once per process, reused by later passes
     fresh = torch.tensor([0 if mm is not None else 1], dtype=torch.int64, device=dev)
     if G > 1:
         dist.all_reduce(fresh, op=dist.ReduceOp.MAX, group=group)
     if int(fresh[0]):
+        # rank 0 creates the file under a fresh random name (O_EXCL, no symlink is followed) and tells the others:
+        # two jobs of one user can never map each other's staging buffer
+        name = [None]
         if r == 0:
-            with open(stage, "wb") as f:
-                f.truncate(2 * cap)
+            fd, name[0] = tempfile.mkstemp(prefix="yakb_stage_", dir=stage_dir)
+            os.ftruncate(fd, 2 * cap)
+            os.close(fd)
         if G > 1:
-            dist.barrier(group=group)
+            dist.broadcast_object_list(name, 0, group=group)
+        stage = name[0]
         mm = np.memmap(stage, dtype=np.uint8, mode="r+", shape=(2 * cap,))
         if dev.type == "cuda":
             torch.cuda.cudart().cudaHostRegister(mm.ctypes.data, 2 * cap, 0)   # best effort: pageable copies work too
-        _STAGES[(stage, cap)] = mm
+        _STAGES[(id(group), cap)] = mm
         if G > 1:
             dist.barrier(group=group)
         if r == 0:
@@ -272,7 +325,7 @@ def _count_file_sharded_pool(fn, sc: ShardedCounter, k, create_new, batch_bases,
 
 
 def count_file_sharded(fn: str, backend, records_per_chunk: int = 1 << 20, k: int = 31, two_pass: bool = False,
-                       fn2: str | None = None, group=None, batch_bases: int = 0) -> ShardedCounter:
+                       fn2: str | None = None, group=None, batch_bases: int = 0, timings: dict | None = None) -> ShardedCounter:
     """`yak count` of one shared file on all ranks of ONE node.  batch_bases > 0: plain files are parsed once by rank 0's
     parser pool into shared memory, each rank taking its contiguous part of every batch (the fast path, bench.py's e2e
     at N GPUs); otherwise, and for gzip / stdin, every rank walks the file record by record and keeps its slice of
@@ -308,7 +361,14 @@ def count_file_sharded(fn: str, backend, records_per_chunk: int = 1 << 20, k: in
                 break
         L.yakb_fastx_close(rd)
 
+    import time
+    t0 = time.time()
     one_pass(fn, 1)
+    if timings is not None:                   # bench.py's e2e: pass 1 up to the result every rank reads back
+        timings["distinct_after_pass1"] = sc.total_distinct()
+        if sc._dev().type == "cuda":
+            torch.cuda.synchronize()
+        timings["pass1_seconds"] = time.time() - t0
     if two_pass:
         sc.second_pass_prepare()
         one_pass(fn2 or fn, 0)
