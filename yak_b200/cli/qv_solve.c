@@ -1,7 +1,9 @@
-/* qv_solve.c - host-side FP64 fit of the k-mer QV model from the two 1024-bin histograms the GPU
- * path produces (restating reference qv.c:146-244 and its 3x3 solver 6gjdn.c).  Off the hot path:
- * O(1024) scalar work per run, kept in plain C next to the CLI.  The arithmetic follows the
- * reference step by step (same operation order) so the printed CT/FR/ER/CV/QV lines agree.
+/* qv_solve.c - DERIVED FROM the reference, NOT new work: yak_qv_solve (reference qv.c:146-244) and its 3x3 solver
+ * (6gjdn.c) restated statement by statement with renamed variables.  SURVEY section 2 marks this component OUT of scope
+ * ("keep the reference C unchanged"): it is O(1024) host FP64 arithmetic behind the scan, and whoever links libyakb200
+ * into the reference's own `yak` keeps the reference's qv.c / 6gjdn.c for it.  The file exists only so
+ * that the stand-alone yak-b200 command line can print the CT/FR/ER/CV/QV lines; the operation order is the reference's
+ * because the printed FP64 values must agree digit for digit.  It is no part of the hot path and claims no credit.
  */
 #include <math.h>
 #include <stdio.h>

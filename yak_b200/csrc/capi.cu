@@ -8,6 +8,7 @@
 #include "../../include/yak_b200.h"
 #include "engine.cuh"
 #include "extras.cuh"
+#include "ingest.cuh"
 #include "fastx.h"
 #include "fastx_par.h"
 #include "yakfile.h"
@@ -21,6 +22,7 @@
 #include <math.h>
 #include <algorithm>
 #include <map>
+#include <tuple>
 #include <mutex>
 #include <sys/stat.h>
 #include <sys/mman.h>
@@ -59,6 +61,7 @@ struct ChBox {
 	std::vector<yak_bf_t> filters;
 	std::mutex mu;
 	DBuf d_in, d_in2, d_aux, d_aux2;
+	IngestScratch ing;                  // the device-side text ingest of yak_count (csrc/ingest.cu)
 	cudaStream_t copy_stream = nullptr; // host->device copies of yak_count batches, overlapping the kernels
 };
 static const uint32_t kMagic = 0x59414B42; // "YAKB"
@@ -264,6 +267,7 @@ extern "C" void yak_ch_destroy(yak_ch_t *h) // htab.c:41-49
 	free(b->pub.h);
 	if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
 	b->d_in.release(); b->d_in2.release(); b->d_aux.release(); b->d_aux2.release();
+	b->ing.release();
 	b->magic = 0;
 	delete b;
 }
@@ -429,14 +433,14 @@ extern "C" void yak_ch_tighten(yak_ch_t *h)
 // Sub-table ranges [s0, s1) whose key totals stay below `max_keys` (one sub-table at least): the slices in which
 // a table is brought to the host.  A fixed 1024 sub-tables was the whole table at -p10, i.e. tens of gigabytes
 // of host memory and more than 2^31 events in one count_events() call for human-size assemblies.
-static std::vector<int> slice_bounds(Engine *e, uint64_t max_keys = 1ull << 28)
+static std::vector<int> slice_bounds(Engine *e, uint64_t max_keys = 1ull << 28, int max_sub = 1024)
 {
 	std::vector<uint32_t> z;
 	e->sizes(z);
 	std::vector<int> b(1, 0);
 	uint64_t acc = 0;
 	for (int s = 0; s < e->P; ++s) {
-		if (s > b.back() && (acc + z[s] > max_keys || s - b.back() >= 1024)) { b.push_back(s); acc = 0; }
+		if (s > b.back() && (acc + z[s] > max_keys || s - b.back() >= max_sub)) { b.push_back(s); acc = 0; }
 		acc += z[s];
 	}
 	if (e->P > b.back()) b.push_back(e->P);
@@ -570,21 +574,30 @@ template<class Sink> static void serialise_engine(ChBox *b, Engine *eng, Sink &&
 		sink(t, 12);
 	}
 	double t_lay = 0, t_sink = 0;
-	LayoutOut lo; // one for all steps: Engine::layout resets it, and its key array (gigabytes) keeps its pages
-	const std::vector<int> bounds = slice_bounds(eng, 1ull << 30);
+	// two buffers: while the device rebuilds the layout of slice i+1, a writer thread hands slice i to the sink (the file)
+	LayoutOut lo[2]; // Engine::layout resets them, and their key arrays (gigabytes) keep their pages
+	const std::vector<int> bounds = slice_bounds(eng, 1ull << 28, 512);
+	std::thread writer;
+	struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_on_unwind{writer};
 	for (size_t bi = 0; bi + 1 < bounds.size(); ++bi) {
 		const int s0 = bounds[bi], s1 = bounds[bi + 1];
+		LayoutOut &cur = lo[bi & 1]; // the writer, if any, still reads the other one
 		double t0 = wall_now();
-		eng->layout(s0, s1, lo, true);
-		double t1 = wall_now();
-		for (int s = s0; s < s1; ++s) {
-			uint32_t u[2] = {lo.cap[s - s0], lo.size[s - s0]};
-			sink(u, 8);
-			if (u[1]) sink(lo.keys.data() + lo.off[s - s0], (size_t)u[1] * 8);
-		}
-		t_lay += t1 - t0; t_sink += wall_now() - t1;
+		eng->layout(s0, s1, cur, true);
+		t_lay += wall_now() - t0;
+		if (writer.joinable()) writer.join();
+		writer = std::thread([&sink, &cur, &t_sink, s0, s1] {
+			const double tw = wall_now();
+			for (int s = s0; s < s1; ++s) {
+				uint32_t u[2] = {cur.cap[s - s0], cur.size[s - s0]};
+				sink(u, 8);
+				if (u[1]) sink(cur.keys.data() + cur.off[s - s0], (size_t)u[1] * 8);
+			}
+			t_sink += wall_now() - tw;
+		});
 	}
-	if (timing_on()) fprintf(stderr, "[T::serialise] layout %.3f s, sink %.3f s\n", t_lay, t_sink);
+	if (writer.joinable()) writer.join();
+	if (timing_on()) fprintf(stderr, "[T::serialise] layout %.3f s, sink %.3f s (overlapped)\n", t_lay, t_sink);
 }
 
 extern "C" int yak_ch_dump(const yak_ch_t *h, const char *fn)
@@ -1033,6 +1046,137 @@ static void multi_batch(ChBox *b, const uint8_t *host, size_t n, int create_new)
 	for (int r = 0; r < G; ++r) b->pub.tot += n_new[r];
 }
 
+// ---- yak_count with the text parsed on the device (csrc/ingest.cu).  For plain files in the strict 4-line FASTQ / 2-line
+//      FASTA layout the host does nothing but move bytes: a few threads copy the next batch of the memory-mapped file into
+//      page-locked memory and on to the GPU while the GPU turns the previous batch into the dense base stream (validating
+//      the layout of every record) and counts it.  Batches are cut where a record starts; that cut is only a guess (a line
+//      that starts with the marker and, for FASTQ, is followed two lines later by a '+' line) - the device check decides.
+//      Returns 0 = the whole file was counted; 1 = the layout does not hold and NOTHING was counted (the caller takes the host
+//      parser); 2 = the layout broke after batches had been counted (the caller must start the pass over).
+namespace {
+struct FileId {
+	dev_t dev; ino_t ino; off_t size; int64_t mtime_ns;
+	bool operator<(const FileId &o) const { return std::tie(dev, ino, size, mtime_ns) < std::tie(o.dev, o.ino, o.size, o.mtime_ns); }
+};
+std::mutex g_strict_mu;
+std::map<FileId, bool> g_strict_files; // files a whole pass went through the device check (main.c:57 reads the same file again)
+FileId file_id(const struct stat &st) { return FileId{st.st_dev, st.st_ino, st.st_size, (int64_t)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec}; }
+}
+
+// YAKB_GPU_INGEST: 0 = never, 1 = whenever the file qualifies (tests), unset = files of at least 256 MB
+static int gpu_ingest_mode() { static int v = -2; if (v == -2) { const char *e = getenv("YAKB_GPU_INGEST"); v = e ? atoi(e) : -1; } return v; }
+
+// the last record start at or before `pos` (and behind `lo`), or `lo` when the window holds none
+static uint64_t record_start_before(const uint8_t *m, uint64_t lo, uint64_t pos, uint64_t size, int lpr, uint8_t marker)
+{
+	if (pos >= size) return size;
+	for (uint64_t p = pos; p > lo; --p) {
+		if (m[p - 1] != '\n' || m[p] != marker) continue;
+		if (lpr == 2) return p;
+		const uint8_t *e1 = (const uint8_t*)memchr(m + p, '\n', size - p);
+		if (!e1) continue;
+		const uint8_t *e2 = (const uint8_t*)memchr(e1 + 1, '\n', size - (uint64_t)(e1 + 1 - m));
+		if (!e2 || (uint64_t)(e2 + 1 - m) >= size) continue;
+		if (e2[1] == '+') return p; // a quality line that starts with '@' is followed two lines later by bases, not by '+'
+	}
+	return lo;
+}
+
+static void parallel_copy(uint8_t *dst, const uint8_t *src, size_t n, int threads)
+{
+	if (n < (8u << 20) || threads <= 1) { memcpy(dst, src, n); return; }
+	std::vector<std::thread> th;
+	for (int t = 0; t < threads; ++t) {
+		const size_t a = n * (size_t)t / threads, e = n * (size_t)(t + 1) / threads;
+		th.emplace_back([=] { memcpy(dst + a, src + a, e - a); });
+	}
+	for (auto &t : th) t.join();
+}
+
+static int count_gpu_ingest(yak_ch_t *h, const char *src, const struct stat &st, int create_new)
+{
+	StageTimer tm("yak_count(device ingest)");
+	ChBox *b = box_of(h);
+	std::lock_guard<std::mutex> lk(b->mu);
+	const uint64_t size = (uint64_t)st.st_size;
+	const int fd = open(src, O_RDONLY);
+	if (fd < 0) return 1;
+	const uint8_t *m = (const uint8_t*)mmap(nullptr, size, PROT_READ, MAP_SHARED, fd, 0);
+	close(fd);
+	if (m == MAP_FAILED) return 1;
+	struct Unmap { const uint8_t *p; uint64_t n; ~Unmap() { munmap((void*)p, n); } } unmap{m, size};
+	madvise((void*)m, size, MADV_SEQUENTIAL);
+	const uint8_t marker = m[0];
+	const int lpr = marker == '@' ? 4 : marker == '>' ? 2 : 0;
+	if (lpr == 0 || m[size - 1] != '\n') return 1;
+	// raw bytes per batch: ~1/32 of the file, between 128 MB and 1.5 GB (the dense stream of a batch must stay below 2^31 bytes)
+	uint64_t B = std::min<uint64_t>(std::max<uint64_t>(size / 32, 128ull << 20), 1536ull << 20);
+	if (const char *e = getenv("YAKB_INGEST_BATCH")) if (atoll(e) > 0) B = (uint64_t)atoll(e);
+	B = std::min<uint64_t>(B, size);
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (!b->copy_stream) YAKB_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+	uint8_t *pinned[2] = {nullptr, nullptr};
+	size_t pinned_cap[2] = {0, 0};
+	struct Release { uint8_t **p; size_t *c; ~Release() { for (int i = 0; i < 2; ++i) g_pinned.put(p[i], c[i]); } } release{pinned, pinned_cap};
+	auto ensure_pinned = [&](int i, size_t bytes) {
+		if (pinned_cap[i] < bytes) { g_pinned.put(pinned[i], pinned_cap[i]); pinned[i] = nullptr; pinned_cap[i] = 0; pinned[i] = g_pinned.get(bytes, &pinned_cap[i]); }
+	};
+	const int cthreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+	DBuf *d_raw[2] = {&b->d_in, &b->d_in2};
+	struct Batch { uint64_t a = 0, e = 0; std::string err; };
+	Batch batch[2];
+	auto produce = [&](int slot, uint64_t a) { // [a, e): whole records, about B bytes (one record at least)
+		Batch &t = batch[slot];
+		t = Batch();
+		t.a = a;
+		try {
+			cudaSetDevice(dev);
+			const uint64_t e = a + B >= size ? size : record_start_before(m, a, a + B, size, lpr, marker);
+			if (e <= a) { t.err = "a record longer than a batch"; return; } // a chromosome on one line: the host parser's business
+			t.e = e;
+			const uint64_t n = e - a;
+			ensure_pinned(slot, n + 4096);
+			parallel_copy(pinned[slot], m + a, n, cthreads);
+			uint8_t *d = d_raw[slot]->as<uint8_t>(n + 64);
+			YAKB_CUDA(cudaMemcpyAsync(d, pinned[slot], n, cudaMemcpyHostToDevice, b->copy_stream));
+			YAKB_CUDA(cudaStreamSynchronize(b->copy_stream));
+		} catch (const std::exception &ex) { t.err = ex.what(); }
+	};
+	int slot = 0, n_batches = 0;
+	double t_dev = 0, t_wait = 0;
+	produce(0, 0);
+	for (;;) {
+		Batch cur = batch[slot];
+		if (!cur.err.empty()) { if (cur.err[0] == 'a') return n_batches ? 2 : 1; throw CudaError(cur.err); }
+		std::thread producer;
+		if (cur.e < size) producer = std::thread(produce, slot ^ 1, cur.e);
+		struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_on_unwind{producer};
+		const uint64_t n = cur.e - cur.a;
+		const double td = wall_now();
+		uint8_t *dense = b->d_aux.as<uint8_t>(n + 64);
+		unsigned long long *d_res = b->d_aux2.as<unsigned long long>(4), res[3] = {0, 0, 0};
+		if (ingest_strict((const uint8_t*)d_raw[slot]->p, n, lpr, dense, d_res, b->eng->stream, b->ing) != 0) return n_batches ? 2 : 1;
+		YAKB_CUDA(cudaMemcpyAsync(res, d_res, sizeof(res), cudaMemcpyDeviceToHost, b->eng->stream));
+		YAKB_CUDA(cudaStreamSynchronize(b->eng->stream));
+		if (res[0] != 0 || res[1] >= 0x7FFFFF00ull) {
+			if (yak_verbose >= 3) fprintf(stderr, "[M::%s] '%s' is not in the strict %d-line layout (check %llx at batch %d): using the host parser\n", __func__, src, lpr, res[0], n_batches + 1);
+			return n_batches ? 2 : 1;
+		}
+		run_ascii_dev(b, dense, res[1], create_new, nullptr);
+		t_dev += wall_now() - td; ++n_batches;
+		if (timing_on()) fprintf(stderr, "[T::yak_count] batch %d: %llu bytes of text, %llu of bases, device %.4f s\n", n_batches, (unsigned long long)n, res[1], wall_now() - td);
+		fprintf(stderr, "[M::%s::%.3f*%.2f] processed %d sequences; %ld distinct k-mers in the hash table\n", "count_impl",
+		        wall_now() - g_t0, cpu_now() / (wall_now() - g_t0 + 1e-9), (int)(res[2] / lpr), (long)h->tot);
+		{ const double tw = wall_now(); if (producer.joinable()) producer.join(); t_wait += wall_now() - tw; }
+		if (cur.e >= size) break;
+		slot ^= 1;
+	}
+	{ std::lock_guard<std::mutex> g(g_strict_mu); g_strict_files[file_id(st)] = true; }
+	if (timing_on()) fprintf(stderr, "[T::yak_count] device ingest: %d batches, device %.3f s, waiting for the copies %.3f s\n", n_batches, t_dev, t_wait);
+	return 0;
+}
+
 static yak_ch_t *count_impl(const char *fn, const yak_copt_t *opt, yak_ch_t *h0, int ref_workers);
 extern "C" yak_ch_t *yak_count(const char *fn, const yak_copt_t *opt, yak_ch_t *h0) { return count_impl(fn, opt, h0, 3); } // count.c:162
 
@@ -1062,6 +1206,27 @@ static yak_ch_t *count_impl(const char *fn, const yak_copt_t *opt, yak_ch_t *h0,
 		                                          : yak_ch_init(opt->k, opt->pre, opt->bf_n_hash, opt->bf_shift);
 	}
 	if (!h) return 0;
+	// Large plain files in the strict FASTQ / FASTA layout are parsed on the device (count_gpu_ingest above).  A counting-only
+	// pass (h0 given: counts cannot be taken back) goes that way only for a file an earlier pass of this process has checked.
+	{
+		struct stat sti;
+		const int gi = gpu_ingest_mode();
+		if (par && gi != 0 && box_of(h)->shards.empty() && stat(src, &sti) == 0 && S_ISREG(sti.st_mode) && sti.st_size > 0 &&
+		    (gi == 1 || sti.st_size >= (256ll << 20))) {
+			bool known = false;
+			{ std::lock_guard<std::mutex> g(g_strict_mu); known = g_strict_files.count(file_id(sti)) != 0; }
+			if (!h0 || known) {
+				const int rc = count_gpu_ingest(h, src, sti, h0 == 0);
+				if (rc == 0) return h;
+				if (rc == 2) {
+					if (h0) { fprintf(stderr, "[yakb] FATAL: '%s' changed while it was being counted\n", src); abort(); }
+					yak_ch_destroy(h); // our own table: start the pass over with the host parser
+					h = yak_ch_init(opt->k, opt->pre, opt->bf_n_hash, opt->bf_shift);
+					if (!h) return 0;
+				}
+			}
+		}
+	}
 	ChBox *b = box_of(h);
 	std::lock_guard<std::mutex> lk(b->mu);
 	const bool multi = !b->shards.empty();

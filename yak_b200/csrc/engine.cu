@@ -366,14 +366,44 @@ __global__ void __launch_bounds__(256, 3) k1_fused(const uint64_t *__restrict__ 
 //      Counter updates commute, and the pending flag / last-put bookkeeping are per position, so the order in
 //      which events reach the table is free.
 //
-//      zone_probe: persistent CTAs take slices of 2048 events from a global work counter, in zone order, so
+//      zone_probe: persistent CTAs take slices of YAKB_ZSLICE events from a global work counter, in zone order, so
 //      at any moment the whole grid works on one or two zones.  Per event the same bucket probe + counter
 //      CAS as k1_fused; a miss sets the position's bit in flags[] (pass 1).  n_list = Z zone lists of zcap
 //      entries each (fill counts in zfill[]), or one list (the spill).
-#define YAKB_ZSLICE 2048
+//      The kernel is bound by memory latency (ncu: long-scoreboard stalls, 20 % issue slots used), so it runs one group
+//      of 1024 events ahead of itself: while a group is probed, the next group's events are already in registers and
+//      their home buckets on the way into L2 (prefetch.global.L2), across slice boundaries too - thread 0 fetches the
+//      CTA's next work item a slice early.
 //      zsub = sub-tables per zone when that is at most 8 (0 otherwise, and for the spill list): the last-put times of a
 //      slice's hits are then reduced per sub-table inside the warp - one shared-memory atomic per (warp, slice, sub-table)
 //      instead of one per hit, which in a zone list all fall on the same few counters and serialise.
+#define YAKB_ZSLICE 4096
+#define YAKB_ZGROUPS (YAKB_ZSLICE / 1024)
+struct ZGroup { uint64_t v[4]; uint32_t pos[4]; uint32_t vm; };
+
+__device__ __forceinline__ void zone_fetch(ZGroup &q, uint64_t item, uint32_t g, uint64_t n_items, uint32_t spz, uint32_t zcap,
+                                           const uint64_t *__restrict__ zev, const uint32_t *__restrict__ zpos, const unsigned int *__restrict__ zfill,
+                                           int pre, uint32_t Pmask, const uint64_t *slots, uint32_t cap, uint32_t nbk)
+{
+	q.vm = 0;
+	if (item >= n_items) return;
+	const uint32_t z = (uint32_t)(item / spz), sl = (uint32_t)(item % spz);
+	const uint32_t nz = min(zfill[z], zcap), start = sl * YAKB_ZSLICE + g * 1024;
+	const uint64_t *ev = zev + (uint64_t)z * zcap;
+	const uint32_t *ep = zpos + (uint64_t)z * zcap;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const uint32_t i = start + j * 256 + threadIdx.x;
+		q.v[j] = 0; q.pos[j] = 0;
+		if (i < nz) {
+			q.v[j] = ev[i]; q.pos[j] = ep[i];
+			q.vm |= 1u << j;
+			const uint64_t *bp = slots + (uint64_t)((uint32_t)q.v[j] & Pmask) * cap + (uint64_t)tab_home(q.v[j] >> pre, nbk) * YAKB_BUCKET;
+			asm volatile("prefetch.global.L2 [%0];" :: "l"(bp));
+		}
+	}
+}
+
 template<int MINB>
 __global__ void __launch_bounds__(256, MINB) zone_probe(const uint64_t *__restrict__ zev, const uint32_t *__restrict__ zpos, uint32_t n_list, uint32_t zcap,
                                                     const unsigned int *__restrict__ zfill, int pre, uint32_t Pmask,
@@ -381,57 +411,57 @@ __global__ void __launch_bounds__(256, MINB) zone_probe(const uint64_t *__restri
                                                     uint32_t *glob_lput, int smem_lp, unsigned int *work, uint32_t zsub)
 {
 	extern __shared__ uint32_t s_lp[];
-	__shared__ uint32_t s_item;
+	__shared__ uint32_t s_item[2];
 	const uint32_t P = Pmask + 1, nbk = cap / YAKB_BUCKET;
 	if (smem_lp) for (uint32_t i = threadIdx.x; i < P; i += 256) s_lp[i] = 0;
 	// slices per list; a single list (the spill) is cut by its actual fill, which is usually zero
 	const uint32_t spz = ((n_list == 1 ? min(zfill[0], zcap) : zcap) + YAKB_ZSLICE - 1) / YAKB_ZSLICE;
 	const uint64_t n_items = (uint64_t)n_list * spz;
-	for (;;) {
-		__syncthreads();
-		if (threadIdx.x == 0) s_item = atomicAdd(work, 1u);
-		__syncthreads();
-		const uint64_t item = s_item;
-		if (item >= n_items) break;
-		const uint32_t z = (uint32_t)(item / spz), sl = (uint32_t)(item % spz);
-		const uint32_t nz = min(zfill[z], zcap), start = sl * YAKB_ZSLICE;
-		if (start >= nz) continue; // an empty tail slice of this list
-		const uint64_t *ev = zev + (uint64_t)z * zcap;
-		const uint32_t *ep = zpos + (uint64_t)z * zcap;
-		const uint32_t s0 = z * zsub; // first sub-table of the zone
+	if (threadIdx.x == 0) s_item[0] = atomicAdd(work, 1u);
+	__syncthreads();
+	uint64_t item = s_item[0];
+	ZGroup nx;
+	zone_fetch(nx, item, 0, n_items, spz, zcap, zev, zpos, zfill, pre, Pmask, slots, cap, nbk);
+	for (uint32_t it = 0; item < n_items; ++it) {
+		if (threadIdx.x == 0) s_item[(it + 1) & 1] = atomicAdd(work, 1u); // needed one slice from now
+		const uint32_t s0 = (uint32_t)(item / spz) * zsub; // first sub-table of the slice's zone
 		uint32_t tm[8];
 #pragma unroll
 		for (int i = 0; i < 8; ++i) tm[i] = 0;
+		uint64_t next_item = item;
 #pragma unroll 1
-		for (uint32_t g = 0; g < YAKB_ZSLICE / 1024; ++g) { // 4 events per thread at a time, lanes on consecutive entries
-			uint64_t v[4];
+		for (uint32_t g = 0; g < YAKB_ZGROUPS; ++g) {
+			ZGroup cur = nx;
+			if (g + 1 < YAKB_ZGROUPS) zone_fetch(nx, item, g + 1, n_items, spz, zcap, zev, zpos, zfill, pre, Pmask, slots, cap, nbk);
+			else {
+				__syncthreads(); // thread 0's fetch of the next item, issued a slice ago, is visible; one barrier per slice
+				next_item = s_item[(it + 1) & 1];
+				zone_fetch(nx, next_item, 0, n_items, spz, zcap, zev, zpos, zfill, pre, Pmask, slots, cap, nbk);
+			}
 			Bucket bk[4];
-			uint32_t bi[4], pos[4], vm = 0;
+			uint32_t bi[4];
 #pragma unroll
 			for (int j = 0; j < 4; ++j) {
-				const uint32_t i = start + g * 1024 + j * 256 + threadIdx.x;
-				bi[j] = 0; v[j] = 0; pos[j] = 0;
-				if (i < nz) {
-					v[j] = ev[i]; pos[j] = ep[i];
-					vm |= 1u << j;
-					bi[j] = tab_home(v[j] >> pre, nbk);
-					bk[j] = load_bucket(slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET);
+				bi[j] = 0;
+				if (cur.vm >> j & 1) {
+					bi[j] = tab_home(cur.v[j] >> pre, nbk);
+					bk[j] = load_bucket(slots + (uint64_t)((uint32_t)cur.v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET);
 				}
 			}
-			const uint32_t hit = probe_inc4(slots, cap, nbk, pre, Pmask, v, vm, bi, bk);
+			const uint32_t hit = probe_inc4(slots, cap, nbk, pre, Pmask, cur.v, cur.vm, bi, bk);
 			if (create_new) {
 #pragma unroll
 				for (int j = 0; j < 4; ++j) {
-					if (!(vm >> j & 1)) continue;
+					if (!(cur.vm >> j & 1)) continue;
 					if (hit >> j & 1) {
-						const uint32_t s = (uint32_t)v[j] & Pmask, t = pos[j] + 1;
+						const uint32_t s = (uint32_t)cur.v[j] & Pmask, t = cur.pos[j] + 1;
 						if (zsub) {
 							const uint32_t sl = s - s0;
 #pragma unroll
 							for (int i = 0; i < 8; ++i) if (sl == (uint32_t)i) tm[i] = max(tm[i], t);
 						} else if (smem_lp) atomicMax(&s_lp[s], t);
 						else atomicMax(&glob_lput[s], t);
-					} else atomicOr(&flags[pos[j] >> 5], 1u << (pos[j] & 31));
+					} else atomicOr(&flags[cur.pos[j] >> 5], 1u << (cur.pos[j] & 31));
 				}
 			}
 		}
@@ -443,6 +473,7 @@ __global__ void __launch_bounds__(256, MINB) zone_probe(const uint64_t *__restri
 					if ((threadIdx.x & 31) == 0 && t) { if (smem_lp) atomicMax(&s_lp[s0 + i], t); else atomicMax(&glob_lput[s0 + i], t); }
 				}
 		}
+		item = next_item;
 	}
 	__syncthreads();
 	if (smem_lp && create_new)
@@ -562,16 +593,44 @@ __global__ void max_need_kernel(const uint32_t *nkeys, const uint32_t *pend, uin
 
 // ---- the ordered part: one thread per group, events of a group walked in file order.
 //      pflag[j]: bit0 = put-event, bit1 = this put inserted a new key.
+//      Groups are short (1-4 events) and only their first event starts a walk: a thread per event leaves 6 of 32 lanes busy
+//      (ncu).  So a warp takes 128 consecutive events, finds the group heads among them (each lane looks at 4 events), lists
+//      them in shared memory, and its lanes then take the heads 32 at a time - every lane walks a group.
 __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__ sv, const uint32_t *__restrict__ sj, uint64_t n,
                                                     int G, int pre, uint32_t Pmask, int lw, uint64_t *slots, uint32_t cap,
                                                     uint32_t *bloom32, int nb, int sub_shift, int n_hash,
                                                     uint8_t *__restrict__ pflag)
 {
-	const uint64_t i = blockIdx.x * 256ull + threadIdx.x;
-	if (i >= n) return;
+	__shared__ uint8_t s_heads[8][128];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint64_t gmask = G >= 64 ? ~0ull : (1ull << G) - 1;
+	const uint64_t ntile = (n + 127) / 128;
+	for (uint64_t tile = blockIdx.x * 8ull + warp; tile < ntile; tile += gridDim.x * 8ull) {
+	const uint64_t base = tile * 128 + (uint64_t)lane * 4;
+	uint32_t hm = 0;
+	{
+		uint64_t prevk = base > 0 && base - 1 < n ? sv[base - 1] & gmask : 0;
+#pragma unroll
+		for (int q = 0; q < 4; ++q)
+			if (base + q < n) {
+				const uint64_t kq = sv[base + q] & gmask;
+				if (base + q == 0 || kq != prevk) hm |= 1u << q;
+				prevk = kq;
+			}
+	}
+	uint32_t incl = __popc(hm);
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+	const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+	{
+		uint32_t o = incl - __popc(hm);
+#pragma unroll
+		for (int q = 0; q < 4; ++q) if (hm >> q & 1) s_heads[warp][o++] = (uint8_t)(lane * 4 + q);
+	}
+	__syncwarp();
+	for (uint32_t hr = lane; hr < total; hr += 32) {
+	const uint64_t i = tile * 128 + s_heads[warp][hr];
 	const uint64_t gk = sv[i] & gmask;
-	if (i > 0 && (sv[i - 1] & gmask) == gk) return;
 	// block address: the group key with the (constant) owner bits of a shard squeezed out
 	const uint64_t baddr = lw ? ((gk >> pre) << (pre - lw)) | (gk & Pmask) : gk;
 	for (uint64_t e = i; e < n; ++e) {
@@ -626,6 +685,9 @@ __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__
 			else { slot_inc(slot, cur, 1); flag = 1; }
 		}
 		pflag[j] = flag;
+	}
+	}
+	__syncwarp(); // the next tile's head list overwrites this one
 	}
 }
 
@@ -1341,7 +1403,7 @@ bool Engine::probe_partitioned(uint64_t nwords, int create_new, const uint64_t *
 	if (create_new) YAKB_CUDA(cudaMemsetAsync(flags, 0, nwords * 4, stream));
 	{ ProfScope ps("zone_probe", stream);
 	const uint32_t zsub = (1u << zshift) <= 8 ? (1u << zshift) : 0;
-	static const int zocc = getenv("YAKB_ZPROBE_OCC") ? atoi(getenv("YAKB_ZPROBE_OCC")) : 3; // resident CTAs per SM (2: no register spills)
+	static const int zocc = getenv("YAKB_ZPROBE_OCC") ? atoi(getenv("YAKB_ZPROBE_OCC")) : 2; // resident CTAs per SM (2: no register spills; measured 11.5 vs 10.2 G events/s for 3)
 	if (zocc == 2) {
 		set_smem(zone_probe<2>, sm1);
 		zone_probe<2><<<nsm * 2, 256, sm1, stream>>>(zev, zpos, Z, zcap, zfill, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 1, zsub);
@@ -1409,8 +1471,8 @@ uint64_t Engine::pending_range(uint64_t t0, uint64_t t1, uint32_t off0, uint32_t
 	if (radix_sort_pairs(pv, nullptr, sv, sj, sv2, sj2, n_pending, 0, G, stream, rs)) { sv = sv2; sj = sj2; } }
 	uint8_t *pflag = b_pflag.as<uint8_t>(2 * (size_t)n_pending); // [0,n): put/new bits, [n,2n): new-key flag
 	{ ProfScope ps("group_insert", stream);
-	group_insert<<<cdiv(n_pending, 256), 256, 0, stream>>>(sv, sj, n_pending, G, pre, Pmask, lw, slots, cap,
-	                                                       (uint32_t*)bloom, nb, n_shift - pre, n_hash, pflag); }
+	group_insert<<<std::min<uint32_t>(cdiv(n_pending, 1024), nsm * 8), 256, 0, stream>>>(sv, sj, n_pending, G, pre, Pmask, lw, slots, cap,
+	                                                                                  (uint32_t*)bloom, nb, n_shift - pre, n_hash, pflag); }
 	YAKB_CUDA(cudaGetLastError());
 	const int smem2 = smem_lp_ok(P, 2);
 	const size_t sm2 = smem2 ? (size_t)P * 8 : 0;

@@ -95,10 +95,11 @@ __device__ __forceinline__ uint32_t tab_home(uint64_t x, uint32_t nbk) // home b
 	return (uint32_t)(((uint64_t)h * nbk) >> 32);
 }
 
+// one 256-bit load per bucket (sm_100: LDG.E.256; two 128-bit loads were two L2 requests for the same sector)
 __device__ __forceinline__ Bucket load_bucket(const uint64_t *p)
 {
-	const ulonglong2 a = __ldcg((const ulonglong2*)p), b = __ldcg((const ulonglong2*)p + 1);
-	Bucket r; r.k[0] = a.x; r.k[1] = a.y; r.k[2] = b.x; r.k[3] = b.y;
+	Bucket r;
+	asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.k[0]), "=l"(r.k[1]), "=l"(r.k[2]), "=l"(r.k[3]) : "l"(p));
 	return r;
 }
 

@@ -66,7 +66,7 @@ int read_yak_file(const char *fn, int mode, int min_cnt, int mid_cnt, YakFile &y
 		if (fread(t, 4, 3, fp) != 3) return -1;
 		yf.k = t[0]; yf.pre = t[1]; yf.counter_bits = t[2];
 		if (t[2] != YAK_COUNTER_BITS) return -3;
-		if (yf.pre > 30) return -1;
+		if (yf.pre < YAK_COUNTER_BITS || yf.pre > 30 || yf.k < 1 || yf.k > 63) return -1; // not a table yak_ch_init could have made (htab.c:17, main.c:46)
 		const int P = 1 << yf.pre; // (a pipe cannot be opened twice: header_only is not honoured here, the body comes along)
 		yf.caps.assign(P, 0); yf.off.assign(P + 1, 0);
 		std::vector<uint64_t> tmp;
@@ -91,8 +91,9 @@ int read_yak_file(const char *fn, int mode, int min_cnt, int mid_cnt, YakFile &y
 		memcpy(t, head + 4, 12);
 		yf.k = t[0]; yf.pre = t[1]; yf.counter_bits = t[2];
 		if (t[2] != YAK_COUNTER_BITS) return -3;
+		// before anything is sized from the header of an untrusted file: what yak_ch_init could have made (htab.c:17, main.c:46)
+		if (yf.pre < YAK_COUNTER_BITS || yf.pre > 30 || yf.k < 1 || yf.k > 63) return -1;
 		if (header_only) return 0;
-		if (yf.pre > 30) return -1;
 		const int P = 1 << yf.pre;
 		yf.caps.assign(P, 0); yf.off.assign(P + 1, 0);
 		std::vector<uint64_t> at(P, 0); // file offset of each sub-table's keys
