@@ -380,7 +380,7 @@ def main():
     ap.add_argument("--reads-per-step", type=int, default=16_000_000, help="the global batch of one step (all ranks together)")
     ap.add_argument("--chunk-reads", type=int, default=8_000_000, help="reads per engine chunk / all-to-all round on one rank")
     ap.add_argument("--bf-shift", type=int, default=BF)
-    ap.add_argument("--e2e-reads", type=int, default=16_000_000)
+    ap.add_argument("--e2e-reads", type=int, default=32_000_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the reference run on the e2e sample (no cpu_baseline, no parity)")
     ap.add_argument("--verbose", action="store_true")
@@ -537,8 +537,7 @@ def main():
             what1 = f"yak_count(pass 1, -b{args.bf_shift}) of {args.e2e_reads} FASTQ reads ({fsz} B in tmpfs): parse + H2D + kernels, {n_ev} events"
         else:
             from yak_b200 import dist as ydist
-            batch = (args.chunk_reads * rec // 1) * 1   # bases per round per rank, times the ranks = one global batch
-            batch = min(batch, 1 << 30) * world
+            batch = max(256 << 20, (64 << 20) * world)   # bases per global batch: several batches, so copies and kernels overlap
             dt1 = dt = 0.0
             tot1 = 0
             for rep in range(2):            # warm-up (pinned buffers, page cache), then the timed run

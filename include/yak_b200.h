@@ -40,6 +40,16 @@ int yakb_extract_route_dev(const void *d_asc, uint64_t n, int k, int pre, int wo
 int yakb_extract_route_async(const void *d_asc, uint64_t n, int k, int pre, int world,
                              uint64_t *d_out, uint64_t *d_counts, void *cuda_stream);
 
+/* Device-side text ingest (csrc/ingest.cu): FASTA/FASTQ text in the strict 2- / 4-line layout -> the dense "SEQ\nSEQ\n..."
+ * base stream the calls above take, with every record's layout checked on the device.
+ * yakb_record_start_before: the last offset in (lo, pos] of `text` (host memory, `size` bytes) where a record starts, or lo;
+ * a guess that the device check confirms or refutes.
+ * yakb_ingest_dev: d_raw[n] (n < 2^32) must start at a record and end behind a record's newline; d_out (capacity n)
+ * receives the bases; d_res (DEVICE, 3 x u64): [0] = 0 if the layout holds for every record (else the caller must use the
+ * host parser, kseq.h:192-232 semantics), [1] = bytes written to d_out, [2] = lines.  Does not wait for the device. */
+uint64_t yakb_record_start_before(const void *text, uint64_t lo, uint64_t pos, uint64_t size, int lines_per_record);
+int yakb_ingest_dev(const void *d_raw, uint64_t n, int lines_per_record, void *d_out, uint64_t *d_res, void *cuda_stream);
+
 /* Multi-GPU: one shard of a table whose 2^pre sub-tables are split over `world` (power of two)
  * GPUs; shard `rank` owns sub-tables [rank*2^pre/world, (rank+1)*2^pre/world) and ignores events
  * of other sub-tables.  Feed it with yakb_count_events_dev after the all-to-all.  The shards'
@@ -47,6 +57,10 @@ int yakb_extract_route_async(const void *d_asc, uint64_t n, int k, int pre, int 
  * bytes yak_ch_dump would write for the whole table. */
 yak_ch_t *yakb_ch_init_shard(int k, int pre, int n_hash, int n_shift, int rank, int world);
 int64_t yakb_ch_dump_shard_mem(const yak_ch_t *h, int with_header, uint8_t **out);
+/* the same image written at `offset` of the existing file `fn` (the ranks of a job write one .yak side by side);
+ * _size tells beforehand how many bytes it takes.  Both return -1 on failure. */
+int64_t yakb_ch_dump_shard_size(const yak_ch_t *h, int with_header);
+int64_t yakb_ch_dump_shard_at(const yak_ch_t *h, int with_header, const char *fn, uint64_t offset);
 
 /* batched yak_ch_get (reference htab.c:93-100): out[i] = count or -1 */
 int yakb_ch_get_batch(const yak_ch_t *h, uint64_t n, const uint64_t *x, int32_t *out);

@@ -14,6 +14,9 @@ pytestmark = pytest.mark.gpu
 
 def _worker(rank, world, port, fn, k, pre, b, out, batch_bases=0):
     import torch
+    if batch_bases < 0:          # the per-rank device ingest (yak_b200/dist.py _count_file_sharded_ingest), forced on a small file
+        os.environ["YAKB_GPU_INGEST"] = "1"
+        batch_bases = -batch_bases
     import torch.distributed as dist
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
@@ -30,7 +33,8 @@ def _worker(rank, world, port, fn, k, pre, b, out, batch_bases=0):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,pre,b,batch", [(31, 12, 0, 0), (31, 10, 20, 0), (47, 12, 0, 0), (31, 12, 22, 60_000), (31, 10, 0, 1 << 20)])
+@pytest.mark.parametrize("k,pre,b,batch", [(31, 12, 0, 0), (31, 10, 20, 0), (47, 12, 0, 0), (31, 12, 22, 60_000), (31, 10, 0, 1 << 20),
+                                           (31, 12, 22, -40_000), (31, 10, 0, -(1 << 20))])
 def test_nccl_sharded_count_equals_oracle(yakb, k, pre, b, batch):
     import torch
     import torch.multiprocessing as mp
@@ -70,7 +74,10 @@ def test_multi_gpu_count_command_equals_oracle(yakb, b, compressed):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), "-m", "yak_b200.dist", "count", "-k31", "-p12", f"-b{b}", "-o", out, gz if compressed else fn]
-    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    if b == 22:                  # this case through the per-rank device ingest (forced: the file is small)
+        env["YAKB_GPU_INGEST"] = "1"
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
     h, _ = O.count_file(fn, k=31, pre=12, bf_shift=b)
     want = O.dump_bytes(h)

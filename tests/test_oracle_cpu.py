@@ -901,3 +901,53 @@ def test_yak_file_reader_of_restore_equals_a_plain_parse():
     t.join()
     os.unlink(fifo)
     assert same(got, _parse_yak_like_the_reference(small, 1, 0, 0))
+
+
+def test_cpu_read_generator_equals_the_python_specification():
+    """oracle/_bin/synthgen (bench.py's reference arm writes its input with it) against yak_b200/synth.py: same bytes, same event count"""
+    import subprocess
+    from yak_b200 import synth
+    gen = os.path.join(ROOT, "oracle", "_bin", "synthgen")
+    if not os.path.exists(gen):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    for fmt, fastq in ((1, False), (2, True)):
+        out = os.path.join(util.TMP, f"yakb_synthgen{fmt}.txt")
+        r = subprocess.run([gen, "7", "200000", "11", "5", "3000", "150", "0.005", "1", str(fmt), "31", out, "3"], capture_output=True, text=True, check=True)
+        codes = synth.read_codes(7, 200000, 11, 5, 3000, 150, 0.005, 1)
+        exp = bytearray()
+        for row in synth.codes_to_ascii(codes):
+            exp += (b"@r\n" if fastq else b">r\n") + row.tobytes() + b"\n" + ((b"+\n" + b"I" * 150 + b"\n") if fastq else b"")
+        assert open(out, "rb").read() == bytes(exp)
+        assert int(r.stdout) == synth.count_events(codes, 31)
+
+
+def test_record_boundary_guess_on_adversarial_quality_lines():
+    """yakb_record_start_before (csrc/capi.cu; host code, no GPU): where the device ingest cuts its batches.  Quality lines that start
+    with '@' must not be taken for headers: two lines behind a header comes a '+' line, two lines behind such a quality line come bases."""
+    import ctypes as C
+    from yak_b200 import capi
+    L = capi.lib()
+    rng = np.random.default_rng(3)
+    recs, starts, off = [], [], 0
+    for i in range(400):
+        n = int(rng.integers(1, 80))
+        seq = bytes(rng.choice(list(b"ACGT"), n).astype(np.uint8))
+        qual = (b"@" if i % 2 else b"+") + bytes(rng.integers(33, 74, n - 1).astype(np.uint8)) if n > 1 else b"@"
+        rec = b"@r%d\n" % i + seq + b"\n+\n" + qual + b"\n"
+        starts.append(off); off += len(rec); recs.append(rec)
+    text = b"".join(recs)
+    buf = C.create_string_buffer(text, len(text))
+    starts = np.array(starts)
+    for pos in list(rng.integers(1, len(text), 300)) + [len(text) - 1]:
+        lo = int(rng.integers(0, pos))
+        got = L.yakb_record_start_before(buf, lo, int(pos), len(text), 4)
+        cand = starts[(starts > lo) & (starts <= pos)]
+        # the last record start in (lo, pos] whose '+' line is still inside the text; lo when there is none
+        want = lo
+        for s in cand[::-1]:
+            want = int(s)
+            break
+        assert got == want, (lo, pos, got, want)
+    fa = b"".join(b">c%d\n" % i + b"ACGT" * 5 + b"\n" for i in range(50))
+    fbuf = C.create_string_buffer(fa, len(fa))
+    assert L.yakb_record_start_before(fbuf, 0, 100, len(fa), 2) == max(i for i in range(0, 101) if fa[i:i + 1] == b">" and (i == 0 or fa[i - 1:i] == b"\n"))

@@ -81,6 +81,8 @@ def lib() -> C.CDLL:
         "yakb_count_events_dev": (C.c_int, [ChP, vp, u64, C.c_int, C.POINTER(u64)]),
         "yakb_extract_route_dev": (C.c_int, [vp, u64, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u64), vp]),
         "yakb_extract_route_async": (C.c_int, [vp, u64, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+        "yakb_record_start_before": (u64, [vp, u64, u64, u64, C.c_int]),
+        "yakb_ingest_dev": (C.c_int, [vp, u64, C.c_int, vp, vp, vp]),
         "yakb_ch_get_batch": (C.c_int, [ChP, u64, C.POINTER(u64), C.POINTER(i32)]),
         "yakb_ch_get_batch_dev": (C.c_int, [ChP, u64, vp, vp]),
         "yakb_qv_seqs": (C.c_int, [ChP, i64, C.POINTER(i64), C.c_char_p, C.c_int, C.c_double, C.POINTER(i64),
@@ -89,6 +91,8 @@ def lib() -> C.CDLL:
         "yakb_ch_dump_mem": (i64, [ChP, C.POINTER(vp)]),
         "yakb_ch_init_shard": (ChP, [C.c_int] * 6),
         "yakb_ch_dump_shard_mem": (i64, [ChP, C.c_int, C.POINTER(vp)]),
+        "yakb_ch_dump_shard_size": (i64, [ChP, C.c_int]),
+        "yakb_ch_dump_shard_at": (i64, [ChP, C.c_int, C.c_char_p, u64]),
         "yakb_ch_reserve": (C.c_int, [ChP, u64]),
         "yakb_ch_stream": (vp, [ChP]),
         "yakb_ch_device_bytes": (u64, [ChP]),

@@ -631,6 +631,52 @@ static int64_t dump_mem(const yak_ch_t *h, uint8_t **out, bool header)
 	GUARD_END(-1)
 }
 extern "C" int64_t yakb_ch_dump_mem(const yak_ch_t *h, uint8_t **out) { return dump_mem(h, out, true); }
+
+// a shard's image straight into its place in a file the ranks write side by side (no copy through the caller: images of
+// gigabytes).  size = what the image will take; at = write it at `offset` of the existing file `fn`.
+extern "C" int64_t yakb_ch_dump_shard_size(const yak_ch_t *h, int with_header)
+{
+	GUARD_BEGIN
+	ChBox *b = box_single(h, __func__);
+	std::lock_guard<std::mutex> lk(b->mu);
+	std::vector<uint32_t> z;
+	b->eng->sizes(z);
+	int64_t n = with_header ? 16 : 0;
+	for (uint32_t v : z) n += 8 + 8 * (int64_t)v;
+	return n;
+	GUARD_END(-1)
+}
+extern "C" int64_t yakb_ch_dump_shard_at(const yak_ch_t *h, int with_header, const char *fn, uint64_t offset)
+{
+	GUARD_BEGIN
+	ChBox *b = box_single(h, __func__);
+	std::lock_guard<std::mutex> lk(b->mu);
+	const int fd = open(fn, O_WRONLY);
+	if (fd < 0) return -1;
+	std::vector<uint8_t> buf;
+	buf.reserve(16u << 20);
+	uint64_t at = offset;
+	bool ok = true;
+	auto flush = [&]() {
+		size_t done = 0;
+		while (ok && done < buf.size()) { const ssize_t w = pwrite(fd, buf.data() + done, buf.size() - done, (off_t)(at + done)); if (w <= 0) ok = false; else done += (size_t)w; }
+		at += buf.size();
+		buf.clear();
+	};
+	serialise(b, [&](const void *p, size_t n) {
+		const uint8_t *q = (const uint8_t*)p;
+		while (n) {
+			const size_t m = std::min(n, (size_t)(16u << 20) - buf.size());
+			buf.insert(buf.end(), q, q + m);
+			q += m; n -= m;
+			if (buf.size() >= (16u << 20)) flush();
+		}
+	}, with_header != 0);
+	flush();
+	close(fd);
+	return ok ? (int64_t)(at - offset) : -1;
+	GUARD_END(-1)
+}
 extern "C" int64_t yakb_ch_dump_shard_mem(const yak_ch_t *h, int with_header, uint8_t **out) { return dump_mem(h, out, with_header != 0); }
 
 // test hook (no GPU): the arrays yak_ch_restore_core hands to the device, malloc'd for the caller
@@ -1175,6 +1221,22 @@ static int count_gpu_ingest(yak_ch_t *h, const char *src, const struct stat &st,
 	{ std::lock_guard<std::mutex> g(g_strict_mu); g_strict_files[file_id(st)] = true; }
 	if (timing_on()) fprintf(stderr, "[T::yak_count] device ingest: %d batches, device %.3f s, waiting for the copies %.3f s\n", n_batches, t_dev, t_wait);
 	return 0;
+}
+
+// the two halves of the device ingest as calls of their own (yak_b200/dist.py: every rank of a multi-GPU job takes its own
+// byte range of the file): where to cut, and text -> dense base stream + layout check on the current device
+extern "C" uint64_t yakb_record_start_before(const void *text, uint64_t lo, uint64_t pos, uint64_t size, int lines_per_record)
+{
+	return record_start_before((const uint8_t*)text, lo, pos, size, lines_per_record, lines_per_record == 4 ? '@' : '>');
+}
+static IngestScratch g_ingest_scratch;
+static std::mutex g_ingest_mu;
+extern "C" int yakb_ingest_dev(const void *d_raw, uint64_t n, int lines_per_record, void *d_out, uint64_t *d_res, void *cuda_stream)
+{
+	GUARD_BEGIN
+	std::lock_guard<std::mutex> lk(g_ingest_mu);
+	return ingest_strict((const uint8_t*)d_raw, n, lines_per_record, (uint8_t*)d_out, (unsigned long long*)d_res, (cudaStream_t)cuda_stream, g_ingest_scratch);
+	GUARD_END(-1)
 }
 
 static yak_ch_t *count_impl(const char *fn, const yak_copt_t *opt, yak_ch_t *h0, int ref_workers);

@@ -592,14 +592,16 @@ __global__ void max_need_kernel(const uint32_t *nkeys, const uint32_t *pend, uin
 }
 
 // ---- the ordered part: one thread per group, events of a group walked in file order.
-//      pflag[j]: bit0 = put-event, bit1 = this put inserted a new key.
+//      pflag: 2 bits per pending event j (file-order index), bit0 = put-event, bit1 = this put inserted a new key, as a
+//      bitmap of u32 words set with atomicOr: 64 MB for a range of 256 M events, which stays in L2 - one byte per event
+//      written at a random j was a partial-sector write to DRAM each (ncu: 238 B of DRAM traffic per pending event).
 //      Groups are short (1-4 events) and only their first event starts a walk: a thread per event leaves 6 of 32 lanes busy
 //      (ncu).  So a warp takes 128 consecutive events, finds the group heads among them (each lane looks at 4 events), lists
 //      them in shared memory, and its lanes then take the heads 32 at a time - every lane walks a group.
 __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__ sv, const uint32_t *__restrict__ sj, uint64_t n,
                                                     int G, int pre, uint32_t Pmask, int lw, uint64_t *slots, uint32_t cap,
                                                     uint32_t *bloom32, int nb, int sub_shift, int n_hash,
-                                                    uint8_t *__restrict__ pflag)
+                                                    uint32_t *__restrict__ pflag)
 {
 	__shared__ uint8_t s_heads[8][128];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -684,7 +686,7 @@ __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__
 			if (tab_insert(slots + (uint64_t)s * cap, cap, x << YAKB_COUNTER_BITS | 1, &slot, &cur)) flag = 3;
 			else { slot_inc(slot, cur, 1); flag = 1; }
 		}
-		pflag[j] = flag;
+		if (flag) atomicOr(&pflag[j >> 4], (uint32_t)flag << ((j & 15) * 2));
 	}
 	}
 	__syncwarp(); // the next tile's head list overwrites this one
@@ -693,7 +695,7 @@ __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__
 
 // ---- per sub-table max position (+1) of pending put-events / new-key puts of this chunk
 __global__ void __launch_bounds__(256) post_pending(const uint64_t *__restrict__ pv, const uint32_t *__restrict__ ppos,
-                                                    uint8_t *__restrict__ pflag, uint64_t n, uint32_t Pmask,
+                                                    const uint32_t *__restrict__ pflag, uint8_t *__restrict__ isnew, uint64_t n, uint32_t Pmask,
                                                     uint32_t *glob_lput, uint32_t *glob_lnew, int smem_ok, unsigned long long *stats)
 {
 	extern __shared__ uint32_t s_arr[];
@@ -703,8 +705,8 @@ __global__ void __launch_bounds__(256) post_pending(const uint64_t *__restrict__
 	__syncthreads();
 	uint32_t nput = 0;
 	for (uint64_t j = blockIdx.x * 256ull + threadIdx.x; j < n; j += gridDim.x * 256ull) {
-		uint8_t f = pflag[j];
-		pflag[n + j] = f >> 1 & 1;
+		const uint32_t f = pflag[j >> 4] >> ((j & 15) * 2) & 3;
+		isnew[j] = f >> 1 & 1;
 		if (!(f & 1)) continue;
 		++nput;
 		uint32_t s = (uint32_t)pv[j] & Pmask, t = ppos[j] + 1;
@@ -1198,8 +1200,8 @@ Engine *Engine::create(int k, int pre, int n_hash, int n_shift, int rank, int wo
 	if (pre < YAKB_COUNTER_BITS) return nullptr; // htab.c:17
 	int lw = 0;
 	while ((1 << lw) < world) ++lw;
-	if ((1 << lw) != world || lw > pre || rank < 0 || rank >= world) {
-		fprintf(stderr, "[yakb] ERROR: world size must be a power of two <= 2^pre and 0 <= rank < world\n");
+	if ((1 << lw) != world || lw > pre || world > 16 || rank < 0 || rank >= world) { // 16: what the route kernels (extras.cu) partition by
+		fprintf(stderr, "[yakb] ERROR: world size must be a power of two <= 16 and 0 <= rank < world\n");
 		return nullptr;
 	}
 	int ndev = 0;
@@ -1469,7 +1471,10 @@ uint64_t Engine::pending_range(uint64_t t0, uint64_t t1, uint32_t off0, uint32_t
 	uint32_t *sj = b_sj.as<uint32_t>(n_pending), *sj2 = b_sj2.as<uint32_t>(n_pending);
 	{ ProfScope ps("group_sort", stream);
 	if (radix_sort_pairs(pv, nullptr, sv, sj, sv2, sj2, n_pending, 0, G, stream, rs)) { sv = sv2; sj = sj2; } }
-	uint8_t *pflag = b_pflag.as<uint8_t>(2 * (size_t)n_pending); // [0,n): put/new bits, [n,2n): new-key flag
+	const size_t pf_words = ((size_t)n_pending + 15) / 16;
+	uint32_t *pflag = b_pflag.as<uint32_t>(pf_words + ((size_t)n_pending + 3) / 4 + 4); // 2 bits per event, then one new-key byte per event
+	uint8_t *isnew_w = (uint8_t*)(pflag + pf_words);
+	YAKB_CUDA(cudaMemsetAsync(pflag, 0, pf_words * 4, stream));
 	{ ProfScope ps("group_insert", stream);
 	group_insert<<<std::min<uint32_t>(cdiv(n_pending, 1024), nsm * 8), 256, 0, stream>>>(sv, sj, n_pending, G, pre, Pmask, lw, slots, cap,
 	                                                                                  (uint32_t*)bloom, nb, n_shift - pre, n_hash, pflag); }
@@ -1478,13 +1483,13 @@ uint64_t Engine::pending_range(uint64_t t0, uint64_t t1, uint32_t off0, uint32_t
 	const size_t sm2 = smem2 ? (size_t)P * 8 : 0;
 	set_smem(post_pending, sm2);
 	{ ProfScope ps("post_pending", stream);
-	post_pending<<<std::min<uint32_t>(cdiv(n_pending, 256), nsm * 4), 256, sm2, stream>>>(pv, ppos, pflag, n_pending, Pmask, lput, lnew, smem2, stats); }
+	post_pending<<<std::min<uint32_t>(cdiv(n_pending, 256), nsm * 4), 256, sm2, stream>>>(pv, ppos, pflag, isnew_w, n_pending, Pmask, lput, lnew, smem2, stats); }
 	YAKB_CUDA(cudaGetLastError());
 	note_launch(5); // compact, pend_hist, max_need, group_insert, post_pending
 	// new keys in file order, then stably by sub-table -> journal segment
 	uint64_t *newv = b_newv.as<uint64_t>(n_pending);
 	uint32_t *d_nsel = (uint32_t*)(stats + 2);
-	const uint8_t *isnew = pflag + n_pending; // written by post_pending
+	const uint8_t *isnew = isnew_w; // written by post_pending
 	{ ProfScope ps("journal(compact)", stream);
 	compact_flagged_u64(pv, isnew, n_pending, newv, d_nsel, stream, rs); }
 	uint32_t n_new = 0;

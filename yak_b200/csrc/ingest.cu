@@ -103,6 +103,9 @@ __global__ void __launch_bounds__(256) ingest_scatter(const uint8_t *__restrict_
                                                       const uint32_t *__restrict__ tile_line, const uint32_t *__restrict__ keepoff,
                                                       uint8_t *__restrict__ out)
 {
+	// the tile's kept bytes are first packed in shared memory, then leave as one contiguous run: consecutive lanes write
+	// consecutive bytes / words (a thread storing its own 16 bytes one by one cost 16 scattered sector writes per warp store)
+	__shared__ __align__(16) uint8_t s_out[ING_TILE + 16];
 	uint8_t c[16];
 	const uint64_t off = blockIdx.x * (uint64_t)ING_TILE + threadIdx.x * 16ull;
 	const uint32_t m = ing_load16(raw, off, n, c);
@@ -115,12 +118,28 @@ __global__ void __launch_bounds__(256) ingest_scatter(const uint8_t *__restrict_
 		if ((l2 & lmask) == 1) ++keep;
 		if (m >> i & 1) ++l2;
 	}
-	uint64_t o = (uint64_t)keepoff[blockIdx.x] + block_excl_scan_256(keep, nullptr);
+	uint32_t tot;
+	uint32_t o = block_excl_scan_256(keep, &tot);
+	const uint64_t gbase = keepoff[blockIdx.x];
+	const uint32_t lead = (uint32_t)((4 - (gbase & 3)) & 3); // bytes in front of the first 4-byte aligned output address
+	// place so that shared-memory word w (w >= 1) is output word (gbase + lead) / 4 + w - 1: byte j of the run sits at 4 - lead + j
+	const uint32_t shift = 4 - lead;
 #pragma unroll
 	for (int i = 0; i < 16; ++i) {
 		if (off + i >= n) break;
-		if ((line & lmask) == 1) out[o++] = c[i];
+		if ((line & lmask) == 1) s_out[shift + o++] = c[i];
 		if (m >> i & 1) ++line;
+	}
+	__syncthreads();
+	// head bytes, whole words, tail bytes
+	if (threadIdx.x < lead && threadIdx.x < tot) out[gbase + threadIdx.x] = s_out[shift + threadIdx.x];
+	if (tot > lead) {
+		const uint32_t body = tot - lead, nw = body / 4;
+		uint32_t *ow = (uint32_t*)(out + gbase + lead);
+		const uint32_t *sw = (const uint32_t*)(s_out + 4);
+		for (uint32_t w = threadIdx.x; w < nw; w += 256) ow[w] = sw[w];
+		const uint32_t done = lead + nw * 4;
+		if (threadIdx.x < tot - done) out[gbase + done + threadIdx.x] = s_out[shift + done + threadIdx.x];
 	}
 }
 

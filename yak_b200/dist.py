@@ -82,6 +82,18 @@ class GpuBackend:
         C.CDLL(None).free(out)
         return data
 
+    def dump_shard_size(self, with_header: bool) -> int:
+        n = self.lib.yakb_ch_dump_shard_size(self.h, int(with_header))
+        if n < 0:
+            raise RuntimeError("yakb_ch_dump_shard_size failed")
+        return int(n)
+
+    def dump_shard_at(self, with_header: bool, path: str, offset: int) -> int:
+        n = self.lib.yakb_ch_dump_shard_at(self.h, int(with_header), path.encode(), offset)
+        if n < 0:
+            raise RuntimeError("yakb_ch_dump_shard_at failed")
+        return int(n)
+
     def close(self):
         self._out = self._recv = None
         if self.h:
@@ -182,29 +194,38 @@ class ShardedCounter:
 
     def dump_file(self, path: str) -> int:
         """The .yak file written by all ranks of one node side by side: every rank writes its shard image at its own offset
-        (rank-ordered concatenation, htab.c:373-394); returns the file size.  No shard travels between processes."""
+        (rank-ordered concatenation, htab.c:373-394); returns the file size.  No shard travels between processes - or through
+        Python: a backend with `dump_shard_size` / `dump_shard_at` (the GPU library) writes straight from C."""
         import os
-        part = self.b.dump_shard(self.rank == 0)
+        direct = hasattr(self.b, "dump_shard_at")
+        part = None if direct else self.b.dump_shard(self.rank == 0)
+        mine = self.b.dump_shard_size(self.rank == 0) if direct else len(part)
         if self.world == 1:
             with open(path, "wb") as f:
-                f.write(part)
-            return len(part)
+                if not direct:
+                    f.write(part)
+            if direct:
+                self.b.dump_shard_at(True, path, 0)
+            return mine
         lens = torch.zeros(self.world, dtype=torch.int64, device=self._dev())
-        lens[self.rank] = len(part)
+        lens[self.rank] = mine
         dist.all_reduce(lens, group=self.group)
         off = [0] + [int(x) for x in torch.cumsum(lens, 0).tolist()]
         if self.rank == 0:
             with open(path, "wb") as f:
                 f.truncate(off[-1])
         dist.barrier(group=self.group)
-        fd = os.open(path, os.O_WRONLY)
-        try:
-            done = 0
-            view = memoryview(part)
-            while done < len(part):
-                done += os.pwrite(fd, view[done:done + (1 << 30)], off[self.rank] + done)
-        finally:
-            os.close(fd)
+        if direct:
+            self.b.dump_shard_at(self.rank == 0, path, off[self.rank])
+        else:
+            fd = os.open(path, os.O_WRONLY)
+            try:
+                done = 0
+                view = memoryview(part)
+                while done < len(part):
+                    done += os.pwrite(fd, view[done:done + (1 << 30)], off[self.rank] + done)
+            finally:
+                os.close(fd)
         dist.barrier(group=self.group)
         return off[-1]
 
@@ -324,6 +345,103 @@ def _count_file_sharded_pool(fn, sc: ShardedCounter, k, create_new, batch_bases,
     return True
 
 
+def _count_file_sharded_ingest(fn, sc: ShardedCounter, k, create_new, batch_bytes, group):
+    """One pass over a plain file in the strict 4-line FASTQ / 2-line FASTA layout with NO host parsing: every rank maps the
+    file, takes its own byte range of every batch (cut where a record starts: csrc/capi.cu record_start_before, the same
+    arithmetic on every rank), copies it to its GPU and has the device turn it into the base stream, checking the layout of
+    every record (csrc/ingest.cu).  Returns True when the whole file went through; False when the file does not qualify or
+    its FIRST batch fails the check (nothing was counted: the caller takes the parser path).  A later failure raises."""
+    import os
+    import threading
+    from . import capi
+    L = capi.lib()
+    G, r, dev = sc.world, sc.rank, sc._dev()
+    if dev.type != "cuda" or os.environ.get("YAKB_GPU_INGEST", "") == "0":
+        return False
+    try:
+        size = os.path.getsize(fn)
+        mm = np.memmap(fn, dtype=np.uint8, mode="r") if size > 0 else None
+    except (OSError, ValueError):
+        return False
+    if mm is None or size < (256 << 20) and os.environ.get("YAKB_GPU_INGEST", "") != "1":
+        return False
+    marker = int(mm[0])
+    lpr = 4 if marker == ord("@") else 2 if marker == ord(">") else 0
+    if lpr == 0 or int(mm[size - 1]) != 10:
+        return False
+    base = mm.ctypes.data
+    B = max(1 << 16, int(batch_bytes))
+
+    def cut(lo, pos):
+        return int(L.yakb_record_start_before(base, lo, min(pos, size), size, lpr)) if pos < size else size
+
+    pinned = [torch.empty(0, dtype=torch.uint8).pin_memory(), torch.empty(0, dtype=torch.uint8).pin_memory()]
+    d_res = torch.zeros(3, dtype=torch.int64, device=dev)
+    state = {}
+
+    def stage(slot, a):
+        """my part of the batch that starts at a: -> (next batch start, bytes staged in pinned[slot])"""
+        e = cut(a, a + B)
+        if e <= a:
+            e = -1                       # a record longer than a batch: not this path's business
+            state[slot] = (e, 0)
+            return
+        n = e - a
+        lo = a if r == 0 else cut(a, a + n * r // G)
+        hi = e if r == G - 1 else cut(a, a + n * (r + 1) // G)
+        m = max(0, hi - lo)
+        if pinned[slot].numel() < m:
+            pinned[slot] = torch.empty(int(m * 1.1) + 4096, dtype=torch.uint8).pin_memory()
+        if m:                            # a few threads: one memcpy out of the page cache runs at 5-8 GB/s
+            dst = pinned[slot].numpy()
+            parts = 4 if m >= (32 << 20) else 1
+            ths = [threading.Thread(target=np.copyto, args=(dst[m * i // parts:m * (i + 1) // parts], mm[lo + m * i // parts:lo + m * (i + 1) // parts]))
+                   for i in range(parts)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        state[slot] = (e, m)
+
+    a, slot, n_batches = 0, 0, 0
+    stage(0, 0)
+    while True:
+        e, m = state[slot]
+        th = None
+        if 0 < e < size:
+            th = threading.Thread(target=stage, args=(slot ^ 1, e))
+            th.start()
+        ok = 1
+        dense = None
+        if e < 0:
+            ok = 0
+        else:
+            raw = pinned[slot][:m].to(dev, non_blocking=True)
+            dense = torch.empty(max(m, 1), dtype=torch.uint8, device=dev)
+            if L.yakb_ingest_dev(raw.data_ptr(), m, lpr, dense.data_ptr(), d_res.data_ptr(), torch.cuda.current_stream().cuda_stream) != 0:
+                ok = 0
+            res = d_res.cpu().tolist()
+            if res[0] != 0:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int64, device=dev)
+        if G > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag[0]) == 0:
+            if th:
+                th.join()
+            if n_batches == 0:
+                return False
+            raise RuntimeError(f"{fn}: the strict {lpr}-line layout breaks after {n_batches} batches; rerun with YAKB_GPU_INGEST=0")
+        sc.count_chunk(dense[:int(res[1])], create_new)
+        n_batches += 1
+        if th:
+            th.join()
+        if e >= size:
+            break
+        slot ^= 1
+    return True
+
+
 def count_file_sharded(fn: str, backend, records_per_chunk: int = 1 << 20, k: int = 31, two_pass: bool = False,
                        fn2: str | None = None, group=None, batch_bases: int = 0, timings: dict | None = None) -> ShardedCounter:
     """`yak count` of one shared file on all ranks of ONE node.  batch_bases > 0: plain files are parsed once by rank 0's
@@ -337,6 +455,9 @@ def count_file_sharded(fn: str, backend, records_per_chunk: int = 1 << 20, k: in
     per = max(1, records_per_chunk // G)
 
     def one_pass(path, create_new):
+        # plain files in the strict layout: every rank ingests its own byte range on its GPU (2 bytes of FASTQ text per base)
+        if batch_bases > 0 and _count_file_sharded_ingest(path, sc, k, create_new, 2 * batch_bases, group):
+            return
         if batch_bases > 0 and _count_file_sharded_pool(path, sc, k, create_new, batch_bases, group):
             return
         rd = L.yakb_fastx_open(path.encode())
