@@ -203,20 +203,26 @@ static yak_ch_t *ch_init_multi(int k, int pre, int n_hash, int n_shift, int G)
 	b->magic = kMagic; b->eng = nullptr;
 	int dev0 = 0;
 	cudaGetDevice(&dev0);
-	bool ok = true;
-	for (int r = 0; r < G && ok; ++r) {
-		Shard *sh = new Shard;
-		sh->dev = r;
-		b->shards.push_back(sh);
-		DevGuard g(r);
-		for (int q = 0; q < G; ++q) // peers read each other's routed events directly over NVLink; without peer access the copies are staged
-			if (q != r) { int can = 0; cudaDeviceCanAccessPeer(&can, r, q); if (can && cudaDeviceEnablePeerAccess(q, 0) != cudaSuccess) (void)cudaGetLastError(); }
-		sh->eng = Engine::create(k, pre, n_hash, n_shift, r, G);
-		if (!sh->eng) { ok = false; break; }
-		YAKB_CUDA(cudaStreamCreateWithFlags(&sh->stream, cudaStreamNonBlocking));
+	std::atomic<bool> ok{true};
+	for (int r = 0; r < G; ++r) { Shard *sh = new Shard; sh->dev = r; b->shards.push_back(sh); }
+	{ // side by side: a 16 GiB filter takes the driver half a second to allocate, per GPU
+		std::vector<std::thread> th;
+		for (int r = 0; r < G; ++r)
+			th.emplace_back([&, r] {
+				Shard *sh = b->shards[r];
+				try {
+					cudaSetDevice(r);
+					for (int q = 0; q < G; ++q) // peers read each other's routed events directly over NVLink; without peer access the copies are staged
+						if (q != r) { int can = 0; cudaDeviceCanAccessPeer(&can, r, q); if (can && cudaDeviceEnablePeerAccess(q, 0) != cudaSuccess) (void)cudaGetLastError(); }
+					sh->eng = Engine::create(k, pre, n_hash, n_shift, r, G);
+					if (!sh->eng) { ok = false; return; }
+					YAKB_CUDA(cudaStreamCreateWithFlags(&sh->stream, cudaStreamNonBlocking));
+				} catch (const std::exception &e) { fprintf(stderr, "[yakb] ERROR: %s\n", e.what()); ok = false; }
+			});
+		for (auto &t : th) t.join();
 	}
 	cudaSetDevice(dev0);
-	if (!ok) {
+	if (!ok.load()) {
 		for (Shard *sh : b->shards) { DevGuard g(sh->dev); delete sh->eng; if (sh->stream) cudaStreamDestroy(sh->stream); delete sh; }
 		delete b;
 		return 0;
@@ -600,6 +606,40 @@ template<class Sink> static void serialise_engine(ChBox *b, Engine *eng, Sink &&
 	if (timing_on()) fprintf(stderr, "[T::serialise] layout %.3f s, sink %.3f s (overlapped)\n", t_lay, t_sink);
 }
 
+// one engine's image written at `offset` of an open file, through a 16 MB buffer; returns the bytes written or -1
+static int64_t dump_engine_at(ChBox *b, Engine *eng, bool header, int fd, uint64_t offset)
+{
+	std::vector<uint8_t> buf;
+	buf.reserve(16u << 20);
+	uint64_t at = offset;
+	bool ok = true;
+	auto flush = [&]() {
+		size_t done = 0;
+		while (ok && done < buf.size()) { const ssize_t w = pwrite(fd, buf.data() + done, buf.size() - done, (off_t)(at + done)); if (w <= 0) ok = false; else done += (size_t)w; }
+		at += buf.size();
+		buf.clear();
+	};
+	serialise_engine(b, eng, [&](const void *p, size_t n) {
+		const uint8_t *q = (const uint8_t*)p;
+		while (n) {
+			const size_t m = std::min(n, (size_t)(16u << 20) - buf.size());
+			buf.insert(buf.end(), q, q + m);
+			q += m; n -= m;
+			if (buf.size() >= (16u << 20)) flush();
+		}
+	}, header);
+	flush();
+	return ok ? (int64_t)(at - offset) : -1;
+}
+static int64_t engine_image_bytes(Engine *eng, bool header)
+{
+	std::vector<uint32_t> z;
+	eng->sizes(z);
+	int64_t n = header ? 16 : 0;
+	for (uint32_t v : z) n += 8 + 8 * (int64_t)v;
+	return n;
+}
+
 extern "C" int yak_ch_dump(const yak_ch_t *h, const char *fn)
 {
 	GUARD_BEGIN
@@ -607,6 +647,19 @@ extern "C" int yak_ch_dump(const yak_ch_t *h, const char *fn)
 	std::lock_guard<std::mutex> lk(b->mu);
 	StageTimer tm("yak_ch_dump");
 	if (b->eng->lw && b->shards.empty()) { fprintf(stderr, "[yakb] ERROR: yak_ch_dump on one shard of a multi-GPU table; use yakb_ch_dump_shard_mem\n"); return -1; }
+	if (!b->shards.empty() && strcmp(fn, "-")) { // a multi-GPU table into a file: every shard writes its own part, side by side
+		const int fd = open(fn, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+		if (fd < 0) return -1;
+		const int G = (int)b->shards.size();
+		std::vector<uint64_t> off(G + 1, 0);
+		for (int r = 0; r < G; ++r) { DevGuard g(b->shards[r]->dev); off[r + 1] = off[r] + (uint64_t)engine_image_bytes(b->shards[r]->eng, r == 0); }
+		std::vector<int64_t> wrote(G, 0);
+		each_shard(b, true, [&](Engine *e, int r) { wrote[r] = dump_engine_at(b, e, r == 0, fd, off[r]); });
+		close(fd);
+		for (int r = 0; r < G; ++r) if (wrote[r] != (int64_t)(off[r + 1] - off[r])) return -1;
+		fprintf(stderr, "[M::%s] dumpped the hash table to file '%s'.\n", __func__, fn);
+		return 0;
+	}
 	FILE *fp = strcmp(fn, "-") ? fopen(fn, "wb") : stdout;
 	if (fp == 0) return -1;
 	std::unique_ptr<char[]> iobuf(new char[1 << 20]); // per call: tables may be dumped from several threads at once
@@ -634,16 +687,13 @@ extern "C" int64_t yakb_ch_dump_mem(const yak_ch_t *h, uint8_t **out) { return d
 
 // a shard's image straight into its place in a file the ranks write side by side (no copy through the caller: images of
 // gigabytes).  size = what the image will take; at = write it at `offset` of the existing file `fn`.
+extern "C" int64_t yakb_ch_dump_shard_mem(const yak_ch_t *h, int with_header, uint8_t **out) { return dump_mem(h, out, with_header != 0); }
 extern "C" int64_t yakb_ch_dump_shard_size(const yak_ch_t *h, int with_header)
 {
 	GUARD_BEGIN
 	ChBox *b = box_single(h, __func__);
 	std::lock_guard<std::mutex> lk(b->mu);
-	std::vector<uint32_t> z;
-	b->eng->sizes(z);
-	int64_t n = with_header ? 16 : 0;
-	for (uint32_t v : z) n += 8 + 8 * (int64_t)v;
-	return n;
+	return engine_image_bytes(b->eng, with_header != 0);
 	GUARD_END(-1)
 }
 extern "C" int64_t yakb_ch_dump_shard_at(const yak_ch_t *h, int with_header, const char *fn, uint64_t offset)
@@ -653,31 +703,11 @@ extern "C" int64_t yakb_ch_dump_shard_at(const yak_ch_t *h, int with_header, con
 	std::lock_guard<std::mutex> lk(b->mu);
 	const int fd = open(fn, O_WRONLY);
 	if (fd < 0) return -1;
-	std::vector<uint8_t> buf;
-	buf.reserve(16u << 20);
-	uint64_t at = offset;
-	bool ok = true;
-	auto flush = [&]() {
-		size_t done = 0;
-		while (ok && done < buf.size()) { const ssize_t w = pwrite(fd, buf.data() + done, buf.size() - done, (off_t)(at + done)); if (w <= 0) ok = false; else done += (size_t)w; }
-		at += buf.size();
-		buf.clear();
-	};
-	serialise(b, [&](const void *p, size_t n) {
-		const uint8_t *q = (const uint8_t*)p;
-		while (n) {
-			const size_t m = std::min(n, (size_t)(16u << 20) - buf.size());
-			buf.insert(buf.end(), q, q + m);
-			q += m; n -= m;
-			if (buf.size() >= (16u << 20)) flush();
-		}
-	}, with_header != 0);
-	flush();
+	const int64_t n = dump_engine_at(b, b->eng, with_header != 0, fd, offset);
 	close(fd);
-	return ok ? (int64_t)(at - offset) : -1;
+	return n;
 	GUARD_END(-1)
 }
-extern "C" int64_t yakb_ch_dump_shard_mem(const yak_ch_t *h, int with_header, uint8_t **out) { return dump_mem(h, out, with_header != 0); }
 
 // test hook (no GPU): the arrays yak_ch_restore_core hands to the device, malloc'd for the caller
 extern "C" int yakb_yak_file_read(const char *fn, int mode, int min_cnt, int mid_cnt, int threads, uint32_t *k, uint32_t *pre,
