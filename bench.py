@@ -379,6 +379,7 @@ def main():
     ap.add_argument("--k", type=int, default=K, help="k-mer length (configs[4] sweeps 21/31/47/63)")
     ap.add_argument("--reads-per-step", type=int, default=16_000_000, help="the global batch of one step (all ranks together)")
     ap.add_argument("--chunk-reads", type=int, default=8_000_000, help="reads per engine chunk / all-to-all round on one rank")
+    ap.add_argument("--min-rounds", type=int, default=2, help="N > 1: rounds per step at least (the exchange of a round overlaps the count of the one before)")
     ap.add_argument("--bf-shift", type=int, default=BF)
     ap.add_argument("--e2e-reads", type=int, default=32_000_000)
     ap.add_argument("--no-e2e", action="store_true")
@@ -408,6 +409,8 @@ def main():
     assert R % world == 0, "--reads-per-step must be a multiple of the number of ranks"
     mine = R // world                                   # this rank's reads of every step (strong scaling)
     rounds = max(1, -(-mine // args.chunk_reads))
+    if world > 1:                                       # at least two rounds per step: extraction + exchange of round i+1 run behind the count of round i
+        rounds = max(rounds, args.min_rounds)
     per_round = -(-mine // rounds)
     rec = L + 1
     genome2 = torch.empty((G + 31) // 32 + 1, dtype=torch.int64, device="cuda")
@@ -446,13 +449,20 @@ def main():
         h = be.h
         stream = torch.cuda.current_stream()
 
+        class _Acc:          # the backend's per-chunk stats, summed over the rounds of a step
+            def __init__(self, inner): self.inner, self.tot = inner, [0, 0, 0, 0]
+            def __getattr__(self, k): return getattr(self.inner, k)
+            def count_events(self, ev, create_new):
+                n = self.inner.count_events(ev, create_new)
+                self.tot = [x + int(y) for x, y in zip(self.tot, self.inner.stats)]
+                return n
+        acc = _Acc(be)
+        sc.b = acc
+
         def step(i):
-            tot = [0, 0, 0, 0]
-            for c in range(rounds):
-                a, b = c * per_round, min(mine, (c + 1) * per_round)
-                n = sc.count_chunk(buf[a * rec:b * rec], 1)
-                tot = [x + y for x, y in zip(tot, [n, int(be.stats[1]), int(be.stats[2]), int(be.stats[3])])]
-            return tot
+            acc.tot = [0, 0, 0, 0]
+            sc.count_rounds([buf[c * per_round * rec:min(mine, (c + 1) * per_round) * rec] for c in range(rounds)], 1)
+            return list(acc.tot)
     for i in range(W):
         make_input(i)
         step(i)

@@ -214,3 +214,53 @@ def test_in_library_multi_gpu_table_operations(yakb):
     r = subprocess.run([sys.executable, "-c", MULTI_SNIPPET.format(root=root, fn=G.input_path("reads_q"), world=world)],
                        env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "multi ok" in r.stdout, r.stderr[-3000:]
+
+
+def _rounds_worker(rank, world, port, fn, k, pre, b, out):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from yak_b200 import dist as yd
+    seqs = [ln.strip() for ln in open(fn, "rb") if ln[:1] in b"ACGTN"]
+    be = yd.GpuBackend(k, pre, b, 4, rank, world)
+    sc = yd.ShardedCounter(be)
+    n_chunks = 7
+
+    def my_part(c):      # chunk c of the file = reads [c*n/7, (c+1)*n/7); rank r takes its world-th of it (file order = chunk, then rank)
+        lo, hi = len(seqs) * c // n_chunks, len(seqs) * (c + 1) // n_chunks
+        a, e = lo + (hi - lo) * rank // world, lo + (hi - lo) * (rank + 1) // world
+        return torch.from_numpy(np.frombuffer(b"".join(s + b"\n" for s in seqs[a:e]) or b"\n", dtype=np.uint8).copy())
+
+    for create_new in ((1, 0) if b > 0 else (1,)):
+        if create_new == 0:
+            sc.second_pass_prepare()
+        sc.count_rounds([my_part(c) for c in range(0, 4)], create_new)      # four rounds pipelined, then three
+        sc.count_rounds([my_part(c) for c in range(4, 7)], create_new)
+    if b > 0:
+        sc.shrink(2, 1023)
+    data = sc.dump_bytes()
+    if rank == 0:
+        open(out, "wb").write(data)
+    be.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k,pre,b", [(31, 12, 0), (31, 10, 21)])
+def test_pipelined_rounds_equal_oracle(yakb, k, pre, b):
+    """ShardedCounter.count_rounds: extraction + exchange of round i+1 behind the count of round i (helper thread, two buffer sets)"""
+    import torch
+    import torch.multiprocessing as mp
+    world = _gpus_pow2()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    fn = G.input_path("reads_q")
+    out = os.path.join(util.TMP, f"yakb_rounds_{k}_{pre}_{b}.yak")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_rounds_worker, args=(world, port, fn, k, pre, b, out), nprocs=world, join=True)
+    h, _ = O.count_file(fn, k=k, pre=pre, bf_shift=b)
+    want = O.dump_bytes(h)
+    got = open(out, "rb").read()
+    assert got == want, util.explain_diff(got, want)
+    O.lib().yo_ch_destroy(h)

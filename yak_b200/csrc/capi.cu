@@ -582,7 +582,9 @@ template<class Sink> static void serialise_engine(ChBox *b, Engine *eng, Sink &&
 	double t_lay = 0, t_sink = 0;
 	// two buffers: while the device rebuilds the layout of slice i+1, a writer thread hands slice i to the sink (the file)
 	LayoutOut lo[2]; // Engine::layout resets them, and their key arrays (gigabytes) keep their pages
-	const std::vector<int> bounds = slice_bounds(eng, 1ull << 28, 512);
+	// slices as large as the host buffers allow (2 x 8 GB of keys): the replay runs one warp per sub-table, so its time per slice
+	// is that of the largest sub-table whatever the number of sub-tables - 8 slices of 512 sub-tables took 8 times as long as one
+	const std::vector<int> bounds = slice_bounds(eng, 1ull << 30, 1 << 30);
 	std::thread writer;
 	struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_on_unwind{writer};
 	for (size_t bi = 0; bi + 1 < bounds.size(); ++bi) {

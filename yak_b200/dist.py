@@ -30,7 +30,7 @@ class GpuBackend:
             raise RuntimeError("yakb_ch_init_shard failed")
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.stats = (C.c_uint64 * 4)()
-        self._out = self._recv = None          # grow-only exchange buffers: NCCL sees the same addresses every chunk
+        self._out = self._recv = self._out1 = self._recv1 = None   # grow-only exchange buffers (two sets: count_rounds works a round ahead)
 
     def _buf(self, name: str, n: int) -> torch.Tensor:
         cur = getattr(self, name)
@@ -40,8 +40,8 @@ class GpuBackend:
             setattr(self, name, cur)
         return cur
 
-    def recv_buffer(self, n: int) -> torch.Tensor:
-        return self._buf("_recv", n)[:n]
+    def recv_buffer(self, n: int, slot: int = 0) -> torch.Tensor:
+        return self._buf("_recv" if slot == 0 else "_recv1", n)[:n]
 
     def to_device(self, asc: bytes | np.ndarray | torch.Tensor) -> torch.Tensor:
         if isinstance(asc, torch.Tensor):
@@ -49,11 +49,11 @@ class GpuBackend:
         a = np.frombuffer(asc, dtype=np.uint8) if isinstance(asc, (bytes, bytearray)) else asc
         return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
 
-    def extract_route(self, asc: torch.Tensor):
+    def extract_route(self, asc: torch.Tensor, slot: int = 0):
         """hashed k-mers of `asc` grouped by owner rank (file order inside a group) and the events per owner as a DEVICE
         tensor: nothing here waits for the GPU (the host learns the counts once, from the all-gather of the exchange)"""
         n = asc.numel()
-        out = self._buf("_out", max(n, 1))
+        out = self._buf("_out" if slot == 0 else "_out1", max(n, 1))
         counts = torch.zeros(self.world, dtype=torch.int64, device=self.device)
         rc = self.lib.yakb_extract_route_async(asc.data_ptr(), n, self.k, self.pre, self.world, out.data_ptr(), counts.data_ptr(),
                                                torch.cuda.current_stream().cuda_stream)
@@ -95,7 +95,7 @@ class GpuBackend:
         return int(n)
 
     def close(self):
-        self._out = self._recv = None
+        self._out = self._recv = self._out1 = self._recv1 = None
         if self.h:
             self.lib.yak_ch_destroy(self.h)
             self.h = None
@@ -157,6 +157,68 @@ class ShardedCounter:
                   tuple([(b - a) * 1e3 for a, b in zip(t, t[1:])] + [recv.numel()]), file=sys.stderr)
         self.events += n
         return n
+
+    def count_rounds(self, slices, create_new: int = 1) -> int:
+        """Several chunks in a row, software-pipelined: while the shard counts round i (the library's own stream), a helper thread
+        extracts round i+1 and runs its exchange (its own stream, NCCL's stream) - the compute-bound extraction and the NVLink
+        transfer hide behind the memory-bound count.  Two sets of exchange buffers; a round is extracted only when the count of
+        the round before last has finished with its buffers.  Results are those of count_chunk per slice."""
+        slices = list(slices)
+        if self.world == 1 or len(slices) < 2 or self._dev().type != "cuda" or not hasattr(self.b, "recv_buffer"):
+            return sum(self.count_chunk(s, create_new) for s in slices)
+        import queue
+        import threading
+        ready: "queue.Queue" = queue.Queue()
+        free = threading.Semaphore(2)
+        err = []
+        dev = self._dev()
+
+        def producer():
+            try:
+                torch.cuda.set_device(dev)
+                stream = torch.cuda.Stream(device=dev)
+                with torch.cuda.stream(stream):
+                    for i, sl in enumerate(slices):
+                        free.acquire()
+                        recv = self._extract_exchange(sl, i & 1)
+                        stream.synchronize()            # the routed events of round i are all here
+                        ready.put(recv)
+            except BaseException as e:                  # noqa: BLE001 - handed to the caller
+                err.append(e)
+                ready.put(None)
+
+        th = threading.Thread(target=producer, daemon=True)
+        th.start()
+        n = 0
+        for _ in slices:
+            recv = ready.get()
+            if recv is None:
+                break
+            n += self.b.count_events(recv, create_new)
+            free.release()
+        th.join()
+        if err:
+            raise err[0]
+        self.events += n
+        return n
+
+    def _extract_exchange(self, asc_local, slot: int) -> torch.Tensor:
+        """count_chunk without the count, on the buffers of `slot`: this rank's share of the events after the exchange"""
+        ev, c_out = self.b.extract_route(self.b.to_device(asc_local), slot)
+        dev = ev.device
+        allc = torch.empty(self.world * self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, c_out.contiguous(), group=self.group)
+        m = allc.view(self.world, self.world).cpu()
+        out_splits = [int(x) for x in m[self.rank].tolist()]
+        in_splits = [int(x) for x in m[:, self.rank].tolist()]
+        recv = self.b.recv_buffer(sum(in_splits), slot)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_to_all_single(recv, ev[:sum(out_splits)], output_split_sizes=in_splits, input_split_sizes=out_splits, group=self.group)
+        e1.record()
+        self._a2a_events.append((e0, e1))
+        self.a2a_bytes += 8 * (sum(out_splits) - out_splits[self.rank])
+        return recv
 
     def a2a_ms(self) -> float:
         """device time of the payload all-to-alls so far (call after a synchronize)"""
