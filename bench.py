@@ -379,7 +379,10 @@ def main():
     ap.add_argument("--k", type=int, default=K, help="k-mer length (configs[4] sweeps 21/31/47/63)")
     ap.add_argument("--reads-per-step", type=int, default=16_000_000, help="the global batch of one step (all ranks together)")
     ap.add_argument("--chunk-reads", type=int, default=8_000_000, help="reads per engine chunk / all-to-all round on one rank")
-    ap.add_argument("--min-rounds", type=int, default=2, help="N > 1: rounds per step at least (the exchange of a round overlaps the count of the one before)")
+    ap.add_argument("--min-rounds", type=int, default=1,
+                    help="N > 1: rounds per step at least; with 2 or more, extraction + exchange of a round run behind the count of the one before "
+                         "(ShardedCounter.count_rounds) - measured at N = 2: 17.30 vs 17.41 G events/s, the count saturates the memory system and the "
+                         "overlapped extraction just takes longer (profiles/r02_bench_2gpu.md), so the default is one round")
     ap.add_argument("--bf-shift", type=int, default=BF)
     ap.add_argument("--e2e-reads", type=int, default=32_000_000)
     ap.add_argument("--no-e2e", action="store_true")
@@ -409,7 +412,7 @@ def main():
     assert R % world == 0, "--reads-per-step must be a multiple of the number of ranks"
     mine = R // world                                   # this rank's reads of every step (strong scaling)
     rounds = max(1, -(-mine // args.chunk_reads))
-    if world > 1:                                       # at least two rounds per step: extraction + exchange of round i+1 run behind the count of round i
+    if world > 1:
         rounds = max(rounds, args.min_rounds)
     per_round = -(-mine // rounds)
     rec = L + 1

@@ -7,9 +7,9 @@ import bench
 from yak_b200 import capi
 lib = capi.lib()
 G = int(float(sys.argv[1])) if len(sys.argv) > 1 else 3_000_000_000
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 75
 bf = int(sys.argv[3]) if len(sys.argv) > 3 else 37
-nr, L = 2_000_000, 150
+nr, L = 8_000_000, 150   # chunks of 8 M reads: 75 of them are config 2's 600 M reads
 cur = torch.cuda.current_stream().cuda_stream
 g2 = torch.empty((G + 31) // 32 + 1, dtype=torch.int64, device="cuda")
 lib.yakb_synth_genome_dev(bench.SEED_G, G, g2.data_ptr(), cur)
