@@ -352,7 +352,14 @@ def roofline_objects(prof, ms, peak, peak_kind):
         ab = ALG_UNIT[nm] * units
         ach = ab / (tms / 1000.0) / 1e9
         tr = traffic.get(nm, {})
-        per[nm] = {"kernel": nm, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        # a table update is one random 32-byte sector read-modify-write: what binds such kernels is how many sector accesses per
+        # second DRAM serves, not bytes (tools/gups.cu on this pool: 37.7 G random sector loads/s, 2 x 15.8 G for load+store pairs
+        # spread over 32 GiB, profiles/r01_gups_random_access.txt); reported next to the byte roofline when ncu traffic is known
+        acc = None
+        if tr.get("dram_bytes_per_unit"):
+            acc = {"achieved_G_sectors_per_s": tr["dram_bytes_per_unit"] * units / 32.0 / (tms / 1000.0) / 1e9,
+                   "unconfined_random_G_sectors_per_s": 37.7, "source": "ncu DRAM bytes / 32 B over the live kernel time; peak: profiles/r01_gups_random_access.txt"}
+        per[nm] = {"kernel": nm, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "dram_access_rate": acc,
                    "traffic": (tr.get("dram_bytes_per_unit") * units / max(nl, 1)) if tr.get("dram_bytes_per_unit") else None,
                    "traffic_source": tr.get("source"), "peak_source": peak_kind, "launches": nl, "kernel_ms_total": tms,
                    "units": units, "algorithmic_bytes_per_unit": ALG_UNIT[nm], "algorithmic_bytes_per_launch": ab / max(nl, 1),
@@ -570,9 +577,12 @@ def main():
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             dt1, dt = float(tmax[0]), float(tmax[1])
             what1 = f"pass 1 (-b{args.bf_shift}) of {args.e2e_reads} FASTQ reads in tmpfs on {world} GPUs: parse + H2D + extract + all-to-all + count, {n_ev} events (max over ranks)"
-        e2e = {"value": n_ev / dt1, "unit": "events/s", "n_gpus_used": world, "h2d_bytes_per_step": args.e2e_reads * (L + 1),
+        # the text itself crosses PCIe (device-side ingest of files >= 256 MB); with YAKB_GPU_INGEST=0 it would be the L+1 bytes per read the host parser keeps
+        text_bytes = args.e2e_reads * (2 * L + 7)
+        h2d = text_bytes if text_bytes >= (256 << 20) and os.environ.get("YAKB_GPU_INGEST", "") != "0" else args.e2e_reads * (L + 1)
+        e2e = {"value": n_ev / dt1, "unit": "events/s", "n_gpus_used": world, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 8 * world, "seconds": dt1, "distinct_after_pass1": tot1, "events": n_ev, "what": what1}
-        e2e_full = {"value": n_ev / dt, "unit": "input events/s", "seconds": dt, "h2d_bytes": 2 * args.e2e_reads * (L + 1),
+        e2e_full = {"value": n_ev / dt, "unit": "input events/s", "seconds": dt, "h2d_bytes": 2 * h2d,
                     "what": f"the whole `yak count -b{args.bf_shift} -o` job on the same file on {world} GPU(s): both passes + shrink + dump"}
     lib.yakb_device_cache_trim()
     if world > 1:  # every rank leaves the process group together; the legs below are rank 0's alone

@@ -408,3 +408,60 @@ def test_public_bloom_filter_matches_oracle(oracle, yakb, n_shift, n_hashes):
         assert L.yak_bf_insert(bg, int(x)) == OL.yo_bloom_insert(bo, int(x))
     L.yak_bf_destroy(bg); OL.yo_bloom_destroy(bo)
     L.yak_bf_destroy(None)                                                 # bbf.c:22: NULL-safe
+
+
+@pytest.mark.parametrize("k", [32, 63])
+def test_the_key_that_looks_like_an_empty_slot(oracle, yakb, k):
+    """k >= 32 with -p10: the stored key whose 54 id bits are all ones, at count 1023, is the bit pattern the device table uses for an
+    empty slot (csrc/yakb_dev.cuh YAKB_SAT_BYTES).  Every way a counter is written or read, on exactly that key: counting up to and past
+    the cap, lookups, histogram, increments one by one, dump, restore of a file that holds the pattern, shrink, clear - against the oracle
+    (khashl has a used-bit per slot, khashl.h:92-96, and no such special value)."""
+    OL, L = oracle.lib(), yakb.lib()
+    OL.yo_ch_inc.restype = C.c_int
+    OL.yo_ch_inc.argtypes = [C.POINTER(oracle.YoCh), C.c_uint64]
+    pre = 10
+    star = np.uint64(0xFFFFFFFFFFFFFFFF)                         # id bits all ones, sub-table 1023
+    near = [np.uint64(0xFFFFFFFFFFFFFFFF ^ (1 << b)) for b in (10, 11, 40, 63)] + [np.uint64(0x7FFFFFFFFFFFFBFF)]   # neighbours in the same and other sub-tables
+    rng = np.random.default_rng(k)
+    filler = rng.integers(0, 1 << 63, 3000, dtype=np.uint64) | np.uint64(1023)   # more keys of sub-table 1023: the table grows around it
+    ho, hg = OL.yo_ch_init(k, pre, 4, 0), L.yak_ch_init(k, pre, 4, 0)
+
+    def feed(ev, create_new=1):
+        ev = np.ascontiguousarray(ev, dtype=np.uint64)
+        sub = (ev & np.uint64((1 << pre) - 1)).astype(np.int64)
+        order = np.argsort(sub, kind="stable")
+        evs, subs = ev[order], sub[order]
+        for lst in np.split(evs, np.flatnonzero(np.diff(subs)) + 1):
+            a, p = util.u64_array(lst)
+            assert OL.yo_ch_insert_list(ho, create_new, len(a), p) == L.yak_ch_insert_list(hg, create_new, len(a), p)
+
+    def same(tag):
+        a, b = yakb.dump_bytes(hg), oracle.dump_bytes(ho)
+        assert a == b, (tag, util.explain_diff(a, b))
+        h1, h2 = (C.c_int64 * 1024)(), (C.c_int64 * 1024)()
+        OL.yo_ch_hist(ho, h1); L.yak_ch_hist(hg, h2, 1)
+        assert list(h1) == list(h2), tag
+        for x in [star] + near:
+            assert L.yak_ch_get(hg, int(x)) == OL.yo_ch_get(ho, int(x)), (tag, hex(int(x)))
+
+    feed(np.concatenate([np.full(1020, star), near, filler[:1000], np.full(700, near[0])]))
+    same("1020")
+    feed(np.concatenate([np.full(2, star), filler[1000:2000]]))           # 1022: the last value a slot holds
+    same("1022")
+    feed(np.full(1, star)); same("1023")                                  # the step that would write the empty pattern
+    feed(np.concatenate([np.full(50, star), filler[2000:]])); same("past the cap, table grown")
+    assert L.yak_ch_inc(hg, int(star)) == OL.yo_ch_inc(ho, int(star)) == 1023
+    fn = os.path.join(util.TMP, f"yakb_star_{k}.yak")
+    assert OL.yo_ch_dump(ho, fn.encode()) == 0                            # the file holds the pattern as a key
+    hr = L.yak_ch_restore(fn.encode())
+    ho2 = OL.yo_ch_restore(fn.encode())
+    assert yakb.dump_bytes(hr) == oracle.dump_bytes(ho2)
+    assert L.yak_ch_get(hr, int(star)) == 1023
+    L.yak_ch_destroy(hr); OL.yo_ch_destroy(ho2)
+    OL.yo_ch_shrink(ho, 1000, 1023); L.yak_ch_shrink(hg, 1000, 1023, 1); same("shrink keeps it")
+    OL.yo_ch_clear(ho); L.yak_ch_clear(hg, 1); same("clear")
+    feed(np.full(1022, star), create_new=0); same("count-only pass to 1022")
+    for want in (1023, 1023):                                             # one by one over the edge (htab.c:80-91)
+        assert L.yak_ch_inc(hg, int(star)) == OL.yo_ch_inc(ho, int(star)) == want
+    same("inc over the edge")
+    L.yak_ch_destroy(hg); OL.yo_ch_destroy(ho)

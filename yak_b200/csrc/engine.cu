@@ -193,7 +193,7 @@ std::string Prof::json()
 // Probe one event per lane, all 32 lanes in lock step (explicit convergence: data-dependent
 // probe lengths otherwise leave the warp serialised).  `first` is the already loaded home bucket.
 // Returns 1 if the key is in the table (its counter bumped by one, saturating), 0 if absent.
-__device__ __forceinline__ int probe_inc_warp(uint64_t *reg, uint32_t nbk, uint64_t x, uint32_t bi, Bucket b, bool valid)
+__device__ __forceinline__ int probe_inc_warp(uint64_t *reg, uint32_t nbk, uint64_t x, uint32_t bi, Bucket b, bool valid, uint8_t *sat_s)
 {
 	bool done = !valid;
 	int found = 0;
@@ -203,6 +203,7 @@ __device__ __forceinline__ int probe_inc_warp(uint64_t *reg, uint32_t nbk, uint6
 			if (m >= 0) {
 				const uint64_t c = bucket_get(b, m);
 				if ((c & YAKB_MAX_COUNT) == YAKB_MAX_COUNT) { found = 1; done = true; }
+				else if (c == YAKB_ALMOST_EMPTY) { *sat_s = 1; found = 1; done = true; } // c + 1 would be EMPTY (YAKB_SAT_BYTES)
 				else {
 					uint64_t *p = reg + (uint64_t)bi * YAKB_BUCKET + m;
 					const uint64_t prev = atomicCAS((unsigned long long*)p, (unsigned long long)c, (unsigned long long)(c + 1));
@@ -240,7 +241,10 @@ __device__ __forceinline__ uint32_t probe_inc4(uint64_t *slots, uint32_t cap, ui
 				if (m >= 0) {
 					const uint64_t c = bucket_get(bk[j], m);
 					if ((c & YAKB_MAX_COUNT) == YAKB_MAX_COUNT) { hit |= 1u << j; todo &= ~(1u << j); } // htab.c:69: stays at the cap
-					else {
+					else if (c == YAKB_ALMOST_EMPTY) { // c + 1 would be EMPTY: the last step of this one key is a flag (YAKB_SAT_BYTES)
+						sat_of(slots)[(uint32_t)v[j] & Pmask & (YAKB_SAT_BYTES - 1)] = 1;
+						hit |= 1u << j; todo &= ~(1u << j);
+					} else {
 						uint64_t *q = slots + (uint64_t)((uint32_t)v[j] & Pmask) * cap + (uint64_t)bi[j] * YAKB_BUCKET + m;
 						expect[j] = c;
 						prev[j] = atomicCAS((unsigned long long*)q, (unsigned long long)c, (unsigned long long)(c + 1));
@@ -383,7 +387,7 @@ struct ZGroup { uint64_t v[4]; uint32_t pos[4]; uint32_t vm; };
 
 __device__ __forceinline__ void zone_fetch(ZGroup &q, uint64_t item, uint32_t g, uint64_t n_items, uint32_t spz, uint32_t zcap,
                                            const uint64_t *__restrict__ zev, const uint32_t *__restrict__ zpos, const unsigned int *__restrict__ zfill,
-                                           int pre, uint32_t Pmask, const uint64_t *slots, uint32_t cap, uint32_t nbk)
+                                           int pre, uint32_t Pmask, const uint64_t *slots, uint32_t cap, uint32_t nbk, bool prefetch)
 {
 	q.vm = 0;
 	if (item >= n_items) return;
@@ -398,8 +402,10 @@ __device__ __forceinline__ void zone_fetch(ZGroup &q, uint64_t item, uint32_t g,
 		if (i < nz) {
 			q.v[j] = ev[i]; q.pos[j] = ep[i];
 			q.vm |= 1u << j;
-			const uint64_t *bp = slots + (uint64_t)((uint32_t)q.v[j] & Pmask) * cap + (uint64_t)tab_home(q.v[j] >> pre, nbk) * YAKB_BUCKET;
-			asm volatile("prefetch.global.L2 [%0];" :: "l"(bp));
+			if (prefetch) { // off by default: ncu shows 92 instead of 69 B of DRAM reads per event with it (whole lines come in) and no gain
+				const uint64_t *bp = slots + (uint64_t)((uint32_t)q.v[j] & Pmask) * cap + (uint64_t)tab_home(q.v[j] >> pre, nbk) * YAKB_BUCKET;
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(bp));
+			}
 		}
 	}
 }
@@ -408,7 +414,7 @@ template<int MINB>
 __global__ void __launch_bounds__(256, MINB) zone_probe(const uint64_t *__restrict__ zev, const uint32_t *__restrict__ zpos, uint32_t n_list, uint32_t zcap,
                                                     const unsigned int *__restrict__ zfill, int pre, uint32_t Pmask,
                                                     uint64_t *slots, uint32_t cap, int create_new, uint32_t *flags,
-                                                    uint32_t *glob_lput, int smem_lp, unsigned int *work, uint32_t zsub)
+                                                    uint32_t *glob_lput, int smem_lp, unsigned int *work, uint32_t zsub, bool prefetch)
 {
 	extern __shared__ uint32_t s_lp[];
 	__shared__ uint32_t s_item[2];
@@ -421,7 +427,7 @@ __global__ void __launch_bounds__(256, MINB) zone_probe(const uint64_t *__restri
 	__syncthreads();
 	uint64_t item = s_item[0];
 	ZGroup nx;
-	zone_fetch(nx, item, 0, n_items, spz, zcap, zev, zpos, zfill, pre, Pmask, slots, cap, nbk);
+	zone_fetch(nx, item, 0, n_items, spz, zcap, zev, zpos, zfill, pre, Pmask, slots, cap, nbk, prefetch);
 	for (uint32_t it = 0; item < n_items; ++it) {
 		if (threadIdx.x == 0) s_item[(it + 1) & 1] = atomicAdd(work, 1u); // needed one slice from now
 		const uint32_t s0 = (uint32_t)(item / spz) * zsub; // first sub-table of the slice's zone
@@ -432,11 +438,11 @@ __global__ void __launch_bounds__(256, MINB) zone_probe(const uint64_t *__restri
 #pragma unroll 1
 		for (uint32_t g = 0; g < YAKB_ZGROUPS; ++g) {
 			ZGroup cur = nx;
-			if (g + 1 < YAKB_ZGROUPS) zone_fetch(nx, item, g + 1, n_items, spz, zcap, zev, zpos, zfill, pre, Pmask, slots, cap, nbk);
+			if (g + 1 < YAKB_ZGROUPS) zone_fetch(nx, item, g + 1, n_items, spz, zcap, zev, zpos, zfill, pre, Pmask, slots, cap, nbk, prefetch);
 			else {
 				__syncthreads(); // thread 0's fetch of the next item, issued a slice ago, is visible; one barrier per slice
 				next_item = s_item[(it + 1) & 1];
-				zone_fetch(nx, next_item, 0, n_items, spz, zcap, zev, zpos, zfill, pre, Pmask, slots, cap, nbk);
+				zone_fetch(nx, next_item, 0, n_items, spz, zcap, zev, zpos, zfill, pre, Pmask, slots, cap, nbk, prefetch);
 			}
 			Bucket bk[4];
 			uint32_t bi[4];
@@ -525,7 +531,7 @@ __global__ void __launch_bounds__(256) k1_array(const uint64_t *__restrict__ ev,
 				uint32_t bi = 0;
 				Bucket bk;
 				if (valid) { bi = tab_home(v >> pre, nbk); bk = load_bucket(reg + (uint64_t)bi * YAKB_BUCKET); }
-				found = probe_inc_warp(reg, nbk, v >> pre, bi, bk, valid);
+				found = probe_inc_warp(reg, nbk, v >> pre, bi, bk, valid, sat_of(slots) + (s & (YAKB_SAT_BYTES - 1)));
 			}
 			if (valid) {
 				if (found && create_new) {
@@ -684,7 +690,7 @@ __global__ void __launch_bounds__(256) group_insert(const uint64_t *__restrict__
 		if (put) { // htab.c:66-70
 			uint64_t *slot, cur;
 			if (tab_insert(slots + (uint64_t)s * cap, cap, x << YAKB_COUNTER_BITS | 1, &slot, &cur)) flag = 3;
-			else { slot_inc(slot, cur, 1); flag = 1; }
+			else { slot_inc(slot, cur, 1, sat_of(slots) + (s & (YAKB_SAT_BYTES - 1))); flag = 1; }
 		}
 		if (flag) atomicOr(&pflag[j >> 4], (uint32_t)flag << ((j & 15) * 2));
 	}
@@ -769,8 +775,16 @@ __global__ void bulk_insert_kernel(const uint64_t *__restrict__ keys, const uint
 	if (i >= n) return;
 	uint32_t lo = 0, hi = P; // sub-table s with off[s] <= i < off[s+1]
 	while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
-	uint64_t *slot, cur;
-	tab_insert(slots + (uint64_t)lo * cap, cap, keys[i], &slot, &cur); // a duplicate key in the file: first claim wins
+	uint64_t *slot, cur, val = keys[i];
+	if (val == YAKB_EMPTY) { val = YAKB_ALMOST_EMPTY; sat_of(slots)[lo & (YAKB_SAT_BYTES - 1)] = 1; } // YAKB_SAT_BYTES
+	tab_insert(slots + (uint64_t)lo * cap, cap, val, &slot, &cur); // a duplicate key in the file: first claim wins
+}
+
+// journal entries are keys without counts; unlike a table slot, a journal entry may legitimately be all ones (YAKB_SAT_BYTES)
+__global__ void strip_counts_kernel(uint64_t *keys, uint64_t n)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (i < n) keys[i] &= ~(uint64_t)YAKB_MAX_COUNT;
 }
 
 __global__ void clear_kernel(uint64_t *slots, uint64_t total)
@@ -779,14 +793,14 @@ __global__ void clear_kernel(uint64_t *slots, uint64_t total)
 	if (i < total) { uint64_t v = slots[i]; if (v != YAKB_EMPTY) slots[i] = v & ~(uint64_t)YAKB_MAX_COUNT; }
 }
 
-__global__ void __launch_bounds__(256) hist_kernel(const uint64_t *__restrict__ slots, uint64_t total, unsigned long long *hist)
+__global__ void __launch_bounds__(256) hist_kernel(const uint64_t *__restrict__ slots, uint64_t total, uint32_t cap, unsigned long long *hist)
 {
 	__shared__ uint32_t s_h[1024];
 	for (int i = threadIdx.x; i < 1024; i += 256) s_h[i] = 0;
 	__syncthreads();
 	for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < total; i += gridDim.x * 256ull) {
 		uint64_t v = slots[i];
-		if (v != YAKB_EMPTY) atomicAdd(&s_h[v & YAKB_MAX_COUNT], 1u);
+		if (v != YAKB_EMPTY) atomicAdd(&s_h[v == YAKB_ALMOST_EMPTY ? slot_count(slots, (uint32_t)(i / cap), v) : (uint32_t)(v & YAKB_MAX_COUNT)], 1u);
 	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < 1024; i += 256) if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
@@ -802,7 +816,7 @@ __global__ void get_batch_kernel(const uint64_t *__restrict__ xs, uint64_t n, in
 	int32_t r = -1;
 	if (cap && ((uint32_t)(v >> own.shift) & own.mask) == own.rank) {
 		int64_t q = tab_find(slots + (uint64_t)((uint32_t)v & Pmask) * cap, cap, v >> pre);
-		if (q >= 0) r = (int32_t)(slots[(uint64_t)((uint32_t)v & Pmask) * cap + q] & YAKB_MAX_COUNT);
+		if (q >= 0) r = (int32_t)slot_count(slots, (uint32_t)v & Pmask, slots[(uint64_t)((uint32_t)v & Pmask) * cap + q]);
 	}
 	out[i] = r;
 }
@@ -825,7 +839,7 @@ __global__ void __launch_bounds__(256) qv_scan_kernel(const uint64_t *__restrict
 		if (cap && ((uint32_t)(v >> own.shift) & own.mask) == own.rank) {
 			const uint64_t *reg = slots + (uint64_t)((uint32_t)v & Pmask) * cap;
 			int64_t q = tab_find(reg, cap, v >> pre);
-			if (q >= 0) c = (int16_t)(reg[q] & YAKB_MAX_COUNT);
+			if (q >= 0) c = (int16_t)slot_count(slots, (uint32_t)v & Pmask, reg[q]);
 		}
 		res[r] = c;
 	});
@@ -1190,7 +1204,7 @@ __global__ void fill_counts_kernel(uint64_t *keys, const uint64_t *__restrict__ 
 	const uint64_t *reg = slots + (uint64_t)(s0 + lo) * cap;
 	uint64_t key = keys[i];
 	int64_t q = tab_find(reg, cap, key >> YAKB_COUNTER_BITS);
-	if (q >= 0) keys[i] = (key & ~(uint64_t)YAKB_MAX_COUNT) | (reg[q] & YAKB_MAX_COUNT);
+	if (q >= 0) keys[i] = (key & ~(uint64_t)YAKB_MAX_COUNT) | slot_count(slots, (uint32_t)(s0 + lo), reg[q]);
 }
 
 // ============================================================ host side
@@ -1242,7 +1256,7 @@ Engine *Engine::create(int k, int pre, int n_hash, int n_shift, int rank, int wo
 
 Engine::~Engine()
 {
-	dev_free(slots); dev_free(nkeys); dev_free(bloom); dev_free(last_put); dev_free(last_new);
+	free_slots(); dev_free(nkeys); dev_free(bloom); dev_free(last_put); dev_free(last_new);
 	journal_free_all();
 	DBuf *all[] = {&b_w2, &b_wm, &b_flags, &b_tilecnt, &b_tileoff, &b_pv, &b_ppos, &b_sv, &b_sj, &b_sv2, &b_sj2, &b_pflag, &b_newv,
 	               &b_newsorted, &b_tmp, &b_pend, &b_lput, &b_lnew, &b_stats, &b_misc, &b_zev, &b_zpos, &b_zsp, &b_zspp, &b_zfill,
@@ -1276,6 +1290,7 @@ void Engine::journal_free_all()
 }
 
 void Engine::destroy_bloom() { if (bloom) { dev_free(bloom); bloom = nullptr; } }
+void Engine::free_slots() { if (slots) dev_free((uint8_t*)slots - YAKB_SAT_BYTES); slots = nullptr; }
 
 uint64_t Engine::device_bytes() const
 {
@@ -1292,14 +1307,20 @@ void Engine::grow(uint32_t new_cap)
 		YAKB_CUDA(cudaStreamSynchronize(stream));
 		b_zev.release(); b_zpos.release(); b_zsp.release(); b_zspp.release();
 	}
-	ns = (uint64_t*)dev_alloc(total_new * 8);
+	// YAKB_SAT_BYTES of flags in front of the table (yakb_dev.cuh): they move with the table
+	uint8_t *base = (uint8_t*)dev_alloc(total_new * 8 + YAKB_SAT_BYTES);
+	ns = (uint64_t*)(base + YAKB_SAT_BYTES);
+	YAKB_CUDA(cudaMemsetAsync(base, 0, YAKB_SAT_BYTES, stream));
 	YAKB_CUDA(cudaMemsetAsync(ns, 0xFF, total_new * 8, stream));
+	if (slots) YAKB_CUDA(cudaMemcpyAsync(base, (uint8_t*)slots - YAKB_SAT_BYTES, YAKB_SAT_BYTES, cudaMemcpyDeviceToDevice, stream));
 	if (slots && cap) {
 		const uint64_t total_old = (uint64_t)P * cap;
 		rehash_kernel<<<cdiv(total_old, 256), 256, 0, stream>>>(slots, cap, total_old, ns, new_cap);
 		YAKB_CUDA(cudaGetLastError());
+	}
+	if (slots) {
 		YAKB_CUDA(cudaStreamSynchronize(stream));
-		dev_free(slots);
+		free_slots();
 	}
 	slots = ns; cap = new_cap;
 }
@@ -1405,17 +1426,18 @@ bool Engine::probe_partitioned(uint64_t nwords, int create_new, const uint64_t *
 	if (create_new) YAKB_CUDA(cudaMemsetAsync(flags, 0, nwords * 4, stream));
 	{ ProfScope ps("zone_probe", stream);
 	const uint32_t zsub = (1u << zshift) <= 8 ? (1u << zshift) : 0;
+	static const int zpref = getenv("YAKB_ZPROBE_PREFETCH") ? atoi(getenv("YAKB_ZPROBE_PREFETCH")) : 0;
 	static const int zocc = getenv("YAKB_ZPROBE_OCC") ? atoi(getenv("YAKB_ZPROBE_OCC")) : 2; // resident CTAs per SM (2: no register spills; measured 11.5 vs 10.2 G events/s for 3)
 	if (zocc == 2) {
 		set_smem(zone_probe<2>, sm1);
-		zone_probe<2><<<nsm * 2, 256, sm1, stream>>>(zev, zpos, Z, zcap, zfill, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 1, zsub);
+		zone_probe<2><<<nsm * 2, 256, sm1, stream>>>(zev, zpos, Z, zcap, zfill, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 1, zsub, zpref != 0);
 	} else {
 		set_smem(zone_probe<3>, sm1);
-		zone_probe<3><<<nsm * 3, 256, sm1, stream>>>(zev, zpos, Z, zcap, zfill, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 1, zsub);
+		zone_probe<3><<<nsm * 3, 256, sm1, stream>>>(zev, zpos, Z, zcap, zfill, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 1, zsub, zpref != 0);
 	}
 	// the spill list: one more list whose fill count is n_spill
 	if (n_spill) set_smem(zone_probe<3>, sm1);
-	if (n_spill) zone_probe<3><<<nsm * 3, 256, sm1, stream>>>(sp_ev, sp_pos, 1, spill_cap, zfill + Z, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 2, 0);
+	if (n_spill) zone_probe<3><<<nsm * 3, 256, sm1, stream>>>(sp_ev, sp_pos, 1, spill_cap, zfill + Z, pre, P - 1, slots, cap, create_new, flags, lput, smem1, zfill + Z + 2, 0, false);
 	if (create_new) flag_tilecnt_kernel<<<(uint32_t)ntiles, 256, 0, stream>>>(flags, nwords, tilecnt); }
 	YAKB_CUDA(cudaGetLastError());
 	note_launch(1 + (n_spill ? 1 : 0) + (create_new ? 1 : 0));
@@ -1628,15 +1650,27 @@ __global__ void upsert_kernel(const uint64_t *__restrict__ keys, const uint64_t 
 	if (i >= n) return;
 	uint32_t lo = 0, hi = P; // sub-table s with off[s] <= i < off[s+1]
 	while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
-	const uint64_t val = keys[i];
+	uint64_t val = keys[i];
 	uint64_t *slot, cur;
+	if (val == YAKB_EMPTY) { val = YAKB_ALMOST_EMPTY; sat_of(slots)[lo & (YAKB_SAT_BYTES - 1)] = 1; } // YAKB_SAT_BYTES
 	if (tab_insert(slots + (uint64_t)lo * cap, cap, val, &slot, &cur)) {
 		isnew[i] = 1;
 		atomicAdd(&newcnt[lo], 1u);
 		atomicMax(&lnew[lo], (uint32_t)(i - off[lo]) + 1);
 	} else {
 		isnew[i] = 0;
-		if (or_bits && (val & YAKB_MAX_COUNT)) atomicOr((unsigned long long*)slot, (unsigned long long)(val & YAKB_MAX_COUNT));
+		if (or_bits && (val & YAKB_MAX_COUNT)) {
+			// OR the bits in; the result EMPTY (all id bits and all ten low bits set) is stored as ALMOST_EMPTY + the flag
+			uint64_t bits = keys[i] & YAKB_MAX_COUNT;
+			for (;;) {
+				uint64_t want = cur | bits;
+				if (want == YAKB_EMPTY) { want = YAKB_ALMOST_EMPTY; sat_of(slots)[lo & (YAKB_SAT_BYTES - 1)] = 1; }
+				if (want == cur) break;
+				const uint64_t prev = atomicCAS((unsigned long long*)slot, (unsigned long long)cur, (unsigned long long)want);
+				if (prev == cur) break;
+				cur = prev;
+			}
+		}
 	}
 }
 
@@ -1689,7 +1723,7 @@ uint64_t Engine::upsert(const std::vector<uint32_t> &caps, const std::vector<uin
 		seg.off = (uint64_t*)journal_alloc((uint64_t)(P + 1) * 8);
 		YAKB_CUDA(cudaMemcpyAsync(seg.keys, d_new, n_new * 8, cudaMemcpyDeviceToDevice, stream));
 		YAKB_CUDA(cudaMemcpyAsync(seg.off, noff.data(), (uint64_t)(P + 1) * 8, cudaMemcpyHostToDevice, stream));
-		clear_kernel<<<cdiv(n_new, 256), 256, 0, stream>>>(seg.keys, n_new); // journal entries are puts: no low bits
+		strip_counts_kernel<<<cdiv(n_new, 256), 256, 0, stream>>>(seg.keys, n_new); // journal entries are puts: no low bits
 		YAKB_CUDA(cudaGetLastError());
 		journal.push_back(seg);
 	}
@@ -1706,6 +1740,7 @@ void Engine::clear()
 {
 	const uint64_t total = (uint64_t)P * cap;
 	if (total) clear_kernel<<<cdiv(total, 256), 256, 0, stream>>>(slots, total);
+	if (slots) YAKB_CUDA(cudaMemsetAsync((uint8_t*)slots - YAKB_SAT_BYTES, 0, YAKB_SAT_BYTES, stream)); // the flags are counter bits too
 	YAKB_CUDA(cudaGetLastError());
 	YAKB_CUDA(cudaStreamSynchronize(stream));
 }
@@ -1715,7 +1750,7 @@ void Engine::hist(int64_t cnt[1024])
 	unsigned long long *d = (unsigned long long*)b_tmp.need(1024 * 8);
 	YAKB_CUDA(cudaMemsetAsync(d, 0, 1024 * 8, stream));
 	const uint64_t total = (uint64_t)P * cap;
-	if (total) hist_kernel<<<std::min<uint32_t>(cdiv(total, 256), 148 * 8), 256, 0, stream>>>(slots, total, d);
+	if (total) hist_kernel<<<std::min<uint32_t>(cdiv(total, 256), 148 * 8), 256, 0, stream>>>(slots, total, cap, d);
 	YAKB_CUDA(cudaGetLastError());
 	YAKB_CUDA(cudaMemcpyAsync(cnt, d, 1024 * 8, cudaMemcpyDeviceToHost, stream));
 	YAKB_CUDA(cudaStreamSynchronize(stream));
@@ -1934,7 +1969,7 @@ void Engine::load_subtables(const std::vector<uint32_t> &caps, const std::vector
 		ProfScope ps("load(bulk insert)", stream);
 		YAKB_CUDA(cudaMemcpyAsync(seg.keys, keys, n * 8, keys_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
 		bulk_insert_kernel<<<cdiv(n, 256), 256, 0, stream>>>(seg.keys, seg.off, P, n, slots, cap);
-		clear_kernel<<<cdiv(n, 256), 256, 0, stream>>>(seg.keys, n); // journal keeps keys without counts
+		strip_counts_kernel<<<cdiv(n, 256), 256, 0, stream>>>(seg.keys, n); // journal keeps keys without counts
 		YAKB_CUDA(cudaGetLastError());
 	}
 	YAKB_CUDA(cudaMemcpyAsync(nkeys, cnt.data(), P * 4, cudaMemcpyHostToDevice, stream));
@@ -2004,8 +2039,10 @@ void Engine::reset_table(const std::vector<uint64_t> &off)
 	uint64_t mx = 8;
 	for (int s = 0; s < P; ++s) mx = std::max<uint64_t>(mx, off[s + 1] - off[s]);
 	const uint64_t want = ((uint64_t)(mx / load_limit) + 16 + 3) & ~3ull;
-	if (slots && cap >= want) YAKB_CUDA(cudaMemsetAsync(slots, 0xFF, (uint64_t)P * cap * 8, stream));
-	else if (slots) { dev_free(slots); slots = nullptr; cap = 0; }
+	if (slots && cap >= want) {
+		YAKB_CUDA(cudaMemsetAsync(slots, 0xFF, (uint64_t)P * cap * 8, stream));
+		YAKB_CUDA(cudaMemsetAsync((uint8_t*)slots - YAKB_SAT_BYTES, 0, YAKB_SAT_BYTES, stream));
+	} else if (slots) { free_slots(); cap = 0; }
 }
 
 void Engine::rebuild(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys)

@@ -95,6 +95,7 @@ struct Engine {
 	static Engine *create(int k, int pre, int n_hash, int n_shift, int rank = 0, int world = 1);
 	~Engine();
 	void destroy_bloom();
+	void free_slots();                             // the table allocation starts YAKB_SAT_BYTES in front of `slots` (yakb_dev.cuh)
 
 	// ---- per-chunk hot path ----
 	// bases: device ASCII (any non-ACGTU byte separates reads), n bytes

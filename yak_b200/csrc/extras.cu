@@ -265,8 +265,11 @@ __global__ void inc_one_kernel(uint64_t *slots, uint32_t cap, int pre, uint32_t 
 		int64_t q = tab_find(reg, cap, v >> pre);
 		if (q >= 0) {
 			uint64_t cur = reg[q];
-			if ((cur & YAKB_MAX_COUNT) < YAKB_MAX_COUNT) reg[q] = ++cur;
-			r = (int32_t)(cur & YAKB_MAX_COUNT);
+			if (cur == YAKB_ALMOST_EMPTY) { sat_of(slots)[(uint32_t)v & Pmask & (YAKB_SAT_BYTES - 1)] = 1; r = YAKB_MAX_COUNT; } // YAKB_SAT_BYTES
+			else {
+				if ((cur & YAKB_MAX_COUNT) < YAKB_MAX_COUNT) reg[q] = ++cur;
+				r = (int32_t)(cur & YAKB_MAX_COUNT);
+			}
 		}
 	}
 	*out = r;
@@ -281,15 +284,23 @@ int inc_one(Engine *e, uint64_t v)
 }
 
 // ---- htab.c:219-235
-__global__ void setcnt_kernel(uint64_t *slots, uint64_t total, uint32_t c)
+__global__ void setcnt_kernel(uint64_t *slots, uint64_t total, uint32_t cap, uint32_t c)
 {
 	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-	if (i < total) { uint64_t v = slots[i]; if (v != YAKB_EMPTY) slots[i] = (v & ~(uint64_t)YAKB_MAX_COUNT) | c; }
+	if (i >= total) return;
+	uint64_t v = slots[i];
+	if (v == YAKB_EMPTY) return;
+	uint64_t w = (v & ~(uint64_t)YAKB_MAX_COUNT) | c;
+	if ((v | YAKB_MAX_COUNT) == YAKB_EMPTY) { // the key whose count 1023 is kept as a flag (YAKB_SAT_BYTES)
+		sat_of(slots)[(uint32_t)(i / cap) & (YAKB_SAT_BYTES - 1)] = c == YAKB_MAX_COUNT;
+		if (w == YAKB_EMPTY) w = YAKB_ALMOST_EMPTY;
+	}
+	slots[i] = w;
 }
 void setcnt(Engine *e, int c)
 {
 	const uint64_t total = (uint64_t)e->P * e->cap;
-	if (total) setcnt_kernel<<<cdiv(total, 256), 256, 0, e->stream>>>(e->slots, total, (uint32_t)c);
+	if (total) setcnt_kernel<<<cdiv(total, 256), 256, 0, e->stream>>>(e->slots, total, e->cap, (uint32_t)c);
 	YAKB_CUDA(cudaGetLastError());
 	YAKB_CUDA(cudaStreamSynchronize(e->stream));
 }

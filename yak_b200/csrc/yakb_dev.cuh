@@ -87,6 +87,20 @@ __host__ __device__ __forceinline__ uint32_t nt4(uint32_t c)
 // EMPTY slot.  Most lookups therefore cost exactly one sector.
 #define YAKB_BUCKET 4
 
+// EMPTY = ~0 is itself a possible stored value: the key whose id bits are all ones at count 1023 - which needs a 54-bit id,
+// i.e. k >= 32 together with pre = 10.  That value is never written: the key's counter stops at 1022 in its slot
+// (YAKB_ALMOST_EMPTY) and the last step is kept as one byte per sub-table in front of the table, YAKB_SAT_BYTES before
+// slots[0] (pre = 10 means at most 1024 sub-tables).  Every test is on the VALUE, so configurations in which the value cannot
+// occur pay one compare on the paths that write or read a counter and nothing else.
+#define YAKB_SAT_BYTES 1024
+#define YAKB_ALMOST_EMPTY 0xFFFFFFFFFFFFFFFEull
+__device__ __forceinline__ uint8_t *sat_of(const uint64_t *slots) { return (uint8_t*)slots - YAKB_SAT_BYTES; }
+// the 10-bit count of stored value v of sub-table s
+__device__ __forceinline__ uint32_t slot_count(const uint64_t *slots, uint32_t s, uint64_t v)
+{
+	return (v == YAKB_ALMOST_EMPTY && sat_of(slots)[s]) ? YAKB_MAX_COUNT : (uint32_t)(v & YAKB_MAX_COUNT);
+}
+
 struct Bucket { uint64_t k[4]; };
 
 __device__ __forceinline__ uint32_t tab_home(uint64_t x, uint32_t nbk) // home bucket of x among nbk buckets
@@ -139,13 +153,14 @@ __device__ __forceinline__ int64_t tab_find(const uint64_t *reg, uint32_t cap, u
 
 // Saturating ++ of the 10-bit counter with other threads possibly incrementing the same slot
 // (htab.c:69-70 / 73-74: "if (count < 1023) ++count").
-__device__ __forceinline__ void slot_inc(uint64_t *p, uint64_t cur, uint32_t by)
+__device__ __forceinline__ void slot_inc(uint64_t *p, uint64_t cur, uint32_t by, uint8_t *sat_s)
 {
 	for (;;) {
 		uint32_t c = (uint32_t)(cur & YAKB_MAX_COUNT);
 		if (c >= YAKB_MAX_COUNT) return;
 		uint32_t nc = c + by > YAKB_MAX_COUNT ? YAKB_MAX_COUNT : c + by;
 		uint64_t want = (cur & ~(uint64_t)YAKB_MAX_COUNT) | nc;
+		if (want == YAKB_EMPTY) { *sat_s = 1; want = YAKB_ALMOST_EMPTY; if (want == cur) return; } // see YAKB_SAT_BYTES
 		uint64_t prev = atomicCAS((unsigned long long*)p, (unsigned long long)cur, (unsigned long long)want);
 		if (prev == cur) return;
 		cur = prev;
