@@ -14,7 +14,7 @@ of cfg2 (600 M reads = 90 Gbp = 30x of 3 Gbp), table growth and rehash included.
 STRONG scaling: every N consumes the IDENTICAL read stream.  With N ranks, rank r takes the r-th
 contiguous N-th of each step's batch (16/N M reads), extracts its k-mers, one NCCL all-to-all routes
 them to the owners of their sub-tables, each rank counts on its shard.  A rank's share of a step is
-cut into rounds of at most --chunk-reads reads (one engine chunk / one all-to-all per round).
+cut into rounds of at most --chunk-reads reads (one engine chunk / one all-to-all per round; default: the whole step).
 Each step is bracketed by its own pair of CUDA events; its input is generated on the device before
 it, outside the timed region (max over ranks of the summed step times).
 
@@ -385,7 +385,9 @@ def main():
     ap.add_argument("--genome", type=int, default=3_000_000_000)
     ap.add_argument("--k", type=int, default=K, help="k-mer length (configs[4] sweeps 21/31/47/63)")
     ap.add_argument("--reads-per-step", type=int, default=16_000_000, help="the global batch of one step (all ranks together)")
-    ap.add_argument("--chunk-reads", type=int, default=8_000_000, help="reads per engine chunk / all-to-all round on one rank")
+    ap.add_argument("--chunk-reads", type=int, default=16_000_000,
+                    help="reads per engine chunk / all-to-all round on one rank (16 M reads = 2.4 G positions: one chunk per step at N = 1; "
+                         "12.6 vs 11.9 G events/s for chunks of 8 M, profiles/r02_chunk_size.md)")
     ap.add_argument("--min-rounds", type=int, default=1,
                     help="N > 1: rounds per step at least; with 2 or more, extraction + exchange of a round run behind the count of the one before "
                          "(ShardedCounter.count_rounds) - measured at N = 2: 17.30 vs 17.41 G events/s, the count saturates the memory system and the "

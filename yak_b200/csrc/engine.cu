@@ -1343,7 +1343,7 @@ ChunkStats Engine::count_ascii(const uint8_t *d_asc, uint64_t n, int create_new)
 {
 	ChunkStats st = {0, 0, 0, 0};
 	if (n == 0) return st;
-	if (n >= 0x7FFFFF00ull) throw CudaError("[yakb] chunk too large (positions are 31-bit)");
+	if (n >= 0xFFFFFF00ull) throw CudaError("[yakb] chunk too large (positions are 32-bit)");
 	const uint64_t nwords = (n + 31) / 32;
 	uint64_t *w2 = b_w2.as<uint64_t>(packed_words(nwords)) + YAKB_PADW;
 	uint32_t *wm = b_wm.as<uint32_t>(packed_words(nwords)) + YAKB_PADW;
@@ -1359,7 +1359,7 @@ ChunkStats Engine::count_events(const uint64_t *d_ev, uint64_t n, int create_new
 {
 	ChunkStats st = {0, 0, 0, 0};
 	if (n == 0) return st;
-	if (n >= 0x7FFFFF00ull) throw CudaError("[yakb] chunk too large (positions are 31-bit)");
+	if (n >= 0xFFFFFF00ull) throw CudaError("[yakb] chunk too large (positions are 32-bit)");
 	return finish_chunk((n + 31) / 32, create_new, nullptr, nullptr, d_ev, n, only_s, ignore_bloom);
 }
 

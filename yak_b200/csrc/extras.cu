@@ -141,7 +141,7 @@ int extract_events_async(const uint8_t *d_asc, uint64_t n, int k, int pre, int w
 	}
 	YAKB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)world * 8, stream));
 	if (n == 0) return 0;
-	if (n >= 0x7FFFFF00ull) { fprintf(stderr, "[yakb] ERROR: chunk too large (positions are 31-bit)\n"); return -1; }
+	if (n >= 0xFFFFFF00ull) { fprintf(stderr, "[yakb] ERROR: chunk too large (positions are 32-bit)\n"); return -1; }
 	const uint64_t nwords = (n + 31) / 32, ntiles = (nwords + 255) / 256;
 	uint64_t *w2 = sc.b[0].as<uint64_t>(packed_words(nwords)) + YAKB_PADW;
 	uint32_t *wm = sc.b[1].as<uint32_t>(packed_words(nwords)) + YAKB_PADW;
