@@ -571,41 +571,93 @@ template<class Sink> static void serialise(ChBox *b, Sink &&sink, bool header = 
 	if (b->shards.empty()) { serialise_engine(b, b->eng, sink, header); return; }
 	for (size_t r = 0; r < b->shards.size(); ++r) { DevGuard g(b->shards[r]->dev); serialise_engine(b, b->shards[r]->eng, sink, header && r == 0); }
 }
+// Pinned staging buffers are process-wide and outlive a table: cudaMallocHost of two batch-sized
+// buffers costs more than counting a small file, and yak_count is called once per pass.
+namespace {
+struct PinnedPool {
+	std::mutex mu;
+	std::vector<std::pair<uint8_t*, size_t>> idle;
+	uint8_t *get(size_t bytes, size_t *cap)
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		int best = -1;
+		for (int i = 0; i < (int)idle.size(); ++i)
+			if (idle[i].second >= bytes && (best < 0 || idle[i].second < idle[best].second)) best = i;
+		if (best >= 0) { uint8_t *p = idle[best].first; *cap = idle[best].second; idle.erase(idle.begin() + best); return p; }
+		if (idle.size() >= 2) { cudaFreeHost(idle.back().first); idle.pop_back(); } // too small to be useful: do not hoard
+		uint8_t *p = nullptr;
+		YAKB_CUDA(cudaMallocHost(&p, bytes));
+		*cap = bytes;
+		return p;
+	}
+	void put(uint8_t *p, size_t cap) { if (p) { std::lock_guard<std::mutex> lk(mu); idle.push_back({p, cap}); } }
+};
+PinnedPool g_pinned;
+}
+
+// the keys of one layout batch, read front to back from the device through two page-locked pieces: while the sink (the file) takes
+// piece i, piece i+1 is on its way - the image never exists as one host array (it was a pageable vector of gigabytes: page faults
+// and a pageable copy cost more than the layout itself)
+namespace {
+struct KeyStream {
+	static const uint64_t PIECE = 8ull << 20; // keys per piece (64 MB)
+	const uint64_t *d; uint64_t n; cudaStream_t st;
+	uint64_t *pin[2] = {nullptr, nullptr};
+	size_t pcap[2] = {0, 0};
+	cudaEvent_t ev[2];
+	int64_t issued = -1;
+	KeyStream(const uint64_t *d_, uint64_t n_, cudaStream_t st_) : d(d_), n(n_), st(st_)
+	{
+		for (int i = 0; i < 2; ++i) { pin[i] = (uint64_t*)g_pinned.get(PIECE * 8, &pcap[i]); YAKB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); }
+	}
+	~KeyStream() { for (int i = 0; i < 2; ++i) { cudaEventSynchronize(ev[i]); cudaEventDestroy(ev[i]); g_pinned.put((uint8_t*)pin[i], pcap[i]); } }
+	void issue(int64_t k)
+	{
+		const uint64_t a = (uint64_t)k * PIECE;
+		if (a >= n) return;
+		YAKB_CUDA(cudaMemcpyAsync(pin[k & 1], d + a, std::min(PIECE, n - a) * 8, cudaMemcpyDeviceToHost, st));
+		YAKB_CUDA(cudaEventRecord(ev[k & 1], st));
+	}
+	// keys [a, a + *avail) on the host; accesses must go front to back
+	const uint64_t *at(uint64_t a, uint64_t *avail)
+	{
+		const int64_t k = (int64_t)(a / PIECE);
+		while (issued < k + 1) issue(++issued); // piece k and the one behind it (its buffer was consumed: we are past piece k-1)
+		YAKB_CUDA(cudaEventSynchronize(ev[k & 1]));
+		*avail = std::min(n, (uint64_t)(k + 1) * PIECE) - a;
+		return pin[k & 1] + (a - (uint64_t)k * PIECE);
+	}
+};
+}
+
 template<class Sink> static void serialise_engine(ChBox *b, Engine *eng, Sink &&sink, bool header)
 {
 	const yak_ch_t *h = &b->pub;
-	uint32_t t[3] = {(uint32_t)h->k, (uint32_t)h->pre, YAK_COUNTER_BITS};
+	uint32_t t3[3] = {(uint32_t)h->k, (uint32_t)h->pre, YAK_COUNTER_BITS};
 	if (header) {
 		sink(YAK_MAGIC, 4);
-		sink(t, 12);
+		sink(t3, 12);
 	}
-	double t_lay = 0, t_sink = 0;
-	// two buffers: while the device rebuilds the layout of slice i+1, a writer thread hands slice i to the sink (the file)
-	LayoutOut lo[2]; // Engine::layout resets them, and their key arrays (gigabytes) keep their pages
-	// slices as large as the host buffers allow (2 x 8 GB of keys): the replay runs one warp per sub-table, so its time per slice
-	// is that of the largest sub-table whatever the number of sub-tables - 8 slices of 512 sub-tables took 8 times as long as one
-	const std::vector<int> bounds = slice_bounds(eng, 1ull << 30, 1 << 30);
-	std::thread writer;
-	struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_on_unwind{writer};
-	for (size_t bi = 0; bi + 1 < bounds.size(); ++bi) {
-		const int s0 = bounds[bi], s1 = bounds[bi + 1];
-		LayoutOut &cur = lo[bi & 1]; // the writer, if any, still reads the other one
-		double t0 = wall_now();
-		eng->layout(s0, s1, cur, true);
-		t_lay += wall_now() - t0;
-		if (writer.joinable()) writer.join();
-		writer = std::thread([&sink, &cur, &t_sink, s0, s1] {
-			const double tw = wall_now();
-			for (int s = s0; s < s1; ++s) {
-				uint32_t u[2] = {cur.cap[s - s0], cur.size[s - s0]};
-				sink(u, 8);
-				if (u[1]) sink(cur.keys.data() + cur.off[s - s0], (size_t)u[1] * 8);
+	const double t0 = wall_now();
+	double t_sink = 0;
+	eng->layout_device(0, eng->P, true, [&](int, int ns, const std::vector<uint64_t> &voff, const uint64_t *d_dense,
+	                                         const std::vector<uint32_t> &cap, const std::vector<uint32_t> &size) {
+		const double tw = wall_now();
+		KeyStream ks(d_dense, voff[ns], eng->stream);
+		for (int t = 0; t < ns; ++t) { // htab.c:379-390: capacity, size, the keys in slot order
+			uint32_t u[2] = {cap[t], size[t]};
+			sink(u, 8);
+			for (uint64_t a = voff[t]; a < voff[t + 1];) {
+				uint64_t avail = 0;
+				const uint64_t *p = ks.at(a, &avail);
+				const uint64_t m = std::min(avail, voff[t + 1] - a);
+				sink(p, (size_t)m * 8);
+				a += m;
 			}
-			t_sink += wall_now() - tw;
-		});
-	}
-	if (writer.joinable()) writer.join();
-	if (timing_on()) fprintf(stderr, "[T::serialise] layout %.3f s, sink %.3f s (overlapped)\n", t_lay, t_sink);
+		}
+		t_sink += wall_now() - tw;
+	});
+	if (timing_on()) fprintf(stderr, "[T::serialise] %.3f s, of which streaming the image to the sink %.3f s\n", wall_now() - t0, t_sink);
 }
 
 // one engine's image written at `offset` of an open file, through a 16 MB buffer; returns the bytes written or -1
@@ -1024,29 +1076,6 @@ static uint64_t batch_bases(int64_t chunk_size)
 	return b;
 }
 
-// Pinned staging buffers are process-wide and outlive a table: cudaMallocHost of two batch-sized
-// buffers costs more than counting a small file, and yak_count is called once per pass.
-namespace {
-struct PinnedPool {
-	std::mutex mu;
-	std::vector<std::pair<uint8_t*, size_t>> idle;
-	uint8_t *get(size_t bytes, size_t *cap)
-	{
-		std::lock_guard<std::mutex> lk(mu);
-		int best = -1;
-		for (int i = 0; i < (int)idle.size(); ++i)
-			if (idle[i].second >= bytes && (best < 0 || idle[i].second < idle[best].second)) best = i;
-		if (best >= 0) { uint8_t *p = idle[best].first; *cap = idle[best].second; idle.erase(idle.begin() + best); return p; }
-		if (idle.size() >= 2) { cudaFreeHost(idle.back().first); idle.pop_back(); } // too small to be useful: do not hoard
-		uint8_t *p = nullptr;
-		YAKB_CUDA(cudaMallocHost(&p, bytes));
-		*cap = bytes;
-		return p;
-	}
-	void put(uint8_t *p, size_t cap) { if (p) { std::lock_guard<std::mutex> lk(mu); idle.push_back({p, cap}); } }
-};
-PinnedPool g_pinned;
-}
 
 // count.c:147-166 with 85-145 folded in: read records, drop those shorter than k (count.c:95),
 // concatenate with '\n' separators into pinned memory, ship the batch, run the device path.

@@ -74,7 +74,11 @@ void *dev_alloc(size_t bytes)
 		g_dc.idle.erase(it);
 		return p;
 	}
+	struct timespec t0, t1;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
 	cudaError_t e = cudaMalloc(&p, bytes);
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	Prof::host("host:cudaMalloc", (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6); // 1-30 ms per GiB depending on the box
 	if (e == cudaErrorMemoryAllocation && !g_dc.idle.empty()) { // idle blocks of the wrong sizes are in the way
 		(void)cudaGetLastError();
 		cudaDeviceSynchronize();
@@ -146,6 +150,12 @@ void Prof::enable(bool on) { g_prof_on = on; }
 bool Prof::on() { return g_prof_on; }
 void Prof::reset() { std::lock_guard<std::mutex> lk(g_prof_mu); g_prof_acc.clear(); g_prof_units.clear(); }
 void Prof::units(const char *name, uint64_t n) { if (g_prof_on) { std::lock_guard<std::mutex> lk(g_prof_mu); g_prof_units[name] += n; } }
+void Prof::host(const char *name, double ms)
+{
+	if (!g_prof_on) return;
+	std::lock_guard<std::mutex> lk(g_prof_mu);
+	auto &e = g_prof_acc[name]; e.first += ms; e.second += 1;
+}
 void Prof::begin(const char *name, cudaStream_t s)
 {
 	std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -1273,6 +1283,10 @@ void *Engine::journal_alloc(size_t bytes)
 	if (slabs.empty() || slabs.back().used + bytes > slabs.back().cap) {
 		Slab sl;
 		sl.cap = std::max<size_t>(bytes, (size_t)2 << 30);
+		// The first slab of a table with a filter is sized from the filter: -b tells the scale of the job (2^37 bits are meant for
+		// ~3 G distinct k-mers = 25 GB of journal), and cudaMalloc costs 1-30 ms per GiB depending on the box - a 2 GiB slab every
+		// other chunk was 40 ms per bench step on some boxes and none on others.  One allocation, in the first chunk.
+		if (slabs.empty() && bloom) sl.cap = std::max<size_t>(sl.cap, ((size_t)3 << (n_shift - 3 - lw)) / 2);
 		sl.used = 0;
 		sl.p = (char*)dev_alloc(sl.cap);
 		slabs.push_back(sl);
@@ -1477,7 +1491,9 @@ uint64_t Engine::pending_range(uint64_t t0, uint64_t t1, uint32_t off0, uint32_t
 	YAKB_CUDA(cudaMemcpyAsync(&need, pend + P, 4, cudaMemcpyDeviceToHost, stream));
 	YAKB_CUDA(cudaStreamSynchronize(stream));
 	if ((double)need > load_limit * cap) {
-		uint64_t want = (std::max<uint64_t>((uint64_t)(need / load_limit) + 16, (uint64_t)cap * 2) + 3) & ~3ull;
+		// double; small tables (below 8 GB after the step) go up four times at once: half as many rehashes and allocations on the way up
+		const uint64_t mult = (uint64_t)P * cap * 8 * 4 <= (8ull << 30) ? 4 : 2;
+		uint64_t want = (std::max<uint64_t>((uint64_t)(need / load_limit) + 16, (uint64_t)cap * mult) + 3) & ~3ull;
 		if (want > 0xFFFFFFF0ull) throw CudaError("[yakb] sub-table capacity overflow");
 		ProfScope ps("grow", stream);
 		grow((uint32_t)want);
@@ -1950,6 +1966,15 @@ void Engine::layout(int s0, int s1, LayoutOut &out, bool with_counts)
 			out.cap[b0 + t] = h_cap[t]; out.size[b0 + t] = h_size[t];
 			out.off[b0 + t + 1] = base + voff[t + 1];
 		}
+	});
+}
+
+void Engine::layout_device(int s0, int s1, bool with_counts, const LayoutFn &fn)
+{
+	layout_batches(s0, s1, with_counts, 0, [&](int b0, int ns, const std::vector<uint64_t> &voff, const uint64_t *, const uint64_t *d_dense,
+	                                             const std::vector<uint32_t> &h_cap, const std::vector<uint32_t> &h_size) {
+		YAKB_CUDA(cudaStreamSynchronize(stream)); // d_dense is complete
+		fn(b0, ns, voff, d_dense, h_cap, h_size);
 	});
 }
 

@@ -19,6 +19,7 @@
 #include <string>
 #include <stdexcept>
 #include <algorithm>
+#include <functional>
 #include <cuda_runtime.h>
 #include "dbuf.cuh"
 #include "radix.cuh"
@@ -30,6 +31,7 @@ struct Prof {
 	static void enable(bool on);
 	static bool on();
 	static void reset();
+	static void host(const char *name, double ms);     // host-side time inside the timed region that no kernel accounts for (cudaMalloc)
 	static void begin(const char *name, cudaStream_t s);
 	static void end(cudaStream_t s);
 	static void units(const char *name, uint64_t n);   // work items processed under this name (events, positions)
@@ -117,6 +119,10 @@ struct Engine {
 	void reserve(uint64_t keys_per_subtable);      // grow regions so every sub-table can take this many
 	// rebuild the reference's khashl layout of sub-tables [s0, s1) and bring it to the host
 	void layout(int s0, int s1, LayoutOut &out, bool with_counts = true);
+	// the same, left on the device: fn(b0, ns, voff, d_dense, cap, size) per batch of sub-tables b0 .. b0+ns (relative to s0) - the stored
+	// keys of sub-table b0+t in slot order are d_dense[voff[t] .. voff[t+1]) (device memory, valid inside the call), cap / size as khashl's
+	typedef std::function<void(int, int, const std::vector<uint64_t>&, const uint64_t*, const std::vector<uint32_t>&, const std::vector<uint32_t>&)> LayoutFn;
+	void layout_device(int s0, int s1, bool with_counts, const LayoutFn &fn);
 	// restore: sub-table s gets `keys` (stored form, with counts) in file order, khashl pre-sized to cap
 	void load_subtables(const std::vector<uint32_t> &caps, const std::vector<uint64_t> &off, const uint64_t *keys, bool keys_on_device = false);
 	// restore into the table as it is (htab.c:436-472): resize every sub-table to caps[s], then put the keys
