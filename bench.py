@@ -257,6 +257,9 @@ def run_reference_arm(args):
     fn = os.path.join(shm_dir(), f"yakb_refarm_{os.getpid()}.fq")
     threads = os.cpu_count() or 1
     gen = os.path.join(ROOT, "oracle", "_bin", "synthgen")
+    if not os.path.exists(gen):      # normally built by __graft_entry__.build(); gcc is all it needs
+        os.makedirs(os.path.dirname(gen), exist_ok=True)
+        subprocess.run(["gcc", "-O2", "-o", gen, os.path.join(ROOT, "oracle", "synthgen.c"), "-lpthread"], check=True)
     # batch i of the sample = the first `per` reads of step i of the workload: one generator call per batch, concatenated
     n_ev = 0
     with open(fn, "wb") as out_f:
