@@ -2,15 +2,17 @@
 //
 // Per chunk (pass 1, create_new=1; reference count.c:111-143 + htab.c:51-78):
 //   pack_ascii      ASCII -> 2-bit words + invalid mask                     (misc.c:4-21)
-//   k1_fused        roll canonical k-mers, yak_hash64, probe the table: a key already present is
-//                   a put-event whatever the bloom says (all its bits are set) -> counter++;
-//                   otherwise the position is flagged "pending"              (count.c:28-60)
-//   compact_*       pending events, in file order
+//   stage 1         every k-mer event meets the table: a key already present is a put-event whatever
+//                   the bloom says (all its bits are set) -> counter++; otherwise its position is flagged
+//                   "pending".  Large tables and chunks: part_scatter (partition.cuh: roll canonical k-mers,
+//                   yak_hash64, radix partition into per-zone lists; count.c:17-60) + zone_probe (the table
+//                   probed zone by zone).  Small ones: k1_fused (roll + probe in one kernel) / k1_array.
+//   compact_*       pending events, in file order, in ranges of at most 256 M
 //   sort by group   group = bloom block (= low n_shift-9 bits of the hash) or a hash-bit bucket
 //   group_insert    one thread walks a group in file order: exact sequential bloom semantics
 //                   (bbf.c:25-42), first-put detection, insert + counter++    (htab.c:62-71)
 //   journal         new keys ordered by (sub-table, first-put time) appended as a segment
-// Pass 2 / lookups (create_new=0) are k1_fused alone.
+// Pass 2 / lookups (create_new=0) are stage 1 alone.
 // The scans, the stable radix sorts and the ordered compactions between these kernels are ours too
 // (radix.cu); no library kernels run on this path.
 #include "engine.cuh"
