@@ -612,16 +612,20 @@ def main():
             cli = os.path.join(ROOT, "yak_b200", "bin", "yak-b200")
             out_cli = sample + ".cli.yak"
             t0 = time.time()
-            r = subprocess.run([cli, "count", f"-k{K}", f"-p{PRE}", f"-b{args.bf_shift}", f"-H{NH}", "-g", str(world), "-o", out_cli, sample],
-                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+            try:
+                r = subprocess.run([cli, "count", f"-k{K}", f"-p{PRE}", f"-b{args.bf_shift}", f"-H{NH}", "-g", str(world), "-o", out_cli, sample],
+                                   stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=900)
+                rc, err_tail = r.returncode, r.stderr[-600:]
+            except Exception as e:  # noqa: BLE001 - a secondary leg must not take the bench line with it
+                rc, err_tail = -1, repr(e)[-600:]
             dtc = time.time() - t0
-            ok = r.returncode == 0 and os.path.exists(out_cli)
+            ok = rc == 0 and os.path.exists(out_cli)
             gc = sha256_file(out_cli) if ok else None
-            parity["c_api_multi_gpu"] = {"sha256_equal": bool(ok and gc == rb), "n_gpus": world, "seconds": dtc, "rc": r.returncode,
+            parity["c_api_multi_gpu"] = {"sha256_equal": bool(ok and gc == rb), "n_gpus": world, "seconds": dtc, "rc": rc,
                                          "input_events_per_s": n_ev / dtc if dtc > 0 else None,
                                          "what": f"`yak-b200 count -g {world} -b{args.bf_shift} -o` on the same file: process start, both passes, shrink, dump"}
             if not ok:
-                parity["c_api_multi_gpu"]["stderr_tail"] = r.stderr[-600:]
+                parity["c_api_multi_gpu"]["stderr_tail"] = err_tail
             # reported, not folded into sha256_equal / the exit code: that flag is about the arm that was timed above
             try:
                 os.unlink(out_cli)
