@@ -228,8 +228,8 @@ def test_sequential_reader_buffer_boundaries_on_adversarial_input(seed):
     import test_oracle_cpu as T
     rng = np.random.default_rng(4000 + seed)
     text = T._random_fastx(rng, int(rng.integers(20, 150)), False, bad=(0.0, 0.15)[seed % 2])
-    plain = _write("yakb_bgzf_adv.fx", text)
-    fn = _write("yakb_bgzf_adv.fx.gz", bgzf_bytes(text, int(rng.choice([1, 2, 7, 33, 150, 1000])), rng if seed % 3 else None))
+    plain = _write(f"yakb_bgzf_adv{seed}.fx", text)          # per-seed names: the cases may run side by side (pytest -n)
+    fn = _write(f"yakb_bgzf_adv{seed}.fx.gz", bgzf_bytes(text, int(rng.choice([1, 2, 7, 33, 150, 1000])), rng if seed % 3 else None))
     L = lib()
     L.yakb_fastx_set_chunk.argtypes = [C.c_void_p, C.c_int64]
 
